@@ -1,0 +1,100 @@
+#!/usr/bin/env python
+"""Generate tests/golden/ from the UNMODIFIED reference binaries in oracle/_ref/.
+
+TEST INFRASTRUCTURE ONLY.  Run in the build container (where /root/reference
+exists and `make -C oracle ref` has compiled it).  The fixtures are small on
+purpose; full-size runs are pinned by md5 in MANIFEST.json.
+
+Fixtures
+  mam15.lnf                 reference example input (example/mam15.lnf), config C1
+  g100.{rmt,vt,pv,ci,cnt,rep,txt}   makermt -s 1234 -b 0.01 --paml mam15 ; consel -r -c ; catpv
+  g100e.{pv,ci,cnt,rep,txt} + mam15.ass   treeass mam15 ; consel -a (edge associations)
+  tiny.{mt,pa,rmt,vt,...}   synthetic K=6 n=40, ragged scales/replicate counts
+  MANIFEST.json             md5 of every fixture + md5s of the full-size seeded runs
+"""
+from __future__ import annotations
+
+import hashlib
+import json
+import shutil
+import sys
+import tempfile
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+from oracle import oracle as orc  # noqa: E402
+
+GOLD = ROOT / "tests" / "golden"
+REF_EXAMPLE = Path("/root/reference/example")
+
+
+def md5(p: Path) -> str:
+    return hashlib.md5(p.read_bytes()).hexdigest()
+
+
+def main() -> None:
+    orc.build(ref=True)
+    GOLD.mkdir(parents=True, exist_ok=True)
+    work = Path(tempfile.mkdtemp(prefix="consel_golden_"))
+    manifest = {"generated_by": "oracle/gen_golden.py", "reference_flags": "-O2 -ffp-contract=off", "files": {},
+                "full_size": {}}
+
+    shutil.copy(REF_EXAMPLE / "mam15.lnf", work / "mam15.lnf")
+    shutil.copy(REF_EXAMPLE / "mam15.tpl", work / "mam15.tpl")
+    keep = ["mam15.lnf"]
+
+    # --- g100: mam15, 10 scales x 100 replicates, seed 1234
+    orc.run_ref("makermt", ["-s", "1234", "-b", "0.01", "--paml", "mam15", "g100"], work)
+    orc.run_ref("consel", ["-r", "-c", "g100"], work)
+    (work / "g100.txt").write_text(orc.run_ref("catpv", ["g100"], work))
+    keep += [f"g100.{e}" for e in ("rmt", "vt", "pv", "ci", "cnt", "rep", "txt")]
+
+    # --- g100e: edge associations on the same replicates
+    (work / "mam15ass.log").write_text(orc.run_ref("treeass", ["mam15"], work))
+    orc.run_ref("consel", ["-a", "mam15", "-r", "-c", "g100", "g100e"], work)
+    (work / "g100e.txt").write_text(orc.run_ref("catpv", ["g100e"], work))
+    keep += ["mam15.ass"] + [f"g100e.{e}" for e in ("pv", "ci", "cnt", "rep", "txt")]
+
+    # --- tiny: synthetic ragged case (different r and B per scale, bn < n and > n)
+    rng = np.random.Generator(np.random.PCG64(20261019))
+    K, n = 6, 40
+    base = -2.3 - 4.07 * rng.exponential(size=n)
+    L = base[None, :] + 0.106 * rng.standard_normal((K, n)) - 0.5 * np.arange(K)[:, None] / n
+    orc.write_mt(work / "tiny.mt", L)
+    orc.write_pa(work / "tiny.pa", [0.5, 0.77, 1.0, 1.37, 2.05], [37, 64, 50, 33, 41])
+    orc.run_ref("makermt", ["-s", "7", "-p", "tiny", "tiny"], work)
+    orc.run_ref("consel", ["-r", "-c", "tiny"], work)
+    (work / "tiny.txt").write_text(orc.run_ref("catpv", ["tiny"], work))
+    keep += [f"tiny.{e}" for e in ("mt", "pa", "rmt", "vt", "pv", "ci", "cnt", "rep", "txt")]
+
+    for name in keep:
+        shutil.copy(work / name, GOLD / name)
+        manifest["files"][name] = md5(GOLD / name)
+
+    # --- full-size pins (md5 only): SURVEY Appendix C
+    orc.run_ref("makermt", ["-s", "1234", "--paml", "mam15", "full"], work)
+    orc.run_ref("consel", ["-r", "-c", "full"], work)
+    for e in ("rmt", "vt", "pv", "ci", "cnt", "rep"):
+        manifest["full_size"][f"mam15_s1234.{e}"] = md5(work / f"full.{e}")
+    orc.run_ref("makermt", ["-s", "1234", "-p", str(REF_EXAMPLE / "k10s"), "--paml", "mam15", "g10s"], work)
+    orc.run_ref("consel", ["-r", "-c", "g10s"], work)
+    for e in ("rmt", "pv", "ci", "cnt", "rep"):
+        manifest["full_size"][f"mam15_s1234_k10s.{e}"] = md5(work / f"g10s.{e}")
+    # a few spot values of the full run
+    full = orc.read_rmt(work / "full.rmt")
+    manifest["full_size"]["spot"] = {
+        "datvec0_2": [float(x) for x in full["datvec"][:3]],
+        "rr1": [float(x) for x in full["rr"]],
+        "rep_s0_k0_b0_3": [float(x) for x in full["reps"][0][0, :4]],
+        "cnt_row0": [float(x) for x in orc.read_cnt(work / "full.cnt")["cnt"][0]],
+    }
+    (GOLD / "MANIFEST.json").write_text(json.dumps(manifest, indent=1) + "\n")
+    shutil.rmtree(work)
+    print("wrote", len(keep) + 1, "files to", GOLD)
+
+
+if __name__ == "__main__":
+    main()
