@@ -1,0 +1,581 @@
+// C ABI of libconselgpu.so (include/consel_gpu.h): lifecycle, the makermt-side
+// pipeline (MT19937 jump-ahead -> draws -> site histograms -> contraction) and its
+// batching over device memory.  The consel-side entry points live in capi_stats.cu.
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "cgpu_internal.h"
+
+namespace cgpu {
+
+static thread_local char t_err[512] = "no error";
+std::atomic<long long> g_launches{0};
+
+void set_error(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    int off = snprintf(t_err, sizeof(t_err), "cgpu error %d: ", code);
+    vsnprintf(t_err + off, sizeof(t_err) - off, fmt, ap);
+    va_end(ap);
+}
+
+Globals &G() {
+    static Globals g;
+    return g;
+}
+
+int ensure_init() { return G().inited ? CGPU_OK : cgpu_init(-1); }
+
+// accumulates device time per phase over many (start, stop) event pairs
+struct PhaseTimer {
+    struct Span {
+        int phase;
+        cudaEvent_t a, b;
+    };
+    std::vector<Span> spans;
+    cudaStream_t st;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    explicit PhaseTimer(cudaStream_t s) : st(s) {
+        cudaEventCreate(&t0);
+        cudaEventCreate(&t1);
+        cudaEventRecord(t0, st);
+    }
+    void begin(int phase) {
+        Span sp{phase, nullptr, nullptr};
+        cudaEventCreate(&sp.a);
+        cudaEventCreate(&sp.b);
+        cudaEventRecord(sp.a, st);
+        spans.push_back(sp);
+    }
+    void end() { cudaEventRecord(spans.back().b, st); }
+    // call after the stream has been synchronised
+    void finish(double *ms5) {
+        for (int i = 0; i < 6; i++) ms5[i] = 0;
+        cudaEventRecord(t1, st);
+        cudaEventSynchronize(t1);
+        float tot = 0;
+        if (cudaEventElapsedTime(&tot, t0, t1) == cudaSuccess) ms5[5] = tot;
+        cudaEventDestroy(t0);
+        cudaEventDestroy(t1);
+        for (auto &sp : spans) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) ms5[sp.phase] += ms;
+            cudaEventDestroy(sp.a);
+            cudaEventDestroy(sp.b);
+        }
+        spans.clear();
+    }
+};
+
+static void shard_range(int bb, int *b0, int *b1) {
+    const Globals &g = G();
+    *b0 = (int)((long long)bb * g.shard_rank / g.shard_world);
+    *b1 = (int)((long long)bb * (g.shard_rank + 1) / g.shard_world);
+}
+
+static void free_reps(DevReps *r) {
+    if (!r) return;
+    if (r->d_rep)
+        for (int s = 0; s < r->S; s++) cudaFree(r->d_rep[s]);
+    if (r->d_stat)
+        for (int s = 0; s < r->S; s++) cudaFree(r->d_stat[s]);
+    cudaFree(r->d_edges);
+    cudaFree(r->d_ass_ptr);
+    cudaFree(r->d_ass_idx);
+    free(r->d_rep);
+    free(r->d_stat);
+    free(r->bb);
+    free(r->b0);
+    free(r->nb);
+    delete r;
+}
+
+static int alloc_reps(int K, int S, const int *bb, DevReps **out) {
+    DevReps *r = new DevReps();
+    r->K = K;
+    r->S = S;
+    r->bb = (int *)calloc(S, sizeof(int));
+    r->b0 = (int *)calloc(S, sizeof(int));
+    r->nb = (int *)calloc(S, sizeof(int));
+    r->d_rep = (double **)calloc(S, sizeof(double *));
+    for (int s = 0; s < S; s++) {
+        int b0, b1;
+        shard_range(bb[s], &b0, &b1);
+        r->bb[s] = bb[s];
+        r->b0[s] = b0;
+        r->nb[s] = b1 - b0;
+        size_t bytes = (size_t)K * std::max(1, b1 - b0) * sizeof(double);
+        cudaError_t e = cudaMalloc(&r->d_rep[s], bytes);
+        if (e != cudaSuccess) {
+            set_error(CGPU_ENOMEM, "cudaMalloc(%zu) for replicate block %d: %s", bytes, s, cudaGetErrorString(e));
+            free_reps(r);
+            return CGPU_ENOMEM;
+        }
+    }
+    *out = r;
+    return CGPU_OK;
+}
+
+// chunk size (log2 draws) of the MT19937 doubling tree: about 2k chunks, each long
+// enough that its jump (~6M word-XORs) is amortised.
+static int pick_chunk_log2(unsigned long long total_draws) {
+    int m = 12;
+    while (m < 23 && (total_draws >> m) > 2048) m++;
+    return m;
+}
+
+struct MtPlan {
+    uint32_t *d_states = nullptr;
+    int chunk_log2 = 0;
+    unsigned long long nchunks = 0;
+};
+
+// window states W_{offset + p*2^m}, p = 0..P-1, by the doubling tree
+static int mt_prepare(unsigned long seed, unsigned long long stream_offset, unsigned long long total_draws,
+                      MtPlan *plan, cudaStream_t st) {
+    Globals &g = G();
+    plan->chunk_log2 = pick_chunk_log2(total_draws);
+    const int m = plan->chunk_log2;
+    unsigned long long P = (total_draws + (1ull << m) - 1) >> m;
+    if (P == 0) P = 1;
+    plan->nchunks = P;
+    int top = 0;
+    while ((1ull << top) < P) top++;
+    if (m + top > MT_MAXLOG) {
+        set_error(CGPU_EINVAL, "stream of %llu draws exceeds the jump table", total_draws);
+        return CGPU_EINVAL;
+    }
+    CGPU_CUDA(cudaMalloc(&plan->d_states, (size_t)P * MT_N * sizeof(uint32_t)));
+    uint32_t w0[MT_N];
+    mt_seed_window((uint32_t)(seed & 0xffffffffUL), w0);
+    if (stream_offset) {
+        Gf2Poly gp;
+        mt_poly_xpow(stream_offset, &gp);
+        uint32_t w1[MT_N];
+        mt_jump_host(w0, &gp, w1);
+        memcpy(w0, w1, sizeof(w0));
+    }
+    CGPU_CUDA(cudaMemcpyAsync(plan->d_states, w0, sizeof(w0), cudaMemcpyHostToDevice, st));
+    CGPU_CUDA(cudaStreamSynchronize(st));  // w0 is a stack buffer
+    for (int r = 0; (1ull << r) < P; r++) {
+        unsigned long long have = 1ull << r;
+        int cnt = (int)std::min<unsigned long long>(have, P - have);
+        CGPU_TRY(launch_mt_jump(plan->d_states, plan->d_states + have * MT_N,
+                                g.d_jump_table + (size_t)(m + r) * MT_N, cnt, st));
+    }
+    return CGPU_OK;
+}
+
+struct Workspace {
+    uint32_t *d_idx = nullptr;
+    unsigned long long *d_counts = nullptr;
+    int *d_err = nullptr;
+    ~Workspace() {
+        cudaFree(d_idx);
+        cudaFree(d_counts);
+        cudaFree(d_err);
+    }
+};
+
+static int scaleboot_core(const DevMatrix &m, int S, const int *bn, const int *bb, unsigned long seed,
+                          unsigned long long stream_offset, int rng_mode, int sum_mode, DevReps *reps,
+                          PhaseTimer &pt, cudaStream_t st) {
+    if (sum_mode == CGPU_SUM_INT8) {
+        set_error(CGPU_EINVAL, "sum_mode CGPU_SUM_INT8 (tcgen05 fixed-point path) is not built in this version");
+        return CGPU_EINVAL;
+    }
+    if (sum_mode != CGPU_SUM_STRICT && sum_mode != CGPU_SUM_FAST) {
+        set_error(CGPU_EINVAL, "unknown sum_mode %d", sum_mode);
+        return CGPU_EINVAL;
+    }
+    if (rng_mode != CGPU_RNG_MT19937 && rng_mode != CGPU_RNG_PHILOX) {
+        set_error(CGPU_EINVAL, "unknown rng_mode %d", rng_mode);
+        return CGPU_EINVAL;
+    }
+    const int n = m.n, NP = m.NP;
+    // batch size: bound the index and count buffers (device memory is 180 GB; keep the
+    // workspace near 8 GB so several processes can share a GPU in tests)
+    const size_t budget = (size_t)4 << 30;
+    int max_bn = 1;
+    for (int s = 0; s < S; s++) max_bn = std::max(max_bn, bn[s]);
+    long long cap = std::min<long long>((long long)(budget / ((size_t)max_bn * 4)), (long long)(budget / (size_t)NP));
+    cap = std::max<long long>(64, cap / 64 * 64);
+    int max_nb = 0;
+    for (int s = 0; s < S; s++) max_nb = std::max(max_nb, reps->nb[s]);
+    const int batch = (int)std::min<long long>(cap, std::max(64, (max_nb + 63) / 64 * 64));
+
+    Workspace ws;
+    CGPU_CUDA(cudaMalloc(&ws.d_counts, (size_t)(batch / 8) * NP * 8));
+    CGPU_CUDA(cudaMalloc(&ws.d_err, sizeof(int)));
+    CGPU_CUDA(cudaMemsetAsync(ws.d_err, 0, sizeof(int), st));
+    // padding sites and replicates must read as zero counts
+    CGPU_CUDA(cudaMemsetAsync(ws.d_counts, 0, (size_t)(batch / 8) * NP * 8, st));
+
+    MtPlan plan;
+    struct PlanGuard {
+        MtPlan &p;
+        ~PlanGuard() { cudaFree(p.d_states); }
+    } guard{plan};
+    std::vector<unsigned long long> base(S + 1, 0);
+    for (int s = 0; s < S; s++) base[s + 1] = base[s] + (unsigned long long)bb[s] * (unsigned long long)bn[s];
+    if (rng_mode == CGPU_RNG_MT19937) {
+        CGPU_CUDA(cudaMalloc(&ws.d_idx, (size_t)batch * max_bn * sizeof(uint32_t)));
+        pt.begin(1);
+        CGPU_TRY(mt_prepare(seed, stream_offset, base[S], &plan, st));
+        pt.end();
+    }
+
+    for (int s = 0; s < S; s++) {
+        if (bn[s] <= 0 || bb[s] < 0) {
+            set_error(CGPU_EINVAL, "scale %d: bn=%d bb=%d", s, bn[s], bb[s]);
+            return CGPU_EINVAL;
+        }
+        const double r = (double)bn[s] / (double)n;  // src/makermt.c:48
+        for (int a = 0; a < reps->nb[s]; a += batch) {
+            const int nbat = std::min(batch, reps->nb[s] - a);
+            const int bA = reps->b0[s] + a;  // global replicate index of the batch
+            if (rng_mode == CGPU_RNG_MT19937) {
+                const unsigned long long lo = base[s] + (unsigned long long)bA * bn[s];
+                const unsigned long long hi = lo + (unsigned long long)nbat * bn[s];
+                const unsigned long long c0 = lo >> plan.chunk_log2, c1 = (hi - 1) >> plan.chunk_log2;
+                pt.begin(1);
+                CGPU_TRY(launch_mt_draw(plan.d_states, plan.chunk_log2, c0, (int)(c1 - c0 + 1), lo, hi, (uint32_t)n, ws.d_idx, st));
+                pt.end();
+                pt.begin(2);
+                CGPU_TRY(launch_hist_from_idx(ws.d_idx, n, NP, bn[s], nbat, ws.d_counts, ws.d_err, st));
+                pt.end();
+            } else {
+                pt.begin(2);
+                CGPU_TRY(launch_hist_philox((unsigned long long)seed, s, bA, n, NP, bn[s], nbat, ws.d_counts, ws.d_err, st));
+                pt.end();
+            }
+            pt.begin(3);
+            CGPU_TRY(launch_contract(m, ws.d_counts, nbat, r, reps->d_rep[s], reps->nb[s], a, sum_mode, st));
+            pt.end();
+        }
+    }
+    int h_err = 0;
+    CGPU_CUDA(cudaMemcpyAsync(&h_err, ws.d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CGPU_CUDA(cudaStreamSynchronize(st));
+    if (h_err) {
+        set_error(CGPU_ERANGE, "a site was drawn more than 255 times in one replicate (n=%d too small for int8 counts)", n);
+        return CGPU_ERANGE;
+    }
+    return CGPU_OK;
+}
+
+static int matrix_upload(const double *L, int K, int n, DevMatrix **out, cudaStream_t st) {
+    if (!L || K <= 0 || n <= 0) {
+        set_error(CGPU_EINVAL, "matrix_upload: K=%d n=%d", K, n);
+        return CGPU_EINVAL;
+    }
+    DevMatrix *m = new DevMatrix();
+    m->K = K;
+    m->n = n;
+    m->NP = pad_sites(n);
+    m->TK = pick_tk(K);
+    m->KT = 32 * m->TK;
+    m->ktiles = (K + m->KT - 1) / m->KT;
+    int *d_flag = nullptr;
+    int rc = CGPU_OK;
+    auto fail = [&](cudaError_t e, const char *what) {
+        set_error(CGPU_ECUDA, "matrix_upload %s: %s", what, cudaGetErrorString(e));
+        rc = e == cudaErrorMemoryAllocation ? CGPU_ENOMEM : CGPU_ECUDA;
+    };
+    cudaError_t e;
+    if ((e = cudaMalloc(&m->d_L, (size_t)K * n * sizeof(double))) != cudaSuccess) fail(e, "alloc L");
+    if (!rc && (e = cudaMalloc(&m->d_LT, (size_t)m->ktiles * m->NP * m->KT * sizeof(double))) != cudaSuccess) fail(e, "alloc LT");
+    if (!rc && (e = cudaMalloc(&d_flag, sizeof(int))) != cudaSuccess) fail(e, "alloc flag");
+    if (!rc && (e = cudaMemsetAsync(d_flag, 0, sizeof(int), st)) != cudaSuccess) fail(e, "memset");
+    if (!rc && (e = cudaMemcpyAsync(m->d_L, L, (size_t)K * n * sizeof(double), cudaMemcpyHostToDevice, st)) != cudaSuccess) fail(e, "H2D");
+    if (!rc) rc = launch_transpose_L(m->d_L, K, n, m->NP, m->TK, m->d_LT, d_flag, st);
+    int h_flag = 0;
+    if (!rc && (e = cudaMemcpyAsync(&h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st)) != cudaSuccess) fail(e, "D2H flag");
+    if (!rc && (e = cudaStreamSynchronize(st)) != cudaSuccess) fail(e, "sync");
+    cudaFree(d_flag);
+    if (rc) {
+        cudaFree(m->d_L);
+        cudaFree(m->d_LT);
+        delete m;
+        return rc;
+    }
+    m->finite = !h_flag;
+    *out = m;
+    return CGPU_OK;
+}
+
+static int reps_download(const DevReps *r, double *const *rep_out, cudaStream_t st) {
+    for (int s = 0; s < r->S; s++) {
+        if (r->nb[s] <= 0) continue;
+        CGPU_CUDA(cudaMemcpy2DAsync(rep_out[s] + r->b0[s], (size_t)r->bb[s] * sizeof(double), r->d_rep[s],
+                                    (size_t)r->nb[s] * sizeof(double), (size_t)r->nb[s] * sizeof(double), r->K,
+                                    cudaMemcpyDeviceToHost, st));
+    }
+    CGPU_CUDA(cudaStreamSynchronize(st));
+    return CGPU_OK;
+}
+
+}  // namespace cgpu
+
+using namespace cgpu;
+
+extern "C" {
+
+int cgpu_version(void) { return 100; }
+
+const char *cgpu_last_error(void) { return t_err; }
+
+int cgpu_init(int device) {
+    Globals &g = G();
+    if (g.inited) return CGPU_OK;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0) {
+        set_error(CGPU_ENODEV, "no CUDA device (%s); this library has no CPU fallback",
+                  e == cudaSuccess ? "count=0" : cudaGetErrorString(e));
+        return CGPU_ENODEV;
+    }
+    if (device < 0) {
+        const char *lr = getenv("LOCAL_RANK");
+        device = lr ? atoi(lr) % count : 0;
+    }
+    if (device >= count) {
+        set_error(CGPU_EINVAL, "device %d of %d", device, count);
+        return CGPU_EINVAL;
+    }
+    CGPU_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CGPU_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) {
+        set_error(CGPU_ENODEV, "device %d is sm_%d%d; libconselgpu is built for sm_100a (B200) only", device,
+                  prop.major, prop.minor);
+        return CGPU_ENODEV;
+    }
+    g.device = device;
+    g.sm_count = prop.multiProcessorCount;
+    CGPU_CUDA(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+    const Gf2Poly *T = mt_jump_table();
+    CGPU_CUDA(cudaMalloc(&g.d_jump_table, (size_t)(MT_MAXLOG + 1) * MT_N * sizeof(uint32_t)));
+    CGPU_CUDA(cudaMemcpy(g.d_jump_table, T, (size_t)(MT_MAXLOG + 1) * MT_N * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    g.inited = true;
+    return CGPU_OK;
+}
+
+void cgpu_shutdown(void) {
+    Globals &g = G();
+    if (!g.inited) return;
+    cudaStreamSynchronize(g.stream);
+    cudaFree(g.d_jump_table);
+    cudaStreamDestroy(g.stream);
+    g.d_jump_table = nullptr;
+    g.stream = nullptr;
+    g.inited = false;
+}
+
+int cgpu_set_shard(int rank, int world) {
+    if (world < 1 || rank < 0 || rank >= world) {
+        set_error(CGPU_EINVAL, "shard %d/%d", rank, world);
+        return CGPU_EINVAL;
+    }
+    G().shard_rank = rank;
+    G().shard_world = world;
+    return CGPU_OK;
+}
+
+int cgpu_shard_range(int bb, int *b_begin, int *b_end) {
+    if (bb < 0 || !b_begin || !b_end) return CGPU_EINVAL;
+    shard_range(bb, b_begin, b_end);
+    return CGPU_OK;
+}
+
+long long cgpu_launch_count(void) { return g_launches.load(); }
+
+int cgpu_last_timing(double *ms6) {
+    if (!ms6) return CGPU_EINVAL;
+    memcpy(ms6, G().last_ms, sizeof(double) * 6);
+    return CGPU_OK;
+}
+
+int cgpu_matrix_upload(const double *L, int K, int n, cgpu_matrix **out) {
+    CGPU_TRY(ensure_init());
+    if (!out) return CGPU_EINVAL;
+    DevMatrix *m = nullptr;
+    CGPU_TRY(matrix_upload(L, K, n, &m, G().stream));
+    *out = reinterpret_cast<cgpu_matrix *>(m);
+    return CGPU_OK;
+}
+
+void cgpu_matrix_free(cgpu_matrix *mm) {
+    DevMatrix *m = reinterpret_cast<DevMatrix *>(mm);
+    if (!m) return;
+    cudaFree(m->d_L);
+    cudaFree(m->d_LT);
+    delete m;
+}
+
+int cgpu_scaleboot_dev(const cgpu_matrix *mm, int S, const int *bn, const int *bb, unsigned long seed,
+                       unsigned long long stream_offset, int rng_mode, int sum_mode, cgpu_reps **out) {
+    CGPU_TRY(ensure_init());
+    const DevMatrix *m = reinterpret_cast<const DevMatrix *>(mm);
+    if (!m || S <= 0 || !bn || !bb || !out) {
+        set_error(CGPU_EINVAL, "scaleboot_dev: bad arguments");
+        return CGPU_EINVAL;
+    }
+    DevReps *r = nullptr;
+    CGPU_TRY(alloc_reps(m->K, S, bb, &r));
+    PhaseTimer pt(G().stream);
+    int rc = scaleboot_core(*m, S, bn, bb, seed, stream_offset, rng_mode, sum_mode, r, pt, G().stream);
+    cudaStreamSynchronize(G().stream);
+    pt.finish(G().last_ms);
+    if (rc != CGPU_OK) {
+        free_reps(r);
+        return rc;
+    }
+    *out = reinterpret_cast<cgpu_reps *>(r);
+    return CGPU_OK;
+}
+
+int cgpu_reps_download(const cgpu_reps *rr, double *const *rep_out) {
+    CGPU_TRY(ensure_init());
+    const DevReps *r = reinterpret_cast<const DevReps *>(rr);
+    if (!r || !rep_out) return CGPU_EINVAL;
+    return reps_download(r, rep_out, G().stream);
+}
+
+void cgpu_reps_free(cgpu_reps *rr) { free_reps(reinterpret_cast<DevReps *>(rr)); }
+
+int cgpu_reps_devptr(const cgpu_reps *rr, int s, void **ptr, int *rows, int *cols, int *ld) {
+    const DevReps *r = reinterpret_cast<const DevReps *>(rr);
+    if (!r || s < 0 || s >= r->S) return CGPU_EINVAL;
+    if (ptr) *ptr = r->d_rep[s];
+    if (rows) *rows = r->K;
+    if (cols) *cols = r->nb[s];
+    if (ld) *ld = r->nb[s];
+    return CGPU_OK;
+}
+
+int cgpu_scaleboot_all(const double *L, int K, int n, int S, const int *bn, const int *bb, unsigned long seed,
+                       unsigned long long stream_offset, int rng_mode, int sum_mode, double *const *rep_out) {
+    CGPU_TRY(ensure_init());
+    if (!L || !bn || !bb || !rep_out || S <= 0) {
+        set_error(CGPU_EINVAL, "scaleboot_all: bad arguments");
+        return CGPU_EINVAL;
+    }
+    cudaStream_t st = G().stream;
+    PhaseTimer pt(st);
+    DevMatrix *m = nullptr;
+    pt.begin(0);
+    int rc = matrix_upload(L, K, n, &m, st);
+    pt.end();
+    DevReps *r = nullptr;
+    if (rc == CGPU_OK) rc = alloc_reps(K, S, bb, &r);
+    if (rc == CGPU_OK) rc = scaleboot_core(*m, S, bn, bb, seed, stream_offset, rng_mode, sum_mode, r, pt, st);
+    if (rc == CGPU_OK) {
+        pt.begin(4);
+        rc = reps_download(r, rep_out, st);
+        pt.end();
+    }
+    cudaStreamSynchronize(st);
+    pt.finish(G().last_ms);
+    free_reps(r);
+    cgpu_matrix_free(reinterpret_cast<cgpu_matrix *>(m));
+    return rc;
+}
+
+int cgpu_resample_counts(int n, int S, const int *bn, const int *bb, unsigned long seed,
+                         unsigned long long stream_offset, int rng_mode, int s, unsigned char *counts) {
+    CGPU_TRY(ensure_init());
+    if (n <= 0 || S <= 0 || !bn || !bb || s < 0 || s >= S || !counts) {
+        set_error(CGPU_EINVAL, "resample_counts: bad arguments");
+        return CGPU_EINVAL;
+    }
+    cudaStream_t st = G().stream;
+    int b0, b1;
+    shard_range(bb[s], &b0, &b1);
+    const int nb = b1 - b0;
+    if (nb <= 0) return CGPU_OK;
+    const int NP = pad_sites(n);
+    Workspace ws;
+    const size_t cbytes = (size_t)((nb + 7) / 8) * NP * 8;
+    CGPU_CUDA(cudaMalloc(&ws.d_counts, cbytes));
+    CGPU_CUDA(cudaMemsetAsync(ws.d_counts, 0, cbytes, st));
+    CGPU_CUDA(cudaMalloc(&ws.d_err, sizeof(int)));
+    CGPU_CUDA(cudaMemsetAsync(ws.d_err, 0, sizeof(int), st));
+    MtPlan plan;
+    struct PlanGuard {
+        MtPlan &p;
+        ~PlanGuard() { cudaFree(p.d_states); }
+    } guard{plan};
+    if (rng_mode == CGPU_RNG_MT19937) {
+        unsigned long long base = 0, total = 0;
+        for (int t = 0; t < S; t++) {
+            if (t < s) base += (unsigned long long)bb[t] * bn[t];
+            total += (unsigned long long)bb[t] * bn[t];
+        }
+        CGPU_CUDA(cudaMalloc(&ws.d_idx, (size_t)nb * bn[s] * sizeof(uint32_t)));
+        CGPU_TRY(mt_prepare(seed, stream_offset, total, &plan, st));
+        const unsigned long long lo = base + (unsigned long long)b0 * bn[s], hi = lo + (unsigned long long)nb * bn[s];
+        const unsigned long long c0 = lo >> plan.chunk_log2, c1 = (hi - 1) >> plan.chunk_log2;
+        CGPU_TRY(launch_mt_draw(plan.d_states, plan.chunk_log2, c0, (int)(c1 - c0 + 1), lo, hi, (uint32_t)n, ws.d_idx, st));
+        CGPU_TRY(launch_hist_from_idx(ws.d_idx, n, NP, bn[s], nb, ws.d_counts, ws.d_err, st));
+    } else if (rng_mode == CGPU_RNG_PHILOX) {
+        CGPU_TRY(launch_hist_philox((unsigned long long)seed, s, b0, n, NP, bn[s], nb, ws.d_counts, ws.d_err, st));
+    } else {
+        set_error(CGPU_EINVAL, "unknown rng_mode %d", rng_mode);
+        return CGPU_EINVAL;
+    }
+    unsigned char *d_out = nullptr;
+    CGPU_CUDA(cudaMalloc(&d_out, (size_t)nb * n));
+    int rc = launch_counts_unpack(ws.d_counts, n, NP, nb, d_out, st);
+    int h_err = 0;
+    if (rc == CGPU_OK) {
+        cudaMemcpyAsync(counts, d_out, (size_t)nb * n, cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(&h_err, ws.d_err, sizeof(int), cudaMemcpyDeviceToHost, st);
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) {
+            set_error(CGPU_ECUDA, "resample_counts: %s", cudaGetErrorString(e));
+            rc = CGPU_ECUDA;
+        }
+    }
+    cudaFree(d_out);
+    if (rc == CGPU_OK && h_err) {
+        set_error(CGPU_ERANGE, "a site was drawn more than 255 times in one replicate");
+        rc = CGPU_ERANGE;
+    }
+    return rc;
+}
+
+int cgpu_mt19937_stream(unsigned long seed, unsigned long long skip, unsigned long long count, unsigned int *out) {
+    CGPU_TRY(ensure_init());
+    if (!out && count) return CGPU_EINVAL;
+    if (count == 0) return CGPU_OK;
+    cudaStream_t st = G().stream;
+    MtPlan plan;
+    struct PlanGuard {
+        MtPlan &p;
+        ~PlanGuard() { cudaFree(p.d_states); }
+    } guard{plan};
+    CGPU_TRY(mt_prepare(seed, 0, skip + count, &plan, st));
+    uint32_t *d_idx = nullptr;
+    CGPU_CUDA(cudaMalloc(&d_idx, (size_t)count * sizeof(uint32_t)));
+    const unsigned long long lo = skip, hi = skip + count;
+    const unsigned long long c0 = lo >> plan.chunk_log2, c1 = (hi - 1) >> plan.chunk_log2;
+    // n = 2^32 is not representable: ask for the raw tempered word via the identity n -> y
+    int rc = launch_mt_draw(plan.d_states, plan.chunk_log2, c0, (int)(c1 - c0 + 1), lo, hi, 0u, d_idx, st);
+    if (rc == CGPU_OK) {
+        cudaMemcpyAsync(out, d_idx, (size_t)count * sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) {
+            set_error(CGPU_ECUDA, "mt19937_stream: %s", cudaGetErrorString(e));
+            rc = CGPU_ECUDA;
+        }
+    }
+    cudaFree(d_idx);
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,127 @@
+// Internal declarations shared by the translation units of libconselgpu.so.
+// Nothing here is part of the C ABI (include/consel_gpu.h is).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <atomic>
+#include <string>
+
+#include "../../include/consel_gpu.h"
+
+namespace cgpu {
+
+// ---------------------------------------------------------------- errors
+void set_error(int code, const char *fmt, ...);
+extern std::atomic<long long> g_launches;
+
+#define CGPU_CUDA(call)                                                                      \
+    do {                                                                                     \
+        cudaError_t e__ = (call);                                                            \
+        if (e__ != cudaSuccess) {                                                            \
+            cgpu::set_error(CGPU_ECUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call,           \
+                            cudaGetErrorString(e__));                                        \
+            return CGPU_ECUDA;                                                               \
+        }                                                                                    \
+    } while (0)
+
+#define CGPU_LAUNCH_CHECK()                                                                  \
+    do {                                                                                     \
+        cgpu::g_launches.fetch_add(1, std::memory_order_relaxed);                            \
+        cudaError_t e__ = cudaGetLastError();                                                \
+        if (e__ != cudaSuccess) {                                                            \
+            cgpu::set_error(CGPU_ECUDA, "%s:%d kernel launch: %s", __FILE__, __LINE__,       \
+                            cudaGetErrorString(e__));                                        \
+            return CGPU_ECUDA;                                                               \
+        }                                                                                    \
+    } while (0)
+
+#define CGPU_TRY(expr)                                                                       \
+    do {                                                                                     \
+        int rc__ = (expr);                                                                   \
+        if (rc__ != CGPU_OK) return rc__;                                                    \
+    } while (0)
+
+// ---------------------------------------------------------------- MT19937
+constexpr int MT_N = 624;
+constexpr int MT_M = 397;
+constexpr int MT_DEG = 19937;
+constexpr int MT_POLY_W64 = 312;  // 64-bit words holding a residue mod phi (19968 bits)
+constexpr int MT_POLY_W32 = 624;
+constexpr int MT_MAXLOG = 48;     // jump table covers x^(2^i), i = 0..MT_MAXLOG
+
+struct Gf2Poly {
+    uint64_t w[MT_POLY_W64];
+};
+
+// x^(2^i) mod phi for i = 0..MT_MAXLOG (host table, built once)
+const Gf2Poly *mt_jump_table();
+// x^J mod phi for arbitrary J (square and multiply-by-x)
+void mt_poly_xpow(uint64_t J, Gf2Poly *out);
+// seeded state array of init_genrand (window W_0 = x_0..x_623)
+void mt_seed_window(uint32_t seed, uint32_t *w624);
+// host application of a jump polynomial to a window (tests / stream_offset set-up)
+void mt_jump_host(const uint32_t *in624, const Gf2Poly *g, uint32_t *out624);
+
+// ---------------------------------------------------------------- globals
+struct Globals {
+    bool inited = false;
+    int device = -1;
+    int sm_count = 0;
+    int shard_rank = 0, shard_world = 1;
+    cudaStream_t stream = nullptr;
+    uint32_t *d_jump_table = nullptr;  // (MT_MAXLOG+1) x 624 u32
+    cudaEvent_t ev[8] = {};
+    double last_ms[6] = {0, 0, 0, 0, 0, 0};
+};
+Globals &G();
+int ensure_init();
+
+// ---------------------------------------------------------------- layouts
+// Site axis padded to a multiple of 128 so every pipeline chunk is full.
+inline int pad_sites(int n) { return (n + 127) / 128 * 128; }
+// trees per lane for the contraction kernels (tile of KT = 32*TK trees)
+inline int pick_tk(int K) { return K <= 32 ? 1 : (K <= 64 ? 2 : (K <= 128 ? 4 : 8)); }
+
+struct DevMatrix {  // cgpu_matrix
+    int K = 0, n = 0, NP = 0, TK = 0, KT = 0, ktiles = 0;
+    bool finite = true;
+    double *d_L = nullptr;   // K x n row-major (as uploaded)
+    double *d_LT = nullptr;  // [ktiles][NP][KT] site-major tiles, zero padded
+};
+
+struct DevReps {  // cgpu_reps
+    int K = 0, S = 0;
+    int *bb = nullptr;       // host: full replicate counts per scale
+    int *b0 = nullptr;       // host: first column owned by this rank
+    int *nb = nullptr;       // host: number of columns owned by this rank
+    double **d_rep = nullptr;   // host array of device pointers, K x nb[s]
+    // statistics (cgpu_stats_build)
+    int cm = 0;
+    double **d_stat = nullptr;  // cm x nb[s]
+    void *d_edges = nullptr;    // cm x S x 4 doubles: min1,min2,max1,max2
+    int *d_ass_ptr = nullptr, *d_ass_idx = nullptr;
+};
+
+// ---------------------------------------------------------------- kernels (host launchers)
+// mt_kernels.cu
+int launch_mt_jump(const uint32_t *d_src, uint32_t *d_dst, const uint32_t *d_poly, int count,
+                   cudaStream_t st);
+int launch_mt_draw(const uint32_t *d_states, int chunk_log2, unsigned long long first_chunk,
+                   int nchunks, unsigned long long lo, unsigned long long hi, uint32_t n,
+                   uint32_t *d_idx, cudaStream_t st);
+// resample_kernels.cu
+int launch_hist_from_idx(const uint32_t *d_idx, int n, int NP, int bn, int nb,
+                         unsigned long long *d_counts, int *d_err, cudaStream_t st);
+int launch_hist_philox(unsigned long long seed, int scale, int b_first, int n, int NP, int bn, int nb,
+                       unsigned long long *d_counts, int *d_err, cudaStream_t st);
+int launch_counts_unpack(const unsigned long long *d_counts, int n, int NP, int nb,
+                         unsigned char *d_out, cudaStream_t st);
+// contract_kernels.cu
+int launch_transpose_L(const double *d_L, int K, int n, int NP, int TK, double *d_LT, int *d_nonfinite,
+                       cudaStream_t st);
+int launch_contract(const DevMatrix &m, const unsigned long long *d_counts, int nb, double r,
+                    double *d_rep, int ldrep, int col0, int sum_mode, cudaStream_t st);
+
+}  // namespace cgpu

@@ -1,0 +1,182 @@
+// MT19937 on the device: polynomial jump-ahead and chunked block regeneration that
+// reproduce the reference's process-global uniform stream (src/mt19937.c:57-60,
+// 108-127, 182-197; consumed by mrandlist, src/rand.c:25-29) and turn each draw
+// into the site index of src/makermt.c:55-60.
+//
+// Stream model.  x_0..x_623 is the seeded array (init_genrand, src/mt19937.c:63-76),
+// x_{t+624} = x_{t+397} ^ twist(x_t, x_{t+1}); draw d (0-based) is temper(x_{624+d}).
+// "Window" W_d = (x_d .. x_{d+623}) is everything needed to produce draws d, d+1, ...
+//
+// Kernels
+//   mt_jump_kernel   W_{d+J} = g(F) W_d for g = x^J mod phi: regenerate 19937+624
+//                    words from the source window into shared memory, then every
+//                    output word j is the XOR of x_{i+j} over the set bits i of g.
+//                    The bit range of g is sliced over gridDim.y CTAs (atomicXor
+//                    combine) so early rounds of the doubling tree still fill SMs.
+//   mt_draw_kernel   one CTA per chunk of 2^m draws: ping-pong block regeneration
+//                    in shared memory (3 phases of <=227 independent lanes, exactly
+//                    the dependency structure of next_state), tempering, site index,
+//                    coalesced store of the indices.
+#include "cgpu_internal.h"
+
+namespace cgpu {
+
+__device__ __forceinline__ uint32_t mt_twist(uint32_t hi, uint32_t lo) {
+    uint32_t y = (hi & 0x80000000u) | (lo & 0x7fffffffu);
+    return (y >> 1) ^ ((lo & 1u) ? 0x9908b0dfu : 0u);
+}
+
+__device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
+    y ^= y >> 11;
+    y ^= (y << 7) & 0x9d2c5680u;
+    y ^= (y << 15) & 0xefc60000u;
+    y ^= y >> 18;
+    return y;
+}
+
+// ------------------------------------------------------------------ jump
+constexpr int JUMP_THREADS = 640;
+constexpr int JUMP_SEQ = MT_DEG + MT_N + 63;  // words of the regenerated sequence kept in smem
+
+__global__ void __launch_bounds__(JUMP_THREADS, 1)
+mt_jump_kernel(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst,
+               const uint32_t *__restrict__ poly, int words_per_slice) {
+    extern __shared__ uint32_t sm[];
+    uint32_t *x = sm;                 // JUMP_SEQ words
+    uint32_t *g = sm + JUMP_SEQ + 1;  // 624 words of the polynomial
+    const int tid = threadIdx.x;
+    const uint32_t *w = src + (size_t)blockIdx.x * MT_N;
+    uint32_t *o = dst + (size_t)blockIdx.x * MT_N;
+
+    const int w_lo = blockIdx.y * words_per_slice;
+    const int w_hi = min(w_lo + words_per_slice, MT_POLY_W32);
+    if (w_lo >= w_hi) return;
+    const int need = min(w_hi * 32, MT_DEG) + MT_N;  // sequence words x[0..need)
+
+    if (tid < MT_N) {
+        x[tid] = w[tid];
+        g[tid] = poly[tid];
+    }
+    __syncthreads();
+    // x[t+624] depends on x[t+397]: 227 new words per step are independent
+    for (int t0 = 0; t0 + MT_N < need; t0 += MT_N - MT_M) {
+        int t = t0 + tid;
+        if (tid < MT_N - MT_M && t + MT_N < need)
+            x[t + MT_N] = x[t + MT_M] ^ mt_twist(x[t], x[t + 1]);
+        __syncthreads();
+    }
+    if (tid < MT_N) {
+        uint32_t r = 0;
+        const uint32_t *xj = x + tid;
+        for (int wi = w_lo; wi < w_hi; wi++) {
+            uint32_t gw = g[wi];
+            if (wi == MT_POLY_W32 - 1) gw &= 0xffffffffu >> (MT_POLY_W32 * 32 - MT_DEG);  // bits >= 19937 are not part of a residue
+            const uint32_t *xb = xj + wi * 32;
+#pragma unroll
+            for (int b = 0; b < 32; b++)
+                if (gw >> b & 1) r ^= xb[b];
+        }
+        if (gridDim.y == 1) o[tid] = r;
+        else if (r) atomicXor(&o[tid], r);
+    }
+}
+
+int launch_mt_jump(const uint32_t *d_src, uint32_t *d_dst, const uint32_t *d_poly, int count,
+                   cudaStream_t st) {
+    if (count <= 0) return CGPU_OK;
+    static bool attr_done = false;
+    const size_t smem = (size_t)(JUMP_SEQ + 1 + MT_N) * sizeof(uint32_t);
+    if (!attr_done) {
+        CGPU_CUDA(cudaFuncSetAttribute(mt_jump_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_done = true;
+    }
+    // slice the polynomial over enough CTAs to cover the SMs when few windows jump
+    int sms = G().sm_count > 0 ? G().sm_count : 148;
+    int slices = 1;
+    while (slices < 16 && count * slices < sms) slices *= 2;
+    int wps = (MT_POLY_W32 + slices - 1) / slices;
+    if (slices > 1) CGPU_CUDA(cudaMemsetAsync(d_dst, 0, (size_t)count * MT_N * sizeof(uint32_t), st));
+    mt_jump_kernel<<<dim3(count, slices), JUMP_THREADS, smem, st>>>(d_src, d_dst, d_poly, wps);
+    CGPU_LAUNCH_CHECK();
+    return CGPU_OK;
+}
+
+// ------------------------------------------------------------------ draws
+constexpr int DRAW_THREADS = 256;
+
+// site index of a draw: (int)((double)y * 2^-32 * n) with the reference's clamp
+// (src/mt19937.c:195, src/makermt.c:55-60).  For n < 2^21 the product y*n is exact
+// in fp64, so the truncation equals the integer high word of y*n.
+// PATH 0: integer, 1: fp64, 2: raw tempered word (cgpu_mt19937_stream)
+template <int PATH>
+__device__ __forceinline__ uint32_t site_index(uint32_t y, uint32_t n, double dn) {
+    if (PATH == 2) return y;
+    if (PATH == 0) return __umulhi(y, n);
+    double rv = __dmul_rn((double)y, 1.0 / 4294967296.0);
+    int k = (int)__dmul_rn(rv, dn);
+    if (k < 0) k = 0;
+    else if (k >= (int)n) k = (int)n - 1;
+    return (uint32_t)k;
+}
+
+template <int PATH>
+__global__ void __launch_bounds__(DRAW_THREADS)
+mt_draw_kernel(const uint32_t *__restrict__ states, int chunk_log2, unsigned long long first_chunk,
+               unsigned long long lo, unsigned long long hi, uint32_t n, uint32_t *__restrict__ idx) {
+    __shared__ uint32_t buf[2][MT_N + 1];
+    const int tid = threadIdx.x;
+    const unsigned long long chunk = first_chunk + blockIdx.x;
+    const unsigned long long d_begin = chunk << chunk_log2;
+    unsigned long long d_end = d_begin + (1ull << chunk_log2);
+    if (d_end > hi) d_end = hi;
+    const double dn = (double)n;
+    const uint32_t *w = states + chunk * MT_N;
+    for (int i = tid; i < MT_N; i += DRAW_THREADS) buf[0][i] = w[i];
+    __syncthreads();
+    int cur = 0;
+    for (unsigned long long d0 = d_begin; d0 < d_end; d0 += MT_N) {
+        const uint32_t *o = buf[cur];
+        uint32_t *nw = buf[cur ^ 1];
+        // phase A: k in [0,227) reads only old words
+        if (tid < MT_N - MT_M) nw[tid] = o[tid + MT_M] ^ mt_twist(o[tid], o[tid + 1]);
+        __syncthreads();
+        // phase B: k in [227,454) reads new[k-227]
+        if (tid < MT_N - MT_M) {
+            int k = tid + (MT_N - MT_M);
+            nw[k] = nw[k - (MT_N - MT_M)] ^ mt_twist(o[k], o[k + 1]);
+        }
+        __syncthreads();
+        // phase C: k in [454,624); the last word wraps to new[0]
+        if (tid < MT_N - 2 * (MT_N - MT_M)) {
+            int k = tid + 2 * (MT_N - MT_M);
+            uint32_t nxt = (k == MT_N - 1) ? nw[0] : o[k + 1];
+            nw[k] = nw[k - (MT_N - MT_M)] ^ mt_twist(o[k], nxt);
+        }
+        __syncthreads();
+        if (d0 + MT_N > lo) {
+            for (int i = tid; i < MT_N; i += DRAW_THREADS) {
+                unsigned long long d = d0 + i;
+                if (d >= lo && d < d_end) idx[d - lo] = site_index<PATH>(mt_temper(nw[i]), n, dn);
+            }
+        }
+        cur ^= 1;
+        // no barrier needed here: the next phase A only writes buf[cur^1] (= the old
+        // array, last read in phase C before the barrier above) and reads buf[cur].
+    }
+}
+
+int launch_mt_draw(const uint32_t *d_states, int chunk_log2, unsigned long long first_chunk,
+                   int nchunks, unsigned long long lo, unsigned long long hi, uint32_t n,
+                   uint32_t *d_idx, cudaStream_t st) {
+    if (nchunks <= 0) return CGPU_OK;
+    if (n == 0)
+        mt_draw_kernel<2><<<nchunks, DRAW_THREADS, 0, st>>>(d_states, chunk_log2, first_chunk, lo, hi, n, d_idx);
+    else if (n < (1u << 21))
+        mt_draw_kernel<0><<<nchunks, DRAW_THREADS, 0, st>>>(d_states, chunk_log2, first_chunk, lo, hi, n, d_idx);
+    else
+        mt_draw_kernel<1><<<nchunks, DRAW_THREADS, 0, st>>>(d_states, chunk_log2, first_chunk, lo, hi, n, d_idx);
+    CGPU_LAUNCH_CHECK();
+    return CGPU_OK;
+}
+
+}  // namespace cgpu

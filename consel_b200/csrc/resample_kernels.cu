@@ -1,0 +1,222 @@
+// Site histograms: c[b, j] = #{draws of replicate b that hit site j}
+// (src/makermt.c:53-62), written in the layout the contraction kernels read.
+//
+// Count layout ("BJ8"): one 64-bit word per (replicate group g = b/8, site j) holding
+// the eight byte-counts of replicates 8g..8g+7 (byte t = replicate 8g+t); rows are
+// NP = pad_sites(n) words long and zero padded, so a warp of the contraction kernel
+// fetches the counts of its 8 replicates at a site with ONE broadcast 8-byte load.
+//
+// Two ways of producing it:
+//   hist_group_kernel  n <= HIST_SMEM_SITES: one CTA per replicate group, one WARP per
+//                      replicate, warp-private byte histogram in shared memory.  Lanes
+//                      of a warp resolve collisions with match.any, so no atomics are
+//                      needed; the CTA then interleaves its eight histograms and writes
+//                      the BJ8 words with coalesced 32-byte stores.
+//   hist_global_kernel larger n (the histogram of one replicate no longer fits shared
+//                      memory): one thread per draw, 32-bit atomic add on the word that
+//                      holds the byte.
+// Draw sources: the index buffer written by mt_draw_kernel (reference stream) or a
+// counter-based Philox4x32-10 keyed by (seed; scale, replicate) — Salmon, Moraes, Dror,
+// Shaw, "Parallel random numbers: as easy as 1, 2, 3", SC'11.
+#include <algorithm>
+
+#include "cgpu_internal.h"
+
+namespace cgpu {
+
+constexpr int HIST_SMEM_SITES = 28160;  // 8 * 28160 B = 220 KB of shared memory
+constexpr int HIST_THREADS = 256;
+
+// ------------------------------------------------------------------ Philox4x32-10
+struct Philox4 {
+    uint32_t v[4];
+};
+__device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                 uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return Philox4{{c0, c1, c2, c3}};
+}
+
+// one warp adds the site indices its lanes hold to a warp-private byte histogram
+__device__ __forceinline__ void warp_hist_add(unsigned char *hist, uint32_t k, bool valid, int lane,
+                                              int *overflow) {
+    unsigned active = __ballot_sync(0xffffffffu, valid);
+    if (valid) {
+        unsigned peers = __match_any_sync(active, k);
+        if (lane == __ffs(peers) - 1) {
+            unsigned v = hist[k] + __popc(peers);
+            if (v > 255u) *overflow = 1;
+            hist[k] = (unsigned char)v;
+        }
+    }
+    __syncwarp();
+}
+
+// SRC 0: indices from the buffer (replicate r of this launch at idx[r*bn ..));  SRC 1: Philox
+template <int SRC>
+__global__ void __launch_bounds__(HIST_THREADS)
+hist_group_kernel(const uint32_t *__restrict__ idx, int n, int NP, int bn, int nb,
+                  unsigned long long *__restrict__ counts, int *__restrict__ err,
+                  uint32_t key0, uint32_t key1, uint32_t scale, uint32_t b_first) {
+    extern __shared__ unsigned char hsm[];  // 8 histograms of NP bytes
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int ngroups = (nb + 7) / 8;
+    for (int g = blockIdx.x; g < ngroups; g += gridDim.x) {
+        for (int i = tid; i < NP * 2; i += HIST_THREADS) reinterpret_cast<uint32_t *>(hsm)[i] = 0;
+        __syncthreads();
+        const int r = g * 8 + wid;  // replicate within this launch
+        if (r < nb) {
+            unsigned char *hist = hsm + (size_t)wid * NP;
+            int overflow = 0;
+            if (SRC == 0) {
+                const uint32_t *src = idx + (size_t)r * bn;
+                for (int i0 = 0; i0 < bn; i0 += 32) {
+                    int i = i0 + lane;
+                    bool valid = i < bn;
+                    uint32_t k = valid ? src[i] : 0u;
+                    warp_hist_add(hist, k, valid, lane, &overflow);
+                }
+            } else {
+                // draw i of replicate b is word (i & 3) of Philox(counter = (i >> 2, b, scale, 0))
+                const uint32_t b = b_first + (uint32_t)r;
+                for (int i0 = 0; i0 < bn; i0 += 128) {
+                    int q = (i0 >> 2) + lane;
+                    Philox4 p = philox4x32_10((uint32_t)q, b, scale, 0u, key0, key1);
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        bool valid = q * 4 + u < bn;
+                        warp_hist_add(hist, __umulhi(p.v[u], (uint32_t)n), valid, lane, &overflow);
+                    }
+                }
+            }
+            if (overflow) atomicExch(err, 1);
+        }
+        __syncthreads();
+        // interleave: 4 consecutive sites of all 8 histograms -> 4 BJ8 words (32 bytes)
+        unsigned long long *row = counts + (size_t)g * NP;
+        for (int j4 = tid; j4 < NP / 4; j4 += HIST_THREADS) {
+            uint32_t h[8];
+#pragma unroll
+            for (int w = 0; w < 8; w++) h[w] = reinterpret_cast<const uint32_t *>(hsm + (size_t)w * NP)[j4];
+            uint32_t out[8];
+#pragma unroll
+            for (int s = 0; s < 4; s++) {
+                // site j4*4+s: byte s of every h[w]
+                const uint32_t sel = (uint32_t)s | ((4u + s) << 4);  // low two bytes = {a.byte[s], b.byte[s]}
+                uint32_t lo01 = __byte_perm(h[0], h[1], sel) & 0xffffu, lo23 = __byte_perm(h[2], h[3], sel);
+                uint32_t hi01 = __byte_perm(h[4], h[5], sel) & 0xffffu, hi23 = __byte_perm(h[6], h[7], sel);
+                out[2 * s] = lo01 | (lo23 << 16);
+                out[2 * s + 1] = hi01 | (hi23 << 16);
+            }
+            uint4 *dst = reinterpret_cast<uint4 *>(row + (size_t)j4 * 4);
+            dst[0] = make_uint4(out[0], out[1], out[2], out[3]);
+            dst[1] = make_uint4(out[4], out[5], out[6], out[7]);
+        }
+        __syncthreads();
+    }
+}
+
+template <int SRC>
+__global__ void __launch_bounds__(256)
+hist_global_kernel(const uint32_t *__restrict__ idx, int n, int NP, int bn, int nb,
+                   unsigned int *__restrict__ counts32, uint32_t key0, uint32_t key1, uint32_t scale,
+                   uint32_t b_first) {
+    const unsigned long long total = SRC == 0 ? (unsigned long long)nb * bn
+                                              : (unsigned long long)nb * ((bn + 3) / 4);
+    for (unsigned long long d = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; d < total;
+         d += (unsigned long long)gridDim.x * blockDim.x) {
+        if (SRC == 0) {
+            uint32_t r = (uint32_t)(d / bn);
+            uint32_t k = idx[d];
+            size_t word = ((size_t)(r >> 3) * NP + k) * 2 + ((r & 7) >> 2);
+            atomicAdd(&counts32[word], 1u << ((r & 3) * 8));
+        } else {
+            uint32_t qn = (uint32_t)((bn + 3) / 4);
+            uint32_t r = (uint32_t)(d / qn), q = (uint32_t)(d % qn);
+            Philox4 p = philox4x32_10(q, b_first + r, scale, 0u, key0, key1);
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if ((int)(q * 4 + u) < bn) {
+                    uint32_t k = __umulhi(p.v[u], (uint32_t)n);
+                    size_t word = ((size_t)(r >> 3) * NP + k) * 2 + ((r & 7) >> 2);
+                    atomicAdd(&counts32[word], 1u << ((r & 3) * 8));
+                }
+            }
+        }
+    }
+}
+
+static int hist_dispatch(int src, const uint32_t *d_idx, int n, int NP, int bn, int nb,
+                         unsigned long long *d_counts, int *d_err, uint32_t k0, uint32_t k1, uint32_t scale,
+                         uint32_t b_first, cudaStream_t st) {
+    if (nb <= 0) return CGPU_OK;
+    const int ngroups = (nb + 7) / 8;
+    if (NP <= HIST_SMEM_SITES) {
+        static bool attr_done = false;
+        if (!attr_done) {
+            CGPU_CUDA(cudaFuncSetAttribute(hist_group_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * HIST_SMEM_SITES));
+            CGPU_CUDA(cudaFuncSetAttribute(hist_group_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * HIST_SMEM_SITES));
+            attr_done = true;
+        }
+        size_t smem = (size_t)8 * NP;
+        int sms = G().sm_count > 0 ? G().sm_count : 148;
+        int per_sm = (int)std::min<size_t>(8, (220 * 1024) / smem);
+        if (per_sm < 1) per_sm = 1;
+        int grid = std::min(ngroups, sms * per_sm);
+        if (src == 0)
+            hist_group_kernel<0><<<grid, HIST_THREADS, smem, st>>>(d_idx, n, NP, bn, nb, d_counts, d_err, k0, k1, scale, b_first);
+        else
+            hist_group_kernel<1><<<grid, HIST_THREADS, smem, st>>>(d_idx, n, NP, bn, nb, d_counts, d_err, k0, k1, scale, b_first);
+        CGPU_LAUNCH_CHECK();
+    } else {
+        CGPU_CUDA(cudaMemsetAsync(d_counts, 0, (size_t)ngroups * NP * 8, st));
+        int sms = G().sm_count > 0 ? G().sm_count : 148;
+        int grid = sms * 16;
+        if (src == 0)
+            hist_global_kernel<0><<<grid, 256, 0, st>>>(d_idx, n, NP, bn, nb, reinterpret_cast<unsigned int *>(d_counts), k0, k1, scale, b_first);
+        else
+            hist_global_kernel<1><<<grid, 256, 0, st>>>(d_idx, n, NP, bn, nb, reinterpret_cast<unsigned int *>(d_counts), k0, k1, scale, b_first);
+        CGPU_LAUNCH_CHECK();
+    }
+    return CGPU_OK;
+}
+
+int launch_hist_from_idx(const uint32_t *d_idx, int n, int NP, int bn, int nb,
+                         unsigned long long *d_counts, int *d_err, cudaStream_t st) {
+    return hist_dispatch(0, d_idx, n, NP, bn, nb, d_counts, d_err, 0, 0, 0, 0, st);
+}
+
+int launch_hist_philox(unsigned long long seed, int scale, int b_first, int n, int NP, int bn, int nb,
+                       unsigned long long *d_counts, int *d_err, cudaStream_t st) {
+    return hist_dispatch(1, nullptr, n, NP, bn, nb, d_counts, d_err, (uint32_t)seed, (uint32_t)(seed >> 32),
+                         (uint32_t)scale, (uint32_t)b_first, st);
+}
+
+// BJ8 -> plain counts[b*n + j] bytes (test seam: cgpu_resample_counts)
+__global__ void counts_unpack_kernel(const unsigned long long *__restrict__ counts, int n, int NP, int nb,
+                                     unsigned char *__restrict__ out) {
+    size_t total = (size_t)nb * n;
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        int b = (int)(e / n), j = (int)(e % n);
+        unsigned long long w = counts[(size_t)(b >> 3) * NP + j];
+        out[e] = (unsigned char)(w >> ((b & 7) * 8));
+    }
+}
+
+int launch_counts_unpack(const unsigned long long *d_counts, int n, int NP, int nb, unsigned char *d_out,
+                         cudaStream_t st) {
+    if (nb <= 0) return CGPU_OK;
+    counts_unpack_kernel<<<1024, 256, 0, st>>>(d_counts, n, NP, nb, d_out);
+    CGPU_LAUNCH_CHECK();
+    return CGPU_OK;
+}
+
+}  // namespace cgpu

@@ -1,0 +1,424 @@
+// consel's replicate-statistics loops on the device (src/consel.c, H4-H11 of SURVEY 2.3).
+//
+// Everything the AU/BP/KH/SH machinery needs from a row v[0..B) of replicate
+// statistics is a "row summary" against a threshold t:
+//     cnt = #{v <= t}, lo = max{v <= t}, hi = min{v > t}, the two smallest and the two
+//     largest values
+// from which cntdist2/cntdist3 (src/consel.c:1806-1860) are reproduced bit for bit
+// (cgpu_smooth_count), so no row is ever sorted: sort_vec (src/consel.c:1466-1471,
+// 80% of consel at K=15) becomes one streaming pass per query round.  All reductions
+// used here (integer count, max, min) are exact and order independent, which is why
+// the results do not depend on tiling or on how replicates are sharded over GPUs.
+//
+// Layouts: replicate block rep[k*ld + b] (tree-major, as in .rmt); statistic block
+// stat[e*ld + b] (item-major, as in .rep).  These kernels are HBM-streaming: 8 bytes
+// per (row, replicate) element per pass.
+#include "cgpu_internal.h"
+
+namespace cgpu {
+
+#define CG_HUGE 1.0e30  // src/consel.c:155
+
+// ------------------------------------------------------------------ top-2 per replicate
+// For column b: m1 = max_k x, a1 = first index attaining it, m2 = max_{k != a1} x, all
+// with the reference's -1e30 floor, so max_{j != i} x_j == (i == a1 ? m2 : m1) exactly
+// as the prefix/suffix scan of calcmaxs (src/consel.c:1894-1916) yields it.
+__global__ void __launch_bounds__(128)
+col_top2_kernel(const double *__restrict__ x, int K, int B, int ld, double *__restrict__ m1o,
+                double *__restrict__ m2o, int *__restrict__ a1o) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double m1 = -CG_HUGE, m2 = -CG_HUGE;
+    int a1 = -1;
+    for (int k = 0; k < K; k++) {
+        double v = x[(size_t)k * ld + b];
+        if (v > m1) {
+            m2 = m1;
+            m1 = v;
+            a1 = k;
+        } else if (v > m2) {
+            m2 = v;
+        }
+    }
+    m1o[b] = m1;
+    m2o[b] = m2;
+    a1o[b] = a1;
+}
+
+// repminmaxs (src/consel.c:1939-1959): stat[e][b] = min_{i in A_e} (max_{j!=i} x_j - x_i)
+__global__ void __launch_bounds__(128)
+stat_build_kernel(const double *__restrict__ x, int K, int B, int ld, const double *__restrict__ m1v,
+                  const double *__restrict__ m2v, const int *__restrict__ a1v, int cm,
+                  const int *__restrict__ ass_ptr, const int *__restrict__ ass_idx,
+                  double *__restrict__ stat) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const double m1 = m1v[b], m2 = m2v[b];
+    const int a1 = a1v[b];
+    for (int e = blockIdx.y; e < cm; e += gridDim.y) {
+        double y = CG_HUGE;
+        for (int q = ass_ptr[e]; q < ass_ptr[e + 1]; q++) {
+            int i = ass_idx[q];
+            double st = __dsub_rn(i == a1 ? m2 : m1, x[(size_t)i * ld + b]);
+            if (st < y) y = st;
+        }
+        stat[(size_t)e * ld + b] = y;
+    }
+}
+
+// ------------------------------------------------------------------ row summaries
+struct RowAcc {
+    unsigned long long cnt;
+    double lo, hi;
+};
+
+__device__ __forceinline__ void edge_insert(double v, double &mn1, double &mn2, double &mx1, double &mx2) {
+    if (v < mn1) { mn2 = mn1; mn1 = v; } else if (v < mn2) mn2 = v;
+    if (v > mx1) { mx2 = mx1; mx1 = v; } else if (v > mx2) mx2 = v;
+}
+__device__ __forceinline__ void edge_merge(double &mn1, double &mn2, double &mx1, double &mx2, double o1,
+                                           double o2, double p1, double p2) {
+    // two smallest of {mn1<=mn2, o1<=o2}; two largest of {mx1>=mx2, p1>=p2}
+    double a = fmin(mn1, o1), bb = fmax(mn1, o1);
+    mn2 = fmin(bb, fmin(mn2, o2));
+    mn1 = a;
+    double c = fmax(mx1, p1), d = fmin(mx1, p1);
+    mx2 = fmax(d, fmax(mx2, p2));
+    mx1 = c;
+}
+
+constexpr int RS_THREADS = 256;
+constexpr int RS_MAXQ = 16;
+
+// value of element b of row `row` under the three row definitions
+//  MODE 0: plain row            v = x[row*ld + b]
+//  MODE 1: KH difference        v = x[ja*ld + b] - x[ia*ld + b]            (src/consel.c:2145-2146)
+//  MODE 2: singleton SH/stat    v = (i == a1[b] ? m2[b] : m1[b]) - x[i*ld + b]  (src/consel.c:2026-2030 with |A|=1)
+struct RowSrc {
+    const double *x;
+    int ld;
+    const int *ia, *ja;           // MODE 1 (per row) / MODE 2: ia = tree of the row
+    const double *m1, *m2;        // MODE 2
+    const int *a1;                // MODE 2
+};
+
+template <int MODE>
+__device__ __forceinline__ double row_value(const RowSrc &s, int row, int b, int i_row, int j_row) {
+    if (MODE == 0) return s.x[(size_t)row * s.ld + b];
+    if (MODE == 1) return __dsub_rn(s.x[(size_t)j_row * s.ld + b], s.x[(size_t)i_row * s.ld + b]);
+    return __dsub_rn(i_row == s.a1[b] ? s.m2[b] : s.m1[b], s.x[(size_t)i_row * s.ld + b]);
+}
+
+// one CTA per row; nq thresholds per row: thr[row*nq + q]; out[(row*out_stride + out_off)*nq + q]
+template <int MODE>
+__global__ void __launch_bounds__(RS_THREADS)
+rowsum_kernel(RowSrc src, int B, int nq, const double *__restrict__ thr, cgpu_rowsum *__restrict__ out,
+              int out_stride, int out_off) {
+    const int row = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    __shared__ double s_thr[RS_MAXQ];
+    __shared__ unsigned long long s_cnt[RS_THREADS / 32][RS_MAXQ];
+    __shared__ double s_lo[RS_THREADS / 32][RS_MAXQ], s_hi[RS_THREADS / 32][RS_MAXQ];
+    __shared__ double s_edge[RS_THREADS / 32][4];
+    if (tid < nq) s_thr[tid] = thr[(size_t)row * nq + tid];
+    __syncthreads();
+    const int i_row = (MODE == 0) ? 0 : src.ia[row];
+    const int j_row = (MODE == 1) ? src.ja[row] : 0;
+
+    unsigned long long cnt[RS_MAXQ];
+    double lo[RS_MAXQ], hi[RS_MAXQ];
+#pragma unroll
+    for (int q = 0; q < RS_MAXQ; q++) {
+        cnt[q] = 0;
+        lo[q] = -CG_HUGE;
+        hi[q] = CG_HUGE;
+    }
+    double mn1 = CG_HUGE, mn2 = CG_HUGE, mx1 = -CG_HUGE, mx2 = -CG_HUGE;
+    for (int b = tid; b < B; b += RS_THREADS) {
+        const double v = row_value<MODE>(src, row, b, i_row, j_row);
+        edge_insert(v, mn1, mn2, mx1, mx2);
+#pragma unroll
+        for (int q = 0; q < RS_MAXQ; q++) {
+            if (q < nq) {
+                const double t = s_thr[q];
+                if (v <= t) {
+                    cnt[q]++;
+                    lo[q] = fmax(lo[q], v);
+                } else {
+                    hi[q] = fmin(hi[q], v);
+                }
+            }
+        }
+    }
+    // warp reduce, then across warps through shared memory
+#pragma unroll
+    for (int off = 16; off; off >>= 1) {
+#pragma unroll
+        for (int q = 0; q < RS_MAXQ; q++) {
+            if (q < nq) {
+                cnt[q] += __shfl_xor_sync(0xffffffffu, cnt[q], off);
+                lo[q] = fmax(lo[q], __shfl_xor_sync(0xffffffffu, lo[q], off));
+                hi[q] = fmin(hi[q], __shfl_xor_sync(0xffffffffu, hi[q], off));
+            }
+        }
+        double o1 = __shfl_xor_sync(0xffffffffu, mn1, off), o2 = __shfl_xor_sync(0xffffffffu, mn2, off);
+        double p1 = __shfl_xor_sync(0xffffffffu, mx1, off), p2 = __shfl_xor_sync(0xffffffffu, mx2, off);
+        edge_merge(mn1, mn2, mx1, mx2, o1, o2, p1, p2);
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < RS_MAXQ; q++)
+            if (q < nq) {
+                s_cnt[wid][q] = cnt[q];
+                s_lo[wid][q] = lo[q];
+                s_hi[wid][q] = hi[q];
+            }
+        s_edge[wid][0] = mn1; s_edge[wid][1] = mn2; s_edge[wid][2] = mx1; s_edge[wid][3] = mx2;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < RS_THREADS / 32; w++)
+            edge_merge(mn1, mn2, mx1, mx2, s_edge[w][0], s_edge[w][1], s_edge[w][2], s_edge[w][3]);
+        s_edge[0][0] = mn1; s_edge[0][1] = mn2; s_edge[0][2] = mx1; s_edge[0][3] = mx2;
+    }
+    __syncthreads();
+    if (tid < nq) {
+        unsigned long long c = 0;
+        double l = -CG_HUGE, h = CG_HUGE;
+        for (int w = 0; w < RS_THREADS / 32; w++) {
+            c += s_cnt[w][tid];
+            l = fmax(l, s_lo[w][tid]);
+            h = fmin(h, s_hi[w][tid]);
+        }
+        cgpu_rowsum r;
+        r.cnt = (double)c;
+        r.lo = l;
+        r.hi = h;
+        r.min1 = s_edge[0][0]; r.min2 = s_edge[0][1]; r.max1 = s_edge[0][2]; r.max2 = s_edge[0][3];
+        out[((size_t)row * out_stride + out_off) * nq + tid] = r;
+    }
+}
+
+int launch_rowsum(int mode, const RowSrc &src, int rows, int B, int nq, const double *d_thr, cgpu_rowsum *d_out,
+                  int out_stride, int out_off, cudaStream_t st) {
+    if (rows <= 0) return CGPU_OK;
+    if (nq < 1 || nq > RS_MAXQ) {
+        set_error(CGPU_EINVAL, "nq=%d (1..%d)", nq, RS_MAXQ);
+        return CGPU_EINVAL;
+    }
+    if (mode == 0) rowsum_kernel<0><<<rows, RS_THREADS, 0, st>>>(src, B, nq, d_thr, d_out, out_stride, out_off);
+    else if (mode == 1) rowsum_kernel<1><<<rows, RS_THREADS, 0, st>>>(src, B, nq, d_thr, d_out, out_stride, out_off);
+    else rowsum_kernel<2><<<rows, RS_THREADS, 0, st>>>(src, B, nq, d_thr, d_out, out_stride, out_off);
+    CGPU_LAUNCH_CHECK();
+    return CGPU_OK;
+}
+
+// ------------------------------------------------------------------ order statistic
+// k-th smallest (0-based) of each row by bisection on the bits of the order-preserving
+// integer image of a double: 64 counting passes over a row that stays in L1/L2.
+__device__ __forceinline__ unsigned long long dkey(double v) {
+    unsigned long long u = (unsigned long long)__double_as_longlong(v);
+    return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double dunkey(unsigned long long k) {
+    unsigned long long u = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+    return __longlong_as_double((long long)u);
+}
+
+__global__ void __launch_bounds__(256)
+order_stat_kernel(const double *__restrict__ stat, int B, int ld, const int *__restrict__ rank,
+                  double *__restrict__ val) {
+    const int row = blockIdx.x, tid = threadIdx.x;
+    const double *v = stat + (size_t)row * ld;
+    const unsigned int k = (unsigned int)rank[row];
+    __shared__ unsigned int s_cnt[8];
+    __shared__ unsigned long long s_res;
+    if (tid == 0) s_res = 0;
+    __syncthreads();
+    for (int bit = 63; bit >= 0; bit--) {
+        const unsigned long long cand = s_res | (1ull << bit);
+        unsigned int c = 0;
+        for (int b = tid; b < B; b += 256) c += dkey(v[b]) < cand;
+#pragma unroll
+        for (int off = 16; off; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
+        if ((tid & 31) == 0) s_cnt[tid >> 5] = c;
+        __syncthreads();
+        if (tid == 0) {
+            unsigned int tot = 0;
+            for (int w = 0; w < 8; w++) tot += s_cnt[w];
+            if (tot <= k) s_res = cand;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) val[row] = dunkey(s_res);
+}
+
+int launch_order_stat(const double *d_stat, int rows, int B, int ld, const int *d_rank, double *d_val,
+                      cudaStream_t st) {
+    if (rows <= 0) return CGPU_OK;
+    order_stat_kernel<<<rows, 256, 0, st>>>(d_stat, B, ld, d_rank, d_val);
+    CGPU_LAUNCH_CHECK();
+    return CGPU_OK;
+}
+
+// ------------------------------------------------------------------ mc-test pieces
+// centring (src/consel.c:1378-1382): one warp per tree; the row sum is accumulated in
+// the reference's order (b ascending, one rounded add per element): lanes fetch 32
+// consecutive values, every lane replays the 32 adds through shuffles.
+__global__ void __launch_bounds__(128)
+center_rows_kernel(const double *__restrict__ x, int K, int B, int ld, double *__restrict__ xc) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= K) return;
+    const double *src = x + (size_t)row * ld;
+    double s = 0.0;
+    for (int b0 = 0; b0 < B; b0 += 32) {
+        const int b = b0 + lane;
+        const double v = b < B ? src[b] : 0.0;
+        const int m = min(32, B - b0);
+        for (int t = 0; t < m; t++) s = __dadd_rn(s, __shfl_sync(0xffffffffu, v, t));
+    }
+    const double mean = __ddiv_rn(s, (double)B);
+    double *dst = xc + (size_t)row * ld;
+    for (int b = lane; b < B; b += 32) dst[b] = __dsub_rn(src[b], mean);
+}
+
+// pairwise variances -> weights (src/consel.c:1404-1415):
+//   wt[i][j] = 1/sqrt((sum_b (x_i - x_j)^2 + varadd)/(B-1)), sum in replicate order.
+// 16x16 pairs per CTA, one pair per thread, replicates staged through shared memory.
+constexpr int PV_T = 16, PV_BC = 64;
+__global__ void __launch_bounds__(PV_T * PV_T)
+pair_weight_kernel(const double *__restrict__ xc, int K, int B, int ld, double varadd, double *__restrict__ wt,
+                   int *__restrict__ nsmall) {
+    const int ti = blockIdx.y, tj = blockIdx.x;
+    if (tj > ti) return;
+    __shared__ double si[PV_T][PV_BC + 1], sj[PV_T][PV_BC + 1];
+    const int tx = threadIdx.x % PV_T, ty = threadIdx.x / PV_T;  // pair (i = ti*16+ty, j = tj*16+tx)
+    const int i = ti * PV_T + ty, j = tj * PV_T + tx;
+    double acc = 0.0;
+    for (int b0 = 0; b0 < B; b0 += PV_BC) {
+        for (int e = threadIdx.x; e < PV_T * PV_BC; e += PV_T * PV_T) {
+            int r = e / PV_BC, c = e % PV_BC;
+            int b = b0 + c;
+            int gi = ti * PV_T + r, gj = tj * PV_T + r;
+            si[r][c] = (gi < K && b < B) ? xc[(size_t)gi * ld + b] : 0.0;
+            sj[r][c] = (gj < K && b < B) ? xc[(size_t)gj * ld + b] : 0.0;
+        }
+        __syncthreads();
+        const int m = min(PV_BC, B - b0);
+        for (int c = 0; c < m; c++) {
+            double d = __dsub_rn(si[ty][c], sj[tx][c]);
+            acc = __dadd_rn(acc, __dmul_rn(d, d));
+        }
+        __syncthreads();
+    }
+    if (i < K && j < i) {
+        if (acc < varadd * 100.0) atomicAdd(nsmall, 1);  // VARADDWARN, src/consel.c:154,1409
+        double w = __ddiv_rn(1.0, __dsqrt_rn(__ddiv_rn(__dadd_rn(acc, varadd), (double)(B - 1))));
+        wt[(size_t)i * K + j] = w;
+        wt[(size_t)j * K + i] = w;
+    }
+    if (i < K && i == j) wt[(size_t)i * K + i] = 0.0;
+}
+
+// SH statistic rows for general association sets (src/consel.c:2026-2030, 2017-2024):
+//   unweighted: out[q][b] = max_{j in cass(e)} x[j][b] - x[i_q][b]
+//   weighted:   out[q][b] = max_{j in cass(e)} wt[i_q][j] * (x[j][b] - x[i_q][b])
+// q runs over the members (CSR positions) of the items; comp marks complement by item.
+template <bool WEIGHTED>
+__global__ void __launch_bounds__(128)
+sh_rows_kernel(const double *__restrict__ x, int K, int B, int ld, const double *__restrict__ wt,
+               const int *__restrict__ mem_item, const int *__restrict__ mem_tree,
+               const int *__restrict__ cass_ptr, const int *__restrict__ cass_idx, double *__restrict__ out) {
+    const int q = blockIdx.y;
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int e = mem_item[q], i = mem_tree[q];
+    const double x0 = x[(size_t)i * ld + b];
+    double mx = -CG_HUGE;
+    if (WEIGHTED) {
+        const double *wp = wt + (size_t)i * K;
+        for (int p = cass_ptr[e]; p < cass_ptr[e + 1]; p++) {
+            int j = cass_idx[p];
+            double y = __dmul_rn(wp[j], __dsub_rn(x[(size_t)j * ld + b], x0));
+            if (y > mx) mx = y;
+        }
+        out[(size_t)q * ld + b] = mx;
+    } else {
+        for (int p = cass_ptr[e]; p < cass_ptr[e + 1]; p++) {
+            double y = x[(size_t)cass_idx[p] * ld + b];
+            if (y > mx) mx = y;
+        }
+        out[(size_t)q * ld + b] = __dsub_rn(mx, x0);
+    }
+}
+
+// observed statistics and KH contrasts that depend on the weights (src/consel.c:2121-2134,
+// 2017-2024 applied to datvec): one thread per member.
+__global__ void __launch_bounds__(128)
+weighted_obs_kernel(const double *__restrict__ dat, int K, const double *__restrict__ wt, int nmem,
+                    const int *__restrict__ mem_item, const int *__restrict__ mem_tree,
+                    const int *__restrict__ cass_ptr, const int *__restrict__ cass_idx,
+                    double *__restrict__ obs, int *__restrict__ argj) {
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nmem) return;
+    const int e = mem_item[q], i = mem_tree[q];
+    const double x0 = dat[i];
+    const double *wp = wt + (size_t)i * K;
+    double mx = -CG_HUGE;
+    int jj = 0;
+    for (int p = cass_ptr[e]; p < cass_ptr[e + 1]; p++) {
+        int j = cass_idx[p];
+        double y = __dmul_rn(wp[j], __dsub_rn(dat[j], x0));
+        if (y > mx) { mx = y; jj = p - cass_ptr[e]; }
+    }
+    obs[q] = mx;
+    argj[q] = jj;
+}
+
+int launch_col_top2(const double *x, int K, int B, int ld, double *m1, double *m2, int *a1, cudaStream_t st) {
+    if (B <= 0) return CGPU_OK;
+    col_top2_kernel<<<(B + 127) / 128, 128, 0, st>>>(x, K, B, ld, m1, m2, a1);
+    CGPU_LAUNCH_CHECK();
+    return CGPU_OK;
+}
+int launch_stat_build(const double *x, int K, int B, int ld, const double *m1, const double *m2, const int *a1,
+                      int cm, const int *ass_ptr, const int *ass_idx, double *stat, cudaStream_t st) {
+    if (B <= 0 || cm <= 0) return CGPU_OK;
+    int gy = std::min(cm, 64);
+    stat_build_kernel<<<dim3((B + 127) / 128, gy), 128, 0, st>>>(x, K, B, ld, m1, m2, a1, cm, ass_ptr, ass_idx, stat);
+    CGPU_LAUNCH_CHECK();
+    return CGPU_OK;
+}
+int launch_center(const double *x, int K, int B, int ld, double *xc, cudaStream_t st) {
+    center_rows_kernel<<<(K + 3) / 4, 128, 0, st>>>(x, K, B, ld, xc);
+    CGPU_LAUNCH_CHECK();
+    return CGPU_OK;
+}
+int launch_pair_weight(const double *xc, int K, int B, int ld, double varadd, double *wt, int *nsmall,
+                       cudaStream_t st) {
+    int t = (K + PV_T - 1) / PV_T;
+    pair_weight_kernel<<<dim3(t, t), PV_T * PV_T, 0, st>>>(xc, K, B, ld, varadd, wt, nsmall);
+    CGPU_LAUNCH_CHECK();
+    return CGPU_OK;
+}
+int launch_sh_rows(bool weighted, const double *x, int K, int B, int ld, const double *wt, int nmem,
+                   const int *mem_item, const int *mem_tree, const int *cass_ptr, const int *cass_idx, double *out,
+                   cudaStream_t st) {
+    if (nmem <= 0 || B <= 0) return CGPU_OK;
+    dim3 grid((B + 127) / 128, nmem);
+    if (weighted) sh_rows_kernel<true><<<grid, 128, 0, st>>>(x, K, B, ld, wt, mem_item, mem_tree, cass_ptr, cass_idx, out);
+    else sh_rows_kernel<false><<<grid, 128, 0, st>>>(x, K, B, ld, wt, mem_item, mem_tree, cass_ptr, cass_idx, out);
+    CGPU_LAUNCH_CHECK();
+    return CGPU_OK;
+}
+int launch_weighted_obs(const double *dat, int K, const double *wt, int nmem, const int *mem_item,
+                        const int *mem_tree, const int *cass_ptr, const int *cass_idx, double *obs, int *argj,
+                        cudaStream_t st) {
+    if (nmem <= 0) return CGPU_OK;
+    weighted_obs_kernel<<<(nmem + 127) / 128, 128, 0, st>>>(dat, K, wt, nmem, mem_item, mem_tree, cass_ptr, cass_idx, obs, argj);
+    CGPU_LAUNCH_CHECK();
+    return CGPU_OK;
+}
+
+}  // namespace cgpu

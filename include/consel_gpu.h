@@ -1,0 +1,158 @@
+/*
+ * consel_gpu.h — C ABI of libconselgpu.so: the B200 (sm_100a) implementation of
+ * CONSEL's multiscale RELL bootstrap hot path.
+ *
+ * The reference (shimo-lab/consel) has no plugin/FFI interface; its drop-in
+ * surface is the makermt/consel command lines + file formats, and, at source
+ * level, the call sites named beside each entry point below (paths relative to
+ * the reference tree).  A reference maintainer replaces exactly those loops with
+ * these calls (INTEGRATION.md shows the patch); our own host programs
+ * (consel_b200/host/) do the same.
+ *
+ * Conventions
+ *   - plain C, no C++/torch types; every size is a 32-bit int like the
+ *     reference's, matrices are caller-owned HOST memory unless the name says
+ *     "dev"; the library owns all device memory behind opaque handles.
+ *   - return 0 on success, a negative CGPU_E* code on failure;
+ *     cgpu_last_error() then returns a static, thread-local message.  The host
+ *     programs turn a failure into the reference's `#! Terminated: ...` + exit(1)
+ *     (src/misc.c:40-49).  There is NO CPU fallback: without a CUDA device every
+ *     compute entry point fails with CGPU_ENODEV.
+ *   - calls on one handle are serialised by the caller (the reference is
+ *     single-threaded).
+ */
+#ifndef CONSEL_GPU_H
+#define CONSEL_GPU_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CGPU_OK 0
+#define CGPU_EINVAL (-1)  /* bad argument                                   */
+#define CGPU_ENODEV (-2)  /* no usable CUDA device / wrong architecture      */
+#define CGPU_ECUDA (-3)   /* CUDA runtime error (message has the details)    */
+#define CGPU_ENOMEM (-4)  /* device or host allocation failed                */
+#define CGPU_ERANGE (-5)  /* a site count exceeded the int8 range (tiny n)   */
+
+/* rng_mode */
+#define CGPU_RNG_MT19937 0 /* replays the reference's seeded stream (src/mt19937.c, src/rand.c:25-37) */
+#define CGPU_RNG_PHILOX 1  /* counter-based Philox4x32-10 keyed by (seed; scale, replicate)           */
+/* sum_mode */
+#define CGPU_SUM_STRICT 0 /* reference order of operations: bit-identical to src/makermt.c:65-70     */
+#define CGPU_SUM_FAST 1   /* fp64 FMA, same site order (<= 1 ulp per term from the reference)        */
+#define CGPU_SUM_INT8 2   /* fixed-point int8 slices on tcgen05 tensor cores, exact integer sum      */
+
+/* ------------------------------------------------------------------ lifecycle */
+/* Select the device (device < 0: honour LOCAL_RANK, else device 0), create the
+ * streams and build the MT19937 jump table.  Idempotent.                        */
+int cgpu_init(int device);
+void cgpu_shutdown(void);
+const char *cgpu_last_error(void);
+/* Library/ABI version (major*100+minor) — lets a host binary check what it loaded. */
+int cgpu_version(void);
+
+/* Replicate sharding for one-process-per-GPU runs: this process computes, for
+ * every scale s, the replicate columns [ bb[s]*rank/world , bb[s]*(rank+1)/world ).
+ * Default (0,1) = everything.  Results do not depend on the partition.           */
+int cgpu_set_shard(int rank, int world);
+int cgpu_shard_range(int bb, int *b_begin, int *b_end);
+
+/* --------------------------------------------------------------- makermt side */
+/* Replaces the loop `for(i<kk){repmat=new_lmat; scaleboot(datmat,repmat,mm,nn,
+ * bn[i],bb[i]); fwrite_bmat;}` of genrmt (src/makermt.c:201-211) together with
+ * scaleboot itself (src/makermt.c:35-75) and the process-global MT19937 stream
+ * it consumes (src/mt19937.c:57-60, src/rand.c:25-29).
+ *
+ *   L          K*n doubles, row-major == datmat[0] of new_mat (src/misc.c:115-126)
+ *   bn[s]      replicate sample size (int)(rr[s]*n), computed by the HOST exactly
+ *              as src/makermt.c:165-168 does
+ *   bb[s]      number of replicates of scale s
+ *   seed       already time()-substituted (src/rand.c:33-37)
+ *   stream_offset  uniform draws already consumed from the stream (makermt -g
+ *              continues one stream across files); 0 otherwise
+ *   rep_out[s] K*bb[s] doubles, row-major (tree-major, replicate fastest): the
+ *              exact payload fwrite_bmat (src/misc.c:637-645) writes after its
+ *              two-int header.  With sharding only this rank's columns are written.
+ */
+int cgpu_scaleboot_all(const double *L, int K, int n, int S, const int *bn, const int *bb,
+                       unsigned long seed, unsigned long long stream_offset, int rng_mode,
+                       int sum_mode, double *const *rep_out);
+
+/* The same path in three steps, so a caller can keep data resident on the device
+ * (bench `value`, and makermt|consel fusion a la src/makerep.c:304-376).          */
+typedef struct cgpu_matrix cgpu_matrix; /* site-log-likelihood matrix on the device */
+typedef struct cgpu_reps cgpu_reps;     /* replicate blocks (+ derived statistics)  */
+
+int cgpu_matrix_upload(const double *L, int K, int n, cgpu_matrix **out);
+void cgpu_matrix_free(cgpu_matrix *m);
+int cgpu_scaleboot_dev(const cgpu_matrix *m, int S, const int *bn, const int *bb, unsigned long seed,
+                       unsigned long long stream_offset, int rng_mode, int sum_mode, cgpu_reps **out);
+/* copy this rank's replicate columns into rep_out[s] (K x bb[s], see above) */
+int cgpu_reps_download(const cgpu_reps *r, double *const *rep_out);
+void cgpu_reps_free(cgpu_reps *r);
+
+/* Test/diagnostic seam: site-count matrix of scale s as the resampler produced it,
+ * counts[b*n + j] for this rank's replicates (bit-exact contract of the north star:
+ * equals the histogram of src/makermt.c:53-62 under CGPU_RNG_MT19937).            */
+int cgpu_resample_counts(int n, int S, const int *bn, const int *bb, unsigned long seed,
+                         unsigned long long stream_offset, int rng_mode, int s, unsigned char *counts);
+/* first `count` tempered outputs of the seeded MT19937 stream after `skip` draws,
+ * produced by the device jump-ahead + block regeneration (src/mt19937.c:108-127) */
+int cgpu_mt19937_stream(unsigned long seed, unsigned long long skip, unsigned long long count,
+                        unsigned int *out);
+
+/* ---------------------------------------------------------------- consel side */
+/* Replaces fread_blmat'ed repmats (src/consel.c:808-818): upload K x bb[s] blocks. */
+int cgpu_reps_upload(int K, int S, const int *bb, const double *const *rep, cgpu_reps **out);
+
+/* Replaces genrep -> repminmaxs -> calcmaxs/calcassmins (src/consel.c:751-787,
+ * 1894-1959): statistic blocks stat[s] = cm x bb[s], row e =
+ * min_{i in A_e} ( max_{j != i} rep[j][b] - rep[i][b] ).  Associations in CSR form,
+ * already permuted into the output item order (orderv, src/consel.c:514-530).     */
+int cgpu_stats_build(cgpu_reps *r, int cm, const int *ass_ptr, const int *ass_idx);
+/* stat_out[s] = cm x bb[s] doubles row-major; sorted != 0 sorts every row ascending
+ * like sort_vec (src/consel.c:1466-1471) — the payload of `.rep`.                 */
+int cgpu_stats_download(const cgpu_reps *r, int sorted, double *const *stat_out);
+
+/* Summary of one row of replicates against a threshold t: everything cntdist1/2/3
+ * (src/consel.c:1796-1860) need, without sorting.  For the sorted row v[0..B):
+ *   cnt = #{v <= t};  lo = max{v <= t} (or -1e30);  hi = min{v > t} (or +1e30);
+ *   min1,min2 = v[0],v[1];  max1,max2 = v[B-1],v[B-2].                             */
+typedef struct cgpu_rowsum {
+    double cnt, lo, hi, min1, min2, max1, max2;
+} cgpu_rowsum;
+/* cntdist(v,B,t,3) (src/consel.c:1842-1860) from a row summary: pure host helper. */
+double cgpu_smooth_count(const cgpu_rowsum *q, int B);
+
+/* Replaces cntdist(statmats[s][i],bb[s],x,mode) inside vcalpval/invtpval/do_bptest/
+ * do_bootrep (src/consel.c:2775-2778, 2845-2848, 1503-1507): nq thresholds per item,
+ * thr[i*nq+q]; out[(i*S+s)*nq+q].                                                   */
+int cgpu_count_query(const cgpu_reps *r, int nq, const double *thr, cgpu_rowsum *out);
+/* k-th smallest (0-based rank[i]) of stat[s][i][:] for every item — the median and
+ * the min/max that vcalpval/invtpval start from (src/consel.c:2765, 2837).         */
+int cgpu_order_stat(const cgpu_reps *r, int s, const int *rank, double *val);
+
+/* Replaces do_mctest (src/consel.c:1352-1439): centring, calckhpval (:2111-2149),
+ * calcmcpval/calcmaxass (:2065-2102, 2010-2033), pairwise variances (:1404-1415)
+ * and their weighted versions, on scale i0.  Outputs cm-vectors of p-values.      */
+int cgpu_mctest(const cgpu_reps *r, int i0, const double *datvec, double varadd, int cm,
+                const int *ass_ptr, const int *ass_idx, double *kh, double *sh, double *wkh,
+                double *wsh);
+
+/* -------------------------------------------------------------- introspection */
+/* Device time (ms, CUDA events on the library's stream) of the last cgpu_scaleboot_*
+ * call: [0] upload, [1] rng/jump, [2] resample, [3] contraction, [4] download,
+ * [5] whole call (first to last event, includes launch gaps).                     */
+int cgpu_last_timing(double *ms6);
+/* number of kernels launched by this library since cgpu_init (bench `gpu_launches`) */
+long long cgpu_launch_count(void);
+/* raw device pointer + shape of a replicate block, so a host framework can wrap it
+ * (e.g. for an NCCL all-gather) without a copy: K x ld doubles, this rank's columns
+ * [b_begin,b_end) at column offset 0.                                              */
+int cgpu_reps_devptr(const cgpu_reps *r, int s, void **ptr, int *rows, int *cols, int *ld);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CONSEL_GPU_H */
