@@ -203,9 +203,12 @@ class Reps:
 
     def count_query(self, thr: np.ndarray) -> np.ndarray:
         """thr: (cm, nq) thresholds -> structured array (cm, S, nq) of row summaries."""
-        thr = np.ascontiguousarray(thr, dtype=np.float64).reshape(self.cm, -1)
+        thr = np.ascontiguousarray(thr, dtype=np.float64)
+        thr = thr.reshape(thr.shape[0], -1)
         nq = thr.shape[1]
-        out = np.zeros((self.cm, self.S, nq), dtype=ROWSUM_DTYPE)
+        if self.cm and thr.shape[0] != self.cm:
+            raise CgpuError(-1, f"count_query: {thr.shape[0]} threshold rows for {self.cm} items")
+        out = np.zeros((thr.shape[0], self.S, nq), dtype=ROWSUM_DTYPE)
         _check(load().cgpu_count_query(self._h, nq, _dp(thr), out.ctypes.data_as(C.POINTER(RowSum))))
         return out
 
@@ -243,9 +246,9 @@ class Reps:
             pass
 
 
-def smooth_count(rowsum, B: int) -> float:
+def smooth_count(rowsum, B: int, t: float) -> float:
     q = RowSum(*[float(rowsum[k]) for k in ("cnt", "lo", "hi", "min1", "min2", "max1", "max2")])
-    return float(load().cgpu_smooth_count(C.byref(q), int(B)))
+    return float(load().cgpu_smooth_count(C.byref(q), int(B), C.c_double(t)))
 
 
 def resample_counts(n: int, bn, bb, seed: int, s: int, rng_mode: int = RNG_MT19937, stream_offset: int = 0):

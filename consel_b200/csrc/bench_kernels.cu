@@ -26,7 +26,7 @@ extern "C" int cgpu_bench_fp64_peak(double *tflops) {
     CGPU_TRY(ensure_init());
     cudaStream_t st = G().stream;
     double *d = nullptr;
-    CGPU_CUDA(cudaMalloc(&d, 8));
+    CGPU_CUDA(dev_alloc(&d, 8));
     const int iters = 4096, blocks = G().sm_count * 8;
     cudaEvent_t a, b;
     cudaEventCreate(&a);
@@ -44,7 +44,7 @@ extern "C" int cgpu_bench_fp64_peak(double *tflops) {
     CGPU_LAUNCH_CHECK();
     cudaEventDestroy(a);
     cudaEventDestroy(b);
-    cudaFree(d);
+    dev_free(d);
     double flops = 2.0 * 16 * (double)iters * 256.0 * blocks;
     *tflops = flops / (best * 1e-3) / 1e12;
     return CGPU_OK;

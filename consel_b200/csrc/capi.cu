@@ -80,12 +80,12 @@ static void shard_range(int bb, int *b0, int *b1) {
 static void free_reps(DevReps *r) {
     if (!r) return;
     if (r->d_rep)
-        for (int s = 0; s < r->S; s++) cudaFree(r->d_rep[s]);
+        for (int s = 0; s < r->S; s++) dev_free(r->d_rep[s]);
     if (r->d_stat)
-        for (int s = 0; s < r->S; s++) cudaFree(r->d_stat[s]);
-    cudaFree(r->d_edges);
-    cudaFree(r->d_ass_ptr);
-    cudaFree(r->d_ass_idx);
+        for (int s = 0; s < r->S; s++) dev_free(r->d_stat[s]);
+    dev_free(r->d_edges);
+    dev_free(r->d_ass_ptr);
+    dev_free(r->d_ass_idx);
     free(r->d_rep);
     free(r->d_stat);
     free(r->bb);
@@ -109,9 +109,9 @@ static int alloc_reps(int K, int S, const int *bb, DevReps **out) {
         r->b0[s] = b0;
         r->nb[s] = b1 - b0;
         size_t bytes = (size_t)K * std::max(1, b1 - b0) * sizeof(double);
-        cudaError_t e = cudaMalloc(&r->d_rep[s], bytes);
+        cudaError_t e = dev_alloc(&r->d_rep[s], bytes);
         if (e != cudaSuccess) {
-            set_error(CGPU_ENOMEM, "cudaMalloc(%zu) for replicate block %d: %s", bytes, s, cudaGetErrorString(e));
+            set_error(CGPU_ENOMEM, "device allocation (%zu bytes) for replicate block %d: %s", bytes, s, cudaGetErrorString(e));
             free_reps(r);
             return CGPU_ENOMEM;
         }
@@ -149,7 +149,7 @@ static int mt_prepare(unsigned long seed, unsigned long long stream_offset, unsi
         set_error(CGPU_EINVAL, "stream of %llu draws exceeds the jump table", total_draws);
         return CGPU_EINVAL;
     }
-    CGPU_CUDA(cudaMalloc(&plan->d_states, (size_t)P * MT_N * sizeof(uint32_t)));
+    CGPU_CUDA(dev_alloc(&plan->d_states, (size_t)P * MT_N * sizeof(uint32_t)));
     uint32_t w0[MT_N];
     mt_seed_window((uint32_t)(seed & 0xffffffffUL), w0);
     if (stream_offset) {
@@ -175,9 +175,9 @@ struct Workspace {
     unsigned long long *d_counts = nullptr;
     int *d_err = nullptr;
     ~Workspace() {
-        cudaFree(d_idx);
-        cudaFree(d_counts);
-        cudaFree(d_err);
+        dev_free(d_idx);
+        dev_free(d_counts);
+        dev_free(d_err);
     }
 };
 
@@ -209,8 +209,8 @@ static int scaleboot_core(const DevMatrix &m, int S, const int *bn, const int *b
     const int batch = (int)std::min<long long>(cap, std::max(64, (max_nb + 63) / 64 * 64));
 
     Workspace ws;
-    CGPU_CUDA(cudaMalloc(&ws.d_counts, (size_t)(batch / 8) * NP * 8));
-    CGPU_CUDA(cudaMalloc(&ws.d_err, sizeof(int)));
+    CGPU_CUDA(dev_alloc(&ws.d_counts, (size_t)(batch / 8) * NP * 8));
+    CGPU_CUDA(dev_alloc(&ws.d_err, sizeof(int)));
     CGPU_CUDA(cudaMemsetAsync(ws.d_err, 0, sizeof(int), st));
     // padding sites and replicates must read as zero counts
     CGPU_CUDA(cudaMemsetAsync(ws.d_counts, 0, (size_t)(batch / 8) * NP * 8, st));
@@ -218,12 +218,12 @@ static int scaleboot_core(const DevMatrix &m, int S, const int *bn, const int *b
     MtPlan plan;
     struct PlanGuard {
         MtPlan &p;
-        ~PlanGuard() { cudaFree(p.d_states); }
+        ~PlanGuard() { dev_free(p.d_states); }
     } guard{plan};
     std::vector<unsigned long long> base(S + 1, 0);
     for (int s = 0; s < S; s++) base[s + 1] = base[s] + (unsigned long long)bb[s] * (unsigned long long)bn[s];
     if (rng_mode == CGPU_RNG_MT19937) {
-        CGPU_CUDA(cudaMalloc(&ws.d_idx, (size_t)batch * max_bn * sizeof(uint32_t)));
+        CGPU_CUDA(dev_alloc(&ws.d_idx, (size_t)batch * max_bn * sizeof(uint32_t)));
         pt.begin(1);
         CGPU_TRY(mt_prepare(seed, stream_offset, base[S], &plan, st));
         pt.end();
@@ -287,19 +287,19 @@ static int matrix_upload(const double *L, int K, int n, DevMatrix **out, cudaStr
         rc = e == cudaErrorMemoryAllocation ? CGPU_ENOMEM : CGPU_ECUDA;
     };
     cudaError_t e;
-    if ((e = cudaMalloc(&m->d_L, (size_t)K * n * sizeof(double))) != cudaSuccess) fail(e, "alloc L");
-    if (!rc && (e = cudaMalloc(&m->d_LT, (size_t)m->ktiles * m->NP * m->KT * sizeof(double))) != cudaSuccess) fail(e, "alloc LT");
-    if (!rc && (e = cudaMalloc(&d_flag, sizeof(int))) != cudaSuccess) fail(e, "alloc flag");
+    if ((e = dev_alloc(&m->d_L, (size_t)K * n * sizeof(double))) != cudaSuccess) fail(e, "alloc L");
+    if (!rc && (e = dev_alloc(&m->d_LT, (size_t)m->ktiles * m->NP * m->KT * sizeof(double))) != cudaSuccess) fail(e, "alloc LT");
+    if (!rc && (e = dev_alloc(&d_flag, sizeof(int))) != cudaSuccess) fail(e, "alloc flag");
     if (!rc && (e = cudaMemsetAsync(d_flag, 0, sizeof(int), st)) != cudaSuccess) fail(e, "memset");
     if (!rc && (e = cudaMemcpyAsync(m->d_L, L, (size_t)K * n * sizeof(double), cudaMemcpyHostToDevice, st)) != cudaSuccess) fail(e, "H2D");
     if (!rc) rc = launch_transpose_L(m->d_L, K, n, m->NP, m->TK, m->d_LT, d_flag, st);
     int h_flag = 0;
     if (!rc && (e = cudaMemcpyAsync(&h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st)) != cudaSuccess) fail(e, "D2H flag");
     if (!rc && (e = cudaStreamSynchronize(st)) != cudaSuccess) fail(e, "sync");
-    cudaFree(d_flag);
+    dev_free(d_flag);
     if (rc) {
-        cudaFree(m->d_L);
-        cudaFree(m->d_LT);
+        dev_free(m->d_L);
+        dev_free(m->d_LT);
         delete m;
         return rc;
     }
@@ -358,8 +358,16 @@ int cgpu_init(int device) {
     g.device = device;
     g.sm_count = prop.multiProcessorCount;
     CGPU_CUDA(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+    {
+        // keep freed blocks in the default stream-ordered pool: the per-call workspaces
+        // (index/count buffers, replicate blocks) are then recycled without a cudaMalloc
+        cudaMemPool_t pool;
+        CGPU_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+        unsigned long long thresh = ~0ull;
+        CGPU_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
+    }
     const Gf2Poly *T = mt_jump_table();
-    CGPU_CUDA(cudaMalloc(&g.d_jump_table, (size_t)(MT_MAXLOG + 1) * MT_N * sizeof(uint32_t)));
+    CGPU_CUDA(dev_alloc(&g.d_jump_table, (size_t)(MT_MAXLOG + 1) * MT_N * sizeof(uint32_t)));
     CGPU_CUDA(cudaMemcpy(g.d_jump_table, T, (size_t)(MT_MAXLOG + 1) * MT_N * sizeof(uint32_t), cudaMemcpyHostToDevice));
     g.inited = true;
     return CGPU_OK;
@@ -369,7 +377,7 @@ void cgpu_shutdown(void) {
     Globals &g = G();
     if (!g.inited) return;
     cudaStreamSynchronize(g.stream);
-    cudaFree(g.d_jump_table);
+    dev_free(g.d_jump_table);
     cudaStreamDestroy(g.stream);
     g.d_jump_table = nullptr;
     g.stream = nullptr;
@@ -412,8 +420,8 @@ int cgpu_matrix_upload(const double *L, int K, int n, cgpu_matrix **out) {
 void cgpu_matrix_free(cgpu_matrix *mm) {
     DevMatrix *m = reinterpret_cast<DevMatrix *>(mm);
     if (!m) return;
-    cudaFree(m->d_L);
-    cudaFree(m->d_LT);
+    dev_free(m->d_L);
+    dev_free(m->d_LT);
     delete m;
 }
 
@@ -501,14 +509,14 @@ int cgpu_resample_counts(int n, int S, const int *bn, const int *bb, unsigned lo
     const int NP = pad_sites(n);
     Workspace ws;
     const size_t cbytes = (size_t)((nb + 7) / 8) * NP * 8;
-    CGPU_CUDA(cudaMalloc(&ws.d_counts, cbytes));
+    CGPU_CUDA(dev_alloc(&ws.d_counts, cbytes));
     CGPU_CUDA(cudaMemsetAsync(ws.d_counts, 0, cbytes, st));
-    CGPU_CUDA(cudaMalloc(&ws.d_err, sizeof(int)));
+    CGPU_CUDA(dev_alloc(&ws.d_err, sizeof(int)));
     CGPU_CUDA(cudaMemsetAsync(ws.d_err, 0, sizeof(int), st));
     MtPlan plan;
     struct PlanGuard {
         MtPlan &p;
-        ~PlanGuard() { cudaFree(p.d_states); }
+        ~PlanGuard() { dev_free(p.d_states); }
     } guard{plan};
     if (rng_mode == CGPU_RNG_MT19937) {
         unsigned long long base = 0, total = 0;
@@ -516,7 +524,7 @@ int cgpu_resample_counts(int n, int S, const int *bn, const int *bb, unsigned lo
             if (t < s) base += (unsigned long long)bb[t] * bn[t];
             total += (unsigned long long)bb[t] * bn[t];
         }
-        CGPU_CUDA(cudaMalloc(&ws.d_idx, (size_t)nb * bn[s] * sizeof(uint32_t)));
+        CGPU_CUDA(dev_alloc(&ws.d_idx, (size_t)nb * bn[s] * sizeof(uint32_t)));
         CGPU_TRY(mt_prepare(seed, stream_offset, total, &plan, st));
         const unsigned long long lo = base + (unsigned long long)b0 * bn[s], hi = lo + (unsigned long long)nb * bn[s];
         const unsigned long long c0 = lo >> plan.chunk_log2, c1 = (hi - 1) >> plan.chunk_log2;
@@ -529,7 +537,7 @@ int cgpu_resample_counts(int n, int S, const int *bn, const int *bb, unsigned lo
         return CGPU_EINVAL;
     }
     unsigned char *d_out = nullptr;
-    CGPU_CUDA(cudaMalloc(&d_out, (size_t)nb * n));
+    CGPU_CUDA(dev_alloc(&d_out, (size_t)nb * n));
     int rc = launch_counts_unpack(ws.d_counts, n, NP, nb, d_out, st);
     int h_err = 0;
     if (rc == CGPU_OK) {
@@ -541,7 +549,7 @@ int cgpu_resample_counts(int n, int S, const int *bn, const int *bb, unsigned lo
             rc = CGPU_ECUDA;
         }
     }
-    cudaFree(d_out);
+    dev_free(d_out);
     if (rc == CGPU_OK && h_err) {
         set_error(CGPU_ERANGE, "a site was drawn more than 255 times in one replicate");
         rc = CGPU_ERANGE;
@@ -557,11 +565,11 @@ int cgpu_mt19937_stream(unsigned long seed, unsigned long long skip, unsigned lo
     MtPlan plan;
     struct PlanGuard {
         MtPlan &p;
-        ~PlanGuard() { cudaFree(p.d_states); }
+        ~PlanGuard() { dev_free(p.d_states); }
     } guard{plan};
     CGPU_TRY(mt_prepare(seed, 0, skip + count, &plan, st));
     uint32_t *d_idx = nullptr;
-    CGPU_CUDA(cudaMalloc(&d_idx, (size_t)count * sizeof(uint32_t)));
+    CGPU_CUDA(dev_alloc(&d_idx, (size_t)count * sizeof(uint32_t)));
     const unsigned long long lo = skip, hi = skip + count;
     const unsigned long long c0 = lo >> plan.chunk_log2, c1 = (hi - 1) >> plan.chunk_log2;
     // n = 2^32 is not representable: ask for the raw tempered word via the identity n -> y
@@ -574,7 +582,7 @@ int cgpu_mt19937_stream(unsigned long seed, unsigned long long skip, unsigned lo
             rc = CGPU_ECUDA;
         }
     }
-    cudaFree(d_idx);
+    dev_free(d_idx);
     return rc;
 }
 

@@ -1,0 +1,484 @@
+// consel-side entry points of the C ABI (include/consel_gpu.h): replicate statistics,
+// sort-free count queries, order statistics and the KH/SH/wKH/wSH tests.
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "cgpu_internal.h"
+
+namespace cgpu {
+
+#define CG_HUGE 1.0e30
+
+// small RAII holder so early returns release device buffers
+struct DevBuf {
+    void *p = nullptr;
+    ~DevBuf() { dev_free(p); }
+    template <typename T>
+    T *as() { return reinterpret_cast<T *>(p); }
+    int alloc(size_t bytes) {
+        cudaError_t e = dev_alloc(&p, bytes);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            set_error(CGPU_ENOMEM, "device allocation of %zu bytes: %s", bytes, cudaGetErrorString(e));
+            return CGPU_ENOMEM;
+        }
+        return CGPU_OK;
+    }
+    template <typename T>
+    int upload(const T *h, size_t count, cudaStream_t st) {
+        CGPU_TRY(alloc(count * sizeof(T)));
+        if (count) CGPU_CUDA(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, st));
+        return CGPU_OK;
+    }
+};
+
+static int check_csr(int K, int cm, const int *ptr, const int *idx) {
+    if (cm <= 0 || !ptr || !idx || ptr[0] != 0) {
+        set_error(CGPU_EINVAL, "association: cm=%d", cm);
+        return CGPU_EINVAL;
+    }
+    for (int e = 0; e < cm; e++) {
+        if (ptr[e + 1] < ptr[e]) {
+            set_error(CGPU_EINVAL, "association %d has negative length", e);
+            return CGPU_EINVAL;
+        }
+        for (int q = ptr[e]; q < ptr[e + 1]; q++)
+            if (idx[q] < 0 || idx[q] >= K) {
+                set_error(CGPU_EINVAL, "ass out of range: ass[%d][%d]=%d", e + 1, q - ptr[e] + 1, idx[q] + 1);
+                return CGPU_EINVAL;
+            }
+    }
+    return CGPU_OK;
+}
+
+// cntdist3 (src/consel.c:1842-1860) from a row summary
+static double smooth_count(const cgpu_rowsum &q, int B, double t) {
+    const double n = (double)B;
+    const long long cnt = (long long)q.cnt;
+    double p;
+    if (B < 2) return cnt > 0 ? n : 0.0;
+    if (cnt <= 0) {
+        if (q.min2 > q.min1) p = 0.5 + (t - q.min1) / (q.min2 - q.min1);
+        else p = 0.0;
+    } else if (cnt < B) {
+        const double i = (double)(cnt - 1);
+        if (q.hi > q.lo) p = 0.5 + i + (t - q.lo) / (q.hi - q.lo);
+        else p = 0.5 + i;
+    } else {
+        if (q.max1 - q.max2 > 0) p = n - 0.5 + (t - q.max1) / (q.max1 - q.max2);
+        else p = n;
+    }
+    if (p > n) p = n;
+    else if (p < 0.0) p = 0.0;
+    return p;
+}
+
+}  // namespace cgpu
+
+using namespace cgpu;
+
+extern "C" {
+
+double cgpu_smooth_count(const cgpu_rowsum *q, int B, double t) { return smooth_count(*q, B, t); }
+
+int cgpu_reps_upload(int K, int S, const int *bb, const double *const *rep, cgpu_reps **out) {
+    CGPU_TRY(ensure_init());
+    if (K <= 0 || S <= 0 || !bb || !rep || !out) {
+        set_error(CGPU_EINVAL, "reps_upload: bad arguments");
+        return CGPU_EINVAL;
+    }
+    cudaStream_t st = G().stream;
+    DevReps *r = new DevReps();
+    r->K = K;
+    r->S = S;
+    r->bb = (int *)calloc(S, sizeof(int));
+    r->b0 = (int *)calloc(S, sizeof(int));
+    r->nb = (int *)calloc(S, sizeof(int));
+    r->d_rep = (double **)calloc(S, sizeof(double *));
+    int rc = CGPU_OK;
+    for (int s = 0; s < S && rc == CGPU_OK; s++) {
+        int b0 = (int)((long long)bb[s] * G().shard_rank / G().shard_world);
+        int b1 = (int)((long long)bb[s] * (G().shard_rank + 1) / G().shard_world);
+        r->bb[s] = bb[s];
+        r->b0[s] = b0;
+        r->nb[s] = b1 - b0;
+        cudaError_t e = dev_alloc(&r->d_rep[s], (size_t)K * std::max(1, b1 - b0) * sizeof(double));
+        if (e == cudaSuccess && b1 > b0)
+            e = cudaMemcpy2DAsync(r->d_rep[s], (size_t)(b1 - b0) * sizeof(double), rep[s] + b0,
+                                  (size_t)bb[s] * sizeof(double), (size_t)(b1 - b0) * sizeof(double), K,
+                                  cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) {
+            set_error(CGPU_ECUDA, "reps_upload scale %d: %s", s, cudaGetErrorString(e));
+            rc = CGPU_ECUDA;
+        }
+    }
+    if (rc == CGPU_OK && cudaStreamSynchronize(st) != cudaSuccess) {
+        set_error(CGPU_ECUDA, "reps_upload: sync failed");
+        rc = CGPU_ECUDA;
+    }
+    if (rc != CGPU_OK) {
+        cgpu_reps_free(reinterpret_cast<cgpu_reps *>(r));
+        return rc;
+    }
+    *out = reinterpret_cast<cgpu_reps *>(r);
+    return CGPU_OK;
+}
+
+int cgpu_stats_build(cgpu_reps *rr, int cm, const int *ass_ptr, const int *ass_idx) {
+    CGPU_TRY(ensure_init());
+    DevReps *r = reinterpret_cast<DevReps *>(rr);
+    if (!r) return CGPU_EINVAL;
+    CGPU_TRY(check_csr(r->K, cm, ass_ptr, ass_idx));
+    cudaStream_t st = G().stream;
+    if (r->d_stat) {
+        for (int s = 0; s < r->S; s++) dev_free(r->d_stat[s]);
+        free(r->d_stat);
+        r->d_stat = nullptr;
+    }
+    dev_free(r->d_ass_ptr);
+    dev_free(r->d_ass_idx);
+    r->d_ass_ptr = r->d_ass_idx = nullptr;
+    r->cm = cm;
+    CGPU_CUDA(dev_alloc(&r->d_ass_ptr, (size_t)(cm + 1) * sizeof(int)));
+    CGPU_CUDA(dev_alloc(&r->d_ass_idx, (size_t)std::max(1, ass_ptr[cm]) * sizeof(int)));
+    CGPU_CUDA(cudaMemcpyAsync(r->d_ass_ptr, ass_ptr, (size_t)(cm + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
+    CGPU_CUDA(cudaMemcpyAsync(r->d_ass_idx, ass_idx, (size_t)ass_ptr[cm] * sizeof(int), cudaMemcpyHostToDevice, st));
+    r->d_stat = (double **)calloc(r->S, sizeof(double *));
+    for (int s = 0; s < r->S; s++) {
+        const int B = r->nb[s];
+        CGPU_CUDA(dev_alloc(&r->d_stat[s], (size_t)cm * std::max(1, B) * sizeof(double)));
+        if (B <= 0) continue;
+        DevBuf m1, m2, a1;
+        CGPU_TRY(m1.alloc((size_t)B * 8));
+        CGPU_TRY(m2.alloc((size_t)B * 8));
+        CGPU_TRY(a1.alloc((size_t)B * 4));
+        CGPU_TRY(launch_col_top2(r->d_rep[s], r->K, B, B, m1.as<double>(), m2.as<double>(), a1.as<int>(), st));
+        CGPU_TRY(launch_stat_build(r->d_rep[s], r->K, B, B, m1.as<double>(), m2.as<double>(), a1.as<int>(), cm,
+                                   r->d_ass_ptr, r->d_ass_idx, r->d_stat[s], st));
+    }
+    CGPU_CUDA(cudaStreamSynchronize(st));
+    return CGPU_OK;
+}
+
+int cgpu_stats_download(const cgpu_reps *rr, int sorted, double *const *stat_out) {
+    CGPU_TRY(ensure_init());
+    const DevReps *r = reinterpret_cast<const DevReps *>(rr);
+    if (!r || !r->d_stat || !stat_out) {
+        set_error(CGPU_EINVAL, "stats_download: statistics not built");
+        return CGPU_EINVAL;
+    }
+    cudaStream_t st = G().stream;
+    for (int s = 0; s < r->S; s++) {
+        if (r->nb[s] <= 0) continue;
+        CGPU_CUDA(cudaMemcpy2DAsync(stat_out[s] + r->b0[s], (size_t)r->bb[s] * sizeof(double), r->d_stat[s],
+                                    (size_t)r->nb[s] * sizeof(double), (size_t)r->nb[s] * sizeof(double), r->cm,
+                                    cudaMemcpyDeviceToHost, st));
+    }
+    CGPU_CUDA(cudaStreamSynchronize(st));
+    if (sorted) {
+        // `.rep` payload only (consel -r): rows are sorted on the host after the copy; the
+        // AU/BP path itself never sorts (count queries below).
+        for (int s = 0; s < r->S; s++) {
+            if (r->nb[s] != r->bb[s]) {
+                set_error(CGPU_EINVAL, "stats_download(sorted) needs unsharded rows");
+                return CGPU_EINVAL;
+            }
+            for (int i = 0; i < r->cm; i++) std::sort(stat_out[s] + (size_t)i * r->bb[s], stat_out[s] + (size_t)(i + 1) * r->bb[s]);
+        }
+    }
+    return CGPU_OK;
+}
+
+int cgpu_count_query(const cgpu_reps *rr, int nq, const double *thr, cgpu_rowsum *out) {
+    CGPU_TRY(ensure_init());
+    const DevReps *r = reinterpret_cast<const DevReps *>(rr);
+    if (!r || !r->d_stat || !thr || !out || nq < 1) {
+        set_error(CGPU_EINVAL, "count_query: statistics not built or bad arguments");
+        return CGPU_EINVAL;
+    }
+    cudaStream_t st = G().stream;
+    const int cm = r->cm, S = r->S;
+    DevBuf d_thr, d_out;
+    CGPU_TRY(d_thr.upload(thr, (size_t)cm * nq, st));
+    const size_t nout = (size_t)cm * S * nq;
+    CGPU_TRY(d_out.alloc(nout * sizeof(cgpu_rowsum)));
+    for (int s = 0; s < S; s++) {
+        RowSrc src{r->d_stat[s], r->nb[s], nullptr, nullptr, nullptr, nullptr, nullptr};
+        CGPU_TRY(launch_rowsum(0, src, cm, r->nb[s], nq, d_thr.as<double>(), d_out.as<cgpu_rowsum>(), S, s, st));
+    }
+    CGPU_CUDA(cudaMemcpyAsync(out, d_out.p, nout * sizeof(cgpu_rowsum), cudaMemcpyDeviceToHost, st));
+    CGPU_CUDA(cudaStreamSynchronize(st));
+    return CGPU_OK;
+}
+
+int cgpu_order_stat(const cgpu_reps *rr, int s, const int *rank, double *val) {
+    CGPU_TRY(ensure_init());
+    const DevReps *r = reinterpret_cast<const DevReps *>(rr);
+    if (!r || !r->d_stat || s < 0 || s >= r->S || !rank || !val) {
+        set_error(CGPU_EINVAL, "order_stat: statistics not built or bad arguments");
+        return CGPU_EINVAL;
+    }
+    if (r->nb[s] != r->bb[s]) {
+        set_error(CGPU_EINVAL, "order_stat needs the whole row on one device (gather scale %d first)", s);
+        return CGPU_EINVAL;
+    }
+    for (int i = 0; i < r->cm; i++)
+        if (rank[i] < 0 || rank[i] >= r->bb[s]) {
+            set_error(CGPU_EINVAL, "order_stat: rank[%d]=%d of %d", i, rank[i], r->bb[s]);
+            return CGPU_EINVAL;
+        }
+    cudaStream_t st = G().stream;
+    DevBuf d_rank, d_val;
+    CGPU_TRY(d_rank.upload(rank, (size_t)r->cm, st));
+    CGPU_TRY(d_val.alloc((size_t)r->cm * 8));
+    CGPU_TRY(launch_order_stat(r->d_stat[s], r->cm, r->nb[s], r->nb[s], d_rank.as<int>(), d_val.as<double>(), st));
+    CGPU_CUDA(cudaMemcpyAsync(val, d_val.p, (size_t)r->cm * 8, cudaMemcpyDeviceToHost, st));
+    CGPU_CUDA(cudaStreamSynchronize(st));
+    return CGPU_OK;
+}
+
+int cgpu_mctest(const cgpu_reps *rr, int i0, const double *datvec, double varadd, int cm, const int *ass_ptr,
+                const int *ass_idx, double *kh, double *sh, double *wkh, double *wsh) {
+    CGPU_TRY(ensure_init());
+    const DevReps *r = reinterpret_cast<const DevReps *>(rr);
+    if (!r || i0 < 0 || i0 >= r->S || !datvec || !kh || !sh || !wkh || !wsh) {
+        set_error(CGPU_EINVAL, "mctest: bad arguments");
+        return CGPU_EINVAL;
+    }
+    const int K = r->K, B = r->nb[i0];
+    CGPU_TRY(check_csr(K, cm, ass_ptr, ass_idx));
+    if (B != r->bb[i0]) {
+        set_error(CGPU_EINVAL, "mctest needs every replicate of scale %d on this device (row means are sequential sums)", i0);
+        return CGPU_EINVAL;
+    }
+    if (B < 2 || K < 2) {
+        set_error(CGPU_EINVAL, "mctest: K=%d B=%d", K, B);
+        return CGPU_EINVAL;
+    }
+    cudaStream_t st = G().stream;
+    const int nmem = ass_ptr[cm];
+
+    // ---- host bookkeeping: complements (getcass, src/consel.c:2040-2063) and members
+    std::vector<int> cass_ptr(cm + 1, 0), cass_idx, mem_item(nmem), mem_tree(nmem);
+    {
+        std::vector<char> mark(K);
+        for (int e = 0; e < cm; e++) {
+            std::fill(mark.begin(), mark.end(), 0);
+            for (int q = ass_ptr[e]; q < ass_ptr[e + 1]; q++) {
+                if (mark[ass_idx[q]]) {
+                    set_error(CGPU_EINVAL, "duplicate associations");
+                    return CGPU_EINVAL;
+                }
+                mark[ass_idx[q]] = 1;
+                mem_item[q] = e;
+                mem_tree[q] = ass_idx[q];
+            }
+            // identity-sized problems would make this O(K^2) ints; singleton items share
+            // the "all but i" complement implicitly (handled by the top-2 path below)
+            if (ass_ptr[e + 1] - ass_ptr[e] != 1)
+                for (int j = 0; j < K; j++)
+                    if (!mark[j]) cass_idx.push_back(j);
+            cass_ptr[e + 1] = (int)cass_idx.size();
+        }
+    }
+    bool all_single = true;
+    for (int e = 0; e < cm; e++) all_single = all_single && (ass_ptr[e + 1] - ass_ptr[e] == 1);
+
+    // first-argmax top-2 of datvec (for "max over all j != i" on the host)
+    int da = 0, db = -1;
+    for (int j = 1; j < K; j++)
+        if (datvec[j] > datvec[da]) da = j;
+    for (int j = 0; j < K; j++)
+        if (j != da && (db < 0 || datvec[j] > datvec[db])) db = j;
+
+    // ---- device: centred copy of scale i0
+    DevBuf xc;
+    CGPU_TRY(xc.alloc((size_t)K * B * 8));
+    CGPU_TRY(launch_center(r->d_rep[i0], K, B, B, xc.as<double>(), st));
+
+    // ---- unweighted KH contrasts (src/consel.c:2135-2143) and SH observed statistics
+    std::vector<int> kia(cm), kja(cm);
+    std::vector<double> kx0(cm), shobs(nmem);
+    for (int e = 0; e < cm; e++) {
+        const int a0 = ass_ptr[e], alen = ass_ptr[e + 1] - a0;
+        int ja;
+        if (alen == 1) {
+            ja = (ass_idx[a0] == da) ? db : da;
+        } else {
+            double x = -CG_HUGE;
+            ja = cass_idx[cass_ptr[e]];
+            for (int p = cass_ptr[e]; p < cass_ptr[e + 1]; p++)
+                if (datvec[cass_idx[p]] > x) { x = datvec[cass_idx[p]]; ja = cass_idx[p]; }
+        }
+        double x = CG_HUGE;
+        int ia = ass_idx[a0];
+        for (int q = a0; q < a0 + alen; q++) {
+            double y = -datvec[ass_idx[q]];
+            if (y < x) { x = y; ia = ass_idx[q]; }
+        }
+        kia[e] = ia;
+        kja[e] = ja;
+        kx0[e] = datvec[ja] - datvec[ia];
+        // calcmaxass(datvec, NULL, ...) (src/consel.c:2026-2030): max over the complement with the -1e30 floor
+        double mx = -CG_HUGE;
+        if (datvec[ja] > mx) mx = datvec[ja];
+        for (int q = a0; q < a0 + alen; q++) shobs[q] = mx - datvec[ass_idx[q]];
+    }
+
+    DevBuf d_ia, d_ja, d_thr, d_rs;
+    CGPU_TRY(d_ia.upload(kia.data(), (size_t)cm, st));
+    CGPU_TRY(d_ja.upload(kja.data(), (size_t)cm, st));
+    CGPU_TRY(d_thr.upload(kx0.data(), (size_t)cm, st));
+    CGPU_TRY(d_rs.alloc((size_t)std::max(cm, nmem) * sizeof(cgpu_rowsum)));
+    std::vector<cgpu_rowsum> rs((size_t)std::max(cm, nmem));
+    auto fetch = [&](int rows) -> int {
+        CGPU_CUDA(cudaMemcpyAsync(rs.data(), d_rs.p, (size_t)rows * sizeof(cgpu_rowsum), cudaMemcpyDeviceToHost, st));
+        CGPU_CUDA(cudaStreamSynchronize(st));
+        return CGPU_OK;
+    };
+    auto pval = [&](const cgpu_rowsum &q, double t) { return 1.0 - smooth_count(q, B, t) / B; };  // pvaldist :1876-1884
+
+    {  // KH
+        RowSrc src{xc.as<double>(), B, d_ia.as<int>(), d_ja.as<int>(), nullptr, nullptr, nullptr};
+        CGPU_TRY(launch_rowsum(1, src, cm, B, 1, d_thr.as<double>(), d_rs.as<cgpu_rowsum>(), 1, 0, st));
+        CGPU_TRY(fetch(cm));
+        for (int e = 0; e < cm; e++) kh[e] = pval(rs[e], kx0[e]);
+    }
+
+    // members / complements on the device
+    DevBuf d_mem_item, d_mem_tree, d_cass_ptr, d_cass_idx, d_tmp;
+    CGPU_TRY(d_mem_item.upload(mem_item.data(), (size_t)nmem, st));
+    CGPU_TRY(d_mem_tree.upload(mem_tree.data(), (size_t)nmem, st));
+    auto reduce_items = [&](const std::vector<double> &thr, double *outp) {
+        for (int e = 0; e < cm; e++) {
+            double x = 0.0;
+            for (int q = ass_ptr[e]; q < ass_ptr[e + 1]; q++) {
+                double p = pval(rs[q], thr[q]);
+                if (p > x) x = p;
+            }
+            outp[e] = x;
+        }
+    };
+
+    // every member as its own "row": rows of nmem x B in chunks that fit the workspace
+    const int chunk_rows = (int)std::max<size_t>(1, std::min<size_t>((size_t)nmem, ((size_t)2 << 30) / ((size_t)B * 8)));
+
+    {  // SH (unweighted)
+        DevBuf d_t;
+        CGPU_TRY(d_t.upload(shobs.data(), (size_t)nmem, st));
+        if (all_single) {
+            DevBuf m1, m2, a1;
+            CGPU_TRY(m1.alloc((size_t)B * 8));
+            CGPU_TRY(m2.alloc((size_t)B * 8));
+            CGPU_TRY(a1.alloc((size_t)B * 4));
+            CGPU_TRY(launch_col_top2(xc.as<double>(), K, B, B, m1.as<double>(), m2.as<double>(), a1.as<int>(), st));
+            RowSrc src{xc.as<double>(), B, d_mem_tree.as<int>(), nullptr, m1.as<double>(), m2.as<double>(), a1.as<int>()};
+            CGPU_TRY(launch_rowsum(2, src, nmem, B, 1, d_t.as<double>(), d_rs.as<cgpu_rowsum>(), 1, 0, st));
+            CGPU_TRY(fetch(nmem));
+        } else {
+            // singleton items inside a mixed set still need an explicit complement
+            std::vector<int> cp(cm + 1, 0), ci;
+            std::vector<char> mark(K);
+            for (int e = 0; e < cm; e++) {
+                std::fill(mark.begin(), mark.end(), 0);
+                for (int q = ass_ptr[e]; q < ass_ptr[e + 1]; q++) mark[ass_idx[q]] = 1;
+                for (int j = 0; j < K; j++)
+                    if (!mark[j]) ci.push_back(j);
+                cp[e + 1] = (int)ci.size();
+            }
+            cass_ptr = cp;
+            cass_idx = ci;
+            CGPU_TRY(d_cass_ptr.upload(cass_ptr.data(), (size_t)cm + 1, st));
+            CGPU_TRY(d_cass_idx.upload(cass_idx.data(), cass_idx.size(), st));
+            CGPU_TRY(d_tmp.alloc((size_t)chunk_rows * B * 8));
+            for (int q0 = 0; q0 < nmem; q0 += chunk_rows) {
+                const int rows = std::min(chunk_rows, nmem - q0);
+                CGPU_TRY(launch_sh_rows(false, xc.as<double>(), K, B, B, nullptr, rows, d_mem_item.as<int>() + q0,
+                                        d_mem_tree.as<int>() + q0, d_cass_ptr.as<int>(), d_cass_idx.as<int>(),
+                                        d_tmp.as<double>(), st));
+                RowSrc src{d_tmp.as<double>(), B, nullptr, nullptr, nullptr, nullptr, nullptr};
+                CGPU_TRY(launch_rowsum(0, src, rows, B, 1, d_t.as<double>() + q0, d_rs.as<cgpu_rowsum>() + q0, 1, 0, st));
+            }
+            CGPU_TRY(fetch(nmem));
+        }
+        reduce_items(shobs, sh);
+    }
+
+    // ---- weights (src/consel.c:1404-1415)
+    DevBuf d_wt, d_nsmall, d_dat;
+    CGPU_TRY(d_wt.alloc((size_t)K * K * 8));
+    CGPU_TRY(d_nsmall.alloc(4));
+    CGPU_CUDA(cudaMemsetAsync(d_nsmall.p, 0, 4, st));
+    CGPU_TRY(launch_pair_weight(xc.as<double>(), K, B, B, varadd, d_wt.as<double>(), d_nsmall.as<int>(), st));
+    CGPU_TRY(d_dat.upload(datvec, (size_t)K, st));
+
+    // the weighted kernels walk explicit complements: build the identity ones now if needed
+    if (all_single) {
+        if ((size_t)cm * (size_t)(K - 1) > ((size_t)1 << 31) - 1) {
+            set_error(CGPU_EINVAL, "mctest: %d singleton items x %d trees exceeds the complement index range", cm, K);
+            return CGPU_EINVAL;
+        }
+        cass_idx.clear();
+        cass_idx.reserve((size_t)cm * (K - 1));
+        for (int e = 0; e < cm; e++) {
+            const int i = ass_idx[ass_ptr[e]];
+            for (int j = 0; j < K; j++)
+                if (j != i) cass_idx.push_back(j);
+            cass_ptr[e + 1] = (int)cass_idx.size();
+        }
+        CGPU_TRY(d_cass_ptr.upload(cass_ptr.data(), (size_t)cm + 1, st));
+        CGPU_TRY(d_cass_idx.upload(cass_idx.data(), cass_idx.size(), st));
+        CGPU_TRY(d_tmp.alloc((size_t)chunk_rows * B * 8));
+    }
+
+    // weighted observed statistics and contrasts
+    DevBuf d_wobs, d_argj;
+    CGPU_TRY(d_wobs.alloc((size_t)nmem * 8));
+    CGPU_TRY(d_argj.alloc((size_t)nmem * 4));
+    CGPU_TRY(launch_weighted_obs(d_dat.as<double>(), K, d_wt.as<double>(), nmem, d_mem_item.as<int>(),
+                                 d_mem_tree.as<int>(), d_cass_ptr.as<int>(), d_cass_idx.as<int>(),
+                                 d_wobs.as<double>(), d_argj.as<int>(), st));
+    std::vector<double> wobs(nmem);
+    std::vector<int> argj(nmem);
+    CGPU_CUDA(cudaMemcpyAsync(wobs.data(), d_wobs.p, (size_t)nmem * 8, cudaMemcpyDeviceToHost, st));
+    CGPU_CUDA(cudaMemcpyAsync(argj.data(), d_argj.p, (size_t)nmem * 4, cudaMemcpyDeviceToHost, st));
+    CGPU_CUDA(cudaStreamSynchronize(st));
+
+    {  // wKH: the weights only choose the contrast (src/consel.c:2121-2134, 2145)
+        for (int e = 0; e < cm; e++) {
+            double x0 = CG_HUGE;
+            int qi = ass_ptr[e];
+            for (int q = ass_ptr[e]; q < ass_ptr[e + 1]; q++)
+                if (wobs[q] < x0) { x0 = wobs[q]; qi = q; }
+            kia[e] = ass_idx[qi];
+            kja[e] = cass_idx[cass_ptr[e] + argj[qi]];
+            kx0[e] = datvec[kja[e]] - datvec[kia[e]];
+        }
+        CGPU_CUDA(cudaMemcpyAsync(d_ia.p, kia.data(), (size_t)cm * 4, cudaMemcpyHostToDevice, st));
+        CGPU_CUDA(cudaMemcpyAsync(d_ja.p, kja.data(), (size_t)cm * 4, cudaMemcpyHostToDevice, st));
+        CGPU_CUDA(cudaMemcpyAsync(d_thr.p, kx0.data(), (size_t)cm * 8, cudaMemcpyHostToDevice, st));
+        RowSrc src{xc.as<double>(), B, d_ia.as<int>(), d_ja.as<int>(), nullptr, nullptr, nullptr};
+        CGPU_TRY(launch_rowsum(1, src, cm, B, 1, d_thr.as<double>(), d_rs.as<cgpu_rowsum>(), 1, 0, st));
+        CGPU_TRY(fetch(cm));
+        for (int e = 0; e < cm; e++) wkh[e] = pval(rs[e], kx0[e]);
+    }
+
+    {  // wSH
+        for (int q0 = 0; q0 < nmem; q0 += chunk_rows) {
+            const int rows = std::min(chunk_rows, nmem - q0);
+            CGPU_TRY(launch_sh_rows(true, xc.as<double>(), K, B, B, d_wt.as<double>(), rows, d_mem_item.as<int>() + q0,
+                                    d_mem_tree.as<int>() + q0, d_cass_ptr.as<int>(), d_cass_idx.as<int>(),
+                                    d_tmp.as<double>(), st));
+            RowSrc src{d_tmp.as<double>(), B, nullptr, nullptr, nullptr, nullptr, nullptr};
+            CGPU_TRY(launch_rowsum(0, src, rows, B, 1, d_wobs.as<double>() + q0, d_rs.as<cgpu_rowsum>() + q0, 1, 0, st));
+        }
+        CGPU_TRY(fetch(nmem));
+        reduce_items(wobs, wsh);
+    }
+    return CGPU_OK;
+}
+
+}  // extern "C"

@@ -78,6 +78,15 @@ struct Globals {
 Globals &G();
 int ensure_init();
 
+// stream-ordered device allocations from the default pool (recycled across calls)
+template <typename T>
+inline cudaError_t dev_alloc(T **p, size_t bytes) {
+    return cudaMallocAsync(reinterpret_cast<void **>(p), bytes ? bytes : 16, G().stream);
+}
+inline void dev_free(void *p) {
+    if (p) cudaFreeAsync(p, G().stream);
+}
+
 // ---------------------------------------------------------------- layouts
 // Site axis padded to a multiple of 128 so every pipeline chunk is full.
 inline int pad_sites(int n) { return (n + 127) / 128 * 128; }
@@ -123,5 +132,32 @@ int launch_transpose_L(const double *d_L, int K, int n, int NP, int TK, double *
                        cudaStream_t st);
 int launch_contract(const DevMatrix &m, const unsigned long long *d_counts, int nb, double r,
                     double *d_rep, int ldrep, int col0, int sum_mode, cudaStream_t st);
+
+// stats_kernels.cu
+// Row definitions for the row-summary kernel:
+//  mode 0: plain row            v = x[row*ld + b]
+//  mode 1: KH difference        v = x[ja[row]*ld + b] - x[ia[row]*ld + b]
+//  mode 2: singleton SH/stat    v = (i == a1[b] ? m2[b] : m1[b]) - x[i*ld + b], i = ia[row]
+struct RowSrc {
+    const double *x;
+    int ld;
+    const int *ia, *ja;
+    const double *m1, *m2;
+    const int *a1;
+};
+int launch_rowsum(int mode, const RowSrc &src, int rows, int B, int nq, const double *d_thr, cgpu_rowsum *d_out,
+                  int out_stride, int out_off, cudaStream_t st);
+int launch_order_stat(const double *d_stat, int rows, int B, int ld, const int *d_rank, double *d_val, cudaStream_t st);
+int launch_col_top2(const double *x, int K, int B, int ld, double *m1, double *m2, int *a1, cudaStream_t st);
+int launch_stat_build(const double *x, int K, int B, int ld, const double *m1, const double *m2, const int *a1,
+                      int cm, const int *ass_ptr, const int *ass_idx, double *stat, cudaStream_t st);
+int launch_center(const double *x, int K, int B, int ld, double *xc, cudaStream_t st);
+int launch_pair_weight(const double *xc, int K, int B, int ld, double varadd, double *wt, int *nsmall, cudaStream_t st);
+int launch_sh_rows(bool weighted, const double *x, int K, int B, int ld, const double *wt, int nmem,
+                   const int *mem_item, const int *mem_tree, const int *cass_ptr, const int *cass_idx, double *out,
+                   cudaStream_t st);
+int launch_weighted_obs(const double *dat, int K, const double *wt, int nmem, const int *mem_item,
+                        const int *mem_tree, const int *cass_ptr, const int *cass_idx, double *obs, int *argj,
+                        cudaStream_t st);
 
 }  // namespace cgpu

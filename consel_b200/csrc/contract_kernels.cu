@@ -1,27 +1,31 @@
 // Replicate sums rep[k][b] = ( sum_j c[b,j] * L[k][j] ) / r — the inner product that is
 // >= 82% of makermt (src/makermt.c:65-70, marked "time consuming" at :68).
 //
-// contract_kernel<TK, MODE, SKIPZERO>: sparse, order-preserving FP64 contraction.
+// contract_kernel<TK, MODE, ALGO>: order-preserving FP64 contraction.
 //   * CTA tile = KT = 32*TK trees x 64 replicates; warp w owns replicate group
 //     g = 8*blockIdx.x + w (8 replicates, one BJ8 count word per site), lane l owns
 //     trees k = ktile*KT + l + 32*i.  Every thread keeps 8*TK fp64 accumulators in
 //     registers and walks the sites j = 0..n-1 IN ORDER, so each output sees exactly
-//     the reference's sequence of roundings:  x = x + rn(c*L)  (MODE 0), and the final
-//     true division by r.  The count byte of (replicate, site) is warp-uniform, so the
-//     branch "c == 0 -> nothing to add" (x + (+-0) == x exactly) skips ~1-exp(-r) of the
-//     work without divergence; c == 1 needs no multiply (1*L == L exactly).
+//     the reference's sequence of roundings:  x = rn(x + rn(c*L))  (MODE 0), then the
+//     final true division by r.  MODE 1 (CGPU_SUM_FAST) fuses the two roundings (DFMA).
+//   * ALGO 0 (default) is dense and branch free: the count byte is turned into fp64
+//     through a 256-entry shared table and every (tree, replicate, site) term is formed,
+//     including 0*L, so non-finite inputs behave exactly like the reference.
+//     ALGO 1 is the sparse variant: the count byte of (replicate, site) is warp-uniform,
+//     so "c == 0 -> nothing to add" (x + (+-0) == x) and "c == 1 -> no multiply"
+//     (1*L == L) are divergence-free branches that skip ~exp(-r) of the terms; it is
+//     kept behind CGPU_CONTRACT_ALGO=1 until its branch overhead is tuned.
 //   * operands are staged through shared memory by a dedicated producer warp with
 //     cp.async.bulk (TMA bulk copies) completing on mbarriers: per stage one contiguous
 //     tile of the site-major matrix LT[ktile][j0..j0+JC)[KT] and the eight count rows
 //     of the CTA's replicate groups; consumers release a stage through an "empty"
 //     mbarrier.  Site-major LT makes the per-site read of 32*TK trees conflict free.
-//   * MODE 1 (CGPU_SUM_FAST) fuses multiply and add (one rounding per term).
-//   * SKIPZERO=false is used when L holds non-finite values (0*inf must stay NaN as in
-//     the reference).
 //
 // Bound: FP64 pipe (and the issue slots of the per-(replicate,site) branches), not HBM:
 // algorithmic HBM bytes per launch are 8*K*n (L once) + n*nb (counts) + 8*K*nb (rep),
 // see DESIGN.md.
+#include <stdlib.h>
+
 #include "cgpu_internal.h"
 
 namespace cgpu {
@@ -114,7 +118,9 @@ struct CtSmem {
     static constexpr size_t total = l_bytes + c_bytes + 2 * CT_STAGES * sizeof(uint64_t);
 };
 
-template <int TK, int MODE, bool SKIPZERO>
+// ALGO 0: dense, branch free (count -> fp64 through a 256-entry shared table)
+// ALGO 1: sparse, warp-uniform branches on the count byte (requires finite L)
+template <int TK, int MODE, int ALGO>
 __global__ void __launch_bounds__(CT_THREADS, (TK >= 8 ? 1 : 2))
 contract_kernel(const double *__restrict__ LT, const unsigned long long *__restrict__ C,
                 double *__restrict__ rep, int K, int NP, int nb, int ldrep, int col0, double r) {
@@ -132,6 +138,8 @@ contract_kernel(const double *__restrict__ LT, const unsigned long long *__restr
     const int ktile = blockIdx.y;
     const int nchunks = NP / JC;
 
+    __shared__ double dtab[256];
+    if (tid < 256) dtab[tid] = (double)tid;
     if (tid == 0) {
         for (int s = 0; s < CT_STAGES; s++) {
             mbar_init(&full[s], 1);
@@ -184,16 +192,24 @@ contract_kernel(const double *__restrict__ LT, const unsigned long long *__restr
 #pragma unroll
                 for (int t = 0; t < 8; t++) {
                     const uint32_t cnt = ((t < 4 ? clo : chi) >> (8 * (t & 3))) & 0xffu;
-                    if (SKIPZERO && cnt == 0) continue;
-                    if (cnt == 1) {
-#pragma unroll
-                        for (int i = 0; i < TK; i++) acc[t][i] = __dadd_rn(acc[t][i], lv[i]);
-                    } else {
-                        const double dc = __uint2double_rn(cnt);
+                    if (ALGO == 0) {
+                        const double dc = dtab[cnt];
 #pragma unroll
                         for (int i = 0; i < TK; i++)
                             acc[t][i] = MODE == CGPU_SUM_STRICT ? __dadd_rn(acc[t][i], __dmul_rn(dc, lv[i]))
                                                                 : __fma_rn(dc, lv[i], acc[t][i]);
+                    } else {
+                        if (cnt == 0) continue;
+                        if (cnt == 1) {
+#pragma unroll
+                            for (int i = 0; i < TK; i++) acc[t][i] = __dadd_rn(acc[t][i], lv[i]);
+                        } else {
+                            const double dc = __uint2double_rn(cnt);
+#pragma unroll
+                            for (int i = 0; i < TK; i++)
+                                acc[t][i] = MODE == CGPU_SUM_STRICT ? __dadd_rn(acc[t][i], __dmul_rn(dc, lv[i]))
+                                                                    : __fma_rn(dc, lv[i], acc[t][i]);
+                        }
                     }
                 }
             }
@@ -216,10 +232,10 @@ contract_kernel(const double *__restrict__ LT, const unsigned long long *__restr
     }
 }
 
-template <int TK, int MODE, bool SKIPZERO>
+template <int TK, int MODE, int ALGO>
 static int launch_contract_t(const DevMatrix &m, const unsigned long long *d_counts, int nb, double r,
                              double *d_rep, int ldrep, int col0, cudaStream_t st) {
-    auto kern = contract_kernel<TK, MODE, SKIPZERO>;
+    auto kern = contract_kernel<TK, MODE, ALGO>;
     static bool attr_done = false;
     if (!attr_done) {
         CGPU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CtSmem<TK>::total));
@@ -232,15 +248,26 @@ static int launch_contract_t(const DevMatrix &m, const unsigned long long *d_cou
     return CGPU_OK;
 }
 
+// CGPU_CONTRACT_ALGO=1 selects the sparse variant (development A/B switch); it needs
+// finite inputs because it never forms 0*L.
+static int contract_algo(const DevMatrix &m) {
+    static int env = [] {
+        const char *e = getenv("CGPU_CONTRACT_ALGO");
+        return e ? atoi(e) : 0;
+    }();
+    return (env == 1 && m.finite) ? 1 : 0;
+}
+
 template <int TK>
 static int launch_contract_tk(const DevMatrix &m, const unsigned long long *d_counts, int nb, double r,
                               double *d_rep, int ldrep, int col0, int sum_mode, cudaStream_t st) {
+    const int algo = contract_algo(m);
     if (sum_mode == CGPU_SUM_STRICT) {
-        if (m.finite) return launch_contract_t<TK, CGPU_SUM_STRICT, true>(m, d_counts, nb, r, d_rep, ldrep, col0, st);
-        return launch_contract_t<TK, CGPU_SUM_STRICT, false>(m, d_counts, nb, r, d_rep, ldrep, col0, st);
+        if (algo == 1) return launch_contract_t<TK, CGPU_SUM_STRICT, 1>(m, d_counts, nb, r, d_rep, ldrep, col0, st);
+        return launch_contract_t<TK, CGPU_SUM_STRICT, 0>(m, d_counts, nb, r, d_rep, ldrep, col0, st);
     }
-    if (m.finite) return launch_contract_t<TK, CGPU_SUM_FAST, true>(m, d_counts, nb, r, d_rep, ldrep, col0, st);
-    return launch_contract_t<TK, CGPU_SUM_FAST, false>(m, d_counts, nb, r, d_rep, ldrep, col0, st);
+    if (algo == 1) return launch_contract_t<TK, CGPU_SUM_FAST, 1>(m, d_counts, nb, r, d_rep, ldrep, col0, st);
+    return launch_contract_t<TK, CGPU_SUM_FAST, 0>(m, d_counts, nb, r, d_rep, ldrep, col0, st);
 }
 
 int launch_contract(const DevMatrix &m, const unsigned long long *d_counts, int nb, double r, double *d_rep,

@@ -13,6 +13,8 @@
 // Layouts: replicate block rep[k*ld + b] (tree-major, as in .rmt); statistic block
 // stat[e*ld + b] (item-major, as in .rep).  These kernels are HBM-streaming: 8 bytes
 // per (row, replicate) element per pass.
+#include <algorithm>
+
 #include "cgpu_internal.h"
 
 namespace cgpu {
@@ -89,18 +91,6 @@ __device__ __forceinline__ void edge_merge(double &mn1, double &mn2, double &mx1
 
 constexpr int RS_THREADS = 256;
 constexpr int RS_MAXQ = 16;
-
-// value of element b of row `row` under the three row definitions
-//  MODE 0: plain row            v = x[row*ld + b]
-//  MODE 1: KH difference        v = x[ja*ld + b] - x[ia*ld + b]            (src/consel.c:2145-2146)
-//  MODE 2: singleton SH/stat    v = (i == a1[b] ? m2[b] : m1[b]) - x[i*ld + b]  (src/consel.c:2026-2030 with |A|=1)
-struct RowSrc {
-    const double *x;
-    int ld;
-    const int *ia, *ja;           // MODE 1 (per row) / MODE 2: ia = tree of the row
-    const double *m1, *m2;        // MODE 2
-    const int *a1;                // MODE 2
-};
 
 template <int MODE>
 __device__ __forceinline__ double row_value(const RowSrc &s, int row, int b, int i_row, int j_row) {

@@ -122,8 +122,9 @@ int cgpu_stats_download(const cgpu_reps *r, int sorted, double *const *stat_out)
 typedef struct cgpu_rowsum {
     double cnt, lo, hi, min1, min2, max1, max2;
 } cgpu_rowsum;
-/* cntdist(v,B,t,3) (src/consel.c:1842-1860) from a row summary: pure host helper. */
-double cgpu_smooth_count(const cgpu_rowsum *q, int B);
+/* cntdist(v,B,t,3) (src/consel.c:1842-1860) from the summary of row v at threshold t:
+ * pure host helper (cntdist(...,2) is q->cnt itself).                               */
+double cgpu_smooth_count(const cgpu_rowsum *q, int B, double t);
 
 /* Replaces cntdist(statmats[s][i],bb[s],x,mode) inside vcalpval/invtpval/do_bptest/
  * do_bootrep (src/consel.c:2775-2778, 2845-2848, 1503-1507): nq thresholds per item,
