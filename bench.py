@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""bench.py — tree-site accumulations per second of the multiscale RELL bootstrap.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Metric (BASELINE.json): acc/s = K*n*sum_s(B_s) / t, where one "step" is one full
+makermt resampling pass (all scales) over one synthetic site-log-likelihood matrix.
+Workload = BASELINE.json configs[1] ("C2"): K=105 trees x n=3414 sites, 10 scales
+r=0.5..1.4, 100000 replicates per scale PER GPU (replicates are sharded over ranks with
+no data-path collective, so N GPUs resample N x 100000 replicates per scale: weak
+scaling), reference-parity mode: MT19937 stream of the reference (seed 7) + strict
+order of operations, i.e. the output is bit-identical to `makermt -s 7`.
+
+  value  device-resident: L already in HBM, replicate blocks left in HBM
+         (cgpu_scaleboot_dev), timed with CUDA events on the library's stream.
+  e2e    through the drop-in C-ABI call cgpu_scaleboot_all with HOST buffers:
+         H2D of L, compute, D2H of the replicate blocks, all inside the timed region.
+
+--impl reference times the UNMODIFIED reference program (oracle/_ref/makermt, built
+from /root/reference/src by oracle/Makefile) on the host cores with the reference's
+own parallel recipe (one process per scale, doc: src/program.tex:1089-1109), on a
+bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "bootstrap tree-site accumulations/sec (K*n*B)"
+UNIT = "acc/s"
+RR = [0.5, 0.6, 0.7, 0.8, 0.9, 1.0, 1.1, 1.2, 1.3, 1.4]
+K, N_SITES, B_PER_SCALE = 105, 3414, 100000
+
+
+def synth_matrix(k: int, n: int, seed: int = 20261019) -> np.ndarray:
+    """mam15-like site log-likelihoods."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    base = -2.3 - 4.07 * rng.exponential(size=n)
+    return np.ascontiguousarray(base[None, :] + 0.106 * rng.standard_normal((k, n)) - 0.5 * np.arange(k)[:, None] / n)
+
+
+def config(world: int) -> dict:
+    return {
+        "workload": "C2 (BASELINE.json configs[1]): synthetic K=105 trees x n=3414 sites, 10 scales "
+                    "r=0.5..1.4 x 100000 replicates per scale per GPU",
+        "K": K, "n": N_SITES, "scales": len(RR), "replicates_per_scale_per_gpu": B_PER_SCALE,
+        "replicates_per_scale_total": B_PER_SCALE * world,
+        "rng_mode": "mt19937 reference stream (seed 7), device jump-ahead",
+        "sum_mode": "strict (bit-identical to src/makermt.c:65-70)",
+        "l2": "per-scale working set (index buffer 1.9 GB + counts 0.35 GB + replicate block 84 MB) "
+              "exceeds the 126 MB L2; a 256 MB buffer is also written between timed steps",
+    }
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        super().__init__(daemon=True)
+        self.idx = gpu_index
+        self.rows = []
+        self._halt = threading.Event()
+
+    def run(self):
+        while not self._halt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.idx)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self._halt.wait(0.2)
+
+    def stop(self) -> dict:
+        self._halt.set()
+        self.join(timeout=6)
+        sm = [float(r[1]) for r in self.rows if len(r) > 2 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for name, val in zip(names, r[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+# ----------------------------------------------------------------------------- ours
+def run_ours(args) -> None:
+    import torch
+    import torch.distributed as dist
+
+    import consel_b200 as cg
+
+    rank, world, local = dist_env()
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"WORLD_SIZE={world} but --gpus {args.gpus}")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    cg.init(local)
+    cg.set_shard(rank, world)
+
+    L = synth_matrix(K, N_SITES)
+    _, bn, _ = cg.scale_setup(L, RR)
+    bb = np.full(len(RR), B_PER_SCALE * world, dtype=np.int32)
+    acc_per_step_total = float(K) * N_SITES * float(bb.sum())
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident arm
+    mat = cg.Matrix(L)
+    for w in range(args.warmup):
+        mat.scaleboot(bn, bb, 7).free()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = cg.launch_count()
+    dev_ms, wall_ms, contract_ms, phases = 0.0, 0.0, 0.0, {}
+    for step in range(args.steps):
+        flush.fill_(step & 0xFF)
+        barrier()
+        t0 = time.perf_counter()
+        reps = mat.scaleboot(bn, bb, 7)  # synchronous: returns after the stream drained
+        torch.cuda.synchronize()
+        wall_ms += (time.perf_counter() - t0) * 1e3
+        tm = cg.last_timing()
+        dev_ms += tm["total"]
+        contract_ms += tm["contract"]
+        for k_, v in tm.items():
+            phases[k_] = phases.get(k_, 0.0) + v / args.steps
+        reps.free()
+    barrier()
+    launches = cg.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    dev_ms = max_over_ranks(dev_ms)
+    wall_ms = max_over_ranks(wall_ms)
+
+    # ---- end-to-end arm: host buffers through cgpu_scaleboot_all
+    Lh = torch.empty((K, N_SITES), dtype=torch.float64, pin_memory=True)
+    Lh.numpy()[:] = L
+    b0, b1 = cg.shard_range(int(bb[0]))
+    out_t = [torch.empty((K, b1 - b0), dtype=torch.float64, pin_memory=True) for _ in bb]  # rank-local blocks
+    outs = [t.numpy() for t in out_t]
+    h2d = int(L.nbytes)
+    d2h = int(K * (b1 - b0) * 8 * len(RR))
+    e2e_steps = max(1, min(args.steps, 3))
+    cg.scaleboot_all(Lh.numpy(), bn, bb, 7, out=outs)  # warm-up (page-locks, pool growth)
+    e2e_ms = 0.0
+    for step in range(e2e_steps):
+        flush.fill_(step & 0xFF)
+        barrier()
+        t0 = time.perf_counter()
+        cg.scaleboot_all(Lh.numpy(), bn, bb, 7, out=outs)
+        checksum = float(outs[0][0, 0])  # the step's result is read on the host
+        e2e_ms += (time.perf_counter() - t0) * 1e3
+    barrier()
+    e2e_ms = max_over_ranks(e2e_ms)
+    assert np.isfinite(checksum)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (contract_kernel), measured live
+    import ctypes as C
+    tf = C.c_double()
+    cg.api._check(cg.load().cgpu_bench_fp64_peak(C.byref(tf)))
+    n_contract = len(RR) * args.steps
+    t_launch = contract_ms / n_contract * 1e-3
+    b_loc = b1 - b0
+    flops_launch = 2.0 * K * N_SITES * b_loc
+    bytes_launch = 8.0 * K * N_SITES + float(N_SITES) * b_loc + 8.0 * K * b_loc
+    peaks = {}
+    try:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    traffic = None
+    tp = ROOT / "profiles" / "contract_traffic.json"
+    if tp.exists():
+        try:
+            traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch_bench_config")
+        except Exception:
+            traffic = None
+    roofline = {
+        "kernel": "contract_kernel<TK=4, strict, dense>",
+        "bound": "fp64",
+        "achieved": flops_launch / t_launch / 1e12,
+        "peak": tf.value,
+        "unit": "TFLOP/s",
+        "frac": flops_launch / t_launch / 1e12 / tf.value,
+        "peak_source": "measured live in this run: FP64 DFMA loop (cgpu_bench_fp64_peak); MEASURED_PEAKS.json "
+                       "has no FP64 figure",
+        "algorithmic": "2 flops per tree-site accumulation (SURVEY 8d) x K*n*B_s per launch; the strict kernel "
+                       "issues a DMUL and a DADD per accumulation, so its own pipe ceiling is frac=0.5",
+        "share_of_step": contract_ms / max(dev_ms, 1e-9),
+        "hbm_view": {"achieved": bytes_launch / t_launch / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": bytes_launch / t_launch / 1e9 / hbm_peak,
+                     "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"},
+        "traffic": traffic,
+    }
+
+    # ---- CPU baseline: the oracle port, single thread, bounded sample
+    from oracle import oracle as orc
+    b_cpu = 3000
+    t0 = time.perf_counter()
+    orc.makermt(L, bn, [b_cpu] * len(RR), 7)
+    t_cpu = time.perf_counter() - t0
+    cpu_baseline = {"value": K * N_SITES * b_cpu * len(RR) / t_cpu, "unit": UNIT, "cores": 1, "kind": "port",
+                    "sample": f"same matrix and scales, {b_cpu} replicates per scale ({t_cpu:.1f} s of oracle/oracle.c)"}
+
+    line = {
+        "metric": METRIC, "value": acc_per_step_total * args.steps / (dev_ms * 1e-3), "unit": UNIT,
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": config(world),
+        "timing": "CUDA events on the library stream, first to last event of each step, max over ranks",
+        "wall_ms_per_step": wall_ms / args.steps, "phases_ms_per_step": phases,
+        "e2e": {"value": acc_per_step_total * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
+                "api": "cgpu_scaleboot_all (pinned host L in, pinned host replicate blocks out)"},
+        "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------ reference
+def run_reference(args) -> None:
+    rank, world, _ = dist_env()
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+    exe = orc.ref_bin("makermt")
+    if exe is None:
+        try:
+            orc.build(ref=True)
+        except Exception:
+            pass
+        exe = orc.ref_bin("makermt")
+    L = synth_matrix(K, N_SITES)
+    cores = os.cpu_count() or 1
+    # the reference's parallel recipe is one process per scale; to use every host core each
+    # scale is further split into `parts` independent processes (own seed), and the
+    # 10*parts jobs run through a pool of `cores` concurrent processes
+    parts = max(1, -(-2 * cores // len(RR))) if cores > len(RR) else 1
+    nproc = len(RR) * parts
+    # ~10 s per job at ~1.5e9 acc/s per core
+    b_each = max(50, int(15e9 / (K * N_SITES)))
+    cfg = config(world)
+    with tempfile.TemporaryDirectory(prefix="consel_ref_") as td:
+        td = Path(td)
+        kind = "reference"
+        if exe is not None:
+            orc.write_mt(td / "in.mt", L)
+            for s, r in enumerate(RR):
+                for p in range(parts):
+                    orc.write_pa(td / f"p{s}_{p}.pa", [r], [b_each])
+
+            def step():
+                jobs = [(s, p) for s in range(len(RR)) for p in range(parts)]
+                running = []
+                while jobs or running:
+                    while jobs and len(running) < cores:
+                        s, p = jobs.pop()
+                        running.append(subprocess.Popen(
+                            [str(exe), "-s", str(151 + s * parts + p), "-p", f"p{s}_{p}", "in", f"o{s}_{p}"],
+                            cwd=td, stdout=subprocess.DEVNULL))
+                    still = []
+                    for pr in running:
+                        rc = pr.poll()
+                        if rc is None:
+                            still.append(pr)
+                        elif rc != 0:
+                            raise RuntimeError("reference makermt failed")
+                    running = still
+                    time.sleep(0.005)
+            total_b = b_each * nproc
+        else:
+            kind = "port"
+            _, bn, _ = orc.scale_setup(L, RR)
+
+            def step():
+                orc.makermt(L, bn, [b_each] * len(RR), 7)
+            total_b = b_each * len(RR)
+            nproc = 1
+        for _ in range(min(args.warmup, 1)):
+            step()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step()
+        t = time.perf_counter() - t0
+    value = K * N_SITES * total_b * args.steps / t
+    sample = (f"{nproc} `makermt -s SEED -p one_scale.pa` processes, at most {cores} at a time (reference binary, -O2), "
+              f"{b_each} replicates each, same matrix read from a 17-digit .mt text file; wall clock "
+              f"includes process start and text parse") if kind == "reference" else \
+             f"oracle port, 1 thread, {b_each} replicates per scale"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": t / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": min(cores, nproc) if kind == "reference" else 1, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

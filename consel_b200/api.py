@@ -123,13 +123,14 @@ def _ptr_array(arrs):
 
 def scaleboot_all(L: np.ndarray, bn, bb, seed: int, stream_offset: int = 0, rng_mode: int = RNG_MT19937,
                   sum_mode: int = SUM_STRICT, out=None):
-    """cgpu_scaleboot_all: host matrix in, host replicate blocks out (list of K x bb[s])."""
+    """cgpu_scaleboot_all: host matrix in, host replicate blocks out: list of K x bb[s]
+    arrays (K x this rank's columns when sharded)."""
     L = np.ascontiguousarray(L, dtype=np.float64)
     K, n = L.shape
     bn = np.ascontiguousarray(bn, dtype=np.int32)
     bb = np.ascontiguousarray(bb, dtype=np.int32)
     if out is None:
-        out = [np.zeros((K, int(b)), dtype=np.float64) for b in bb]
+        out = [np.zeros((K, shard_range(int(b))[1] - shard_range(int(b))[0]), dtype=np.float64) for b in bb]
     _check(load().cgpu_scaleboot_all(_dp(L), K, n, len(bn), _ip(bn), _ip(bb), C.c_ulong(seed),
                                      C.c_ulonglong(stream_offset), rng_mode, sum_mode, _ptr_array(out)))
     return out
@@ -184,9 +185,12 @@ class Reps:
         _check(load().cgpu_reps_upload(K, len(reps), _ip(bb), _ptr_array(reps), C.byref(h)))
         return cls(h, K, bb)
 
+    def _local_cols(self):
+        return [shard_range(int(b))[1] - shard_range(int(b))[0] for b in self.bb]
+
     def download(self, out=None):
         if out is None:
-            out = [np.zeros((self.K, int(b)), dtype=np.float64) for b in self.bb]
+            out = [np.zeros((self.K, nb), dtype=np.float64) for nb in self._local_cols()]
         _check(load().cgpu_reps_download(self._h, _ptr_array(out)))
         return out
 
@@ -197,7 +201,7 @@ class Reps:
         _check(load().cgpu_stats_build(self._h, self.cm, _ip(ass_ptr), _ip(ass_idx)))
 
     def stats_download(self, sorted_rows: bool = False):
-        out = [np.zeros((self.cm, int(b)), dtype=np.float64) for b in self.bb]
+        out = [np.zeros((self.cm, nb), dtype=np.float64) for nb in self._local_cols()]
         _check(load().cgpu_stats_download(self._h, int(sorted_rows), _ptr_array(out)))
         return out
 

@@ -311,9 +311,9 @@ static int matrix_upload(const double *L, int K, int n, DevMatrix **out, cudaStr
 static int reps_download(const DevReps *r, double *const *rep_out, cudaStream_t st) {
     for (int s = 0; s < r->S; s++) {
         if (r->nb[s] <= 0) continue;
-        CGPU_CUDA(cudaMemcpy2DAsync(rep_out[s] + r->b0[s], (size_t)r->bb[s] * sizeof(double), r->d_rep[s],
-                                    (size_t)r->nb[s] * sizeof(double), (size_t)r->nb[s] * sizeof(double), r->K,
-                                    cudaMemcpyDeviceToHost, st));
+        // rank-local compact block K x nb[s] (== the whole K x bb[s] block when unsharded)
+        CGPU_CUDA(cudaMemcpyAsync(rep_out[s], r->d_rep[s], (size_t)r->K * r->nb[s] * sizeof(double),
+                                  cudaMemcpyDeviceToHost, st));
     }
     CGPU_CUDA(cudaStreamSynchronize(st));
     return CGPU_OK;

@@ -173,9 +173,8 @@ int cgpu_stats_download(const cgpu_reps *rr, int sorted, double *const *stat_out
     cudaStream_t st = G().stream;
     for (int s = 0; s < r->S; s++) {
         if (r->nb[s] <= 0) continue;
-        CGPU_CUDA(cudaMemcpy2DAsync(stat_out[s] + r->b0[s], (size_t)r->bb[s] * sizeof(double), r->d_stat[s],
-                                    (size_t)r->nb[s] * sizeof(double), (size_t)r->nb[s] * sizeof(double), r->cm,
-                                    cudaMemcpyDeviceToHost, st));
+        CGPU_CUDA(cudaMemcpyAsync(stat_out[s], r->d_stat[s], (size_t)r->cm * r->nb[s] * sizeof(double),
+                                  cudaMemcpyDeviceToHost, st));
     }
     CGPU_CUDA(cudaStreamSynchronize(st));
     if (sorted) {

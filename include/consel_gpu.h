@@ -73,7 +73,8 @@ int cgpu_shard_range(int bb, int *b_begin, int *b_end);
  *              continues one stream across files); 0 otherwise
  *   rep_out[s] K*bb[s] doubles, row-major (tree-major, replicate fastest): the
  *              exact payload fwrite_bmat (src/misc.c:637-645) writes after its
- *              two-int header.  With sharding only this rank's columns are written.
+ *              two-int header.  With sharding (cgpu_set_shard) rep_out[s] is the
+ *              rank-local compact block K x (b_end-b_begin) of cgpu_shard_range(bb[s]).
  */
 int cgpu_scaleboot_all(const double *L, int K, int n, int S, const int *bn, const int *bb,
                        unsigned long seed, unsigned long long stream_offset, int rng_mode,
@@ -88,7 +89,7 @@ int cgpu_matrix_upload(const double *L, int K, int n, cgpu_matrix **out);
 void cgpu_matrix_free(cgpu_matrix *m);
 int cgpu_scaleboot_dev(const cgpu_matrix *m, int S, const int *bn, const int *bb, unsigned long seed,
                        unsigned long long stream_offset, int rng_mode, int sum_mode, cgpu_reps **out);
-/* copy this rank's replicate columns into rep_out[s] (K x bb[s], see above) */
+/* copy this rank's replicate columns into rep_out[s] (compact K x nb[s], see above) */
 int cgpu_reps_download(const cgpu_reps *r, double *const *rep_out);
 void cgpu_reps_free(cgpu_reps *r);
 
@@ -111,8 +112,9 @@ int cgpu_reps_upload(int K, int S, const int *bb, const double *const *rep, cgpu
  * min_{i in A_e} ( max_{j != i} rep[j][b] - rep[i][b] ).  Associations in CSR form,
  * already permuted into the output item order (orderv, src/consel.c:514-530).     */
 int cgpu_stats_build(cgpu_reps *r, int cm, const int *ass_ptr, const int *ass_idx);
-/* stat_out[s] = cm x bb[s] doubles row-major; sorted != 0 sorts every row ascending
- * like sort_vec (src/consel.c:1466-1471) — the payload of `.rep`.                 */
+/* stat_out[s] = cm x nb[s] doubles row-major (nb[s] = bb[s] unless sharded); sorted != 0
+ * sorts every row ascending like sort_vec (src/consel.c:1466-1471) — the payload of
+ * `.rep` (unsharded only).                                                           */
 int cgpu_stats_download(const cgpu_reps *r, int sorted, double *const *stat_out);
 
 /* Summary of one row of replicates against a threshold t: everything cntdist1/2/3

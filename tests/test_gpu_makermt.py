@@ -175,7 +175,11 @@ def test_sharding_does_not_change_results(cg, orc):
         parts = [np.zeros_like(w) for w in whole]
         for rank in range(3):
             cg.set_shard(rank, 3)
-            cg.scaleboot_all(L, bn, bb, 5, rng_mode=mode, out=parts)
+            loc = cg.scaleboot_all(L, bn, bb, 5, rng_mode=mode)  # rank-local compact blocks
+            for s in range(3):
+                b0, b1 = cg.shard_range(bb[s])
+                assert loc[s].shape == (40, b1 - b0)
+                parts[s][:, b0:b1] = loc[s]
         cg.set_shard(0, 1)
         for s in range(3):
             assert np.array_equal(parts[s], whole[s]), (mode, s)
