@@ -1,0 +1,59 @@
+// C handles over the AU-fit state machines (aufit.h) so the host fit can be unit-tested
+// from Python on a CPU-only box (tests/test_host_fit.py feeds it counts taken from the
+// reference's golden .rep rows).  Not used by the programs themselves.
+#include "aufit.h"
+#include "specfun.h"
+
+extern "C" {
+
+struct aufit_opts_c {
+    int fitmode;
+    double kappa, rrmin, rrmax;
+    int dfmin;
+};
+static aufit::Options make(const aufit_opts_c *o) {
+    aufit::Options opt;
+    if (o) {
+        opt.fitmode = o->fitmode;
+        opt.kappa = o->kappa;
+        opt.rrmin = o->rrmin;
+        opt.rrmax = o->rrmax;
+        opt.dfmin = o->dfmin;
+    }
+    return opt;
+}
+
+void *aufit_vc_new(double x_start, double threshold) { return new aufit::VcIter(x_start, threshold); }
+void aufit_vc_free(void *h) { delete static_cast<aufit::VcIter *>(h); }
+double aufit_vc_x(void *h) { return static_cast<aufit::VcIter *>(h)->x; }
+int aufit_vc_done(void *h) { return static_cast<aufit::VcIter *>(h)->done; }
+void aufit_vc_step(void *h, const double *cnts, const double *rr, const double *bb, int kk, const aufit_opts_c *o) {
+    static_cast<aufit::VcIter *>(h)->step(cnts, rr, bb, kk, make(o));
+}
+// out: pv se pv0 se0 rss df th beta0 beta1 beta2 ret
+void aufit_vc_get(void *h, double *out) {
+    auto *it = static_cast<aufit::VcIter *>(h);
+    double v[11] = {it->pv, it->se, it->pv0, it->se0, it->rss, it->df, it->th_out, it->beta[0], it->beta[1],
+                    it->beta[2], (double)(it->done ? it->ret : 2)};
+    for (int i = 0; i < 11; i++) out[i] = v[i];
+}
+
+void *aufit_ci_new(double xmin, double xmax, double alpha, double kappa) {
+    return new aufit::CiIter(xmin, xmax, alpha, kappa);
+}
+void aufit_ci_free(void *h) { delete static_cast<aufit::CiIter *>(h); }
+double aufit_ci_x(void *h) { return static_cast<aufit::CiIter *>(h)->x; }
+int aufit_ci_done(void *h) { return static_cast<aufit::CiIter *>(h)->done; }
+void aufit_ci_step(void *h, const double *cnts, const double *rr, const double *bb, int kk, const aufit_opts_c *o) {
+    static_cast<aufit::CiIter *>(h)->step(cnts, rr, bb, kk, make(o));
+}
+// out: cival seval eival ret
+void aufit_ci_get(void *h, double *out) {
+    auto *it = static_cast<aufit::CiIter *>(h);
+    out[0] = it->cival; out[1] = it->seval; out[2] = it->eival; out[3] = it->ret;
+}
+
+double aufit_pochisq(double x, int df) { return specfun::pochisq(x, df); }
+double aufit_pnorm(double x) { return specfun::pnorm(x); }
+double aufit_qnorm(double p) { return specfun::qnorm(p); }
+}

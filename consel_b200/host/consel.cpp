@@ -1,0 +1,592 @@
+// consel — drop-in command line of the reference's consel (src/consel.c), rmt mode
+// (do_rmtmode, :800-883).  The replicate-statistics loops run on the GPU through the C
+// ABI: cgpu_mctest (do_mctest :1352-1439), cgpu_stats_build (genrep/repminmaxs :751-787,
+// 1939-1959), cgpu_count_query + cgpu_order_stat (every cntdist / sorted-row access of
+// do_bptest :1286-1303, do_bootrep :1441-1538, vcalpval :2744-2808, invtpval :2816-2879).
+// The per-item AU curve fit stays on the host (aufit.cpp) and is driven in LOCKSTEP over
+// all items so that one device query per round serves every item; the fits of a round
+// run on all host threads.
+//
+// Not carried by this build (error at the command line): -R/-C input modes, -g multi-gene
+// mode, -f rescaling approximation, --chi* spherical fit, --pdm AIC correction,
+// --quick_mctest.  They are off the hot path (SURVEY 8f "next").
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <atomic>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/consel_gpu.h"
+#include "aufit.h"
+#include "refio.h"
+#include "specfun.h"
+
+using namespace refio;
+
+static void byebye() { die("error in command line"); }
+static void dots(int n) {
+    for (int i = 0; i < n; i++) putchar('.');
+    fflush(stdout);
+}
+#define CG(call)                                           \
+    do {                                                   \
+        if ((call) != CGPU_OK) die("%s", cgpu_last_error()); \
+    } while (0)
+
+static const double kHuge = 1.0e30;  // src/consel.c:155
+
+// the per-item fits of one lockstep round are independent: spread them over the host cores
+template <typename F>
+static void parallel_for(int n, F body) {
+    unsigned hw = std::thread::hardware_concurrency();
+    int nt = (int)std::min<unsigned>(hw ? hw : 1, (unsigned)((n + 15) / 16));
+    if (refio::debugmode > 0) nt = 1;  // keep debug traces in item order
+    if (nt <= 1) {
+        for (int i = 0; i < n; i++) body(i);
+        return;
+    }
+    std::atomic<int> next{0};
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; t++)
+        th.emplace_back([&] {
+            for (;;) {
+                int i0 = next.fetch_add(16);
+                if (i0 >= n) break;
+                for (int i = i0; i < std::min(n, i0 + 16); i++) body(i);
+            }
+        });
+    for (auto &t : th) t.join();
+}
+
+struct Assoc {
+    std::vector<int> ptr{0}, idx;
+    int size() const { return (int)ptr.size() - 1; }
+    int len(int e) const { return ptr[e + 1] - ptr[e]; }
+    const int *at(int e) const { return idx.data() + ptr[e]; }
+    void push(const std::vector<int> &v) {
+        idx.insert(idx.end(), v.begin(), v.end());
+        ptr.push_back((int)idx.size());
+    }
+};
+
+int main(int argc, char **argv) {
+    const char *fname_in = nullptr, *fname_out_arg = nullptr, *fname_ass = nullptr, *fname_vt = nullptr;
+    bool outrep = false, outcnt = false, smoothcnt = false, nosort = false;
+    bool dobp = true, doba = true, domc = true, doau = true;
+    int cm_arg = 0, gpu = -1;
+    double threshold = 0.0, varadd = 1.0, bapcoef = 1.0;
+    aufit::Options opt;
+
+    printf("# consel_b200 consel (sm_100a); command line of consel.c,v 1.20");
+
+    for (int i = 1, j = 1; i < argc; i++) {  // src/consel.c:268-431
+        const std::string a = argv[i];
+        auto need = [&]() { if (i + 1 >= argc) byebye(); };
+        auto dbl = [&](double *x) { need(); if (sscanf(argv[++i], "%lf", x) != 1) byebye(); };
+        auto integer = [&](int *x) { need(); if (sscanf(argv[++i], "%d", x) != 1) byebye(); };
+        if (argv[i][0] != '-') {
+            if (j == 1) fname_in = argv[i];
+            else if (j == 2) fname_out_arg = argv[i];
+            else byebye();
+            j++;
+        } else if (a == "-r") outrep = true;
+        else if (a == "-c") outcnt = true;
+        else if (a == "-a") { need(); fname_ass = argv[++i]; }
+        else if (a == "-v") { need(); fname_vt = argv[++i]; }
+        else if (a == "-d") integer(&debugmode);
+        else if (a == "-t") integer(&cm_arg);
+        else if (a == "--no_sort") nosort = true;
+        else if (a == "--no_bp") dobp = false;
+        else if (a == "--no_pp") doba = false;
+        else if (a == "--no_sh") domc = false;
+        else if (a == "--no_au") doau = false;
+        else if (a == "--smooth_cnt") smoothcnt = true;
+        else if (a == "--th") dbl(&threshold);
+        else if (a == "--kappa") dbl(&opt.kappa);
+        else if (a == "--ppcoef") dbl(&bapcoef);
+        else if (a == "--cieps") dbl(&opt.cieps);
+        else if (a == "--vceps2") dbl(&opt.vceps2);
+        else if (a == "--rmin") dbl(&opt.rrmin);
+        else if (a == "--rmax") dbl(&opt.rrmax);
+        else if (a == "--dmin") integer(&opt.dfmin);
+        else if (a == "--mleeps") dbl(&opt.mleeps);
+        else if (a == "--mle") opt.fitmode = aufit::FIT_MLE;
+        else if (a == "--wls") opt.fitmode = aufit::FIT_WLS;
+        else if (a == "--gpu") integer(&gpu);
+        else if (a == "-R" || a == "-C" || a == "-g" || a == "-f" || a == "-p" || a == "--pdm" ||
+                 a == "--quick_mctest" || a.rfind("--chi", 0) == 0 || a == "--aictype" || a == "--ppn" ||
+                 a == "--pmin" || a == "--congbp")
+            die("switch %s is not supported by the B200 build of consel (rmt mode only)", a.c_str());
+        else byebye();
+    }
+
+    std::string outbase;
+    if (fname_in && !fname_out_arg) fname_out_arg = fname_in;
+    if (fname_out_arg) outbase = strip_extension(fname_out_arg);
+    const char *fname_out = fname_out_arg ? outbase.c_str() : nullptr;
+
+    // ---------------- read .rmt (src/consel.c:806-834)
+    std::string used;
+    std::vector<double> datvec, rr;
+    std::vector<int> bb;
+    std::vector<std::vector<double>> repmats;
+    int mm = 0, kk = 0;
+    if (fname_in) {
+        FILE *fp = open_file(fname_in, ".rmt", "rb", &used);
+        printf("\n# reading %s", used.c_str());
+        datvec = read_bvec(fp);
+        mm = (int)datvec.size();
+        rr = read_bvec(fp);
+        kk = (int)rr.size();
+        bb = read_bivec(fp, kk);
+        if (read_bint(fp) != kk) die("wrong size in rmt");
+        repmats.resize(kk);
+        for (int i = 0; i < kk; i++) {
+            int m = mm, b = bb[i];
+            repmats[i] = read_bmat(fp, &m, &b);
+            putchar('.');
+            fflush(stdout);
+        }
+        fclose(fp);
+    } else {
+        printf("\n# reading from stdin");
+        datvec = read_vec(stdin);
+        mm = (int)datvec.size();
+        rr = read_vec(stdin);
+        kk = (int)rr.size();
+        bb = read_ivec(stdin, kk);
+        if (read_int(stdin) != kk) die("wrong size in rmt");
+        repmats.resize(kk);
+        for (int i = 0; i < kk; i++) {
+            int m = mm, b = bb[i];
+            repmats[i] = read_mat(stdin, &m, &b);
+            putchar('.');
+            fflush(stdout);
+        }
+    }
+    printf("\n# K:%d", kk);
+    printf("\n# R:");
+    for (int i = 0; i < kk; i++) printf("%g ", rr[i]);
+    printf("\n# B:");
+    for (int i = 0; i < kk; i++) printf("%d ", bb[i]);
+    printf("\n# M:%d", mm);
+    if (kk < 1) { printf("\n# exit normally\n"); return 0; }
+    if (mm < 2) {
+        warn("M should be at least two");
+        printf("\n# exit normally\n");
+        return 0;
+    }
+
+    // ---------------- associations and item order (read_assoc, src/consel.c:459-541)
+    Assoc ass0;
+    if (fname_ass) {
+        FILE *fp = open_file(fname_ass, ".ass", "r", &used);
+        printf("\n# reading %s", used.c_str());
+        const int cm0 = read_int(fp);
+        for (int i = 0; i < cm0; i++) {
+            std::vector<int> v = read_ivec(fp);
+            for (size_t j = 0; j < v.size(); j++)
+                if (v[j] < 0 || v[j] >= mm) die("ass out of range: ass[%d][%d]=%d", i + 1, (int)j + 1, v[j] + 1);
+            ass0.push(v);
+        }
+        fclose(fp);
+    } else {
+        printf("\n# generate the identity association");
+        for (int i = 0; i < mm; i++) ass0.push({i});
+    }
+    const int cm0 = ass0.size();
+    // observed statistics: max over the complement minus each member, sorted ascending
+    std::vector<std::vector<double>> obsv(cm0);
+    {
+        std::vector<char> mark(mm);
+        for (int e = 0; e < cm0; e++) {
+            std::fill(mark.begin(), mark.end(), 0);
+            int nset = 0;
+            for (int q = 0; q < ass0.len(e); q++) {
+                if (!mark[ass0.at(e)[q]]) nset++;
+                mark[ass0.at(e)[q]] = 1;
+            }
+            if (nset != ass0.len(e)) die("\n# duplicate associations");
+            double mx = -kHuge;
+            for (int jx = 0; jx < mm; jx++)
+                if (!mark[jx] && datvec[jx] > mx) mx = datvec[jx];
+            std::vector<double> v(ass0.len(e));
+            for (int q = 0; q < ass0.len(e); q++) v[q] = mx - datvec[ass0.at(e)[q]];
+            sort_with_order(v, nullptr);
+            obsv[e] = v;
+        }
+    }
+    printf("\n# CM:%d", cm0);
+    int cm = cm_arg;
+    if (cm <= 0 || cm > cm0) cm = cm0;
+    if (cm < cm0) printf(" -> %d", cm);
+    std::vector<int> orderv(cm0);
+    if (nosort) {
+        for (int i = 0; i < cm0; i++) orderv[i] = i;
+    } else {
+        psort_order(cm0, orderv, [&](int a, int b) {  // compdvec, src/consel.c:1986-2000
+            const std::vector<double> &x = obsv[a], &y = obsv[b];
+            int out, len;
+            if (x.size() < y.size()) { out = -1; len = (int)x.size(); }
+            else if (x.size() > y.size()) { out = 1; len = (int)y.size(); }
+            else { out = 0; len = (int)y.size(); }
+            for (int i = 0; i < len; i++) {
+                if (x[i] < y[i]) { out = -1; break; }
+                else if (x[i] > y[i]) { out = 1; break; }
+            }
+            return out;
+        });
+    }
+    dprint(1, "\n# observed statistics for the associations");
+    dprint(1, "\n# %4s %4s ", "rank", "item");
+    for (int i = 0; i < cm0; i++) {
+        dprint(1, "\n# %4d %4d ", i + 1, orderv[i] + 1);
+        for (double v : obsv[orderv[i]]) dprint(1, " %6.2f", v);
+    }
+    Assoc ass;
+    std::vector<double> obsvec(cm);
+    for (int i = 0; i < cm; i++) {
+        obsvec[i] = obsv[orderv[i]][0];
+        ass.push(std::vector<int>(ass0.at(orderv[i]), ass0.at(orderv[i]) + ass0.len(orderv[i])));
+    }
+
+    // ---------------- alphas (read_alpha, src/consel.c:543-560)
+    std::vector<double> alphavec = {0.05, 0.10, 0.5, 0.90, 0.95};
+    if (fname_vt) {
+        FILE *fp = open_file(fname_vt, ".vt", "r", &used);
+        printf("\n# reading %s", used.c_str());
+        alphavec = read_vec(fp);
+        fclose(fp);
+    }
+    const int nalpha = (int)alphavec.size();
+
+    // ---------------- Bayesian posterior (do_batest, src/consel.c:1311-1340)
+    std::vector<double> bapvec(cm, 0.0);
+    if (doba) {
+        double x = -kHuge;
+        for (int i = 0; i < mm; i++)
+            if (datvec[i] > x) x = datvec[i];
+        std::vector<double> w(mm);
+        double y = 0.0;
+        for (int i = 0; i < mm; i++) y += w[i] = exp(bapcoef * (datvec[i] - x));
+        for (int i = 0; i < mm; i++) w[i] = w[i] / y;
+        for (int i = 0; i < cm; i++) {
+            double s = 0.0;
+            for (int q = 0; q < ass.len(i); q++) s += w[ass.at(i)[q]];
+            bapvec[i] = s;
+        }
+    }
+
+    // ---------------- device: upload the replicate blocks
+    CG(cgpu_init(gpu));
+    cgpu_reps *reps = nullptr;
+    {
+        std::vector<const double *> ptrs(kk);
+        for (int i = 0; i < kk; i++) ptrs[i] = repmats[i].data();
+        CG(cgpu_reps_upload(mm, kk, bb.data(), ptrs.data(), &reps));
+    }
+    int i0 = 0;  // scale closest to r = 1 (find_i0, src/consel.c:1778-1789)
+    for (int i = 1; i < kk; i++)
+        if (fabs(rr[i] - 1.0) < fabs(rr[i0] - 1.0)) i0 = i;
+    const int nb0 = bb[i0];
+    auto seval = [](double p, double nb) { return sqrt(p * (1.0 - p) / nb); };  // getseval :2151-2158
+
+    // ---------------- KH / SH tests (do_mctest)
+    std::vector<double> khp(cm), mcp(cm), khwp(cm), mcwp(cm);
+    if (domc) {
+        printf("\n# MC-TEST STARTS");
+        printf("\n# centering the replicates");
+        CG(cgpu_mctest(reps, i0, datvec.data(), varadd, cm, ass.ptr.data(), ass.idx.data(), khp.data(), mcp.data(),
+                       khwp.data(), mcwp.data()));
+        printf("\n# calculating kh-pvalue"); dots(cm);
+        printf("\n# calculating mc-pvalue"); dots(cm);
+        printf("\n# calculating the variances"); dots(mm);
+        printf("\n# calculating weighted kh-pvalue"); dots(cm);
+        printf("\n# calculating weighted mc-pvalue"); dots(cm);
+        printf("\n# MC-TEST DONE");
+    }
+
+    // ---------------- statistics of the replicates (genrep)
+    std::vector<double> npvec(cm), pvvec(cm), sevec(cm), pv0vec(cm), se0vec(cm), rssvec(cm), dfvec(cm), pfvec(cm),
+        thvec(cm), beta(3 * (size_t)cm, 0.0);
+    std::vector<double> cimat, csmat, eimat, ci0mat, cs0mat, ei0mat, cntmat;
+    std::vector<cgpu_rowsum> r0;
+    if (doau || dobp || outrep || outcnt) {
+        printf("\n# calculate replicates of the statistics");
+        CG(cgpu_stats_build(reps, cm, ass.ptr.data(), ass.idx.data()));
+        dots(kk);
+        // one query at the region threshold serves BP, the .cnt file and the row extremes
+        std::vector<double> thr(cm, threshold);
+        r0.resize((size_t)cm * kk);
+        CG(cgpu_count_query(reps, 1, thr.data(), r0.data()));
+    }
+    if (kk < 2) doau = false;
+
+    if (dobp) {  // do_bptest
+        printf("\n# BP-TEST STARTS");
+        for (int jx = 0; jx < cm; jx++) {
+            double x = cgpu_smooth_count(&r0[(size_t)jx * kk + i0], nb0, threshold);
+            npvec[jx] = 1.0 - (1.0 - x / nb0);
+        }
+        printf(" - DONE");
+    }
+
+    std::vector<double> bbd(kk);
+    for (int k = 0; k < kk; k++) bbd[k] = (double)bb[k];
+
+    if (doau) {  // do_bootrep
+        printf("\n# AU-TEST STARTS");
+        printf("\n# counting the replicates (sort-free row summaries on the device)");
+        dots(kk);
+        printf("\n# calculating approximately unbiased p-values by ");
+        printf(opt.fitmode == aufit::FIT_WLS ? "WLS (very fast)" : "MLE (fast)");
+        printf(" fitting");
+        fflush(stdout);
+        const double t0 = cpu_seconds();
+
+        // starting point of every item: the median of the r~1 row (src/consel.c:2765)
+        std::vector<int> rank(cm, nb0 / 2);
+        std::vector<double> med(cm);
+        CG(cgpu_order_stat(reps, i0, rank.data(), med.data()));
+        std::vector<aufit::VcIter> vc;
+        vc.reserve(cm);
+        for (int i = 0; i < cm; i++) vc.emplace_back(med[i], threshold);
+        std::vector<double> thr(cm);
+        std::vector<cgpu_rowsum> rs((size_t)cm * kk);
+        for (int round = 0; round < opt.vcloopmax; round++) {
+            bool any = false;
+            for (int i = 0; i < cm; i++) {
+                thr[i] = vc[i].x;
+                any = any || !vc[i].done;
+            }
+            if (!any) break;
+            CG(cgpu_count_query(reps, 1, thr.data(), rs.data()));
+            parallel_for(cm, [&](int i) {
+                if (vc[i].done) return;
+                std::vector<double> cnts(kk);
+                for (int k = 0; k < kk; k++) cnts[k] = cgpu_smooth_count(&rs[(size_t)i * kk + k], bb[k], thr[i]);
+                vc[i].step(cnts.data(), rr.data(), bbd.data(), kk, opt);
+            });
+        }
+        for (int i = 0; i < cm; i++) {
+            dprint(1, "\n# rank=%d item=%d", i + 1, orderv[i] + 1);
+            const aufit::VcIter &it = vc[i];
+            const int ret = it.done ? it.ret : 2;
+            dprint(1, "\n# ret=%d", ret);
+            pvvec[i] = it.pv; sevec[i] = it.se; pv0vec[i] = it.pv0; se0vec[i] = it.se0;
+            rssvec[i] = it.rss; dfvec[i] = it.df; thvec[i] = it.th_out;
+            if (ret) {
+                pfvec[i] = 0.0;
+                warn("regression degenerated: df[%d]=%g", i + 1, dfvec[i]);
+            } else {
+                pfvec[i] = specfun::pochisq(rssvec[i], (int)dfvec[i]);
+                if (pfvec[i] < 0.01) warn("theory does not fit well: pfit[%d]=%.4f", i + 1, pfvec[i]);
+                for (int c = 0; c < 3; c++) beta[3 * (size_t)i + c] = it.beta[c];
+            }
+            putchar('.');
+        }
+        fflush(stdout);
+        const double t1 = cpu_seconds();
+        printf("\n# time elapsed for AU test is t=%g sec", t1 - t0);
+
+        // ---- confidence limits (invtpval for au and bp)
+        printf("\n# ALPHA:");
+        for (int i = 0; i < nalpha; i++) printf("%g ", alphavec[i]);
+        printf("\n# calculating confidence intervals");
+        const int nq = 2 * nalpha;
+        std::vector<aufit::CiIter> ci;
+        ci.reserve((size_t)cm * nq);
+        for (int jx = 0; jx < cm; jx++) {
+            const cgpu_rowsum &e = r0[(size_t)jx * kk + i0];
+            for (int a = 0; a < nalpha; a++) {
+                ci.emplace_back(e.min1, e.max1, alphavec[a], opt.kappa);
+                ci.emplace_back(e.min1, e.max1, alphavec[a], -1.0);
+            }
+        }
+        // at most 16 thresholds per item and query
+        const int qchunk = 16;
+        std::vector<double> cthr;
+        std::vector<cgpu_rowsum> crs;
+        for (int round = 0; round < opt.ciloopmax; round++) {
+            bool any = false;
+            for (auto &c : ci) any = any || !c.done;
+            if (!any) break;
+            for (int q0 = 0; q0 < nq; q0 += qchunk) {
+                const int nqc = std::min(qchunk, nq - q0);
+                cthr.assign((size_t)cm * nqc, 0.0);
+                for (int jx = 0; jx < cm; jx++)
+                    for (int q = 0; q < nqc; q++) cthr[(size_t)jx * nqc + q] = ci[(size_t)jx * nq + q0 + q].x;
+                crs.resize((size_t)cm * kk * nqc);
+                CG(cgpu_count_query(reps, nqc, cthr.data(), crs.data()));
+                parallel_for(cm, [&](int jx) {
+                    std::vector<double> cnts(kk);
+                    for (int q = 0; q < nqc; q++) {
+                        aufit::CiIter &c = ci[(size_t)jx * nq + q0 + q];
+                        if (c.done) continue;
+                        const double t = cthr[(size_t)jx * nqc + q];
+                        for (int k = 0; k < kk; k++)
+                            cnts[k] = cgpu_smooth_count(&crs[((size_t)jx * kk + k) * nqc + q], bb[k], t);
+                        c.step(cnts.data(), rr.data(), bbd.data(), kk, opt);
+                    }
+                });
+            }
+        }
+        cimat.resize((size_t)cm * nalpha); csmat = cimat; eimat = cimat;
+        ci0mat = cimat; cs0mat = cimat; ei0mat = cimat;
+        for (int jx = 0; jx < cm; jx++) {
+            for (int a = 0; a < nalpha; a++) {
+                for (int which = 0; which < 2; which++) {
+                    const aufit::CiIter &c = ci[(size_t)jx * nq + 2 * a + which];
+                    dprint(1, "\n# invtpval item=%d alpha=%g ", jx + 1, alphavec[a]);
+                    if (c.degenerate_warning) warn("degenerecy in pval df=%g", c.warn_value);
+                    if (c.noconv_warning) warn("no convergence in ci: ei=%6.3f", c.warn_value);
+                    if (c.ret) printf(" %s item=%2d, alpha=%4.2f", which ? "bp" : "au", jx + 1, alphavec[a]);
+                    std::vector<double> &cm_ = which ? ci0mat : cimat, &cs_ = which ? cs0mat : csmat,
+                                        &ce_ = which ? ei0mat : eimat;
+                    cm_[(size_t)jx * nalpha + a] = c.cival;
+                    cs_[(size_t)jx * nalpha + a] = c.seval;
+                    ce_[(size_t)jx * nalpha + a] = c.eival;
+                }
+            }
+            putchar('.');
+        }
+        fflush(stdout);
+        printf("\n# AU-TEST DONE");
+    }
+
+    if (outcnt && (doau || dobp)) {
+        cntmat.resize((size_t)cm * kk);
+        for (int i = 0; i < cm; i++)
+            for (int k = 0; k < kk; k++) {
+                const cgpu_rowsum &q = r0[(size_t)i * kk + k];
+                cntmat[(size_t)i * kk + k] = smoothcnt ? cgpu_smooth_count(&q, bb[k], threshold) : q.cnt;
+            }
+    }
+
+    // ---------------- outputs (write_pv :1611-1683, write_ci :1685-1711, write_rep, write_cnt)
+    if (dobp || domc || doau || doba) {
+        FILE *fp = stdout;
+        if (fname_out) {
+            fp = open_file(fname_out, ".pv", "w", &used);
+            printf("\n# writing %s", used.c_str());
+        } else {
+            printf("\n# writing to stdout\n");
+        }
+        const int outbit = (dobp ? 1 : 0) + (doba ? 2 : 0) + (domc ? 4 : 0) + (doau ? 8 : 0);
+        const int pvnum = (dobp ? 1 : 0) + (doba ? 1 : 0) + (domc ? 4 : 0) + (doau ? 2 : 0);
+        const int auxnum = doau ? 7 : 0;
+        fprintf(fp, "\n# ID:\n%d\n", 1);
+        fprintf(fp, "\n# ITEM:\n"); write_ivec(fp, orderv.data(), cm);
+        fprintf(fp, "\n# STAT:\n"); write_vec(fp, obsvec.data(), cm);
+        fprintf(fp, "\n# BIT:\n%d\n", outbit);
+        std::vector<double> pvmat((size_t)cm * pvnum), semat((size_t)cm * pvnum), auxmat((size_t)cm * auxnum);
+        for (int i = 0; i < cm; i++) {
+            int j = 0;
+            auto put = [&](double p, double s) {
+                pvmat[(size_t)i * pvnum + j] = p;
+                semat[(size_t)i * pvnum + j] = s;
+                j++;
+            };
+            if (dobp) put(npvec[i], seval(npvec[i], (double)nb0));
+            if (doba) put(bapvec[i], 0.0);
+            if (domc) {
+                put(khp[i], seval(khp[i], (double)nb0));
+                put(mcp[i], seval(mcp[i], (double)nb0));
+                put(khwp[i], seval(khwp[i], (double)nb0));
+                put(mcwp[i], seval(mcwp[i], (double)nb0));
+            }
+            if (doau) {
+                put(pvvec[i], sevec[i]);
+                put(pv0vec[i], se0vec[i]);
+                double *ax = &auxmat[(size_t)i * auxnum];
+                ax[0] = pfvec[i]; ax[1] = rssvec[i]; ax[2] = dfvec[i];
+                ax[3] = beta[3 * (size_t)i]; ax[4] = beta[3 * (size_t)i + 1];
+                ax[5] = thvec[i]; ax[6] = beta[3 * (size_t)i + 2];
+            }
+        }
+        fprintf(fp, "\n# PV:\n"); write_mat(fp, pvmat.data(), cm, pvnum);
+        fprintf(fp, "\n# SE:\n"); write_mat(fp, semat.data(), cm, pvnum);
+        fprintf(fp, "\n# AX:\n"); write_mat(fp, auxnum ? auxmat.data() : pvmat.data(), cm, auxnum);
+        if (fname_out) fclose(fp);
+    }
+    if (doau) {
+        FILE *fp = stdout;
+        if (fname_out) {
+            fp = open_file(fname_out, ".ci", "w", &used);
+            printf("\n# writing %s", used.c_str());
+        } else {
+            printf("\n# writing to stdout\n");
+        }
+        fprintf(fp, "\n# ITEM:\n"); write_ivec(fp, orderv.data(), cm);
+        fprintf(fp, "\n# STAT:\n"); write_vec(fp, obsvec.data(), cm);
+        fprintf(fp, "\n# ALPHA:\n"); write_vec(fp, alphavec.data(), nalpha);
+        fprintf(fp, "\n# CI:\n"); write_mat(fp, cimat.data(), cm, nalpha);
+        fprintf(fp, "\n# SE:\n"); write_mat(fp, csmat.data(), cm, nalpha);
+        fprintf(fp, "\n# EI:\n"); write_mat(fp, eimat.data(), cm, nalpha);
+        fprintf(fp, "\n# CI0:\n"); write_mat(fp, ci0mat.data(), cm, nalpha);
+        fprintf(fp, "\n# SE0:\n"); write_mat(fp, cs0mat.data(), cm, nalpha);
+        fprintf(fp, "\n# EI0:\n"); write_mat(fp, ei0mat.data(), cm, nalpha);
+        if (fname_out) fclose(fp);
+    }
+    if (outrep) {
+        std::vector<std::vector<double>> st(kk);
+        std::vector<double *> ptrs(kk);
+        for (int k = 0; k < kk; k++) {
+            st[k].resize((size_t)cm * bb[k]);
+            ptrs[k] = st[k].data();
+        }
+        // the reference writes the rows after do_bootrep/do_bptest sorted them in place
+        const bool sorted = doau || dobp;
+        CG(cgpu_stats_download(reps, sorted ? 1 : 0, ptrs.data()));
+        if (fname_out) {
+            FILE *fp = open_file(fname_out, ".rep", "wb", &used);
+            printf("\n# writing %s", used.c_str());
+            write_bivec(fp, orderv.data(), cm);
+            write_bvec(fp, obsvec.data(), cm);
+            write_bvec(fp, rr.data(), kk);
+            write_bivec(fp, bb.data(), kk);
+            write_bint(fp, kk);
+            for (int k = 0; k < kk; k++) {
+                write_bmat(fp, st[k].data(), cm, bb[k]);
+                putchar('.');
+            }
+            fclose(fp);
+        } else {
+            printf("\n# writing to stdout\n");
+            write_ivec(stdout, orderv.data(), cm);
+            write_vec(stdout, obsvec.data(), cm);
+            write_vec(stdout, rr.data(), kk);
+            write_ivec(stdout, bb.data(), kk);
+            printf("%d\n", kk);
+            for (int k = 0; k < kk; k++) write_mat(stdout, st[k].data(), cm, bb[k]);
+        }
+    }
+    if (outcnt && !cntmat.empty()) {
+        FILE *fp = stdout;
+        if (fname_out) {
+            fp = open_file(fname_out, ".cnt", "w", &used);
+            printf("\n# writing %s", used.c_str());
+        } else {
+            printf("\n# writing to stdout\n");
+        }
+        std::vector<double> rrmat((size_t)cm * kk), bbmat((size_t)cm * kk);
+        for (int i = 0; i < cm; i++)
+            for (int k = 0; k < kk; k++) {
+                rrmat[(size_t)i * kk + k] = rr[k];
+                bbmat[(size_t)i * kk + k] = (double)bb[k];
+            }
+        fprintf(fp, "\n# ITEM:\n"); write_ivec(fp, orderv.data(), cm);
+        fprintf(fp, "\n# STAT:\n"); write_vec(fp, obsvec.data(), cm);
+        fprintf(fp, "\n# R:\n"); write_mat(fp, rrmat.data(), cm, kk);
+        fprintf(fp, "\n# B:\n"); write_mat(fp, bbmat.data(), cm, kk);
+        fprintf(fp, "\n# CNT:\n"); write_mat(fp, cntmat.data(), cm, kk);
+        if (fname_out) fclose(fp);
+    }
+    cgpu_reps_free(reps);
+    printf("\n# exit normally\n");
+    cgpu_shutdown();
+    return 0;
+}

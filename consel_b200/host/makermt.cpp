@@ -1,0 +1,246 @@
+// makermt — drop-in command line of the reference's makermt (src/makermt.c) whose
+// resampling loop (genrmt's `for scale: scaleboot(); fwrite_bmat();`, :201-211) runs on
+// the GPU through the C ABI (cgpu_scaleboot_all).  Everything else — argument parsing,
+// .pa/.mt/.lnf/... readers, scale set-up, .vt/.rmt writers, stdout lines — is host code
+// that follows the reference's observable behaviour line by line (citations inline).
+//
+// Extensions (not in the reference): --rng mt|philox, --sum strict|fast, --gpu N.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+#include <string>
+#include <vector>
+
+#include "../../include/consel_gpu.h"
+#include "refio.h"
+
+using namespace refio;
+
+enum SeqMode { SEQ_MT, SEQ_MOLPHY, SEQ_PAML, SEQ_PAUP, SEQ_PUZZLE, SEQ_PHYML };
+
+static void byebye() { die("error in command line"); }
+
+struct Params {
+    unsigned long seed = 0;
+    unsigned long seed_used = 0;
+    std::vector<double> rr;
+    std::vector<int> bb;
+    SeqMode seqmode = SEQ_MT;
+    int rng_mode = CGPU_RNG_MT19937, sum_mode = CGPU_SUM_STRICT;
+    unsigned long long consumed = 0;  // draws taken from the stream so far (-g continues it)
+};
+
+static int genrmt(Params &P, const char *infile, const char *outfile) {
+    const char *fext = ".mt";
+    switch (P.seqmode) {  // default extensions: src/freadmat.h:13-18
+        case SEQ_MOLPHY: fext = ".lls"; break;
+        case SEQ_PAML: fext = ".lnf"; break;
+        case SEQ_PAUP: fext = ".txt"; break;
+        case SEQ_PUZZLE: fext = ".sitelh"; break;
+        case SEQ_PHYML: fext = ".txt"; break;
+        default: break;
+    }
+    FILE *fp;
+    std::string used;
+    if (infile) {
+        fp = open_file(infile, fext, "r", &used);
+        printf("\n# reading %s", used.c_str());
+    } else {
+        fp = stdin;
+        printf("\n# reading from stdin");
+    }
+    int mm = 0, nn = 0;
+    std::vector<double> L;
+    switch (P.seqmode) {
+        case SEQ_MOLPHY: L = read_mat_molphy(fp, &mm, &nn); break;
+        case SEQ_PAML: L = read_mat_paml(fp, &mm, &nn); break;
+        case SEQ_PAUP: L = read_mat_paup(fp, &mm, &nn); break;
+        case SEQ_PUZZLE: L = read_mat_puzzle(fp, &mm, &nn); break;
+        case SEQ_PHYML: L = read_mat_phyml(fp, &mm, &nn); break;
+        default: L = read_mat(fp, &mm, &nn); break;
+    }
+    if (infile) fclose(fp);
+    printf("\n# M:%d N:%d", mm, nn);
+    if (mm <= 0 || nn <= 0) die("empty matrix");
+
+    const int kk = (int)P.rr.size();
+    std::vector<double> datvec(mm), rr1(kk);
+    std::vector<int> bn(kk);
+    for (int i = 0; i < mm; i++) {  // src/makermt.c:159-162
+        double x = 0;
+        for (int j = 0; j < nn; j++) x += L[(size_t)i * nn + j];
+        datvec[i] = x;
+    }
+    for (int i = 0; i < kk; i++) {  // :165-168
+        bn[i] = (int)(P.rr[i] * nn);
+        rr1[i] = (double)bn[i] / nn;
+    }
+
+    FILE *out = nullptr;
+    if (outfile) {
+        fp = open_file(outfile, ".vt", "w", &used);
+        printf("\n# writing %s", used.c_str());
+        write_vec(fp, datvec.data(), mm);
+        fclose(fp);
+        out = open_file(outfile, ".rmt", "wb", &used);
+        printf("\n# writing %s", used.c_str());
+        write_bvec(out, datvec.data(), mm);
+        write_bvec(out, rr1.data(), kk);
+        write_bivec(out, P.bb.data(), kk);
+        write_bint(out, kk);
+    } else {
+        printf("\n# writing to stdout");
+        printf("\n# OBS:\n"); write_vec(stdout, datvec.data(), mm);
+        printf("\n# R:\n"); write_vec(stdout, rr1.data(), kk);
+        printf("\n# B:\n"); write_ivec(stdout, P.bb.data(), kk);
+        printf("\n# RMAT:\n");
+        printf("%d\n", kk);
+    }
+
+    int total = 0;
+    for (int i = 0; i < kk; i++) total += P.bb[i];
+    printf("\n# start generating total %d replicates for %d items", total, mm);
+    fflush(stdout);
+    const double t0 = cpu_seconds();
+
+    // ---- the hot loop, on the device
+    std::vector<std::vector<double>> rep(kk);
+    std::vector<double *> rep_ptr(kk);
+    for (int i = 0; i < kk; i++) {
+        rep[i].resize((size_t)mm * (P.bb[i] > 0 ? P.bb[i] : 0) + 1);
+        rep_ptr[i] = rep[i].data();
+    }
+    int rc = cgpu_scaleboot_all(L.data(), mm, nn, kk, bn.data(), P.bb.data(), P.seed_used, P.consumed, P.rng_mode,
+                                P.sum_mode, rep_ptr.data());
+    if (rc != CGPU_OK) die("%s", cgpu_last_error());
+    for (int i = 0; i < kk; i++) P.consumed += (unsigned long long)P.bb[i] * (unsigned long long)bn[i];
+
+    for (int i = 0; i < kk; i++) {
+        if (outfile) {
+            write_bmat(out, rep[i].data(), mm, P.bb[i]);
+            putchar('.');
+            fflush(stdout);
+        } else {
+            printf("\n## RMAT[%d]:\n", i);
+            write_mat(stdout, rep[i].data(), mm, P.bb[i]);
+        }
+    }
+    const double t1 = cpu_seconds();
+    printf("\n# time elapsed for bootstrap t=%g sec", t1 - t0);
+    if (outfile) fclose(out);
+    return 0;
+}
+
+int main(int argc, char **argv) {
+    Params P;
+    const char *fname_pa = nullptr, *fname_mt = nullptr, *fname_rmt = nullptr;
+    double bbfact = 1.0;
+    bool fastrep = false, multi = false;
+    int gpu = -1;
+
+    printf("# consel_b200 makermt (sm_100a); command line of makermt.c,v 1.16");
+
+    for (int i = 1, j = 1; i < argc; i++) {  // src/makermt.c:237-279
+        const std::string a = argv[i];
+        auto need = [&](int more) { if (i + more >= argc) byebye(); };
+        if (argv[i][0] != '-') {
+            if (j == 1) fname_mt = argv[i];
+            else if (j == 2) fname_rmt = argv[i];
+            else byebye();
+            j++;
+        } else if (a == "-s") {
+            need(1);
+            if (sscanf(argv[++i], "%lu", &P.seed) != 1) byebye();
+        } else if (a == "-p") {
+            need(1);
+            fname_pa = argv[++i];
+        } else if (a == "-b") {
+            need(1);
+            if (sscanf(argv[++i], "%lf", &bbfact) != 1) byebye();
+        } else if (a == "-f") fastrep = true;
+        else if (a == "-g") multi = true;
+        else if (a == "--molphy") P.seqmode = SEQ_MOLPHY;
+        else if (a == "--paml") P.seqmode = SEQ_PAML;
+        else if (a == "--paup") P.seqmode = SEQ_PAUP;
+        else if (a == "--puzzle") P.seqmode = SEQ_PUZZLE;
+        else if (a == "--phyml") P.seqmode = SEQ_PHYML;
+        else if (a == "-d") {
+            need(1);
+            if (sscanf(argv[++i], "%d", &debugmode) != 1) byebye();
+        } else if (a == "--rng") {
+            need(1);
+            std::string v = argv[++i];
+            if (v == "mt" || v == "mt19937") P.rng_mode = CGPU_RNG_MT19937;
+            else if (v == "philox") P.rng_mode = CGPU_RNG_PHILOX;
+            else byebye();
+        } else if (a == "--sum") {
+            need(1);
+            std::string v = argv[++i];
+            if (v == "strict") P.sum_mode = CGPU_SUM_STRICT;
+            else if (v == "fast") P.sum_mode = CGPU_SUM_FAST;
+            else byebye();
+        } else if (a == "--gpu") {
+            need(1);
+            if (sscanf(argv[++i], "%d", &gpu) != 1) byebye();
+        } else byebye();
+    }
+
+    // smrand (src/rand.c:33-37): seed 0 means "seed from the clock"
+    P.seed_used = P.seed ? P.seed : (unsigned long)time(nullptr);
+
+    if (fname_pa) {  // src/makermt.c:285-291
+        std::string used;
+        FILE *fp = open_file(fname_pa, ".pa", "r", &used);
+        printf("\n# reading %s", used.c_str());
+        P.rr = read_vec(fp);
+        P.bb = read_ivec(fp, (int)P.rr.size());
+        fclose(fp);
+    } else if (fastrep) {
+        P.rr = {1.0};
+        P.bb = {10000};
+    } else {
+        P.rr = {0.5, 0.6, 0.7, 0.8, 0.9, 1.0, 1.1, 1.2, 1.3, 1.4};
+        P.bb.assign(10, 10000);
+    }
+    const int kk = (int)P.rr.size();
+    for (int i = 0; i < kk; i++) P.bb[i] = (int)(P.bb[i] * bbfact);  // `bb[i] *= bbfact`, :297
+    printf("\n# seed:%lu (MT19937 generator)", P.seed);
+    printf("\n# K:%d", kk);
+    printf("\n# R:");
+    for (int i = 0; i < kk; i++) printf("%g ", P.rr[i]);
+    printf("\n# B:");
+    for (int i = 0; i < kk; i++) printf("%d ", P.bb[i]);
+
+    if (cgpu_init(gpu) != CGPU_OK) die("%s", cgpu_last_error());
+
+    if (multi) {  // src/makermt.c:303-318
+        std::string used;
+        FILE *fp = fname_mt ? open_file(fname_mt, ".svt", "r", &used) : stdin;
+        std::vector<std::string> infiles = read_svec(fp), outfiles;
+        if (fname_mt) fclose(fp);
+        if (fname_rmt) {
+            fp = open_file(fname_rmt, ".svt", "r", &used);
+            outfiles = read_svec(fp);
+            fclose(fp);
+            if (outfiles.size() != infiles.size()) die("size mismatch in svec");
+        } else {
+            for (auto &s : infiles) outfiles.push_back(strip_extension(s));
+        }
+        for (size_t i = 0; i < infiles.size(); i++) {
+            printf("\n# %d/%d %s %s", (int)i + 1, (int)infiles.size(), infiles[i].c_str(), outfiles[i].c_str());
+            genrmt(P, infiles[i].c_str(), outfiles[i].c_str());
+        }
+    } else {
+        std::string outname;
+        if (fname_mt && !fname_rmt) {
+            outname = strip_extension(fname_mt);
+            fname_rmt = outname.c_str();
+        }
+        genrmt(P, fname_mt, fname_rmt);
+    }
+    printf("\n# exit normally\n");
+    cgpu_shutdown();
+    return 0;
+}

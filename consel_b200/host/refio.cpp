@@ -1,0 +1,490 @@
+// See refio.h.  Behaviour restated from the reference's src/misc.c and src/freadmat.c
+// (citations per function); written from the observed file/stdout conventions, not
+// copied: std::vector storage, no global scratch, C++ I/O helpers.
+#include "refio.h"
+
+#include <cctype>
+#include <cmath>
+#include <cstdarg>
+#include <cstdlib>
+#include <cstring>
+#include <ctime>
+
+namespace refio {
+
+int debugmode = 0;
+
+void die(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    printf("\n#! Terminated: ");
+    vprintf(fmt, ap);
+    printf(".\n");
+    va_end(ap);
+    exit(1);
+}
+
+void warn(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    printf("\n#! Warning: ");
+    vprintf(fmt, ap);
+    printf(". ");
+    va_end(ap);
+}
+
+void dprint(int level, const char *fmt, ...) {
+    if (debugmode < level) return;
+    va_list ap;
+    va_start(ap, fmt);
+    vprintf(fmt, ap);
+    va_end(ap);
+}
+
+double cpu_seconds() { return (double)clock() / CLOCKS_PER_SEC; }
+
+// position of the '.' that starts an extension made of alphanumerics, or npos
+static size_t ext_pos(const std::string &name) {
+    int i = (int)name.size() - 1;
+    while (i >= 0 && isalnum((unsigned char)name[i])) i--;
+    if (i > 0 && name[i] == '.' && name[i - 1] != '/' && name[i - 1] != '.') return (size_t)i;
+    return std::string::npos;
+}
+bool has_extension(const std::string &name) { return ext_pos(name) != std::string::npos; }
+std::string strip_extension(const std::string &name) {
+    size_t p = ext_pos(name);
+    return p == std::string::npos ? name : name.substr(0, p);
+}
+FILE *open_file(const std::string &name, const char *ext, const char *mode, std::string *used) {
+    std::string fname = has_extension(name) ? name : name + ext;
+    FILE *fp = fopen(fname.c_str(), mode);
+    if (!fp) die("cant open %s", fname.c_str());
+    if (used) *used = fname;
+    return fp;
+}
+
+// ------------------------------------------------------------------ ascii in
+void skip_junk(FILE *fp) {
+    for (;;) {
+        int c;
+        do c = getc(fp);
+        while (isspace(c));
+        if (c == '#') {
+            while ((c = getc(fp)) != '\n' && c != EOF) {}
+            if (c == EOF) return;
+        } else {
+            ungetc(c, fp);
+            return;
+        }
+    }
+}
+void skip_line(FILE *fp) {
+    for (;;) {
+        int c = getc(fp);
+        if (c == EOF || c == '\n') return;
+        if (c == '\r') {
+            c = getc(fp);
+            if (c != '\n') ungetc(c, fp);
+            return;
+        }
+    }
+}
+void skip_word(FILE *fp) {
+    for (;;) {
+        int c = getc(fp);
+        if (c == EOF || isspace(c)) return;
+    }
+}
+int read_int(FILE *fp) {
+    int x;
+    skip_junk(fp);
+    if (fscanf(fp, "%d", &x) != 1) die("cant read int");
+    return x;
+}
+double read_double(FILE *fp) {
+    double x;
+    skip_junk(fp);
+    if (fscanf(fp, "%lf", &x) != 1) die("cant read double");
+    return x;
+}
+std::string read_word(FILE *fp) {
+    std::string w;
+    skip_junk(fp);
+    for (;;) {
+        int c = getc(fp);
+        if (c == EOF) break;
+        if (isspace(c)) {
+            ungetc(c, fp);
+            break;
+        }
+        w.push_back((char)c);
+        if (w.size() >= BUFSIZ) die("too long word");
+    }
+    return w;
+}
+std::vector<double> read_vec(FILE *fp, int expect) {
+    int m = read_int(fp);
+    if (expect > 0 && expect != m) die("size mismatch in vec");
+    std::vector<double> a(m > 0 ? m : 0);
+    for (int i = 0; i < m; i++) a[i] = read_double(fp);
+    return a;
+}
+std::vector<int> read_ivec(FILE *fp, int expect) {
+    int m = read_int(fp);
+    if (expect > 0 && expect != m) die("size mismatch in ivec");
+    std::vector<int> a(m > 0 ? m : 0);
+    for (int i = 0; i < m; i++) a[i] = read_int(fp);
+    return a;
+}
+std::vector<std::string> read_svec(FILE *fp) {
+    int m = read_int(fp);
+    std::vector<std::string> a;
+    for (int i = 0; i < m; i++) a.push_back(read_word(fp));
+    return a;
+}
+std::vector<double> read_mat(FILE *fp, int *mp, int *np) {
+    int m = read_int(fp), n = read_int(fp);
+    if (*mp > 0 && *mp != m) die("size of rows mismatch in mat");
+    if (*np > 0 && *np != n) die("size of columns mismatch in mat");
+    std::vector<double> a;
+    if ((long long)m * n == 0) return a;
+    a.resize((size_t)m * n);
+    for (size_t e = 0; e < a.size(); e++) a[e] = read_double(fp);
+    *mp = m;
+    *np = n;
+    return a;
+}
+
+// ------------------------------------------------------------------ ascii out
+static const int kPerLine = 5;
+void write_vec(FILE *fp, const double *a, int m) {
+    fprintf(fp, "#!VEC:\n%d\n", m);
+    for (int i = 0, k = 0; i < m; i++) {
+        if (++k > kPerLine) {
+            putc('\n', fp);
+            k = 1;
+        }
+        fprintf(fp, "%14.9g ", a[i]);
+    }
+    putc('\n', fp);
+}
+void write_ivec(FILE *fp, const int *a, int m) {
+    fprintf(fp, "#!VEC:\n%d\n", m);
+    for (int i = 0, k = 0; i < m; i++) {
+        if (++k > kPerLine) {
+            putc('\n', fp);
+            k = 1;
+        }
+        fprintf(fp, "%10d ", a[i]);
+    }
+    putc('\n', fp);
+}
+void write_mat(FILE *fp, const double *a, int m, int n) {
+    fprintf(fp, "#!MAT:\n%d %d\n", m, n);
+    if (!a) return;
+    for (int i = 0; i < m; i++) {
+        fprintf(fp, "\n# row: %d\n", i);
+        for (int j = 0, k = 0; j < n; j++) {
+            if (++k > kPerLine) {
+                putc('\n', fp);
+                k = 1;
+            }
+            fprintf(fp, "%14.9g ", a[(size_t)i * n + j]);
+        }
+        putc('\n', fp);
+    }
+}
+
+// ------------------------------------------------------------------ binary
+int read_bint(FILE *fp) {
+    int x;
+    if (fread(&x, sizeof(int), 1, fp) != 1) die("cant read binary int");
+    return x;
+}
+std::vector<double> read_bvec(FILE *fp, int expect) {
+    int m = read_bint(fp);
+    if (expect > 0 && expect != m) die("size mismatch in bvec");
+    std::vector<double> a(m > 0 ? m : 0);
+    if (m > 0 && fread(a.data(), sizeof(double), m, fp) != (size_t)m) die("cant read bvec");
+    return a;
+}
+std::vector<int> read_bivec(FILE *fp, int expect) {
+    int m = read_bint(fp);
+    if (expect > 0 && expect != m) die("size mismatch in bivec");
+    std::vector<int> a(m > 0 ? m : 0);
+    if (m > 0 && fread(a.data(), sizeof(int), m, fp) != (size_t)m) die("cant read bivec");
+    return a;
+}
+std::vector<double> read_bmat(FILE *fp, int *mp, int *np) {
+    int m = read_bint(fp), n = read_bint(fp);
+    if (*mp > 0 && *mp != m) die("size of rows mismatch in bmat");
+    if (*np > 0 && *np != n) die("size of columns mismatch in bmat");
+    std::vector<double> a((size_t)m * n);
+    if (!a.empty() && fread(a.data(), sizeof(double), a.size(), fp) != a.size()) die("cant read bmat");
+    *mp = m;
+    *np = n;
+    return a;
+}
+void write_bint(FILE *fp, int x) {
+    if (fwrite(&x, sizeof(int), 1, fp) != 1) die("cant write binary int");
+}
+void write_bvec(FILE *fp, const double *a, int m) {
+    write_bint(fp, m);
+    if (m > 0 && fwrite(a, sizeof(double), m, fp) != (size_t)m) die("cant write bvec");
+}
+void write_bivec(FILE *fp, const int *a, int m) {
+    write_bint(fp, m);
+    if (m > 0 && fwrite(a, sizeof(int), m, fp) != (size_t)m) die("cant write bivec");
+}
+void write_bmat(FILE *fp, const double *a, int m, int n) {
+    write_bint(fp, m);
+    write_bint(fp, n);
+    size_t cnt = (size_t)m * n;
+    if (cnt && fwrite(a, sizeof(double), cnt, fp) != cnt) die("cant write bmat");
+}
+
+// ------------------------------------------------------------------ foreign formats
+std::vector<double> read_mat_paml(FILE *fp, int *mp, int *np) {
+    int m = read_int(fp), n = read_int(fp), p = read_int(fp);
+    dprint(2, "\nm=%d n=%d p=%d", m, n, p);
+    if (m < 0) die("negative tree numbers");
+    if (*mp > 0 && *mp != m) die("size of rows mismatch in mat");
+    if (*np > 0 && *np != n) die("size of columns mismatch in mat");
+    skip_line(fp);
+    std::vector<double> a;
+    if ((long long)m * n == 0) return a;
+    a.resize((size_t)m * n);
+    for (int i = 0; i < m; i++) {
+        int t = read_int(fp);
+        dprint(2, "\ni=%d", t);
+        if (t != i + 1) die("wrong row index");
+        int col = 0;
+        for (int j = 0; j < p; j++) {
+            t = read_int(fp);
+            dprint(2, "\n%d", t);
+            if (t != j + 1) die("wrong column index");
+            int reps = read_int(fp);
+            double x = read_double(fp);
+            dprint(2, " %d %lg", reps, x);
+            skip_line(fp);  // only the first three columns of a pattern line are used
+            for (int k = 0; k < reps; k++) {
+                if (col >= n) die("too many repeats");
+                a[(size_t)i * n + col++] = x;
+            }
+        }
+        if (col != n) die("too few repeats");
+    }
+    *mp = m;
+    *np = n;
+    return a;
+}
+
+std::vector<double> read_mat_molphy(FILE *fp, int *mp, int *np) {
+    int m = read_int(fp), n = read_int(fp);
+    skip_line(fp);
+    if (*mp > 0 && *mp != m) die("size of rows mismatch in mat");
+    if (*np > 0 && *np != n) die("size of columns mismatch in mat");
+    std::vector<double> a;
+    if ((long long)m * n == 0) return a;
+    a.resize((size_t)m * n);
+    for (size_t e = 0; e < a.size(); e++) a[e] = read_double(fp);
+    *mp = m;
+    *np = n;
+    return a;
+}
+
+std::vector<double> read_mat_puzzle(FILE *fp, int *mp, int *np) {
+    int m = read_int(fp), n = read_int(fp);
+    dprint(2, "\nm=%d n=%d", m, n);
+    skip_line(fp);
+    if (*mp > 0 && *mp != m) die("size of rows mismatch in mat");
+    if (*np > 0 && *np != n) die("size of columns mismatch in mat");
+    std::vector<double> a;
+    if ((long long)m * n == 0) return a;
+    a.resize((size_t)m * n);
+    for (int i = 0; i < m; i++) {
+        skip_junk(fp);
+        skip_word(fp);  // tree label
+        dprint(2, "\ni=%d", i + 1);
+        for (int j = 0; j < n; j++) {
+            a[(size_t)i * n + j] = read_double(fp);
+            dprint(2, "\n%d %lg", j + 1, a[(size_t)i * n + j]);
+        }
+    }
+    *mp = m;
+    *np = n;
+    return a;
+}
+
+// read up to `length` characters of the current line (the newline is consumed only if
+// reached); returns the number of characters stored              (src/freadmat.c:156-167)
+static int read_line_prefix(FILE *fp, char *buf, int length) {
+    int i;
+    for (i = 0; i < length; i++) {
+        int c = getc(fp);
+        if (c == EOF || c == '\n') break;
+        buf[i] = (char)c;
+    }
+    return i;
+}
+static int read_int_or_zero(FILE *fp) {
+    int x = 0;
+    skip_junk(fp);
+    if (fscanf(fp, "%d", &x) != 1) x = 0;
+    return x;
+}
+static bool line_starts_with(FILE *fp, const char *head) {
+    // the reference reads sizeof(head) characters (one more than strlen) and requires that
+    // many to be present before comparing the first strlen(head)
+    const int want = (int)strlen(head) + 1;
+    std::vector<char> buf(want + 1, 0);
+    int r = read_line_prefix(fp, buf.data(), want);
+    skip_line(fp);
+    return r == want && strncmp(head, buf.data(), want - 1) == 0;
+}
+
+static std::vector<double> rows_to_matrix(const std::vector<std::vector<double>> &rows, int *mp, int *np) {
+    int m = (int)rows.size();
+    if (*mp > 0 && *mp != m) die("size of rows mismatch in mat");
+    *mp = m;
+    std::vector<double> a;
+    for (auto &r : rows) a.insert(a.end(), r.begin(), r.end());
+    return a;
+}
+
+// PAUP "Single-site" blocks                                       (src/freadmat.c:205-233)
+static std::vector<double> read_mat_paup_blocks(FILE *fp, int *mp, int *np) {
+    std::vector<std::vector<double>> rows;
+    for (;;) {
+        bool found = false;
+        while (!feof(fp) && !ferror(fp)) {
+            skip_junk(fp);
+            if (line_starts_with(fp, "Single-site")) {
+                found = true;
+                break;
+            }
+        }
+        if (!found) break;
+        std::vector<double> v;
+        for (; !feof(fp) && !ferror(fp); skip_junk(fp)) {
+            int t = read_int_or_zero(fp);
+            if (t != (int)v.size() + 1) break;
+            v.push_back(read_double(fp));
+        }
+        if (*np > 0 && *np != (int)v.size()) die("size of columns mismatch in mat");
+        *np = (int)v.size();
+        rows.push_back(v);
+    }
+    return rows_to_matrix(rows, mp, np);
+}
+
+// PAUP tab-separated table, values negated, gaps dropped           (src/freadmat.c:235-279)
+static std::vector<double> read_mat_paup_table(FILE *fp, int *mp, int *np) {
+    std::vector<std::vector<double>> rows;
+    std::vector<double> v;
+    while (!feof(fp) && !ferror(fp)) {
+        int c = getc(fp);
+        if (c == '#') {
+            skip_line(fp);
+            continue;
+        }
+        if (c == '\t') {
+            (void)read_int_or_zero(fp);
+            skip_junk(fp);
+            double t;
+            int d = getc(fp);
+            if (d == '-') t = -1.0;  // a gap column
+            else {
+                ungetc(d, fp);
+                t = read_double(fp);
+            }
+            if (t > 0) v.push_back(-t);
+            skip_line(fp);
+        } else {
+            skip_line(fp);
+            if (!v.empty()) {
+                if (*np > 0 && *np != (int)v.size()) die("size of columns mismatch in mat");
+                *np = (int)v.size();
+                rows.push_back(v);
+                v.clear();
+            }
+        }
+    }
+    return rows_to_matrix(rows, mp, np);
+}
+
+std::vector<double> read_mat_paup(FILE *fp, int *mp, int *np) {
+    const char *h2 = "Tree\t-lnL\tSite", *h3 = "Tree\tLength\tCh";
+    const int want2 = (int)strlen(h2) + 1, want3 = (int)strlen(h3) + 1;
+    char buf[32] = {0};
+    int r = read_line_prefix(fp, buf, want2);
+    skip_line(fp);
+    if ((r == want2 && strncmp(h2, buf, want2 - 1) == 0) || (r == want3 && strncmp(h3, buf, want3 - 1) == 0))
+        return read_mat_paup_table(fp, mp, np);
+    return read_mat_paup_blocks(fp, mp, np);
+}
+
+// PhyML: blocks headed "Site   P(D|M)", value log(P)               (src/freadmat.c:304-360)
+std::vector<double> read_mat_phyml(FILE *fp, int *mp, int *np) {
+    std::vector<std::vector<double>> rows;
+    for (;;) {
+        bool found = false;
+        while (!feof(fp) && !ferror(fp)) {
+            skip_junk(fp);
+            if (line_starts_with(fp, "Site   P(D|M)")) {
+                found = true;
+                break;
+            }
+        }
+        if (!found) break;
+        std::vector<double> v;
+        while (!feof(fp) && !ferror(fp)) {
+            int t = read_int_or_zero(fp);
+            if (t == 0) break;
+            double x = read_double(fp);
+            skip_line(fp);
+            v.push_back(log(x));
+        }
+        if (!v.empty()) {
+            if (*np > 0 && *np != (int)v.size()) die("size of columns mismatch in mat");
+            *np = (int)v.size();
+        }
+        rows.push_back(v);
+    }
+    return rows_to_matrix(rows, mp, np);
+}
+
+// ------------------------------------------------------------------ sort
+void sort_with_order(std::vector<double> &x, std::vector<int> *order) {
+    // src/misc.c:657-700: same partition scheme as psort_order, on values
+    const int dim = (int)x.size();
+    std::vector<int> ord(dim);
+    for (int i = 0; i < dim; i++) ord[i] = i;
+    if (dim > 1) {
+        int stack[64], sp = 0, l = 0, r = dim - 1;
+        for (;;) {
+            while (r > l) {
+                int k = (r + l) / 2;
+                const double v = x[k];
+                int i = l - 1, j = r + 1;
+                for (;;) {
+                    while (i < r && x[++i] <= v) {}
+                    while (j > l && x[--j] >= v) {}
+                    if (i > j) break;
+                    if (i == r) j = k; else if (j == l) i = k;
+                    std::swap(x[i], x[j]);
+                    std::swap(ord[i], ord[j]);
+                    if (i == r) { j = r - 1; break; } else if (j == l) { i = l + 1; break; }
+                }
+                if (j - l > r - i) { stack[sp++] = l; stack[sp++] = j; l = i; }
+                else { stack[sp++] = i; stack[sp++] = r; r = j; }
+            }
+            if (sp == 0) break;
+            r = stack[--sp];
+            l = stack[--sp];
+        }
+    }
+    if (order) *order = ord;
+}
+
+}  // namespace refio

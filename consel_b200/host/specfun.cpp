@@ -1,0 +1,142 @@
+#include "specfun.h"
+
+#include <cmath>
+
+#include "refio.h"
+
+namespace specfun {
+
+double dnorm(double x) { return 0.398942280401432677939946059934 * exp(-0.5 * x * x); }
+
+// ln Gamma(x), Lanczos g=5 n=6 (NR 6.1)
+static double lngamma(double xx) {
+    static const double cof[6] = {76.18009172947146,   -86.50532032941677,   24.01409824083091,
+                                  -1.231739572450155,  0.1208650973866179e-2, -0.5395239384953e-5};
+    double x = xx, y = xx;
+    double tmp = x + 5.5;
+    tmp -= (x + 0.5) * log(tmp);
+    double ser = 1.000000000190015;
+    for (int j = 0; j <= 5; j++) ser += cof[j] / ++y;
+    return -tmp + log(2.5066282746310005 * ser / x);
+}
+
+static const int kItMax = 1000;
+static const double kEps = 3.0e-7, kFpMin = 1.0e-30;
+
+// P(a,x) by its series (NR 6.2 gser)
+static double gamma_series(double a, double x) {
+    const double gln = lngamma(a);
+    if (x <= 0.0) {
+        if (x < 0.0) refio::die("x less than 0 in routine gser");
+        return 0.0;
+    }
+    double ap = a, sum = 1.0 / a, del = sum;
+    for (int n = 1; n <= kItMax; n++) {
+        ++ap;
+        del *= x / ap;
+        sum += del;
+        if (fabs(del) < fabs(sum) * kEps) return sum * exp(-x + a * log(x) - gln);
+    }
+    refio::die("a too large, ITMAX too small in routine gser");
+}
+
+// Q(a,x) by the modified Lentz continued fraction (NR 6.2 gcf)
+static double gamma_cfrac(double a, double x) {
+    const double gln = lngamma(a);
+    double b = x + 1.0 - a, c = 1.0 / kFpMin, d = 1.0 / b, h = d;
+    int i;
+    for (i = 1; i <= kItMax; i++) {
+        double an = -i * (i - a);
+        b += 2.0;
+        d = an * d + b;
+        if (fabs(d) < kFpMin) d = kFpMin;
+        c = b + an / c;
+        if (fabs(c) < kFpMin) c = kFpMin;
+        d = 1.0 / d;
+        double del = d * c;
+        h *= del;
+        if (fabs(del - 1.0) < kEps) break;
+    }
+    if (i > kItMax) refio::die("a too large, ITMAX too small in gcf");
+    return exp(-x + a * log(x) - gln) * h;
+}
+
+static double gammp(double a, double x) {
+    if (x < 0.0 || a <= 0.0) refio::die("Invalid arguments in routine gammp");
+    return x < a + 1.0 ? gamma_series(a, x) : 1.0 - gamma_cfrac(a, x);
+}
+static double gammq(double a, double x) {
+    if (x < 0.0 || a <= 0.0) refio::die("Invalid arguments in routine gammq");
+    return x < a + 1.0 ? 1.0 - gamma_series(a, x) : gamma_cfrac(a, x);
+}
+static double erfc_nr(double x) { return x < 0.0 ? 1.0 + gammp(0.5, x * x) : gammq(0.5, x * x); }
+
+double pnorm(double x) { return 0.5 * erfc_nr(-x * 0.707106781186547524400844362105); }
+
+double qnorm(double p) {
+    double lo = -37.0, hi = 37.0, z = 0.0;
+    if (p <= 0.0 || p >= 1.0) return 0.0;
+    while (hi - lo > 1e-10) {
+        if (pnorm(z) > p) hi = z; else lo = z;
+        z = (hi + lo) * 0.5;
+    }
+    return z;
+}
+
+double poz(double z) {
+    double x;
+    if (z == 0.0) {
+        x = 0.0;
+    } else {
+        double y = 0.5 * fabs(z);
+        if (y >= 3.0) {
+            x = 1.0;
+        } else if (y < 1.0) {
+            double w = y * y;
+            x = ((((((((0.000124818987 * w - 0.001075204047) * w + 0.005198775019) * w - 0.019198292004) * w +
+                     0.059054035642) * w - 0.151968751364) * w + 0.319152932694) * w - 0.531923007300) * w +
+                 0.797884560593) * y * 2.0;
+        } else {
+            y -= 2.0;
+            x = (((((((((((((-0.000045255659 * y + 0.000152529290) * y - 0.000019538132) * y - 0.000676904986) * y +
+                          0.001390604284) * y - 0.000794620820) * y - 0.002034254874) * y + 0.006549791214) * y -
+                      0.010557625006) * y + 0.011630447319) * y - 0.009279453341) * y + 0.005353579108) * y -
+                  0.002141268741) * y + 0.000535310849) * y + 0.999936657524;
+        }
+    }
+    return z > 0.0 ? (x + 1.0) * 0.5 : (1.0 - x) * 0.5;
+}
+
+static inline double ex20(double x) { return x < -20.0 ? 0.0 : exp(x); }
+
+double pochisq(double x, int df) {
+    if (x <= 0.0 || df < 1) return 1.0;
+    const double a = 0.5 * x;
+    const bool even = (2 * (df / 2)) == df;
+    double y = 0.0;
+    if (df > 1) y = ex20(-a);
+    double s = even ? y : 2.0 * poz(-sqrt(x));
+    if (df <= 2) return s;
+    const double xm = 0.5 * (df - 1.0);
+    double z = even ? 1.0 : 0.5;
+    if (a > 20.0) {
+        double e = even ? 0.0 : 0.5723649429247000870717135;
+        const double c = log(a);
+        while (z <= xm) {
+            e = log(z) + e;
+            s += ex20(c * z - a - e);
+            z += 1.0;
+        }
+        return s;
+    }
+    double e = even ? 1.0 : 0.5641895835477562869480795 / sqrt(a);
+    double c = 0.0;
+    while (z <= xm) {
+        e = e * (a / z);
+        c = c + e;
+        z += 1.0;
+    }
+    return c * y + s;
+}
+
+}  // namespace specfun

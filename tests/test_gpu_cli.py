@@ -1,0 +1,80 @@
+"""Drop-in command lines on the GPU: our makermt -> consel -> catpv against the files the
+unmodified reference programs wrote for the same seeds (tests/golden)."""
+import shutil
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parent.parent
+BIN = ROOT / "consel_b200" / "bin"
+
+
+def run(prog, args, cwd):
+    r = subprocess.run([str(BIN / prog)] + [str(a) for a in args], cwd=cwd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    return r.stdout
+
+
+def same_numbers(a: Path, b: Path, orc):
+    x, y = orc.read_text_blocks(a), orc.read_text_blocks(b)
+    assert len(x) == len(y)
+    assert np.allclose(x, y, rtol=2e-9, atol=1e-12, equal_nan=True)
+
+
+@pytest.mark.parametrize("case", ["g100", "tiny"])
+def test_makermt_consel_catpv_pipeline(case, gold, orc, tmp_path):
+    if case == "g100":
+        shutil.copy(gold / "mam15.lnf", tmp_path / "mam15.lnf")
+        out = run("makermt", ["-s", "1234", "-b", "0.01", "--paml", "mam15", "g100"], tmp_path)
+    else:
+        shutil.copy(gold / "tiny.mt", tmp_path / "tiny.mt")
+        shutil.copy(gold / "tiny.pa", tmp_path / "tiny.pa")
+        out = run("makermt", ["-s", "7", "-p", "tiny", "tiny"], tmp_path)
+    assert "# exit normally" in out and "# start generating total" in out
+    assert (tmp_path / f"{case}.rmt").read_bytes() == (gold / f"{case}.rmt").read_bytes()
+    assert (tmp_path / f"{case}.vt").read_bytes() == (gold / f"{case}.vt").read_bytes()
+    out = run("consel", ["-r", "-c", case], tmp_path)
+    assert "# exit normally" in out
+    assert (tmp_path / f"{case}.rep").read_bytes() == (gold / f"{case}.rep").read_bytes()
+    assert (tmp_path / f"{case}.cnt").read_bytes() == (gold / f"{case}.cnt").read_bytes()
+    for ext in ("pv", "ci"):
+        same_numbers(tmp_path / f"{case}.{ext}", gold / f"{case}.{ext}", orc)
+    txt = run("catpv", [case], tmp_path)
+    assert txt == (gold / f"{case}.txt").read_text()
+
+
+def test_consel_with_edge_associations(gold, orc, tmp_path):
+    shutil.copy(gold / "g100.rmt", tmp_path / "g100.rmt")
+    shutil.copy(gold / "mam15.ass", tmp_path / "mam15.ass")
+    run("consel", ["-a", "mam15", "-r", "-c", "g100", "g100e"], tmp_path)
+    assert (tmp_path / "g100e.rep").read_bytes() == (gold / "g100e.rep").read_bytes()
+    assert (tmp_path / "g100e.cnt").read_bytes() == (gold / "g100e.cnt").read_bytes()
+    same_numbers(tmp_path / "g100e.pv", gold / "g100e.pv", orc)
+    same_numbers(tmp_path / "g100e.ci", gold / "g100e.ci", orc)
+    assert run("catpv", ["g100e"], tmp_path) == (gold / "g100e.txt").read_text()
+
+
+def test_cli_error_protocol(tmp_path):
+    r = subprocess.run([str(BIN / "makermt"), "--bogus"], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 1 and "#! Terminated: error in command line." in r.stdout
+    r = subprocess.run([str(BIN / "consel"), "nofile"], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 1 and "#! Terminated: cant open nofile.rmt." in r.stdout
+
+
+@pytest.mark.skipif(not (ROOT / "oracle" / "_ref" / "makermt").exists(), reason="oracle/_ref not built")
+def test_full_pipeline_against_fresh_reference_run(gold, orc, tmp_path):
+    """k10s-sized run (10 x 1000 replicates): reference and ours side by side, same seed."""
+    shutil.copy(gold / "mam15.lnf", tmp_path / "mam15.lnf")
+    orc.write_pa(tmp_path / "k.pa", [0.5, 0.6, 0.7, 0.8, 0.9, 1.0, 1.1, 1.2, 1.3, 1.4], [1000] * 10)
+    orc.run_ref("makermt", ["-s", "99", "-p", "k", "--paml", "mam15", "ref"], tmp_path)
+    orc.run_ref("consel", ["-r", "-c", "ref"], tmp_path)
+    run("makermt", ["-s", "99", "-p", "k", "--paml", "mam15", "our"], tmp_path)
+    run("consel", ["-r", "-c", "our"], tmp_path)
+    for ext in ("rmt", "rep", "cnt"):
+        assert (tmp_path / f"our.{ext}").read_bytes() == (tmp_path / f"ref.{ext}").read_bytes(), ext
+    same_numbers(tmp_path / "our.pv", tmp_path / "ref.pv", orc)
+    same_numbers(tmp_path / "our.ci", tmp_path / "ref.ci", orc)
+    assert run("catpv", ["our"], tmp_path).replace("our.pv", "X") == orc.run_ref("catpv", ["ref"], tmp_path).replace("ref.pv", "X")

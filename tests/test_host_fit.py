@@ -1,0 +1,119 @@
+"""The host-side AU fit (consel_b200/host/aufit.cpp) driven exactly like our consel
+drives it — lockstep threshold iterations fed by row counts — but with the counts taken
+on the CPU from the reference's golden sorted .rep rows, so the fit arithmetic is pinned
+against the reference's .pv / .ci digits without a GPU."""
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+SO = ROOT / "consel_b200" / "bin" / "libaufit_test.so"
+
+pytestmark = pytest.mark.skipif(not SO.exists(), reason="host programs not built (run __graft_entry__.build())")
+
+
+class Opts(C.Structure):
+    _fields_ = [("fitmode", C.c_int), ("kappa", C.c_double), ("rrmin", C.c_double), ("rrmax", C.c_double),
+                ("dfmin", C.c_int)]
+
+
+@pytest.fixture(scope="module")
+def fit():
+    lib = C.CDLL(str(SO))
+    for f in ("aufit_vc_new", "aufit_ci_new"):
+        getattr(lib, f).restype = C.c_void_p
+    for f in ("aufit_vc_x", "aufit_ci_x", "aufit_pochisq", "aufit_pnorm", "aufit_qnorm"):
+        getattr(lib, f).restype = C.c_double
+    lib.aufit_vc_new.argtypes = [C.c_double, C.c_double]
+    lib.aufit_ci_new.argtypes = [C.c_double] * 4
+    lib.aufit_pochisq.argtypes = [C.c_double, C.c_int]
+    lib.aufit_pnorm.argtypes = [C.c_double]
+    lib.aufit_qnorm.argtypes = [C.c_double]
+    for f in ("aufit_vc_free", "aufit_vc_x", "aufit_vc_done", "aufit_vc_get", "aufit_ci_free", "aufit_ci_x",
+              "aufit_ci_done", "aufit_ci_get"):
+        getattr(lib, f).argtypes = [C.c_void_p] + ([C.POINTER(C.c_double)] if f.endswith("get") else [])
+    for f in ("aufit_vc_step", "aufit_ci_step"):
+        getattr(lib, f).argtypes = [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                    C.c_int, C.POINTER(Opts)]
+    return lib
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.POINTER(C.c_double))
+
+
+@pytest.mark.parametrize("name", ["g100", "tiny", "g100e"])
+def test_au_pvalues_and_confidence_limits_match_reference(fit, orc, gold, name):
+    rep = orc.read_rep(gold / f"{name}.rep")
+    pv = orc.read_pv(gold / f"{name}.pv")
+    ci_txt = orc.read_text_blocks(gold / f"{name}.ci")
+    rr = np.ascontiguousarray(rep["rr"], dtype=np.float64)
+    bb = np.ascontiguousarray(rep["bb"], dtype=np.float64)
+    kk = len(rr)
+    cm = len(rep["order"])
+    i0 = orc.find_i0(rr)
+    opts = Opts(1, 1.0, 0.0, 100.0, 0)
+    got_pv = np.zeros((cm, 2)); got_se = np.zeros((cm, 2)); got_ax = np.zeros((cm, 7))
+    for i in range(cm):
+        rows = [rep["stats"][k][i] for k in range(kk)]
+        h = fit.aufit_vc_new(float(rows[i0][int(bb[i0]) // 2]), 0.0)
+        while not fit.aufit_vc_done(h):
+            x = fit.aufit_vc_x(h)
+            cnts = np.array([orc.cntdist(rows[k], x, 3) for k in range(kk)])
+            fit.aufit_vc_step(h, _dp(cnts), _dp(rr), _dp(bb), kk, C.byref(opts))
+        out = np.zeros(11)
+        fit.aufit_vc_get(h, _dp(out))
+        fit.aufit_vc_free(h)
+        ret = int(out[10])
+        got_pv[i] = out[0], out[2]
+        got_se[i] = out[1], out[3]
+        pf = fit.aufit_pochisq(out[4], int(out[5])) if ret == 0 else 0.0
+        beta = out[7:10] if ret == 0 else np.zeros(3)
+        got_ax[i] = pf, out[4], out[5], beta[0], beta[1], out[6], beta[2]
+    tol = dict(rtol=6e-9, atol=1e-12)
+    assert np.allclose(got_pv, pv["pv"][:, 6:8], **tol), (got_pv, pv["pv"][:, 6:8])
+    assert np.allclose(got_se, pv["se"][:, 6:8], **tol)
+    assert np.allclose(got_ax, pv["ax"], **tol), (got_ax, pv["ax"])
+
+    # confidence limits: .ci holds ITEM, STAT, ALPHA then CI SE EI CI0 SE0 EI0 (cm x nalpha each)
+    p = 0
+    def vec():
+        nonlocal p
+        m = int(ci_txt[p]); p += 1
+        a = np.array(ci_txt[p:p + m]); p += m
+        return a
+    def mat():
+        nonlocal p
+        m, n = int(ci_txt[p]), int(ci_txt[p + 1]); p += 2
+        a = np.array(ci_txt[p:p + m * n]).reshape(m, n); p += m * n
+        return a
+    vec(); vec()
+    alpha = vec()
+    want = [mat() for _ in range(6)]
+    got = [np.zeros((cm, len(alpha))) for _ in range(6)]
+    for i in range(cm):
+        rows = [rep["stats"][k][i] for k in range(kk)]
+        for a, al in enumerate(alpha):
+            for which, kappa in enumerate((1.0, -1.0)):
+                h = fit.aufit_ci_new(float(rows[i0][0]), float(rows[i0][-1]), float(al), kappa)
+                while not fit.aufit_ci_done(h):
+                    x = fit.aufit_ci_x(h)
+                    cnts = np.array([orc.cntdist(rows[k], x, 3) for k in range(kk)])
+                    fit.aufit_ci_step(h, _dp(cnts), _dp(rr), _dp(bb), kk, C.byref(opts))
+                out = np.zeros(4)
+                fit.aufit_ci_get(h, _dp(out))
+                fit.aufit_ci_free(h)
+                for c in range(3):
+                    got[3 * which + c][i, a] = out[c]
+    for g, w in zip(got, want):
+        assert np.allclose(g, w, rtol=6e-9, atol=1e-12, equal_nan=True), (g, w)
+
+
+def test_distribution_functions(fit):
+    assert fit.aufit_pnorm(0.0) == 0.5
+    assert abs(fit.aufit_pnorm(1.959963984540054) - 0.975) < 1e-7
+    assert abs(fit.aufit_qnorm(0.975) - 1.959963984540054) < 1e-6
+    assert abs(fit.aufit_pochisq(3.841458820694124, 1) - 0.05) < 1e-5
+    assert fit.aufit_pochisq(0.0, 3) == 1.0
