@@ -44,14 +44,16 @@ struct PhaseTimer {
         cudaEventCreate(&t1);
         cudaEventRecord(t0, st);
     }
-    void begin(int phase) {
+    cudaStream_t cur = nullptr;
+    void begin(int phase, cudaStream_t on = nullptr) {
+        cur = on ? on : st;
         Span sp{phase, nullptr, nullptr};
         cudaEventCreate(&sp.a);
         cudaEventCreate(&sp.b);
-        cudaEventRecord(sp.a, st);
+        cudaEventRecord(sp.a, cur);
         spans.push_back(sp);
     }
-    void end() { cudaEventRecord(spans.back().b, st); }
+    void end() { cudaEventRecord(spans.back().b, cur); }
     // call after the stream has been synchronised
     void finish(double *ms5) {
         for (int i = 0; i < 6; i++) ms5[i] = 0;
@@ -172,12 +174,26 @@ static int mt_prepare(unsigned long seed, unsigned long long stream_offset, unsi
 
 struct Workspace {
     uint32_t *d_idx = nullptr;
-    unsigned long long *d_counts = nullptr;
+    unsigned long long *d_counts[2] = {nullptr, nullptr};
     int *d_err = nullptr;
+    cudaEvent_t hist_done[2] = {nullptr, nullptr}, contract_done[2] = {nullptr, nullptr}, idx_ready = nullptr;
+    Workspace() {
+        for (int i = 0; i < 2; i++) {
+            cudaEventCreateWithFlags(&hist_done[i], cudaEventDisableTiming);
+            cudaEventCreateWithFlags(&contract_done[i], cudaEventDisableTiming);
+        }
+        cudaEventCreateWithFlags(&idx_ready, cudaEventDisableTiming);
+    }
     ~Workspace() {
         dev_free(d_idx);
-        dev_free(d_counts);
+        dev_free(d_counts[0]);
+        dev_free(d_counts[1]);
         dev_free(d_err);
+        for (int i = 0; i < 2; i++) {
+            cudaEventDestroy(hist_done[i]);
+            cudaEventDestroy(contract_done[i]);
+        }
+        cudaEventDestroy(idx_ready);
     }
 };
 
@@ -196,6 +212,11 @@ static int scaleboot_core(const DevMatrix &m, int S, const int *bn, const int *b
         set_error(CGPU_EINVAL, "unknown rng_mode %d", rng_mode);
         return CGPU_EINVAL;
     }
+    for (int s = 0; s < S; s++)
+        if (bn[s] <= 0 || bb[s] < 0) {
+            set_error(CGPU_EINVAL, "scale %d: bn=%d bb=%d", s, bn[s], bb[s]);
+            return CGPU_EINVAL;
+        }
     const int n = m.n, NP = m.NP;
     // batch size: bound the index and count buffers (device memory is 180 GB; keep the
     // workspace near 8 GB so several processes can share a GPU in tests)
@@ -209,11 +230,13 @@ static int scaleboot_core(const DevMatrix &m, int S, const int *bn, const int *b
     const int batch = (int)std::min<long long>(cap, std::max(64, (max_nb + 63) / 64 * 64));
 
     Workspace ws;
-    CGPU_CUDA(dev_alloc(&ws.d_counts, (size_t)(batch / 8) * NP * 8));
+    for (int i = 0; i < 2; i++) {
+        CGPU_CUDA(dev_alloc(&ws.d_counts[i], (size_t)(batch / 8) * NP * 8));
+        // padding sites and replicates must read as zero counts
+        CGPU_CUDA(cudaMemsetAsync(ws.d_counts[i], 0, (size_t)(batch / 8) * NP * 8, st));
+    }
     CGPU_CUDA(dev_alloc(&ws.d_err, sizeof(int)));
     CGPU_CUDA(cudaMemsetAsync(ws.d_err, 0, sizeof(int), st));
-    // padding sites and replicates must read as zero counts
-    CGPU_CUDA(cudaMemsetAsync(ws.d_counts, 0, (size_t)(batch / 8) * NP * 8, st));
 
     MtPlan plan;
     struct PlanGuard {
@@ -222,40 +245,69 @@ static int scaleboot_core(const DevMatrix &m, int S, const int *bn, const int *b
     } guard{plan};
     std::vector<unsigned long long> base(S + 1, 0);
     for (int s = 0; s < S; s++) base[s + 1] = base[s] + (unsigned long long)bb[s] * (unsigned long long)bn[s];
+    // When the whole run's index stream fits the workspace and this process owns every
+    // replicate, ONE draw launch covers all chunks (fills the machine; per-scale launches
+    // have only ~100-200 chunk CTAs).  Otherwise indices are produced batch by batch.
+    bool idx_whole_run = false;
     if (rng_mode == CGPU_RNG_MT19937) {
-        CGPU_CUDA(dev_alloc(&ws.d_idx, (size_t)batch * max_bn * sizeof(uint32_t)));
+        const unsigned long long idx_budget = (unsigned long long)24 << 30;
+        idx_whole_run = G().shard_world == 1 && base[S] * 4ull <= idx_budget && base[S] > 0;
+        const size_t idx_elems = idx_whole_run ? (size_t)base[S] : (size_t)batch * max_bn;
+        CGPU_CUDA(dev_alloc(&ws.d_idx, idx_elems * sizeof(uint32_t)));
         pt.begin(1);
         CGPU_TRY(mt_prepare(seed, stream_offset, base[S], &plan, st));
+        if (idx_whole_run)
+            CGPU_TRY(launch_mt_draw(plan.d_states, plan.chunk_log2, 0, (int)plan.nchunks, 0, base[S], (uint32_t)n, ws.d_idx, st));
         pt.end();
     }
 
+    // Two-stream software pipeline over (scale, batch) items: the histogram of item i+1
+    // (shared-memory bound) runs on the aux stream while the contraction of item i (FP64
+    // bound) runs on the main stream; the two count buffers alternate.  With per-batch
+    // index generation (sharded or very long streams) everything stays on one stream.
+    static const bool no_overlap = getenv("CGPU_NO_OVERLAP") != nullptr;
+    const bool overlap = !no_overlap && (rng_mode == CGPU_RNG_PHILOX || idx_whole_run);
+    cudaStream_t aux = overlap ? G().stream2 : st;
+    if (overlap) {
+        CGPU_CUDA(cudaEventRecord(ws.idx_ready, st));  // memsets, jump tree and index stream are queued on st
+        CGPU_CUDA(cudaStreamWaitEvent(aux, ws.idx_ready, 0));
+    }
+    int item = 0;
     for (int s = 0; s < S; s++) {
-        if (bn[s] <= 0 || bb[s] < 0) {
-            set_error(CGPU_EINVAL, "scale %d: bn=%d bb=%d", s, bn[s], bb[s]);
-            return CGPU_EINVAL;
-        }
         const double r = (double)bn[s] / (double)n;  // src/makermt.c:48
-        for (int a = 0; a < reps->nb[s]; a += batch) {
+        for (int a = 0; a < reps->nb[s]; a += batch, item++) {
             const int nbat = std::min(batch, reps->nb[s] - a);
             const int bA = reps->b0[s] + a;  // global replicate index of the batch
+            const int buf = item & 1;
+            if (overlap && item >= 2) CGPU_CUDA(cudaStreamWaitEvent(aux, ws.contract_done[buf], 0));
             if (rng_mode == CGPU_RNG_MT19937) {
                 const unsigned long long lo = base[s] + (unsigned long long)bA * bn[s];
                 const unsigned long long hi = lo + (unsigned long long)nbat * bn[s];
-                const unsigned long long c0 = lo >> plan.chunk_log2, c1 = (hi - 1) >> plan.chunk_log2;
-                pt.begin(1);
-                CGPU_TRY(launch_mt_draw(plan.d_states, plan.chunk_log2, c0, (int)(c1 - c0 + 1), lo, hi, (uint32_t)n, ws.d_idx, st));
-                pt.end();
-                pt.begin(2);
-                CGPU_TRY(launch_hist_from_idx(ws.d_idx, n, NP, bn[s], nbat, ws.d_counts, ws.d_err, st));
+                const uint32_t *idx_src = ws.d_idx;
+                if (idx_whole_run) {
+                    idx_src = ws.d_idx + lo;
+                } else {
+                    const unsigned long long c0 = lo >> plan.chunk_log2, c1 = (hi - 1) >> plan.chunk_log2;
+                    pt.begin(1);
+                    CGPU_TRY(launch_mt_draw(plan.d_states, plan.chunk_log2, c0, (int)(c1 - c0 + 1), lo, hi, (uint32_t)n, ws.d_idx, st));
+                    pt.end();
+                }
+                pt.begin(2, aux);
+                CGPU_TRY(launch_hist_from_idx(idx_src, n, NP, bn[s], nbat, ws.d_counts[buf], ws.d_err, aux));
                 pt.end();
             } else {
-                pt.begin(2);
-                CGPU_TRY(launch_hist_philox((unsigned long long)seed, s, bA, n, NP, bn[s], nbat, ws.d_counts, ws.d_err, st));
+                pt.begin(2, aux);
+                CGPU_TRY(launch_hist_philox((unsigned long long)seed, s, bA, n, NP, bn[s], nbat, ws.d_counts[buf], ws.d_err, aux));
                 pt.end();
             }
+            if (overlap) {
+                CGPU_CUDA(cudaEventRecord(ws.hist_done[buf], aux));
+                CGPU_CUDA(cudaStreamWaitEvent(st, ws.hist_done[buf], 0));
+            }
             pt.begin(3);
-            CGPU_TRY(launch_contract(m, ws.d_counts, nbat, r, reps->d_rep[s], reps->nb[s], a, sum_mode, st));
+            CGPU_TRY(launch_contract(m, ws.d_counts[buf], nbat, r, reps->d_rep[s], reps->nb[s], a, sum_mode, st));
             pt.end();
+            if (overlap) CGPU_CUDA(cudaEventRecord(ws.contract_done[buf], st));
         }
     }
     int h_err = 0;
@@ -358,6 +410,7 @@ int cgpu_init(int device) {
     g.device = device;
     g.sm_count = prop.multiProcessorCount;
     CGPU_CUDA(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+    CGPU_CUDA(cudaStreamCreateWithFlags(&g.stream2, cudaStreamNonBlocking));
     {
         // keep freed blocks in the default stream-ordered pool: the per-call workspaces
         // (index/count buffers, replicate blocks) are then recycled without a cudaMalloc
@@ -379,6 +432,8 @@ void cgpu_shutdown(void) {
     cudaStreamSynchronize(g.stream);
     dev_free(g.d_jump_table);
     cudaStreamDestroy(g.stream);
+    cudaStreamDestroy(g.stream2);
+    g.stream2 = nullptr;
     g.d_jump_table = nullptr;
     g.stream = nullptr;
     g.inited = false;
@@ -509,8 +564,8 @@ int cgpu_resample_counts(int n, int S, const int *bn, const int *bb, unsigned lo
     const int NP = pad_sites(n);
     Workspace ws;
     const size_t cbytes = (size_t)((nb + 7) / 8) * NP * 8;
-    CGPU_CUDA(dev_alloc(&ws.d_counts, cbytes));
-    CGPU_CUDA(cudaMemsetAsync(ws.d_counts, 0, cbytes, st));
+    CGPU_CUDA(dev_alloc(&ws.d_counts[0], cbytes));
+    CGPU_CUDA(cudaMemsetAsync(ws.d_counts[0], 0, cbytes, st));
     CGPU_CUDA(dev_alloc(&ws.d_err, sizeof(int)));
     CGPU_CUDA(cudaMemsetAsync(ws.d_err, 0, sizeof(int), st));
     MtPlan plan;
@@ -529,16 +584,16 @@ int cgpu_resample_counts(int n, int S, const int *bn, const int *bb, unsigned lo
         const unsigned long long lo = base + (unsigned long long)b0 * bn[s], hi = lo + (unsigned long long)nb * bn[s];
         const unsigned long long c0 = lo >> plan.chunk_log2, c1 = (hi - 1) >> plan.chunk_log2;
         CGPU_TRY(launch_mt_draw(plan.d_states, plan.chunk_log2, c0, (int)(c1 - c0 + 1), lo, hi, (uint32_t)n, ws.d_idx, st));
-        CGPU_TRY(launch_hist_from_idx(ws.d_idx, n, NP, bn[s], nb, ws.d_counts, ws.d_err, st));
+        CGPU_TRY(launch_hist_from_idx(ws.d_idx, n, NP, bn[s], nb, ws.d_counts[0], ws.d_err, st));
     } else if (rng_mode == CGPU_RNG_PHILOX) {
-        CGPU_TRY(launch_hist_philox((unsigned long long)seed, s, b0, n, NP, bn[s], nb, ws.d_counts, ws.d_err, st));
+        CGPU_TRY(launch_hist_philox((unsigned long long)seed, s, b0, n, NP, bn[s], nb, ws.d_counts[0], ws.d_err, st));
     } else {
         set_error(CGPU_EINVAL, "unknown rng_mode %d", rng_mode);
         return CGPU_EINVAL;
     }
     unsigned char *d_out = nullptr;
     CGPU_CUDA(dev_alloc(&d_out, (size_t)nb * n));
-    int rc = launch_counts_unpack(ws.d_counts, n, NP, nb, d_out, st);
+    int rc = launch_counts_unpack(ws.d_counts[0], n, NP, nb, d_out, st);
     int h_err = 0;
     if (rc == CGPU_OK) {
         cudaMemcpyAsync(counts, d_out, (size_t)nb * n, cudaMemcpyDeviceToHost, st);

@@ -71,6 +71,7 @@ struct Globals {
     int sm_count = 0;
     int shard_rank = 0, shard_world = 1;
     cudaStream_t stream = nullptr;
+    cudaStream_t stream2 = nullptr;  // aux stream of the resample/contract software pipeline
     uint32_t *d_jump_table = nullptr;  // (MT_MAXLOG+1) x 624 u32
     cudaEvent_t ev[8] = {};
     double last_ms[6] = {0, 0, 0, 0, 0, 0};

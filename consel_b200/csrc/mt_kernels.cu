@@ -38,7 +38,7 @@ __device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
 constexpr int JUMP_THREADS = 640;
 constexpr int JUMP_SEQ = MT_DEG + MT_N + 63;  // words of the regenerated sequence kept in smem
 
-__global__ void __launch_bounds__(JUMP_THREADS, 1)
+__global__ void __launch_bounds__(JUMP_THREADS, 2)
 mt_jump_kernel(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst,
                const uint32_t *__restrict__ poly, int words_per_slice) {
     extern __shared__ uint32_t sm[];

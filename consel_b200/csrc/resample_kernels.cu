@@ -18,6 +18,8 @@
 // Draw sources: the index buffer written by mt_draw_kernel (reference stream) or a
 // counter-based Philox4x32-10 keyed by (seed; scale, replicate) — Salmon, Moraes, Dror,
 // Shaw, "Parallel random numbers: as easy as 1, 2, 3", SC'11.
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include "cgpu_internal.h"
@@ -45,28 +47,58 @@ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint3
     return Philox4{{c0, c1, c2, c3}};
 }
 
-// one warp adds the site indices its lanes hold to a warp-private byte histogram
-__device__ __forceinline__ void warp_hist_add(unsigned char *hist, uint32_t k, bool valid, int lane,
-                                              int *overflow) {
-    unsigned active = __ballot_sync(0xffffffffu, valid);
-    if (valid) {
-        unsigned peers = __match_any_sync(active, k);
-        if (lane == __ffs(peers) - 1) {
-            unsigned v = hist[k] + __popc(peers);
-            if (v > 255u) *overflow = 1;
-            hist[k] = (unsigned char)v;
+// one warp adds the site indices its lanes hold to a warp-private byte histogram.
+//  HALGO 0  match.any + popcount: the first lane of each group of equal sites adds the
+//           group size (no atomics, no extra memory)
+//  HALGO 1  shared-memory atomic add on the 32-bit word that holds the byte
+//  HALGO 2  claim-and-verify: every pending lane writes its lane id into a tag byte of its
+//           site, re-reads it, and the lane that owns the tag increments; lanes that lost
+//           a duplicate retry (a site drawn m times in one 32-draw step takes m rounds).
+//           Plain byte loads/stores only; needs a second NP-byte array per warp.
+template <int HALGO>
+__device__ __forceinline__ void warp_hist_add(unsigned char *hist, unsigned char *tag, uint32_t k, bool valid,
+                                              int lane, int *overflow) {
+    if (HALGO == 0) {
+        unsigned active = __ballot_sync(0xffffffffu, valid);
+        if (valid) {
+            unsigned peers = __match_any_sync(active, k);
+            if (lane == __ffs(peers) - 1) {
+                unsigned v = hist[k] + __popc(peers);
+                if (v > 255u) *overflow = 1;
+                hist[k] = (unsigned char)v;
+            }
+        }
+        __syncwarp();
+    } else if (HALGO == 1) {
+        if (valid) {
+            const unsigned sh = (k & 3u) * 8u;
+            unsigned old = atomicAdd(reinterpret_cast<unsigned *>(hist) + (k >> 2), 1u << sh);
+            if (((old >> sh) & 0xffu) == 0xffu) *overflow = 1;
+        }
+    } else {
+        bool pending = valid;
+        while (__any_sync(0xffffffffu, pending)) {
+            if (pending) tag[k] = (unsigned char)lane;
+            __syncwarp();
+            if (pending && tag[k] == (unsigned char)lane) {
+                unsigned v = hist[k] + 1u;
+                if (v > 255u) *overflow = 1;
+                hist[k] = (unsigned char)v;
+                pending = false;
+            }
+            __syncwarp();
         }
     }
-    __syncwarp();
 }
 
 // SRC 0: indices from the buffer (replicate r of this launch at idx[r*bn ..));  SRC 1: Philox
-template <int SRC>
+template <int SRC, int HALGO>
 __global__ void __launch_bounds__(HIST_THREADS)
 hist_group_kernel(const uint32_t *__restrict__ idx, int n, int NP, int bn, int nb,
                   unsigned long long *__restrict__ counts, int *__restrict__ err,
                   uint32_t key0, uint32_t key1, uint32_t scale, uint32_t b_first) {
-    extern __shared__ unsigned char hsm[];  // 8 histograms of NP bytes
+    extern __shared__ unsigned char hsm[];  // 8 histograms of NP bytes (+ 8 tag arrays for HALGO 2)
+    unsigned char *tag = hsm + (size_t)8 * NP + (size_t)(threadIdx.x >> 5) * NP;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int ngroups = (nb + 7) / 8;
     for (int g = blockIdx.x; g < ngroups; g += gridDim.x) {
@@ -82,7 +114,7 @@ hist_group_kernel(const uint32_t *__restrict__ idx, int n, int NP, int bn, int n
                     int i = i0 + lane;
                     bool valid = i < bn;
                     uint32_t k = valid ? src[i] : 0u;
-                    warp_hist_add(hist, k, valid, lane, &overflow);
+                    warp_hist_add<HALGO>(hist, tag, k, valid, lane, &overflow);
                 }
             } else {
                 // draw i of replicate b is word (i & 3) of Philox(counter = (i >> 2, b, scale, 0))
@@ -93,7 +125,7 @@ hist_group_kernel(const uint32_t *__restrict__ idx, int n, int NP, int bn, int n
 #pragma unroll
                     for (int u = 0; u < 4; u++) {
                         bool valid = q * 4 + u < bn;
-                        warp_hist_add(hist, __umulhi(p.v[u], (uint32_t)n), valid, lane, &overflow);
+                        warp_hist_add<HALGO>(hist, tag, __umulhi(p.v[u], (uint32_t)n), valid, lane, &overflow);
                     }
                 }
             }
@@ -154,28 +186,51 @@ hist_global_kernel(const uint32_t *__restrict__ idx, int n, int NP, int bn, int 
     }
 }
 
+// CGPU_HIST_ALGO selects the in-warp conflict scheme (development A/B switch)
+static int hist_algo() {
+    static int v = [] {
+        const char *e = getenv("CGPU_HIST_ALGO");
+        return e ? atoi(e) : 1;
+    }();
+    return v;
+}
+
+template <int SRC, int HALGO>
+static int hist_group_launch(const uint32_t *d_idx, int n, int NP, int bn, int nb, unsigned long long *d_counts,
+                             int *d_err, uint32_t k0, uint32_t k1, uint32_t scale, uint32_t b_first, cudaStream_t st) {
+    auto kern = hist_group_kernel<SRC, HALGO>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        CGPU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * HIST_SMEM_SITES));
+        attr_done = true;
+    }
+    const int ngroups = (nb + 7) / 8;
+    const size_t smem = (size_t)8 * NP * (HALGO == 2 ? 2 : 1);
+    const int sms = G().sm_count > 0 ? G().sm_count : 148;
+    int per_sm = (int)std::min<size_t>(8, (220 * 1024) / smem);
+    if (per_sm < 1) per_sm = 1;
+    const int grid = std::min(ngroups, sms * per_sm);
+    kern<<<grid, HIST_THREADS, smem, st>>>(d_idx, n, NP, bn, nb, d_counts, d_err, k0, k1, scale, b_first);
+    CGPU_LAUNCH_CHECK();
+    return CGPU_OK;
+}
+
 static int hist_dispatch(int src, const uint32_t *d_idx, int n, int NP, int bn, int nb,
                          unsigned long long *d_counts, int *d_err, uint32_t k0, uint32_t k1, uint32_t scale,
                          uint32_t b_first, cudaStream_t st) {
     if (nb <= 0) return CGPU_OK;
     const int ngroups = (nb + 7) / 8;
+    int algo = hist_algo();
+    if (algo == 2 && 2 * NP > HIST_SMEM_SITES) algo = 0;  // tag arrays double the footprint
     if (NP <= HIST_SMEM_SITES) {
-        static bool attr_done = false;
-        if (!attr_done) {
-            CGPU_CUDA(cudaFuncSetAttribute(hist_group_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * HIST_SMEM_SITES));
-            CGPU_CUDA(cudaFuncSetAttribute(hist_group_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * HIST_SMEM_SITES));
-            attr_done = true;
-        }
-        size_t smem = (size_t)8 * NP;
-        int sms = G().sm_count > 0 ? G().sm_count : 148;
-        int per_sm = (int)std::min<size_t>(8, (220 * 1024) / smem);
-        if (per_sm < 1) per_sm = 1;
-        int grid = std::min(ngroups, sms * per_sm);
-        if (src == 0)
-            hist_group_kernel<0><<<grid, HIST_THREADS, smem, st>>>(d_idx, n, NP, bn, nb, d_counts, d_err, k0, k1, scale, b_first);
-        else
-            hist_group_kernel<1><<<grid, HIST_THREADS, smem, st>>>(d_idx, n, NP, bn, nb, d_counts, d_err, k0, k1, scale, b_first);
-        CGPU_LAUNCH_CHECK();
+#define CGPU_HIST_CASE(S, A)                                                                                     \
+    if (src == S && algo == A)                                                                                    \
+        return hist_group_launch<S, A>(d_idx, n, NP, bn, nb, d_counts, d_err, k0, k1, scale, b_first, st);
+        CGPU_HIST_CASE(0, 0) CGPU_HIST_CASE(0, 1) CGPU_HIST_CASE(0, 2)
+        CGPU_HIST_CASE(1, 0) CGPU_HIST_CASE(1, 1) CGPU_HIST_CASE(1, 2)
+#undef CGPU_HIST_CASE
+        set_error(CGPU_EINVAL, "CGPU_HIST_ALGO=%d", algo);
+        return CGPU_EINVAL;
     } else {
         CGPU_CUDA(cudaMemsetAsync(d_counts, 0, (size_t)ngroups * NP * 8, st));
         int sms = G().sm_count > 0 ? G().sm_count : 148;
