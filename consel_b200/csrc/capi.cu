@@ -197,14 +197,11 @@ struct Workspace {
     }
 };
 
-static int scaleboot_core(const DevMatrix &m, int S, const int *bn, const int *bb, unsigned long seed,
+static int scaleboot_core(DevMatrix &m, int S, const int *bn, const int *bb, unsigned long seed,
                           unsigned long long stream_offset, int rng_mode, int sum_mode, DevReps *reps,
                           PhaseTimer &pt, cudaStream_t st) {
-    if (sum_mode == CGPU_SUM_INT8) {
-        set_error(CGPU_EINVAL, "sum_mode CGPU_SUM_INT8 (tcgen05 fixed-point path) is not built in this version");
-        return CGPU_EINVAL;
-    }
-    if (sum_mode != CGPU_SUM_STRICT && sum_mode != CGPU_SUM_FAST) {
+    const bool i8 = sum_mode == CGPU_SUM_INT8;
+    if (sum_mode != CGPU_SUM_STRICT && sum_mode != CGPU_SUM_FAST && !i8) {
         set_error(CGPU_EINVAL, "unknown sum_mode %d", sum_mode);
         return CGPU_EINVAL;
     }
@@ -227,7 +224,25 @@ static int scaleboot_core(const DevMatrix &m, int S, const int *bn, const int *b
     cap = std::max<long long>(64, cap / 64 * 64);
     int max_nb = 0;
     for (int s = 0; s < S; s++) max_nb = std::max(max_nb, reps->nb[s]);
-    const int batch = (int)std::min<long long>(cap, std::max(64, (max_nb + 63) / 64 * 64));
+    int *d_partial = nullptr;  // int32 partial sums of the tensor-core path
+    struct PartialGuard {
+        int *&p;
+        ~PartialGuard() { dev_free(p); }
+    } pguard{d_partial};
+    if (i8) {
+        pt.begin(0);
+        CGPU_TRY(fx_prepare(m, st));
+        pt.end();
+        if ((long long)max_bn * 128 >= (1ll << 31)) {
+            set_error(CGPU_ERANGE, "CGPU_SUM_INT8: %d draws per replicate can overflow the int32 accumulators", max_bn);
+            return CGPU_ERANGE;
+        }
+        cap = std::min<long long>(cap, (long long)(budget / (m.fxMpad * 4)));
+        cap = std::max<long long>(256, cap / 256 * 256);
+    }
+    const int align = i8 ? 256 : 64;
+    const int batch = (int)std::min<long long>(cap, std::max(align, (max_nb + align - 1) / align * align));
+    if (i8) CGPU_CUDA(dev_alloc(&d_partial, m.fxMpad * (size_t)batch * sizeof(int)));
 
     Workspace ws;
     for (int i = 0; i < 2; i++) {
@@ -293,11 +308,11 @@ static int scaleboot_core(const DevMatrix &m, int S, const int *bn, const int *b
                     pt.end();
                 }
                 pt.begin(2, aux);
-                CGPU_TRY(launch_hist_from_idx(idx_src, n, NP, bn[s], nbat, ws.d_counts[buf], ws.d_err, aux));
+                CGPU_TRY(launch_hist_from_idx(idx_src, n, NP, bn[s], nbat, ws.d_counts[buf], ws.d_err, aux, i8));
                 pt.end();
             } else {
                 pt.begin(2, aux);
-                CGPU_TRY(launch_hist_philox((unsigned long long)seed, s, bA, n, NP, bn[s], nbat, ws.d_counts[buf], ws.d_err, aux));
+                CGPU_TRY(launch_hist_philox((unsigned long long)seed, s, bA, n, NP, bn[s], nbat, ws.d_counts[buf], ws.d_err, aux, i8));
                 pt.end();
             }
             if (overlap) {
@@ -305,7 +320,11 @@ static int scaleboot_core(const DevMatrix &m, int S, const int *bn, const int *b
                 CGPU_CUDA(cudaStreamWaitEvent(st, ws.hist_done[buf], 0));
             }
             pt.begin(3);
-            CGPU_TRY(launch_contract(m, ws.d_counts[buf], nbat, r, reps->d_rep[s], reps->nb[s], a, sum_mode, st));
+            if (i8)
+                CGPU_TRY(launch_contract_i8(m, reinterpret_cast<const unsigned char *>(ws.d_counts[buf]), nbat,
+                                            (nbat + 255) / 256 * 256, d_partial, r, reps->d_rep[s], reps->nb[s], a, st));
+            else
+                CGPU_TRY(launch_contract(m, ws.d_counts[buf], nbat, r, reps->d_rep[s], reps->nb[s], a, sum_mode, st));
             pt.end();
             if (overlap) CGPU_CUDA(cudaEventRecord(ws.contract_done[buf], st));
         }
@@ -477,13 +496,14 @@ void cgpu_matrix_free(cgpu_matrix *mm) {
     if (!m) return;
     dev_free(m->d_L);
     dev_free(m->d_LT);
+    dev_free(m->d_A8);
     delete m;
 }
 
 int cgpu_scaleboot_dev(const cgpu_matrix *mm, int S, const int *bn, const int *bb, unsigned long seed,
                        unsigned long long stream_offset, int rng_mode, int sum_mode, cgpu_reps **out) {
     CGPU_TRY(ensure_init());
-    const DevMatrix *m = reinterpret_cast<const DevMatrix *>(mm);
+    DevMatrix *m = const_cast<DevMatrix *>(reinterpret_cast<const DevMatrix *>(mm));  // lazily caches the int8 slices
     if (!m || S <= 0 || !bn || !bb || !out) {
         set_error(CGPU_EINVAL, "scaleboot_dev: bad arguments");
         return CGPU_EINVAL;

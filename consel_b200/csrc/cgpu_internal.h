@@ -99,6 +99,10 @@ struct DevMatrix {  // cgpu_matrix
     bool finite = true;
     double *d_L = nullptr;   // K x n row-major (as uploaded)
     double *d_LT = nullptr;  // [ktiles][NP][KT] site-major tiles, zero padded
+    // CGPU_SUM_INT8 (built lazily by fx_prepare): L = M * 2^-fxF, M = sum_s digit_s * 256^s
+    signed char *d_A8 = nullptr;  // [fxMpad][NP] int8 digits, row k*fxS+s
+    int fxS = 0, fxF = 0;
+    size_t fxMpad = 0;
 };
 
 struct DevReps {  // cgpu_reps
@@ -122,10 +126,12 @@ int launch_mt_draw(const uint32_t *d_states, int chunk_log2, unsigned long long 
                    int nchunks, unsigned long long lo, unsigned long long hi, uint32_t n,
                    uint32_t *d_idx, cudaStream_t st);
 // resample_kernels.cu
+// counts layout: rows == false -> "BJ8" words (8 replicates interleaved per site);
+//                rows == true  -> plain uint8 rows [replicate][NP] (tensor-core operand)
 int launch_hist_from_idx(const uint32_t *d_idx, int n, int NP, int bn, int nb,
-                         unsigned long long *d_counts, int *d_err, cudaStream_t st);
+                         unsigned long long *d_counts, int *d_err, cudaStream_t st, bool rows = false);
 int launch_hist_philox(unsigned long long seed, int scale, int b_first, int n, int NP, int bn, int nb,
-                       unsigned long long *d_counts, int *d_err, cudaStream_t st);
+                       unsigned long long *d_counts, int *d_err, cudaStream_t st, bool rows = false);
 int launch_counts_unpack(const unsigned long long *d_counts, int n, int NP, int nb,
                          unsigned char *d_out, cudaStream_t st);
 // contract_kernels.cu
@@ -133,6 +139,10 @@ int launch_transpose_L(const double *d_L, int K, int n, int NP, int TK, double *
                        cudaStream_t st);
 int launch_contract(const DevMatrix &m, const unsigned long long *d_counts, int nb, double r,
                     double *d_rep, int ldrep, int col0, int sum_mode, cudaStream_t st);
+// i8_kernels.cu
+int fx_prepare(DevMatrix &m, cudaStream_t st);
+int launch_contract_i8(const DevMatrix &m, const unsigned char *d_counts_rows, int nb, int nb_pad, int *d_partial,
+                       double r, double *d_rep, int ldrep, int col0, cudaStream_t st);
 
 // stats_kernels.cu
 // Row definitions for the row-summary kernel:

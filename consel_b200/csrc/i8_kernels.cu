@@ -1,0 +1,363 @@
+// CGPU_SUM_INT8: the replicate sums as an EXACT fixed-point contraction on the 5th-gen
+// tensor cores (tcgen05.mma kind::i8, accumulators in TMEM).
+//
+//   L[k][j] = M[k][j] * 2^-F with M an integer (F chosen so that EVERY entry is exact),
+//   M = sum_s d_s * 256^s with signed digits d_s in [-128,127]  (S slices, "Ozaki splitting")
+//   T_s[k][b] = sum_j c[b][j] * d_s[k][j]          int8 x uint8 -> int32, one GEMM with the
+//                                                  slices stacked along M (rows k*S+s)
+//   rep[k][b] = rn( rn( sum_s T_s * 256^s * 2^-F ) / r )
+//
+// The integer sum is exact, so the result is the correctly rounded sum (one rounding) and
+// is identical for every tiling, batch split and GPU count; it differs from the
+// reference's sequentially rounded sum by <= n*2^-53 relative (tests: bit-equal to a
+// big-integer restatement, <= 1e-9 relative to the reference).
+//
+// Kernels
+//   fx_scan_kernel     exponent range of L (lowest set mantissa bit, highest magnitude bit)
+//   fx_slice_kernel    L -> digit matrix A[(k*S+s)][j] (int8, K-major rows of NP bytes)
+//   gemm_i8_kernel     D[128 x 256] tiles: TMA (128B swizzle) -> smem ring -> tcgen05.mma
+//                      kind::i8 -> TMEM -> tcgen05.ld -> int32 partial sums in HBM
+//   fx_combine_kernel  exact 128-bit recombination of the S partial sums, one rounding,
+//                      scale, divide by r
+#include <cuda.h>
+
+#include "cgpu_internal.h"
+
+namespace cgpu {
+
+// ------------------------------------------------------------------ fixed-point set-up
+// per entry x = (-1)^s * m * 2^e with m a 53-bit integer: lo = e + ctz(m) (exponent of the
+// lowest set bit), hi = e + 52 - clz-adjust (exponent of the highest set bit)
+__global__ void __launch_bounds__(256)
+fx_scan_kernel(const double *__restrict__ L, size_t count, int *__restrict__ out /* [0]=min lo, [1]=max hi, [2]=nonfinite */) {
+    int lo = 1 << 30, hi = -(1 << 30), bad = 0;
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < count; e += (size_t)gridDim.x * blockDim.x) {
+        const unsigned long long u = (unsigned long long)__double_as_longlong(L[e]);
+        const int ex = (int)((u >> 52) & 0x7ff);
+        unsigned long long m = u & 0xfffffffffffffull;
+        if (ex == 0x7ff) { bad = 1; continue; }
+        int e2;
+        if (ex == 0) {
+            if (m == 0) continue;  // zero contributes nothing
+            e2 = -1074;
+        } else {
+            m |= 1ull << 52;
+            e2 = ex - 1075;
+        }
+        lo = min(lo, e2 + (int)__ffsll((long long)m) - 1);
+        hi = max(hi, e2 + 63 - (int)__clzll((long long)m));
+    }
+    for (int off = 16; off; off >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, off));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, off));
+        bad |= __shfl_xor_sync(0xffffffffu, bad, off);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(&out[0], lo);
+        atomicMax(&out[1], hi);
+        if (bad) atomicExch(&out[2], 1);
+    }
+}
+
+// A[(k*S+s)*NP + j] = digit s of M = L[k][j]*2^F; rows >= K*S and sites >= n stay zero
+__global__ void __launch_bounds__(256)
+fx_slice_kernel(const double *__restrict__ L, int K, int n, int NP, int S, int F, signed char *__restrict__ A) {
+    const size_t total = (size_t)K * n;
+    for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+        const int k = (int)(e / n), j = (int)(e % n);
+        const unsigned long long u = (unsigned long long)__double_as_longlong(L[e]);
+        const int ex = (int)((u >> 52) & 0x7ff);
+        unsigned long long m = u & 0xfffffffffffffull;
+        int e2 = -1074;
+        if (ex) {
+            m |= 1ull << 52;
+            e2 = ex - 1075;
+        }
+        // M = +-m * 2^(e2+F); F >= -lo guarantees the shift loses no set bit
+        const int sh = e2 + F;
+        unsigned __int128 mag = m;
+        if (sh >= 0) mag <<= sh; else mag >>= -sh;
+        __int128 v = (u >> 63) ? -(__int128)mag : (__int128)mag;
+        for (int s = 0; s < S; s++) {
+            int d = (int)(v & 0xff);
+            if (d >= 128) d -= 256;  // balanced digit; the borrow moves to the next slice
+            A[((size_t)k * S + s) * NP + j] = (signed char)d;
+            v = (v - d) >> 8;
+        }
+    }
+}
+
+__device__ __forceinline__ double i128_to_double_rn(__int128 v) {
+    const bool neg = v < 0;
+    unsigned __int128 a = neg ? (unsigned __int128)(-v) : (unsigned __int128)v;
+    if (a == 0) return 0.0;
+    const unsigned long long hi = (unsigned long long)(a >> 64), lo = (unsigned long long)a;
+    const int msb = hi ? 127 - __clzll((long long)hi) : 63 - __clzll((long long)lo);
+    double r;
+    if (msb <= 52) {
+        r = (double)lo;
+    } else {
+        const int sh = msb - 52;
+        unsigned long long mant = (unsigned long long)(a >> sh);
+        const unsigned __int128 rem = a & ((((unsigned __int128)1) << sh) - 1);
+        const unsigned __int128 half = ((unsigned __int128)1) << (sh - 1);
+        if (rem > half || (rem == half && (mant & 1))) mant++;
+        r = scalbn((double)mant, sh);  // mant <= 2^53: exact
+    }
+    return neg ? -r : r;
+}
+
+// P: int32 partial sums [Mpad][ldp] (row k*S+s, column = replicate of the batch)
+__global__ void __launch_bounds__(256)
+fx_combine_kernel(const int *__restrict__ P, int ldp, int K, int S, int F, int nb, double r, double *__restrict__ rep,
+                  int ldrep, int col0) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const int k = blockIdx.y;
+    if (b >= nb || k >= K) return;
+    __int128 t = 0;
+    for (int s = S - 1; s >= 0; s--) t = (t << 8) + (__int128)P[((size_t)k * S + s) * ldp + b];
+    const double x = scalbn(i128_to_double_rn(t), -F);  // exact scaling of the rounded sum
+    rep[(size_t)k * ldrep + col0 + b] = __ddiv_rn(x, r);
+}
+
+// ------------------------------------------------------------------ tcgen05 GEMM
+constexpr int G8_BM = 128, G8_BN = 256, G8_BK = 128;  // BK in bytes == int8 elements (one 128B swizzle atom)
+constexpr int G8_STAGES = 4;
+constexpr int G8_THREADS = 192;  // warp0 TMA, warp1 MMA (+TMEM alloc), warps 2-5 epilogue
+constexpr size_t G8_A_BYTES = (size_t)G8_BM * G8_BK, G8_B_BYTES = (size_t)G8_BN * G8_BK;
+constexpr size_t G8_SMEM = G8_STAGES * (G8_A_BYTES + G8_B_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
+
+__device__ __forceinline__ uint32_t s2u(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mb_init(uint64_t *b, uint32_t n) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s2u(b)), "r"(n) : "memory");
+}
+__device__ __forceinline__ void mb_expect(uint64_t *b, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s2u(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mb_wait(uint64_t *b, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(s2u(b)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            s2u(dst)),
+        "l"(map), "r"(s2u(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+// K-major operand tile, rows of 128 bytes, 128B swizzle, 8-row groups 1024 bytes apart
+__device__ __forceinline__ uint64_t umma_desc_sw128(const void *smem) {
+    uint64_t d = (uint64_t)((s2u(smem) & 0x3ffffu) >> 4);
+    d |= (uint64_t)1 << 16;            // leading byte offset (unused for swizzled K-major) = 1
+    d |= (uint64_t)(1024 >> 4) << 32;  // stride byte offset between 8-row groups
+    d |= (uint64_t)1 << 46;            // descriptor version (Blackwell)
+    d |= (uint64_t)2 << 61;            // SWIZZLE_128B
+    return d;
+}
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s2u(bar)) : "memory");
+}
+
+// D (int32, [Mpad][ldp]) = A (int8 digits, [Mpad][NP]) x B^T (uint8 counts, [Npad][NP])
+__global__ void __launch_bounds__(G8_THREADS, 1)
+gemm_i8_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int NP,
+               int *__restrict__ P, int ldp, int ncols_valid) {
+    extern __shared__ unsigned char g8_raw[];
+    unsigned char *base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(g8_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char *sA = base;
+    unsigned char *sB = base + G8_STAGES * G8_A_BYTES;
+    uint64_t *full = reinterpret_cast<uint64_t *>(base + G8_STAGES * (G8_A_BYTES + G8_B_BYTES));
+    uint64_t *empty = full + G8_STAGES;
+    uint64_t *acc_done = empty + G8_STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_done + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * G8_BM, n0 = blockIdx.y * G8_BN;
+    const int nkb = NP / G8_BK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < G8_STAGES; s++) {
+            mb_init(&full[s], 1);
+            mb_init(&empty[s], 1);
+        }
+        mb_init(acc_done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {  // one warp allocates the accumulator columns in tensor memory
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s2u(tmem_slot)), "n"(G8_BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            for (int kb = 0; kb < nkb; kb++) {
+                const int s = kb % G8_STAGES;
+                mb_wait(&empty[s], ((kb / G8_STAGES) & 1) ^ 1);
+                mb_expect(&full[s], (uint32_t)(G8_A_BYTES + G8_B_BYTES));
+                tma_load_2d(sA + s * G8_A_BYTES, &mapA, kb * G8_BK, m0, &full[s]);
+                tma_load_2d(sB + s * G8_B_BYTES, &mapB, kb * G8_BK, n0, &full[s]);
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // instruction descriptor: D=S32, A=signed 8 bit, B=unsigned 8 bit, both K-major, N=256, M=128
+            const uint32_t idesc = (2u << 4) | (1u << 7) | (0u << 10) | ((uint32_t)(G8_BN >> 3) << 17) | ((uint32_t)(G8_BM >> 4) << 24);
+            for (int kb = 0; kb < nkb; kb++) {
+                const int s = kb % G8_STAGES;
+                mb_wait(&full[s], (kb / G8_STAGES) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint64_t ad = umma_desc_sw128(sA + s * G8_A_BYTES), bd = umma_desc_sw128(sB + s * G8_B_BYTES);
+#pragma unroll
+                for (int k = 0; k < G8_BK / 32; k++)  // UMMA_K = 32 int8 = 32 bytes = 2 descriptor units
+                    umma_i8(tmem, ad + 2 * k, bd + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                umma_commit(&empty[s]);  // frees the smem stage once these MMAs have read it
+            }
+            umma_commit(acc_done);
+        }
+    } else {
+        // epilogue: warp w may only touch TMEM lanes 32*(w%4) .. +31
+        const int q = warp & 3;
+        mb_wait(acc_done, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int row = m0 + q * 32 + lane;
+        int *dst = P + (size_t)row * ldp + n0;
+#pragma unroll 1
+        for (int c = 0; c < G8_BN; c += 32) {
+            uint32_t v[32];
+            const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)c;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                  "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                  "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                : "r"(taddr)
+                : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            if (n0 + c < ncols_valid) {
+                uint4 *d4 = reinterpret_cast<uint4 *>(dst + c);
+#pragma unroll
+                for (int i = 0; i < 8; i++) d4[i] = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(G8_BN) : "memory");
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = [] {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || !p) return (EncodeTiledFn) nullptr;
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+
+// rows x NP bytes, row-major, box = box_rows x 128 bytes, 128B swizzle
+static int make_map(CUtensorMap *map, const void *ptr, size_t rows, int NP, int box_rows) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) {
+        set_error(CGPU_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
+        return CGPU_ECUDA;
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)NP, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)NP};
+    cuuint32_t box[2] = {(cuuint32_t)G8_BK, (cuuint32_t)box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void *>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error(CGPU_ECUDA, "cuTensorMapEncodeTiled failed with %d (rows=%zu NP=%d)", (int)r, rows, NP);
+        return CGPU_ECUDA;
+    }
+    return CGPU_OK;
+}
+
+int fx_prepare(DevMatrix &m, cudaStream_t st) {
+    if (m.d_A8) return CGPU_OK;
+    int *d_rng = nullptr;
+    CGPU_CUDA(dev_alloc(&d_rng, 3 * sizeof(int)));
+    const int init[3] = {1 << 30, -(1 << 30), 0};
+    CGPU_CUDA(cudaMemcpyAsync(d_rng, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    fx_scan_kernel<<<G().sm_count * 4, 256, 0, st>>>(m.d_L, (size_t)m.K * m.n, d_rng);
+    CGPU_LAUNCH_CHECK();
+    int h[3];
+    CGPU_CUDA(cudaMemcpyAsync(h, d_rng, sizeof(h), cudaMemcpyDeviceToHost, st));
+    CGPU_CUDA(cudaStreamSynchronize(st));
+    dev_free(d_rng);
+    if (h[2]) {
+        set_error(CGPU_ERANGE, "CGPU_SUM_INT8 needs finite site log-likelihoods");
+        return CGPU_ERANGE;
+    }
+    if (h[0] > h[1]) { h[0] = 0; h[1] = 0; }  // all-zero matrix
+    // magnitude bits + sign + one spare bit so the carry of the balanced digits cannot
+    // overflow the top slice
+    const int bits = h[1] - h[0] + 3;
+    const int S = (bits + 7) / 8;
+    if (S > 12) {
+        set_error(CGPU_ERANGE, "CGPU_SUM_INT8: the matrix spans %d bits (2^%d .. 2^%d); exact fixed point supports 96", bits, h[0], h[1]);
+        return CGPU_ERANGE;
+    }
+    m.fxS = S < 1 ? 1 : S;
+    m.fxF = -h[0];
+    m.fxMpad = ((size_t)m.K * m.fxS + G8_BM - 1) / G8_BM * G8_BM;
+    CGPU_CUDA(dev_alloc(&m.d_A8, (size_t)m.fxMpad * m.NP));
+    CGPU_CUDA(cudaMemsetAsync(m.d_A8, 0, (size_t)m.fxMpad * m.NP, st));
+    fx_slice_kernel<<<G().sm_count * 8, 256, 0, st>>>(m.d_L, m.K, m.n, m.NP, m.fxS, m.fxF, m.d_A8);
+    CGPU_LAUNCH_CHECK();
+    return CGPU_OK;
+}
+
+// counts: plain rows [nb_pad][NP] uint8 (nb_pad multiple of 256, padding rows zero)
+int launch_contract_i8(const DevMatrix &m, const unsigned char *d_counts_rows, int nb, int nb_pad, int *d_partial,
+                       double r, double *d_rep, int ldrep, int col0, cudaStream_t st) {
+    if (nb <= 0) return CGPU_OK;
+    // int32 accumulators: |sum_j c*d| <= 128 * (draws per replicate)
+    CUtensorMap mapA, mapB;
+    CGPU_TRY(make_map(&mapA, m.d_A8, m.fxMpad, m.NP, G8_BM));
+    CGPU_TRY(make_map(&mapB, d_counts_rows, (size_t)nb_pad, m.NP, G8_BN));
+    static bool attr_done = false;
+    if (!attr_done) {
+        CGPU_CUDA(cudaFuncSetAttribute(gemm_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G8_SMEM));
+        attr_done = true;
+    }
+    dim3 grid((unsigned)(m.fxMpad / G8_BM), (unsigned)(nb_pad / G8_BN));
+    gemm_i8_kernel<<<grid, G8_THREADS, G8_SMEM, st>>>(mapA, mapB, m.NP, d_partial, nb_pad, nb_pad);
+    CGPU_LAUNCH_CHECK();
+    dim3 cgrid((nb + 255) / 256, m.K);
+    fx_combine_kernel<<<cgrid, 256, 0, st>>>(d_partial, nb_pad, m.K, m.fxS, m.fxF, nb, r, d_rep, ldrep, col0);
+    CGPU_LAUNCH_CHECK();
+    return CGPU_OK;
+}
+
+}  // namespace cgpu

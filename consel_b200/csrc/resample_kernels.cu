@@ -92,7 +92,7 @@ __device__ __forceinline__ void warp_hist_add(unsigned char *hist, unsigned char
 }
 
 // SRC 0: indices from the buffer (replicate r of this launch at idx[r*bn ..));  SRC 1: Philox
-template <int SRC, int HALGO>
+template <int SRC, int HALGO, bool ROWS>
 __global__ void __launch_bounds__(HIST_THREADS)
 hist_group_kernel(const uint32_t *__restrict__ idx, int n, int NP, int bn, int nb,
                   unsigned long long *__restrict__ counts, int *__restrict__ err,
@@ -132,6 +132,15 @@ hist_group_kernel(const uint32_t *__restrict__ idx, int n, int NP, int bn, int n
             if (overflow) atomicExch(err, 1);
         }
         __syncthreads();
+        if (ROWS) {
+            // plain rows: replicate 8g+w owns NP consecutive bytes
+            unsigned char *dst = reinterpret_cast<unsigned char *>(counts) + (size_t)g * 8 * NP;
+            const uint4 *src4 = reinterpret_cast<const uint4 *>(hsm);
+            uint4 *dst4 = reinterpret_cast<uint4 *>(dst);
+            for (int i = tid; i < 8 * NP / 16; i += HIST_THREADS) dst4[i] = src4[i];
+            __syncthreads();
+            continue;
+        }
         // interleave: 4 consecutive sites of all 8 histograms -> 4 BJ8 words (32 bytes)
         unsigned long long *row = counts + (size_t)g * NP;
         for (int j4 = tid; j4 < NP / 4; j4 += HIST_THREADS) {
@@ -156,7 +165,7 @@ hist_group_kernel(const uint32_t *__restrict__ idx, int n, int NP, int bn, int n
     }
 }
 
-template <int SRC>
+template <int SRC, bool ROWS>
 __global__ void __launch_bounds__(256)
 hist_global_kernel(const uint32_t *__restrict__ idx, int n, int NP, int bn, int nb,
                    unsigned int *__restrict__ counts32, uint32_t key0, uint32_t key1, uint32_t scale,
@@ -168,8 +177,12 @@ hist_global_kernel(const uint32_t *__restrict__ idx, int n, int NP, int bn, int 
         if (SRC == 0) {
             uint32_t r = (uint32_t)(d / bn);
             uint32_t k = idx[d];
-            size_t word = ((size_t)(r >> 3) * NP + k) * 2 + ((r & 7) >> 2);
-            atomicAdd(&counts32[word], 1u << ((r & 3) * 8));
+            if (ROWS) {
+                atomicAdd(&counts32[((size_t)r * NP + k) >> 2], 1u << ((k & 3) * 8));
+            } else {
+                size_t word = ((size_t)(r >> 3) * NP + k) * 2 + ((r & 7) >> 2);
+                atomicAdd(&counts32[word], 1u << ((r & 3) * 8));
+            }
         } else {
             uint32_t qn = (uint32_t)((bn + 3) / 4);
             uint32_t r = (uint32_t)(d / qn), q = (uint32_t)(d % qn);
@@ -178,8 +191,12 @@ hist_global_kernel(const uint32_t *__restrict__ idx, int n, int NP, int bn, int 
             for (int u = 0; u < 4; u++) {
                 if ((int)(q * 4 + u) < bn) {
                     uint32_t k = __umulhi(p.v[u], (uint32_t)n);
-                    size_t word = ((size_t)(r >> 3) * NP + k) * 2 + ((r & 7) >> 2);
-                    atomicAdd(&counts32[word], 1u << ((r & 3) * 8));
+                    if (ROWS) {
+                        atomicAdd(&counts32[((size_t)r * NP + k) >> 2], 1u << ((k & 3) * 8));
+                    } else {
+                        size_t word = ((size_t)(r >> 3) * NP + k) * 2 + ((r & 7) >> 2);
+                        atomicAdd(&counts32[word], 1u << ((r & 3) * 8));
+                    }
                 }
             }
         }
@@ -195,10 +212,10 @@ static int hist_algo() {
     return v;
 }
 
-template <int SRC, int HALGO>
+template <int SRC, int HALGO, bool ROWS>
 static int hist_group_launch(const uint32_t *d_idx, int n, int NP, int bn, int nb, unsigned long long *d_counts,
                              int *d_err, uint32_t k0, uint32_t k1, uint32_t scale, uint32_t b_first, cudaStream_t st) {
-    auto kern = hist_group_kernel<SRC, HALGO>;
+    auto kern = hist_group_kernel<SRC, HALGO, ROWS>;
     static bool attr_done = false;
     if (!attr_done) {
         CGPU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * HIST_SMEM_SITES));
@@ -217,7 +234,7 @@ static int hist_group_launch(const uint32_t *d_idx, int n, int NP, int bn, int n
 
 static int hist_dispatch(int src, const uint32_t *d_idx, int n, int NP, int bn, int nb,
                          unsigned long long *d_counts, int *d_err, uint32_t k0, uint32_t k1, uint32_t scale,
-                         uint32_t b_first, cudaStream_t st) {
+                         uint32_t b_first, cudaStream_t st, bool rows) {
     if (nb <= 0) return CGPU_OK;
     const int ngroups = (nb + 7) / 8;
     int algo = hist_algo();
@@ -225,7 +242,8 @@ static int hist_dispatch(int src, const uint32_t *d_idx, int n, int NP, int bn, 
     if (NP <= HIST_SMEM_SITES) {
 #define CGPU_HIST_CASE(S, A)                                                                                     \
     if (src == S && algo == A)                                                                                    \
-        return hist_group_launch<S, A>(d_idx, n, NP, bn, nb, d_counts, d_err, k0, k1, scale, b_first, st);
+        return rows ? hist_group_launch<S, A, true>(d_idx, n, NP, bn, nb, d_counts, d_err, k0, k1, scale, b_first, st) \
+                    : hist_group_launch<S, A, false>(d_idx, n, NP, bn, nb, d_counts, d_err, k0, k1, scale, b_first, st);
         CGPU_HIST_CASE(0, 0) CGPU_HIST_CASE(0, 1) CGPU_HIST_CASE(0, 2)
         CGPU_HIST_CASE(1, 0) CGPU_HIST_CASE(1, 1) CGPU_HIST_CASE(1, 2)
 #undef CGPU_HIST_CASE
@@ -235,24 +253,25 @@ static int hist_dispatch(int src, const uint32_t *d_idx, int n, int NP, int bn, 
         CGPU_CUDA(cudaMemsetAsync(d_counts, 0, (size_t)ngroups * NP * 8, st));
         int sms = G().sm_count > 0 ? G().sm_count : 148;
         int grid = sms * 16;
-        if (src == 0)
-            hist_global_kernel<0><<<grid, 256, 0, st>>>(d_idx, n, NP, bn, nb, reinterpret_cast<unsigned int *>(d_counts), k0, k1, scale, b_first);
-        else
-            hist_global_kernel<1><<<grid, 256, 0, st>>>(d_idx, n, NP, bn, nb, reinterpret_cast<unsigned int *>(d_counts), k0, k1, scale, b_first);
+        unsigned int *c32 = reinterpret_cast<unsigned int *>(d_counts);
+        if (src == 0 && !rows) hist_global_kernel<0, false><<<grid, 256, 0, st>>>(d_idx, n, NP, bn, nb, c32, k0, k1, scale, b_first);
+        else if (src == 0) hist_global_kernel<0, true><<<grid, 256, 0, st>>>(d_idx, n, NP, bn, nb, c32, k0, k1, scale, b_first);
+        else if (!rows) hist_global_kernel<1, false><<<grid, 256, 0, st>>>(d_idx, n, NP, bn, nb, c32, k0, k1, scale, b_first);
+        else hist_global_kernel<1, true><<<grid, 256, 0, st>>>(d_idx, n, NP, bn, nb, c32, k0, k1, scale, b_first);
         CGPU_LAUNCH_CHECK();
     }
     return CGPU_OK;
 }
 
 int launch_hist_from_idx(const uint32_t *d_idx, int n, int NP, int bn, int nb,
-                         unsigned long long *d_counts, int *d_err, cudaStream_t st) {
-    return hist_dispatch(0, d_idx, n, NP, bn, nb, d_counts, d_err, 0, 0, 0, 0, st);
+                         unsigned long long *d_counts, int *d_err, cudaStream_t st, bool rows) {
+    return hist_dispatch(0, d_idx, n, NP, bn, nb, d_counts, d_err, 0, 0, 0, 0, st, rows);
 }
 
 int launch_hist_philox(unsigned long long seed, int scale, int b_first, int n, int NP, int bn, int nb,
-                       unsigned long long *d_counts, int *d_err, cudaStream_t st) {
+                       unsigned long long *d_counts, int *d_err, cudaStream_t st, bool rows) {
     return hist_dispatch(1, nullptr, n, NP, bn, nb, d_counts, d_err, (uint32_t)seed, (uint32_t)(seed >> 32),
-                         (uint32_t)scale, (uint32_t)b_first, st);
+                         (uint32_t)scale, (uint32_t)b_first, st, rows);
 }
 
 // BJ8 -> plain counts[b*n + j] bytes (test seam: cgpu_resample_counts)

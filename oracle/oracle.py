@@ -413,3 +413,28 @@ def order_items(datvec, ass_ptr, ass_idx):
         idx += list(ass_idx[ass_ptr[i]:ass_ptr[i + 1]])
         ptr.append(len(idx))
     return (np.array(order, dtype=np.int32), obs, np.array(ptr, dtype=np.int32), np.array(idx, dtype=np.int32))
+
+
+def exact_rounded_contract(L: np.ndarray, counts: np.ndarray, r: float) -> np.ndarray:
+    """Big-integer restatement of the fixed-point path (CGPU_SUM_INT8): the replicate sums
+    sum_j c[b,j]*L[k,j] are formed EXACTLY (Python integers), rounded once to fp64, then
+    divided by r like src/makermt.c:69.  Small cases only."""
+    from fractions import Fraction
+    L = np.asarray(L, dtype=np.float64)
+    K, n = L.shape
+    # common scale: every double is an integer multiple of 2^-1074
+    fr = [[Fraction(float(x)) for x in row] for row in L]
+    den = 1
+    for row in fr:
+        for f in row:
+            den = max(den, f.denominator)
+    M = np.array([[int(f * den) for f in row] for row in fr], dtype=object)  # exact: den is a power of two
+    C = np.asarray(counts).astype(object)
+    T = C.dot(M.T)  # (B, K) exact integers
+    out = np.empty((K, C.shape[0]))
+    rr = np.float64(r)
+    for b in range(C.shape[0]):
+        for k in range(K):
+            x = np.float64(float(Fraction(int(T[b, k]), den)))  # one correctly rounded conversion
+            out[k, b] = x / rr
+    return out

@@ -1,0 +1,79 @@
+"""CGPU_SUM_INT8: exact fixed-point replicate sums on the tcgen05 int8 tensor cores.
+Bit-equal to a big-integer restatement (oracle.exact_rounded_contract), within 1e-9
+relative of the reference's sequentially rounded sums, independent of batch/sharding."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cg():
+    import consel_b200 as cg
+    cg.init()
+    cg.set_shard(0, 1)
+    return cg
+
+
+def synth(K, n, seed=20261019):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    base = -2.3 - 4.07 * rng.exponential(size=n)
+    return base[None, :] + 0.106 * rng.standard_normal((K, n)) - 0.5 * np.arange(K)[:, None] / n
+
+
+@pytest.mark.parametrize("K,n,bb", [(3, 100, [5]), (15, 300, [40, 9]), (40, 700, [64, 257]), (130, 260, [300])])
+def test_int8_path_is_exactly_the_rounded_exact_sum(cg, orc, K, n, bb):
+    L = synth(K, n, seed=K + n)
+    rr = [0.6, 1.3][:len(bb)]
+    _, bn, rr1 = orc.scale_setup(L, rr)
+    got = cg.scaleboot_all(L, bn, bb, 17, sum_mode=cg.SUM_INT8)
+    ref = orc.makermt(L, bn, bb, 17)
+    for s in range(len(bb)):
+        counts = cg.resample_counts(n, bn, bb, 17, s)
+        want = orc.exact_rounded_contract(L, counts, rr1[s])
+        assert np.array_equal(got[s], want), (K, n, s, np.abs(got[s] - want).max())
+        rel = np.abs(got[s] - ref[s]) / np.abs(ref[s])
+        assert rel.max() < 1e-9  # north star tolerance; in practice ~n*2^-53
+
+
+def test_int8_mam15_against_reference_rmt(cg, orc, gold):
+    L = orc.read_lnf(gold / "mam15.lnf")
+    ref = orc.read_rmt(gold / "g100.rmt")
+    out = cg.makermt(L, [0.5, 0.6, 0.7, 0.8, 0.9, 1.0, 1.1, 1.2, 1.3, 1.4], ref["bb"], 1234, sum_mode=cg.SUM_INT8)
+    for s in range(10):
+        rel = np.abs(out["reps"][s] - ref["reps"][s]) / np.abs(ref["reps"][s])
+        assert rel.max() < 1e-12, (s, rel.max())
+    # the fast fp64 mode and the int8 mode bracket the reference the same way
+    fast = cg.makermt(L, [1.0], [64], 5, sum_mode=cg.SUM_FAST)["reps"][0]
+    i8 = cg.makermt(L, [1.0], [64], 5, sum_mode=cg.SUM_INT8)["reps"][0]
+    assert np.abs(fast - i8).max() / np.abs(i8).max() < 1e-12
+
+
+def test_int8_sharding_and_philox(cg, orc):
+    L = synth(20, 500)
+    _, bn, _ = orc.scale_setup(L, [0.7, 1.2])
+    bb = [70, 33]
+    for mode in (cg.RNG_MT19937, cg.RNG_PHILOX):
+        cg.set_shard(0, 1)
+        whole = cg.scaleboot_all(L, bn, bb, 3, rng_mode=mode, sum_mode=cg.SUM_INT8)
+        for rank in range(2):
+            cg.set_shard(rank, 2)
+            loc = cg.scaleboot_all(L, bn, bb, 3, rng_mode=mode, sum_mode=cg.SUM_INT8)
+            for s in range(2):
+                b0, b1 = cg.shard_range(bb[s])
+                assert np.array_equal(loc[s], whole[s][:, b0:b1])
+        cg.set_shard(0, 1)
+
+
+def test_int8_wide_dynamic_range(cg, orc):
+    rng = np.random.default_rng(2)
+    L = -np.exp(rng.uniform(-12, 5, size=(4, 130)))  # magnitudes 6e-6 .. 150: ~80 bits of fixed point
+    _, bn, rr1 = orc.scale_setup(L, [1.0])
+    got = cg.scaleboot_all(L, bn, [9], 1, sum_mode=cg.SUM_INT8)
+    counts = cg.resample_counts(130, bn, [9], 1, 0)
+    assert np.array_equal(got[0], orc.exact_rounded_contract(L, counts, rr1[0]))
+    Lbad = L.copy()
+    Lbad[0, 0] = -1e-30  # > 96 bits: must be refused, not truncated
+    with pytest.raises(cg.CgpuError) as e:
+        cg.scaleboot_all(Lbad, bn, [9], 1, sum_mode=cg.SUM_INT8)
+    assert e.value.code == -5

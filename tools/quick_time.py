@@ -15,7 +15,7 @@ tf = C.c_double()
 cg.load().cgpu_bench_fp64_peak(C.byref(tf))
 print("fp64 DFMA peak TFLOP/s:", tf.value, flush=True)
 RR = [0.5, 0.6, 0.7, 0.8, 0.9, 1.0, 1.1, 1.2, 1.3, 1.4]
-cfgs = [("C1", 15, 3414, 10000), ("C2", 105, 3414, 100000), ("C3/10", 1000, 100000, 1000), ("K300", 300, 3414, 20000)]
+cfgs = [("C1", 15, 3414, 10000), ("C2", 105, 3414, 100000), ("C3/10", 1000, 100000, 1000), ("C3", 1000, 100000, 10000), ("K300", 300, 3414, 20000)]
 if len(sys.argv) > 1:
     cfgs = [c for c in cfgs if c[0] in sys.argv[1:]]
 for name, K, n, B in cfgs:
@@ -24,7 +24,7 @@ for name, K, n, B in cfgs:
     bb = [B] * 10
     m = cg.Matrix(L)
     acc = K * n * sum(bb)
-    for rng, sm in [(0, 0), (1, 0), (1, 1)]:
+    for rng, sm in [(0, 0), (1, 1), (0, 2), (1, 2)]:
         for it in range(3):
             t = time.time()
             r = m.scaleboot(bn, bb, 7, rng_mode=rng, sum_mode=sm)
