@@ -1,0 +1,96 @@
+"""One-process-per-GPU plumbing (torch.distributed) for the sharded path.
+
+Replicates are sharded by column range over ranks (cgpu_set_shard); the makermt side
+needs no data-path collective.  The consel side combines the per-rank row summaries of a
+count query with ONE small collective per fit round: the integer count adds, `lo` is a
+max, `hi` a min and the two smallest / two largest values merge — all exact and order
+independent, so the combined summary is bit-identical to the one a single device would
+compute.  Works with any backend (NCCL on GPUs, gloo in the CPU tests).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+FIELDS = ("cnt", "lo", "hi", "min1", "min2", "max1", "max2")
+
+
+def shard_range(bb: int, rank: int, world: int) -> tuple[int, int]:
+    """Column range of `rank`: mirrors cgpu_shard_range (consel_b200/csrc/capi.cu)."""
+    return bb * rank // world, bb * (rank + 1) // world
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist
+
+
+def _device_for(group=None):
+    import torch
+    dist = _dist()
+    return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+
+
+def combine_rowsums(q: np.ndarray, group=None) -> np.ndarray:
+    """All-reduce a structured array of row summaries (any shape, dtype api.ROWSUM_DTYPE)."""
+    import torch
+    dist = _dist()
+    world = dist.get_world_size(group)
+    if world == 1:
+        return q
+    dev = _device_for(group)
+    flat = np.stack([np.ascontiguousarray(q[f], dtype=np.float64).ravel() for f in FIELDS])  # (7, N)
+    t = torch.from_numpy(flat).to(dev)
+    cnt, lo, hi = t[0].clone(), t[1].clone(), t[2].clone()
+    dist.all_reduce(cnt, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(lo, op=dist.ReduceOp.MAX, group=group)
+    dist.all_reduce(hi, op=dist.ReduceOp.MIN, group=group)
+    # the two smallest / two largest of the union: gather the per-rank pairs (2*world values)
+    edges = t[3:7].contiguous()
+    gathered = [torch.empty_like(edges) for _ in range(world)]
+    dist.all_gather(gathered, edges, group=group)
+    g = torch.stack(gathered)  # (world, 4, N)
+    mins = torch.cat([g[:, 0], g[:, 1]]).sort(dim=0).values[:2]
+    maxs = torch.cat([g[:, 2], g[:, 3]]).sort(dim=0, descending=True).values[:2]
+    out = np.empty_like(q)
+    res = [cnt, lo, hi, mins[0], mins[1], maxs[0], maxs[1]]
+    for f, v in zip(FIELDS, res):
+        out[f] = v.cpu().numpy().reshape(q.shape)
+    return out
+
+
+def gather_columns(local: np.ndarray, bb: int, group=None) -> np.ndarray:
+    """All-gather rank-local column blocks (rows x nb_rank) into the full (rows x bb) block,
+    e.g. the replicate block of the scale nearest r=1 that the KH/SH tests need whole."""
+    import torch
+    dist = _dist()
+    world = dist.get_world_size(group)
+    if world == 1:
+        return local
+    dev = _device_for(group)
+    rows = local.shape[0]
+    parts = []
+    for r in range(world):
+        b0, b1 = shard_range(bb, r, world)
+        parts.append(torch.empty((rows, b1 - b0), dtype=torch.float64, device=dev))
+    mine = torch.from_numpy(np.ascontiguousarray(local, dtype=np.float64)).to(dev)
+    dist.all_gather(parts, mine, group=group) if len({p.shape for p in parts}) == 1 else _uneven_gather(parts, mine, group)
+    return torch.cat(parts, dim=1).cpu().numpy()
+
+
+def _uneven_gather(parts, mine, group):
+    dist = _dist()
+    rank = dist.get_rank(group)
+    for r, p in enumerate(parts):
+        if r == rank:
+            p.copy_(mine)
+        dist.broadcast(p, src=dist.get_global_rank(group, r) if group is not None else r, group=group)
+
+
+def max_over_ranks(x: float, group=None) -> float:
+    import torch
+    dist = _dist()
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return x
+    t = torch.tensor([x], dtype=torch.float64, device=_device_for(group))
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return float(t.item())
