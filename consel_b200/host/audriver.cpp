@@ -1,0 +1,167 @@
+#include "audriver.h"
+
+#include <algorithm>
+#include <atomic>
+#include <thread>
+
+#include "refio.h"
+#include "specfun.h"
+
+namespace audriver {
+
+// the per-item fits of one lockstep round are independent: spread them over the host cores
+template <typename F>
+static void parallel_for(int n, F body) {
+    unsigned hw = std::thread::hardware_concurrency();
+    int nt = (int)std::min<unsigned>(hw ? hw : 1, (unsigned)((n + 15) / 16));
+    if (refio::debugmode > 0) nt = 1;  // keep debug traces in item order
+    if (nt <= 1) {
+        for (int i = 0; i < n; i++) body(i);
+        return;
+    }
+    std::atomic<int> next{0};
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; t++)
+        th.emplace_back([&] {
+            for (;;) {
+                int i0 = next.fetch_add(16);
+                if (i0 >= n) break;
+                for (int i = i0; i < std::min(n, i0 + 16); i++) body(i);
+            }
+        });
+    for (auto &t : th) t.join();
+}
+
+int run(const Input &in, const aufit::Options &opt, QueryFn query, void *ctx, Output *out) {
+    const int cm = in.cm, kk = in.kk;
+    std::vector<double> bbd(kk);
+    for (int k = 0; k < kk; k++) bbd[k] = (double)in.bb[k];
+    const double t0 = refio::cpu_seconds();
+
+    // ---- vcalpval for every item (src/consel.c:2744-2808), one query per round
+    std::vector<aufit::VcIter> vc;
+    vc.reserve(cm);
+    for (int i = 0; i < cm; i++) vc.emplace_back(in.median[i], in.threshold);
+    std::vector<double> thr(cm);
+    std::vector<cgpu_rowsum> rs((size_t)cm * kk);
+    for (int round = 0; round < opt.vcloopmax; round++) {
+        bool any = false;
+        for (int i = 0; i < cm; i++) {
+            thr[i] = vc[i].x;
+            any = any || !vc[i].done;
+        }
+        if (!any) break;
+        if (int rc = query(ctx, 1, thr.data(), rs.data())) return rc;
+        parallel_for(cm, [&](int i) {
+            if (vc[i].done) return;
+            std::vector<double> cnts(kk);
+            for (int k = 0; k < kk; k++) cnts[k] = cgpu_smooth_count(&rs[(size_t)i * kk + k], in.bb[k], thr[i]);
+            vc[i].step(cnts.data(), in.rr, bbd.data(), kk, opt);
+        });
+    }
+    out->pv.assign(cm, 0); out->se.assign(cm, 0); out->pv0.assign(cm, 0); out->se0.assign(cm, 0);
+    out->rss.assign(cm, 0); out->df.assign(cm, 0); out->th.assign(cm, 0); out->pf.assign(cm, 0);
+    out->beta.assign(3 * (size_t)cm, 0); out->ret.assign(cm, 0);
+    for (int i = 0; i < cm; i++) {
+        const aufit::VcIter &it = vc[i];
+        const int ret = it.done ? it.ret : 2;
+        out->ret[i] = ret;
+        out->pv[i] = it.pv; out->se[i] = it.se; out->pv0[i] = it.pv0; out->se0[i] = it.se0;
+        out->rss[i] = it.rss; out->df[i] = it.df; out->th[i] = it.th_out;
+        if (!ret) {
+            out->pf[i] = specfun::pochisq(it.rss, (int)it.df);
+            for (int c = 0; c < 3; c++) out->beta[3 * (size_t)i + c] = it.beta[c];
+        }
+    }
+    out->t_fit_sec = refio::cpu_seconds() - t0;
+    if (!in.confidence || in.nalpha <= 0) return 0;
+
+    // ---- invtpval for every (item, alpha, au|bp) (src/consel.c:2816-2879)
+    const int nalpha = in.nalpha, nq = 2 * nalpha;
+    std::vector<aufit::CiIter> ci;
+    ci.reserve((size_t)cm * nq);
+    for (int j = 0; j < cm; j++) {
+        const cgpu_rowsum &e = in.r0[(size_t)j * kk + in.i0];
+        for (int a = 0; a < nalpha; a++) {
+            ci.emplace_back(e.min1, e.max1, in.alpha[a], opt.kappa);
+            ci.emplace_back(e.min1, e.max1, in.alpha[a], -1.0);
+        }
+    }
+    const int qchunk = 16;  // thresholds per item and query
+    std::vector<double> cthr;
+    std::vector<cgpu_rowsum> crs;
+    for (int round = 0; round < opt.ciloopmax; round++) {
+        bool any = false;
+        for (auto &c : ci) any = any || !c.done;
+        if (!any) break;
+        for (int q0 = 0; q0 < nq; q0 += qchunk) {
+            const int nqc = std::min(qchunk, nq - q0);
+            cthr.assign((size_t)cm * nqc, 0.0);
+            for (int j = 0; j < cm; j++)
+                for (int q = 0; q < nqc; q++) cthr[(size_t)j * nqc + q] = ci[(size_t)j * nq + q0 + q].x;
+            crs.resize((size_t)cm * kk * nqc);
+            if (int rc = query(ctx, nqc, cthr.data(), crs.data())) return rc;
+            parallel_for(cm, [&](int j) {
+                std::vector<double> cnts(kk);
+                for (int q = 0; q < nqc; q++) {
+                    aufit::CiIter &c = ci[(size_t)j * nq + q0 + q];
+                    if (c.done) continue;
+                    const double t = cthr[(size_t)j * nqc + q];
+                    for (int k = 0; k < kk; k++)
+                        cnts[k] = cgpu_smooth_count(&crs[((size_t)j * kk + k) * nqc + q], in.bb[k], t);
+                    c.step(cnts.data(), in.rr, bbd.data(), kk, opt);
+                }
+            });
+        }
+    }
+    const size_t n2 = (size_t)cm * nalpha;
+    out->ci.assign(n2, 0); out->cs.assign(n2, 0); out->ei.assign(n2, 0);
+    out->ci0.assign(n2, 0); out->cs0.assign(n2, 0); out->ei0.assign(n2, 0);
+    out->ci_ret.assign(2 * n2, 0); out->ci_warn.assign(2 * n2, 0); out->ci_warnval.assign(2 * n2, 0);
+    for (int j = 0; j < cm; j++)
+        for (int a = 0; a < nalpha; a++)
+            for (int which = 0; which < 2; which++) {
+                const aufit::CiIter &c = ci[(size_t)j * nq + 2 * a + which];
+                const size_t e = (size_t)j * nalpha + a;
+                (which ? out->ci0 : out->ci)[e] = c.cival;
+                (which ? out->cs0 : out->cs)[e] = c.seval;
+                (which ? out->ei0 : out->ei)[e] = c.eival;
+                out->ci_ret[2 * e + which] = c.ret;
+                out->ci_warn[2 * e + which] = c.degenerate_warning ? 1 : (c.noconv_warning ? 2 : 0);
+                out->ci_warnval[2 * e + which] = c.warn_value;
+            }
+    return 0;
+}
+
+}  // namespace audriver
+
+// ---- C export for the Python pipeline (consel_b200/pipeline.py)
+extern "C" int chost_au_run(int cm, int kk, const double *rr, const int *bb, int i0, double threshold,
+                            const double *median, const cgpu_rowsum *r0, int nalpha, const double *alpha,
+                            int fitmode, double kappa, audriver::QueryFn query, void *ctx,
+                            double *pv2 /*cm x 2: au, np*/, double *se2 /*cm x 2*/, double *ax7 /*cm x 7*/,
+                            double *ci6 /*6 x cm x nalpha: CI SE EI CI0 SE0 EI0*/, int *ret /*cm*/) {
+    audriver::Input in;
+    in.cm = cm; in.kk = kk; in.rr = rr; in.bb = bb; in.i0 = i0; in.threshold = threshold;
+    in.median = median; in.r0 = r0; in.nalpha = nalpha; in.alpha = alpha; in.confidence = ci6 != nullptr;
+    aufit::Options opt;
+    opt.fitmode = fitmode;
+    opt.kappa = kappa;
+    audriver::Output o;
+    int rc = audriver::run(in, opt, query, ctx, &o);
+    if (rc) return rc;
+    for (int i = 0; i < cm; i++) {
+        pv2[2 * i] = o.pv[i]; pv2[2 * i + 1] = o.pv0[i];
+        se2[2 * i] = o.se[i]; se2[2 * i + 1] = o.se0[i];
+        double *ax = ax7 + 7 * (size_t)i;
+        ax[0] = o.pf[i]; ax[1] = o.rss[i]; ax[2] = o.df[i]; ax[3] = o.beta[3 * (size_t)i];
+        ax[4] = o.beta[3 * (size_t)i + 1]; ax[5] = o.th[i]; ax[6] = o.beta[3 * (size_t)i + 2];
+        if (ret) ret[i] = o.ret[i];
+    }
+    if (ci6) {
+        const size_t n2 = (size_t)cm * nalpha;
+        const std::vector<double> *m[6] = {&o.ci, &o.cs, &o.ei, &o.ci0, &o.cs0, &o.ei0};
+        for (int t = 0; t < 6; t++) std::copy(m[t]->begin(), m[t]->end(), ci6 + t * n2);
+    }
+    return 0;
+}

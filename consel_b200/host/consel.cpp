@@ -14,12 +14,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <atomic>
 #include <string>
-#include <thread>
 #include <vector>
 
 #include "../../include/consel_gpu.h"
+#include "audriver.h"
 #include "aufit.h"
 #include "refio.h"
 #include "specfun.h"
@@ -37,29 +36,6 @@ static void dots(int n) {
     } while (0)
 
 static const double kHuge = 1.0e30;  // src/consel.c:155
-
-// the per-item fits of one lockstep round are independent: spread them over the host cores
-template <typename F>
-static void parallel_for(int n, F body) {
-    unsigned hw = std::thread::hardware_concurrency();
-    int nt = (int)std::min<unsigned>(hw ? hw : 1, (unsigned)((n + 15) / 16));
-    if (refio::debugmode > 0) nt = 1;  // keep debug traces in item order
-    if (nt <= 1) {
-        for (int i = 0; i < n; i++) body(i);
-        return;
-    }
-    std::atomic<int> next{0};
-    std::vector<std::thread> th;
-    for (int t = 0; t < nt; t++)
-        th.emplace_back([&] {
-            for (;;) {
-                int i0 = next.fetch_add(16);
-                if (i0 >= n) break;
-                for (int i = i0; i < std::min(n, i0 + 16); i++) body(i);
-            }
-        });
-    for (auto &t : th) t.join();
-}
 
 struct Assoc {
     std::vector<int> ptr{0}, idx;
@@ -345,112 +321,49 @@ int main(int argc, char **argv) {
         printf(opt.fitmode == aufit::FIT_WLS ? "WLS (very fast)" : "MLE (fast)");
         printf(" fitting");
         fflush(stdout);
-        const double t0 = cpu_seconds();
 
         // starting point of every item: the median of the r~1 row (src/consel.c:2765)
         std::vector<int> rank(cm, nb0 / 2);
         std::vector<double> med(cm);
         CG(cgpu_order_stat(reps, i0, rank.data(), med.data()));
-        std::vector<aufit::VcIter> vc;
-        vc.reserve(cm);
-        for (int i = 0; i < cm; i++) vc.emplace_back(med[i], threshold);
-        std::vector<double> thr(cm);
-        std::vector<cgpu_rowsum> rs((size_t)cm * kk);
-        for (int round = 0; round < opt.vcloopmax; round++) {
-            bool any = false;
-            for (int i = 0; i < cm; i++) {
-                thr[i] = vc[i].x;
-                any = any || !vc[i].done;
-            }
-            if (!any) break;
-            CG(cgpu_count_query(reps, 1, thr.data(), rs.data()));
-            parallel_for(cm, [&](int i) {
-                if (vc[i].done) return;
-                std::vector<double> cnts(kk);
-                for (int k = 0; k < kk; k++) cnts[k] = cgpu_smooth_count(&rs[(size_t)i * kk + k], bb[k], thr[i]);
-                vc[i].step(cnts.data(), rr.data(), bbd.data(), kk, opt);
-            });
-        }
+        audriver::Input ain;
+        ain.cm = cm; ain.kk = kk; ain.rr = rr.data(); ain.bb = bb.data(); ain.i0 = i0; ain.threshold = threshold;
+        ain.median = med.data(); ain.r0 = r0.data(); ain.nalpha = nalpha; ain.alpha = alphavec.data();
+        audriver::Output ao;
+        auto query = [](void *ctx, int nq, const double *thr, cgpu_rowsum *out) {
+            return cgpu_count_query(static_cast<const cgpu_reps *>(ctx), nq, thr, out);
+        };
+        if (audriver::run(ain, opt, query, reps, &ao) != 0) die("%s", cgpu_last_error());
         for (int i = 0; i < cm; i++) {
             dprint(1, "\n# rank=%d item=%d", i + 1, orderv[i] + 1);
-            const aufit::VcIter &it = vc[i];
-            const int ret = it.done ? it.ret : 2;
-            dprint(1, "\n# ret=%d", ret);
-            pvvec[i] = it.pv; sevec[i] = it.se; pv0vec[i] = it.pv0; se0vec[i] = it.se0;
-            rssvec[i] = it.rss; dfvec[i] = it.df; thvec[i] = it.th_out;
-            if (ret) {
-                pfvec[i] = 0.0;
+            dprint(1, "\n# ret=%d", ao.ret[i]);
+            pvvec[i] = ao.pv[i]; sevec[i] = ao.se[i]; pv0vec[i] = ao.pv0[i]; se0vec[i] = ao.se0[i];
+            rssvec[i] = ao.rss[i]; dfvec[i] = ao.df[i]; thvec[i] = ao.th[i]; pfvec[i] = ao.pf[i];
+            if (ao.ret[i]) {
                 warn("regression degenerated: df[%d]=%g", i + 1, dfvec[i]);
             } else {
-                pfvec[i] = specfun::pochisq(rssvec[i], (int)dfvec[i]);
                 if (pfvec[i] < 0.01) warn("theory does not fit well: pfit[%d]=%.4f", i + 1, pfvec[i]);
-                for (int c = 0; c < 3; c++) beta[3 * (size_t)i + c] = it.beta[c];
+                for (int c = 0; c < 3; c++) beta[3 * (size_t)i + c] = ao.beta[3 * (size_t)i + c];
             }
             putchar('.');
         }
         fflush(stdout);
-        const double t1 = cpu_seconds();
-        printf("\n# time elapsed for AU test is t=%g sec", t1 - t0);
+        printf("\n# time elapsed for AU test is t=%g sec", ao.t_fit_sec);
 
         // ---- confidence limits (invtpval for au and bp)
         printf("\n# ALPHA:");
         for (int i = 0; i < nalpha; i++) printf("%g ", alphavec[i]);
         printf("\n# calculating confidence intervals");
-        const int nq = 2 * nalpha;
-        std::vector<aufit::CiIter> ci;
-        ci.reserve((size_t)cm * nq);
+        cimat = ao.ci; csmat = ao.cs; eimat = ao.ei; ci0mat = ao.ci0; cs0mat = ao.cs0; ei0mat = ao.ei0;
         for (int jx = 0; jx < cm; jx++) {
-            const cgpu_rowsum &e = r0[(size_t)jx * kk + i0];
-            for (int a = 0; a < nalpha; a++) {
-                ci.emplace_back(e.min1, e.max1, alphavec[a], opt.kappa);
-                ci.emplace_back(e.min1, e.max1, alphavec[a], -1.0);
-            }
-        }
-        // at most 16 thresholds per item and query
-        const int qchunk = 16;
-        std::vector<double> cthr;
-        std::vector<cgpu_rowsum> crs;
-        for (int round = 0; round < opt.ciloopmax; round++) {
-            bool any = false;
-            for (auto &c : ci) any = any || !c.done;
-            if (!any) break;
-            for (int q0 = 0; q0 < nq; q0 += qchunk) {
-                const int nqc = std::min(qchunk, nq - q0);
-                cthr.assign((size_t)cm * nqc, 0.0);
-                for (int jx = 0; jx < cm; jx++)
-                    for (int q = 0; q < nqc; q++) cthr[(size_t)jx * nqc + q] = ci[(size_t)jx * nq + q0 + q].x;
-                crs.resize((size_t)cm * kk * nqc);
-                CG(cgpu_count_query(reps, nqc, cthr.data(), crs.data()));
-                parallel_for(cm, [&](int jx) {
-                    std::vector<double> cnts(kk);
-                    for (int q = 0; q < nqc; q++) {
-                        aufit::CiIter &c = ci[(size_t)jx * nq + q0 + q];
-                        if (c.done) continue;
-                        const double t = cthr[(size_t)jx * nqc + q];
-                        for (int k = 0; k < kk; k++)
-                            cnts[k] = cgpu_smooth_count(&crs[((size_t)jx * kk + k) * nqc + q], bb[k], t);
-                        c.step(cnts.data(), rr.data(), bbd.data(), kk, opt);
-                    }
-                });
-            }
-        }
-        cimat.resize((size_t)cm * nalpha); csmat = cimat; eimat = cimat;
-        ci0mat = cimat; cs0mat = cimat; ei0mat = cimat;
-        for (int jx = 0; jx < cm; jx++) {
-            for (int a = 0; a < nalpha; a++) {
+            for (int a = 0; a < nalpha; a++)
                 for (int which = 0; which < 2; which++) {
-                    const aufit::CiIter &c = ci[(size_t)jx * nq + 2 * a + which];
+                    const size_t e = 2 * ((size_t)jx * nalpha + a) + which;
                     dprint(1, "\n# invtpval item=%d alpha=%g ", jx + 1, alphavec[a]);
-                    if (c.degenerate_warning) warn("degenerecy in pval df=%g", c.warn_value);
-                    if (c.noconv_warning) warn("no convergence in ci: ei=%6.3f", c.warn_value);
-                    if (c.ret) printf(" %s item=%2d, alpha=%4.2f", which ? "bp" : "au", jx + 1, alphavec[a]);
-                    std::vector<double> &cm_ = which ? ci0mat : cimat, &cs_ = which ? cs0mat : csmat,
-                                        &ce_ = which ? ei0mat : eimat;
-                    cm_[(size_t)jx * nalpha + a] = c.cival;
-                    cs_[(size_t)jx * nalpha + a] = c.seval;
-                    ce_[(size_t)jx * nalpha + a] = c.eival;
+                    if (ao.ci_warn[e] == 1) warn("degenerecy in pval df=%g", ao.ci_warnval[e]);
+                    if (ao.ci_warn[e] == 2) warn("no convergence in ci: ei=%6.3f", ao.ci_warnval[e]);
+                    if (ao.ci_ret[e]) printf(" %s item=%2d, alpha=%4.2f", which ? "bp" : "au", jx + 1, alphavec[a]);
                 }
-            }
             putchar('.');
         }
         fflush(stdout);

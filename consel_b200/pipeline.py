@@ -1,0 +1,210 @@
+"""In-process makermt -> consel (no .rmt round trip, the shape the reference
+ships as makerep, src/makerep.c:304-376).
+
+The replicate blocks stay on the device; statistics, count queries and the KH/SH tests
+run through the C ABI; the per-item AU fit runs in the host library libconselhost.so
+(consel_b200/host/audriver.cpp, the same lockstep driver the `consel` program uses).
+With torch.distributed initialised and cgpu_set_shard(rank, world) in effect, every rank
+holds a column shard of every scale and the only collectives are the small combines of
+consel_b200.dist.
+
+Host logic here mirrors src/consel.c: read_assoc (item order, :459-541), do_batest
+(:1311-1340), find_i0 (:1778-1789), getseval (:2151-2158) and the .pv column layout of
+write_pv (:1611-1683): [bp, pp, kh, sh, wkh, wsh, au, np].
+"""
+from __future__ import annotations
+
+import ctypes as C
+import functools
+import time
+
+import numpy as np
+
+from . import api, dist as cdist
+
+_host = None
+QUERY_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_double), C.POINTER(api.RowSum))
+
+
+def host_lib() -> C.CDLL:
+    global _host
+    if _host is None:
+        p = api.PKG / "libconselhost.so"
+        if not p.exists():
+            raise api.CgpuError(-2, f"{p} is missing: run __graft_entry__.build()")
+        api.load()  # libconselhost.so resolves cgpu_smooth_count from libconselgpu.so
+        _host = C.CDLL(str(p), mode=C.RTLD_GLOBAL)
+    return _host
+
+
+def find_i0(rr) -> int:
+    return int(np.argmin(np.abs(np.asarray(rr, dtype=np.float64) - 1.0)))
+
+
+def identity_assoc(K: int):
+    return np.arange(K + 1, dtype=np.int32), np.arange(K, dtype=np.int32)
+
+
+def item_order(datvec, ass_ptr, ass_idx, nosort: bool = False):
+    """read_assoc: observed statistic vectors (max over the complement minus each member,
+    ascending) and the item order by compdvec (length first, then lexicographic)."""
+    datvec = np.asarray(datvec, dtype=np.float64)
+    cm = len(ass_ptr) - 1
+    keys = []
+    for e in range(cm):
+        a = np.asarray(ass_idx[ass_ptr[e]:ass_ptr[e + 1]])
+        mask = np.ones(len(datvec), bool)
+        mask[a] = False
+        mx = datvec[mask].max() if mask.any() else -1.0e30
+        mx = max(mx, -1.0e30)
+        keys.append(np.sort(mx - datvec[a]))
+
+    def cmp(i, j):
+        x, y = keys[i], keys[j]
+        out = -1 if len(x) < len(y) else (1 if len(x) > len(y) else 0)
+        for a, b in zip(x, y):
+            if a < b:
+                return -1
+            if a > b:
+                return 1
+        return out
+
+    order = list(range(cm)) if nosort else sorted(range(cm), key=functools.cmp_to_key(cmp))
+    obs = np.array([keys[i][0] for i in order])
+    ptr, idx = [0], []
+    for i in order:
+        idx += [int(v) for v in ass_idx[ass_ptr[i]:ass_ptr[i + 1]]]
+        ptr.append(len(idx))
+    return np.array(order, dtype=np.int32), obs, np.array(ptr, dtype=np.int32), np.array(idx, dtype=np.int32)
+
+
+def _distributed() -> bool:
+    try:
+        import torch.distributed as dist
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    except Exception:
+        return False
+
+
+def _dist_order_stat(reps: api.Reps, s: int, rank_k: np.ndarray) -> np.ndarray:
+    """k-th smallest of sharded rows: bisection on the 64 bits of the order-preserving
+    integer image of a double, one combined count query per bit (exact)."""
+    cm = reps.cm
+    res = np.zeros(cm, dtype=np.uint64)
+
+    def unkey(k):
+        neg = (k >> np.uint64(63)) == 0
+        u = np.where(neg, ~k, k & np.uint64(0x7FFFFFFFFFFFFFFF))
+        return u.view(np.float64)
+
+    for bit in range(63, -1, -1):
+        cand = res | (np.uint64(1) << np.uint64(bit))
+        # count(key < cand) == count(v < unkey(cand)) == count(v <= prev_double(unkey(cand)))
+        t = np.nextafter(unkey(cand), -np.inf)
+        t = np.where(np.isnan(t), np.inf, t)
+        q = cdist.combine_rowsums(reps.count_query(t.reshape(cm, 1)))
+        cnt = q["cnt"][:, s, 0]
+        res = np.where(cnt <= rank_k, cand, res)
+    return unkey(res)
+
+
+def consel(reps: api.Reps, datvec, rr, bb, ass=None, alpha=(0.05, 0.10, 0.5, 0.90, 0.95), threshold: float = 0.0,
+           kappa: float = 1.0, fitmode: int = 1, do_mc: bool = True, do_au: bool = True, confidence: bool = True,
+           nosort: bool = False, varadd: float = 1.0) -> dict:
+    """Everything `consel foo` computes from foo.rmt, from device-resident replicate blocks."""
+    datvec = np.asarray(datvec, dtype=np.float64)
+    rr = np.ascontiguousarray(rr, dtype=np.float64)
+    bb = np.ascontiguousarray(bb, dtype=np.int32)
+    K, kk = len(datvec), len(rr)
+    ptr0, idx0 = identity_assoc(K) if ass is None else ass
+    order, obs, ptr, idx = item_order(datvec, ptr0, idx0, nosort)
+    cm = len(order)
+    i0 = find_i0(rr)
+    nb0 = int(bb[i0])
+    dist_mode = _distributed()
+    timing = {}
+
+    w = np.exp(datvec - datvec.max())  # do_batest
+    w = w / np.add.accumulate(w)[-1]
+    pp = np.array([np.add.accumulate(w[idx[ptr[i]:ptr[i + 1]]])[-1] for i in range(cm)])
+
+    pv = np.zeros((cm, 8))
+    se = np.zeros((cm, 8))
+    pv[:, 1] = pp
+    t0 = time.perf_counter()
+    if do_mc:
+        if dist_mode:  # the tests need every replicate of scale i0 on one device (sequential row sums)
+            import torch.distributed as dist
+            blocks = reps.download()
+            whole = cdist.gather_columns(blocks[i0], nb0)
+            api.set_shard(0, 1)
+            one = api.Reps.upload([whole])
+            kh, sh, wkh, wsh = one.mctest(0, datvec, ptr, idx, varadd)
+            one.free()
+            api.set_shard(dist.get_rank(), dist.get_world_size())
+        else:
+            kh, sh, wkh, wsh = reps.mctest(i0, datvec, ptr, idx, varadd)
+        pv[:, 2], pv[:, 3], pv[:, 4], pv[:, 5] = kh, sh, wkh, wsh
+    timing["mctest_s"] = time.perf_counter() - t0
+
+    t0 = time.perf_counter()
+    reps.stats_build(ptr, idx)
+    q0 = reps.count_query(np.full((cm, 1), threshold))
+    if dist_mode:
+        q0 = cdist.combine_rowsums(q0)
+    timing["stats_s"] = time.perf_counter() - t0
+    bp = np.array([1.0 - (1.0 - api.smooth_count(q0[i, i0, 0], nb0, threshold) / nb0) for i in range(cm)])
+    pv[:, 0] = bp
+    for c in (0, 2, 3, 4, 5):
+        se[:, c] = np.sqrt(pv[:, c] * (1.0 - pv[:, c]) / nb0)
+    out = dict(item=order, stat=obs, pv=pv, se=se, cnt=q0["cnt"][:, :, 0].copy(), i0=i0, timing=timing)
+
+    if do_au and kk >= 2:
+        t0 = time.perf_counter()
+        rank_k = np.full(cm, nb0 // 2, dtype=np.int32)
+        med = _dist_order_stat(reps, i0, rank_k) if dist_mode else reps.order_stat(i0, rank_k)
+        r0 = np.ascontiguousarray(q0[:, :, 0])
+        alpha = np.ascontiguousarray(alpha, dtype=np.float64)
+        pv2, se2, ax7 = np.zeros((cm, 2)), np.zeros((cm, 2)), np.zeros((cm, 7))
+        ci6 = np.zeros((6, cm, len(alpha)))
+        ret = np.zeros(cm, dtype=np.int32)
+        lib = host_lib()
+        if dist_mode:
+            def py_query(ctx, nq, thr_p, out_p):
+                thr = np.ctypeslib.as_array(thr_p, shape=(cm, nq)).copy()
+                q = cdist.combine_rowsums(reps.count_query(thr))
+                C.memmove(out_p, q.ctypes.data, q.nbytes)
+                return 0
+            cb = QUERY_FN(py_query)
+            ctx = None
+        else:
+            cb = C.cast(api.load().cgpu_count_query, QUERY_FN)
+            ctx = reps._h
+        rc = lib.chost_au_run(cm, kk, api._dp(rr), api._ip(bb), i0, C.c_double(threshold), api._dp(med),
+                              r0.ctypes.data_as(C.POINTER(api.RowSum)), len(alpha), api._dp(alpha), fitmode,
+                              C.c_double(kappa), cb, ctx, api._dp(pv2), api._dp(se2), api._dp(ax7),
+                              api._dp(ci6) if confidence else None, api._ip(ret))
+        if rc:
+            raise api.CgpuError(rc, api.load().cgpu_last_error().decode())
+        pv[:, 6:8], se[:, 6:8] = pv2, se2
+        out.update(ax=ax7, ci=ci6 if confidence else None, alpha=alpha, ret=ret)
+        timing["au_s"] = time.perf_counter() - t0
+    return out
+
+
+def run(L, rr, bb, seed: int, rng_mode: int = api.RNG_MT19937, sum_mode: int = api.SUM_STRICT, matrix=None, **kw) -> dict:
+    """makermt + consel in one process: L (K x n) -> p-value table, nothing touches a file."""
+    L = np.ascontiguousarray(L, dtype=np.float64)
+    datvec, bn, rr1 = api.scale_setup(L, rr)
+    t0 = time.perf_counter()
+    mat = matrix if matrix is not None else api.Matrix(L)
+    reps = mat.scaleboot(bn, bb, seed, 0, rng_mode, sum_mode)
+    t_boot = time.perf_counter() - t0
+    res = consel(reps, datvec, rr1, bb, **kw)
+    res["timing"]["makermt_s"] = t_boot
+    res["timing"]["device_ms"] = api.last_timing()
+    res.update(datvec=datvec, rr=rr1, bb=np.asarray(bb, dtype=np.int32))
+    reps.free()
+    if matrix is None:
+        mat.free()
+    return res

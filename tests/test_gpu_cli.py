@@ -78,3 +78,29 @@ def test_full_pipeline_against_fresh_reference_run(gold, orc, tmp_path):
     same_numbers(tmp_path / "our.pv", tmp_path / "ref.pv", orc)
     same_numbers(tmp_path / "our.ci", tmp_path / "ref.ci", orc)
     assert run("catpv", ["our"], tmp_path).replace("our.pv", "X") == orc.run_ref("catpv", ["ref"], tmp_path).replace("ref.pv", "X")
+
+
+def test_in_process_pipeline_matches_reference_pv(gold, orc):
+    """consel_b200.pipeline.run: makermt+consel without files == the reference's .pv/.ci"""
+    import consel_b200 as cg
+    from consel_b200 import pipeline
+    cg.init()
+    cg.set_shard(0, 1)
+    for name, seed in (("g100", 1234), ("tiny", 7)):
+        ref_pv = orc.read_pv(gold / f"{name}.pv")
+        rmt = orc.read_rmt(gold / f"{name}.rmt")
+        if name == "g100":
+            L, rr = orc.read_lnf(gold / "mam15.lnf"), [0.5, 0.6, 0.7, 0.8, 0.9, 1.0, 1.1, 1.2, 1.3, 1.4]
+        else:
+            L = orc.read_mt(gold / "tiny.mt")
+            rr, _ = orc.read_pa(gold / "tiny.pa")
+        res = pipeline.run(L, rr, rmt["bb"], seed)
+        assert np.array_equal(res["item"], ref_pv["item"])
+        assert np.allclose(res["stat"], ref_pv["stat"], rtol=6e-9)
+        assert np.allclose(res["pv"], ref_pv["pv"], rtol=6e-9, atol=1e-12), (name, res["pv"], ref_pv["pv"])
+        assert np.allclose(res["se"], ref_pv["se"], rtol=6e-9, atol=1e-12)
+        assert np.allclose(res["ax"], ref_pv["ax"], rtol=6e-9, atol=1e-12)
+        assert np.array_equal(res["cnt"], orc.read_cnt(gold / f"{name}.cnt")["cnt"])
+    # the tensor-core sums give the same table to printed precision (catpv prints 3 decimals)
+    res8 = pipeline.run(L, rr, rmt["bb"], 7, sum_mode=cg.SUM_INT8)
+    assert np.allclose(res8["pv"], ref_pv["pv"], rtol=1e-6, atol=1e-9)
