@@ -8,8 +8,11 @@ makermt resampling pass (all scales) over one synthetic site-log-likelihood matr
 Workload = BASELINE.json configs[1] ("C2"): K=105 trees x n=3414 sites, 10 scales
 r=0.5..1.4, 100000 replicates per scale PER GPU (replicates are sharded over ranks with
 no data-path collective, so N GPUs resample N x 100000 replicates per scale: weak
-scaling), reference-parity mode: MT19937 stream of the reference (seed 7) + strict
-order of operations, i.e. the output is bit-identical to `makermt -s 7`.
+scaling).  Headline mode = the north star's parity contract: the reference's own seeded
+MT19937 index stream (site counts bit-exact) + exact fixed-point sums on the tcgen05 int8
+tensor cores (replicate sums = the correctly rounded exact sums, <= 1e-12 relative to
+`makermt -s 7`).  The line also carries `modes`: the bit-identical strict fp64 mode, the
+fast fp64 mode and the counter-based (Philox) resampler, each timed the same way.
 
   value  device-resident: L already in HBM, replicate blocks left in HBM
          (cgpu_scaleboot_dev), timed with CUDA events on the library's stream.
@@ -58,8 +61,9 @@ def config(world: int) -> dict:
                     "r=0.5..1.4 x 100000 replicates per scale per GPU",
         "K": K, "n": N_SITES, "scales": len(RR), "replicates_per_scale_per_gpu": B_PER_SCALE,
         "replicates_per_scale_total": B_PER_SCALE * world,
-        "rng_mode": "mt19937 reference stream (seed 7), device jump-ahead",
-        "sum_mode": "strict (bit-identical to src/makermt.c:65-70)",
+        "rng_mode": "mt19937 reference stream (seed 7), device jump-ahead: site counts bit-exact",
+        "sum_mode": "int8: exact fixed-point sums on tcgen05 tensor cores, one rounding (<=1e-12 rel. to the "
+                    "reference; `modes.strict_mt` is the bit-identical fp64 mode)",
         "l2": "per-scale working set (index buffer 1.9 GB + counts 0.35 GB + replicate block 84 MB) "
               "exceeds the 126 MB L2; a 256 MB buffer is also written between timed steps",
     }
@@ -148,31 +152,45 @@ def run_ours(args) -> None:
 
     # ---- device-resident arm
     mat = cg.Matrix(L)
-    for w in range(args.warmup):
-        mat.scaleboot(bn, bb, 7).free()
+    flush_ctr = [0]
+
+    def timed_steps(rng_mode, sum_mode, steps, warmup):
+        for w in range(warmup):
+            mat.scaleboot(bn, bb, 7, rng_mode=rng_mode, sum_mode=sum_mode).free()
+        dev, wall, ph = 0.0, 0.0, {}
+        for step in range(steps):
+            flush_ctr[0] += 1
+            flush.fill_(flush_ctr[0] & 0xFF)
+            barrier()
+            t0 = time.perf_counter()
+            reps = mat.scaleboot(bn, bb, 7, rng_mode=rng_mode, sum_mode=sum_mode)  # returns after the stream drained
+            torch.cuda.synchronize()
+            wall += (time.perf_counter() - t0) * 1e3
+            tm = cg.last_timing()
+            dev += tm["total"]
+            for k_, v in tm.items():
+                ph[k_] = ph.get(k_, 0.0) + v / steps
+            reps.free()
+        barrier()
+        return max_over_ranks(dev), max_over_ranks(wall), ph
+
+    HEAD = (cg.RNG_MT19937, cg.SUM_INT8)
+    timed_steps(*HEAD, 0, args.warmup)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     launches0 = cg.launch_count()
-    dev_ms, wall_ms, contract_ms, phases = 0.0, 0.0, 0.0, {}
-    for step in range(args.steps):
-        flush.fill_(step & 0xFF)
-        barrier()
-        t0 = time.perf_counter()
-        reps = mat.scaleboot(bn, bb, 7)  # synchronous: returns after the stream drained
-        torch.cuda.synchronize()
-        wall_ms += (time.perf_counter() - t0) * 1e3
-        tm = cg.last_timing()
-        dev_ms += tm["total"]
-        contract_ms += tm["contract"]
-        for k_, v in tm.items():
-            phases[k_] = phases.get(k_, 0.0) + v / args.steps
-        reps.free()
-    barrier()
+    dev_ms, wall_ms, phases = timed_steps(*HEAD, args.steps, 0)
     launches = cg.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
-    dev_ms = max_over_ranks(dev_ms)
-    wall_ms = max_over_ranks(wall_ms)
+    contract_ms = phases["contract"] * args.steps
+    modes = {}
+    side_steps = max(1, min(args.steps, 3))
+    for name, rm, sm in (("strict_mt", cg.RNG_MT19937, cg.SUM_STRICT), ("fast_mt", cg.RNG_MT19937, cg.SUM_FAST),
+                         ("int8_philox", cg.RNG_PHILOX, cg.SUM_INT8)):
+        d, w_, ph = timed_steps(rm, sm, side_steps, 2)
+        modes[name] = {"ms_per_step": d / side_steps, "value": acc_per_step_total * side_steps / (d * 1e-3),
+                       "phases_ms_per_step": ph}
 
     # ---- end-to-end arm: host buffers through cgpu_scaleboot_all
     Lh = torch.empty((K, N_SITES), dtype=torch.float64, pin_memory=True)
@@ -183,13 +201,13 @@ def run_ours(args) -> None:
     h2d = int(L.nbytes)
     d2h = int(K * (b1 - b0) * 8 * len(RR))
     e2e_steps = max(1, min(args.steps, 3))
-    cg.scaleboot_all(Lh.numpy(), bn, bb, 7, out=outs)  # warm-up (page-locks, pool growth)
+    cg.scaleboot_all(Lh.numpy(), bn, bb, 7, sum_mode=cg.SUM_INT8, out=outs)  # warm-up (page-locks, pool growth)
     e2e_ms = 0.0
     for step in range(e2e_steps):
         flush.fill_(step & 0xFF)
         barrier()
         t0 = time.perf_counter()
-        cg.scaleboot_all(Lh.numpy(), bn, bb, 7, out=outs)
+        cg.scaleboot_all(Lh.numpy(), bn, bb, 7, sum_mode=cg.SUM_INT8, out=outs)
         checksum = float(outs[0][0, 0])  # the step's result is read on the host
         e2e_ms += (time.perf_counter() - t0) * 1e3
     barrier()
@@ -201,44 +219,46 @@ def run_ours(args) -> None:
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (contract_kernel), measured live
+    # ---- roofline of the dominant kernel (gemm_i8_kernel), measured live
     import ctypes as C
     tf = C.c_double()
     cg.api._check(cg.load().cgpu_bench_fp64_peak(C.byref(tf)))
     n_contract = len(RR) * args.steps
-    t_launch = contract_ms / n_contract * 1e-3
+    t_launch = contract_ms / n_contract * 1e-3   # gemm_i8_kernel + fx_combine_kernel of one scale
     b_loc = b1 - b0
-    flops_launch = 2.0 * K * N_SITES * b_loc
-    bytes_launch = 8.0 * K * N_SITES + float(N_SITES) * b_loc + 8.0 * K * b_loc
+    S_SLICES = 8   # fixed-point slices of this matrix (57-bit data: see DESIGN.md 4.4)
+    ops_launch = 2.0 * S_SLICES * K * N_SITES * b_loc
+    bytes_launch = float(S_SLICES) * K * N_SITES + float(N_SITES) * b_loc + 4.0 * S_SLICES * K * b_loc * 2 + 8.0 * K * b_loc
     peaks = {}
     try:
         peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
     except Exception:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    bf16_peak = peaks.get("bf16_tflops", 1590.0)
     traffic = None
     tp = ROOT / "profiles" / "contract_traffic.json"
     if tp.exists():
         try:
-            traffic = json.loads(tp.read_text()).get("dram_bytes_per_launch_bench_config")
+            traffic = json.loads(tp.read_text()).get("gemm_i8_dram_bytes_per_launch_bench_config")
         except Exception:
             traffic = None
     roofline = {
-        "kernel": "contract_kernel<TK=4, strict, ALGO 2: dense DFMA + flagged DMUL/DADD fix-ups>",
-        "bound": "fp64",
-        "achieved": flops_launch / t_launch / 1e12,
-        "peak": tf.value,
-        "unit": "TFLOP/s",
-        "frac": flops_launch / t_launch / 1e12 / tf.value,
-        "peak_source": "measured live in this run: FP64 DFMA loop (cgpu_bench_fp64_peak); MEASURED_PEAKS.json "
-                       "has no FP64 figure",
-        "algorithmic": "2 flops per tree-site accumulation (SURVEY 8d) x K*n*B_s per launch; K=105 fills 105 of the "
-                       "128 tree lanes of a tile (0.82), and counts 3,5,6,7.. (~6% of terms) cost an extra DMUL+DADD "
-                       "to keep the reference's two roundings",
+        "kernel": "gemm_i8_kernel (tcgen05.mma kind::i8, 128x256x128 tiles, TMA SW128, TMEM accumulators) "
+                  "+ fx_combine_kernel",
+        "bound": "tensor",
+        "achieved": ops_launch / t_launch / 1e12,
+        "peak": 2.0 * bf16_peak,
+        "unit": "TOP/s (int8)",
+        "frac": ops_launch / t_launch / 1e12 / (2.0 * bf16_peak),
+        "peak_source": ("2 x bf16_tflops of MEASURED_PEAKS.json (dense int8 issues at twice the bf16 rate on B200; "
+                        "the file has no int8 figure)") if peaks else "2 x fallback bf16 (B200_PROFILING.md)",
+        "algorithmic": "2*S int8-ops per tree-site accumulation (SURVEY 8d), S=8 slices, x K*n*B_s per launch",
         "share_of_step": contract_ms / max(dev_ms, 1e-9),
         "hbm_view": {"achieved": bytes_launch / t_launch / 1e9, "peak": hbm_peak, "unit": "GB/s",
                      "frac": bytes_launch / t_launch / 1e9 / hbm_peak,
                      "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"},
+        "fp64_dfma_peak_tflops_measured_live": tf.value,
         "traffic": traffic,
     }
 
@@ -260,8 +280,9 @@ def run_ours(args) -> None:
         "wall_ms_per_step": wall_ms / args.steps, "phases_ms_per_step": phases,
         "e2e": {"value": acc_per_step_total * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
-                "api": "cgpu_scaleboot_all (pinned host L in, pinned host replicate blocks out)"},
+                "api": "cgpu_scaleboot_all(CGPU_RNG_MT19937, CGPU_SUM_INT8): pinned host L in, pinned host replicate blocks out"},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
+        "modes": modes,
     }
     print(json.dumps(line))
     if world > 1:

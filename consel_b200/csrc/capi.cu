@@ -28,13 +28,18 @@ Globals &G() {
     return g;
 }
 
-int ensure_init() { return G().inited ? CGPU_OK : cgpu_init(-1); }
+int ensure_init() {
+    if (!G().inited) return cgpu_init(-1);
+    (void)cudaGetLastError();  // every entry point starts from a clean error state
+    return CGPU_OK;
+}
 
 // accumulates device time per phase over many (start, stop) event pairs
 struct PhaseTimer {
     struct Span {
         int phase;
         cudaEvent_t a, b;
+        bool ended;
     };
     std::vector<Span> spans;
     cudaStream_t st;
@@ -47,13 +52,16 @@ struct PhaseTimer {
     cudaStream_t cur = nullptr;
     void begin(int phase, cudaStream_t on = nullptr) {
         cur = on ? on : st;
-        Span sp{phase, nullptr, nullptr};
+        Span sp{phase, nullptr, nullptr, false};
         cudaEventCreate(&sp.a);
         cudaEventCreate(&sp.b);
         cudaEventRecord(sp.a, cur);
         spans.push_back(sp);
     }
-    void end() { cudaEventRecord(spans.back().b, cur); }
+    void end() {
+        cudaEventRecord(spans.back().b, cur);
+        spans.back().ended = true;
+    }
     // call after the stream has been synchronised
     void finish(double *ms5) {
         for (int i = 0; i < 6; i++) ms5[i] = 0;
@@ -65,7 +73,10 @@ struct PhaseTimer {
         cudaEventDestroy(t1);
         for (auto &sp : spans) {
             float ms = 0;
-            if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) ms5[sp.phase] += ms;
+            // a span left open by an early error return has no end event: skip it (querying it
+            // would leave a stale "invalid resource handle" for the next launch check)
+            if (sp.ended && cudaEventSynchronize(sp.b) == cudaSuccess && cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess)
+                ms5[sp.phase] += ms;
             cudaEventDestroy(sp.a);
             cudaEventDestroy(sp.b);
         }
@@ -173,7 +184,7 @@ static int mt_prepare(unsigned long seed, unsigned long long stream_offset, unsi
 }
 
 struct Workspace {
-    uint32_t *d_idx = nullptr;
+    unsigned char *d_idx = nullptr;  // uint16 or uint32 site indices (idx_bytes(n))
     unsigned long long *d_counts[2] = {nullptr, nullptr};
     int *d_err = nullptr;
     cudaEvent_t hist_done[2] = {nullptr, nullptr}, contract_done[2] = {nullptr, nullptr}, idx_ready = nullptr;
@@ -197,9 +208,12 @@ struct Workspace {
     }
 };
 
+// host_out (optional): rank-local compact blocks K x nb[s]; the copy of scale s is queued on
+// the copy stream as soon as its last contraction is done, so the D2H of one scale hides
+// behind the compute of the next.
 static int scaleboot_core(DevMatrix &m, int S, const int *bn, const int *bb, unsigned long seed,
                           unsigned long long stream_offset, int rng_mode, int sum_mode, DevReps *reps,
-                          PhaseTimer &pt, cudaStream_t st) {
+                          PhaseTimer &pt, cudaStream_t st, double *const *host_out = nullptr) {
     const bool i8 = sum_mode == CGPU_SUM_INT8;
     if (sum_mode != CGPU_SUM_STRICT && sum_mode != CGPU_SUM_FAST && !i8) {
         set_error(CGPU_EINVAL, "unknown sum_mode %d", sum_mode);
@@ -268,7 +282,7 @@ static int scaleboot_core(DevMatrix &m, int S, const int *bn, const int *bb, uns
         const unsigned long long idx_budget = (unsigned long long)24 << 30;
         idx_whole_run = G().shard_world == 1 && base[S] * 4ull <= idx_budget && base[S] > 0;
         const size_t idx_elems = idx_whole_run ? (size_t)base[S] : (size_t)batch * max_bn;
-        CGPU_CUDA(dev_alloc(&ws.d_idx, idx_elems * sizeof(uint32_t)));
+        CGPU_CUDA(dev_alloc(&ws.d_idx, idx_elems * idx_bytes((uint32_t)n)));
         pt.begin(1);
         CGPU_TRY(mt_prepare(seed, stream_offset, base[S], &plan, st));
         if (idx_whole_run)
@@ -298,9 +312,9 @@ static int scaleboot_core(DevMatrix &m, int S, const int *bn, const int *bb, uns
             if (rng_mode == CGPU_RNG_MT19937) {
                 const unsigned long long lo = base[s] + (unsigned long long)bA * bn[s];
                 const unsigned long long hi = lo + (unsigned long long)nbat * bn[s];
-                const uint32_t *idx_src = ws.d_idx;
+                const unsigned char *idx_src = ws.d_idx;
                 if (idx_whole_run) {
-                    idx_src = ws.d_idx + lo;
+                    idx_src = ws.d_idx + lo * idx_bytes((uint32_t)n);
                 } else {
                     const unsigned long long c0 = lo >> plan.chunk_log2, c1 = (hi - 1) >> plan.chunk_log2;
                     pt.begin(1);
@@ -328,6 +342,23 @@ static int scaleboot_core(DevMatrix &m, int S, const int *bn, const int *bb, uns
             pt.end();
             if (overlap) CGPU_CUDA(cudaEventRecord(ws.contract_done[buf], st));
         }
+        if (host_out && reps->nb[s] > 0) {
+            cudaStream_t cp = G().stream3;
+            cudaEvent_t done;
+            CGPU_CUDA(cudaEventCreateWithFlags(&done, cudaEventDisableTiming));
+            CGPU_CUDA(cudaEventRecord(done, st));
+            CGPU_CUDA(cudaStreamWaitEvent(cp, done, 0));
+            cudaEventDestroy(done);
+            pt.begin(4, cp);
+            CGPU_CUDA(cudaMemcpyAsync(host_out[s], reps->d_rep[s], (size_t)reps->K * reps->nb[s] * sizeof(double),
+                                      cudaMemcpyDeviceToHost, cp));
+            pt.end();
+        }
+    }
+    if (host_out) {
+        // the main stream (and with it every later free) must not run ahead of the copies
+        CGPU_CUDA(cudaEventRecord(ws.idx_ready, G().stream3));
+        CGPU_CUDA(cudaStreamWaitEvent(st, ws.idx_ready, 0));
     }
     int h_err = 0;
     CGPU_CUDA(cudaMemcpyAsync(&h_err, ws.d_err, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -430,6 +461,7 @@ int cgpu_init(int device) {
     g.sm_count = prop.multiProcessorCount;
     CGPU_CUDA(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
     CGPU_CUDA(cudaStreamCreateWithFlags(&g.stream2, cudaStreamNonBlocking));
+    CGPU_CUDA(cudaStreamCreateWithFlags(&g.stream3, cudaStreamNonBlocking));
     {
         // keep freed blocks in the default stream-ordered pool: the per-call workspaces
         // (index/count buffers, replicate blocks) are then recycled without a cudaMalloc
@@ -452,7 +484,8 @@ void cgpu_shutdown(void) {
     dev_free(g.d_jump_table);
     cudaStreamDestroy(g.stream);
     cudaStreamDestroy(g.stream2);
-    g.stream2 = nullptr;
+    cudaStreamDestroy(g.stream3);
+    g.stream2 = g.stream3 = nullptr;
     g.d_jump_table = nullptr;
     g.stream = nullptr;
     g.inited = false;
@@ -556,12 +589,7 @@ int cgpu_scaleboot_all(const double *L, int K, int n, int S, const int *bn, cons
     pt.end();
     DevReps *r = nullptr;
     if (rc == CGPU_OK) rc = alloc_reps(K, S, bb, &r);
-    if (rc == CGPU_OK) rc = scaleboot_core(*m, S, bn, bb, seed, stream_offset, rng_mode, sum_mode, r, pt, st);
-    if (rc == CGPU_OK) {
-        pt.begin(4);
-        rc = reps_download(r, rep_out, st);
-        pt.end();
-    }
+    if (rc == CGPU_OK) rc = scaleboot_core(*m, S, bn, bb, seed, stream_offset, rng_mode, sum_mode, r, pt, st, rep_out);
     cudaStreamSynchronize(st);
     pt.finish(G().last_ms);
     free_reps(r);
@@ -599,7 +627,7 @@ int cgpu_resample_counts(int n, int S, const int *bn, const int *bb, unsigned lo
             if (t < s) base += (unsigned long long)bb[t] * bn[t];
             total += (unsigned long long)bb[t] * bn[t];
         }
-        CGPU_CUDA(dev_alloc(&ws.d_idx, (size_t)nb * bn[s] * sizeof(uint32_t)));
+        CGPU_CUDA(dev_alloc(&ws.d_idx, (size_t)nb * bn[s] * idx_bytes((uint32_t)n)));
         CGPU_TRY(mt_prepare(seed, stream_offset, total, &plan, st));
         const unsigned long long lo = base + (unsigned long long)b0 * bn[s], hi = lo + (unsigned long long)nb * bn[s];
         const unsigned long long c0 = lo >> plan.chunk_log2, c1 = (hi - 1) >> plan.chunk_log2;

@@ -72,6 +72,7 @@ struct Globals {
     int shard_rank = 0, shard_world = 1;
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;  // aux stream of the resample/contract software pipeline
+    cudaStream_t stream3 = nullptr;  // copy stream: D2H of finished scales behind the compute
     uint32_t *d_jump_table = nullptr;  // (MT_MAXLOG+1) x 624 u32
     cudaEvent_t ev[8] = {};
     double last_ms[6] = {0, 0, 0, 0, 0, 0};
@@ -122,13 +123,17 @@ struct DevReps {  // cgpu_reps
 // mt_kernels.cu
 int launch_mt_jump(const uint32_t *d_src, uint32_t *d_dst, const uint32_t *d_poly, int count,
                    cudaStream_t st);
+// site indices are stored as uint16 when they fit (halves the index traffic); n == 0 asks
+// for raw tempered 32-bit words
+inline bool idx_is16(uint32_t n) { return n > 0 && n <= 65536; }
+inline size_t idx_bytes(uint32_t n) { return idx_is16(n) ? 2 : 4; }
 int launch_mt_draw(const uint32_t *d_states, int chunk_log2, unsigned long long first_chunk,
                    int nchunks, unsigned long long lo, unsigned long long hi, uint32_t n,
-                   uint32_t *d_idx, cudaStream_t st);
+                   void *d_idx, cudaStream_t st);
 // resample_kernels.cu
 // counts layout: rows == false -> "BJ8" words (8 replicates interleaved per site);
 //                rows == true  -> plain uint8 rows [replicate][NP] (tensor-core operand)
-int launch_hist_from_idx(const uint32_t *d_idx, int n, int NP, int bn, int nb,
+int launch_hist_from_idx(const void *d_idx, int n, int NP, int bn, int nb,
                          unsigned long long *d_counts, int *d_err, cudaStream_t st, bool rows = false);
 int launch_hist_philox(unsigned long long seed, int scale, int b_first, int n, int NP, int bn, int nb,
                        unsigned long long *d_counts, int *d_err, cudaStream_t st, bool rows = false);

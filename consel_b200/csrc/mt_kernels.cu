@@ -119,10 +119,10 @@ __device__ __forceinline__ uint32_t site_index(uint32_t y, uint32_t n, double dn
     return (uint32_t)k;
 }
 
-template <int PATH>
+template <int PATH, typename IdxT>
 __global__ void __launch_bounds__(DRAW_THREADS)
 mt_draw_kernel(const uint32_t *__restrict__ states, int chunk_log2, unsigned long long first_chunk,
-               unsigned long long lo, unsigned long long hi, uint32_t n, uint32_t *__restrict__ idx) {
+               unsigned long long lo, unsigned long long hi, uint32_t n, IdxT *__restrict__ idx) {
     __shared__ uint32_t buf[2][MT_N + 1];
     const int tid = threadIdx.x;
     const unsigned long long chunk = first_chunk + blockIdx.x;
@@ -156,7 +156,7 @@ mt_draw_kernel(const uint32_t *__restrict__ states, int chunk_log2, unsigned lon
         if (d0 + MT_N > lo) {
             for (int i = tid; i < MT_N; i += DRAW_THREADS) {
                 unsigned long long d = d0 + i;
-                if (d >= lo && d < d_end) idx[d - lo] = site_index<PATH>(mt_temper(nw[i]), n, dn);
+                if (d >= lo && d < d_end) idx[d - lo] = (IdxT)site_index<PATH>(mt_temper(nw[i]), n, dn);
             }
         }
         cur ^= 1;
@@ -167,14 +167,18 @@ mt_draw_kernel(const uint32_t *__restrict__ states, int chunk_log2, unsigned lon
 
 int launch_mt_draw(const uint32_t *d_states, int chunk_log2, unsigned long long first_chunk,
                    int nchunks, unsigned long long lo, unsigned long long hi, uint32_t n,
-                   uint32_t *d_idx, cudaStream_t st) {
+                   void *d_idx, cudaStream_t st) {
     if (nchunks <= 0) return CGPU_OK;
+    uint32_t *i32 = static_cast<uint32_t *>(d_idx);
+    uint16_t *i16 = static_cast<uint16_t *>(d_idx);
     if (n == 0)
-        mt_draw_kernel<2><<<nchunks, DRAW_THREADS, 0, st>>>(d_states, chunk_log2, first_chunk, lo, hi, n, d_idx);
+        mt_draw_kernel<2, uint32_t><<<nchunks, DRAW_THREADS, 0, st>>>(d_states, chunk_log2, first_chunk, lo, hi, n, i32);
+    else if (idx_is16(n))
+        mt_draw_kernel<0, uint16_t><<<nchunks, DRAW_THREADS, 0, st>>>(d_states, chunk_log2, first_chunk, lo, hi, n, i16);
     else if (n < (1u << 21))
-        mt_draw_kernel<0><<<nchunks, DRAW_THREADS, 0, st>>>(d_states, chunk_log2, first_chunk, lo, hi, n, d_idx);
+        mt_draw_kernel<0, uint32_t><<<nchunks, DRAW_THREADS, 0, st>>>(d_states, chunk_log2, first_chunk, lo, hi, n, i32);
     else
-        mt_draw_kernel<1><<<nchunks, DRAW_THREADS, 0, st>>>(d_states, chunk_log2, first_chunk, lo, hi, n, d_idx);
+        mt_draw_kernel<1, uint32_t><<<nchunks, DRAW_THREADS, 0, st>>>(d_states, chunk_log2, first_chunk, lo, hi, n, i32);
     CGPU_LAUNCH_CHECK();
     return CGPU_OK;
 }

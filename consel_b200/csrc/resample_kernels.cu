@@ -91,10 +91,11 @@ __device__ __forceinline__ void warp_hist_add(unsigned char *hist, unsigned char
     }
 }
 
-// SRC 0: indices from the buffer (replicate r of this launch at idx[r*bn ..));  SRC 1: Philox
+// SRC 0: uint32 indices from the buffer (replicate r of this launch at idx[r*bn ..));
+// SRC 2: the same with uint16 indices;  SRC 1: Philox
 template <int SRC, int HALGO, bool ROWS>
 __global__ void __launch_bounds__(HIST_THREADS)
-hist_group_kernel(const uint32_t *__restrict__ idx, int n, int NP, int bn, int nb,
+hist_group_kernel(const void *__restrict__ idx_v, int n, int NP, int bn, int nb,
                   unsigned long long *__restrict__ counts, int *__restrict__ err,
                   uint32_t key0, uint32_t key1, uint32_t scale, uint32_t b_first) {
     extern __shared__ unsigned char hsm[];  // 8 histograms of NP bytes (+ 8 tag arrays for HALGO 2)
@@ -108,12 +109,13 @@ hist_group_kernel(const uint32_t *__restrict__ idx, int n, int NP, int bn, int n
         if (r < nb) {
             unsigned char *hist = hsm + (size_t)wid * NP;
             int overflow = 0;
-            if (SRC == 0) {
-                const uint32_t *src = idx + (size_t)r * bn;
+            if (SRC != 1) {
+                const uint32_t *src32 = static_cast<const uint32_t *>(idx_v) + (size_t)r * bn;
+                const uint16_t *src16 = static_cast<const uint16_t *>(idx_v) + (size_t)r * bn;
                 for (int i0 = 0; i0 < bn; i0 += 32) {
                     int i = i0 + lane;
                     bool valid = i < bn;
-                    uint32_t k = valid ? src[i] : 0u;
+                    uint32_t k = valid ? (SRC == 2 ? (uint32_t)src16[i] : src32[i]) : 0u;
                     warp_hist_add<HALGO>(hist, tag, k, valid, lane, &overflow);
                 }
             } else {
@@ -167,16 +169,16 @@ hist_group_kernel(const uint32_t *__restrict__ idx, int n, int NP, int bn, int n
 
 template <int SRC, bool ROWS>
 __global__ void __launch_bounds__(256)
-hist_global_kernel(const uint32_t *__restrict__ idx, int n, int NP, int bn, int nb,
+hist_global_kernel(const void *__restrict__ idx_v, int n, int NP, int bn, int nb,
                    unsigned int *__restrict__ counts32, uint32_t key0, uint32_t key1, uint32_t scale,
                    uint32_t b_first) {
-    const unsigned long long total = SRC == 0 ? (unsigned long long)nb * bn
+    const unsigned long long total = SRC != 1 ? (unsigned long long)nb * bn
                                               : (unsigned long long)nb * ((bn + 3) / 4);
     for (unsigned long long d = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; d < total;
          d += (unsigned long long)gridDim.x * blockDim.x) {
-        if (SRC == 0) {
+        if (SRC != 1) {
             uint32_t r = (uint32_t)(d / bn);
-            uint32_t k = idx[d];
+            uint32_t k = SRC == 2 ? (uint32_t)static_cast<const uint16_t *>(idx_v)[d] : static_cast<const uint32_t *>(idx_v)[d];
             if (ROWS) {
                 atomicAdd(&counts32[((size_t)r * NP + k) >> 2], 1u << ((k & 3) * 8));
             } else {
@@ -213,7 +215,7 @@ static int hist_algo() {
 }
 
 template <int SRC, int HALGO, bool ROWS>
-static int hist_group_launch(const uint32_t *d_idx, int n, int NP, int bn, int nb, unsigned long long *d_counts,
+static int hist_group_launch(const void *d_idx, int n, int NP, int bn, int nb, unsigned long long *d_counts,
                              int *d_err, uint32_t k0, uint32_t k1, uint32_t scale, uint32_t b_first, cudaStream_t st) {
     auto kern = hist_group_kernel<SRC, HALGO, ROWS>;
     static bool attr_done = false;
@@ -232,7 +234,7 @@ static int hist_group_launch(const uint32_t *d_idx, int n, int NP, int bn, int n
     return CGPU_OK;
 }
 
-static int hist_dispatch(int src, const uint32_t *d_idx, int n, int NP, int bn, int nb,
+static int hist_dispatch(int src, const void *d_idx, int n, int NP, int bn, int nb,
                          unsigned long long *d_counts, int *d_err, uint32_t k0, uint32_t k1, uint32_t scale,
                          uint32_t b_first, cudaStream_t st, bool rows) {
     if (nb <= 0) return CGPU_OK;
@@ -246,6 +248,7 @@ static int hist_dispatch(int src, const uint32_t *d_idx, int n, int NP, int bn, 
                     : hist_group_launch<S, A, false>(d_idx, n, NP, bn, nb, d_counts, d_err, k0, k1, scale, b_first, st);
         CGPU_HIST_CASE(0, 0) CGPU_HIST_CASE(0, 1) CGPU_HIST_CASE(0, 2)
         CGPU_HIST_CASE(1, 0) CGPU_HIST_CASE(1, 1) CGPU_HIST_CASE(1, 2)
+        CGPU_HIST_CASE(2, 0) CGPU_HIST_CASE(2, 1) CGPU_HIST_CASE(2, 2)
 #undef CGPU_HIST_CASE
         set_error(CGPU_EINVAL, "CGPU_HIST_ALGO=%d", algo);
         return CGPU_EINVAL;
@@ -254,18 +257,20 @@ static int hist_dispatch(int src, const uint32_t *d_idx, int n, int NP, int bn, 
         int sms = G().sm_count > 0 ? G().sm_count : 148;
         int grid = sms * 16;
         unsigned int *c32 = reinterpret_cast<unsigned int *>(d_counts);
-        if (src == 0 && !rows) hist_global_kernel<0, false><<<grid, 256, 0, st>>>(d_idx, n, NP, bn, nb, c32, k0, k1, scale, b_first);
-        else if (src == 0) hist_global_kernel<0, true><<<grid, 256, 0, st>>>(d_idx, n, NP, bn, nb, c32, k0, k1, scale, b_first);
-        else if (!rows) hist_global_kernel<1, false><<<grid, 256, 0, st>>>(d_idx, n, NP, bn, nb, c32, k0, k1, scale, b_first);
-        else hist_global_kernel<1, true><<<grid, 256, 0, st>>>(d_idx, n, NP, bn, nb, c32, k0, k1, scale, b_first);
+#define CGPU_HISTG_CASE(S, R)                                                                                 \
+    if (src == S && rows == R)                                                                                 \
+        hist_global_kernel<S, R><<<grid, 256, 0, st>>>(d_idx, n, NP, bn, nb, c32, k0, k1, scale, b_first);
+        CGPU_HISTG_CASE(0, false) CGPU_HISTG_CASE(0, true) CGPU_HISTG_CASE(1, false) CGPU_HISTG_CASE(1, true)
+        CGPU_HISTG_CASE(2, false) CGPU_HISTG_CASE(2, true)
+#undef CGPU_HISTG_CASE
         CGPU_LAUNCH_CHECK();
     }
     return CGPU_OK;
 }
 
-int launch_hist_from_idx(const uint32_t *d_idx, int n, int NP, int bn, int nb,
+int launch_hist_from_idx(const void *d_idx, int n, int NP, int bn, int nb,
                          unsigned long long *d_counts, int *d_err, cudaStream_t st, bool rows) {
-    return hist_dispatch(0, d_idx, n, NP, bn, nb, d_counts, d_err, 0, 0, 0, 0, st, rows);
+    return hist_dispatch(idx_is16((uint32_t)n) ? 2 : 0, d_idx, n, NP, bn, nb, d_counts, d_err, 0, 0, 0, 0, st, rows);
 }
 
 int launch_hist_philox(unsigned long long seed, int scale, int b_first, int n, int NP, int bn, int nb,
