@@ -29,6 +29,7 @@ from .api import (  # noqa: F401
     resample_counts,
     scale_setup,
     scaleboot_all,
+    set_option,
     set_shard,
     shard_range,
     smooth_count,

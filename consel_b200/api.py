@@ -91,14 +91,18 @@ def shard_range(bb: int) -> tuple[int, int]:
     return b0.value, b1.value
 
 
+def set_option(name: str, value: int) -> None:
+    _check(load().cgpu_set_option(name.encode(), int(value)))
+
+
 def launch_count() -> int:
     return int(load().cgpu_launch_count())
 
 
 def last_timing() -> dict:
-    ms = (C.c_double * 6)()
+    ms = (C.c_double * 8)()
     _check(load().cgpu_last_timing(ms))
-    keys = ("upload", "rng", "resample", "contract", "download", "total")
+    keys = ("upload", "rng", "resample", "contract", "download", "total", "gemm_i8", "fx_combine")
     return dict(zip(keys, [float(x) for x in ms]))
 
 
@@ -107,10 +111,9 @@ def scale_setup(L: np.ndarray, rr):
     bn = (int)(rr*n) with the fp64 product truncated, rr1 = bn/n."""
     L = np.ascontiguousarray(L, dtype=np.float64)
     K, n = L.shape
-    datvec = np.empty(K)
-    for i in range(K):
-        # sequential left-to-right sum, like the reference loop (np.sum pairs terms)
-        datvec[i] = float(np.add.accumulate(L[i])[-1]) if n else 0.0
+    datvec = np.zeros(K)
+    # sequential left-to-right sums like the reference loop (np.sum pairs terms): host helper
+    load().cgpu_host_rowsums(_dp(L), K, n, _dp(datvec))
     rr = np.asarray(rr, dtype=np.float64)
     bn = (rr * np.float64(n)).astype(np.int32)
     rr1 = bn.astype(np.float64) / np.float64(n)

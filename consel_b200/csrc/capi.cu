@@ -6,6 +6,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <thread>
 #include <vector>
 
 #include "cgpu_internal.h"
@@ -34,55 +35,53 @@ int ensure_init() {
     return CGPU_OK;
 }
 
-// accumulates device time per phase over many (start, stop) event pairs
-struct PhaseTimer {
-    struct Span {
-        int phase;
-        cudaEvent_t a, b;
-        bool ended;
-    };
-    std::vector<Span> spans;
-    cudaStream_t st;
-    cudaEvent_t t0 = nullptr, t1 = nullptr;
-    explicit PhaseTimer(cudaStream_t s) : st(s) {
-        cudaEventCreate(&t0);
-        cudaEventCreate(&t1);
-        cudaEventRecord(t0, st);
+PhaseTimer::PhaseTimer(cudaStream_t s) : st(s) {
+    cudaEventCreate(&t0);
+    cudaEventCreate(&t1);
+    cudaEventRecord(t0, st);
+}
+PhaseTimer::~PhaseTimer() {
+    for (int i = 0; i < nspans; i++) {
+        cudaEventDestroy(spans[i].a);
+        cudaEventDestroy(spans[i].b);
     }
-    cudaStream_t cur = nullptr;
-    void begin(int phase, cudaStream_t on = nullptr) {
-        cur = on ? on : st;
-        Span sp{phase, nullptr, nullptr, false};
-        cudaEventCreate(&sp.a);
-        cudaEventCreate(&sp.b);
-        cudaEventRecord(sp.a, cur);
-        spans.push_back(sp);
+    free(spans);
+    if (t0) cudaEventDestroy(t0);
+    if (t1) cudaEventDestroy(t1);
+}
+void PhaseTimer::begin(int phase, cudaStream_t on) {
+    cur = on ? on : st;
+    if (nspans == cap) {
+        cap = cap ? 2 * cap : 64;
+        spans = (Span *)realloc(spans, sizeof(Span) * cap);
     }
-    void end() {
-        cudaEventRecord(spans.back().b, cur);
-        spans.back().ended = true;
+    Span &sp = spans[nspans++];
+    sp.phase = phase;
+    sp.ended = false;
+    cudaEventCreate(&sp.a);
+    cudaEventCreate(&sp.b);
+    cudaEventRecord(sp.a, cur);
+}
+void PhaseTimer::end() {
+    cudaEventRecord(spans[nspans - 1].b, cur);
+    spans[nspans - 1].ended = true;
+}
+void PhaseTimer::finish(double *ms) {
+    for (int i = 0; i < NPHASE; i++) ms[i] = 0;
+    cudaEventRecord(t1, st);
+    cudaEventSynchronize(t1);
+    float tot = 0;
+    if (cudaEventElapsedTime(&tot, t0, t1) == cudaSuccess) ms[5] = tot;
+    for (int i = 0; i < nspans; i++) {
+        Span &sp = spans[i];
+        float v = 0;
+        // a span left open by an early error return has no end event: skip it (querying it
+        // would leave a stale "invalid resource handle" for the next launch check)
+        if (sp.ended && cudaEventSynchronize(sp.b) == cudaSuccess && cudaEventElapsedTime(&v, sp.a, sp.b) == cudaSuccess)
+            ms[sp.phase] += v;
     }
-    // call after the stream has been synchronised
-    void finish(double *ms5) {
-        for (int i = 0; i < 6; i++) ms5[i] = 0;
-        cudaEventRecord(t1, st);
-        cudaEventSynchronize(t1);
-        float tot = 0;
-        if (cudaEventElapsedTime(&tot, t0, t1) == cudaSuccess) ms5[5] = tot;
-        cudaEventDestroy(t0);
-        cudaEventDestroy(t1);
-        for (auto &sp : spans) {
-            float ms = 0;
-            // a span left open by an early error return has no end event: skip it (querying it
-            // would leave a stale "invalid resource handle" for the next launch check)
-            if (sp.ended && cudaEventSynchronize(sp.b) == cudaSuccess && cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess)
-                ms5[sp.phase] += ms;
-            cudaEventDestroy(sp.a);
-            cudaEventDestroy(sp.b);
-        }
-        spans.clear();
-    }
-};
+    (void)cudaGetLastError();
+}
 
 static void shard_range(int bb, int *b0, int *b1) {
     const Globals &g = G();
@@ -136,6 +135,7 @@ static int alloc_reps(int K, int S, const int *bb, DevReps **out) {
 // chunk size (log2 draws) of the MT19937 doubling tree: about 2k chunks, each long
 // enough that its jump (~6M word-XORs) is amortised.
 static int pick_chunk_log2(unsigned long long total_draws) {
+    if (G().opt_chunk_log2 >= 10 && G().opt_chunk_log2 <= 30) return G().opt_chunk_log2;
     int m = 12;
     while (m < 23 && (total_draws >> m) > 2048) m++;
     return m;
@@ -294,8 +294,11 @@ static int scaleboot_core(DevMatrix &m, int S, const int *bn, const int *bb, uns
     // (shared-memory bound) runs on the aux stream while the contraction of item i (FP64
     // bound) runs on the main stream; the two count buffers alternate.  With per-batch
     // index generation (sharded or very long streams) everything stays on one stream.
+    // (the tensor-core GEMM keeps ~200 KB of shared memory per SM, which starves a
+    // concurrent histogram kernel, so the int8 mode runs its stages back to back)
     static const bool no_overlap = getenv("CGPU_NO_OVERLAP") != nullptr;
-    const bool overlap = !no_overlap && (rng_mode == CGPU_RNG_PHILOX || idx_whole_run);
+    const int want = G().opt_overlap >= 0 ? G().opt_overlap : (i8 ? 0 : 1);
+    const bool overlap = !no_overlap && want && (rng_mode == CGPU_RNG_PHILOX || idx_whole_run);
     cudaStream_t aux = overlap ? G().stream2 : st;
     if (overlap) {
         CGPU_CUDA(cudaEventRecord(ws.idx_ready, st));  // memsets, jump tree and index stream are queued on st
@@ -336,7 +339,7 @@ static int scaleboot_core(DevMatrix &m, int S, const int *bn, const int *bb, uns
             pt.begin(3);
             if (i8)
                 CGPU_TRY(launch_contract_i8(m, reinterpret_cast<const unsigned char *>(ws.d_counts[buf]), nbat,
-                                            (nbat + 255) / 256 * 256, d_partial, r, reps->d_rep[s], reps->nb[s], a, st));
+                                            (nbat + 255) / 256 * 256, d_partial, r, reps->d_rep[s], reps->nb[s], a, st, &pt));
             else
                 CGPU_TRY(launch_contract(m, ws.d_counts[buf], nbat, r, reps->d_rep[s], reps->nb[s], a, sum_mode, st));
             pt.end();
@@ -429,6 +432,28 @@ extern "C" {
 
 int cgpu_version(void) { return 100; }
 
+void cgpu_host_rowsums(const double *L, int K, int n, double *datvec) {
+    if (!L || !datvec || K <= 0) return;
+    unsigned hw = std::thread::hardware_concurrency();
+    int nt = (int)std::min<unsigned>(hw ? hw : 1, (unsigned)K);
+    if ((long long)K * n < (1 << 20)) nt = 1;
+    auto work = [&](int t) {
+        for (int i = t; i < K; i += nt) {
+            const double *row = L + (size_t)i * n;
+            double x = 0;
+            for (int j = 0; j < n; j++) x += row[j];  // -ffp-contract=off, no reassociation: one rounded add per site
+            datvec[i] = x;
+        }
+    };
+    if (nt == 1) {
+        work(0);
+        return;
+    }
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; t++) th.emplace_back(work, t);
+    for (auto &t : th) t.join();
+}
+
 const char *cgpu_last_error(void) { return t_err; }
 
 int cgpu_init(int device) {
@@ -509,9 +534,25 @@ int cgpu_shard_range(int bb, int *b_begin, int *b_end) {
 
 long long cgpu_launch_count(void) { return g_launches.load(); }
 
-int cgpu_last_timing(double *ms6) {
-    if (!ms6) return CGPU_EINVAL;
-    memcpy(ms6, G().last_ms, sizeof(double) * 6);
+int cgpu_set_option(const char *name, int value) {
+    Globals &g = G();
+    if (!name) return CGPU_EINVAL;
+    if (!strcmp(name, "overlap")) g.opt_overlap = value;
+    else if (!strcmp(name, "hist_algo")) g.opt_hist_algo = value;
+    else if (!strcmp(name, "contract_algo")) g.opt_contract_algo = value;
+    else if (!strcmp(name, "i8_oneshot")) g.opt_i8_oneshot = value;
+    else if (!strcmp(name, "draw_nch")) g.opt_draw_nch = value;
+    else if (!strcmp(name, "chunk_log2")) g.opt_chunk_log2 = value;
+    else {
+        set_error(CGPU_EINVAL, "unknown option %s", name);
+        return CGPU_EINVAL;
+    }
+    return CGPU_OK;
+}
+
+int cgpu_last_timing(double *ms8) {
+    if (!ms8) return CGPU_EINVAL;
+    memcpy(ms8, G().last_ms, sizeof(double) * 8);
     return CGPU_OK;
 }
 

@@ -84,6 +84,10 @@ extern "C" {
 
 double cgpu_smooth_count(const cgpu_rowsum *q, int B, double t) { return smooth_count(*q, B, t); }
 
+void cgpu_smooth_count_many(const cgpu_rowsum *q, int count, int B, double t, double *out) {
+    for (int i = 0; i < count; i++) out[i] = smooth_count(q[i], B, t);
+}
+
 int cgpu_reps_upload(int K, int S, const int *bb, const double *const *rep, cgpu_reps **out) {
     CGPU_TRY(ensure_init());
     if (K <= 0 || S <= 0 || !bb || !rep || !out) {
@@ -200,13 +204,24 @@ int cgpu_count_query(const cgpu_reps *rr, int nq, const double *thr, cgpu_rowsum
     }
     cudaStream_t st = G().stream;
     const int cm = r->cm, S = r->S;
-    DevBuf d_thr, d_out;
+    DevBuf d_thr, d_out, d_part;
     CGPU_TRY(d_thr.upload(thr, (size_t)cm * nq, st));
     const size_t nout = (size_t)cm * S * nq;
     CGPU_TRY(d_out.alloc(nout * sizeof(cgpu_rowsum)));
-    for (int s = 0; s < S; s++) {
-        RowSrc src{r->d_stat[s], r->nb[s], nullptr, nullptr, nullptr, nullptr, nullptr};
-        CGPU_TRY(launch_rowsum(0, src, cm, r->nb[s], nq, d_thr.as<double>(), d_out.as<cgpu_rowsum>(), S, s, st));
+    if (S <= 32) {
+        // one launch for all scales; long rows are split so few items still fill the SMs
+        long long maxB = 1;
+        for (int s = 0; s < S; s++) maxB = std::max<long long>(maxB, r->nb[s]);
+        int nsplit = (int)std::min<long long>(16, std::max<long long>(1, (4LL * G().sm_count + (long long)cm * S - 1) / ((long long)cm * S)));
+        nsplit = (int)std::min<long long>(nsplit, std::max<long long>(1, maxB / 1024));
+        CGPU_TRY(d_part.alloc(nout * nsplit * sizeof(cgpu_rowsum)));
+        CGPU_TRY(launch_rowsum_all_scales(r->d_stat, r->nb, S, cm, nq, d_thr.as<double>(), d_part.as<cgpu_rowsum>(),
+                                          d_out.as<cgpu_rowsum>(), nsplit, st));
+    } else {
+        for (int s = 0; s < S; s++) {
+            RowSrc src{r->d_stat[s], r->nb[s], nullptr, nullptr, nullptr, nullptr, nullptr};
+            CGPU_TRY(launch_rowsum(0, src, cm, r->nb[s], nq, d_thr.as<double>(), d_out.as<cgpu_rowsum>(), S, s, st));
+        }
     }
     CGPU_CUDA(cudaMemcpyAsync(out, d_out.p, nout * sizeof(cgpu_rowsum), cudaMemcpyDeviceToHost, st));
     CGPU_CUDA(cudaStreamSynchronize(st));

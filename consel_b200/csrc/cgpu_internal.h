@@ -75,7 +75,9 @@ struct Globals {
     cudaStream_t stream3 = nullptr;  // copy stream: D2H of finished scales behind the compute
     uint32_t *d_jump_table = nullptr;  // (MT_MAXLOG+1) x 624 u32
     cudaEvent_t ev[8] = {};
-    double last_ms[6] = {0, 0, 0, 0, 0, 0};
+    double last_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    // tuning switches (cgpu_set_option); -1 = built-in default
+    int opt_overlap = -1, opt_hist_algo = -1, opt_contract_algo = -1, opt_i8_oneshot = -1, opt_draw_nch = -1, opt_chunk_log2 = -1;
 };
 Globals &G();
 int ensure_init();
@@ -146,8 +148,29 @@ int launch_contract(const DevMatrix &m, const unsigned long long *d_counts, int 
                     double *d_rep, int ldrep, int col0, int sum_mode, cudaStream_t st);
 // i8_kernels.cu
 int fx_prepare(DevMatrix &m, cudaStream_t st);
+struct PhaseTimer;
 int launch_contract_i8(const DevMatrix &m, const unsigned char *d_counts_rows, int nb, int nb_pad, int *d_partial,
-                       double r, double *d_rep, int ldrep, int col0, cudaStream_t st);
+                       double r, double *d_rep, int ldrep, int col0, cudaStream_t st, PhaseTimer *pt = nullptr);
+
+// accumulates device time per phase over many (start, stop) event pairs
+struct PhaseTimer {
+    struct Span {
+        int phase;
+        cudaEvent_t a, b;
+        bool ended;
+    };
+    static constexpr int NPHASE = 8;
+    Span *spans = nullptr;
+    int nspans = 0, cap = 0;
+    cudaStream_t st;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    cudaStream_t cur = nullptr;
+    explicit PhaseTimer(cudaStream_t s);
+    ~PhaseTimer();
+    void begin(int phase, cudaStream_t on = nullptr);
+    void end();
+    void finish(double *ms);  // call after the streams have been synchronised
+};
 
 // stats_kernels.cu
 // Row definitions for the row-summary kernel:
@@ -163,6 +186,8 @@ struct RowSrc {
 };
 int launch_rowsum(int mode, const RowSrc &src, int rows, int B, int nq, const double *d_thr, cgpu_rowsum *d_out,
                   int out_stride, int out_off, cudaStream_t st);
+int launch_rowsum_all_scales(const double *const *d_stat, const int *B, int S, int cm, int nq, const double *d_thr,
+                             cgpu_rowsum *d_part, cgpu_rowsum *d_out, int nsplit, cudaStream_t st);
 int launch_order_stat(const double *d_stat, int rows, int B, int ld, const int *d_rank, double *d_val, cudaStream_t st);
 int launch_col_top2(const double *x, int K, int B, int ld, double *m1, double *m2, int *a1, cudaStream_t st);
 int launch_stat_build(const double *x, int K, int B, int ld, const double *m1, const double *m2, const int *a1,

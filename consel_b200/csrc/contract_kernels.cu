@@ -330,7 +330,8 @@ static int contract_algo(const DevMatrix &m, int sum_mode) {
         const char *e = getenv("CGPU_CONTRACT_ALGO");
         return e ? atoi(e) : -1;
     }();
-    int algo = env >= 0 ? env : (sum_mode == CGPU_SUM_STRICT ? 2 : 0);
+    const int forced = G().opt_contract_algo >= 0 ? G().opt_contract_algo : env;
+    int algo = forced >= 0 ? forced : (sum_mode == CGPU_SUM_STRICT ? 2 : 0);
     if (!m.finite) algo = 0;
     if (algo == 2 && sum_mode != CGPU_SUM_STRICT) algo = 0;
     return algo;

@@ -20,6 +20,9 @@
 //   fx_combine_kernel  exact 128-bit recombination of the S partial sums, one rounding,
 //                      scale, divide by r
 #include <cuda.h>
+#include <stdlib.h>
+
+#include <algorithm>
 
 #include "cgpu_internal.h"
 
@@ -267,6 +270,121 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(G8_BN) : "memory");
 }
 
+// Persistent variant: one CTA per SM walks the tile list (m fastest, so CTAs running at the
+// same time share count rows in L2); the shared-memory ring runs across tiles, and two
+// accumulator stages in tensor memory (2 x 256 columns) let the epilogue of tile i drain
+// while the MMAs of tile i+1 are issued.
+__global__ void __launch_bounds__(G8_THREADS, 1)
+gemm_i8_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int NP,
+                          int *__restrict__ P, int ldp, int m_tiles, int n_tiles) {
+    extern __shared__ unsigned char g8_raw[];
+    unsigned char *base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(g8_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char *sA = base;
+    unsigned char *sB = base + G8_STAGES * G8_A_BYTES;
+    uint64_t *full = reinterpret_cast<uint64_t *>(base + G8_STAGES * (G8_A_BYTES + G8_B_BYTES));
+    uint64_t *empty = full + G8_STAGES;
+    uint64_t *acc_full = empty + G8_STAGES;  // [2]
+    uint64_t *acc_empty = acc_full + 2;      // [2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nkb = NP / G8_BK;
+    const int total_tiles = m_tiles * n_tiles;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < G8_STAGES; s++) {
+            mb_init(&full[s], 1);
+            mb_init(&empty[s], 1);
+        }
+        for (int a = 0; a < 2; a++) {
+            mb_init(&acc_full[a], 1);
+            mb_init(&acc_empty[a], 4);  // one arrival per epilogue warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s2u(tmem_slot)), "n"(2 * G8_BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int it = 0;  // k-block counter across tiles
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int m0 = (tile % m_tiles) * G8_BM, n0 = (tile / m_tiles) * G8_BN;
+                for (int kb = 0; kb < nkb; kb++, it++) {
+                    const int s = it % G8_STAGES;
+                    mb_wait(&empty[s], ((it / G8_STAGES) & 1) ^ 1);
+                    mb_expect(&full[s], (uint32_t)(G8_A_BYTES + G8_B_BYTES));
+                    tma_load_2d(sA + s * G8_A_BYTES, &mapA, kb * G8_BK, m0, &full[s]);
+                    tma_load_2d(sB + s * G8_B_BYTES, &mapB, kb * G8_BK, n0, &full[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = (2u << 4) | (1u << 7) | (0u << 10) | ((uint32_t)(G8_BN >> 3) << 17) | ((uint32_t)(G8_BM >> 4) << 24);
+            int it = 0, tcount = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, tcount++) {
+                const int acc = tcount & 1;
+                mb_wait(&acc_empty[acc], ((tcount >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t d_tmem = tmem + (uint32_t)(acc * G8_BN);
+                for (int kb = 0; kb < nkb; kb++, it++) {
+                    const int s = it % G8_STAGES;
+                    mb_wait(&full[s], (it / G8_STAGES) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint64_t ad = umma_desc_sw128(sA + s * G8_A_BYTES), bd = umma_desc_sw128(sB + s * G8_B_BYTES);
+#pragma unroll
+                    for (int k = 0; k < G8_BK / 32; k++) umma_i8(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                    umma_commit(&empty[s]);
+                }
+                umma_commit(&acc_full[acc]);
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        int tcount = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, tcount++) {
+            const int acc = tcount & 1;
+            const int m0 = (tile % m_tiles) * G8_BM, n0 = (tile / m_tiles) * G8_BN;
+            mb_wait(&acc_full[acc], (tcount >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            int *dst = P + (size_t)(m0 + q * 32 + lane) * ldp + n0;
+#pragma unroll 1
+            for (int c = 0; c < G8_BN; c += 32) {
+                uint32_t v[32];
+                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * G8_BN + c);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                      "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                      "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                    : "r"(taddr)
+                    : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                uint4 *d4 = reinterpret_cast<uint4 *>(dst + c);
+#pragma unroll
+                for (int i = 0; i < 8; i++) d4[i] = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            }
+            // all of this warp's reads of the accumulator are complete: hand it back
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s2u(&acc_empty[acc])) : "memory");
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * G8_BN) : "memory");
+}
+
 // ------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
@@ -340,7 +458,7 @@ int fx_prepare(DevMatrix &m, cudaStream_t st) {
 
 // counts: plain rows [nb_pad][NP] uint8 (nb_pad multiple of 256, padding rows zero)
 int launch_contract_i8(const DevMatrix &m, const unsigned char *d_counts_rows, int nb, int nb_pad, int *d_partial,
-                       double r, double *d_rep, int ldrep, int col0, cudaStream_t st) {
+                       double r, double *d_rep, int ldrep, int col0, cudaStream_t st, PhaseTimer *pt) {
     if (nb <= 0) return CGPU_OK;
     // int32 accumulators: |sum_j c*d| <= 128 * (draws per replicate)
     CUtensorMap mapA, mapB;
@@ -349,14 +467,30 @@ int launch_contract_i8(const DevMatrix &m, const unsigned char *d_counts_rows, i
     static bool attr_done = false;
     if (!attr_done) {
         CGPU_CUDA(cudaFuncSetAttribute(gemm_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G8_SMEM));
+        CGPU_CUDA(cudaFuncSetAttribute(gemm_i8_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G8_SMEM));
         attr_done = true;
     }
-    dim3 grid((unsigned)(m.fxMpad / G8_BM), (unsigned)(nb_pad / G8_BN));
-    gemm_i8_kernel<<<grid, G8_THREADS, G8_SMEM, st>>>(mapA, mapB, m.NP, d_partial, nb_pad, nb_pad);
+    static const bool env_one_shot = getenv("CGPU_I8_ONESHOT") != nullptr;  // development A/B switch
+    const bool one_shot = G().opt_i8_oneshot >= 0 ? G().opt_i8_oneshot != 0 : env_one_shot;
+    if (pt) pt->begin(6, st);
+    const int m_tiles = (int)(m.fxMpad / G8_BM), n_tiles = nb_pad / G8_BN;
+    if (one_shot) {
+        dim3 grid((unsigned)m_tiles, (unsigned)n_tiles);
+        gemm_i8_kernel<<<grid, G8_THREADS, G8_SMEM, st>>>(mapA, mapB, m.NP, d_partial, nb_pad, nb_pad);
+    } else {
+        const int sms = G().sm_count > 0 ? G().sm_count : 148;
+        const int grid = std::min(sms, m_tiles * n_tiles);
+        gemm_i8_persistent_kernel<<<grid, G8_THREADS, G8_SMEM, st>>>(mapA, mapB, m.NP, d_partial, nb_pad, m_tiles, n_tiles);
+    }
     CGPU_LAUNCH_CHECK();
+    if (pt) {
+        pt->end();
+        pt->begin(7, st);
+    }
     dim3 cgrid((nb + 255) / 256, m.K);
     fx_combine_kernel<<<cgrid, 256, 0, st>>>(d_partial, nb_pad, m.K, m.fxS, m.fxF, nb, r, d_rep, ldrep, col0);
     CGPU_LAUNCH_CHECK();
+    if (pt) pt->end();
     return CGPU_OK;
 }
 

@@ -119,50 +119,101 @@ __device__ __forceinline__ uint32_t site_index(uint32_t y, uint32_t n, double dn
     return (uint32_t)k;
 }
 
-template <int PATH, typename IdxT>
+// NCH chunks per CTA: the four block barriers of a regeneration step are shared by NCH
+// independent generator states, which is what the kernel is bound by (a lone state
+// spends ~820 cycles per 624 draws mostly waiting at barriers).
+template <int PATH, typename IdxT, int NCH>
 __global__ void __launch_bounds__(DRAW_THREADS)
-mt_draw_kernel(const uint32_t *__restrict__ states, int chunk_log2, unsigned long long first_chunk,
+mt_draw_kernel(const uint32_t *__restrict__ states, int chunk_log2, unsigned long long first_chunk, int nchunks,
                unsigned long long lo, unsigned long long hi, uint32_t n, IdxT *__restrict__ idx) {
-    __shared__ uint32_t buf[2][MT_N + 1];
+    __shared__ uint32_t buf[NCH][2][MT_N + 1];
     const int tid = threadIdx.x;
-    const unsigned long long chunk = first_chunk + blockIdx.x;
-    const unsigned long long d_begin = chunk << chunk_log2;
-    unsigned long long d_end = d_begin + (1ull << chunk_log2);
-    if (d_end > hi) d_end = hi;
     const double dn = (double)n;
-    const uint32_t *w = states + chunk * MT_N;
-    for (int i = tid; i < MT_N; i += DRAW_THREADS) buf[0][i] = w[i];
+    unsigned long long d_begin[NCH], d_end[NCH];
+    unsigned long long steps = 0;
+#pragma unroll
+    for (int c = 0; c < NCH; c++) {
+        const int ci = blockIdx.x * NCH + c;
+        const unsigned long long chunk = first_chunk + ci;
+        d_begin[c] = chunk << chunk_log2;
+        d_end[c] = d_begin[c] + (1ull << chunk_log2);
+        if (d_end[c] > hi) d_end[c] = hi;
+        if (ci >= nchunks || d_end[c] <= d_begin[c]) {
+            d_end[c] = d_begin[c];  // inactive slot
+        } else {
+            const uint32_t *w = states + chunk * MT_N;
+            for (int i = tid; i < MT_N; i += DRAW_THREADS) buf[c][0][i] = w[i];
+            const unsigned long long st = (d_end[c] - d_begin[c] + MT_N - 1) / MT_N;
+            steps = st > steps ? st : steps;
+        }
+    }
     __syncthreads();
     int cur = 0;
-    for (unsigned long long d0 = d_begin; d0 < d_end; d0 += MT_N) {
-        const uint32_t *o = buf[cur];
-        uint32_t *nw = buf[cur ^ 1];
+    constexpr int H = MT_N - MT_M;  // 227 words become computable per dependent step
+    for (unsigned long long it = 0; it < steps; it++) {
         // phase A: k in [0,227) reads only old words
-        if (tid < MT_N - MT_M) nw[tid] = o[tid + MT_M] ^ mt_twist(o[tid], o[tid + 1]);
+        if (tid < H) {
+#pragma unroll
+            for (int c = 0; c < NCH; c++) {
+                const uint32_t *o = buf[c][cur];
+                buf[c][cur ^ 1][tid] = o[tid + MT_M] ^ mt_twist(o[tid], o[tid + 1]);
+            }
+        }
         __syncthreads();
         // phase B: k in [227,454) reads new[k-227]
-        if (tid < MT_N - MT_M) {
-            int k = tid + (MT_N - MT_M);
-            nw[k] = nw[k - (MT_N - MT_M)] ^ mt_twist(o[k], o[k + 1]);
+        if (tid < H) {
+            const int k = tid + H;
+#pragma unroll
+            for (int c = 0; c < NCH; c++) {
+                const uint32_t *o = buf[c][cur];
+                uint32_t *nw = buf[c][cur ^ 1];
+                nw[k] = nw[k - H] ^ mt_twist(o[k], o[k + 1]);
+            }
         }
         __syncthreads();
         // phase C: k in [454,624); the last word wraps to new[0]
-        if (tid < MT_N - 2 * (MT_N - MT_M)) {
-            int k = tid + 2 * (MT_N - MT_M);
-            uint32_t nxt = (k == MT_N - 1) ? nw[0] : o[k + 1];
-            nw[k] = nw[k - (MT_N - MT_M)] ^ mt_twist(o[k], nxt);
+        if (tid < MT_N - 2 * H) {
+            const int k = tid + 2 * H;
+#pragma unroll
+            for (int c = 0; c < NCH; c++) {
+                const uint32_t *o = buf[c][cur];
+                uint32_t *nw = buf[c][cur ^ 1];
+                const uint32_t nxt = (k == MT_N - 1) ? nw[0] : o[k + 1];
+                nw[k] = nw[k - H] ^ mt_twist(o[k], nxt);
+            }
         }
         __syncthreads();
-        if (d0 + MT_N > lo) {
-            for (int i = tid; i < MT_N; i += DRAW_THREADS) {
-                unsigned long long d = d0 + i;
-                if (d >= lo && d < d_end) idx[d - lo] = (IdxT)site_index<PATH>(mt_temper(nw[i]), n, dn);
+#pragma unroll
+        for (int c = 0; c < NCH; c++) {
+            const unsigned long long d0 = d_begin[c] + it * MT_N;
+            if (d0 < d_end[c] && d0 + MT_N > lo) {
+                // 32-bit window [i_lo, i_hi) of this block's draws that fall inside [lo, d_end)
+                const int i_lo = d0 >= lo ? 0 : (int)(lo - d0);
+                const int i_hi = d_end[c] - d0 >= (unsigned long long)MT_N ? MT_N : (int)(d_end[c] - d0);
+                const uint32_t *nw = buf[c][cur ^ 1];
+                IdxT *out = idx + (long long)(d0 - lo);  // may point before idx when i_lo > 0; only [i_lo, i_hi) is touched
+#pragma unroll
+                for (int i = tid; i < MT_N; i += DRAW_THREADS)
+                    if (i >= i_lo && i < i_hi) out[i] = (IdxT)site_index<PATH>(mt_temper(nw[i]), n, dn);
             }
         }
         cur ^= 1;
-        // no barrier needed here: the next phase A only writes buf[cur^1] (= the old
-        // array, last read in phase C before the barrier above) and reads buf[cur].
+        // no barrier needed here: the next phase A only writes buf[.][cur^1] (= the old
+        // array, last read in phase C before the barrier above) and reads buf[.][cur].
     }
+}
+
+template <int PATH, typename IdxT>
+static void mt_draw_launch(const uint32_t *d_states, int chunk_log2, unsigned long long first_chunk, int nchunks,
+                           unsigned long long lo, unsigned long long hi, uint32_t n, IdxT *idx, cudaStream_t st) {
+    const int sms = G().sm_count > 0 ? G().sm_count : 148;
+    const int force = G().opt_draw_nch;
+    if (force == 4 || (force < 0 && nchunks >= 8 * sms))
+        mt_draw_kernel<PATH, IdxT, 4><<<(nchunks + 3) / 4, DRAW_THREADS, 0, st>>>(d_states, chunk_log2, first_chunk, nchunks, lo, hi, n, idx);
+    else if (force == 2 || (force < 0 && nchunks >= 4 * sms))
+        mt_draw_kernel<PATH, IdxT, 2><<<(nchunks + 1) / 2, DRAW_THREADS, 0, st>>>(d_states, chunk_log2, first_chunk, nchunks, lo, hi, n, idx);
+    else
+        mt_draw_kernel<PATH, IdxT, 1><<<nchunks, DRAW_THREADS, 0, st>>>(d_states, chunk_log2, first_chunk, nchunks, lo, hi, n, idx);
 }
 
 int launch_mt_draw(const uint32_t *d_states, int chunk_log2, unsigned long long first_chunk,
@@ -171,14 +222,10 @@ int launch_mt_draw(const uint32_t *d_states, int chunk_log2, unsigned long long 
     if (nchunks <= 0) return CGPU_OK;
     uint32_t *i32 = static_cast<uint32_t *>(d_idx);
     uint16_t *i16 = static_cast<uint16_t *>(d_idx);
-    if (n == 0)
-        mt_draw_kernel<2, uint32_t><<<nchunks, DRAW_THREADS, 0, st>>>(d_states, chunk_log2, first_chunk, lo, hi, n, i32);
-    else if (idx_is16(n))
-        mt_draw_kernel<0, uint16_t><<<nchunks, DRAW_THREADS, 0, st>>>(d_states, chunk_log2, first_chunk, lo, hi, n, i16);
-    else if (n < (1u << 21))
-        mt_draw_kernel<0, uint32_t><<<nchunks, DRAW_THREADS, 0, st>>>(d_states, chunk_log2, first_chunk, lo, hi, n, i32);
-    else
-        mt_draw_kernel<1, uint32_t><<<nchunks, DRAW_THREADS, 0, st>>>(d_states, chunk_log2, first_chunk, lo, hi, n, i32);
+    if (n == 0) mt_draw_launch<2, uint32_t>(d_states, chunk_log2, first_chunk, nchunks, lo, hi, n, i32, st);
+    else if (idx_is16(n)) mt_draw_launch<0, uint16_t>(d_states, chunk_log2, first_chunk, nchunks, lo, hi, n, i16, st);
+    else if (n < (1u << 21)) mt_draw_launch<0, uint32_t>(d_states, chunk_log2, first_chunk, nchunks, lo, hi, n, i32, st);
+    else mt_draw_launch<1, uint32_t>(d_states, chunk_log2, first_chunk, nchunks, lo, hi, n, i32, st);
     CGPU_LAUNCH_CHECK();
     return CGPU_OK;
 }

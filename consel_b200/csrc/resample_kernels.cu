@@ -112,11 +112,21 @@ hist_group_kernel(const void *__restrict__ idx_v, int n, int NP, int bn, int nb,
             if (SRC != 1) {
                 const uint32_t *src32 = static_cast<const uint32_t *>(idx_v) + (size_t)r * bn;
                 const uint16_t *src16 = static_cast<const uint16_t *>(idx_v) + (size_t)r * bn;
-                for (int i0 = 0; i0 < bn; i0 += 32) {
-                    int i = i0 + lane;
-                    bool valid = i < bn;
-                    uint32_t k = valid ? (SRC == 2 ? (uint32_t)src16[i] : src32[i]) : 0u;
-                    warp_hist_add<HALGO>(hist, tag, k, valid, lane, &overflow);
+                // 8 independent index loads in flight per lane before the histogram updates
+                // (the loop is otherwise bound by global-load latency)
+                for (int i0 = 0; i0 < bn; i0 += 256) {
+                    uint32_t kk[8];
+                    bool vv[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        const int i = i0 + u * 32 + lane;
+                        vv[u] = i < bn;
+                        kk[u] = vv[u] ? (SRC == 2 ? (uint32_t)src16[i] : src32[i]) : 0u;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        if (i0 + u * 32 < bn) warp_hist_add<HALGO>(hist, tag, kk[u], vv[u], lane, &overflow);
+                    }
                 }
             } else {
                 // draw i of replicate b is word (i & 3) of Philox(counter = (i >> 2, b, scale, 0))
@@ -211,7 +221,7 @@ static int hist_algo() {
         const char *e = getenv("CGPU_HIST_ALGO");
         return e ? atoi(e) : 1;
     }();
-    return v;
+    return G().opt_hist_algo >= 0 ? G().opt_hist_algo : v;
 }
 
 template <int SRC, int HALGO, bool ROWS>

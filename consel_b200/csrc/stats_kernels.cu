@@ -189,6 +189,137 @@ rowsum_kernel(RowSrc src, int B, int nq, const double *__restrict__ thr, cgpu_ro
     }
 }
 
+// All scales of a count query in ONE launch: grid (row, scale, split).  Rows are cut into
+// `nsplit` column ranges so that a query over few long rows (K=105, B=100000) still
+// fills the machine; the partial summaries are merged by rowsum_merge_kernel (count: sum,
+// lo: max, hi: min, edges: two smallest / two largest — all exact).
+struct ScaleList {
+    const double *stat[32];
+    int B[32];
+};
+
+__global__ void __launch_bounds__(RS_THREADS)
+rowsum_multi_kernel(ScaleList sl, int nq, int nsplit, const double *__restrict__ thr, cgpu_rowsum *__restrict__ part) {
+    const int row = blockIdx.x, sc = blockIdx.y, sp = blockIdx.z, S = gridDim.y;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int B = sl.B[sc];
+    const double *v = sl.stat[sc] + (size_t)row * B;
+    const int chunk = (B + nsplit - 1) / nsplit;
+    const int b_lo = sp * chunk, b_hi = min(B, b_lo + chunk);
+    __shared__ double s_thr[RS_MAXQ];
+    __shared__ unsigned long long s_cnt[RS_THREADS / 32][RS_MAXQ];
+    __shared__ double s_lo[RS_THREADS / 32][RS_MAXQ], s_hi[RS_THREADS / 32][RS_MAXQ];
+    __shared__ double s_edge[RS_THREADS / 32][4];
+    if (tid < nq) s_thr[tid] = thr[(size_t)row * nq + tid];
+    __syncthreads();
+    unsigned long long cnt[RS_MAXQ];
+    double lo[RS_MAXQ], hi[RS_MAXQ];
+#pragma unroll
+    for (int q = 0; q < RS_MAXQ; q++) {
+        cnt[q] = 0;
+        lo[q] = -CG_HUGE;
+        hi[q] = CG_HUGE;
+    }
+    double mn1 = CG_HUGE, mn2 = CG_HUGE, mx1 = -CG_HUGE, mx2 = -CG_HUGE;
+    for (int b = b_lo + tid; b < b_hi; b += RS_THREADS) {
+        const double x = v[b];
+        edge_insert(x, mn1, mn2, mx1, mx2);
+#pragma unroll
+        for (int q = 0; q < RS_MAXQ; q++) {
+            if (q < nq) {
+                if (x <= s_thr[q]) {
+                    cnt[q]++;
+                    lo[q] = fmax(lo[q], x);
+                } else {
+                    hi[q] = fmin(hi[q], x);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int off = 16; off; off >>= 1) {
+#pragma unroll
+        for (int q = 0; q < RS_MAXQ; q++) {
+            if (q < nq) {
+                cnt[q] += __shfl_xor_sync(0xffffffffu, cnt[q], off);
+                lo[q] = fmax(lo[q], __shfl_xor_sync(0xffffffffu, lo[q], off));
+                hi[q] = fmin(hi[q], __shfl_xor_sync(0xffffffffu, hi[q], off));
+            }
+        }
+        double o1 = __shfl_xor_sync(0xffffffffu, mn1, off), o2 = __shfl_xor_sync(0xffffffffu, mn2, off);
+        double p1 = __shfl_xor_sync(0xffffffffu, mx1, off), p2 = __shfl_xor_sync(0xffffffffu, mx2, off);
+        edge_merge(mn1, mn2, mx1, mx2, o1, o2, p1, p2);
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < RS_MAXQ; q++)
+            if (q < nq) {
+                s_cnt[wid][q] = cnt[q];
+                s_lo[wid][q] = lo[q];
+                s_hi[wid][q] = hi[q];
+            }
+        s_edge[wid][0] = mn1; s_edge[wid][1] = mn2; s_edge[wid][2] = mx1; s_edge[wid][3] = mx2;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        for (int w = 1; w < RS_THREADS / 32; w++)
+            edge_merge(mn1, mn2, mx1, mx2, s_edge[w][0], s_edge[w][1], s_edge[w][2], s_edge[w][3]);
+        s_edge[0][0] = mn1; s_edge[0][1] = mn2; s_edge[0][2] = mx1; s_edge[0][3] = mx2;
+    }
+    __syncthreads();
+    if (tid < nq) {
+        unsigned long long c = 0;
+        double l = -CG_HUGE, h = CG_HUGE;
+        for (int w = 0; w < RS_THREADS / 32; w++) {
+            c += s_cnt[w][tid];
+            l = fmax(l, s_lo[w][tid]);
+            h = fmin(h, s_hi[w][tid]);
+        }
+        cgpu_rowsum r;
+        r.cnt = (double)c;
+        r.lo = l;
+        r.hi = h;
+        r.min1 = s_edge[0][0]; r.min2 = s_edge[0][1]; r.max1 = s_edge[0][2]; r.max2 = s_edge[0][3];
+        part[(((size_t)row * S + sc) * nsplit + sp) * nq + tid] = r;
+    }
+}
+
+__global__ void __launch_bounds__(128)
+rowsum_merge_kernel(const cgpu_rowsum *__restrict__ part, int total, int nsplit, int nq, cgpu_rowsum *__restrict__ out) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;  // (row*S + sc)*nq + q
+    if (e >= total) return;
+    const int rs = e / nq, q = e % nq;
+    cgpu_rowsum r = part[((size_t)rs * nsplit) * nq + q];
+    for (int sp = 1; sp < nsplit; sp++) {
+        const cgpu_rowsum p = part[((size_t)rs * nsplit + sp) * nq + q];
+        r.cnt += p.cnt;  // integers below 2^53: exact
+        r.lo = fmax(r.lo, p.lo);
+        r.hi = fmin(r.hi, p.hi);
+        edge_merge(r.min1, r.min2, r.max1, r.max2, p.min1, p.min2, p.max1, p.max2);
+    }
+    out[e] = r;
+}
+
+int launch_rowsum_all_scales(const double *const *d_stat, const int *B, int S, int cm, int nq, const double *d_thr,
+                             cgpu_rowsum *d_part, cgpu_rowsum *d_out, int nsplit, cudaStream_t st) {
+    if (cm <= 0 || S <= 0) return CGPU_OK;
+    if (S > 32 || nq < 1 || nq > RS_MAXQ) {
+        set_error(CGPU_EINVAL, "count query with %d scales / %d thresholds", S, nq);
+        return CGPU_EINVAL;
+    }
+    ScaleList sl;
+    for (int s = 0; s < S; s++) {
+        sl.stat[s] = d_stat[s];
+        sl.B[s] = B[s];
+    }
+    rowsum_multi_kernel<<<dim3(cm, S, nsplit), RS_THREADS, 0, st>>>(sl, nq, nsplit, d_thr, d_part);
+    CGPU_LAUNCH_CHECK();
+    const int total = cm * S * nq;
+    rowsum_merge_kernel<<<(total + 127) / 128, 128, 0, st>>>(d_part, total, nsplit, nq, d_out);
+    CGPU_LAUNCH_CHECK();
+    return CGPU_OK;
+}
+
 int launch_rowsum(int mode, const RowSrc &src, int rows, int B, int nq, const double *d_thr, cgpu_rowsum *d_out,
                   int out_stride, int out_off, cudaStream_t st) {
     if (rows <= 0) return CGPU_OK;

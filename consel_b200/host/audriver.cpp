@@ -2,6 +2,9 @@
 
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <thread>
 
 #include "refio.h"
@@ -9,27 +12,90 @@
 
 namespace audriver {
 
-// the per-item fits of one lockstep round are independent: spread them over the host cores
-template <typename F>
-static void parallel_for(int n, F body) {
-    unsigned hw = std::thread::hardware_concurrency();
-    int nt = (int)std::min<unsigned>(hw ? hw : 1, (unsigned)((n + 15) / 16));
-    if (refio::debugmode > 0) nt = 1;  // keep debug traces in item order
-    if (nt <= 1) {
+// The fits of one lockstep round are independent (one per item, or one per (item, alpha,
+// au|bp) in the confidence-limit rounds) and each costs tens of microseconds (ten qnorm
+// bisections): spread them one at a time over a small persistent pool of host threads.
+namespace {
+class Pool {
+  public:
+    explicit Pool(int nthreads) {
+        for (int t = 0; t < nthreads; t++) workers.emplace_back([this] { loop(); });
+    }
+    ~Pool() {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            quit = true;
+        }
+        cv.notify_all();
+        for (auto &w : workers) w.join();
+    }
+    int size() const { return (int)workers.size(); }
+    void run(int n, const std::function<void(int)> &body) {
+        if (n <= 0) return;
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            fn = &body;
+            total = n;
+            next.store(0);
+            pending = (int)workers.size();
+            epoch++;
+        }
+        cv.notify_all();
+        work(body, n);  // the caller helps
+        std::unique_lock<std::mutex> lk(mu);
+        done_cv.wait(lk, [this] { return pending == 0; });
+        fn = nullptr;
+    }
+
+  private:
+    void work(const std::function<void(int)> &body, int n) {
+        for (;;) {
+            int i = next.fetch_add(1);
+            if (i >= n) break;
+            body(i);
+        }
+    }
+    void loop() {
+        unsigned seen = 0;
+        for (;;) {
+            const std::function<void(int)> *f;
+            int n;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return quit || epoch != seen; });
+                if (quit) return;
+                seen = epoch;
+                f = fn;
+                n = total;
+            }
+            work(*f, n);
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                if (--pending == 0) done_cv.notify_all();
+            }
+        }
+    }
+    std::vector<std::thread> workers;
+    std::mutex mu;
+    std::condition_variable cv, done_cv;
+    const std::function<void(int)> *fn = nullptr;
+    std::atomic<int> next{0};
+    int total = 0, pending = 0;
+    unsigned epoch = 0;
+    bool quit = false;
+};
+}  // namespace
+
+static void parallel_for(int n, const std::function<void(int)> &body) {
+    if (refio::debugmode > 0 || n < 2) {  // keep debug traces in item order
         for (int i = 0; i < n; i++) body(i);
         return;
     }
-    std::atomic<int> next{0};
-    std::vector<std::thread> th;
-    for (int t = 0; t < nt; t++)
-        th.emplace_back([&] {
-            for (;;) {
-                int i0 = next.fetch_add(16);
-                if (i0 >= n) break;
-                for (int i = i0; i < std::min(n, i0 + 16); i++) body(i);
-            }
-        });
-    for (auto &t : th) t.join();
+    static Pool pool([] {
+        unsigned hw = std::thread::hardware_concurrency();
+        return (int)std::max(1u, hw ? hw - 1 : 1u);
+    }());
+    pool.run(n, body);
 }
 
 int run(const Input &in, const aufit::Options &opt, QueryFn query, void *ctx, Output *out) {
@@ -101,16 +167,15 @@ int run(const Input &in, const aufit::Options &opt, QueryFn query, void *ctx, Ou
                 for (int q = 0; q < nqc; q++) cthr[(size_t)j * nqc + q] = ci[(size_t)j * nq + q0 + q].x;
             crs.resize((size_t)cm * kk * nqc);
             if (int rc = query(ctx, nqc, cthr.data(), crs.data())) return rc;
-            parallel_for(cm, [&](int j) {
+            parallel_for(cm * nqc, [&](int e) {
+                const int j = e / nqc, q = e % nqc;
+                aufit::CiIter &c = ci[(size_t)j * nq + q0 + q];
+                if (c.done) return;
                 std::vector<double> cnts(kk);
-                for (int q = 0; q < nqc; q++) {
-                    aufit::CiIter &c = ci[(size_t)j * nq + q0 + q];
-                    if (c.done) continue;
-                    const double t = cthr[(size_t)j * nqc + q];
-                    for (int k = 0; k < kk; k++)
-                        cnts[k] = cgpu_smooth_count(&crs[((size_t)j * kk + k) * nqc + q], in.bb[k], t);
-                    c.step(cnts.data(), in.rr, bbd.data(), kk, opt);
-                }
+                const double t = cthr[(size_t)j * nqc + q];
+                for (int k = 0; k < kk; k++)
+                    cnts[k] = cgpu_smooth_count(&crs[((size_t)j * kk + k) * nqc + q], in.bb[k], t);
+                c.step(cnts.data(), in.rr, bbd.data(), kk, opt);
             });
         }
     }

@@ -50,6 +50,17 @@ def item_order(datvec, ass_ptr, ass_idx, nosort: bool = False):
     ascending) and the item order by compdvec (length first, then lexicographic)."""
     datvec = np.asarray(datvec, dtype=np.float64)
     cm = len(ass_ptr) - 1
+    ass_ptr = np.asarray(ass_ptr)
+    ass_idx = np.asarray(ass_idx)
+    if cm and np.all(np.diff(ass_ptr) == 1):
+        # singleton associations (the default identity): max over "all but i" from the top two
+        a = int(np.argmax(datvec))
+        second = np.max(np.delete(datvec, a)) if len(datvec) > 1 else -1.0e30
+        trees = ass_idx[ass_ptr[:-1]]
+        obs_all = np.where(trees == a, second, datvec[a]) - datvec[trees]
+        order = np.arange(cm) if nosort else np.argsort(obs_all, kind="stable")
+        order = order.astype(np.int32)
+        return order, obs_all[order], np.arange(cm + 1, dtype=np.int32), trees[order].astype(np.int32)
     keys = []
     for e in range(cm):
         a = np.asarray(ass_idx[ass_ptr[e]:ass_ptr[e + 1]])
@@ -126,7 +137,10 @@ def consel(reps: api.Reps, datvec, rr, bb, ass=None, alpha=(0.05, 0.10, 0.5, 0.9
 
     w = np.exp(datvec - datvec.max())  # do_batest
     w = w / np.add.accumulate(w)[-1]
-    pp = np.array([np.add.accumulate(w[idx[ptr[i]:ptr[i + 1]]])[-1] for i in range(cm)])
+    if np.all(np.diff(ptr) == 1):
+        pp = w[idx[ptr[:-1]]]
+    else:
+        pp = np.array([np.add.accumulate(w[idx[ptr[i]:ptr[i + 1]]])[-1] for i in range(cm)])
 
     pv = np.zeros((cm, 8))
     se = np.zeros((cm, 8))
@@ -153,7 +167,12 @@ def consel(reps: api.Reps, datvec, rr, bb, ass=None, alpha=(0.05, 0.10, 0.5, 0.9
     if dist_mode:
         q0 = cdist.combine_rowsums(q0)
     timing["stats_s"] = time.perf_counter() - t0
-    bp = np.array([1.0 - (1.0 - api.smooth_count(q0[i, i0, 0], nb0, threshold) / nb0) for i in range(cm)])
+    sm0 = np.zeros(cm)
+    api.load().cgpu_smooth_count_many.restype = None
+    r0_i0 = np.ascontiguousarray(q0[:, i0, 0])
+    api.load().cgpu_smooth_count_many(r0_i0.ctypes.data_as(C.POINTER(api.RowSum)), cm, nb0, C.c_double(threshold),
+                                      api._dp(sm0))
+    bp = 1.0 - (1.0 - sm0 / nb0)
     pv[:, 0] = bp
     for c in (0, 2, 3, 4, 5):
         se[:, c] = np.sqrt(pv[:, c] * (1.0 - pv[:, c]) / nb0)

@@ -58,6 +58,10 @@ int cgpu_version(void);
 int cgpu_set_shard(int rank, int world);
 int cgpu_shard_range(int bb, int *b_begin, int *b_end);
 
+/* Host helper: datvec[i] = sum_j L[i][j] in the reference's left-to-right order
+ * (src/makermt.c:159-162), rows spread over host threads.  No device involved.      */
+void cgpu_host_rowsums(const double *L, int K, int n, double *datvec);
+
 /* --------------------------------------------------------------- makermt side */
 /* Replaces the loop `for(i<kk){repmat=new_lmat; scaleboot(datmat,repmat,mm,nn,
  * bn[i],bb[i]); fwrite_bmat;}` of genrmt (src/makermt.c:201-211) together with
@@ -127,6 +131,8 @@ typedef struct cgpu_rowsum {
 /* cntdist(v,B,t,3) (src/consel.c:1842-1860) from the summary of row v at threshold t:
  * pure host helper (cntdist(...,2) is q->cnt itself).                               */
 double cgpu_smooth_count(const cgpu_rowsum *q, int B, double t);
+/* the same for `count` summaries of rows of equal length B at one threshold t */
+void cgpu_smooth_count_many(const cgpu_rowsum *q, int count, int B, double t, double *out);
 
 /* Replaces cntdist(statmats[s][i],bb[s],x,mode) inside vcalpval/invtpval/do_bptest/
  * do_bootrep (src/consel.c:2775-2778, 2845-2848, 1503-1507): nq thresholds per item,
@@ -144,10 +150,15 @@ int cgpu_mctest(const cgpu_reps *r, int i0, const double *datvec, double varadd,
                 double *wsh);
 
 /* -------------------------------------------------------------- introspection */
-/* Device time (ms, CUDA events on the library's stream) of the last cgpu_scaleboot_*
- * call: [0] upload, [1] rng/jump, [2] resample, [3] contraction, [4] download,
- * [5] whole call (first to last event, includes launch gaps).                     */
-int cgpu_last_timing(double *ms6);
+/* Device time (ms, CUDA events on the library's streams) of the last cgpu_scaleboot_*
+ * call: [0] upload, [1] rng/jump, [2] resample, [3] contraction (all kernels),
+ * [4] download, [5] whole call (first to last event, includes launch gaps),
+ * [6] tensor-core GEMM only, [7] fixed-point recombination only (CGPU_SUM_INT8).   */
+int cgpu_last_timing(double *ms8);
+/* Tuning switches (development / measurement): "overlap" 0|1 (two-stream pipeline of
+ * resampling and contraction), "hist_algo" 0|1|2, "contract_algo" -1|0|1|2,
+ * "i8_oneshot" 0|1.  Returns CGPU_EINVAL for an unknown name.                       */
+int cgpu_set_option(const char *name, int value);
 /* number of kernels launched by this library since cgpu_init (bench `gpu_launches`) */
 long long cgpu_launch_count(void);
 /* raw device pointer + shape of a replicate block, so a host framework can wrap it

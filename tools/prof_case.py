@@ -14,7 +14,8 @@ L = base[None, :] + 0.106 * rng.standard_normal((K, n)) - 0.5 * np.arange(K)[:, 
 cg.init()
 m = cg.Matrix(L)
 _, bn, _ = cg.scale_setup(L, [0.5, 1.0, 1.4])
-for sm in (0, 1):
+modes = [int(x) for x in sys.argv[5].split(',')] if len(sys.argv) > 5 else [0, 1]
+for sm in modes:
     for it in range(2):
         r = m.scaleboot(bn, [B] * 3, 7, rng_mode=rng_mode, sum_mode=sm)
         t = cg.last_timing()
