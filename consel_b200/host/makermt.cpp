@@ -4,7 +4,7 @@
 // .pa/.mt/.lnf/... readers, scale set-up, .vt/.rmt writers, stdout lines — is host code
 // that follows the reference's observable behaviour line by line (citations inline).
 //
-// Extensions (not in the reference): --rng mt|philox, --sum strict|fast, --gpu N.
+// Extensions (not in the reference): --rng mt|philox, --sum strict|fast|int8, --gpu N.
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -180,6 +180,7 @@ int main(int argc, char **argv) {
             std::string v = argv[++i];
             if (v == "strict") P.sum_mode = CGPU_SUM_STRICT;
             else if (v == "fast") P.sum_mode = CGPU_SUM_FAST;
+            else if (v == "int8") P.sum_mode = CGPU_SUM_INT8;
             else byebye();
         } else if (a == "--gpu") {
             need(1);
