@@ -274,19 +274,30 @@ static int scaleboot_core(DevMatrix &m, int S, const int *bn, const int *bb, uns
     } guard{plan};
     std::vector<unsigned long long> base(S + 1, 0);
     for (int s = 0; s < S; s++) base[s + 1] = base[s] + (unsigned long long)bb[s] * (unsigned long long)bn[s];
-    // When the whole run's index stream fits the workspace and this process owns every
-    // replicate, ONE draw launch covers all chunks (fills the machine; per-scale launches
-    // have only ~100-200 chunk CTAs).  Otherwise indices are produced batch by batch.
+    // When this rank's share of the index stream fits the workspace, ONE draw launch covers
+    // all of its scales (fills the machine; a per-scale launch has only ~100-200 chunk
+    // CTAs): the kept draws are S disjoint stream ranges packed into a compact buffer.
+    // Otherwise indices are produced batch by batch.
     bool idx_whole_run = false;
+    std::vector<unsigned long long> idx_off(S + 1, 0);
     if (rng_mode == CGPU_RNG_MT19937) {
+        for (int s = 0; s < S; s++) idx_off[s + 1] = idx_off[s] + (unsigned long long)reps->nb[s] * (unsigned long long)bn[s];
         const unsigned long long idx_budget = (unsigned long long)24 << 30;
-        idx_whole_run = G().shard_world == 1 && base[S] * 4ull <= idx_budget && base[S] > 0;
-        const size_t idx_elems = idx_whole_run ? (size_t)base[S] : (size_t)batch * max_bn;
+        idx_whole_run = S <= 32 && idx_off[S] > 0 && idx_off[S] * idx_bytes((uint32_t)n) <= idx_budget;
+        const size_t idx_elems = idx_whole_run ? (size_t)idx_off[S] : (size_t)batch * max_bn;
         CGPU_CUDA(dev_alloc(&ws.d_idx, idx_elems * idx_bytes((uint32_t)n)));
         pt.begin(1);
         CGPU_TRY(mt_prepare(seed, stream_offset, base[S], &plan, st));
-        if (idx_whole_run)
-            CGPU_TRY(launch_mt_draw(plan.d_states, plan.chunk_log2, 0, (int)plan.nchunks, 0, base[S], (uint32_t)n, ws.d_idx, st));
+        if (idx_whole_run) {
+            std::vector<unsigned long long> lo(S), hi(S);
+            for (int s = 0; s < S; s++) {
+                lo[s] = base[s] + (unsigned long long)reps->b0[s] * (unsigned long long)bn[s];
+                hi[s] = lo[s] + (unsigned long long)reps->nb[s] * (unsigned long long)bn[s];
+            }
+            DrawPlan dp;
+            CGPU_TRY(make_draw_plan(S, lo.data(), hi.data(), idx_off.data(), plan.chunk_log2, base[S], &dp));
+            CGPU_TRY(launch_mt_draw(plan.d_states, plan.chunk_log2, dp, (uint32_t)n, ws.d_idx, st));
+        }
         pt.end();
     }
 
@@ -317,11 +328,10 @@ static int scaleboot_core(DevMatrix &m, int S, const int *bn, const int *bb, uns
                 const unsigned long long hi = lo + (unsigned long long)nbat * bn[s];
                 const unsigned char *idx_src = ws.d_idx;
                 if (idx_whole_run) {
-                    idx_src = ws.d_idx + lo * idx_bytes((uint32_t)n);
+                    idx_src = ws.d_idx + (idx_off[s] + (unsigned long long)a * bn[s]) * idx_bytes((uint32_t)n);
                 } else {
-                    const unsigned long long c0 = lo >> plan.chunk_log2, c1 = (hi - 1) >> plan.chunk_log2;
                     pt.begin(1);
-                    CGPU_TRY(launch_mt_draw(plan.d_states, plan.chunk_log2, c0, (int)(c1 - c0 + 1), lo, hi, (uint32_t)n, ws.d_idx, st));
+                    CGPU_TRY(launch_mt_draw_range(plan.d_states, plan.chunk_log2, lo, hi, (uint32_t)n, ws.d_idx, st));
                     pt.end();
                 }
                 pt.begin(2, aux);
@@ -671,8 +681,7 @@ int cgpu_resample_counts(int n, int S, const int *bn, const int *bb, unsigned lo
         CGPU_CUDA(dev_alloc(&ws.d_idx, (size_t)nb * bn[s] * idx_bytes((uint32_t)n)));
         CGPU_TRY(mt_prepare(seed, stream_offset, total, &plan, st));
         const unsigned long long lo = base + (unsigned long long)b0 * bn[s], hi = lo + (unsigned long long)nb * bn[s];
-        const unsigned long long c0 = lo >> plan.chunk_log2, c1 = (hi - 1) >> plan.chunk_log2;
-        CGPU_TRY(launch_mt_draw(plan.d_states, plan.chunk_log2, c0, (int)(c1 - c0 + 1), lo, hi, (uint32_t)n, ws.d_idx, st));
+        CGPU_TRY(launch_mt_draw_range(plan.d_states, plan.chunk_log2, lo, hi, (uint32_t)n, ws.d_idx, st));
         CGPU_TRY(launch_hist_from_idx(ws.d_idx, n, NP, bn[s], nb, ws.d_counts[0], ws.d_err, st));
     } else if (rng_mode == CGPU_RNG_PHILOX) {
         CGPU_TRY(launch_hist_philox((unsigned long long)seed, s, b0, n, NP, bn[s], nb, ws.d_counts[0], ws.d_err, st));
@@ -715,9 +724,8 @@ int cgpu_mt19937_stream(unsigned long seed, unsigned long long skip, unsigned lo
     uint32_t *d_idx = nullptr;
     CGPU_CUDA(dev_alloc(&d_idx, (size_t)count * sizeof(uint32_t)));
     const unsigned long long lo = skip, hi = skip + count;
-    const unsigned long long c0 = lo >> plan.chunk_log2, c1 = (hi - 1) >> plan.chunk_log2;
-    // n = 2^32 is not representable: ask for the raw tempered word via the identity n -> y
-    int rc = launch_mt_draw(plan.d_states, plan.chunk_log2, c0, (int)(c1 - c0 + 1), lo, hi, 0u, d_idx, st);
+    // n = 0 asks for the raw tempered words
+    int rc = launch_mt_draw_range(plan.d_states, plan.chunk_log2, lo, hi, 0u, d_idx, st);
     if (rc == CGPU_OK) {
         cudaMemcpyAsync(out, d_idx, (size_t)count * sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
         cudaError_t e = cudaStreamSynchronize(st);

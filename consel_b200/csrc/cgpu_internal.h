@@ -129,9 +129,19 @@ int launch_mt_jump(const uint32_t *d_src, uint32_t *d_dst, const uint32_t *d_pol
 // for raw tempered 32-bit words
 inline bool idx_is16(uint32_t n) { return n > 0 && n <= 65536; }
 inline size_t idx_bytes(uint32_t n) { return idx_is16(n) ? 2 : 4; }
-int launch_mt_draw(const uint32_t *d_states, int chunk_log2, unsigned long long first_chunk,
-                   int nchunks, unsigned long long lo, unsigned long long hi, uint32_t n,
-                   void *d_idx, cudaStream_t st);
+struct DrawPlan {
+    int nranges, nintervals;
+    unsigned long long lo[32], hi[32], off[32];  // stream ranges to keep -> index-buffer offsets
+    unsigned long long first[32];                // chunk intervals to run
+    int cum[33];
+    unsigned long long stream_end;               // draws beyond this are never generated
+};
+int make_draw_plan(int nranges, const unsigned long long *lo, const unsigned long long *hi,
+                   const unsigned long long *off, int chunk_log2, unsigned long long stream_end, DrawPlan *plan);
+int launch_mt_draw(const uint32_t *d_states, int chunk_log2, const DrawPlan &plan, uint32_t n, void *d_idx,
+                   cudaStream_t st);
+int launch_mt_draw_range(const uint32_t *d_states, int chunk_log2, unsigned long long lo, unsigned long long hi,
+                         uint32_t n, void *d_idx, cudaStream_t st);
 // resample_kernels.cu
 // counts layout: rows == false -> "BJ8" words (8 replicates interleaved per site);
 //                rows == true  -> plain uint8 rows [replicate][NP] (tensor-core operand)

@@ -119,32 +119,45 @@ __device__ __forceinline__ uint32_t site_index(uint32_t y, uint32_t n, double dn
     return (uint32_t)k;
 }
 
-// NCH chunks per CTA: the four block barriers of a regeneration step are shared by NCH
-// independent generator states, which is what the kernel is bound by (a lone state
-// spends ~820 cycles per 624 draws mostly waiting at barriers).
+// NCH chunks per CTA share the four block barriers of a regeneration step.
+// The draws to keep are given as up to 32 disjoint stream ranges [lo, hi) (one per scale:
+// the replicate columns this rank owns), each mapped to an offset of the compact index
+// buffer; the chunks to run are the union of the chunk intervals covering those ranges.
 template <int PATH, typename IdxT, int NCH>
 __global__ void __launch_bounds__(DRAW_THREADS)
-mt_draw_kernel(const uint32_t *__restrict__ states, int chunk_log2, unsigned long long first_chunk, int nchunks,
-               unsigned long long lo, unsigned long long hi, uint32_t n, IdxT *__restrict__ idx) {
+mt_draw_kernel(const uint32_t *__restrict__ states, int chunk_log2, DrawPlan plan, uint32_t n, IdxT *__restrict__ idx) {
     __shared__ uint32_t buf[NCH][2][MT_N + 1];
     const int tid = threadIdx.x;
     const double dn = (double)n;
     unsigned long long d_begin[NCH], d_end[NCH];
+    int rcur[NCH];
+    unsigned long long fast_until[NCH];  // steps below this take the branch-free store (or skip) path
+    bool inside[NCH];
+    IdxT *outp[NCH];
     unsigned long long steps = 0;
 #pragma unroll
     for (int c = 0; c < NCH; c++) {
         const int ci = blockIdx.x * NCH + c;
-        const unsigned long long chunk = first_chunk + ci;
-        d_begin[c] = chunk << chunk_log2;
-        d_end[c] = d_begin[c] + (1ull << chunk_log2);
-        if (d_end[c] > hi) d_end[c] = hi;
-        if (ci >= nchunks || d_end[c] <= d_begin[c]) {
-            d_end[c] = d_begin[c];  // inactive slot
-        } else {
-            const uint32_t *w = states + chunk * MT_N;
-            for (int i = tid; i < MT_N; i += DRAW_THREADS) buf[c][0][i] = w[i];
-            const unsigned long long st = (d_end[c] - d_begin[c] + MT_N - 1) / MT_N;
-            steps = st > steps ? st : steps;
+        d_begin[c] = d_end[c] = 0;
+        rcur[c] = 0;
+        fast_until[c] = 0;
+        inside[c] = false;
+        outp[c] = idx;
+        if (ci < plan.cum[plan.nintervals]) {
+            int iv = 0;
+            while (ci >= plan.cum[iv + 1]) iv++;
+            const unsigned long long chunk = plan.first[iv] + (unsigned long long)(ci - plan.cum[iv]);
+            d_begin[c] = chunk << chunk_log2;
+            d_end[c] = d_begin[c] + (1ull << chunk_log2);
+            if (d_end[c] > plan.stream_end) d_end[c] = plan.stream_end;
+            if (d_end[c] > d_begin[c]) {
+                const uint32_t *w = states + chunk * MT_N;
+                for (int i = tid; i < MT_N; i += DRAW_THREADS) buf[c][0][i] = w[i];
+                const unsigned long long st = (d_end[c] - d_begin[c] + MT_N - 1) / MT_N;
+                steps = st > steps ? st : steps;
+            } else {
+                d_end[c] = d_begin[c];
+            }
         }
     }
     __syncthreads();
@@ -185,16 +198,52 @@ mt_draw_kernel(const uint32_t *__restrict__ states, int chunk_log2, unsigned lon
         __syncthreads();
 #pragma unroll
         for (int c = 0; c < NCH; c++) {
+            const uint32_t *nw = buf[c][cur ^ 1];
+            if (it < fast_until[c]) {
+                // fast path: the whole block lies inside one range (store all 624) or outside all
+                if (inside[c]) {
+#pragma unroll
+                    for (int i = tid; i < MT_N; i += DRAW_THREADS) outp[c][i] = (IdxT)site_index<PATH>(mt_temper(nw[i]), n, dn);
+                    outp[c] += MT_N;
+                }
+                continue;
+            }
+            // slow path (a few times per chunk): block touching a range boundary or the chunk end
             const unsigned long long d0 = d_begin[c] + it * MT_N;
-            if (d0 < d_end[c] && d0 + MT_N > lo) {
-                // 32-bit window [i_lo, i_hi) of this block's draws that fall inside [lo, d_end)
+            if (d0 >= d_end[c]) {
+                fast_until[c] = ~0ull;
+                inside[c] = false;
+                continue;
+            }
+            const unsigned long long d1 = d_end[c] - d0 >= (unsigned long long)MT_N ? d0 + MT_N : d_end[c];
+            while (rcur[c] < plan.nranges && d0 >= plan.hi[rcur[c]]) rcur[c]++;
+            for (int r = rcur[c]; r < plan.nranges && plan.lo[r] < d1; r++) {
+                const unsigned long long lo = plan.lo[r], hi = plan.hi[r];
                 const int i_lo = d0 >= lo ? 0 : (int)(lo - d0);
-                const int i_hi = d_end[c] - d0 >= (unsigned long long)MT_N ? MT_N : (int)(d_end[c] - d0);
-                const uint32_t *nw = buf[c][cur ^ 1];
-                IdxT *out = idx + (long long)(d0 - lo);  // may point before idx when i_lo > 0; only [i_lo, i_hi) is touched
+                const int i_hi = (int)((d1 < hi ? d1 : hi) - d0);
+                IdxT *out = idx + plan.off[r] + (long long)(d0 - lo);  // only [i_lo, i_hi) is touched
 #pragma unroll
                 for (int i = tid; i < MT_N; i += DRAW_THREADS)
                     if (i >= i_lo && i < i_hi) out[i] = (IdxT)site_index<PATH>(mt_temper(nw[i]), n, dn);
+            }
+            // plan the following blocks: how many of them are entirely inside / outside
+            const unsigned long long dn0 = d0 + MT_N;
+            while (rcur[c] < plan.nranges && dn0 >= plan.hi[rcur[c]]) rcur[c]++;
+            fast_until[c] = it + 1;
+            inside[c] = false;
+            if (rcur[c] < plan.nranges && dn0 < d_end[c]) {
+                const int r = rcur[c];
+                if (plan.lo[r] <= dn0) {
+                    const unsigned long long lim = plan.hi[r] < d_end[c] ? plan.hi[r] : d_end[c];
+                    fast_until[c] = it + 1 + (lim - dn0) / MT_N;
+                    inside[c] = true;
+                    outp[c] = idx + plan.off[r] + (dn0 - plan.lo[r]);
+                } else {
+                    const unsigned long long lim = plan.lo[r] < d_end[c] ? plan.lo[r] : d_end[c];
+                    fast_until[c] = it + 1 + (lim - dn0) / MT_N;
+                }
+            } else if (rcur[c] >= plan.nranges) {
+                fast_until[c] = ~0ull;  // nothing left to keep in this chunk
             }
         }
         cur ^= 1;
@@ -204,30 +253,75 @@ mt_draw_kernel(const uint32_t *__restrict__ states, int chunk_log2, unsigned lon
 }
 
 template <int PATH, typename IdxT>
-static void mt_draw_launch(const uint32_t *d_states, int chunk_log2, unsigned long long first_chunk, int nchunks,
-                           unsigned long long lo, unsigned long long hi, uint32_t n, IdxT *idx, cudaStream_t st) {
+static void mt_draw_launch(const uint32_t *d_states, int chunk_log2, const DrawPlan &plan, uint32_t n, IdxT *idx,
+                           cudaStream_t st) {
     const int sms = G().sm_count > 0 ? G().sm_count : 148;
+    const int nchunks = plan.cum[plan.nintervals];
     const int force = G().opt_draw_nch;
     if (force == 4 || (force < 0 && nchunks >= 8 * sms))
-        mt_draw_kernel<PATH, IdxT, 4><<<(nchunks + 3) / 4, DRAW_THREADS, 0, st>>>(d_states, chunk_log2, first_chunk, nchunks, lo, hi, n, idx);
+        mt_draw_kernel<PATH, IdxT, 4><<<(nchunks + 3) / 4, DRAW_THREADS, 0, st>>>(d_states, chunk_log2, plan, n, idx);
     else if (force == 2 || (force < 0 && nchunks >= 4 * sms))
-        mt_draw_kernel<PATH, IdxT, 2><<<(nchunks + 1) / 2, DRAW_THREADS, 0, st>>>(d_states, chunk_log2, first_chunk, nchunks, lo, hi, n, idx);
+        mt_draw_kernel<PATH, IdxT, 2><<<(nchunks + 1) / 2, DRAW_THREADS, 0, st>>>(d_states, chunk_log2, plan, n, idx);
     else
-        mt_draw_kernel<PATH, IdxT, 1><<<nchunks, DRAW_THREADS, 0, st>>>(d_states, chunk_log2, first_chunk, nchunks, lo, hi, n, idx);
+        mt_draw_kernel<PATH, IdxT, 1><<<nchunks, DRAW_THREADS, 0, st>>>(d_states, chunk_log2, plan, n, idx);
 }
 
-int launch_mt_draw(const uint32_t *d_states, int chunk_log2, unsigned long long first_chunk,
-                   int nchunks, unsigned long long lo, unsigned long long hi, uint32_t n,
-                   void *d_idx, cudaStream_t st) {
-    if (nchunks <= 0) return CGPU_OK;
+// plan for `nranges` disjoint, ascending stream ranges; off[r] = index-buffer offset of range r
+int make_draw_plan(int nranges, const unsigned long long *lo, const unsigned long long *hi,
+                   const unsigned long long *off, int chunk_log2, unsigned long long stream_end, DrawPlan *plan) {
+    if (nranges < 1 || nranges > 32) {
+        set_error(CGPU_EINVAL, "draw plan with %d ranges (1..32)", nranges);
+        return CGPU_EINVAL;
+    }
+    plan->nranges = 0;
+    plan->nintervals = 0;
+    plan->cum[0] = 0;
+    plan->stream_end = stream_end;
+    for (int r = 0; r < nranges; r++) {
+        if (hi[r] <= lo[r]) continue;
+        const int k = plan->nranges++;
+        plan->lo[k] = lo[r];
+        plan->hi[k] = hi[r];
+        plan->off[k] = off[r];
+        unsigned long long c0 = lo[r] >> chunk_log2, c1 = (hi[r] - 1) >> chunk_log2;
+        if (plan->nintervals > 0) {
+            const int p = plan->nintervals - 1;
+            const unsigned long long last = plan->first[p] + (unsigned long long)(plan->cum[p + 1] - plan->cum[p]) - 1;
+            if (c0 <= last) c0 = last + 1;  // the boundary chunk is already scheduled (it stores into every range it touches)
+            if (c0 > c1) continue;
+            if (c0 == last + 1) {  // extend the previous interval
+                plan->cum[p + 1] += (int)(c1 - c0 + 1);
+                continue;
+            }
+        }
+        const int p = plan->nintervals++;
+        plan->first[p] = c0;
+        plan->cum[p + 1] = plan->cum[p] + (int)(c1 - c0 + 1);
+    }
+    return CGPU_OK;
+}
+
+int launch_mt_draw(const uint32_t *d_states, int chunk_log2, const DrawPlan &plan, uint32_t n, void *d_idx,
+                   cudaStream_t st) {
+    if (plan.nranges <= 0 || plan.cum[plan.nintervals] <= 0) return CGPU_OK;
     uint32_t *i32 = static_cast<uint32_t *>(d_idx);
     uint16_t *i16 = static_cast<uint16_t *>(d_idx);
-    if (n == 0) mt_draw_launch<2, uint32_t>(d_states, chunk_log2, first_chunk, nchunks, lo, hi, n, i32, st);
-    else if (idx_is16(n)) mt_draw_launch<0, uint16_t>(d_states, chunk_log2, first_chunk, nchunks, lo, hi, n, i16, st);
-    else if (n < (1u << 21)) mt_draw_launch<0, uint32_t>(d_states, chunk_log2, first_chunk, nchunks, lo, hi, n, i32, st);
-    else mt_draw_launch<1, uint32_t>(d_states, chunk_log2, first_chunk, nchunks, lo, hi, n, i32, st);
+    if (n == 0) mt_draw_launch<2, uint32_t>(d_states, chunk_log2, plan, n, i32, st);
+    else if (idx_is16(n)) mt_draw_launch<0, uint16_t>(d_states, chunk_log2, plan, n, i16, st);
+    else if (n < (1u << 21)) mt_draw_launch<0, uint32_t>(d_states, chunk_log2, plan, n, i32, st);
+    else mt_draw_launch<1, uint32_t>(d_states, chunk_log2, plan, n, i32, st);
     CGPU_LAUNCH_CHECK();
     return CGPU_OK;
+}
+
+// one contiguous range [lo, hi) stored at idx[0 ..)
+int launch_mt_draw_range(const uint32_t *d_states, int chunk_log2, unsigned long long lo, unsigned long long hi,
+                         uint32_t n, void *d_idx, cudaStream_t st) {
+    if (hi <= lo) return CGPU_OK;
+    DrawPlan plan;
+    const unsigned long long off = 0;
+    CGPU_TRY(make_draw_plan(1, &lo, &hi, &off, chunk_log2, hi, &plan));
+    return launch_mt_draw(d_states, chunk_log2, plan, n, d_idx, st);
 }
 
 }  // namespace cgpu
