@@ -13,10 +13,9 @@
 //                    output word j is the XOR of x_{i+j} over the set bits i of g.
 //                    The bit range of g is sliced over gridDim.y CTAs (atomicXor
 //                    combine) so early rounds of the doubling tree still fill SMs.
-//   mt_draw_kernel   one CTA per chunk of 2^m draws: ping-pong block regeneration
-//                    in shared memory (3 phases of <=227 independent lanes, exactly
-//                    the dependency structure of next_state), tempering, site index,
-//                    coalesced store of the indices.
+//   mt_draw_kernel   227 lanes per chunk of 2^m draws: block regeneration with the
+//                    three dependent phases of next_state chained in registers (one
+//                    barrier per 624 draws), tempering, site index, coalesced stores.
 #include "cgpu_internal.h"
 
 namespace cgpu {
@@ -33,6 +32,31 @@ __device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
     y ^= y >> 18;
     return y;
 }
+
+// The draw kernel is bound by the integer-logic pipe (LOP3/SHF issue every other cycle per
+// scheduler; the multiplier pipe is a separate one with the same rate), so its copies of the
+// two functions do their right shifts as high halves of products with a power of two.  The
+// multiplier is read from a register the compiler cannot see through (strength reduction
+// would turn it back into a shift).
+__device__ __forceinline__ uint32_t shr_mul(uint32_t v, uint32_t pow2_32_minus_s) {
+    uint32_t r;
+    asm("mul.hi.u32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(pow2_32_minus_s));
+    return r;
+}
+
+struct DrawConsts { uint32_t p31, p21, p14; };  // 2^(32-1), 2^(32-11), 2^(32-18)
+
+__device__ __forceinline__ uint32_t mt_twist_bal(uint32_t hi, uint32_t lo, const DrawConsts &k) {
+    const uint32_t l1 = shr_mul(lo, k.p31), h1 = shr_mul(hi, k.p31);
+    uint32_t y1;  // (l1 & ~0x40000000) | (h1 & 0x40000000): bit select as ONE lop3 (LUT 0xd8)
+    asm("lop3.b32 %0, %1, %2, 0x40000000, 0xd8;" : "=r"(y1) : "r"(l1), "r"(h1));
+    const uint32_t bit = lo - 2u * l1;  // lo & 1 as a multiply-add
+    return y1 ^ (bit * 0x9908b0dfu);
+}
+
+// tempering: left shifts become multiplies on their own, right shifts stay on the logic pipe
+// (with the twist above that evens out the two pipes: 7 multiplier / 8 logic ops per draw)
+__device__ __forceinline__ uint32_t mt_temper_bal(uint32_t y, const DrawConsts &) { return mt_temper(y); }
 
 // ------------------------------------------------------------------ jump
 constexpr int JUMP_THREADS = 640;
@@ -102,7 +126,6 @@ int launch_mt_jump(const uint32_t *d_src, uint32_t *d_dst, const uint32_t *d_pol
 }
 
 // ------------------------------------------------------------------ draws
-constexpr int DRAW_THREADS = 256;
 
 // site index of a draw: (int)((double)y * 2^-32 * n) with the reference's clamp
 // (src/mt19937.c:195, src/makermt.c:55-60).  For n < 2^21 the product y*n is exact
@@ -119,136 +142,165 @@ __device__ __forceinline__ uint32_t site_index(uint32_t y, uint32_t n, double dn
     return (uint32_t)k;
 }
 
-// NCH chunks per CTA share the four block barriers of a regeneration step.
-// The draws to keep are given as up to 32 disjoint stream ranges [lo, hi) (one per scale:
-// the replicate columns this rank owns), each mapped to an offset of the compact index
-// buffer; the chunks to run are the union of the chunk intervals covering those ranges.
-template <int PATH, typename IdxT, int NCH>
-__global__ void __launch_bounds__(DRAW_THREADS)
-mt_draw_kernel(const uint32_t *__restrict__ states, int chunk_log2, DrawPlan plan, uint32_t n, IdxT *__restrict__ idx) {
-    __shared__ uint32_t buf[NCH][2][MT_N + 1];
-    const int tid = threadIdx.x;
+// Block regeneration with the dependency chain in registers.  Lane t (0..226) of a chunk
+// owns words t, t+227, t+454 of the 624-word block.  new[t] needs only old words;
+// new[t+227] = new[t] ^ twist(old[t+227], old[t+228]) and new[t+454] = new[t+227] ^
+// twist(old[t+454], old[t+455]) chain through the SAME lane, so the three "phases" of
+// next_state need no barrier between them; the only cross-lane exception (word 623 wants
+// new[0]) is recomputed by lane 169.  The lane keeps its three words in registers from one
+// block to the next, reads its four neighbour words from the ping-pong shared buffer, and
+// tempers + stores the indices straight from registers: one barrier per block.
+//
+// CPC chunks are packed 227 lanes apiece into one CTA.  The draws to keep are given as up
+// to 32 disjoint stream ranges [lo, hi) (one per scale: the replicate columns this rank
+// owns), each mapped to an offset of the compact index buffer; the chunks to run are the
+// union of the chunk intervals covering those ranges.
+constexpr int DRAW_H = MT_N - MT_M;  // 227
+template <int CPC> struct DrawCfg {
+    static constexpr int threads = (CPC * DRAW_H + 31) / 32 * 32;
+    static constexpr int ctas = 6 / CPC;  // resident CTAs per SM the register budget is held to (6 chunks, <= 40 registers)
+};
+
+template <int PATH, typename IdxT>
+struct DrawLane {
+    uint32_t r0, r1, r2;      // words t, t+227, t+454 of the current block
+    unsigned int fast_until;  // blocks below this index take the unconditional store (or skip) path
+    int rcur;
+    bool inside, third;
+    IdxT *outp;
+};
+
+// one block (624 draws) of one chunk; CUR = which half of the ping-pong buffer holds the old block
+template <int PATH, typename IdxT, int CUR>
+__device__ __forceinline__ void draw_step(DrawLane<PATH, IdxT> &L, uint32_t *bt, int t, unsigned int it, int c,
+                                          const unsigned long long *s_begin, const unsigned long long *s_end,
+                                          const DrawPlan &plan, uint32_t n, double dn, IdxT *idx, const DrawConsts &kc) {
+    constexpr int H = DRAW_H;
+    // bt = &buf[c][0][t]; the other half is MT_N words further
+    const uint32_t *o = bt + CUR * MT_N;
+    uint32_t *nw = bt + (CUR ^ 1) * MT_N;
+    L.r0 = o[MT_M] ^ mt_twist_bal(L.r0, o[1], kc);
+    L.r1 = L.r0 ^ mt_twist_bal(L.r1, o[H + 1], kc);
+    nw[0] = L.r0;
+    nw[H] = L.r1;
+    if (L.third) {
+        uint32_t nxt;
+        if (t == MT_N - 2 * H - 1) nxt = o[MT_M - t] ^ mt_twist_bal(o[-t], o[1 - t], kc);  // new[0]
+        else nxt = o[2 * H + 1];
+        L.r2 = L.r1 ^ mt_twist_bal(L.r2, nxt, kc);
+        nw[2 * H] = L.r2;
+    }
+    if (it < L.fast_until) {
+        if (L.inside) {
+            L.outp[0] = (IdxT)site_index<PATH>(mt_temper_bal(L.r0, kc), n, dn);
+            L.outp[H] = (IdxT)site_index<PATH>(mt_temper_bal(L.r1, kc), n, dn);
+            if (L.third) L.outp[2 * H] = (IdxT)site_index<PATH>(mt_temper_bal(L.r2, kc), n, dn);
+            L.outp += MT_N;
+        }
+        return;
+    }
+    // slow path (a few times per chunk): block touching a range boundary or the chunk end
+    const unsigned long long d_end = s_end[c];
+    const unsigned long long d0 = s_begin[c] + (unsigned long long)it * MT_N;
+    if (d0 >= d_end) {
+        L.fast_until = ~0u;
+        L.inside = false;
+        return;
+    }
+    const unsigned long long d1 = d_end - d0 >= (unsigned long long)MT_N ? d0 + MT_N : d_end;
+    int rcur = L.rcur;
+    while (rcur < plan.nranges && d0 >= plan.hi[rcur]) rcur++;
+    for (int r = rcur; r < plan.nranges && plan.lo[r] < d1; r++) {
+        const unsigned long long lo = plan.lo[r], hi = plan.hi[r];
+        const int i_lo = d0 >= lo ? 0 : (int)(lo - d0);
+        const int i_hi = (int)((d1 < hi ? d1 : hi) - d0);
+        IdxT *out = idx + plan.off[r] + (long long)(d0 - lo) + t;  // only [i_lo, i_hi) is touched
+        if (t >= i_lo && t < i_hi) out[0] = (IdxT)site_index<PATH>(mt_temper_bal(L.r0, kc), n, dn);
+        if (t + H >= i_lo && t + H < i_hi) out[H] = (IdxT)site_index<PATH>(mt_temper_bal(L.r1, kc), n, dn);
+        if (L.third && t + 2 * H >= i_lo && t + 2 * H < i_hi)
+            out[2 * H] = (IdxT)site_index<PATH>(mt_temper_bal(L.r2, kc), n, dn);
+    }
+    // plan the following blocks: how many of them are entirely inside / outside
+    const unsigned long long dn0 = d0 + MT_N;
+    while (rcur < plan.nranges && dn0 >= plan.hi[rcur]) rcur++;
+    L.fast_until = it + 1;
+    L.inside = false;
+    if (rcur < plan.nranges && dn0 < d_end) {
+        if (plan.lo[rcur] <= dn0) {
+            const unsigned long long lim = plan.hi[rcur] < d_end ? plan.hi[rcur] : d_end;
+            L.fast_until = it + 1 + (unsigned int)((lim - dn0) / MT_N);
+            L.inside = true;
+            L.outp = idx + plan.off[rcur] + (dn0 - plan.lo[rcur]) + t;
+        } else {
+            const unsigned long long lim = plan.lo[rcur] < d_end ? plan.lo[rcur] : d_end;
+            L.fast_until = it + 1 + (unsigned int)((lim - dn0) / MT_N);
+        }
+    } else if (rcur >= plan.nranges) {
+        L.fast_until = ~0u;  // nothing left to keep in this chunk
+    }
+    L.rcur = rcur;
+}
+
+template <int PATH, typename IdxT, int CPC>
+__global__ void __launch_bounds__(DrawCfg<CPC>::threads, DrawCfg<CPC>::ctas)
+mt_draw_kernel(const uint32_t *__restrict__ states, int chunk_log2, DrawPlan plan, uint32_t n, IdxT *__restrict__ idx,
+               DrawConsts kc) {
+    __shared__ uint32_t buf[CPC + 1][2][MT_N];  // +1: the padding lanes of the last warp index a dummy slot
+    __shared__ unsigned long long s_begin[CPC + 1], s_end[CPC + 1];  // read on the slow path only
+    constexpr int H = DRAW_H;
+    const int c = threadIdx.x / H, t = threadIdx.x - c * H;
     const double dn = (double)n;
-    unsigned long long d_begin[NCH], d_end[NCH];
-    int rcur[NCH];
-    unsigned long long fast_until[NCH];  // steps below this take the branch-free store (or skip) path
-    bool inside[NCH];
-    IdxT *outp[NCH];
-    unsigned long long steps = 0;
-#pragma unroll
-    for (int c = 0; c < NCH; c++) {
-        const int ci = blockIdx.x * NCH + c;
-        d_begin[c] = d_end[c] = 0;
-        rcur[c] = 0;
-        fast_until[c] = 0;
-        inside[c] = false;
-        outp[c] = idx;
-        if (ci < plan.cum[plan.nintervals]) {
+    const unsigned int steps = (unsigned int)(((1ull << chunk_log2) + MT_N - 1) / MT_N);
+
+    DrawLane<PATH, IdxT> L;
+    L.r0 = L.r1 = L.r2 = 0;
+    L.third = t < MT_N - 2 * H;  // lanes 0..169 own a third word
+    L.rcur = 0;
+    L.fast_until = 0;
+    L.inside = false;
+    L.outp = idx;
+    uint32_t *bt = &buf[c][0][t];
+    {
+        unsigned long long d_begin = 0, d_end = 0;
+        const int ci = blockIdx.x * CPC + c;
+        if (c < CPC && ci < plan.cum[plan.nintervals]) {
             int iv = 0;
             while (ci >= plan.cum[iv + 1]) iv++;
             const unsigned long long chunk = plan.first[iv] + (unsigned long long)(ci - plan.cum[iv]);
-            d_begin[c] = chunk << chunk_log2;
-            d_end[c] = d_begin[c] + (1ull << chunk_log2);
-            if (d_end[c] > plan.stream_end) d_end[c] = plan.stream_end;
-            if (d_end[c] > d_begin[c]) {
-                const uint32_t *w = states + chunk * MT_N;
-                for (int i = tid; i < MT_N; i += DRAW_THREADS) buf[c][0][i] = w[i];
-                const unsigned long long st = (d_end[c] - d_begin[c] + MT_N - 1) / MT_N;
-                steps = st > steps ? st : steps;
+            d_begin = chunk << chunk_log2;
+            d_end = d_begin + (1ull << chunk_log2);
+            if (d_end > plan.stream_end) d_end = plan.stream_end;
+            if (d_end > d_begin) {
+                const uint32_t *w = states + chunk * MT_N + t;
+                L.r0 = w[0];
+                L.r1 = w[H];
+                bt[0] = L.r0;
+                bt[H] = L.r1;
+                if (L.third) {
+                    L.r2 = w[2 * H];
+                    bt[2 * H] = L.r2;
+                }
             } else {
-                d_end[c] = d_begin[c];
+                d_end = d_begin;
             }
+        }
+        if (t == 0) {
+            s_begin[c] = d_begin;
+            s_end[c] = d_end;
         }
     }
     __syncthreads();
-    int cur = 0;
-    constexpr int H = MT_N - MT_M;  // 227 words become computable per dependent step
-    for (unsigned long long it = 0; it < steps; it++) {
-        // phase A: k in [0,227) reads only old words
-        if (tid < H) {
-#pragma unroll
-            for (int c = 0; c < NCH; c++) {
-                const uint32_t *o = buf[c][cur];
-                buf[c][cur ^ 1][tid] = o[tid + MT_M] ^ mt_twist(o[tid], o[tid + 1]);
-            }
-        }
+    // One barrier per block: every read of the old half and write of the new half is done
+    // before the next step swaps their roles.  Lanes without a chunk (padding of the last
+    // warp, chunks past the end) run the same code on zeros in their own buffer slot: their
+    // bounds are empty, so the first slow-path visit turns their stores off for good.
+    for (unsigned int it = 0; it < steps; it += 2) {
+        draw_step<PATH, IdxT, 0>(L, bt, t, it, c, s_begin, s_end, plan, n, dn, idx, kc);
         __syncthreads();
-        // phase B: k in [227,454) reads new[k-227]
-        if (tid < H) {
-            const int k = tid + H;
-#pragma unroll
-            for (int c = 0; c < NCH; c++) {
-                const uint32_t *o = buf[c][cur];
-                uint32_t *nw = buf[c][cur ^ 1];
-                nw[k] = nw[k - H] ^ mt_twist(o[k], o[k + 1]);
-            }
+        if (it + 1 < steps) {
+            draw_step<PATH, IdxT, 1>(L, bt, t, it + 1, c, s_begin, s_end, plan, n, dn, idx, kc);
+            __syncthreads();
         }
-        __syncthreads();
-        // phase C: k in [454,624); the last word wraps to new[0]
-        if (tid < MT_N - 2 * H) {
-            const int k = tid + 2 * H;
-#pragma unroll
-            for (int c = 0; c < NCH; c++) {
-                const uint32_t *o = buf[c][cur];
-                uint32_t *nw = buf[c][cur ^ 1];
-                const uint32_t nxt = (k == MT_N - 1) ? nw[0] : o[k + 1];
-                nw[k] = nw[k - H] ^ mt_twist(o[k], nxt);
-            }
-        }
-        __syncthreads();
-#pragma unroll
-        for (int c = 0; c < NCH; c++) {
-            const uint32_t *nw = buf[c][cur ^ 1];
-            if (it < fast_until[c]) {
-                // fast path: the whole block lies inside one range (store all 624) or outside all
-                if (inside[c]) {
-#pragma unroll
-                    for (int i = tid; i < MT_N; i += DRAW_THREADS) outp[c][i] = (IdxT)site_index<PATH>(mt_temper(nw[i]), n, dn);
-                    outp[c] += MT_N;
-                }
-                continue;
-            }
-            // slow path (a few times per chunk): block touching a range boundary or the chunk end
-            const unsigned long long d0 = d_begin[c] + it * MT_N;
-            if (d0 >= d_end[c]) {
-                fast_until[c] = ~0ull;
-                inside[c] = false;
-                continue;
-            }
-            const unsigned long long d1 = d_end[c] - d0 >= (unsigned long long)MT_N ? d0 + MT_N : d_end[c];
-            while (rcur[c] < plan.nranges && d0 >= plan.hi[rcur[c]]) rcur[c]++;
-            for (int r = rcur[c]; r < plan.nranges && plan.lo[r] < d1; r++) {
-                const unsigned long long lo = plan.lo[r], hi = plan.hi[r];
-                const int i_lo = d0 >= lo ? 0 : (int)(lo - d0);
-                const int i_hi = (int)((d1 < hi ? d1 : hi) - d0);
-                IdxT *out = idx + plan.off[r] + (long long)(d0 - lo);  // only [i_lo, i_hi) is touched
-#pragma unroll
-                for (int i = tid; i < MT_N; i += DRAW_THREADS)
-                    if (i >= i_lo && i < i_hi) out[i] = (IdxT)site_index<PATH>(mt_temper(nw[i]), n, dn);
-            }
-            // plan the following blocks: how many of them are entirely inside / outside
-            const unsigned long long dn0 = d0 + MT_N;
-            while (rcur[c] < plan.nranges && dn0 >= plan.hi[rcur[c]]) rcur[c]++;
-            fast_until[c] = it + 1;
-            inside[c] = false;
-            if (rcur[c] < plan.nranges && dn0 < d_end[c]) {
-                const int r = rcur[c];
-                if (plan.lo[r] <= dn0) {
-                    const unsigned long long lim = plan.hi[r] < d_end[c] ? plan.hi[r] : d_end[c];
-                    fast_until[c] = it + 1 + (lim - dn0) / MT_N;
-                    inside[c] = true;
-                    outp[c] = idx + plan.off[r] + (dn0 - plan.lo[r]);
-                } else {
-                    const unsigned long long lim = plan.lo[r] < d_end[c] ? plan.lo[r] : d_end[c];
-                    fast_until[c] = it + 1 + (lim - dn0) / MT_N;
-                }
-            } else if (rcur[c] >= plan.nranges) {
-                fast_until[c] = ~0ull;  // nothing left to keep in this chunk
-            }
-        }
-        cur ^= 1;
-        // no barrier needed here: the next phase A only writes buf[.][cur^1] (= the old
-        // array, last read in phase C before the barrier above) and reads buf[.][cur].
     }
 }
 
@@ -258,12 +310,13 @@ static void mt_draw_launch(const uint32_t *d_states, int chunk_log2, const DrawP
     const int sms = G().sm_count > 0 ? G().sm_count : 148;
     const int nchunks = plan.cum[plan.nintervals];
     const int force = G().opt_draw_nch;
-    if (force == 4 || (force < 0 && nchunks >= 8 * sms))
-        mt_draw_kernel<PATH, IdxT, 4><<<(nchunks + 3) / 4, DRAW_THREADS, 0, st>>>(d_states, chunk_log2, plan, n, idx);
-    else if (force == 2 || (force < 0 && nchunks >= 4 * sms))
-        mt_draw_kernel<PATH, IdxT, 2><<<(nchunks + 1) / 2, DRAW_THREADS, 0, st>>>(d_states, chunk_log2, plan, n, idx);
+    const DrawConsts kc = {1u << 31, 1u << 21, 1u << 14};
+    if (force == 3 || (force < 0 && nchunks >= 6 * sms))
+        mt_draw_kernel<PATH, IdxT, 3><<<(nchunks + 2) / 3, DrawCfg<3>::threads, 0, st>>>(d_states, chunk_log2, plan, n, idx, kc);
+    else if (force == 2 || (force < 0 && nchunks >= 3 * sms))
+        mt_draw_kernel<PATH, IdxT, 2><<<(nchunks + 1) / 2, DrawCfg<2>::threads, 0, st>>>(d_states, chunk_log2, plan, n, idx, kc);
     else
-        mt_draw_kernel<PATH, IdxT, 1><<<nchunks, DRAW_THREADS, 0, st>>>(d_states, chunk_log2, plan, n, idx);
+        mt_draw_kernel<PATH, IdxT, 1><<<nchunks, DrawCfg<1>::threads, 0, st>>>(d_states, chunk_log2, plan, n, idx, kc);
 }
 
 // plan for `nranges` disjoint, ascending stream ranges; off[r] = index-buffer offset of range r

@@ -8,7 +8,7 @@ cg.init()
 m = cg.Matrix(L)
 _, bn, _ = cg.scale_setup(L, [0.5, 0.6, 0.7, 0.8, 0.9, 1.0, 1.1, 1.2, 1.3, 1.4])
 for log2 in (19, 20, 21, 22):
-    for nch in (1, 2, 4):
+    for nch in (1, 2, 3):
         cg.set_option("chunk_log2", log2); cg.set_option("draw_nch", nch)
         for it in range(3):
             r = m.scaleboot(bn, [B] * 10, 7, rng_mode=0, sum_mode=2); t = cg.last_timing(); r.free()
