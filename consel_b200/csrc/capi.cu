@@ -132,53 +132,123 @@ static int alloc_reps(int K, int S, const int *bb, DevReps **out) {
     return CGPU_OK;
 }
 
-// chunk size (log2 draws) of the MT19937 doubling tree: about 2k chunks, each long
-// enough that its jump (~6M word-XORs) is amortised.
-static int pick_chunk_log2(unsigned long long total_draws) {
+// Chunk size (log2 draws) of the MT19937 jump tree, from a cost model measured on B200:
+// a jump costs ~0.85 us of whole-GPU time (126 us on one SM), a tree level ~20 us of
+// latency, and a draw CTA slot (6 chunks resident per SM) produces one draw per ~1.1 ns;
+// the draw launch runs in whole waves of 6 x SMs chunks.
+static int pick_chunk_log2(unsigned long long needed_draws, unsigned long long stream_end, int nranges) {
     if (G().opt_chunk_log2 >= 10 && G().opt_chunk_log2 <= 30) return G().opt_chunk_log2;
-    int m = 12;
-    while (m < 23 && (total_draws >> m) > 2048) m++;
-    return m;
+    const int sms = G().sm_count > 0 ? G().sm_count : 148;
+    const double slots = 6.0 * sms;
+    int best = 12;
+    double best_cost = 1e300;
+    for (int m = 12; m <= 24; m++) {
+        const double chunk = (double)(1ull << m);
+        const double pn = std::ceil((double)needed_draws / chunk) + nranges;
+        int top = 0;
+        while (((stream_end + (1ull << m) - 1) >> m) > (1ull << top)) top++;
+        if (m + top > MT_MAXLOG) continue;
+        const double waves = std::ceil(pn / slots);
+        const double cost = pn * 0.85e-6 + top * 20e-6 + waves * chunk * 1.1e-9;
+        if (cost < best_cost) {
+            best_cost = cost;
+            best = m;
+        }
+    }
+    return best;
 }
 
-struct MtPlan {
-    uint32_t *d_states = nullptr;
-    int chunk_log2 = 0;
-    unsigned long long nchunks = 0;
-};
-
-// window states W_{offset + p*2^m}, p = 0..P-1, by the doubling tree
-static int mt_prepare(unsigned long seed, unsigned long long stream_offset, unsigned long long total_draws,
-                      MtPlan *plan, cudaStream_t st) {
+// Chunk start states W_{offset + c*2^m} for the chunks c that cover the kept ranges, by a
+// binary jump tree walked from the top bit down: at bit r every live node a (a multiple of
+// 2^(r+1)) hands its state to a + 2^r through the jump x^(2^(m+r)) if any wanted chunk lies
+// in [a + 2^r, a + 2^(r+1)).  One launch per level; the jumps of a level are independent.
+static int mt_prepare(unsigned long seed, unsigned long long stream_offset, unsigned long long stream_end, int nranges,
+                      const unsigned long long *lo, const unsigned long long *hi, MtPlan *plan, cudaStream_t st) {
     Globals &g = G();
-    plan->chunk_log2 = pick_chunk_log2(total_draws);
+    unsigned long long needed = 0;
+    for (int r = 0; r < nranges; r++) needed += hi[r] > lo[r] ? hi[r] - lo[r] : 0;
+    plan->chunk_log2 = pick_chunk_log2(needed, stream_end, nranges);
     const int m = plan->chunk_log2;
-    unsigned long long P = (total_draws + (1ull << m) - 1) >> m;
-    if (P == 0) P = 1;
-    plan->nchunks = P;
+    DrawPlan dp;
+    {
+        std::vector<unsigned long long> off(nranges, 0);
+        CGPU_TRY(make_draw_plan(nranges, lo, hi, off.data(), m, stream_end, &dp));
+    }
+    plan->nintervals = dp.nintervals;
+    for (int i = 0; i < dp.nintervals; i++) {
+        plan->first[i] = dp.first[i];
+        plan->count[i] = dp.cum[i + 1] - dp.cum[i];
+        plan->slot[i] = dp.cum[i];
+    }
+    int nslots = dp.cum[dp.nintervals];
+    if (nslots == 0) return CGPU_OK;
+    const unsigned long long maxchunk = plan->first[plan->nintervals - 1] + (unsigned long long)(plan->count[plan->nintervals - 1] - 1);
     int top = 0;
-    while ((1ull << top) < P) top++;
-    if (m + top > MT_MAXLOG) {
-        set_error(CGPU_EINVAL, "stream of %llu draws exceeds the jump table", total_draws);
+    while (top < 63 && (maxchunk >> top) != 0) top++;
+    if (top > 0 && m + top - 1 > MT_MAXLOG) {
+        set_error(CGPU_EINVAL, "stream of %llu draws exceeds the jump table", stream_end);
         return CGPU_EINVAL;
     }
-    CGPU_CUDA(dev_alloc(&plan->d_states, (size_t)P * MT_N * sizeof(uint32_t)));
-    uint32_t w0[MT_N];
+    auto wanted = [&](unsigned long long a, unsigned long long b) {  // any wanted chunk in [a, b]?
+        for (int i = 0; i < plan->nintervals; i++)
+            if (plan->first[i] <= b && plan->first[i] + (unsigned long long)(plan->count[i] - 1) >= a) return true;
+        return false;
+    };
+    std::vector<std::pair<unsigned long long, int>> extra;  // inner nodes that are not wanted chunks themselves
+    auto slot_get = [&](unsigned long long a) {
+        long long s = plan->slot_of(a);
+        if (s >= 0) return (int)s;
+        for (auto &e : extra)
+            if (e.first == a) return e.second;
+        extra.emplace_back(a, nslots);
+        return nslots++;
+    };
+    std::vector<std::vector<int2>> levels(top);
+    std::vector<unsigned long long> cur{0}, next;
+    const int root = slot_get(0);
+    for (int r = top - 1; r >= 0; r--) {
+        const unsigned long long step = 1ull << r;
+        next.clear();
+        for (unsigned long long a : cur) {
+            if (wanted(a, a + step - 1)) next.push_back(a);
+            if (wanted(a + step, a + 2 * step - 1)) {
+                levels[r].push_back(make_int2(slot_get(a), slot_get(a + step)));
+                next.push_back(a + step);
+            }
+        }
+        cur.swap(next);
+    }
+    size_t npairs = 0;
+    for (auto &l : levels) npairs += l.size();
+    plan->h_stage.assign(MT_N + 2 * npairs, 0u);
+    uint32_t *w0 = plan->h_stage.data();
     mt_seed_window((uint32_t)(seed & 0xffffffffUL), w0);
     if (stream_offset) {
         Gf2Poly gp;
         mt_poly_xpow(stream_offset, &gp);
         uint32_t w1[MT_N];
         mt_jump_host(w0, &gp, w1);
-        memcpy(w0, w1, sizeof(w0));
+        memcpy(w0, w1, sizeof(w1));
     }
-    CGPU_CUDA(cudaMemcpyAsync(plan->d_states, w0, sizeof(w0), cudaMemcpyHostToDevice, st));
-    CGPU_CUDA(cudaStreamSynchronize(st));  // w0 is a stack buffer
-    for (int r = 0; (1ull << r) < P; r++) {
-        unsigned long long have = 1ull << r;
-        int cnt = (int)std::min<unsigned long long>(have, P - have);
-        CGPU_TRY(launch_mt_jump(plan->d_states, plan->d_states + have * MT_N,
-                                g.d_jump_table + (size_t)(m + r) * MT_N, cnt, st));
+    {
+        int2 *hp = reinterpret_cast<int2 *>(plan->h_stage.data() + MT_N);
+        for (int r = top - 1; r >= 0; r--)
+            for (auto &pr : levels[r]) *hp++ = pr;
+    }
+    CGPU_CUDA(dev_alloc(&plan->d_states, (size_t)nslots * MT_N * sizeof(uint32_t)));
+    CGPU_CUDA(cudaMemsetAsync(plan->d_states, 0, (size_t)nslots * MT_N * sizeof(uint32_t), st));
+    CGPU_CUDA(cudaMemcpyAsync(plan->d_states + (size_t)root * MT_N, w0, MT_N * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    if (npairs) {
+        CGPU_CUDA(dev_alloc(&plan->d_pairs, npairs * sizeof(int2)));
+        CGPU_CUDA(cudaMemcpyAsync(plan->d_pairs, plan->h_stage.data() + MT_N, npairs * sizeof(int2), cudaMemcpyHostToDevice, st));
+    }
+    size_t done = 0;
+    for (int r = top - 1; r >= 0; r--) {
+        const int cnt = (int)levels[r].size();
+        if (!cnt) continue;
+        CGPU_TRY(launch_mt_jump(plan->d_states, plan->d_pairs + done, g.d_jump_table + (size_t)(m + r) * MT_POS_STRIDE,
+                                g.jump_nquads[m + r], cnt, st));
+        done += cnt;
     }
     return CGPU_OK;
 }
@@ -270,7 +340,10 @@ static int scaleboot_core(DevMatrix &m, int S, const int *bn, const int *bb, uns
     MtPlan plan;
     struct PlanGuard {
         MtPlan &p;
-        ~PlanGuard() { dev_free(p.d_states); }
+        ~PlanGuard() {
+            dev_free(p.d_states);
+            dev_free(p.d_pairs);
+        }
     } guard{plan};
     std::vector<unsigned long long> base(S + 1, 0);
     for (int s = 0; s < S; s++) base[s + 1] = base[s] + (unsigned long long)bb[s] * (unsigned long long)bn[s];
@@ -287,16 +360,21 @@ static int scaleboot_core(DevMatrix &m, int S, const int *bn, const int *bb, uns
         const size_t idx_elems = idx_whole_run ? (size_t)idx_off[S] : (size_t)batch * max_bn;
         CGPU_CUDA(dev_alloc(&ws.d_idx, idx_elems * idx_bytes((uint32_t)n)));
         pt.begin(1);
-        CGPU_TRY(mt_prepare(seed, stream_offset, base[S], &plan, st));
+        std::vector<unsigned long long> lo(S), hi(S);
+        for (int s = 0; s < S; s++) {
+            lo[s] = base[s] + (unsigned long long)reps->b0[s] * (unsigned long long)bn[s];
+            hi[s] = lo[s] + (unsigned long long)reps->nb[s] * (unsigned long long)bn[s];
+        }
+        if (S > 32) {  // more scales than plan ranges: prepare the hull of this rank's draws
+            lo[0] = *std::min_element(lo.begin(), lo.end());
+            hi[0] = *std::max_element(hi.begin(), hi.end());
+        }
+        CGPU_TRY(mt_prepare(seed, stream_offset, base[S], S > 32 ? 1 : S, lo.data(), hi.data(), &plan, st));
         if (idx_whole_run) {
-            std::vector<unsigned long long> lo(S), hi(S);
-            for (int s = 0; s < S; s++) {
-                lo[s] = base[s] + (unsigned long long)reps->b0[s] * (unsigned long long)bn[s];
-                hi[s] = lo[s] + (unsigned long long)reps->nb[s] * (unsigned long long)bn[s];
-            }
             DrawPlan dp;
             CGPU_TRY(make_draw_plan(S, lo.data(), hi.data(), idx_off.data(), plan.chunk_log2, base[S], &dp));
-            CGPU_TRY(launch_mt_draw(plan.d_states, plan.chunk_log2, dp, (uint32_t)n, ws.d_idx, st));
+            CGPU_TRY(resolve_draw_slots(plan, &dp));
+            CGPU_TRY(launch_mt_draw(plan, dp, (uint32_t)n, ws.d_idx, st));
         }
         pt.end();
     }
@@ -331,7 +409,7 @@ static int scaleboot_core(DevMatrix &m, int S, const int *bn, const int *bb, uns
                     idx_src = ws.d_idx + (idx_off[s] + (unsigned long long)a * bn[s]) * idx_bytes((uint32_t)n);
                 } else {
                     pt.begin(1);
-                    CGPU_TRY(launch_mt_draw_range(plan.d_states, plan.chunk_log2, lo, hi, (uint32_t)n, ws.d_idx, st));
+                    CGPU_TRY(launch_mt_draw_range(plan, lo, hi, (uint32_t)n, ws.d_idx, st));
                     pt.end();
                 }
                 pt.begin(2, aux);
@@ -506,8 +584,12 @@ int cgpu_init(int device) {
         CGPU_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thresh));
     }
     const Gf2Poly *T = mt_jump_table();
-    CGPU_CUDA(dev_alloc(&g.d_jump_table, (size_t)(MT_MAXLOG + 1) * MT_N * sizeof(uint32_t)));
-    CGPU_CUDA(cudaMemcpy(g.d_jump_table, T, (size_t)(MT_MAXLOG + 1) * MT_N * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    {
+        std::vector<uint32_t> pos((size_t)(MT_MAXLOG + 1) * MT_POS_STRIDE, 0u);
+        for (int i = 0; i <= MT_MAXLOG; i++) g.jump_nquads[i] = mt_poly_positions(&T[i], pos.data() + (size_t)i * MT_POS_STRIDE);
+        CGPU_CUDA(dev_alloc(&g.d_jump_table, pos.size() * sizeof(uint32_t)));
+        CGPU_CUDA(cudaMemcpy(g.d_jump_table, pos.data(), pos.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    }
     g.inited = true;
     return CGPU_OK;
 }
@@ -670,7 +752,10 @@ int cgpu_resample_counts(int n, int S, const int *bn, const int *bb, unsigned lo
     MtPlan plan;
     struct PlanGuard {
         MtPlan &p;
-        ~PlanGuard() { dev_free(p.d_states); }
+        ~PlanGuard() {
+            dev_free(p.d_states);
+            dev_free(p.d_pairs);
+        }
     } guard{plan};
     if (rng_mode == CGPU_RNG_MT19937) {
         unsigned long long base = 0, total = 0;
@@ -679,9 +764,9 @@ int cgpu_resample_counts(int n, int S, const int *bn, const int *bb, unsigned lo
             total += (unsigned long long)bb[t] * bn[t];
         }
         CGPU_CUDA(dev_alloc(&ws.d_idx, (size_t)nb * bn[s] * idx_bytes((uint32_t)n)));
-        CGPU_TRY(mt_prepare(seed, stream_offset, total, &plan, st));
         const unsigned long long lo = base + (unsigned long long)b0 * bn[s], hi = lo + (unsigned long long)nb * bn[s];
-        CGPU_TRY(launch_mt_draw_range(plan.d_states, plan.chunk_log2, lo, hi, (uint32_t)n, ws.d_idx, st));
+        CGPU_TRY(mt_prepare(seed, stream_offset, total, 1, &lo, &hi, &plan, st));
+        CGPU_TRY(launch_mt_draw_range(plan, lo, hi, (uint32_t)n, ws.d_idx, st));
         CGPU_TRY(launch_hist_from_idx(ws.d_idx, n, NP, bn[s], nb, ws.d_counts[0], ws.d_err, st));
     } else if (rng_mode == CGPU_RNG_PHILOX) {
         CGPU_TRY(launch_hist_philox((unsigned long long)seed, s, b0, n, NP, bn[s], nb, ws.d_counts[0], ws.d_err, st));
@@ -718,14 +803,17 @@ int cgpu_mt19937_stream(unsigned long seed, unsigned long long skip, unsigned lo
     MtPlan plan;
     struct PlanGuard {
         MtPlan &p;
-        ~PlanGuard() { dev_free(p.d_states); }
+        ~PlanGuard() {
+            dev_free(p.d_states);
+            dev_free(p.d_pairs);
+        }
     } guard{plan};
-    CGPU_TRY(mt_prepare(seed, 0, skip + count, &plan, st));
+    const unsigned long long lo = skip, hi = skip + count;
+    CGPU_TRY(mt_prepare(seed, 0, skip + count, 1, &lo, &hi, &plan, st));
     uint32_t *d_idx = nullptr;
     CGPU_CUDA(dev_alloc(&d_idx, (size_t)count * sizeof(uint32_t)));
-    const unsigned long long lo = skip, hi = skip + count;
     // n = 0 asks for the raw tempered words
-    int rc = launch_mt_draw_range(plan.d_states, plan.chunk_log2, lo, hi, 0u, d_idx, st);
+    int rc = launch_mt_draw_range(plan, lo, hi, 0u, d_idx, st);
     if (rc == CGPU_OK) {
         cudaMemcpyAsync(out, d_idx, (size_t)count * sizeof(uint32_t), cudaMemcpyDeviceToHost, st);
         cudaError_t e = cudaStreamSynchronize(st);

@@ -2,6 +2,7 @@
 // Nothing here is part of the C ABI (include/consel_gpu.h is).
 #pragma once
 #include <cuda_runtime.h>
+#include <vector>
 #include <stdint.h>
 #include <stdio.h>
 
@@ -73,7 +74,8 @@ struct Globals {
     cudaStream_t stream = nullptr;
     cudaStream_t stream2 = nullptr;  // aux stream of the resample/contract software pipeline
     cudaStream_t stream3 = nullptr;  // copy stream: D2H of finished scales behind the compute
-    uint32_t *d_jump_table = nullptr;  // (MT_MAXLOG+1) x 624 u32
+    uint32_t *d_jump_table = nullptr;  // (MT_MAXLOG+1) x MT_POS_STRIDE byte offsets of the set bits of x^(2^i) mod phi
+    int jump_nquads[64] = {0};
     cudaEvent_t ev[8] = {};
     double last_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     // tuning switches (cgpu_set_option); -1 = built-in default
@@ -123,7 +125,9 @@ struct DevReps {  // cgpu_reps
 
 // ---------------------------------------------------------------- kernels (host launchers)
 // mt_kernels.cu
-int launch_mt_jump(const uint32_t *d_src, uint32_t *d_dst, const uint32_t *d_poly, int count,
+constexpr int MT_POS_STRIDE = 9984;   // u32 words reserved per position list (two positions per word, MT_DEG rounded up to 8)
+int mt_poly_positions(const Gf2Poly *g, uint32_t *out_stride);  // returns the number of 8-position groups
+int launch_mt_jump(uint32_t *d_states, const int2 *d_pairs, const uint32_t *d_pos, int nocts, int count,
                    cudaStream_t st);
 // site indices are stored as uint16 when they fit (halves the index traffic); n == 0 asks
 // for raw tempered 32-bit words
@@ -134,14 +138,31 @@ struct DrawPlan {
     unsigned long long lo[32], hi[32], off[32];  // stream ranges to keep -> index-buffer offsets
     unsigned long long first[32];                // chunk intervals to run
     int cum[33];
+    int slot[32];                                // state slot of the first chunk of each interval
     unsigned long long stream_end;               // draws beyond this are never generated
+};
+// chunk start states of one MT19937 stream: only the chunks that cover the ranges a rank
+// keeps (plus the inner nodes of the jump tree that leads to them) are materialised
+struct MtPlan {
+    uint32_t *d_states = nullptr;  // nslots x 624 words
+    int2 *d_pairs = nullptr;       // (src slot, dst slot) of every jump, level by level
+    int chunk_log2 = 0;
+    int nintervals = 0;
+    unsigned long long first[32];
+    int count[32], slot[32];
+    std::vector<uint32_t> h_stage;  // host staging of the seed window and the pair lists
+    long long slot_of(unsigned long long chunk) const {
+        for (int i = 0; i < nintervals; i++)
+            if (chunk >= first[i] && chunk < first[i] + (unsigned long long)count[i]) return slot[i] + (long long)(chunk - first[i]);
+        return -1;
+    }
 };
 int make_draw_plan(int nranges, const unsigned long long *lo, const unsigned long long *hi,
                    const unsigned long long *off, int chunk_log2, unsigned long long stream_end, DrawPlan *plan);
-int launch_mt_draw(const uint32_t *d_states, int chunk_log2, const DrawPlan &plan, uint32_t n, void *d_idx,
-                   cudaStream_t st);
-int launch_mt_draw_range(const uint32_t *d_states, int chunk_log2, unsigned long long lo, unsigned long long hi,
-                         uint32_t n, void *d_idx, cudaStream_t st);
+int resolve_draw_slots(const MtPlan &mt, DrawPlan *plan);
+int launch_mt_draw(const MtPlan &mt, const DrawPlan &plan, uint32_t n, void *d_idx, cudaStream_t st);
+int launch_mt_draw_range(const MtPlan &mt, unsigned long long lo, unsigned long long hi, uint32_t n, void *d_idx,
+                         cudaStream_t st);
 // resample_kernels.cu
 // counts layout: rows == false -> "BJ8" words (8 replicates interleaved per site);
 //                rows == true  -> plain uint8 rows [replicate][NP] (tensor-core operand)

@@ -10,9 +10,10 @@
 // Kernels
 //   mt_jump_kernel   W_{d+J} = g(F) W_d for g = x^J mod phi: regenerate 19937+624
 //                    words from the source window into shared memory, then every
-//                    output word j is the XOR of x_{i+j} over the set bits i of g.
-//                    The bit range of g is sliced over gridDim.y CTAs (atomicXor
-//                    combine) so early rounds of the doubling tree still fill SMs.
+//                    output word j is the XOR of x_{i+j} over the set bits i of g
+//                    (walked as a position list).  The list is sliced over gridDim.y
+//                    CTAs (atomicXor combine) so early rounds of the doubling tree
+//                    still fill the SMs.
 //   mt_draw_kernel   227 lanes per chunk of 2^m draws: block regeneration with the
 //                    three dependent phases of next_state chained in registers (one
 //                    barrier per 624 draws), tempering, site index, coalesced stores.
@@ -59,28 +60,53 @@ __device__ __forceinline__ uint32_t mt_twist_bal(uint32_t hi, uint32_t lo, const
 __device__ __forceinline__ uint32_t mt_temper_bal(uint32_t y, const DrawConsts &) { return mt_temper(y); }
 
 // ------------------------------------------------------------------ jump
-constexpr int JUMP_THREADS = 640;
-constexpr int JUMP_SEQ = MT_DEG + MT_N + 63;  // words of the regenerated sequence kept in smem
+// The polynomial arrives as the list of its set bit positions, two per 32-bit word
+// (pos_a | pos_b << 17), padded to a multiple of 8 with the position of a block of zero
+// words.  A CTA copies its slice of the list into shared memory once (streaming it from
+// L2 inside the loop stalls every warp on the same miss), then the inner loop is: one
+// broadcast 16-byte shared load = 8 positions, per position two address ops, two shared
+// loads (each lane owns output words tid and tid+312) and half a 3-input XOR.  That is
+// shared-memory bandwidth bound (624 x ~10^4 word reads per jump).
+constexpr int JUMP_T = MT_N / 2;                  // 312 lanes, two output words each
+constexpr int JUMP_THREADS = 320;
+constexpr int JUMP_SEQ = MT_DEG + MT_N + 63;      // words of the regenerated sequence kept in smem
+constexpr int JUMP_ZERO = JUMP_SEQ + 1;           // word index of MT_N zero words (list padding target)
+constexpr int JUMP_LIST_OCT = 1536;               // list capacity in smem: 1536 x 8 positions per pass
+constexpr int JUMP_SMEM_WORDS = JUMP_ZERO + MT_N + 3 /* align */ + JUMP_LIST_OCT * 4;
 
 __global__ void __launch_bounds__(JUMP_THREADS, 2)
-mt_jump_kernel(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst,
-               const uint32_t *__restrict__ poly, int words_per_slice) {
-    extern __shared__ uint32_t sm[];
-    uint32_t *x = sm;                 // JUMP_SEQ words
-    uint32_t *g = sm + JUMP_SEQ + 1;  // 624 words of the polynomial
+mt_jump_kernel(uint32_t *states, const int2 *__restrict__ pairs,
+               const uint4 *__restrict__ pos8, int octs_per_slice, int nocts) {
+    extern __shared__ __align__(16) uint32_t x[];
+    uint4 *plist = reinterpret_cast<uint4 *>(x + ((JUMP_ZERO + MT_N + 3) & ~3));
     const int tid = threadIdx.x;
-    const uint32_t *w = src + (size_t)blockIdx.x * MT_N;
-    uint32_t *o = dst + (size_t)blockIdx.x * MT_N;
+    const int2 pr = pairs[blockIdx.x];
+    const uint32_t *w = states + (size_t)pr.x * MT_N;
+    uint32_t *o = states + (size_t)pr.y * MT_N;
 
-    const int w_lo = blockIdx.y * words_per_slice;
-    const int w_hi = min(w_lo + words_per_slice, MT_POLY_W32);
-    if (w_lo >= w_hi) return;
-    const int need = min(w_hi * 32, MT_DEG) + MT_N;  // sequence words x[0..need)
-
-    if (tid < MT_N) {
-        x[tid] = w[tid];
-        g[tid] = poly[tid];
+    const int q_lo = blockIdx.y * octs_per_slice;
+    const int q_hi = min(q_lo + octs_per_slice, nocts);
+    if (q_lo >= q_hi) return;
+    // positions ascend, so the last real entry of the slice bounds the sequence to regenerate
+    int need;
+    {
+        const uint4 last = pos8[q_hi - 1];
+        const uint32_t v[4] = {last.x, last.y, last.z, last.w};
+        uint32_t mx = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const uint32_t a = v[k] & 0x7fffu, b = v[k] >> 17;
+            if (a < (uint32_t)JUMP_ZERO) mx = max(mx, a);
+            if (b < (uint32_t)JUMP_ZERO) mx = max(mx, b);
+        }
+        need = (int)mx + 1 + MT_N;  // sequence words x[0..need)
     }
+    for (int i = tid; i < MT_N; i += JUMP_THREADS) {
+        x[i] = w[i];
+        x[JUMP_ZERO + i] = 0;
+    }
+    const int first_pass = min(q_hi - q_lo, JUMP_LIST_OCT);
+    for (int i = tid; i < first_pass; i += JUMP_THREADS) plist[i] = pos8[q_lo + i];
     __syncthreads();
     // x[t+624] depends on x[t+397]: 227 new words per step are independent
     for (int t0 = 0; t0 + MT_N < need; t0 += MT_N - MT_M) {
@@ -89,38 +115,75 @@ mt_jump_kernel(const uint32_t *__restrict__ src, uint32_t *__restrict__ dst,
             x[t + MT_N] = x[t + MT_M] ^ mt_twist(x[t], x[t + 1]);
         __syncthreads();
     }
-    if (tid < MT_N) {
-        uint32_t r = 0;
-        const uint32_t *xj = x + tid;
-        for (int wi = w_lo; wi < w_hi; wi++) {
-            uint32_t gw = g[wi];
-            if (wi == MT_POLY_W32 - 1) gw &= 0xffffffffu >> (MT_POLY_W32 * 32 - MT_DEG);  // bits >= 19937 are not part of a residue
-            const uint32_t *xb = xj + wi * 32;
-#pragma unroll
-            for (int b = 0; b < 32; b++)
-                if (gw >> b & 1) r ^= xb[b];
+    uint32_t r0 = 0, r1 = 0;
+    const char *xb = reinterpret_cast<const char *>(x + (tid < JUMP_T ? tid : 0));
+    for (int q0 = q_lo; q0 < q_hi; q0 += JUMP_LIST_OCT) {
+        const int cnt = min(q_hi - q0, JUMP_LIST_OCT);
+        if (q0 != q_lo) {  // polynomials denser than the smem list: further passes
+            __syncthreads();
+            for (int i = tid; i < cnt; i += JUMP_THREADS) plist[i] = pos8[q0 + i];
+            __syncthreads();
         }
-        if (gridDim.y == 1) o[tid] = r;
-        else if (r) atomicXor(&o[tid], r);
+#pragma unroll 2
+        for (int q = 0; q < cnt; q++) {
+            const uint4 p = plist[q];
+            const uint32_t v[4] = {p.x, p.y, p.z, p.w};
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const char *pa = xb + ((v[k] & 0x7fffu) << 2);
+                const char *pb = xb + ((v[k] >> 17) << 2);
+                const uint32_t a0 = *reinterpret_cast<const uint32_t *>(pa);
+                const uint32_t a1 = *reinterpret_cast<const uint32_t *>(pa + JUMP_T * 4);
+                const uint32_t b0 = *reinterpret_cast<const uint32_t *>(pb);
+                const uint32_t b1 = *reinterpret_cast<const uint32_t *>(pb + JUMP_T * 4);
+                r0 ^= a0 ^ b0;
+                r1 ^= a1 ^ b1;
+            }
+        }
+    }
+    if (tid < JUMP_T) {
+        if (gridDim.y == 1) {
+            o[tid] = r0;
+            o[tid + JUMP_T] = r1;
+        } else {
+            if (r0) atomicXor(&o[tid], r0);
+            if (r1) atomicXor(&o[tid + JUMP_T], r1);
+        }
     }
 }
 
-int launch_mt_jump(const uint32_t *d_src, uint32_t *d_dst, const uint32_t *d_poly, int count,
+// set bit positions of a residue in the packed layout above; returns the number of 8-position groups
+int mt_poly_positions(const Gf2Poly *g, uint32_t *out) {
+    int np = 0;
+    auto put = [&](uint32_t pos) {
+        if (np & 1) out[np >> 1] |= pos << 17;
+        else out[np >> 1] = pos;
+        np++;
+    };
+    for (int i = 0; i < MT_DEG; i++)
+        if (g->w[i >> 6] >> (i & 63) & 1) put((uint32_t)i);
+    while (np & 7) put((uint32_t)JUMP_ZERO);
+    return np / 8;
+}
+
+// destination slots must be zero on entry (sliced launches combine with atomicXor)
+int launch_mt_jump(uint32_t *d_states, const int2 *d_pairs, const uint32_t *d_pos, int nocts, int count,
                    cudaStream_t st) {
     if (count <= 0) return CGPU_OK;
     static bool attr_done = false;
-    const size_t smem = (size_t)(JUMP_SEQ + 1 + MT_N) * sizeof(uint32_t);
+    const size_t smem = (size_t)JUMP_SMEM_WORDS * sizeof(uint32_t);
     if (!attr_done) {
         CGPU_CUDA(cudaFuncSetAttribute(mt_jump_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_done = true;
     }
-    // slice the polynomial over enough CTAs to cover the SMs when few windows jump
+    if (nocts <= 0) return CGPU_OK;  // the zero polynomial cannot occur (x^J mod phi is never 0)
+    // slice the position list over enough CTAs to cover the SMs when few windows jump
     int sms = G().sm_count > 0 ? G().sm_count : 148;
     int slices = 1;
     while (slices < 16 && count * slices < sms) slices *= 2;
-    int wps = (MT_POLY_W32 + slices - 1) / slices;
-    if (slices > 1) CGPU_CUDA(cudaMemsetAsync(d_dst, 0, (size_t)count * MT_N * sizeof(uint32_t), st));
-    mt_jump_kernel<<<dim3(count, slices), JUMP_THREADS, smem, st>>>(d_src, d_dst, d_poly, wps);
+    int ops = (nocts + slices - 1) / slices;
+    mt_jump_kernel<<<dim3(count, slices), JUMP_THREADS, smem, st>>>(d_states, d_pairs, reinterpret_cast<const uint4 *>(d_pos),
+                                                                    ops, nocts);
     CGPU_LAUNCH_CHECK();
     return CGPU_OK;
 }
@@ -271,7 +334,7 @@ mt_draw_kernel(const uint32_t *__restrict__ states, int chunk_log2, DrawPlan pla
             d_end = d_begin + (1ull << chunk_log2);
             if (d_end > plan.stream_end) d_end = plan.stream_end;
             if (d_end > d_begin) {
-                const uint32_t *w = states + chunk * MT_N + t;
+                const uint32_t *w = states + (size_t)(plan.slot[iv] + (ci - plan.cum[iv])) * MT_N + t;
                 L.r0 = w[0];
                 L.r1 = w[H];
                 bt[0] = L.r0;
@@ -311,9 +374,10 @@ static void mt_draw_launch(const uint32_t *d_states, int chunk_log2, const DrawP
     const int nchunks = plan.cum[plan.nintervals];
     const int force = G().opt_draw_nch;
     const DrawConsts kc = {1u << 31, 1u << 21, 1u << 14};
-    if (force == 3 || (force < 0 && nchunks >= 6 * sms))
+    // measured: 3 chunks per CTA beats 2 and 1 whenever there are enough chunks to give every SM a CTA
+    if (force == 3 || (force < 0 && nchunks >= 3 * sms))
         mt_draw_kernel<PATH, IdxT, 3><<<(nchunks + 2) / 3, DrawCfg<3>::threads, 0, st>>>(d_states, chunk_log2, plan, n, idx, kc);
-    else if (force == 2 || (force < 0 && nchunks >= 3 * sms))
+    else if (force == 2)
         mt_draw_kernel<PATH, IdxT, 2><<<(nchunks + 1) / 2, DrawCfg<2>::threads, 0, st>>>(d_states, chunk_log2, plan, n, idx, kc);
     else
         mt_draw_kernel<PATH, IdxT, 1><<<nchunks, DrawCfg<1>::threads, 0, st>>>(d_states, chunk_log2, plan, n, idx, kc);
@@ -354,9 +418,23 @@ int make_draw_plan(int nranges, const unsigned long long *lo, const unsigned lon
     return CGPU_OK;
 }
 
-int launch_mt_draw(const uint32_t *d_states, int chunk_log2, const DrawPlan &plan, uint32_t n, void *d_idx,
-                   cudaStream_t st) {
+int resolve_draw_slots(const MtPlan &mt, DrawPlan *plan) {
+    for (int i = 0; i < plan->nintervals; i++) {
+        const int cnt = plan->cum[i + 1] - plan->cum[i];
+        const long long a = mt.slot_of(plan->first[i]), b = mt.slot_of(plan->first[i] + (unsigned long long)(cnt - 1));
+        if (a < 0 || b != a + cnt - 1) {
+            set_error(CGPU_EINVAL, "draw plan asks for chunks [%llu, +%d) the jump tree did not prepare", plan->first[i], cnt);
+            return CGPU_EINVAL;
+        }
+        plan->slot[i] = (int)a;
+    }
+    return CGPU_OK;
+}
+
+int launch_mt_draw(const MtPlan &mt, const DrawPlan &plan, uint32_t n, void *d_idx, cudaStream_t st) {
     if (plan.nranges <= 0 || plan.cum[plan.nintervals] <= 0) return CGPU_OK;
+    const uint32_t *d_states = mt.d_states;
+    const int chunk_log2 = mt.chunk_log2;
     uint32_t *i32 = static_cast<uint32_t *>(d_idx);
     uint16_t *i16 = static_cast<uint16_t *>(d_idx);
     if (n == 0) mt_draw_launch<2, uint32_t>(d_states, chunk_log2, plan, n, i32, st);
@@ -368,13 +446,14 @@ int launch_mt_draw(const uint32_t *d_states, int chunk_log2, const DrawPlan &pla
 }
 
 // one contiguous range [lo, hi) stored at idx[0 ..)
-int launch_mt_draw_range(const uint32_t *d_states, int chunk_log2, unsigned long long lo, unsigned long long hi,
-                         uint32_t n, void *d_idx, cudaStream_t st) {
+int launch_mt_draw_range(const MtPlan &mt, unsigned long long lo, unsigned long long hi, uint32_t n, void *d_idx,
+                         cudaStream_t st) {
     if (hi <= lo) return CGPU_OK;
     DrawPlan plan;
     const unsigned long long off = 0;
-    CGPU_TRY(make_draw_plan(1, &lo, &hi, &off, chunk_log2, hi, &plan));
-    return launch_mt_draw(d_states, chunk_log2, plan, n, d_idx, st);
+    CGPU_TRY(make_draw_plan(1, &lo, &hi, &off, mt.chunk_log2, hi, &plan));
+    CGPU_TRY(resolve_draw_slots(mt, &plan));
+    return launch_mt_draw(mt, plan, n, d_idx, st);
 }
 
 }  // namespace cgpu
