@@ -100,9 +100,9 @@ def launch_count() -> int:
 
 
 def last_timing() -> dict:
-    ms = (C.c_double * 8)()
-    _check(load().cgpu_last_timing(ms))
-    keys = ("upload", "rng", "resample", "contract", "download", "total", "gemm_i8", "fx_combine")
+    ms = (C.c_double * 10)()
+    _check(load().cgpu_last_timing_ex(ms, 10))
+    keys = ("upload", "rng", "resample", "contract", "download", "total", "gemm_i8", "fx_combine", "mt_jump", "mt_draw")
     return dict(zip(keys, [float(x) for x in ms]))
 
 

@@ -80,6 +80,7 @@ void PhaseTimer::finish(double *ms) {
         if (sp.ended && cudaEventSynchronize(sp.b) == cudaSuccess && cudaEventElapsedTime(&v, sp.a, sp.b) == cudaSuccess)
             ms[sp.phase] += v;
     }
+    ms[1] += ms[8] + ms[9];
     (void)cudaGetLastError();
 }
 
@@ -359,7 +360,7 @@ static int scaleboot_core(DevMatrix &m, int S, const int *bn, const int *bb, uns
         idx_whole_run = S <= 32 && idx_off[S] > 0 && idx_off[S] * idx_bytes((uint32_t)n) <= idx_budget;
         const size_t idx_elems = idx_whole_run ? (size_t)idx_off[S] : (size_t)batch * max_bn;
         CGPU_CUDA(dev_alloc(&ws.d_idx, idx_elems * idx_bytes((uint32_t)n)));
-        pt.begin(1);
+        pt.begin(8);
         std::vector<unsigned long long> lo(S), hi(S);
         for (int s = 0; s < S; s++) {
             lo[s] = base[s] + (unsigned long long)reps->b0[s] * (unsigned long long)bn[s];
@@ -370,6 +371,8 @@ static int scaleboot_core(DevMatrix &m, int S, const int *bn, const int *bb, uns
             hi[0] = *std::max_element(hi.begin(), hi.end());
         }
         CGPU_TRY(mt_prepare(seed, stream_offset, base[S], S > 32 ? 1 : S, lo.data(), hi.data(), &plan, st));
+        pt.end();
+        pt.begin(9);
         if (idx_whole_run) {
             DrawPlan dp;
             CGPU_TRY(make_draw_plan(S, lo.data(), hi.data(), idx_off.data(), plan.chunk_log2, base[S], &dp));
@@ -408,7 +411,7 @@ static int scaleboot_core(DevMatrix &m, int S, const int *bn, const int *bb, uns
                 if (idx_whole_run) {
                     idx_src = ws.d_idx + (idx_off[s] + (unsigned long long)a * bn[s]) * idx_bytes((uint32_t)n);
                 } else {
-                    pt.begin(1);
+                    pt.begin(9);
                     CGPU_TRY(launch_mt_draw_range(plan, lo, hi, (uint32_t)n, ws.d_idx, st));
                     pt.end();
                 }
@@ -645,6 +648,12 @@ int cgpu_set_option(const char *name, int value) {
 int cgpu_last_timing(double *ms8) {
     if (!ms8) return CGPU_EINVAL;
     memcpy(ms8, G().last_ms, sizeof(double) * 8);
+    return CGPU_OK;
+}
+
+int cgpu_last_timing_ex(double *ms, int n) {
+    if (!ms || n < 0) return CGPU_EINVAL;
+    for (int i = 0; i < n; i++) ms[i] = i < PhaseTimer::NPHASE ? G().last_ms[i] : 0.0;
     return CGPU_OK;
 }
 

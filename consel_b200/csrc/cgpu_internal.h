@@ -77,7 +77,7 @@ struct Globals {
     uint32_t *d_jump_table = nullptr;  // (MT_MAXLOG+1) x MT_POS_STRIDE byte offsets of the set bits of x^(2^i) mod phi
     int jump_nquads[64] = {0};
     cudaEvent_t ev[8] = {};
-    double last_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    double last_ms[12] = {0};
     // tuning switches (cgpu_set_option); -1 = built-in default
     int opt_overlap = -1, opt_hist_algo = -1, opt_contract_algo = -1, opt_i8_oneshot = -1, opt_draw_nch = -1, opt_chunk_log2 = -1;
 };
@@ -190,7 +190,7 @@ struct PhaseTimer {
         cudaEvent_t a, b;
         bool ended;
     };
-    static constexpr int NPHASE = 8;
+    static constexpr int NPHASE = 12;  // 0..7 as cgpu_last_timing documents, 8 mt_jump, 9 mt_draw (their sum is slot 1)
     Span *spans = nullptr;
     int nspans = 0, cap = 0;
     cudaStream_t st;

@@ -155,6 +155,9 @@ int cgpu_mctest(const cgpu_reps *r, int i0, const double *datvec, double varadd,
  * [4] download, [5] whole call (first to last event, includes launch gaps),
  * [6] tensor-core GEMM only, [7] fixed-point recombination only (CGPU_SUM_INT8).   */
 int cgpu_last_timing(double *ms8);
+/* the same slots followed by finer ones: [8] MT19937 jump tree, [9] MT19937 draw kernel
+ * ([1] is their sum); slots past the last defined one read 0                          */
+int cgpu_last_timing_ex(double *ms, int n);
 /* Tuning switches (development / measurement): "overlap" 0|1 (two-stream pipeline of
  * resampling and contraction), "hist_algo" 0|1|2, "contract_algo" -1|0|1|2,
  * "i8_oneshot" 0|1.  Returns CGPU_EINVAL for an unknown name.                       */
