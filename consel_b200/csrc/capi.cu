@@ -637,6 +637,7 @@ int cgpu_set_option(const char *name, int value) {
     else if (!strcmp(name, "contract_algo")) g.opt_contract_algo = value;
     else if (!strcmp(name, "i8_oneshot")) g.opt_i8_oneshot = value;
     else if (!strcmp(name, "draw_nch")) g.opt_draw_nch = value;
+    else if (!strcmp(name, "i8_fuse")) g.opt_i8_fuse = value;
     else if (!strcmp(name, "chunk_log2")) g.opt_chunk_log2 = value;
     else {
         set_error(CGPU_EINVAL, "unknown option %s", name);

@@ -23,6 +23,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <cmath>
 
 #include "cgpu_internal.h"
 
@@ -90,24 +91,50 @@ fx_slice_kernel(const double *__restrict__ L, int K, int n, int NP, int S, int F
     }
 }
 
+// Correctly rounded (nearest-even) conversion of a 128-bit integer: values beyond 63 bits are
+// first shortened to 63 bits with the shifted-out bits OR-ed into the last place (round to
+// odd); 63 >= 53 + 2 bits, so the hardware's single rounding of that integer is the
+// rounding of the full value.  The power of two is applied exactly afterwards.
 __device__ __forceinline__ double i128_to_double_rn(__int128 v) {
     const bool neg = v < 0;
-    unsigned __int128 a = neg ? (unsigned __int128)(-v) : (unsigned __int128)v;
-    if (a == 0) return 0.0;
+    const unsigned __int128 a = neg ? (unsigned __int128)(-v) : (unsigned __int128)v;
     const unsigned long long hi = (unsigned long long)(a >> 64), lo = (unsigned long long)a;
-    const int msb = hi ? 127 - __clzll((long long)hi) : 63 - __clzll((long long)lo);
     double r;
-    if (msb <= 52) {
-        r = (double)lo;
+    if (hi == 0 && (long long)lo >= 0) {
+        r = (double)(long long)lo;
     } else {
-        const int sh = msb - 52;
-        unsigned long long mant = (unsigned long long)(a >> sh);
-        const unsigned __int128 rem = a & ((((unsigned __int128)1) << sh) - 1);
-        const unsigned __int128 half = ((unsigned __int128)1) << (sh - 1);
-        if (rem > half || (rem == half && (mant & 1))) mant++;
-        r = scalbn((double)mant, sh);  // mant <= 2^53: exact
+        const int msb = hi ? 127 - __clzll((long long)hi) : 63;
+        const int sh = msb - 62;  // 1..65
+        unsigned long long q = (unsigned long long)(a >> sh);
+        const unsigned __int128 lost = a & ((((unsigned __int128)1) << sh) - 1);
+        q |= (lost != 0) ? 1ull : 0ull;
+        r = (double)(long long)q * __longlong_as_double((long long)(1023 + sh) << 52);
     }
     return neg ? -r : r;
+}
+
+// 2^-F applied to an exactly representable value: one multiply when 2^-F is a normal double
+struct FxScale {
+    double mul;   // 2^-F, or 0 when the exponent is outside the normal range
+    int F;
+};
+__device__ __forceinline__ double fx_scale(double x, const FxScale &sc) {
+    return sc.mul != 0.0 ? x * sc.mul : scalbn(x, -sc.F);
+}
+
+// exact sum of the S digit sums d[s*stride]: digits are folded four at a time in 64 bits
+// (|group| < 2^56), the groups in 128 bits
+template <int S>
+__device__ __forceinline__ __int128 fx_digits_to_int(const int *d, int stride) {
+    __int128 t = 0;
+#pragma unroll
+    for (int g = (S + 3) / 4 - 1; g >= 0; g--) {
+        long long x = 0;
+#pragma unroll
+        for (int sdig = (S < 4 * g + 4 ? S : 4 * g + 4) - 1; sdig >= 4 * g; sdig--) x = x * 256 + (long long)d[sdig * stride];
+        t = (t << 32) + (__int128)x;
+    }
+    return t;
 }
 
 // P: int32 partial sums [Mpad][ldp] (row k*S+s, column = replicate of the batch)
@@ -124,11 +151,39 @@ fx_combine_kernel(const int *__restrict__ P, int ldp, int K, int S, int F, int n
 }
 
 // ------------------------------------------------------------------ tcgen05 GEMM
+// Parameters of the fused recombination epilogue (rep == nullptr: plain int32 partial sums).
+// Requires 32 % S == 0 so that the digits of a tree never straddle an epilogue warp.
+struct FxEpilogue {
+    double *rep;
+    double r;
+    FxScale sc;
+    int K, S, nb, ldrep, col0;
+};
+
+// one 32 x 32 block of digit sums (rows = (tree, digit), transposed in `tile`, stride 33):
+// lane l finishes replicate column b for each of the 32/S trees of the block
+template <int S>
+__device__ __forceinline__ void fx_finish_block(const int *tile, int lane, int k0, int b, const FxEpilogue &ep) {
+    constexpr int TREES = 32 / S;
+#pragma unroll
+    for (int j = 0; j < TREES; j++) {
+        const int k = k0 + j;
+        if (k < ep.K && b < ep.nb) {
+            const __int128 t = fx_digits_to_int<S>(tile + (j * S) * 33 + lane, 33);
+            const double x = fx_scale(i128_to_double_rn(t), ep.sc);
+            ep.rep[(size_t)k * ep.ldrep + ep.col0 + b] = __ddiv_rn(x, ep.r);
+        }
+    }
+}
+
 constexpr int G8_BM = 128, G8_BN = 256, G8_BK = 128;  // BK in bytes == int8 elements (one 128B swizzle atom)
 constexpr int G8_STAGES = 4;
-constexpr int G8_THREADS = 192;  // warp0 TMA, warp1 MMA (+TMEM alloc), warps 2-5 epilogue
+constexpr int G8_THREADS = 192;  // one-shot kernel: warp0 TMA, warp1 MMA (+TMEM alloc), warps 2-5 epilogue
+constexpr int G8P_EPI_WARPS = 8;  // persistent kernel: two epilogue warps per TMEM lane quarter (columns split)
+constexpr int G8P_THREADS = 64 + 32 * G8P_EPI_WARPS;
 constexpr size_t G8_A_BYTES = (size_t)G8_BM * G8_BK, G8_B_BYTES = (size_t)G8_BN * G8_BK;
-constexpr size_t G8_SMEM = G8_STAGES * (G8_A_BYTES + G8_B_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
+constexpr size_t G8_EPI_BYTES = G8P_EPI_WARPS * 32 * 33 * 4;  // per epilogue warp a 32 x 32 int32 transpose tile (stride 33)
+constexpr size_t G8_SMEM = G8_STAGES * (G8_A_BYTES + G8_B_BYTES) + 1024 /*align*/ + 256 /*barriers*/ + G8_EPI_BYTES;
 
 __device__ __forceinline__ uint32_t s2u(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mb_init(uint64_t *b, uint32_t n) {
@@ -274,9 +329,9 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 // same time share count rows in L2); the shared-memory ring runs across tiles, and two
 // accumulator stages in tensor memory (2 x 256 columns) let the epilogue of tile i drain
 // while the MMAs of tile i+1 are issued.
-__global__ void __launch_bounds__(G8_THREADS, 1)
+__global__ void __launch_bounds__(G8P_THREADS, 1)
 gemm_i8_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int NP,
-                          int *__restrict__ P, int ldp, int m_tiles, int n_tiles) {
+                          int *__restrict__ P, int ldp, int m_tiles, int n_tiles, FxEpilogue ep) {
     extern __shared__ unsigned char g8_raw[];
     unsigned char *base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(g8_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char *sA = base;
@@ -286,6 +341,7 @@ gemm_i8_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
     uint64_t *acc_full = empty + G8_STAGES;  // [2]
     uint64_t *acc_empty = acc_full + 2;      // [2]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+    int *epi = reinterpret_cast<int *>(base + G8_STAGES * (G8_A_BYTES + G8_B_BYTES) + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nkb = NP / G8_BK;
@@ -298,7 +354,7 @@ gemm_i8_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
         }
         for (int a = 0; a < 2; a++) {
             mb_init(&acc_full[a], 1);
-            mb_init(&acc_empty[a], 4);  // one arrival per epilogue warp
+            mb_init(&acc_empty[a], G8P_EPI_WARPS);  // one arrival per epilogue warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -347,7 +403,11 @@ gemm_i8_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
             }
         }
     } else {
+        // epilogue warp: TMEM lane quarter q (= warp % 4, the hardware's access rule), column half h
         const int q = warp & 3;
+        const int h = (warp - 2) >> 2;
+        constexpr int COLS = G8_BN / (G8P_EPI_WARPS / 4);
+        int *tile_s = epi + (warp - 2) * (32 * 33);
         int tcount = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, tcount++) {
             const int acc = tcount & 1;
@@ -356,7 +416,7 @@ gemm_i8_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             int *dst = P + (size_t)(m0 + q * 32 + lane) * ldp + n0;
 #pragma unroll 1
-            for (int c = 0; c < G8_BN; c += 32) {
+            for (int c = h * COLS; c < (h + 1) * COLS; c += 32) {
                 uint32_t v[32];
                 const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * G8_BN + c);
                 asm volatile(
@@ -370,14 +430,34 @@ gemm_i8_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
                     : "r"(taddr)
                     : "memory");
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                uint4 *d4 = reinterpret_cast<uint4 *>(dst + c);
+                if (c + 32 == (h + 1) * COLS) {  // last read of this accumulator by this warp: hand it back
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s2u(&acc_empty[acc])) : "memory");
+                }
+                if (ep.rep == nullptr) {
+                    uint4 *d4 = reinterpret_cast<uint4 *>(dst + c);
 #pragma unroll
-                for (int i = 0; i < 8; i++) d4[i] = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                    for (int i = 0; i < 8; i++) d4[i] = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                    continue;
+                }
+                // Fused recombination (what fx_combine_kernel does from HBM): this lane holds
+                // row (k*S+s) of 32 replicates; transpose through shared memory so that lane l
+                // owns replicate column c+l and walks the S digits of each of the 32/S trees.
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < 32; i++) tile_s[lane * 33 + i] = (int)v[i];
+                __syncwarp();
+                const int b = n0 + c + lane;  // replicate (column of the batch)
+                const int k0 = (m0 + q * 32) / ep.S;
+                switch (ep.S) {
+                    case 1: fx_finish_block<1>(tile_s, lane, k0, b, ep); break;
+                    case 2: fx_finish_block<2>(tile_s, lane, k0, b, ep); break;
+                    case 4: fx_finish_block<4>(tile_s, lane, k0, b, ep); break;
+                    case 8: fx_finish_block<8>(tile_s, lane, k0, b, ep); break;
+                    default: fx_finish_block<16>(tile_s, lane, k0, b, ep); break;
+                }
             }
-            // all of this warp's reads of the accumulator are complete: hand it back
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            __syncwarp();
-            if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s2u(&acc_empty[acc])) : "memory");
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -472,6 +552,9 @@ int launch_contract_i8(const DevMatrix &m, const unsigned char *d_counts_rows, i
     }
     static const bool env_one_shot = getenv("CGPU_I8_ONESHOT") != nullptr;  // development A/B switch
     const bool one_shot = G().opt_i8_oneshot >= 0 ? G().opt_i8_oneshot != 0 : env_one_shot;
+    // the recombination runs in the GEMM epilogue when the digits of a tree stay inside one
+    // 32-row epilogue slab ("i8_fuse" 0 keeps the two-kernel form for measurements)
+    const bool fused = !one_shot && 32 % m.fxS == 0 && G().opt_i8_fuse != 0;
     if (pt) pt->begin(6, st);
     const int m_tiles = (int)(m.fxMpad / G8_BM), n_tiles = nb_pad / G8_BN;
     if (one_shot) {
@@ -480,13 +563,14 @@ int launch_contract_i8(const DevMatrix &m, const unsigned char *d_counts_rows, i
     } else {
         const int sms = G().sm_count > 0 ? G().sm_count : 148;
         const int grid = std::min(sms, m_tiles * n_tiles);
-        gemm_i8_persistent_kernel<<<grid, G8_THREADS, G8_SMEM, st>>>(mapA, mapB, m.NP, d_partial, nb_pad, m_tiles, n_tiles);
+        FxEpilogue ep{fused ? d_rep : nullptr, r, {(m.fxF > -1000 && m.fxF < 1000) ? std::ldexp(1.0, -m.fxF) : 0.0, m.fxF},
+                      m.K, m.fxS, nb, ldrep, col0};
+        gemm_i8_persistent_kernel<<<grid, G8P_THREADS, G8_SMEM, st>>>(mapA, mapB, m.NP, d_partial, nb_pad, m_tiles, n_tiles, ep);
     }
     CGPU_LAUNCH_CHECK();
-    if (pt) {
-        pt->end();
-        pt->begin(7, st);
-    }
+    if (pt) pt->end();
+    if (fused) return CGPU_OK;
+    if (pt) pt->begin(7, st);
     dim3 cgrid((nb + 255) / 256, m.K);
     fx_combine_kernel<<<cgrid, 256, 0, st>>>(d_partial, nb_pad, m.K, m.fxS, m.fxF, nb, r, d_rep, ldrep, col0);
     CGPU_LAUNCH_CHECK();

@@ -77,3 +77,24 @@ def test_int8_wide_dynamic_range(cg, orc):
     with pytest.raises(cg.CgpuError) as e:
         cg.scaleboot_all(Lbad, bn, [9], 1, sum_mode=cg.SUM_INT8)
     assert e.value.code == -5
+
+
+@pytest.mark.parametrize("bits", [3, 11, 27, 40, 59, 75])
+def test_int8_slice_counts_fused_and_two_kernel_forms(cg, orc, bits):
+    """Matrices whose fixed-point span needs S = 1, 2, 4, 6, 8, 10 digits: the GEMM epilogue
+    recombination (S divides 32) and the two-kernel form must both equal the exact sum."""
+    rng = np.random.default_rng(bits)
+    K, n, bb = 37, 300, [70]
+    low = min(bits, 40)  # mantissas of up to 40 bits, spread over the span by a random exponent
+    mag = rng.integers(1, 2 ** low, size=(K, n)).astype(np.float64) * 2.0 ** rng.integers(0, bits - low + 1, size=(K, n))
+    L = np.where(rng.random((K, n)) < 0.2, 1.0, -1.0) * mag * 2.0 ** -20
+    _, bn, rr1 = orc.scale_setup(L, [0.9])
+    counts = cg.resample_counts(n, bn, bb, 5, 0)
+    want = orc.exact_rounded_contract(L, counts, rr1[0])
+    try:
+        for fuse in (1, 0):
+            cg.set_option("i8_fuse", fuse)
+            got = cg.scaleboot_all(L, bn, bb, 5, sum_mode=cg.SUM_INT8)
+            assert np.array_equal(got[0], want), (bits, fuse, np.abs(got[0] - want).max())
+    finally:
+        cg.set_option("i8_fuse", -1)
