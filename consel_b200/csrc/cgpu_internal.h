@@ -79,7 +79,7 @@ struct Globals {
     cudaEvent_t ev[8] = {};
     double last_ms[12] = {0};
     // tuning switches (cgpu_set_option); -1 = built-in default
-    int opt_overlap = -1, opt_hist_algo = -1, opt_contract_algo = -1, opt_i8_oneshot = -1, opt_draw_nch = -1, opt_chunk_log2 = -1, opt_i8_fuse = -1;
+    int opt_overlap = -1, opt_hist_algo = -1, opt_contract_algo = -1, opt_i8_oneshot = -1, opt_draw_nch = -1, opt_chunk_log2 = -1, opt_i8_fuse = -1, opt_draw_fuse = -1;
 };
 Globals &G();
 int ensure_init();
@@ -160,6 +160,10 @@ struct MtPlan {
 int make_draw_plan(int nranges, const unsigned long long *lo, const unsigned long long *hi,
                    const unsigned long long *off, int chunk_log2, unsigned long long stream_end, DrawPlan *plan);
 int resolve_draw_slots(const MtPlan &mt, DrawPlan *plan);
+// fused draws + site histograms (byte rows of NP sites; needs bn >= 1248 and NP small enough for shared memory)
+bool mt_draw_hist_fits(int NP);
+int launch_mt_draw_hist(const MtPlan &mt, const DrawPlan &plan, const unsigned int *bn_per_range,
+                        unsigned char *const *row0_per_range, int NP, uint32_t n, int *d_err, cudaStream_t st);
 int launch_mt_draw(const MtPlan &mt, const DrawPlan &plan, uint32_t n, void *d_idx, cudaStream_t st);
 int launch_mt_draw_range(const MtPlan &mt, unsigned long long lo, unsigned long long hi, uint32_t n, void *d_idx,
                          cudaStream_t st);

@@ -367,6 +367,233 @@ mt_draw_kernel(const uint32_t *__restrict__ states, int chunk_log2, DrawPlan pla
     }
 }
 
+// ------------------------------------------------------------------ draws + site histograms, fused
+// Same block regeneration as mt_draw_kernel, but the site indices never leave the SM: every
+// chunk (227 lanes) keeps two 32-bit histograms of NP sites in shared memory, adds its draws
+// with shared-memory atomics, and when a replicate (bn consecutive draws of one kept range)
+// completes, packs the counters to bytes and writes the NP-byte row of the count matrix.
+// A block of 624 draws holds at most one replicate end because bn >= 2*624 is required, so
+// two histograms (the replicate being finished / the one that has begun) are enough; the row
+// of a finished replicate is flushed after the block's barrier while the next block already
+// counts into the other histogram, and the flushed one is reused two blocks later at the
+// earliest.  Replicates cut by a chunk boundary are flushed with 32-bit atomic adds on the
+// packed byte row (both halves land in the same zero-initialised row).
+struct HistPlan {
+    unsigned int bn[32];        // draws per replicate of range r
+    unsigned char *row0[32];    // count row of the first kept replicate of range r (rows of NP bytes)
+    int NP;
+    int *err;                   // set when a counter exceeds 255
+};
+
+template <int CPC>
+__global__ void __launch_bounds__(DrawCfg<CPC>::threads, DrawCfg<CPC>::ctas)
+mt_draw_hist_kernel(const uint32_t *__restrict__ states, int chunk_log2, DrawPlan plan, HistPlan hp, uint32_t n,
+                    DrawConsts kc) {
+    extern __shared__ __align__(16) uint32_t dh_smem[];
+    constexpr int H = DRAW_H;
+    const int NP = hp.NP;
+    uint32_t *buf_base = dh_smem;                               // [CPC+1][2][MT_N]
+    uint32_t *hist_base = dh_smem + (CPC + 1) * 2 * MT_N;       // [CPC][2][NP]; the padding lanes alias group 0 (they only zero it)
+    const int c = threadIdx.x / H, t = threadIdx.x - c * H;
+    const bool third = t < MT_N - 2 * H;
+    const unsigned int steps = (unsigned int)(((1ull << chunk_log2) + MT_N - 1) / MT_N);
+    uint32_t *bt = buf_base + (size_t)c * 2 * MT_N + t;
+    uint32_t *hist = hist_base + (size_t)(c < CPC ? c : 0) * 2 * NP;
+
+    uint32_t r0 = 0, r1 = 0, r2 = 0;
+    unsigned long long d_begin = 0, d_end = 0;
+    {
+        const int ci = blockIdx.x * CPC + c;
+        if (c < CPC && ci < plan.cum[plan.nintervals]) {
+            int iv = 0;
+            while (ci >= plan.cum[iv + 1]) iv++;
+            const unsigned long long chunk = plan.first[iv] + (unsigned long long)(ci - plan.cum[iv]);
+            d_begin = chunk << chunk_log2;
+            d_end = d_begin + (1ull << chunk_log2);
+            if (d_end > plan.stream_end) d_end = plan.stream_end;
+            if (d_end > d_begin) {
+                const uint32_t *w = states + (size_t)(plan.slot[iv] + (ci - plan.cum[iv])) * MT_N + t;
+                r0 = w[0];
+                r1 = w[H];
+                bt[0] = r0;
+                bt[H] = r1;
+                if (third) {
+                    r2 = w[2 * H];
+                    bt[2 * H] = r2;
+                }
+            } else {
+                d_end = d_begin;
+            }
+        }
+    }
+    for (int i = t; i < 2 * NP; i += H) hist[i] = 0;
+
+    // replicate cursor of this chunk (uniform over the chunk's lanes)
+    int rcur = 0;                        // range the cursor is in (or the next one ahead of it)
+    unsigned long long seg_lo = 0;       // first kept draw of the current replicate inside this chunk
+    unsigned long long rep_end = 0;      // stream position where the current replicate ends
+    unsigned char *row = nullptr;        // its count row
+    bool partial = false;                // the replicate began before this chunk: flush with atomics
+    bool have = false;                   // a current replicate exists
+    int hcur = 0;
+    auto seek = [&](unsigned long long pos) {  // position the cursor on the replicate containing / following pos
+        while (rcur < plan.nranges && pos >= plan.hi[rcur]) rcur++;
+        have = rcur < plan.nranges && plan.lo[rcur] < d_end;
+        if (!have) return;
+        const unsigned long long lo = plan.lo[rcur];
+        const unsigned long long p0 = pos > lo ? pos : lo;
+        const unsigned long long rep = (p0 - lo) / hp.bn[rcur];
+        const unsigned long long rstart = lo + rep * hp.bn[rcur];
+        seg_lo = p0;
+        rep_end = rstart + hp.bn[rcur];
+        row = hp.row0[rcur] + rep * (unsigned long long)NP;
+        partial = rstart < p0;
+    };
+    seek(d_begin);
+    // pack one histogram into its byte row and clear it
+    auto flush = [&](uint32_t *h, unsigned char *dst, bool atomic) {
+        uint32_t *dst32 = reinterpret_cast<uint32_t *>(dst);
+        uint4 *h4 = reinterpret_cast<uint4 *>(h);
+        bool over = false;
+        for (int w = t; w < NP / 4; w += H) {
+            const uint4 v = h4[w];
+            h4[w] = make_uint4(0, 0, 0, 0);
+            over |= (v.x | v.y | v.z | v.w) > 255u;
+            const uint32_t packed = (v.x & 255u) | (v.y & 255u) << 8 | (v.z & 255u) << 16 | (v.w & 255u) << 24;
+            if (atomic) {
+                if (packed) atomicAdd(&dst32[w], packed);
+            } else {
+                dst32[w] = packed;
+            }
+        }
+        if (over) atomicExch(hp.err, 1);
+    };
+    __syncthreads();
+
+    unsigned int fast_until = 0;  // blocks below this index are uniform: all inside the current replicate, or all skipped
+    bool counting = false;
+    auto plan_fast = [&](unsigned int it_next) {
+        fast_until = it_next;
+        counting = false;
+        if (!have) {
+            fast_until = ~0u;  // nothing left to count in this chunk
+            return;
+        }
+        const unsigned long long b0 = d_begin + (unsigned long long)it_next * MT_N;
+        const unsigned long long lim = rep_end < d_end ? rep_end : d_end;
+        // all differences are below the chunk length (< 2^31): 32-bit divisions by a constant
+        if (b0 >= seg_lo) {
+            if (lim > b0) {  // full blocks inside [seg_lo, min(rep_end, d_end))
+                fast_until = it_next + (unsigned int)(lim - b0) / (unsigned int)MT_N;
+                counting = true;
+            }
+        } else {  // full blocks before the first kept draw
+            fast_until = it_next + (unsigned int)(seg_lo - b0) / (unsigned int)MT_N;
+        }
+    };
+    plan_fast(0);
+
+    // regeneration of the next block (registers r0..r2 become its words t, t+227, t+454)
+    auto regen = [&](const uint32_t *o, uint32_t *nw) {
+        r0 = o[MT_M] ^ mt_twist_bal(r0, o[1], kc);
+        r1 = r0 ^ mt_twist_bal(r1, o[H + 1], kc);
+        nw[0] = r0;
+        nw[H] = r1;
+        if (third) {
+            uint32_t nxt;
+            if (t == MT_N - 2 * H - 1) nxt = o[MT_M - t] ^ mt_twist_bal(o[-t], o[1 - t], kc);  // new[0]
+            else nxt = o[2 * H + 1];
+            r2 = r1 ^ mt_twist_bal(r2, nxt, kc);
+            nw[2 * H] = r2;
+        }
+    };
+    // histogram updates of block `it`, whose words are still in r0..r2.  They are issued at the
+    // START of the following step, so the shared-memory atomics drain while the next block is
+    // regenerated instead of in front of the barrier.  Returns true when the current replicate
+    // ends inside the block (flush after the next barrier).
+    auto count = [&](unsigned int it) {
+        if (it < fast_until) {
+            if (counting) {
+                uint32_t *h = hist + hcur * NP;
+                atomicAdd(&h[__umulhi(mt_temper(r0), n)], 1u);
+                atomicAdd(&h[__umulhi(mt_temper(r1), n)], 1u);
+                if (third) atomicAdd(&h[__umulhi(mt_temper(r2), n)], 1u);
+            }
+            return false;
+        }
+        // boundary block: draws of the finishing replicate go to hist[hcur], draws of the one that
+        // begins (same range, or the next range after a gap) to hist[hcur^1].  Offsets are
+        // relative to the block start (32-bit).
+        const unsigned long long d0 = d_begin + (unsigned long long)it * MT_N;
+        if (d0 >= d_end) return false;
+        const int len = d_end - d0 >= (unsigned long long)MT_N ? MT_N : (int)(d_end - d0);
+        const int a_lo = seg_lo > d0 ? (seg_lo - d0 < (unsigned long long)len ? (int)(seg_lo - d0) : len) : 0;
+        const int a_hi = rep_end - d0 < (unsigned long long)len ? (int)(rep_end - d0) : len;
+        int b_lo = len;  // bn >= 2*624: the replicate that begins here cannot end inside this block
+        if (a_hi < len) {
+            if (rep_end < plan.hi[rcur]) b_lo = a_hi;
+            else if (rcur + 1 < plan.nranges && plan.lo[rcur + 1] - d0 < (unsigned long long)len) b_lo = (int)(plan.lo[rcur + 1] - d0);
+        }
+        uint32_t *ha = hist + hcur * NP, *hb = hist + (hcur ^ 1) * NP;
+        const int k0 = t, k1 = t + H, k2 = t + 2 * H;
+        if (k0 >= a_lo && k0 < a_hi) atomicAdd(&ha[__umulhi(mt_temper(r0), n)], 1u);
+        else if (k0 >= b_lo && k0 < len) atomicAdd(&hb[__umulhi(mt_temper(r0), n)], 1u);
+        if (k1 >= a_lo && k1 < a_hi) atomicAdd(&ha[__umulhi(mt_temper(r1), n)], 1u);
+        else if (k1 >= b_lo && k1 < len) atomicAdd(&hb[__umulhi(mt_temper(r1), n)], 1u);
+        if (third) {
+            if (k2 >= a_lo && k2 < a_hi) atomicAdd(&ha[__umulhi(mt_temper(r2), n)], 1u);
+            else if (k2 >= b_lo && k2 < len) atomicAdd(&hb[__umulhi(mt_temper(r2), n)], 1u);
+        }
+        return rep_end <= d0 + (unsigned long long)len;  // the current replicate is complete: flush after the barrier
+    };
+    auto after = [&](bool done, unsigned int it) {  // bookkeeping once block `it` has been counted and a barrier passed
+        if (it < fast_until) return;
+        if (done) {
+            flush(hist + hcur * NP, row, partial);
+            hcur ^= 1;
+            partial = false;
+            if (rep_end < plan.hi[rcur]) {  // next replicate of the same range
+                seg_lo = rep_end;
+                rep_end += hp.bn[rcur];
+                row += NP;
+                have = seg_lo < d_end;
+            } else {  // ranges are whole replicates: the next range starts a replicate
+                rcur++;
+                have = rcur < plan.nranges && plan.lo[rcur] < d_end;
+                if (have) {
+                    seg_lo = plan.lo[rcur];
+                    rep_end = seg_lo + hp.bn[rcur];
+                    row = hp.row0[rcur];
+                }
+            }
+        }
+        plan_fast(it + 1);
+    };
+
+    // step `it`: count block it-1, regenerate block it, barrier, bookkeeping for block it-1
+    regen(bt, bt + MT_N);
+    __syncthreads();
+    for (unsigned int it = 1; it < steps; it += 2) {
+        bool done = count(it - 1);
+        regen(bt + MT_N, bt);
+        __syncthreads();
+        after(done, it - 1);
+        if (it + 1 < steps) {
+            done = count(it);
+            regen(bt, bt + MT_N);
+            __syncthreads();
+            after(done, it);
+        }
+    }
+    {
+        const bool done = count(steps - 1);
+        __syncthreads();
+        after(done, steps - 1);
+    }
+    // the replicate left open at the end of the chunk continues in the next chunk
+    if (have && seg_lo < d_end) flush(hist + hcur * NP, row, true);
+}
+
 template <int PATH, typename IdxT>
 static void mt_draw_launch(const uint32_t *d_states, int chunk_log2, const DrawPlan &plan, uint32_t n, IdxT *idx,
                            cudaStream_t st) {
@@ -454,6 +681,49 @@ int launch_mt_draw_range(const MtPlan &mt, unsigned long long lo, unsigned long 
     CGPU_TRY(make_draw_plan(1, &lo, &hi, &off, mt.chunk_log2, hi, &plan));
     CGPU_TRY(resolve_draw_slots(mt, &plan));
     return launch_mt_draw(mt, plan, n, d_idx, st);
+}
+
+// fused draws + histograms: counts rows of NP bytes, one zero-initialised matrix per range
+size_t mt_draw_hist_smem(int NP, int cpc) { return ((size_t)(cpc + 1) * 2 * MT_N + (size_t)cpc * 2 * NP) * sizeof(uint32_t); }
+
+bool mt_draw_hist_fits(int NP) { return mt_draw_hist_smem(NP, 3) <= (size_t)110 * 1024; }
+
+int launch_mt_draw_hist(const MtPlan &mt, const DrawPlan &plan, const unsigned int *bn, unsigned char *const *row0, int NP,
+                        uint32_t n, int *d_err, cudaStream_t st) {
+    const int nchunks = plan.cum[plan.nintervals];
+    if (plan.nranges <= 0 || nchunks <= 0) return CGPU_OK;
+    HistPlan hp;
+    for (int r = 0; r < plan.nranges; r++) {
+        if (bn[r] < 2u * MT_N) {
+            set_error(CGPU_EINVAL, "fused draw+histogram needs at least %d draws per replicate (got %u)", 2 * MT_N, bn[r]);
+            return CGPU_EINVAL;
+        }
+        hp.bn[r] = bn[r];
+        hp.row0[r] = row0[r];
+    }
+    hp.NP = NP;
+    hp.err = d_err;
+    const DrawConsts kc = {1u << 31, 1u << 21, 1u << 14};
+    const int sms = G().sm_count > 0 ? G().sm_count : 148;
+    if (nchunks >= 3 * sms) {
+        const size_t smem = mt_draw_hist_smem(NP, 3);
+        static bool attr3 = false;
+        if (!attr3) {
+            CGPU_CUDA(cudaFuncSetAttribute(mt_draw_hist_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+            attr3 = true;
+        }
+        mt_draw_hist_kernel<3><<<(nchunks + 2) / 3, DrawCfg<3>::threads, smem, st>>>(mt.d_states, mt.chunk_log2, plan, hp, n, kc);
+    } else {
+        const size_t smem = mt_draw_hist_smem(NP, 1);
+        static bool attr1 = false;
+        if (!attr1) {
+            CGPU_CUDA(cudaFuncSetAttribute(mt_draw_hist_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+            attr1 = true;
+        }
+        mt_draw_hist_kernel<1><<<nchunks, DrawCfg<1>::threads, smem, st>>>(mt.d_states, mt.chunk_log2, plan, hp, n, kc);
+    }
+    CGPU_LAUNCH_CHECK();
+    return CGPU_OK;
 }
 
 }  // namespace cgpu

@@ -98,3 +98,53 @@ def test_int8_slice_counts_fused_and_two_kernel_forms(cg, orc, bits):
             assert np.array_equal(got[0], want), (bits, fuse, np.abs(got[0] - want).max())
     finally:
         cg.set_option("i8_fuse", -1)
+
+
+@pytest.mark.parametrize("n,rr,bb", [(2600, [0.5, 1.0, 1.4], [300, 77, 130]), (3414, [0.5, 0.9, 1.4], [513, 256, 40]),
+                                     (4500, [0.7], [1000])])
+def test_fused_draw_histogram_path(cg, orc, n, rr, bb):
+    """n' >= 1248 draws per replicate and n <= 4608 sites: draws and histograms run in one
+    kernel (no index stream).  Same counts, hence bit-equal sums, as the two-kernel path,
+    for the whole run and for every shard of it."""
+    K = 21
+    L = synth(K, n, seed=n)
+    _, bn, rr1 = orc.scale_setup(L, rr)
+    try:
+        cg.set_option("draw_fuse", 0)
+        plain = cg.scaleboot_all(L, bn, bb, 23, sum_mode=cg.SUM_INT8)
+        cg.set_option("draw_fuse", 1)
+        fused = cg.scaleboot_all(L, bn, bb, 23, sum_mode=cg.SUM_INT8)
+        for s in range(len(bb)):
+            counts = cg.resample_counts(n, bn, bb, 23, s)
+            want = orc.exact_rounded_contract(L, counts, rr1[s])
+            assert np.array_equal(plain[s], want)
+            assert np.array_equal(fused[s], want), (s, np.abs(fused[s] - want).max())
+        for world in (2, 3):
+            for rank in range(world):
+                cg.set_shard(rank, world)
+                loc = cg.scaleboot_all(L, bn, bb, 23, sum_mode=cg.SUM_INT8)
+                for s in range(len(bb)):
+                    b0, b1 = cg.shard_range(bb[s])
+                    assert np.array_equal(loc[s], fused[s][:, b0:b1]), (world, rank, s)
+    finally:
+        cg.set_shard(0, 1)
+        cg.set_option("draw_fuse", -1)
+
+
+def test_fused_draw_histogram_small_chunks(cg, orc):
+    """chunks shorter than a replicate: every histogram row is assembled from several chunks"""
+    n, K, bb = 3000, 9, [60, 33]
+    L = synth(K, n, seed=5)
+    _, bn, rr1 = orc.scale_setup(L, [0.8, 1.2])
+    try:
+        cg.set_option("draw_fuse", 0)
+        plain = cg.scaleboot_all(L, bn, bb, 99, sum_mode=cg.SUM_INT8)
+        cg.set_option("draw_fuse", 1)
+        for log2 in (11, 12, 14, 17):
+            cg.set_option("chunk_log2", log2)
+            fused = cg.scaleboot_all(L, bn, bb, 99, sum_mode=cg.SUM_INT8)
+            for s in range(len(bb)):
+                assert np.array_equal(fused[s], plain[s]), (log2, s)
+    finally:
+        cg.set_option("chunk_log2", -1)
+        cg.set_option("draw_fuse", -1)
