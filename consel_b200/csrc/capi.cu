@@ -163,9 +163,8 @@ static int pick_chunk_log2(unsigned long long needed_draws, unsigned long long s
 // binary jump tree walked from the top bit down: at bit r every live node a (a multiple of
 // 2^(r+1)) hands its state to a + 2^r through the jump x^(2^(m+r)) if any wanted chunk lies
 // in [a + 2^r, a + 2^(r+1)).  One launch per level; the jumps of a level are independent.
-static int mt_prepare(unsigned long seed, unsigned long long stream_offset, unsigned long long stream_end, int nranges,
-                      const unsigned long long *lo, const unsigned long long *hi, MtPlan *plan, cudaStream_t st) {
-    Globals &g = G();
+static int mt_plan(unsigned long seed, unsigned long long stream_offset, unsigned long long stream_end, int nranges,
+                   const unsigned long long *lo, const unsigned long long *hi, MtPlan *plan) {
     unsigned long long needed = 0;
     for (int r = 0; r < nranges; r++) needed += hi[r] > lo[r] ? hi[r] - lo[r] : 0;
     plan->chunk_log2 = pick_chunk_log2(needed, stream_end, nranges);
@@ -236,22 +235,42 @@ static int mt_prepare(unsigned long seed, unsigned long long stream_offset, unsi
         for (int r = top - 1; r >= 0; r--)
             for (auto &pr : levels[r]) *hp++ = pr;
     }
+    plan->nslots = nslots;
+    plan->root = root;
+    plan->npairs = npairs;
+    plan->level_cnt.assign(top, 0);
+    for (int r = 0; r < top; r++) plan->level_cnt[r] = (int)levels[r].size();
     CGPU_CUDA(dev_alloc(&plan->d_states, (size_t)nslots * MT_N * sizeof(uint32_t)));
-    CGPU_CUDA(cudaMemsetAsync(plan->d_states, 0, (size_t)nslots * MT_N * sizeof(uint32_t), st));
-    CGPU_CUDA(cudaMemcpyAsync(plan->d_states + (size_t)root * MT_N, w0, MT_N * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-    if (npairs) {
-        CGPU_CUDA(dev_alloc(&plan->d_pairs, npairs * sizeof(int2)));
-        CGPU_CUDA(cudaMemcpyAsync(plan->d_pairs, plan->h_stage.data() + MT_N, npairs * sizeof(int2), cudaMemcpyHostToDevice, st));
-    }
+    if (npairs) CGPU_CUDA(dev_alloc(&plan->d_pairs, npairs * sizeof(int2)));
+    return CGPU_OK;
+}
+
+// second half of the preparation: copies and the jump launches, on any stream that is ordered
+// after the allocations above (made on the library stream)
+static int mt_launch(MtPlan *plan, cudaStream_t st) {
+    Globals &g = G();
+    if (plan->nslots == 0) return CGPU_OK;
+    const int m = plan->chunk_log2;
+    CGPU_CUDA(cudaMemsetAsync(plan->d_states, 0, (size_t)plan->nslots * MT_N * sizeof(uint32_t), st));
+    CGPU_CUDA(cudaMemcpyAsync(plan->d_states + (size_t)plan->root * MT_N, plan->h_stage.data(), MT_N * sizeof(uint32_t),
+                              cudaMemcpyHostToDevice, st));
+    if (plan->npairs)
+        CGPU_CUDA(cudaMemcpyAsync(plan->d_pairs, plan->h_stage.data() + MT_N, plan->npairs * sizeof(int2), cudaMemcpyHostToDevice, st));
     size_t done = 0;
-    for (int r = top - 1; r >= 0; r--) {
-        const int cnt = (int)levels[r].size();
+    for (int r = (int)plan->level_cnt.size() - 1; r >= 0; r--) {
+        const int cnt = plan->level_cnt[r];
         if (!cnt) continue;
         CGPU_TRY(launch_mt_jump(plan->d_states, plan->d_pairs + done, g.d_jump_table + (size_t)(m + r) * MT_POS_STRIDE,
                                 g.jump_nquads[m + r], cnt, st));
         done += cnt;
     }
     return CGPU_OK;
+}
+
+static int mt_prepare(unsigned long seed, unsigned long long stream_offset, unsigned long long stream_end, int nranges,
+                      const unsigned long long *lo, const unsigned long long *hi, MtPlan *plan, cudaStream_t st) {
+    CGPU_TRY(mt_plan(seed, stream_offset, stream_end, nranges, lo, hi, plan));
+    return mt_launch(plan, st);
 }
 
 struct Workspace {
@@ -341,6 +360,20 @@ static int scaleboot_core(DevMatrix &m, int S, const int *bn, const int *bb, uns
             dev_free(p.d_pairs);
         }
     } guard{plan};
+    // staged index production (see below): one jump tree per stage
+    MtPlan plans[3];
+    PlanGuard sguard0{plans[0]}, sguard1{plans[1]}, sguard2{plans[2]};
+    int nstages = 1, stage_first[3] = {0, 0, 0};
+    cudaEvent_t stage_done[3] = {nullptr, nullptr, nullptr};
+    struct EventGuard {
+        cudaEvent_t *e;
+        ~EventGuard() {
+            cudaStreamSynchronize(G().stream2);  // the aux stream may still use the plans on an error path
+            for (int i = 0; i < 3; i++)
+                if (e[i]) cudaEventDestroy(e[i]);
+        }
+    } eguard{stage_done};
+    for (int i = 1; i < 3; i++) CGPU_CUDA(cudaEventCreateWithFlags(&stage_done[i], cudaEventDisableTiming));
     std::vector<unsigned long long> base(S + 1, 0);
     for (int s = 0; s < S; s++) base[s + 1] = base[s] + (unsigned long long)bb[s] * (unsigned long long)bn[s];
     // When this rank's share of the index stream fits the workspace, ONE draw launch covers
@@ -386,12 +419,47 @@ static int scaleboot_core(DevMatrix &m, int S, const int *bn, const int *bb, uns
         idx_whole_run = !fuse_hist && S <= 32 && idx_off[S] > 0 && idx_off[S] * idx_bytes((uint32_t)n) <= idx_budget;
         const size_t idx_elems = fuse_hist ? 1 : idx_whole_run ? (size_t)idx_off[S] : (size_t)batch * max_bn;
         CGPU_CUDA(dev_alloc(&ws.d_idx, idx_elems * idx_bytes((uint32_t)n)));
-        pt.begin(8);
         std::vector<unsigned long long> lo(S), hi(S);
         for (int s = 0; s < S; s++) {
             lo[s] = base[s] + (unsigned long long)reps->b0[s] * (unsigned long long)bn[s];
             hi[s] = lo[s] + (unsigned long long)reps->nb[s] * (unsigned long long)bn[s];
         }
+        // Host-output calls in int8 mode are bound by the device-to-host copy of the replicate
+        // blocks (PCIe), which can only start when the first scale is finished.  The index
+        // stream is therefore produced in three stages of growing size — the first scale
+        // alone with short chunks on the main stream, the rest on the aux stream behind it —
+        // so the copy engine starts early and never waits for the bulk of the draws.
+        if (idx_whole_run && i8 && host_out && S >= 4 && S <= 32 && G().opt_stage != 0 &&
+            (G().opt_stage == 1 || idx_off[S] >= (1ull << 28))) {
+            int g1 = 1, g2 = 2;
+            while (g1 < S - 2 && (double)idx_off[g1] < 0.04 * (double)idx_off[S]) g1++;
+            g2 = g1 + 1;
+            while (g2 < S - 1 && (double)idx_off[g2] < 0.16 * (double)idx_off[S]) g2++;
+            const int cut[4] = {0, g1, g2, S};
+            stage_first[0] = 0;
+            stage_first[1] = g1;
+            stage_first[2] = g2;
+            nstages = 3;
+            for (int g = 0; g < 3; g++)
+                CGPU_TRY(mt_plan(seed, stream_offset, base[S], cut[g + 1] - cut[g], lo.data() + cut[g], hi.data() + cut[g], &plans[g]));
+            CGPU_CUDA(cudaEventRecord(ws.idx_ready, st));  // allocations and memsets are ordered on st
+            CGPU_CUDA(cudaStreamWaitEvent(G().stream2, ws.idx_ready, 0));
+            for (int g = 0; g < 3; g++) {
+                cudaStream_t sg = g == 0 ? st : G().stream2;
+                pt.begin(8, sg);
+                CGPU_TRY(mt_launch(&plans[g], sg));
+                pt.end();
+                pt.begin(9, sg);
+                DrawPlan dp;
+                CGPU_TRY(make_draw_plan(cut[g + 1] - cut[g], lo.data() + cut[g], hi.data() + cut[g], idx_off.data() + cut[g],
+                                        plans[g].chunk_log2, base[S], &dp));
+                CGPU_TRY(resolve_draw_slots(plans[g], &dp));
+                CGPU_TRY(launch_mt_draw(plans[g], dp, (uint32_t)n, ws.d_idx, sg));
+                pt.end();
+                if (g > 0) CGPU_CUDA(cudaEventRecord(stage_done[g], sg));
+            }
+        } else {
+        pt.begin(8);
         if (S > 32) {  // more scales than plan ranges: prepare the hull of this rank's draws
             lo[0] = *std::min_element(lo.begin(), lo.end());
             hi[0] = *std::max_element(hi.begin(), hi.end());
@@ -425,6 +493,7 @@ static int scaleboot_core(DevMatrix &m, int S, const int *bn, const int *bb, uns
             CGPU_TRY(launch_mt_draw(plan, dp, (uint32_t)n, ws.d_idx, st));
         }
         pt.end();
+        }
     }
 
     // Two-stream software pipeline over (scale, batch) items: the histogram of item i+1
@@ -444,6 +513,8 @@ static int scaleboot_core(DevMatrix &m, int S, const int *bn, const int *bb, uns
     int item = 0;
     for (int s = 0; s < S; s++) {
         const double r = (double)bn[s] / (double)n;  // src/makermt.c:48
+        for (int g = 1; g < nstages; g++)
+            if (s == stage_first[g]) CGPU_CUDA(cudaStreamWaitEvent(st, stage_done[g], 0));
         for (int a = 0; a < reps->nb[s]; a += batch, item++) {
             const int nbat = std::min(batch, reps->nb[s] - a);
             const int bA = reps->b0[s] + a;  // global replicate index of the batch
@@ -622,8 +693,14 @@ int cgpu_init(int device) {
     }
     g.device = device;
     g.sm_count = prop.multiProcessorCount;
-    CGPU_CUDA(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
-    CGPU_CUDA(cudaStreamCreateWithFlags(&g.stream2, cudaStreamNonBlocking));
+    {
+        // the main stream outranks the aux stream: when both have blocks pending (staged index
+        // production), the scale that is next to be copied out is served first
+        int pri_lo = 0, pri_hi = 0;
+        CGPU_CUDA(cudaDeviceGetStreamPriorityRange(&pri_lo, &pri_hi));
+        CGPU_CUDA(cudaStreamCreateWithPriority(&g.stream, cudaStreamNonBlocking, pri_hi));
+        CGPU_CUDA(cudaStreamCreateWithPriority(&g.stream2, cudaStreamNonBlocking, pri_lo));
+    }
     CGPU_CUDA(cudaStreamCreateWithFlags(&g.stream3, cudaStreamNonBlocking));
     {
         // keep freed blocks in the default stream-ordered pool: the per-call workspaces
@@ -686,6 +763,7 @@ int cgpu_set_option(const char *name, int value) {
     else if (!strcmp(name, "draw_nch")) g.opt_draw_nch = value;
     else if (!strcmp(name, "i8_fuse")) g.opt_i8_fuse = value;
     else if (!strcmp(name, "draw_fuse")) g.opt_draw_fuse = value;
+    else if (!strcmp(name, "stage")) g.opt_stage = value;
     else if (!strcmp(name, "chunk_log2")) g.opt_chunk_log2 = value;
     else {
         set_error(CGPU_EINVAL, "unknown option %s", name);

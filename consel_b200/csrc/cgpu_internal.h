@@ -79,7 +79,7 @@ struct Globals {
     cudaEvent_t ev[8] = {};
     double last_ms[12] = {0};
     // tuning switches (cgpu_set_option); -1 = built-in default
-    int opt_overlap = -1, opt_hist_algo = -1, opt_contract_algo = -1, opt_i8_oneshot = -1, opt_draw_nch = -1, opt_chunk_log2 = -1, opt_i8_fuse = -1, opt_draw_fuse = -1;
+    int opt_overlap = -1, opt_hist_algo = -1, opt_contract_algo = -1, opt_i8_oneshot = -1, opt_draw_nch = -1, opt_chunk_log2 = -1, opt_i8_fuse = -1, opt_draw_fuse = -1, opt_stage = -1;
 };
 Globals &G();
 int ensure_init();
@@ -151,6 +151,9 @@ struct MtPlan {
     unsigned long long first[32];
     int count[32], slot[32];
     std::vector<uint32_t> h_stage;  // host staging of the seed window and the pair lists
+    std::vector<int> level_cnt;     // jumps per tree level (index = bit of the chunk number)
+    int nslots = 0, root = 0;
+    size_t npairs = 0;
     long long slot_of(unsigned long long chunk) const {
         for (int i = 0; i < nintervals; i++)
             if (chunk >= first[i] && chunk < first[i] + (unsigned long long)count[i]) return slot[i] + (long long)(chunk - first[i]);

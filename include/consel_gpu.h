@@ -161,7 +161,8 @@ int cgpu_last_timing_ex(double *ms, int n);
 /* Tuning switches (development / measurement): "overlap" 0|1 (two-stream pipeline of
  * resampling and contraction), "hist_algo" 0|1|2, "contract_algo" -1|0|1|2,
  * "i8_oneshot" 0|1, "i8_fuse" 0|1 (recombination in the GEMM epilogue), "draw_nch" 1|2|3,
- * "draw_fuse" 0|1 (draws + histograms in one kernel, int8 mode, opt-in),
+ * "draw_fuse" 0|1 (draws + histograms in one kernel, int8 mode, opt-in), "stage" 0|1 (staged
+ * index production of host-output int8 calls: 0 off, 1 always, default by size),
  * "chunk_log2" 10..30.  Returns CGPU_EINVAL for an unknown name.                      */
 int cgpu_set_option(const char *name, int value);
 /* number of kernels launched by this library since cgpu_init (bench `gpu_launches`) */

@@ -148,3 +148,29 @@ def test_fused_draw_histogram_small_chunks(cg, orc):
     finally:
         cg.set_option("chunk_log2", -1)
         cg.set_option("draw_fuse", -1)
+
+
+def test_staged_index_production_same_result(cg, orc):
+    """cgpu_scaleboot_all in int8 mode produces the index stream in three stages on two
+    streams for large runs ("stage" 1 forces it at any size): identical blocks."""
+    K, n = 11, 900
+    L = synth(K, n, seed=3)
+    rr = [0.5, 0.6, 0.7, 0.8, 0.9, 1.0, 1.1, 1.2, 1.3, 1.4]
+    bb = [37, 50, 64, 21, 80, 33, 10, 90, 5, 41]
+    _, bn, _ = orc.scale_setup(L, rr)
+    try:
+        cg.set_option("stage", 0)
+        plain = cg.scaleboot_all(L, bn, bb, 77, sum_mode=cg.SUM_INT8)
+        cg.set_option("stage", 1)
+        staged = cg.scaleboot_all(L, bn, bb, 77, sum_mode=cg.SUM_INT8)
+        for s in range(len(bb)):
+            assert np.array_equal(plain[s], staged[s]), s
+        for rank in range(2):
+            cg.set_shard(rank, 2)
+            loc = cg.scaleboot_all(L, bn, bb, 77, sum_mode=cg.SUM_INT8)
+            for s in range(len(bb)):
+                b0, b1 = cg.shard_range(bb[s])
+                assert np.array_equal(loc[s], plain[s][:, b0:b1]), (rank, s)
+    finally:
+        cg.set_shard(0, 1)
+        cg.set_option("stage", -1)
