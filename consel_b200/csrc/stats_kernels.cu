@@ -198,53 +198,67 @@ struct ScaleList {
     int B[32];
 };
 
+// NQ (compile time) >= nq thresholds; surplus thresholds are +HUGE and never stored.  Each
+// thread keeps four independent 8-byte loads in flight: the kernel is a pure stream over
+// the statistic blocks (8 B per row element and pass) and must be HBM bound.
+template <int NQ>
 __global__ void __launch_bounds__(RS_THREADS)
-rowsum_multi_kernel(ScaleList sl, int nq, int nsplit, const double *__restrict__ thr, cgpu_rowsum *__restrict__ part) {
+rowsum_multi_kernel(ScaleList sl, int nq, int q0, int nqt, int nsplit, const double *__restrict__ thr,
+                    cgpu_rowsum *__restrict__ part) {
+    // thresholds q0 .. q0+nq-1 of the nqt thresholds of each row
     const int row = blockIdx.x, sc = blockIdx.y, sp = blockIdx.z, S = gridDim.y;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int B = sl.B[sc];
-    const double *v = sl.stat[sc] + (size_t)row * B;
+    const double *__restrict__ v = sl.stat[sc] + (size_t)row * B;
     const int chunk = (B + nsplit - 1) / nsplit;
     const int b_lo = sp * chunk, b_hi = min(B, b_lo + chunk);
-    __shared__ double s_thr[RS_MAXQ];
-    __shared__ unsigned long long s_cnt[RS_THREADS / 32][RS_MAXQ];
-    __shared__ double s_lo[RS_THREADS / 32][RS_MAXQ], s_hi[RS_THREADS / 32][RS_MAXQ];
+    __shared__ unsigned long long s_cnt[RS_THREADS / 32][NQ];
+    __shared__ double s_lo[RS_THREADS / 32][NQ], s_hi[RS_THREADS / 32][NQ];
     __shared__ double s_edge[RS_THREADS / 32][4];
-    if (tid < nq) s_thr[tid] = thr[(size_t)row * nq + tid];
-    __syncthreads();
-    unsigned long long cnt[RS_MAXQ];
-    double lo[RS_MAXQ], hi[RS_MAXQ];
+    double t[NQ];
+    unsigned int cnt[NQ];
+    double lo[NQ], hi[NQ];
 #pragma unroll
-    for (int q = 0; q < RS_MAXQ; q++) {
+    for (int q = 0; q < NQ; q++) {
+        t[q] = q < nq ? thr[(size_t)row * nqt + q0 + q] : CG_HUGE;
         cnt[q] = 0;
         lo[q] = -CG_HUGE;
         hi[q] = CG_HUGE;
     }
     double mn1 = CG_HUGE, mn2 = CG_HUGE, mx1 = -CG_HUGE, mx2 = -CG_HUGE;
-    for (int b = b_lo + tid; b < b_hi; b += RS_THREADS) {
-        const double x = v[b];
+    auto take = [&](double x) {
         edge_insert(x, mn1, mn2, mx1, mx2);
 #pragma unroll
-        for (int q = 0; q < RS_MAXQ; q++) {
-            if (q < nq) {
-                if (x <= s_thr[q]) {
-                    cnt[q]++;
-                    lo[q] = fmax(lo[q], x);
-                } else {
-                    hi[q] = fmin(hi[q], x);
-                }
+        for (int q = 0; q < NQ; q++) {
+            if (x <= t[q]) {
+                cnt[q]++;
+                lo[q] = fmax(lo[q], x);
+            } else {
+                hi[q] = fmin(hi[q], x);
             }
         }
+    };
+    constexpr int U = 4;
+    int b = b_lo + tid;
+    for (; b + (U - 1) * RS_THREADS < b_hi; b += U * RS_THREADS) {
+        double x[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) x[u] = v[b + u * RS_THREADS];
+#pragma unroll
+        for (int u = 0; u < U; u++) take(x[u]);
     }
+    for (; b < b_hi; b += RS_THREADS) take(v[b]);
+
+    unsigned long long c64[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; q++) c64[q] = cnt[q];
 #pragma unroll
     for (int off = 16; off; off >>= 1) {
 #pragma unroll
-        for (int q = 0; q < RS_MAXQ; q++) {
-            if (q < nq) {
-                cnt[q] += __shfl_xor_sync(0xffffffffu, cnt[q], off);
-                lo[q] = fmax(lo[q], __shfl_xor_sync(0xffffffffu, lo[q], off));
-                hi[q] = fmin(hi[q], __shfl_xor_sync(0xffffffffu, hi[q], off));
-            }
+        for (int q = 0; q < NQ; q++) {
+            c64[q] += __shfl_xor_sync(0xffffffffu, c64[q], off);
+            lo[q] = fmax(lo[q], __shfl_xor_sync(0xffffffffu, lo[q], off));
+            hi[q] = fmin(hi[q], __shfl_xor_sync(0xffffffffu, hi[q], off));
         }
         double o1 = __shfl_xor_sync(0xffffffffu, mn1, off), o2 = __shfl_xor_sync(0xffffffffu, mn2, off);
         double p1 = __shfl_xor_sync(0xffffffffu, mx1, off), p2 = __shfl_xor_sync(0xffffffffu, mx2, off);
@@ -252,12 +266,11 @@ rowsum_multi_kernel(ScaleList sl, int nq, int nsplit, const double *__restrict__
     }
     if (lane == 0) {
 #pragma unroll
-        for (int q = 0; q < RS_MAXQ; q++)
-            if (q < nq) {
-                s_cnt[wid][q] = cnt[q];
-                s_lo[wid][q] = lo[q];
-                s_hi[wid][q] = hi[q];
-            }
+        for (int q = 0; q < NQ; q++) {
+            s_cnt[wid][q] = c64[q];
+            s_lo[wid][q] = lo[q];
+            s_hi[wid][q] = hi[q];
+        }
         s_edge[wid][0] = mn1; s_edge[wid][1] = mn2; s_edge[wid][2] = mx1; s_edge[wid][3] = mx2;
     }
     __syncthreads();
@@ -280,7 +293,7 @@ rowsum_multi_kernel(ScaleList sl, int nq, int nsplit, const double *__restrict__
         r.lo = l;
         r.hi = h;
         r.min1 = s_edge[0][0]; r.min2 = s_edge[0][1]; r.max1 = s_edge[0][2]; r.max2 = s_edge[0][3];
-        part[(((size_t)row * S + sc) * nsplit + sp) * nq + tid] = r;
+        part[(((size_t)row * S + sc) * nsplit + sp) * nqt + q0 + tid] = r;
     }
 }
 
@@ -312,7 +325,16 @@ int launch_rowsum_all_scales(const double *const *d_stat, const int *B, int S, i
         sl.stat[s] = d_stat[s];
         sl.B[s] = B[s];
     }
-    rowsum_multi_kernel<<<dim3(cm, S, nsplit), RS_THREADS, 0, st>>>(sl, nq, nsplit, d_thr, d_part);
+    const dim3 grid(cm, S, nsplit);
+    // more than 8 thresholds per row: two passes of <= 8 (64 registers, 3 CTAs/SM) stream faster
+    // than one pass of 16 (204 registers)
+    for (int q0 = 0; q0 < nq; q0 += 8) {
+        const int n = std::min(8, nq - q0);
+        if (n <= 1) rowsum_multi_kernel<1><<<grid, RS_THREADS, 0, st>>>(sl, n, q0, nq, nsplit, d_thr, d_part);
+        else if (n <= 2) rowsum_multi_kernel<2><<<grid, RS_THREADS, 0, st>>>(sl, n, q0, nq, nsplit, d_thr, d_part);
+        else if (n <= 4) rowsum_multi_kernel<4><<<grid, RS_THREADS, 0, st>>>(sl, n, q0, nq, nsplit, d_thr, d_part);
+        else rowsum_multi_kernel<8><<<grid, RS_THREADS, 0, st>>>(sl, n, q0, nq, nsplit, d_thr, d_part);
+    }
     CGPU_LAUNCH_CHECK();
     const int total = cm * S * nq;
     rowsum_merge_kernel<<<(total + 127) / 128, 128, 0, st>>>(d_part, total, nsplit, nq, d_out);

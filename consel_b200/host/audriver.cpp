@@ -1,5 +1,6 @@
 #include "audriver.h"
 
+#include <chrono>
 #include <algorithm>
 #include <atomic>
 #include <condition_variable>
@@ -98,8 +99,15 @@ static void parallel_for(int n, const std::function<void(int)> &body) {
     pool.run(n, body);
 }
 
+static double wall_now() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
 int run(const Input &in, const aufit::Options &opt, QueryFn query, void *ctx, Output *out) {
     const int cm = in.cm, kk = in.kk;
+    static const bool trace = getenv("CHOST_TIMING") != nullptr;  // per-phase wall times on stderr
+    double tq = 0, tf = 0;
+    int nround = 0;
     std::vector<double> bbd(kk);
     for (int k = 0; k < kk; k++) bbd[k] = (double)in.bb[k];
     const double t0 = refio::cpu_seconds();
@@ -117,14 +125,22 @@ int run(const Input &in, const aufit::Options &opt, QueryFn query, void *ctx, Ou
             any = any || !vc[i].done;
         }
         if (!any) break;
+        double w0 = wall_now();
         if (int rc = query(ctx, 1, thr.data(), rs.data())) return rc;
+        double w1 = wall_now();
+        tq += w1 - w0;
+        nround++;
         parallel_for(cm, [&](int i) {
             if (vc[i].done) return;
             std::vector<double> cnts(kk);
             for (int k = 0; k < kk; k++) cnts[k] = cgpu_smooth_count(&rs[(size_t)i * kk + k], in.bb[k], thr[i]);
             vc[i].step(cnts.data(), in.rr, bbd.data(), kk, opt);
         });
+        tf += wall_now() - w1;
     }
+    if (trace) fprintf(stderr, "[audriver] vcalpval: %d rounds, query %.2f ms, fits %.2f ms\n", nround, tq * 1e3, tf * 1e3);
+    tq = tf = 0;
+    nround = 0;
     out->pv.assign(cm, 0); out->se.assign(cm, 0); out->pv0.assign(cm, 0); out->se0.assign(cm, 0);
     out->rss.assign(cm, 0); out->df.assign(cm, 0); out->th.assign(cm, 0); out->pf.assign(cm, 0);
     out->beta.assign(3 * (size_t)cm, 0); out->ret.assign(cm, 0);
@@ -166,7 +182,11 @@ int run(const Input &in, const aufit::Options &opt, QueryFn query, void *ctx, Ou
             for (int j = 0; j < cm; j++)
                 for (int q = 0; q < nqc; q++) cthr[(size_t)j * nqc + q] = ci[(size_t)j * nq + q0 + q].x;
             crs.resize((size_t)cm * kk * nqc);
+            double w0 = wall_now();
             if (int rc = query(ctx, nqc, cthr.data(), crs.data())) return rc;
+            double w1 = wall_now();
+            tq += w1 - w0;
+            nround++;
             parallel_for(cm * nqc, [&](int e) {
                 const int j = e / nqc, q = e % nqc;
                 aufit::CiIter &c = ci[(size_t)j * nq + q0 + q];
@@ -177,8 +197,10 @@ int run(const Input &in, const aufit::Options &opt, QueryFn query, void *ctx, Ou
                     cnts[k] = cgpu_smooth_count(&crs[((size_t)j * kk + k) * nqc + q], in.bb[k], t);
                 c.step(cnts.data(), in.rr, bbd.data(), kk, opt);
             });
+            tf += wall_now() - w1;
         }
     }
+    if (trace) fprintf(stderr, "[audriver] invtpval: %d rounds, query %.2f ms, fits %.2f ms\n", nround, tq * 1e3, tf * 1e3);
     const size_t n2 = (size_t)cm * nalpha;
     out->ci.assign(n2, 0); out->cs.assign(n2, 0); out->ei.assign(n2, 0);
     out->ci0.assign(n2, 0); out->cs0.assign(n2, 0); out->ei0.assign(n2, 0);
