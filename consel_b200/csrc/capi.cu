@@ -90,6 +90,29 @@ static void shard_range(int bb, int *b0, int *b1) {
     *b1 = (int)((long long)bb * (g.shard_rank + 1) / g.shard_world);
 }
 
+// scratch arena (slots: 0 index stream, 1/2 count buffers, 3 int32 partial sums); stream-ordered on
+// the library stream, valid until the next request for the same slot
+static cudaError_t scratch_get(int slot, size_t bytes, void **out) {
+    Globals &g = G();
+    if (g.scratch_cap[slot] < bytes) {
+        dev_free(g.scratch[slot]);
+        g.scratch[slot] = nullptr;
+        g.scratch_cap[slot] = 0;
+        const size_t want = bytes + bytes / 8;
+        cudaError_t e = dev_alloc(&g.scratch[slot], want);
+        if (e != cudaSuccess) {
+            (void)cudaGetLastError();
+            e = dev_alloc(&g.scratch[slot], bytes);
+            if (e != cudaSuccess) return e;
+            g.scratch_cap[slot] = bytes;
+        } else {
+            g.scratch_cap[slot] = want;
+        }
+    }
+    *out = g.scratch[slot];
+    return cudaSuccess;
+}
+
 static void free_reps(DevReps *r) {
     if (!r) return;
     if (r->d_rep)
@@ -274,6 +297,7 @@ static int mt_prepare(unsigned long seed, unsigned long long stream_offset, unsi
 }
 
 struct Workspace {
+    bool borrowed = false;  // index / count buffers belong to the scratch arena
     unsigned char *d_idx = nullptr;  // uint16 or uint32 site indices (idx_bytes(n))
     unsigned long long *d_counts[2] = {nullptr, nullptr};
     int *d_err = nullptr;
@@ -286,9 +310,11 @@ struct Workspace {
         cudaEventCreateWithFlags(&idx_ready, cudaEventDisableTiming);
     }
     ~Workspace() {
-        dev_free(d_idx);
-        dev_free(d_counts[0]);
-        dev_free(d_counts[1]);
+        if (!borrowed) {
+            dev_free(d_idx);
+            dev_free(d_counts[0]);
+            dev_free(d_counts[1]);
+        }
         dev_free(d_err);
         for (int i = 0; i < 2; i++) {
             cudaEventDestroy(hist_done[i]);
@@ -329,10 +355,7 @@ static int scaleboot_core(DevMatrix &m, int S, const int *bn, const int *bb, uns
     int max_nb = 0;
     for (int s = 0; s < S; s++) max_nb = std::max(max_nb, reps->nb[s]);
     int *d_partial = nullptr;  // int32 partial sums of the tensor-core path
-    struct PartialGuard {
-        int *&p;
-        ~PartialGuard() { dev_free(p); }
-    } pguard{d_partial};
+
     if (i8) {
         pt.begin(0);
         CGPU_TRY(fx_prepare(m, st));
@@ -346,9 +369,10 @@ static int scaleboot_core(DevMatrix &m, int S, const int *bn, const int *bb, uns
     }
     const int align = i8 ? 256 : 64;
     const int batch = (int)std::min<long long>(cap, std::max(align, (max_nb + align - 1) / align * align));
-    if (i8) CGPU_CUDA(dev_alloc(&d_partial, m.fxMpad * (size_t)batch * sizeof(int)));
+    if (i8) CGPU_CUDA(scratch_get(3, m.fxMpad * (size_t)batch * sizeof(int), reinterpret_cast<void **>(&d_partial)));
 
     Workspace ws;
+    ws.borrowed = true;
     CGPU_CUDA(dev_alloc(&ws.d_err, sizeof(int)));
     CGPU_CUDA(cudaMemsetAsync(ws.d_err, 0, sizeof(int), st));
 
@@ -409,7 +433,7 @@ static int scaleboot_core(DevMatrix &m, int S, const int *bn, const int *bb, uns
     }
     if (!fuse_hist)
         for (int i = 0; i < 2; i++) {
-            CGPU_CUDA(dev_alloc(&ws.d_counts[i], (size_t)(batch / 8) * NP * 8));
+            CGPU_CUDA(scratch_get(1 + i, (size_t)(batch / 8) * NP * 8, reinterpret_cast<void **>(&ws.d_counts[i])));
             // padding sites and replicates must read as zero counts
             CGPU_CUDA(cudaMemsetAsync(ws.d_counts[i], 0, (size_t)(batch / 8) * NP * 8, st));
         }
@@ -418,7 +442,7 @@ static int scaleboot_core(DevMatrix &m, int S, const int *bn, const int *bb, uns
         const unsigned long long idx_budget = (unsigned long long)24 << 30;
         idx_whole_run = !fuse_hist && S <= 32 && idx_off[S] > 0 && idx_off[S] * idx_bytes((uint32_t)n) <= idx_budget;
         const size_t idx_elems = fuse_hist ? 1 : idx_whole_run ? (size_t)idx_off[S] : (size_t)batch * max_bn;
-        CGPU_CUDA(dev_alloc(&ws.d_idx, idx_elems * idx_bytes((uint32_t)n)));
+        CGPU_CUDA(scratch_get(0, idx_elems * idx_bytes((uint32_t)n), reinterpret_cast<void **>(&ws.d_idx)));
         std::vector<unsigned long long> lo(S), hi(S);
         for (int s = 0; s < S; s++) {
             lo[s] = base[s] + (unsigned long long)reps->b0[s] * (unsigned long long)bn[s];
@@ -726,6 +750,12 @@ void cgpu_shutdown(void) {
     if (!g.inited) return;
     cudaStreamSynchronize(g.stream);
     dev_free(g.d_jump_table);
+    for (int i = 0; i < 4; i++) {
+        dev_free(g.scratch[i]);
+        g.scratch[i] = nullptr;
+        g.scratch_cap[i] = 0;
+    }
+    cudaStreamSynchronize(g.stream);
     cudaStreamDestroy(g.stream);
     cudaStreamDestroy(g.stream2);
     cudaStreamDestroy(g.stream3);

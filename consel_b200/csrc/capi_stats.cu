@@ -146,6 +146,7 @@ int cgpu_stats_build(cgpu_reps *rr, int cm, const int *ass_ptr, const int *ass_i
     dev_free(r->d_ass_idx);
     r->d_ass_ptr = r->d_ass_idx = nullptr;
     r->cm = cm;
+    r->h_edges.clear();  // new statistics: the cached row edges are stale
     CGPU_CUDA(dev_alloc(&r->d_ass_ptr, (size_t)(cm + 1) * sizeof(int)));
     CGPU_CUDA(dev_alloc(&r->d_ass_idx, (size_t)std::max(1, ass_ptr[cm]) * sizeof(int)));
     CGPU_CUDA(cudaMemcpyAsync(r->d_ass_ptr, ass_ptr, (size_t)(cm + 1) * sizeof(int), cudaMemcpyHostToDevice, st));
@@ -204,6 +205,7 @@ int cgpu_count_query(const cgpu_reps *rr, int nq, const double *thr, cgpu_rowsum
     }
     cudaStream_t st = G().stream;
     const int cm = r->cm, S = r->S;
+    const bool have_edges = r->h_edges.size() == (size_t)cm * S * 4;
     DevBuf d_thr, d_out, d_part;
     CGPU_TRY(d_thr.upload(thr, (size_t)cm * nq, st));
     const size_t nout = (size_t)cm * S * nq;
@@ -216,7 +218,7 @@ int cgpu_count_query(const cgpu_reps *rr, int nq, const double *thr, cgpu_rowsum
         nsplit = (int)std::min<long long>(nsplit, std::max<long long>(1, maxB / 1024));
         CGPU_TRY(d_part.alloc(nout * nsplit * sizeof(cgpu_rowsum)));
         CGPU_TRY(launch_rowsum_all_scales(r->d_stat, r->nb, S, cm, nq, d_thr.as<double>(), d_part.as<cgpu_rowsum>(),
-                                          d_out.as<cgpu_rowsum>(), nsplit, st));
+                                          d_out.as<cgpu_rowsum>(), nsplit, st, !have_edges));
     } else {
         for (int s = 0; s < S; s++) {
             RowSrc src{r->d_stat[s], r->nb[s], nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -225,6 +227,24 @@ int cgpu_count_query(const cgpu_reps *rr, int nq, const double *thr, cgpu_rowsum
     }
     CGPU_CUDA(cudaMemcpyAsync(out, d_out.p, nout * sizeof(cgpu_rowsum), cudaMemcpyDeviceToHost, st));
     CGPU_CUDA(cudaStreamSynchronize(st));
+    if (S <= 32) {
+        if (!have_edges) {
+            r->h_edges.resize((size_t)cm * S * 4);
+            for (size_t e = 0; e < (size_t)cm * S; e++) {
+                const cgpu_rowsum &q = out[e * nq];
+                double *c = &r->h_edges[4 * e];
+                c[0] = q.min1; c[1] = q.min2; c[2] = q.max1; c[3] = q.max2;
+            }
+        } else {
+            for (size_t e = 0; e < (size_t)cm * S; e++) {
+                const double *c = &r->h_edges[4 * e];
+                for (int q = 0; q < nq; q++) {
+                    cgpu_rowsum &o = out[e * nq + q];
+                    o.min1 = c[0]; o.min2 = c[1]; o.max1 = c[2]; o.max2 = c[3];
+                }
+            }
+        }
+    }
     return CGPU_OK;
 }
 

@@ -78,6 +78,11 @@ struct Globals {
     int jump_nquads[64] = {0};
     cudaEvent_t ev[8] = {};
     double last_ms[12] = {0};
+    // grow-only scratch arena for the large per-call workspaces of the resampling path (index
+    // stream, count buffers, int32 partial sums): they keep their addresses between calls, so
+    // interleaved smaller allocations cannot fragment the pool and force a re-map of GBs
+    void *scratch[4] = {nullptr, nullptr, nullptr, nullptr};
+    size_t scratch_cap[4] = {0, 0, 0, 0};
     // tuning switches (cgpu_set_option); -1 = built-in default
     int opt_overlap = -1, opt_hist_algo = -1, opt_contract_algo = -1, opt_i8_oneshot = -1, opt_draw_nch = -1, opt_chunk_log2 = -1, opt_i8_fuse = -1, opt_draw_fuse = -1, opt_stage = -1;
 };
@@ -119,7 +124,10 @@ struct DevReps {  // cgpu_reps
     // statistics (cgpu_stats_build)
     int cm = 0;
     double **d_stat = nullptr;  // cm x nb[s]
-    void *d_edges = nullptr;    // cm x S x 4 doubles: min1,min2,max1,max2
+    void *d_edges = nullptr;    // (unused)
+    // host cache of the row edges (min1, min2, max1, max2 per (item, scale)); filled by the first
+    // count query after a statistics build, so later queries skip the edge tracking
+    mutable std::vector<double> h_edges;
     int *d_ass_ptr = nullptr, *d_ass_idx = nullptr;
 };
 
@@ -225,7 +233,7 @@ struct RowSrc {
 int launch_rowsum(int mode, const RowSrc &src, int rows, int B, int nq, const double *d_thr, cgpu_rowsum *d_out,
                   int out_stride, int out_off, cudaStream_t st);
 int launch_rowsum_all_scales(const double *const *d_stat, const int *B, int S, int cm, int nq, const double *d_thr,
-                             cgpu_rowsum *d_part, cgpu_rowsum *d_out, int nsplit, cudaStream_t st);
+                             cgpu_rowsum *d_part, cgpu_rowsum *d_out, int nsplit, cudaStream_t st, bool edges = true);
 int launch_order_stat(const double *d_stat, int rows, int B, int ld, const int *d_rank, double *d_val, cudaStream_t st);
 int launch_col_top2(const double *x, int K, int B, int ld, double *m1, double *m2, int *a1, cudaStream_t st);
 int launch_stat_build(const double *x, int K, int B, int ld, const double *m1, const double *m2, const int *a1,

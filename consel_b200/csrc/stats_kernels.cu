@@ -201,7 +201,9 @@ struct ScaleList {
 // NQ (compile time) >= nq thresholds; surplus thresholds are +HUGE and never stored.  Each
 // thread keeps four independent 8-byte loads in flight: the kernel is a pure stream over
 // the statistic blocks (8 B per row element and pass) and must be HBM bound.
-template <int NQ>
+// EDGES: also track the two smallest / two largest values of the row (needed once per
+// statistics build; later queries take them from the host-side cache and skip the work)
+template <int NQ, bool EDGES>
 __global__ void __launch_bounds__(RS_THREADS)
 rowsum_multi_kernel(ScaleList sl, int nq, int q0, int nqt, int nsplit, const double *__restrict__ thr,
                     cgpu_rowsum *__restrict__ part) {
@@ -227,7 +229,7 @@ rowsum_multi_kernel(ScaleList sl, int nq, int q0, int nqt, int nsplit, const dou
     }
     double mn1 = CG_HUGE, mn2 = CG_HUGE, mx1 = -CG_HUGE, mx2 = -CG_HUGE;
     auto take = [&](double x) {
-        edge_insert(x, mn1, mn2, mx1, mx2);
+        if (EDGES) edge_insert(x, mn1, mn2, mx1, mx2);
 #pragma unroll
         for (int q = 0; q < NQ; q++) {
             if (x <= t[q]) {
@@ -314,7 +316,7 @@ rowsum_merge_kernel(const cgpu_rowsum *__restrict__ part, int total, int nsplit,
 }
 
 int launch_rowsum_all_scales(const double *const *d_stat, const int *B, int S, int cm, int nq, const double *d_thr,
-                             cgpu_rowsum *d_part, cgpu_rowsum *d_out, int nsplit, cudaStream_t st) {
+                             cgpu_rowsum *d_part, cgpu_rowsum *d_out, int nsplit, cudaStream_t st, bool edges) {
     if (cm <= 0 || S <= 0) return CGPU_OK;
     if (S > 32 || nq < 1 || nq > RS_MAXQ) {
         set_error(CGPU_EINVAL, "count query with %d scales / %d thresholds", S, nq);
@@ -328,13 +330,19 @@ int launch_rowsum_all_scales(const double *const *d_stat, const int *B, int S, i
     const dim3 grid(cm, S, nsplit);
     // more than 8 thresholds per row: two passes of <= 8 (64 registers, 3 CTAs/SM) stream faster
     // than one pass of 16 (204 registers)
+#define CGPU_RSM(NQ_)                                                                                                     \
+    do {                                                                                                                  \
+        if (edges) rowsum_multi_kernel<NQ_, true><<<grid, RS_THREADS, 0, st>>>(sl, n, q0, nq, nsplit, d_thr, d_part);     \
+        else rowsum_multi_kernel<NQ_, false><<<grid, RS_THREADS, 0, st>>>(sl, n, q0, nq, nsplit, d_thr, d_part);          \
+    } while (0)
     for (int q0 = 0; q0 < nq; q0 += 8) {
         const int n = std::min(8, nq - q0);
-        if (n <= 1) rowsum_multi_kernel<1><<<grid, RS_THREADS, 0, st>>>(sl, n, q0, nq, nsplit, d_thr, d_part);
-        else if (n <= 2) rowsum_multi_kernel<2><<<grid, RS_THREADS, 0, st>>>(sl, n, q0, nq, nsplit, d_thr, d_part);
-        else if (n <= 4) rowsum_multi_kernel<4><<<grid, RS_THREADS, 0, st>>>(sl, n, q0, nq, nsplit, d_thr, d_part);
-        else rowsum_multi_kernel<8><<<grid, RS_THREADS, 0, st>>>(sl, n, q0, nq, nsplit, d_thr, d_part);
+        if (n <= 1) CGPU_RSM(1);
+        else if (n <= 2) CGPU_RSM(2);
+        else if (n <= 4) CGPU_RSM(4);
+        else CGPU_RSM(8);
     }
+#undef CGPU_RSM
     CGPU_LAUNCH_CHECK();
     const int total = cm * S * nq;
     rowsum_merge_kernel<<<(total + 127) / 128, 128, 0, st>>>(d_part, total, nsplit, nq, d_out);

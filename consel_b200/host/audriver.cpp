@@ -172,15 +172,26 @@ int run(const Input &in, const aufit::Options &opt, QueryFn query, void *ctx, Ou
     const int qchunk = 16;  // thresholds per item and query
     std::vector<double> cthr;
     std::vector<cgpu_rowsum> crs;
+    // Each round queries only the searches that have not converged yet: per item the active
+    // thresholds are packed to the front (padded with a value above every statistic), so the
+    // device pass gets narrower as the round count grows.
+    std::vector<int> act((size_t)cm * nq), nact(cm);
     for (int round = 0; round < opt.ciloopmax; round++) {
-        bool any = false;
-        for (auto &c : ci) any = any || !c.done;
-        if (!any) break;
-        for (int q0 = 0; q0 < nq; q0 += qchunk) {
-            const int nqc = std::min(qchunk, nq - q0);
-            cthr.assign((size_t)cm * nqc, 0.0);
+        int nmax = 0;
+        for (int j = 0; j < cm; j++) {
+            int n = 0;
+            for (int q = 0; q < nq; q++)
+                if (!ci[(size_t)j * nq + q].done) act[(size_t)j * nq + n++] = q;
+            nact[j] = n;
+            nmax = std::max(nmax, n);
+        }
+        if (nmax == 0) break;
+        for (int a0 = 0; a0 < nmax; a0 += qchunk) {
+            const int nqc = std::min(qchunk, nmax - a0);
+            cthr.assign((size_t)cm * nqc, 1.0e300);
             for (int j = 0; j < cm; j++)
-                for (int q = 0; q < nqc; q++) cthr[(size_t)j * nqc + q] = ci[(size_t)j * nq + q0 + q].x;
+                for (int a = 0; a < nqc && a0 + a < nact[j]; a++)
+                    cthr[(size_t)j * nqc + a] = ci[(size_t)j * nq + act[(size_t)j * nq + a0 + a]].x;
             crs.resize((size_t)cm * kk * nqc);
             double w0 = wall_now();
             if (int rc = query(ctx, nqc, cthr.data(), crs.data())) return rc;
@@ -188,13 +199,13 @@ int run(const Input &in, const aufit::Options &opt, QueryFn query, void *ctx, Ou
             tq += w1 - w0;
             nround++;
             parallel_for(cm * nqc, [&](int e) {
-                const int j = e / nqc, q = e % nqc;
-                aufit::CiIter &c = ci[(size_t)j * nq + q0 + q];
-                if (c.done) return;
+                const int j = e / nqc, a = e % nqc;
+                if (a0 + a >= nact[j]) return;
+                aufit::CiIter &c = ci[(size_t)j * nq + act[(size_t)j * nq + a0 + a]];
                 std::vector<double> cnts(kk);
-                const double t = cthr[(size_t)j * nqc + q];
+                const double t = cthr[(size_t)j * nqc + a];
                 for (int k = 0; k < kk; k++)
-                    cnts[k] = cgpu_smooth_count(&crs[((size_t)j * kk + k) * nqc + q], in.bb[k], t);
+                    cnts[k] = cgpu_smooth_count(&crs[((size_t)j * kk + k) * nqc + a], in.bb[k], t);
                 c.step(cnts.data(), in.rr, bbd.data(), kk, opt);
             });
             tf += wall_now() - w1;

@@ -18,10 +18,11 @@ for name in sys.argv[1:]:
     L = synth(K, n)
     mat = cg.Matrix(L)
     for sm in (2,):
-        for it in range(2):
+        for it in range(int(__import__("os").environ.get("PIPE_ITERS", "2"))):
             t = time.perf_counter()
             res = pipeline.run(L, RR, [B] * 10, 7, sum_mode=sm, matrix=mat)
             wall = time.perf_counter() - t
+            print("   iter", it, f"{wall*1e3:.1f} ms", flush=True)
         print(name, "sum_mode", sm, f"wall {wall*1e3:.1f} ms", {k: (round(v*1e3, 1) if isinstance(v, float) else v) for k, v in res["timing"].items() if k != "device_ms"},
               "dev", {k: round(v, 1) for k, v in res["timing"]["device_ms"].items() if v > 0.05}, flush=True)
         print("   au[:3]", res["pv"][:3, 6], "bp[:3]", res["pv"][:3, 0])
