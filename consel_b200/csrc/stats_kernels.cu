@@ -416,18 +416,42 @@ int launch_order_stat(const double *d_stat, int rows, int B, int ld, const int *
 // centring (src/consel.c:1378-1382): one warp per tree; the row sum is accumulated in
 // the reference's order (b ascending, one rounded add per element): lanes fetch 32
 // consecutive values, every lane replays the 32 adds through shuffles.
+constexpr int CR_CHUNK = 256;  // elements staged per warp and step
 __global__ void __launch_bounds__(128)
 center_rows_kernel(const double *__restrict__ x, int K, int B, int ld, double *__restrict__ xc) {
-    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + w;
+    __shared__ double stage[4][CR_CHUNK];
     if (row >= K) return;
     const double *src = x + (size_t)row * ld;
+    double *buf = stage[w];
+    // The row sum is one chain of rounded adds in replicate order.  The next 256 values are
+    // fetched (coalesced, 8 per lane) while every lane replays the chain over the staged ones
+    // from shared memory: the only serial latency left is the add itself.
+    double nxt[CR_CHUNK / 32];
+#pragma unroll
+    for (int u = 0; u < CR_CHUNK / 32; u++) {
+        const int b = u * 32 + lane;
+        nxt[u] = b < B ? src[b] : 0.0;
+    }
     double s = 0.0;
-    for (int b0 = 0; b0 < B; b0 += 32) {
-        const int b = b0 + lane;
-        const double v = b < B ? src[b] : 0.0;
-        const int m = min(32, B - b0);
-        for (int t = 0; t < m; t++) s = __dadd_rn(s, __shfl_sync(0xffffffffu, v, t));
+    for (int b0 = 0; b0 < B; b0 += CR_CHUNK) {
+        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < CR_CHUNK / 32; u++) buf[u * 32 + lane] = nxt[u];
+        __syncwarp();
+#pragma unroll
+        for (int u = 0; u < CR_CHUNK / 32; u++) {
+            const int b = b0 + CR_CHUNK + u * 32 + lane;
+            nxt[u] = b < B ? src[b] : 0.0;
+        }
+        const int m = min(CR_CHUNK, B - b0);
+        if (m == CR_CHUNK) {
+#pragma unroll 32
+            for (int t = 0; t < CR_CHUNK; t++) s = __dadd_rn(s, buf[t]);
+        } else {
+            for (int t = 0; t < m; t++) s = __dadd_rn(s, buf[t]);
+        }
     }
     const double mean = __ddiv_rn(s, (double)B);
     double *dst = xc + (size_t)row * ld;
@@ -446,20 +470,51 @@ pair_weight_kernel(const double *__restrict__ xc, int K, int B, int ld, double v
     __shared__ double si[PV_T][PV_BC + 1], sj[PV_T][PV_BC + 1];
     const int tx = threadIdx.x % PV_T, ty = threadIdx.x / PV_T;  // pair (i = ti*16+ty, j = tj*16+tx)
     const int i = ti * PV_T + ty, j = tj * PV_T + tx;
+    // staging: thread e loads rows r = e/64 (+4, +8, +12) at column e%64 of both tiles; the next
+    // chunk is fetched into registers while the current one is consumed from shared memory
+    constexpr int PER = PV_T * PV_BC / (PV_T * PV_T);  // 4 elements per thread and tile
+    const int lc = threadIdx.x % PV_BC, lr = threadIdx.x / PV_BC;
+    double ni[PER], nj[PER];
+    auto fetch = [&](int b0) {
+#pragma unroll
+        for (int u = 0; u < PER; u++) {
+            const int r = lr + u * (PV_T * PV_T / PV_BC);
+            const int b = b0 + lc;
+            const int gi = ti * PV_T + r, gj = tj * PV_T + r;
+            ni[u] = (gi < K && b < B) ? xc[(size_t)gi * ld + b] : 0.0;
+            nj[u] = (gj < K && b < B) ? xc[(size_t)gj * ld + b] : 0.0;
+        }
+    };
+    fetch(0);
     double acc = 0.0;
     for (int b0 = 0; b0 < B; b0 += PV_BC) {
-        for (int e = threadIdx.x; e < PV_T * PV_BC; e += PV_T * PV_T) {
-            int r = e / PV_BC, c = e % PV_BC;
-            int b = b0 + c;
-            int gi = ti * PV_T + r, gj = tj * PV_T + r;
-            si[r][c] = (gi < K && b < B) ? xc[(size_t)gi * ld + b] : 0.0;
-            sj[r][c] = (gj < K && b < B) ? xc[(size_t)gj * ld + b] : 0.0;
+#pragma unroll
+        for (int u = 0; u < PER; u++) {
+            const int r = lr + u * (PV_T * PV_T / PV_BC);
+            si[r][lc] = ni[u];
+            sj[r][lc] = nj[u];
         }
         __syncthreads();
+        fetch(b0 + PV_BC);
         const int m = min(PV_BC, B - b0);
-        for (int c = 0; c < m; c++) {
-            double d = __dsub_rn(si[ty][c], sj[tx][c]);
-            acc = __dadd_rn(acc, __dmul_rn(d, d));
+        if (m == PV_BC) {
+            // squares first (independent), then the chain of rounded adds in replicate order
+#pragma unroll
+            for (int c0 = 0; c0 < PV_BC; c0 += 8) {
+                double q[8];
+#pragma unroll
+                for (int c = 0; c < 8; c++) {
+                    const double d = __dsub_rn(si[ty][c0 + c], sj[tx][c0 + c]);
+                    q[c] = __dmul_rn(d, d);
+                }
+#pragma unroll
+                for (int c = 0; c < 8; c++) acc = __dadd_rn(acc, q[c]);
+            }
+        } else {
+            for (int c = 0; c < m; c++) {
+                double d = __dsub_rn(si[ty][c], sj[tx][c]);
+                acc = __dadd_rn(acc, __dmul_rn(d, d));
+            }
         }
         __syncthreads();
     }
