@@ -70,11 +70,9 @@ __device__ __forceinline__ void warp_hist_add(unsigned char *hist, unsigned char
         }
         __syncwarp();
     } else if (HALGO == 1) {
-        if (valid) {
-            const unsigned sh = (k & 3u) * 8u;
-            unsigned old = atomicAdd(reinterpret_cast<unsigned *>(hist) + (k >> 2), 1u << sh);
-            if (((old >> sh) & 0xffu) == 0xffu) *overflow = 1;
-        }
+        // fire-and-forget add on the packed byte; a byte that wraps past 255 is caught by the
+        // row checksum after the counting phase (a wrap changes the byte sum by -255)
+        if (valid) atomicAdd(reinterpret_cast<unsigned *>(hist) + (k >> 2), 1u << ((k & 3u) * 8u));
     } else {
         bool pending = valid;
         while (__any_sync(0xffffffffu, pending)) {
@@ -93,28 +91,34 @@ __device__ __forceinline__ void warp_hist_add(unsigned char *hist, unsigned char
 
 // SRC 0: uint32 indices from the buffer (replicate r of this launch at idx[r*bn ..));
 // SRC 2: the same with uint16 indices;  SRC 1: Philox
-template <int SRC, int HALGO, bool ROWS>
+// RPC replicates per CTA (8 warps): 8 = one warp per replicate; 4 / 2 / 1 (byte rows only) let
+// 2 / 4 / 8 warps share one histogram, so alignments of up to 225280 sites still count in
+// shared memory instead of with global atomics.
+template <int SRC, int HALGO, bool ROWS, int RPC>
 __global__ void __launch_bounds__(HIST_THREADS)
 hist_group_kernel(const void *__restrict__ idx_v, int n, int NP, int bn, int nb,
                   unsigned long long *__restrict__ counts, int *__restrict__ err,
                   uint32_t key0, uint32_t key1, uint32_t scale, uint32_t b_first) {
-    extern __shared__ unsigned char hsm[];  // 8 histograms of NP bytes (+ 8 tag arrays for HALGO 2)
+    extern __shared__ unsigned char hsm[];  // RPC histograms of NP bytes (+ 8 tag arrays for HALGO 2)
+    static_assert(RPC == 8 || (ROWS && HALGO == 1), "shared histograms need the atomic update and the row layout");
+    constexpr int WPR = 8 / RPC;  // warps per replicate
     unsigned char *tag = hsm + (size_t)8 * NP + (size_t)(threadIdx.x >> 5) * NP;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const int ngroups = (nb + 7) / 8;
+    const int slot = wid / WPR, sub = wid % WPR;
+    const int ngroups = (nb + RPC - 1) / RPC;
     for (int g = blockIdx.x; g < ngroups; g += gridDim.x) {
-        for (int i = tid; i < NP * 2; i += HIST_THREADS) reinterpret_cast<uint32_t *>(hsm)[i] = 0;
+        for (int i = tid; i < NP * RPC / 4; i += HIST_THREADS) reinterpret_cast<uint32_t *>(hsm)[i] = 0;
         __syncthreads();
-        const int r = g * 8 + wid;  // replicate within this launch
+        const int r = g * RPC + slot;  // replicate within this launch
         if (r < nb) {
-            unsigned char *hist = hsm + (size_t)wid * NP;
+            unsigned char *hist = hsm + (size_t)slot * NP;
             int overflow = 0;
             if (SRC != 1) {
                 const uint32_t *src32 = static_cast<const uint32_t *>(idx_v) + (size_t)r * bn;
                 const uint16_t *src16 = static_cast<const uint16_t *>(idx_v) + (size_t)r * bn;
                 // 8 independent index loads in flight per lane before the histogram updates
                 // (the loop is otherwise bound by global-load latency)
-                for (int i0 = 0; i0 < bn; i0 += 256) {
+                for (int i0 = sub * 256; i0 < bn; i0 += WPR * 256) {
                     uint32_t kk[8];
                     bool vv[8];
 #pragma unroll
@@ -131,7 +135,7 @@ hist_group_kernel(const void *__restrict__ idx_v, int n, int NP, int bn, int nb,
             } else {
                 // draw i of replicate b is word (i & 3) of Philox(counter = (i >> 2, b, scale, 0))
                 const uint32_t b = b_first + (uint32_t)r;
-                for (int i0 = 0; i0 < bn; i0 += 128) {
+                for (int i0 = sub * 128; i0 < bn; i0 += WPR * 128) {
                     int q = (i0 >> 2) + lane;
                     Philox4 p = philox4x32_10((uint32_t)q, b, scale, 0u, key0, key1);
 #pragma unroll
@@ -144,12 +148,27 @@ hist_group_kernel(const void *__restrict__ idx_v, int n, int NP, int bn, int nb,
             if (overflow) atomicExch(err, 1);
         }
         __syncthreads();
+        if (HALGO == 1 && sub == 0 && r < nb) {
+            // checksum: the bytes of a histogram must add up to the number of draws
+            const uint4 *h4 = reinterpret_cast<const uint4 *>(hsm + (size_t)slot * NP);
+            unsigned int sum = 0;
+            for (int i = lane; i < NP / 16; i += 32) {
+                const uint4 v = h4[i];
+                sum = __dp4a(v.x, 0x01010101u, sum);
+                sum = __dp4a(v.y, 0x01010101u, sum);
+                sum = __dp4a(v.z, 0x01010101u, sum);
+                sum = __dp4a(v.w, 0x01010101u, sum);
+            }
+#pragma unroll
+            for (int off = 16; off; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+            if (lane == 0 && sum != (unsigned int)bn) atomicExch(err, 1);
+        }
         if (ROWS) {
-            // plain rows: replicate 8g+w owns NP consecutive bytes
-            unsigned char *dst = reinterpret_cast<unsigned char *>(counts) + (size_t)g * 8 * NP;
+            // plain rows: replicate RPC*g+slot owns NP consecutive bytes (rows past nb are padding)
+            unsigned char *dst = reinterpret_cast<unsigned char *>(counts) + (size_t)g * RPC * NP;
             const uint4 *src4 = reinterpret_cast<const uint4 *>(hsm);
             uint4 *dst4 = reinterpret_cast<uint4 *>(dst);
-            for (int i = tid; i < 8 * NP / 16; i += HIST_THREADS) dst4[i] = src4[i];
+            for (int i = tid; i < RPC * NP / 16; i += HIST_THREADS) dst4[i] = src4[i];
             __syncthreads();
             continue;
         }
@@ -224,17 +243,17 @@ static int hist_algo() {
     return G().opt_hist_algo >= 0 ? G().opt_hist_algo : v;
 }
 
-template <int SRC, int HALGO, bool ROWS>
+template <int SRC, int HALGO, bool ROWS, int RPC = 8>
 static int hist_group_launch(const void *d_idx, int n, int NP, int bn, int nb, unsigned long long *d_counts,
                              int *d_err, uint32_t k0, uint32_t k1, uint32_t scale, uint32_t b_first, cudaStream_t st) {
-    auto kern = hist_group_kernel<SRC, HALGO, ROWS>;
+    auto kern = hist_group_kernel<SRC, HALGO, ROWS, RPC>;
     static bool attr_done = false;
     if (!attr_done) {
         CGPU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * HIST_SMEM_SITES));
         attr_done = true;
     }
-    const int ngroups = (nb + 7) / 8;
-    const size_t smem = (size_t)8 * NP * (HALGO == 2 ? 2 : 1);
+    const int ngroups = (nb + RPC - 1) / RPC;
+    const size_t smem = (size_t)RPC * NP * (HALGO == 2 ? 2 : 1);
     const int sms = G().sm_count > 0 ? G().sm_count : 148;
     int per_sm = (int)std::min<size_t>(8, (220 * 1024) / smem);
     if (per_sm < 1) per_sm = 1;
@@ -261,6 +280,18 @@ static int hist_dispatch(int src, const void *d_idx, int n, int NP, int bn, int 
         CGPU_HIST_CASE(2, 0) CGPU_HIST_CASE(2, 1) CGPU_HIST_CASE(2, 2)
 #undef CGPU_HIST_CASE
         set_error(CGPU_EINVAL, "CGPU_HIST_ALGO=%d", algo);
+        return CGPU_EINVAL;
+    } else if (rows && NP <= 8 * HIST_SMEM_SITES) {
+        // byte rows of a long alignment: 4, 2 or 1 replicates per CTA share the 8 warps
+#define CGPU_HISTW_CASE(S)                                                                                               \
+    if (src == S) {                                                                                                       \
+        if (NP <= 2 * HIST_SMEM_SITES) return hist_group_launch<S, 1, true, 4>(d_idx, n, NP, bn, nb, d_counts, d_err, k0, k1, scale, b_first, st); \
+        if (NP <= 4 * HIST_SMEM_SITES) return hist_group_launch<S, 1, true, 2>(d_idx, n, NP, bn, nb, d_counts, d_err, k0, k1, scale, b_first, st); \
+        return hist_group_launch<S, 1, true, 1>(d_idx, n, NP, bn, nb, d_counts, d_err, k0, k1, scale, b_first, st);      \
+    }
+        CGPU_HISTW_CASE(0) CGPU_HISTW_CASE(1) CGPU_HISTW_CASE(2)
+#undef CGPU_HISTW_CASE
+        set_error(CGPU_EINVAL, "histogram source %d", src);
         return CGPU_EINVAL;
     } else {
         CGPU_CUDA(cudaMemsetAsync(d_counts, 0, (size_t)ngroups * NP * 8, st));

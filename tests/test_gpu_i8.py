@@ -174,3 +174,23 @@ def test_staged_index_production_same_result(cg, orc):
     finally:
         cg.set_shard(0, 1)
         cg.set_option("stage", -1)
+
+
+@pytest.mark.parametrize("n", [30000, 60000, 120000])
+def test_int8_long_alignments_shared_histograms(cg, orc, n):
+    """28160 < n <= 225280: byte-row histograms with 4, 2, 1 replicates per CTA (the fp64 paths
+    count such alignments with global atomics, cgpu_resample_counts is that path)."""
+    K, bb = 3, [5, 2]
+    L = synth(K, n, seed=n)
+    _, bn, rr1 = orc.scale_setup(L, [0.6, 1.3])
+    for mode in (cg.RNG_MT19937,):
+        got = cg.scaleboot_all(L, bn, bb, 31, rng_mode=mode, sum_mode=cg.SUM_INT8)
+        for s in range(len(bb)):
+            counts = cg.resample_counts(n, bn, bb, 31, s)
+            assert counts.sum(axis=1).tolist() == [int(bn[s])] * bb[s]
+            want = orc.exact_rounded_contract(L, counts, rr1[s])
+            assert np.array_equal(got[s], want), (n, s)
+    ph = cg.scaleboot_all(L, bn, bb, 31, rng_mode=cg.RNG_PHILOX, sum_mode=cg.SUM_INT8)
+    ref = cg.scaleboot_all(L, bn, bb, 31, rng_mode=cg.RNG_PHILOX, sum_mode=cg.SUM_FAST)
+    for s in range(len(bb)):
+        assert np.abs(ph[s] - ref[s]).max() <= 1e-9 * np.abs(ref[s]).max()

@@ -16,16 +16,19 @@ cg.load().cgpu_bench_fp64_peak(C.byref(tf))
 print("fp64 DFMA peak TFLOP/s:", tf.value, flush=True)
 RR = [0.5, 0.6, 0.7, 0.8, 0.9, 1.0, 1.1, 1.2, 1.3, 1.4]
 cfgs = [("C1", 15, 3414, 10000), ("C2", 105, 3414, 100000), ("C3/10", 1000, 100000, 1000), ("C3", 1000, 100000, 10000), ("K300", 300, 3414, 20000)]
+cfgs.append(("C5", 10000, 50000, 10000))
 if len(sys.argv) > 1:
     cfgs = [c for c in cfgs if c[0] in sys.argv[1:]]
+import os
+MODES = [(0, 0), (1, 1), (0, 2), (1, 2)] if not os.environ.get("I8_ONLY") else [(0, 2), (1, 2)]
 for name, K, n, B in cfgs:
     L = synth(K, n)
     _, bn, _ = cg.scale_setup(L, RR)
     bb = [B] * 10
     m = cg.Matrix(L)
     acc = K * n * sum(bb)
-    for rng, sm in [(0, 0), (1, 1), (0, 2), (1, 2)]:
-        for it in range(3):
+    for rng, sm in MODES:
+        for it in range(2 if K * n * B > 5e11 else 3):
             t = time.time()
             r = m.scaleboot(bn, bb, 7, rng_mode=rng, sum_mode=sm)
             wall = time.time() - t
