@@ -439,7 +439,14 @@ static int scaleboot_core(DevMatrix &m, int S, const int *bn, const int *bb, uns
         }
     if (rng_mode == CGPU_RNG_MT19937) {
         for (int s = 0; s < S; s++) idx_off[s + 1] = idx_off[s] + (unsigned long long)reps->nb[s] * (unsigned long long)bn[s];
-        const unsigned long long idx_budget = (unsigned long long)24 << 30;
+        // index stream of the whole call in one buffer when it fits 64 GB and half of the free
+        // device memory (C3: 38 GB of uint32 indices); otherwise batch by batch
+        unsigned long long idx_budget = (unsigned long long)64 << 30;
+        {
+            size_t free_b = 0, total_b = 0;
+            if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
+                idx_budget = std::min<unsigned long long>(idx_budget, (free_b + G().scratch_cap[0]) / 2);
+        }
         idx_whole_run = !fuse_hist && S <= 32 && idx_off[S] > 0 && idx_off[S] * idx_bytes((uint32_t)n) <= idx_budget;
         const size_t idx_elems = fuse_hist ? 1 : idx_whole_run ? (size_t)idx_off[S] : (size_t)batch * max_bn;
         CGPU_CUDA(scratch_get(0, idx_elems * idx_bytes((uint32_t)n), reinterpret_cast<void **>(&ws.d_idx)));
