@@ -211,6 +211,9 @@ __device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *map, i
         "l"(map), "r"(s2u(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap *map, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
 // K-major operand tile, rows of 128 bytes, 128B swizzle, 8-row groups 1024 bytes apart
 __device__ __forceinline__ uint64_t umma_desc_sw128(const void *smem) {
     uint64_t d = (uint64_t)((s2u(smem) & 0x3ffffu) >> 4);
@@ -372,12 +375,19 @@ gemm_i8_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
             int it = 0;  // k-block counter across tiles
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int m0 = (tile % m_tiles) * G8_BM, n0 = (tile / m_tiles) * G8_BN;
+                // The count rows stream from HBM (each tile of them is used by only m_tiles CTAs):
+                // at ~2 us of latency the four stages in flight cannot feed the tensor pipe, so
+                // the rows of this CTA's NEXT tile are pulled into L2 one tile ahead.
+                const int nt = tile + gridDim.x;
+                const bool pre = nt < total_tiles && nt / m_tiles != tile / m_tiles;
+                const int n0n = (nt / m_tiles) * G8_BN;
                 for (int kb = 0; kb < nkb; kb++, it++) {
                     const int s = it % G8_STAGES;
                     mb_wait(&empty[s], ((it / G8_STAGES) & 1) ^ 1);
                     mb_expect(&full[s], (uint32_t)(G8_A_BYTES + G8_B_BYTES));
                     tma_load_2d(sA + s * G8_A_BYTES, &mapA, kb * G8_BK, m0, &full[s]);
                     tma_load_2d(sB + s * G8_B_BYTES, &mapB, kb * G8_BK, n0, &full[s]);
+                    if (pre) tma_prefetch_2d(&mapB, kb * G8_BK, n0n);
                 }
             }
         }
