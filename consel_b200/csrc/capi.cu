@@ -442,7 +442,7 @@ static int scaleboot_core(DevMatrix &m, int S, const int *bn, const int *bb, uns
         // index stream of the whole call in one buffer when it fits 64 GB and half of the free
         // device memory (C3: 38 GB of uint32 indices); otherwise batch by batch
         unsigned long long idx_budget = (unsigned long long)64 << 30;
-        {
+        if (idx_off[S] * idx_bytes((uint32_t)n) > ((unsigned long long)16 << 30)) {  // the query costs ~1 ms: large requests only
             size_t free_b = 0, total_b = 0;
             if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
                 idx_budget = std::min<unsigned long long>(idx_budget, (free_b + G().scratch_cap[0]) / 2);
