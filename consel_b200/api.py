@@ -188,6 +188,16 @@ class Reps:
         _check(load().cgpu_reps_upload(K, len(reps), _ip(bb), _ptr_array(reps), C.byref(h)))
         return cls(h, K, bb)
 
+    @classmethod
+    def upload_ptrs(cls, K: int, bb, ptrs) -> "Reps":
+        """Blocks given by raw addresses (host, or device memory of this process — the copy
+        kind is inferred): K x bb[s] doubles each, row-major."""
+        bb = np.ascontiguousarray(bb, dtype=np.int32)
+        arr = (C.c_void_p * len(bb))(*[C.c_void_p(int(p)) for p in ptrs])
+        h = C.c_void_p()
+        _check(load().cgpu_reps_upload(int(K), len(bb), _ip(bb), C.cast(arr, C.POINTER(C.POINTER(C.c_double))), C.byref(h)))
+        return cls(h, int(K), bb)
+
     def _local_cols(self):
         return [shard_range(int(b))[1] - shard_range(int(b))[0] for b in self.bb]
 

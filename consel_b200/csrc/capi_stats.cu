@@ -113,7 +113,7 @@ int cgpu_reps_upload(int K, int S, const int *bb, const double *const *rep, cgpu
         if (e == cudaSuccess && b1 > b0)
             e = cudaMemcpy2DAsync(r->d_rep[s], (size_t)(b1 - b0) * sizeof(double), rep[s] + b0,
                                   (size_t)bb[s] * sizeof(double), (size_t)(b1 - b0) * sizeof(double), K,
-                                  cudaMemcpyHostToDevice, st);
+                                  cudaMemcpyDefault, st);
         if (e != cudaSuccess) {
             set_error(CGPU_ECUDA, "reps_upload scale %d: %s", s, cudaGetErrorString(e));
             rc = CGPU_ECUDA;

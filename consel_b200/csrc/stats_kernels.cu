@@ -299,6 +299,131 @@ rowsum_multi_kernel(ScaleList sl, int nq, int q0, int nqt, int nsplit, const dou
     }
 }
 
+// Several thresholds per row, sorted: an element falls into exactly one interval
+// (t_(j-1), t_j] of the sorted thresholds, j = #{q : x > t_q}.  Each thread keeps a private
+// (count, min, max) per interval in shared memory and every threshold's (count, lo, hi) is
+// a prefix sum / prefix max / suffix min over the intervals afterwards: NQ compares and
+// three updates per element instead of NQ x (compare, count, max, min).  Exact as before
+// (integer counts, max and min are order independent).  Row edges are never needed here
+// (they come from the host cache).
+template <int NQ>
+__global__ void __launch_bounds__(RS_THREADS)
+rowsum_sorted_kernel(ScaleList sl, int nq, int q0, int nqt, int nsplit, const double *__restrict__ thr,
+                     cgpu_rowsum *__restrict__ part) {
+    const int row = blockIdx.x, sc = blockIdx.y, sp = blockIdx.z, S = gridDim.y;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int B = sl.B[sc];
+    const double *__restrict__ v = sl.stat[sc] + (size_t)row * B;
+    const int chunk = (B + nsplit - 1) / nsplit;
+    const int b_lo = sp * chunk, b_hi = min(B, b_lo + chunk);
+    constexpr int NI = NQ + 1;  // intervals
+    extern __shared__ __align__(16) unsigned char rss_raw[];
+    double *imin = reinterpret_cast<double *>(rss_raw);                 // [NI][RS_THREADS]
+    double *imax = imin + NI * RS_THREADS;                              // [NI][RS_THREADS]
+    unsigned int *icnt = reinterpret_cast<unsigned int *>(imax + NI * RS_THREADS);  // [NI][RS_THREADS]
+    __shared__ double s_t[NQ];
+    __shared__ int s_perm[NQ];
+    __shared__ unsigned long long s_cnt[RS_THREADS / 32][NQ];
+    __shared__ double s_lo[RS_THREADS / 32][NQ], s_hi[RS_THREADS / 32][NQ];
+    if (tid == 0) {  // insertion sort of <= 8 thresholds, remembering where each came from
+        for (int q = 0; q < NQ; q++) {
+            const double t = q < nq ? thr[(size_t)row * nqt + q0 + q] : CG_HUGE;
+            int p = q;
+            while (p > 0 && s_t[p - 1] > t) {
+                s_t[p] = s_t[p - 1];
+                s_perm[p] = s_perm[p - 1];
+                p--;
+            }
+            s_t[p] = t;
+            s_perm[p] = q;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < NI; j++) {
+        imin[j * RS_THREADS + tid] = CG_HUGE;
+        imax[j * RS_THREADS + tid] = -CG_HUGE;
+        icnt[j * RS_THREADS + tid] = 0;
+    }
+    __syncthreads();
+    double t[NQ];
+#pragma unroll
+    for (int q = 0; q < NQ; q++) t[q] = s_t[q];
+    auto take = [&](double x) {
+        if (x != x) return;  // NaN never counts and never becomes a neighbour (as fmax/fmin ignore it)
+        int j = 0;
+#pragma unroll
+        for (int q = 0; q < NQ; q++) j += x > t[q] ? 1 : 0;
+        const int e = j * RS_THREADS + tid;
+        icnt[e]++;
+        imin[e] = fmin(imin[e], x);
+        imax[e] = fmax(imax[e], x);
+    };
+    constexpr int U = 4;
+    int b = b_lo + tid;
+    for (; b + (U - 1) * RS_THREADS < b_hi; b += U * RS_THREADS) {
+        double x[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) x[u] = v[b + u * RS_THREADS];
+#pragma unroll
+        for (int u = 0; u < U; u++) take(x[u]);
+    }
+    for (; b < b_hi; b += RS_THREADS) take(v[b]);
+
+    // per thread: threshold q (sorted order) sees intervals 0..q below it and q+1..NQ above it
+    unsigned long long c64[NQ];
+    double lo[NQ], hi[NQ];
+    {
+        unsigned long long c = 0;
+        double l = -CG_HUGE;
+#pragma unroll
+        for (int q = 0; q < NQ; q++) {
+            c += icnt[q * RS_THREADS + tid];
+            l = fmax(l, imax[q * RS_THREADS + tid]);
+            c64[q] = c;
+            lo[q] = l;
+        }
+        double h = CG_HUGE;
+#pragma unroll
+        for (int q = NQ - 1; q >= 0; q--) {
+            h = fmin(h, imin[(q + 1) * RS_THREADS + tid]);
+            hi[q] = h;
+        }
+    }
+#pragma unroll
+    for (int off = 16; off; off >>= 1) {
+#pragma unroll
+        for (int q = 0; q < NQ; q++) {
+            c64[q] += __shfl_xor_sync(0xffffffffu, c64[q], off);
+            lo[q] = fmax(lo[q], __shfl_xor_sync(0xffffffffu, lo[q], off));
+            hi[q] = fmin(hi[q], __shfl_xor_sync(0xffffffffu, hi[q], off));
+        }
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int q = 0; q < NQ; q++) {
+            s_cnt[wid][q] = c64[q];
+            s_lo[wid][q] = lo[q];
+            s_hi[wid][q] = hi[q];
+        }
+    }
+    __syncthreads();
+    if (tid < NQ && s_perm[tid] < nq) {
+        unsigned long long c = 0;
+        double l = -CG_HUGE, h = CG_HUGE;
+        for (int w = 0; w < RS_THREADS / 32; w++) {
+            c += s_cnt[w][tid];
+            l = fmax(l, s_lo[w][tid]);
+            h = fmin(h, s_hi[w][tid]);
+        }
+        cgpu_rowsum r;
+        r.cnt = (double)c;
+        r.lo = l;
+        r.hi = h;
+        r.min1 = r.min2 = r.max1 = r.max2 = 0.0;  // filled from the host-side edge cache
+        part[(((size_t)row * S + sc) * nsplit + sp) * nqt + q0 + s_perm[tid]] = r;
+    }
+}
+
 __global__ void __launch_bounds__(128)
 rowsum_merge_kernel(const cgpu_rowsum *__restrict__ part, int total, int nsplit, int nq, cgpu_rowsum *__restrict__ out) {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;  // (row*S + sc)*nq + q
@@ -314,6 +439,8 @@ rowsum_merge_kernel(const cgpu_rowsum *__restrict__ part, int total, int nsplit,
     }
     out[e] = r;
 }
+
+static size_t rss_smem(int nq) { return (size_t)(nq + 1) * RS_THREADS * (8 + 8 + 4); }
 
 int launch_rowsum_all_scales(const double *const *d_stat, const int *B, int S, int cm, int nq, const double *d_thr,
                              cgpu_rowsum *d_part, cgpu_rowsum *d_out, int nsplit, cudaStream_t st, bool edges) {
@@ -339,6 +466,8 @@ int launch_rowsum_all_scales(const double *const *d_stat, const int *B, int S, i
         const int n = std::min(8, nq - q0);
         if (n <= 1) CGPU_RSM(1);
         else if (n <= 2) CGPU_RSM(2);
+        else if (!edges && n <= 4) rowsum_sorted_kernel<4><<<grid, RS_THREADS, rss_smem(4), st>>>(sl, n, q0, nq, nsplit, d_thr, d_part);
+        else if (!edges) rowsum_sorted_kernel<8><<<grid, RS_THREADS, rss_smem(8), st>>>(sl, n, q0, nq, nsplit, d_thr, d_part);
         else if (n <= 4) CGPU_RSM(4);
         else CGPU_RSM(8);
     }

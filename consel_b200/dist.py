@@ -77,6 +77,32 @@ def gather_columns(local: np.ndarray, bb: int, group=None) -> np.ndarray:
     return torch.cat(parts, dim=1).cpu().numpy()
 
 
+class _DevBlock:
+    """A rows x cols fp64 device block exposed through __cuda_array_interface__ (no copy)."""
+
+    def __init__(self, ptr: int, rows: int, cols: int, ld: int):
+        self.__cuda_array_interface__ = {"shape": (rows, cols), "typestr": "<f8", "data": (int(ptr), False), "version": 2,
+                                         "strides": (ld * 8, 8)}
+
+
+def gather_columns_device(ptr: int, rows: int, cols: int, ld: int, bb: int, group=None):
+    """gather_columns for a block that already lives on this rank's GPU (cgpu_reps_devptr):
+    NCCL all-gather straight from the library's memory, result a contiguous rows x bb device tensor."""
+    import torch
+    dist = _dist()
+    world = dist.get_world_size(group)
+    dev = _device_for(group)
+    mine = torch.as_tensor(_DevBlock(ptr, rows, cols, ld), device=dev).contiguous()
+    if world == 1:
+        return mine
+    parts = []
+    for r in range(world):
+        b0, b1 = shard_range(bb, r, world)
+        parts.append(torch.empty((rows, b1 - b0), dtype=torch.float64, device=dev))
+    dist.all_gather(parts, mine, group=group) if len({p.shape for p in parts}) == 1 else _uneven_gather(parts, mine, group)
+    return torch.cat(parts, dim=1).contiguous()
+
+
 def _uneven_gather(parts, mine, group):
     dist = _dist()
     rank = dist.get_rank(group)

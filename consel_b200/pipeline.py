@@ -148,13 +148,23 @@ def consel(reps: api.Reps, datvec, rr, bb, ass=None, alpha=(0.05, 0.10, 0.5, 0.9
     t0 = time.perf_counter()
     if do_mc:
         if dist_mode:  # the tests need every replicate of scale i0 on one device (sequential row sums)
+            import torch
             import torch.distributed as dist
-            blocks = reps.download()
-            whole = cdist.gather_columns(blocks[i0], nb0)
-            api.set_shard(0, 1)
-            one = api.Reps.upload([whole])
-            kh, sh, wkh, wsh = one.mctest(0, datvec, ptr, idx, varadd)
+            whole_d = None
+            if dist.get_backend() == "nccl":  # all-gather straight from the library's device block
+                p, rows, cols, ld = reps.devptr(i0)
+                whole_d = cdist.gather_columns_device(p, rows, cols, ld, nb0)
+                torch.cuda.synchronize()
+                api.set_shard(0, 1)
+                one = api.Reps.upload_ptrs(K, [nb0], [whole_d.data_ptr()])
+            else:  # CPU process groups (tests): through the host
+                blocks = reps.download()
+                whole = cdist.gather_columns(blocks[i0], nb0)
+                api.set_shard(0, 1)
+                one = api.Reps.upload([whole])
+            kh, sh, wkh, wsh = one.mctest(0, datvec, ptr, idx, varadd)  # returns after the library stream drained
             one.free()
+            whole_d = None
             api.set_shard(dist.get_rank(), dist.get_world_size())
         else:
             kh, sh, wkh, wsh = reps.mctest(i0, datvec, ptr, idx, varadd)
