@@ -38,23 +38,20 @@ def combine_rowsums(q: np.ndarray, group=None) -> np.ndarray:
     if world == 1:
         return q
     dev = _device_for(group)
+    # ONE collective per fit round: every rank contributes its packed (7, N) summary block and
+    # reduces the gathered copies itself (sum / max / min / two-smallest / two-largest are all
+    # exact and order independent)
     flat = np.stack([np.ascontiguousarray(q[f], dtype=np.float64).ravel() for f in FIELDS])  # (7, N)
     t = torch.from_numpy(flat).to(dev)
-    cnt, lo, hi = t[0].clone(), t[1].clone(), t[2].clone()
-    dist.all_reduce(cnt, op=dist.ReduceOp.SUM, group=group)
-    dist.all_reduce(lo, op=dist.ReduceOp.MAX, group=group)
-    dist.all_reduce(hi, op=dist.ReduceOp.MIN, group=group)
-    # the two smallest / two largest of the union: gather the per-rank pairs (2*world values)
-    edges = t[3:7].contiguous()
-    gathered = [torch.empty_like(edges) for _ in range(world)]
-    dist.all_gather(gathered, edges, group=group)
-    g = torch.stack(gathered)  # (world, 4, N)
-    mins = torch.cat([g[:, 0], g[:, 1]]).sort(dim=0).values[:2]
-    maxs = torch.cat([g[:, 2], g[:, 3]]).sort(dim=0, descending=True).values[:2]
+    parts = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(parts, t, group=group)
+    g = torch.stack(parts).cpu().numpy()  # (world, 7, N)
+    mins = np.sort(np.concatenate([g[:, 3], g[:, 4]]), axis=0)[:2]
+    maxs = np.sort(np.concatenate([g[:, 5], g[:, 6]]), axis=0)[-2:][::-1]
+    res = [g[:, 0].sum(axis=0), g[:, 1].max(axis=0), g[:, 2].min(axis=0), mins[0], mins[1], maxs[0], maxs[1]]
     out = np.empty_like(q)
-    res = [cnt, lo, hi, mins[0], mins[1], maxs[0], maxs[1]]
     for f, v in zip(FIELDS, res):
-        out[f] = v.cpu().numpy().reshape(q.shape)
+        out[f] = v.reshape(q.shape)
     return out
 
 

@@ -146,25 +146,27 @@ def consel(reps: api.Reps, datvec, rr, bb, ass=None, alpha=(0.05, 0.10, 0.5, 0.9
     se = np.zeros((cm, 8))
     pv[:, 1] = pp
     t0 = time.perf_counter()
+    one = None  # the whole scale-i0 block on this rank (distributed runs): KH/SH tests and the median need it
+    whole_d = None
+    if dist_mode and (do_mc or (do_au and kk >= 2)):
+        import torch
+        import torch.distributed as dist
+        if dist.get_backend() == "nccl":  # all-gather straight from the library's device block
+            p, rows, cols, ld = reps.devptr(i0)
+            whole_d = cdist.gather_columns_device(p, rows, cols, ld, nb0)
+            torch.cuda.synchronize()
+            api.set_shard(0, 1)
+            one = api.Reps.upload_ptrs(K, [nb0], [whole_d.data_ptr()])
+        else:  # CPU process groups (tests): through the host
+            blocks = reps.download()
+            whole = cdist.gather_columns(blocks[i0], nb0)
+            api.set_shard(0, 1)
+            one = api.Reps.upload([whole])
+        api.set_shard(dist.get_rank(), dist.get_world_size())
     if do_mc:
-        if dist_mode:  # the tests need every replicate of scale i0 on one device (sequential row sums)
-            import torch
-            import torch.distributed as dist
-            whole_d = None
-            if dist.get_backend() == "nccl":  # all-gather straight from the library's device block
-                p, rows, cols, ld = reps.devptr(i0)
-                whole_d = cdist.gather_columns_device(p, rows, cols, ld, nb0)
-                torch.cuda.synchronize()
-                api.set_shard(0, 1)
-                one = api.Reps.upload_ptrs(K, [nb0], [whole_d.data_ptr()])
-            else:  # CPU process groups (tests): through the host
-                blocks = reps.download()
-                whole = cdist.gather_columns(blocks[i0], nb0)
-                api.set_shard(0, 1)
-                one = api.Reps.upload([whole])
+        if dist_mode:  # sequential row sums over all replicates of scale i0
+            api.set_shard(0, 1)
             kh, sh, wkh, wsh = one.mctest(0, datvec, ptr, idx, varadd)  # returns after the library stream drained
-            one.free()
-            whole_d = None
             api.set_shard(dist.get_rank(), dist.get_world_size())
         else:
             kh, sh, wkh, wsh = reps.mctest(i0, datvec, ptr, idx, varadd)
@@ -191,7 +193,13 @@ def consel(reps: api.Reps, datvec, rr, bb, ass=None, alpha=(0.05, 0.10, 0.5, 0.9
     if do_au and kk >= 2:
         t0 = time.perf_counter()
         rank_k = np.full(cm, nb0 // 2, dtype=np.int32)
-        med = _dist_order_stat(reps, i0, rank_k) if dist_mode else reps.order_stat(i0, rank_k)
+        if dist_mode:  # the median of the whole scale-i0 rows, from the gathered block
+            api.set_shard(0, 1)
+            one.stats_build(ptr, idx)
+            med = one.order_stat(0, rank_k)
+            api.set_shard(dist.get_rank(), dist.get_world_size())
+        else:
+            med = reps.order_stat(i0, rank_k)
         r0 = np.ascontiguousarray(q0[:, :, 0])
         alpha = np.ascontiguousarray(alpha, dtype=np.float64)
         pv2, se2, ax7 = np.zeros((cm, 2)), np.zeros((cm, 2)), np.zeros((cm, 7))
@@ -218,6 +226,8 @@ def consel(reps: api.Reps, datvec, rr, bb, ass=None, alpha=(0.05, 0.10, 0.5, 0.9
         pv[:, 6:8], se[:, 6:8] = pv2, se2
         out.update(ax=ax7, ci=ci6 if confidence else None, alpha=alpha, ret=ret)
         timing["au_s"] = time.perf_counter() - t0
+    if one is not None:
+        one.free()
     return out
 
 
