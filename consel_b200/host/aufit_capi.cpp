@@ -3,6 +3,11 @@
 // reference's golden .rep rows).  Not used by the programs themselves.
 #include "aufit.h"
 #include "specfun.h"
+#include "refio.h"
+
+#include <cstdio>
+#include <string>
+#include <vector>
 
 extern "C" {
 
@@ -56,4 +61,20 @@ void aufit_ci_get(void *h, double *out) {
 double aufit_pochisq(double x, int df) { return specfun::pochisq(x, df); }
 double aufit_pnorm(double x) { return specfun::pnorm(x); }
 double aufit_qnorm(double p) { return specfun::qnorm(p); }
+}
+
+// test seam for the matrix text reader (tests/test_host_fit.py): reads a .mt file, returns
+// the shape, copies up to `cap` values, and reports the token that follows the matrix
+extern "C" int refio_test_read_mat(const char *path, int *m, int *n, double *out, long long cap, char *next_word, int next_cap) {
+    FILE *fp = fopen(path, "r");
+    if (!fp) return -1;
+    int mm = 0, nn = 0;
+    std::vector<double> a = refio::read_mat(fp, &mm, &nn);
+    *m = mm;
+    *n = nn;
+    for (long long i = 0; i < cap && i < (long long)a.size(); i++) out[i] = a[i];
+    std::string w = refio::read_word(fp);
+    snprintf(next_word, next_cap, "%s", w.c_str());
+    fclose(fp);
+    return 0;
 }

@@ -3,6 +3,10 @@
 // copied: std::vector storage, no global scratch, C++ I/O helpers.
 #include "refio.h"
 
+#include <algorithm>
+#include <sys/stat.h>
+#include <thread>
+#include <charconv>
 #include <cctype>
 #include <cmath>
 #include <cstdarg>
@@ -142,6 +146,94 @@ std::vector<std::string> read_svec(FILE *fp) {
     for (int i = 0; i < m; i++) a.push_back(read_word(fp));
     return a;
 }
+// Parallel text parse of `count` doubles from a regular file (a K=1000 x n=10^5
+// matrix is 2 GB of text, minutes of fscanf).  The rest of the file is read into memory, cut
+// at line ends (a '#' comment never spans a line end), tokenised and converted with
+// std::from_chars on all host threads.  Anything the strict tokenizer does not understand
+// (hex floats, trailing garbage, too few values) makes it give up WITHOUT consuming input,
+// and the caller falls back to the fscanf loop, so error behaviour stays the reference's.
+static bool read_doubles_parallel(FILE *fp, double *out, size_t count) {
+    if (count < (1u << 16)) return false;
+    struct stat st;
+    const int fd = fileno(fp);
+    if (fd < 0 || fstat(fd, &st) != 0 || !S_ISREG(st.st_mode)) return false;
+    const long pos = ftell(fp);
+    if (pos < 0 || st.st_size <= pos) return false;
+    const size_t bytes = (size_t)(st.st_size - pos);
+    std::vector<char> buf(bytes + 1);
+    if (fread(buf.data(), 1, bytes, fp) != bytes) {
+        fseek(fp, pos, SEEK_SET);
+        return false;
+    }
+    buf[bytes] = '\n';
+    const char *base = buf.data();
+    const int nthr = (int)std::max(1u, std::min(64u, std::thread::hardware_concurrency()));
+    std::vector<size_t> cut(nthr + 1, bytes);
+    cut[0] = 0;
+    for (int t = 1; t < nthr; t++) {
+        size_t c = bytes / nthr * t;
+        while (c < bytes && base[c] != '\n') c++;
+        cut[t] = c < bytes ? c + 1 : bytes;
+    }
+    // tokens of [lo, hi): every value, or stop as soon as `limit` values were taken
+    struct Part {
+        std::vector<double> vals;
+        size_t end = 0;  // offset just behind the last token taken
+        bool ok = true;
+    };
+    auto parse = [&](size_t lo, size_t hi, size_t limit, Part *p) {
+        const char *c = base + lo, *e = base + hi;
+        while (c < e && p->vals.size() < limit) {
+            if (isspace((unsigned char)*c)) { c++; continue; }
+            if (*c == '#') {
+                while (c < e && *c != '\n') c++;
+                continue;
+            }
+            const char *tok = c;
+            while (c < e && !isspace((unsigned char)*c)) c++;
+            const char *b = tok;
+            if (*b == '+') b++;
+            double v;
+            auto r = std::from_chars(b, c, v);
+            if (r.ec != std::errc() || r.ptr != c || (b + 1 < c && b[0] == '0' && (b[1] == 'x' || b[1] == 'X'))) {
+                p->ok = false;
+                return;
+            }
+            p->vals.push_back(v);
+            p->end = (size_t)(c - base);
+        }
+    };
+    std::vector<Part> parts(nthr);
+    {
+        std::vector<std::thread> th;
+        for (int t = 0; t < nthr; t++) th.emplace_back([&, t] { parse(cut[t], cut[t + 1], ~(size_t)0, &parts[t]); });
+        for (auto &x : th) x.join();
+    }
+    // the matrix may be followed by other data: take exactly `count` values in file order
+    size_t have = 0, end = 0;
+    bool ok = true;
+    for (int t = 0; t < nthr && have < count; t++) {
+        if (!parts[t].ok && parts[t].vals.size() < count - have) { ok = false; break; }
+        const size_t take = std::min(parts[t].vals.size(), count - have);
+        if (take == parts[t].vals.size()) {
+            end = parts[t].end ? parts[t].end : end;
+        } else {  // the matrix ends inside this part: find where, sequentially
+            Part q;
+            parse(cut[t], cut[t + 1], take, &q);
+            if (!q.ok || q.vals.size() != take) { ok = false; break; }
+            end = q.end;
+        }
+        memcpy(out + have, parts[t].vals.data(), take * sizeof(double));
+        have += take;
+    }
+    if (!ok || have != count) {
+        fseek(fp, pos, SEEK_SET);
+        return false;
+    }
+    fseek(fp, pos + (long)end, SEEK_SET);
+    return true;
+}
+
 std::vector<double> read_mat(FILE *fp, int *mp, int *np) {
     int m = read_int(fp), n = read_int(fp);
     if (*mp > 0 && *mp != m) die("size of rows mismatch in mat");
@@ -149,7 +241,8 @@ std::vector<double> read_mat(FILE *fp, int *mp, int *np) {
     std::vector<double> a;
     if ((long long)m * n == 0) return a;
     a.resize((size_t)m * n);
-    for (size_t e = 0; e < a.size(); e++) a[e] = read_double(fp);
+    if (!read_doubles_parallel(fp, a.data(), a.size()))
+        for (size_t e = 0; e < a.size(); e++) a[e] = read_double(fp);
     *mp = m;
     *np = n;
     return a;

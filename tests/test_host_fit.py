@@ -117,3 +117,40 @@ def test_distribution_functions(fit):
     assert abs(fit.aufit_qnorm(0.975) - 1.959963984540054) < 1e-6
     assert abs(fit.aufit_pochisq(3.841458820694124, 1) - 0.05) < 1e-5
     assert fit.aufit_pochisq(0.0, 3) == 1.0
+
+
+def test_parallel_matrix_reader_equals_token_reader(tmp_path):
+    """refio::read_mat switches to the parallel from_chars parser for large regular files; it must
+    return exactly what the fscanf loop returns, leave the stream behind the matrix, and fall back
+    (same values) when a token is outside its grammar."""
+    import ctypes as C
+    import numpy as np
+    lib = C.CDLL(str(ROOT / "consel_b200" / "bin" / "libaufit_test.so"))
+    lib.refio_test_read_mat.argtypes = [C.c_char_p, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double), C.c_longlong,
+                                        C.c_char_p, C.c_int]
+    rng = np.random.default_rng(5)
+    m, n = 40, 3000  # 120000 values: above the parallel threshold
+    a = -np.exp(rng.uniform(-3, 4, size=(m, n)))
+    a[0, 0], a[1, 7], a[2, 2] = 0.0, -np.inf, 1e-310
+
+    def write(path, hexfirst=False):
+        with open(path, "w") as f:
+            f.write("# a comment before the header\n%d %d\n" % (m, n))
+            for i in range(m):
+                f.write("# row: %d\n" % i)
+                for j in range(n):
+                    tok = float(a[i, j]).hex() if (hexfirst and i == 3 and j == 5) else ("+%.17g" % a[i, j] if a[i, j] > 0 else "%.17g" % a[i, j])
+                    f.write(tok + ("\n" if j % 5 == 4 else "  # c\n" if j % 997 == 0 else " "))
+            f.write("\nTRAILER 1 2 3\n")
+
+    for hexfirst in (False, True):
+        p = tmp_path / ("m%d.mt" % hexfirst)
+        write(p, hexfirst)
+        out = np.zeros(m * n)
+        mm, nn = C.c_int(0), C.c_int(0)
+        word = C.create_string_buffer(64)
+        assert lib.refio_test_read_mat(str(p).encode(), C.byref(mm), C.byref(nn), out.ctypes.data_as(C.POINTER(C.c_double)),
+                                       m * n, word, 64) == 0
+        assert (mm.value, nn.value) == (m, n)
+        assert np.array_equal(out.view(np.uint64), a.ravel().view(np.uint64))
+        assert word.value == b"TRAILER"
