@@ -116,6 +116,32 @@ hist_group_kernel(const void *__restrict__ idx_v, int n, int NP, int bn, int nb,
             if (SRC != 1) {
                 const uint32_t *src32 = static_cast<const uint32_t *>(idx_v) + (size_t)r * bn;
                 const uint16_t *src16 = static_cast<const uint16_t *>(idx_v) + (size_t)r * bn;
+                if (SRC == 2 && HALGO == 1) {
+                    // uint16 indices, atomic byte histogram: each warp owns a contiguous segment of the
+                    // replicate's draws and reads it with 16-byte loads (8 indices per lane), all updates
+                    // unconditional; a scalar head (up to the 16-byte boundary) and tail frame the body
+                    unsigned *h32 = reinterpret_cast<unsigned *>(hist);
+                    auto add = [&](uint32_t k) { atomicAdd(h32 + (k >> 2), 1u << ((k & 3u) * 8u)); };
+                    const int seg = (bn + WPR - 1) / WPR;
+                    int i = sub * seg;
+                    const int hi = min(bn, i + seg);
+                    const int head = min(hi - i, (int)((16 - (reinterpret_cast<uintptr_t>(src16 + i) & 15)) & 15) / 2);
+                    if (lane < head) add(src16[i + lane]);
+                    i += max(head, 0);
+                    if (i + 256 <= hi) {
+                        uint4 v = __ldg(reinterpret_cast<const uint4 *>(src16 + i + lane * 8));
+                        for (; i + 256 <= hi; i += 256) {
+                            uint4 nx = v;  // the next 8 indices are in flight while these are counted
+                            if (i + 512 <= hi) nx = __ldg(reinterpret_cast<const uint4 *>(src16 + i + 256 + lane * 8));
+                            add(v.x & 0xffffu); add(v.x >> 16);
+                            add(v.y & 0xffffu); add(v.y >> 16);
+                            add(v.z & 0xffffu); add(v.z >> 16);
+                            add(v.w & 0xffffu); add(v.w >> 16);
+                            v = nx;
+                        }
+                    }
+                    for (int j = i + lane; j < hi; j += 32) add(src16[j]);
+                } else
                 // 8 independent index loads in flight per lane before the histogram updates
                 // (the loop is otherwise bound by global-load latency)
                 for (int i0 = sub * 256; i0 < bn; i0 += WPR * 256) {
