@@ -17,6 +17,8 @@
 //   mt_draw_kernel   227 lanes per chunk of 2^m draws: block regeneration with the
 //                    three dependent phases of next_state chained in registers (one
 //                    barrier per 624 draws), tempering, site index, coalesced stores.
+#include <cmath>
+
 #include "cgpu_internal.h"
 
 namespace cgpu {
@@ -178,9 +180,21 @@ int launch_mt_jump(uint32_t *d_states, const int2 *d_pairs, const uint32_t *d_po
     }
     if (nocts <= 0) return CGPU_OK;  // the zero polynomial cannot occur (x^J mod phi is never 0)
     // slice the position list over enough CTAs to cover the SMs when few windows jump
-    int sms = G().sm_count > 0 ? G().sm_count : 148;
+    // Slices of the position list per jump: enough CTAs to fill the SMs while the tree is narrow,
+    // and for wide levels the count that wastes the least of the last wave (2 CTAs per SM are
+    // resident; every extra slice re-generates part of the sequence, ~4 % of a jump).
+    const int sms = G().sm_count > 0 ? G().sm_count : 148;
+    const int slots = 2 * sms;
     int slices = 1;
-    while (slices < 16 && count * slices < sms) slices *= 2;
+    double best = 1e300;
+    for (int sl = 1; sl <= 16; sl++) {
+        const double waves = std::ceil((double)count * sl / slots) / sl;
+        const double cost = waves * (1.0 + 0.04 * (sl - 1));
+        if (cost < best - 1e-9) {
+            best = cost;
+            slices = sl;
+        }
+    }
     int ops = (nocts + slices - 1) / slices;
     mt_jump_kernel<<<dim3(count, slices), JUMP_THREADS, smem, st>>>(d_states, d_pairs, reinterpret_cast<const uint4 *>(d_pos),
                                                                     ops, nocts);
