@@ -579,7 +579,7 @@ static int scaleboot_core(DevMatrix &m, int S, const int *bn, const int *bb, uns
             pt.begin(3);
             if (i8)
                 CGPU_TRY(launch_contract_i8(m, fuse_hist ? d_cnt_all + cnt_off[s] : reinterpret_cast<const unsigned char *>(ws.d_counts[buf]), nbat,
-                                            (nbat + 255) / 256 * 256, d_partial, r, reps->d_rep[s], reps->nb[s], a, st, &pt));
+                                            (nbat + 255) / 256 * 256, d_partial, r, reps->d_rep[s], reps->nb[s], a, st, &pt, bn[s]));
             else
                 CGPU_TRY(launch_contract(m, ws.d_counts[buf], nbat, r, reps->d_rep[s], reps->nb[s], a, sum_mode, st));
             pt.end();
@@ -801,6 +801,7 @@ int cgpu_set_option(const char *name, int value) {
     else if (!strcmp(name, "i8_fuse")) g.opt_i8_fuse = value;
     else if (!strcmp(name, "draw_fuse")) g.opt_draw_fuse = value;
     else if (!strcmp(name, "stage")) g.opt_stage = value;
+    else if (!strcmp(name, "i8_dbg")) g.opt_i8_dbg = value;
     else if (!strcmp(name, "chunk_log2")) g.opt_chunk_log2 = value;
     else {
         set_error(CGPU_EINVAL, "unknown option %s", name);

@@ -84,7 +84,7 @@ struct Globals {
     void *scratch[4] = {nullptr, nullptr, nullptr, nullptr};
     size_t scratch_cap[4] = {0, 0, 0, 0};
     // tuning switches (cgpu_set_option); -1 = built-in default
-    int opt_overlap = -1, opt_hist_algo = -1, opt_contract_algo = -1, opt_i8_oneshot = -1, opt_draw_nch = -1, opt_chunk_log2 = -1, opt_i8_fuse = -1, opt_draw_fuse = -1, opt_stage = -1;
+    int opt_overlap = -1, opt_hist_algo = -1, opt_contract_algo = -1, opt_i8_oneshot = -1, opt_draw_nch = -1, opt_chunk_log2 = -1, opt_i8_fuse = -1, opt_draw_fuse = -1, opt_stage = -1, opt_i8_dbg = -1;
 };
 Globals &G();
 int ensure_init();
@@ -196,7 +196,8 @@ int launch_contract(const DevMatrix &m, const unsigned long long *d_counts, int 
 int fx_prepare(DevMatrix &m, cudaStream_t st);
 struct PhaseTimer;
 int launch_contract_i8(const DevMatrix &m, const unsigned char *d_counts_rows, int nb, int nb_pad, int *d_partial,
-                       double r, double *d_rep, int ldrep, int col0, cudaStream_t st, PhaseTimer *pt = nullptr);
+                       double r, double *d_rep, int ldrep, int col0, cudaStream_t st, PhaseTimer *pt = nullptr,
+                       int max_draws = 1 << 30 /* draws per replicate (bounds the digit sums) */);
 
 // accumulates device time per phase over many (start, stop) event pairs
 struct PhaseTimer {

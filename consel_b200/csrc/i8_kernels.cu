@@ -158,24 +158,51 @@ struct FxEpilogue {
     double r;
     FxScale sc;
     int K, S, nb, ldrep, col0;
+    int dbg;  // measurement only: 1 = no conversion/division, 2 = no arithmetic at all, 3 = no transpose either
 };
 
 // one 32 x 32 block of digit sums (rows = (tree, digit), transposed in `tile`, stride 33):
 // lane l finishes replicate column b for each of the 32/S trees of the block
+// S <= 8 on the fused path: the digits fold into two 64-bit groups g1 (digits 4..7) and g0
+// (digits 0..3), |g| < 2^31 * n' < 2^53 (n' < 2^22 is checked on the host), so both convert
+// to fp64 exactly and ONE fused multiply-add rounds the exact value g1*2^32 + g0 once.
+template <int S>
+__device__ __forceinline__ double fx_digits_to_double(const int *d, int stride) {
+    long long g0 = 0, g1 = 0;
+#pragma unroll
+    for (int sdig = (S < 4 ? S : 4) - 1; sdig >= 0; sdig--) g0 = g0 * 256 + (long long)d[sdig * stride];
+    if (S <= 4) return (double)g0;
+#pragma unroll
+    for (int sdig = S - 1; sdig >= 4; sdig--) g1 = g1 * 256 + (long long)d[sdig * stride];
+    return __fma_rn((double)g1, 4294967296.0, (double)g0);
+}
+
 template <int S>
 __device__ __forceinline__ void fx_finish_block(const int *tile, int lane, int k0, int b, const FxEpilogue &ep) {
+    static_assert(S <= 8, "the fused recombination folds at most two 64-bit groups");
     constexpr int TREES = 32 / S;
+    // the TREES results of this lane are independent: every stage is done for all of them
+    // before the next one, so the dependent chains (fold, conversion, division) overlap
+    // instead of running back to back with only two warps per scheduler to hide them
+    double x[TREES];
+#pragma unroll
+    for (int j = 0; j < TREES; j++) x[j] = fx_digits_to_double<S>(tile + (j * S) * 33 + lane, 33) * ep.sc.mul;
+    if (ep.dbg == 1) {
+#pragma unroll
+        for (int j = 0; j < TREES; j++)
+            if (k0 + j < ep.K && b < ep.nb) ep.rep[(size_t)(k0 + j) * ep.ldrep + ep.col0 + b] = x[j];
+        return;
+    }
+#pragma unroll
+    for (int j = 0; j < TREES; j++) x[j] = __ddiv_rn(x[j], ep.r);
 #pragma unroll
     for (int j = 0; j < TREES; j++) {
         const int k = k0 + j;
-        if (k < ep.K && b < ep.nb) {
-            const __int128 t = fx_digits_to_int<S>(tile + (j * S) * 33 + lane, 33);
-            const double x = fx_scale(i128_to_double_rn(t), ep.sc);
-            ep.rep[(size_t)k * ep.ldrep + ep.col0 + b] = __ddiv_rn(x, ep.r);
-        }
+        if (k < ep.K && b < ep.nb) ep.rep[(size_t)k * ep.ldrep + ep.col0 + b] = x[j];
     }
 }
 
+// ------------------------------------------------------------------ tcgen05 GEMM tiles
 constexpr int G8_BM = 128, G8_BN = 256, G8_BK = 128;  // BK in bytes == int8 elements (one 128B swizzle atom)
 constexpr int G8_STAGES = 4;
 constexpr int G8_THREADS = 192;  // one-shot kernel: warp0 TMA, warp1 MMA (+TMEM alloc), warps 2-5 epilogue
@@ -379,7 +406,8 @@ gemm_i8_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
                 // at ~2 us of latency the four stages in flight cannot feed the tensor pipe, so
                 // the rows of this CTA's NEXT tile are pulled into L2 one tile ahead.
                 const int nt = tile + gridDim.x;
-                const bool pre = nt < total_tiles && nt / m_tiles != tile / m_tiles;
+                // (short tiles only: a long tile's rows would evict the operands in use from L2)
+                const bool pre = NP <= 8192 && nt < total_tiles && nt / m_tiles != tile / m_tiles;
                 const int n0n = (nt / m_tiles) * G8_BN;
                 for (int kb = 0; kb < nkb; kb++, it++) {
                     const int s = it % G8_STAGES;
@@ -455,8 +483,10 @@ gemm_i8_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
                 // row (k*S+s) of 32 replicates; transpose through shared memory so that lane l
                 // owns replicate column c+l and walks the S digits of each of the 32/S trees.
                 __syncwarp();
+                if (ep.dbg != 3) {
 #pragma unroll
-                for (int i = 0; i < 32; i++) tile_s[lane * 33 + i] = (int)v[i];
+                    for (int i = 0; i < 32; i++) tile_s[lane * 33 + i] = (int)v[i];
+                }
                 __syncwarp();
                 const int b = n0 + c + lane;  // replicate (column of the batch)
                 const int k0 = (m0 + q * 32) / ep.S;
@@ -464,8 +494,7 @@ gemm_i8_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
                     case 1: fx_finish_block<1>(tile_s, lane, k0, b, ep); break;
                     case 2: fx_finish_block<2>(tile_s, lane, k0, b, ep); break;
                     case 4: fx_finish_block<4>(tile_s, lane, k0, b, ep); break;
-                    case 8: fx_finish_block<8>(tile_s, lane, k0, b, ep); break;
-                    default: fx_finish_block<16>(tile_s, lane, k0, b, ep); break;
+                    default: fx_finish_block<8>(tile_s, lane, k0, b, ep); break;
                 }
             }
         }
@@ -548,7 +577,7 @@ int fx_prepare(DevMatrix &m, cudaStream_t st) {
 
 // counts: plain rows [nb_pad][NP] uint8 (nb_pad multiple of 256, padding rows zero)
 int launch_contract_i8(const DevMatrix &m, const unsigned char *d_counts_rows, int nb, int nb_pad, int *d_partial,
-                       double r, double *d_rep, int ldrep, int col0, cudaStream_t st, PhaseTimer *pt) {
+                       double r, double *d_rep, int ldrep, int col0, cudaStream_t st, PhaseTimer *pt, int max_draws) {
     if (nb <= 0) return CGPU_OK;
     // int32 accumulators: |sum_j c*d| <= 128 * (draws per replicate)
     CUtensorMap mapA, mapB;
@@ -564,7 +593,9 @@ int launch_contract_i8(const DevMatrix &m, const unsigned char *d_counts_rows, i
     const bool one_shot = G().opt_i8_oneshot >= 0 ? G().opt_i8_oneshot != 0 : env_one_shot;
     // the recombination runs in the GEMM epilogue when the digits of a tree stay inside one
     // 32-row epilogue slab ("i8_fuse" 0 keeps the two-kernel form for measurements)
-    const bool fused = !one_shot && 32 % m.fxS == 0 && G().opt_i8_fuse != 0;
+    // (S <= 8, a scale 2^-F that is a normal double, and group sums that are exact in fp64)
+    const bool fused = !one_shot && m.fxS <= 8 && 8 % m.fxS == 0 && G().opt_i8_fuse != 0 && m.fxF > -1000 && m.fxF < 1000 &&
+                       max_draws < (1 << 22);
     if (pt) pt->begin(6, st);
     const int m_tiles = (int)(m.fxMpad / G8_BM), n_tiles = nb_pad / G8_BN;
     if (one_shot) {
@@ -574,7 +605,7 @@ int launch_contract_i8(const DevMatrix &m, const unsigned char *d_counts_rows, i
         const int sms = G().sm_count > 0 ? G().sm_count : 148;
         const int grid = std::min(sms, m_tiles * n_tiles);
         FxEpilogue ep{fused ? d_rep : nullptr, r, {(m.fxF > -1000 && m.fxF < 1000) ? std::ldexp(1.0, -m.fxF) : 0.0, m.fxF},
-                      m.K, m.fxS, nb, ldrep, col0};
+                      m.K, m.fxS, nb, ldrep, col0, G().opt_i8_dbg > 0 ? G().opt_i8_dbg : 0};
         gemm_i8_persistent_kernel<<<grid, G8P_THREADS, G8_SMEM, st>>>(mapA, mapB, m.NP, d_partial, nb_pad, m_tiles, n_tiles, ep);
     }
     CGPU_LAUNCH_CHECK();
