@@ -15,10 +15,15 @@
 // Kernels
 //   fx_scan_kernel     exponent range of L (lowest set mantissa bit, highest magnitude bit)
 //   fx_slice_kernel    L -> digit matrix A[(k*S+s)][j] (int8, K-major rows of NP bytes)
-//   gemm_i8_kernel     D[128 x 256] tiles: TMA (128B swizzle) -> smem ring -> tcgen05.mma
-//                      kind::i8 -> TMEM -> tcgen05.ld -> int32 partial sums in HBM
-//   fx_combine_kernel  exact 128-bit recombination of the S partial sums, one rounding,
-//                      scale, divide by r
+//   gemm_i8_persistent_kernel
+//                      D[128 x 256] tiles, one CTA per SM: TMA (128B swizzle) -> 4-stage smem ring
+//                      -> tcgen05.mma kind::i8 -> two TMEM accumulator stages -> eight epilogue
+//                      warps (tcgen05.ld).  The epilogue either stores the int32 digit sums or,
+//                      for S in {1,2,4,8}, finishes the job in place: transpose through shared
+//                      memory, exact fold of the digits, ONE rounding (an FMA of two exact fp64
+//                      group sums), scale, divide by r, coalesced store of the replicate block.
+//   gemm_i8_kernel     one tile per CTA (kept as the "i8_oneshot" measurement variant)
+//   fx_combine_kernel  the recombination as a separate pass over the int32 sums (other S)
 #include <cuda.h>
 #include <stdlib.h>
 

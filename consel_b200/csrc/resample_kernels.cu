@@ -7,14 +7,16 @@
 // fetches the counts of its 8 replicates at a site with ONE broadcast 8-byte load.
 //
 // Two ways of producing it:
-//   hist_group_kernel  n <= HIST_SMEM_SITES: one CTA per replicate group, one WARP per
-//                      replicate, warp-private byte histogram in shared memory.  Lanes
-//                      of a warp resolve collisions with match.any, so no atomics are
-//                      needed; the CTA then interleaves its eight histograms and writes
-//                      the BJ8 words with coalesced 32-byte stores.
-//   hist_global_kernel larger n (the histogram of one replicate no longer fits shared
-//                      memory): one thread per draw, 32-bit atomic add on the word that
-//                      holds the byte.
+//   hist_group_kernel  histograms in shared memory.  Default: one CTA per replicate group, one
+//                      WARP per replicate with a private byte histogram, fire-and-forget shared
+//                      atomics on the packed bytes (hist_algo 1; 0 = match.any de-duplication and
+//                      2 = tag arbitration are kept for measurements), row checksum against
+//                      overflow, then either the interleaved BJ8 words (fp64 contraction) or plain
+//                      byte rows (tensor-core contraction) are written with coalesced stores.
+//                      Byte rows of long alignments (up to 225280 sites) let 2, 4 or 8 warps share
+//                      one histogram.
+//   hist_global_kernel everything else (BJ8 above 28160 sites, rows above 225280): one thread per
+//                      draw, 32-bit atomic add on the global word that holds the byte.
 // Draw sources: the index buffer written by mt_draw_kernel (reference stream) or a
 // counter-based Philox4x32-10 keyed by (seed; scale, replicate) — Salmon, Moraes, Dror,
 // Shaw, "Parallel random numbers: as easy as 1, 2, 3", SC'11.
