@@ -247,14 +247,11 @@ struct DrawLane {
     IdxT *outp;
 };
 
-// one block (624 draws) of one chunk; CUR = which half of the ping-pong buffer holds the old block
+// regeneration of one block: registers r0..r2 become words t, t+227, t+454 of the new block
 template <int PATH, typename IdxT, int CUR>
-__device__ __forceinline__ void draw_step(DrawLane<PATH, IdxT> &L, uint32_t *bt, int t, unsigned int it, int c,
-                                          const unsigned long long *s_begin, const unsigned long long *s_end,
-                                          const DrawPlan &plan, uint32_t n, double dn, IdxT *idx, const DrawConsts &kc) {
+__device__ __forceinline__ void draw_regen(DrawLane<PATH, IdxT> &L, uint32_t *bt, int t, const DrawConsts &kc) {
     constexpr int H = DRAW_H;
-    // bt = &buf[c][0][t]; the other half is MT_N words further
-    const uint32_t *o = bt + CUR * MT_N;
+    const uint32_t *o = bt + CUR * MT_N;  // bt = &buf[c][0][t]; the other half is MT_N words further
     uint32_t *nw = bt + (CUR ^ 1) * MT_N;
     L.r0 = o[MT_M] ^ mt_twist_bal(L.r0, o[1], kc);
     L.r1 = L.r0 ^ mt_twist_bal(L.r1, o[H + 1], kc);
@@ -267,11 +264,27 @@ __device__ __forceinline__ void draw_step(DrawLane<PATH, IdxT> &L, uint32_t *bt,
         L.r2 = L.r1 ^ mt_twist_bal(L.r2, nxt, kc);
         nw[2 * H] = L.r2;
     }
+}
+
+// the three site indices of a block that lies entirely inside a kept range
+template <int PATH, typename IdxT>
+__device__ __forceinline__ void draw_emit(const DrawLane<PATH, IdxT> &L, IdxT *out, uint32_t n, double dn, const DrawConsts &kc) {
+    constexpr int H = DRAW_H;
+    out[0] = (IdxT)site_index<PATH>(mt_temper_bal(L.r0, kc), n, dn);
+    out[H] = (IdxT)site_index<PATH>(mt_temper_bal(L.r1, kc), n, dn);
+    if (L.third) out[2 * H] = (IdxT)site_index<PATH>(mt_temper_bal(L.r2, kc), n, dn);
+}
+
+// one block (624 draws) of one chunk; CUR = which half of the ping-pong buffer holds the old block
+template <int PATH, typename IdxT, int CUR>
+__device__ __forceinline__ void draw_step(DrawLane<PATH, IdxT> &L, uint32_t *bt, int t, unsigned int it, int c,
+                                          const unsigned long long *s_begin, const unsigned long long *s_end,
+                                          const DrawPlan &plan, uint32_t n, double dn, IdxT *idx, const DrawConsts &kc) {
+    constexpr int H = DRAW_H;
+    draw_regen<PATH, IdxT, CUR>(L, bt, t, kc);
     if (it < L.fast_until) {
         if (L.inside) {
-            L.outp[0] = (IdxT)site_index<PATH>(mt_temper_bal(L.r0, kc), n, dn);
-            L.outp[H] = (IdxT)site_index<PATH>(mt_temper_bal(L.r1, kc), n, dn);
-            if (L.third) L.outp[2 * H] = (IdxT)site_index<PATH>(mt_temper_bal(L.r2, kc), n, dn);
+            draw_emit<PATH, IdxT>(L, L.outp, n, dn, kc);
             L.outp += MT_N;
         }
         return;
@@ -371,12 +384,32 @@ mt_draw_kernel(const uint32_t *__restrict__ states, int chunk_log2, DrawPlan pla
     // before the next step swaps their roles.  Lanes without a chunk (padding of the last
     // warp, chunks past the end) run the same code on zeros in their own buffer slot: their
     // bounds are empty, so the first slow-path visit turns their stores off for good.
-    for (unsigned int it = 0; it < steps; it += 2) {
-        draw_step<PATH, IdxT, 0>(L, bt, t, it, c, s_begin, s_end, plan, n, dn, idx, kc);
-        __syncthreads();
-        if (it + 1 < steps) {
-            draw_step<PATH, IdxT, 1>(L, bt, t, it + 1, c, s_begin, s_end, plan, n, dn, idx, kc);
+    // Warps take different paths (each chunk has its own ranges), but every path does exactly
+    // one barrier after each block, so barrier k always separates block k from block k+1.  Four blocks that all lie
+    // inside the current range go through a branch-free body: no per-block range test, stores
+    // at immediate offsets from one pointer.
+    for (unsigned int it = 0; it < steps;) {
+        // (warp-uniform decision: a warp that straddles two chunks must not split over the barriers)
+        if (__all_sync(0xffffffffu, L.inside && it + 4 <= L.fast_until && it + 4 <= steps && (it & 1u) == 0)) {
+            draw_regen<PATH, IdxT, 0>(L, bt, t, kc);
+            draw_emit<PATH, IdxT>(L, L.outp, n, dn, kc);
             __syncthreads();
+            draw_regen<PATH, IdxT, 1>(L, bt, t, kc);
+            draw_emit<PATH, IdxT>(L, L.outp + MT_N, n, dn, kc);
+            __syncthreads();
+            draw_regen<PATH, IdxT, 0>(L, bt, t, kc);
+            draw_emit<PATH, IdxT>(L, L.outp + 2 * MT_N, n, dn, kc);
+            __syncthreads();
+            draw_regen<PATH, IdxT, 1>(L, bt, t, kc);
+            draw_emit<PATH, IdxT>(L, L.outp + 3 * MT_N, n, dn, kc);
+            __syncthreads();
+            L.outp += 4 * MT_N;
+            it += 4;
+        } else {
+            if (it & 1u) draw_step<PATH, IdxT, 1>(L, bt, t, it, c, s_begin, s_end, plan, n, dn, idx, kc);
+            else draw_step<PATH, IdxT, 0>(L, bt, t, it, c, s_begin, s_end, plan, n, dn, idx, kc);
+            __syncthreads();
+            it++;
         }
     }
 }
