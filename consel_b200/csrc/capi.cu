@@ -157,8 +157,8 @@ static int alloc_reps(int K, int S, const int *bb, DevReps **out) {
 }
 
 // Chunk size (log2 draws) of the MT19937 jump tree, from a cost model measured on B200:
-// a jump costs ~0.85 us of whole-GPU time (126 us on one SM), a tree level ~20 us of
-// latency, and a draw CTA slot (6 chunks resident per SM) produces one draw per ~1.1 ns;
+// a jump costs ~0.75 us of whole-GPU time (126 us on one SM), a tree level ~20 us of
+// latency, and a draw CTA slot (6 chunks resident per SM) produces one draw per ~1.0 ns;
 // the draw launch runs in whole waves of 6 x SMs chunks.
 static int pick_chunk_log2(unsigned long long needed_draws, unsigned long long stream_end, int nranges) {
     if (G().opt_chunk_log2 >= 10 && G().opt_chunk_log2 <= 30) return G().opt_chunk_log2;
@@ -173,7 +173,7 @@ static int pick_chunk_log2(unsigned long long needed_draws, unsigned long long s
         while (((stream_end + (1ull << m) - 1) >> m) > (1ull << top)) top++;
         if (m + top > MT_MAXLOG) continue;
         const double waves = std::ceil(pn / slots);
-        const double cost = pn * 0.85e-6 + top * 20e-6 + waves * chunk * 1.1e-9;
+        const double cost = pn * 0.75e-6 + top * 20e-6 + waves * chunk * 1.0e-9;
         if (cost < best_cost) {
             best_cost = cost;
             best = m;
