@@ -169,7 +169,7 @@ struct FxEpilogue {
 // one 32 x 32 block of digit sums (rows = (tree, digit), transposed in `tile`, stride 33):
 // lane l finishes replicate column b for each of the 32/S trees of the block
 // S <= 8 on the fused path: the digits fold into two 64-bit groups g1 (digits 4..7) and g0
-// (digits 0..3), |g| < 2^31 * n' < 2^53 (n' < 2^22 is checked on the host), so both convert
+// (digits 0..3), |g| <= 128*n'*(256^4-1)/255 < 2^31.01 * n' < 2^53 (n' < 2^21 is checked on the host), so both convert
 // to fp64 exactly and ONE fused multiply-add rounds the exact value g1*2^32 + g0 once.
 template <int S>
 __device__ __forceinline__ double fx_digits_to_double(const int *d, int stride) {
@@ -600,7 +600,7 @@ int launch_contract_i8(const DevMatrix &m, const unsigned char *d_counts_rows, i
     // 32-row epilogue slab ("i8_fuse" 0 keeps the two-kernel form for measurements)
     // (S <= 8, a scale 2^-F that is a normal double, and group sums that are exact in fp64)
     const bool fused = !one_shot && m.fxS <= 8 && 8 % m.fxS == 0 && G().opt_i8_fuse != 0 && m.fxF > -1000 && m.fxF < 1000 &&
-                       max_draws < (1 << 22);
+                       max_draws < (1 << 21);
     if (pt) pt->begin(6, st);
     const int m_tiles = (int)(m.fxMpad / G8_BM), n_tiles = nb_pad / G8_BN;
     if (one_shot) {
