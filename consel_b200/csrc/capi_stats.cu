@@ -196,16 +196,24 @@ int cgpu_stats_download(const cgpu_reps *rr, int sorted, double *const *stat_out
     return CGPU_OK;
 }
 
-int cgpu_count_query(const cgpu_reps *rr, int nq, const double *thr, cgpu_rowsum *out) {
+int cgpu_count_query_rows(const cgpu_reps *rr, int row0, int nrows, int nq, const double *thr, cgpu_rowsum *out) {
     CGPU_TRY(ensure_init());
     const DevReps *r = reinterpret_cast<const DevReps *>(rr);
-    if (!r || !r->d_stat || !thr || !out || nq < 1) {
+    if (!r || !r->d_stat || !thr || !out || nq < 1 || row0 < 0 || nrows < 0 || row0 + nrows > r->cm) {
         set_error(CGPU_EINVAL, "count_query: statistics not built or bad arguments");
         return CGPU_EINVAL;
     }
+    if (nrows == 0) return CGPU_OK;
+    (void)cudaSetDevice(G().device);  // the AU driver calls from a helper thread
     cudaStream_t st = G().stream;
-    const int cm = r->cm, S = r->S;
-    const bool have_edges = r->h_edges.size() == (size_t)cm * S * 4;
+    const int cm = nrows, S = r->S;
+    // row edges are cached once per statistics build, by the first whole-range query
+    const bool whole = row0 == 0 && nrows == r->cm;
+    const bool have_edges = r->h_edges.size() == (size_t)r->cm * S * 4;
+    if (!whole && !have_edges) {
+        set_error(CGPU_EINVAL, "count_query_rows: query all rows once before querying a sub-range");
+        return CGPU_EINVAL;
+    }
     DevBuf d_thr, d_out, d_part;
     CGPU_TRY(d_thr.upload(thr, (size_t)cm * nq, st));
     const size_t nout = (size_t)cm * S * nq;
@@ -218,10 +226,10 @@ int cgpu_count_query(const cgpu_reps *rr, int nq, const double *thr, cgpu_rowsum
         nsplit = (int)std::min<long long>(nsplit, std::max<long long>(1, maxB / 1024));
         CGPU_TRY(d_part.alloc(nout * nsplit * sizeof(cgpu_rowsum)));
         CGPU_TRY(launch_rowsum_all_scales(r->d_stat, r->nb, S, cm, nq, d_thr.as<double>(), d_part.as<cgpu_rowsum>(),
-                                          d_out.as<cgpu_rowsum>(), nsplit, st, !have_edges));
+                                          d_out.as<cgpu_rowsum>(), nsplit, st, !have_edges, row0));
     } else {
         for (int s = 0; s < S; s++) {
-            RowSrc src{r->d_stat[s], r->nb[s], nullptr, nullptr, nullptr, nullptr, nullptr};
+            RowSrc src{r->d_stat[s] + (size_t)row0 * r->nb[s], r->nb[s], nullptr, nullptr, nullptr, nullptr, nullptr};
             CGPU_TRY(launch_rowsum(0, src, cm, r->nb[s], nq, d_thr.as<double>(), d_out.as<cgpu_rowsum>(), S, s, st));
         }
     }
@@ -237,7 +245,7 @@ int cgpu_count_query(const cgpu_reps *rr, int nq, const double *thr, cgpu_rowsum
             }
         } else {
             for (size_t e = 0; e < (size_t)cm * S; e++) {
-                const double *c = &r->h_edges[4 * e];
+                const double *c = &r->h_edges[4 * ((size_t)row0 * S + e)];
                 for (int q = 0; q < nq; q++) {
                     cgpu_rowsum &o = out[e * nq + q];
                     o.min1 = c[0]; o.min2 = c[1]; o.max1 = c[2]; o.max2 = c[3];
@@ -246,6 +254,15 @@ int cgpu_count_query(const cgpu_reps *rr, int nq, const double *thr, cgpu_rowsum
         }
     }
     return CGPU_OK;
+}
+
+int cgpu_count_query(const cgpu_reps *rr, int nq, const double *thr, cgpu_rowsum *out) {
+    const DevReps *r = reinterpret_cast<const DevReps *>(rr);
+    if (!r) {
+        set_error(CGPU_EINVAL, "count_query: statistics not built or bad arguments");
+        return CGPU_EINVAL;
+    }
+    return cgpu_count_query_rows(rr, 0, r->cm, nq, thr, out);
 }
 
 int cgpu_order_stat(const cgpu_reps *rr, int s, const int *rank, double *val) {

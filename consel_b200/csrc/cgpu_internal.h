@@ -234,7 +234,8 @@ struct RowSrc {
 int launch_rowsum(int mode, const RowSrc &src, int rows, int B, int nq, const double *d_thr, cgpu_rowsum *d_out,
                   int out_stride, int out_off, cudaStream_t st);
 int launch_rowsum_all_scales(const double *const *d_stat, const int *B, int S, int cm, int nq, const double *d_thr,
-                             cgpu_rowsum *d_part, cgpu_rowsum *d_out, int nsplit, cudaStream_t st, bool edges = true);
+                             cgpu_rowsum *d_part, cgpu_rowsum *d_out, int nsplit, cudaStream_t st, bool edges = true,
+                             int row0 = 0 /* cm = number of rows queried, starting at this row of the blocks */);
 int launch_order_stat(const double *d_stat, int rows, int B, int ld, const int *d_rank, double *d_val, cudaStream_t st);
 int launch_col_top2(const double *x, int K, int B, int ld, double *m1, double *m2, int *a1, cudaStream_t st);
 int launch_stat_build(const double *x, int K, int B, int ld, const double *m1, const double *m2, const int *a1,

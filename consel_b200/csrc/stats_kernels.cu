@@ -205,13 +205,14 @@ struct ScaleList {
 // statistics build; later queries take them from the host-side cache and skip the work)
 template <int NQ, bool EDGES>
 __global__ void __launch_bounds__(RS_THREADS)
-rowsum_multi_kernel(ScaleList sl, int nq, int q0, int nqt, int nsplit, const double *__restrict__ thr,
+rowsum_multi_kernel(ScaleList sl, int row0, int nq, int q0, int nqt, int nsplit, const double *__restrict__ thr,
                     cgpu_rowsum *__restrict__ part) {
-    // thresholds q0 .. q0+nq-1 of the nqt thresholds of each row
+    // thresholds q0 .. q0+nq-1 of the nqt thresholds of each row; rows row0 .. row0+gridDim.x-1 of
+    // the statistic blocks (thresholds and results are indexed from 0)
     const int row = blockIdx.x, sc = blockIdx.y, sp = blockIdx.z, S = gridDim.y;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int B = sl.B[sc];
-    const double *__restrict__ v = sl.stat[sc] + (size_t)row * B;
+    const double *__restrict__ v = sl.stat[sc] + (size_t)(row0 + row) * B;
     const int chunk = (B + nsplit - 1) / nsplit;
     const int b_lo = sp * chunk, b_hi = min(B, b_lo + chunk);
     __shared__ unsigned long long s_cnt[RS_THREADS / 32][NQ];
@@ -308,12 +309,12 @@ rowsum_multi_kernel(ScaleList sl, int nq, int q0, int nqt, int nsplit, const dou
 // (they come from the host cache).
 template <int NQ>
 __global__ void __launch_bounds__(RS_THREADS)
-rowsum_sorted_kernel(ScaleList sl, int nq, int q0, int nqt, int nsplit, const double *__restrict__ thr,
+rowsum_sorted_kernel(ScaleList sl, int row0, int nq, int q0, int nqt, int nsplit, const double *__restrict__ thr,
                      cgpu_rowsum *__restrict__ part) {
     const int row = blockIdx.x, sc = blockIdx.y, sp = blockIdx.z, S = gridDim.y;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int B = sl.B[sc];
-    const double *__restrict__ v = sl.stat[sc] + (size_t)row * B;
+    const double *__restrict__ v = sl.stat[sc] + (size_t)(row0 + row) * B;
     const int chunk = (B + nsplit - 1) / nsplit;
     const int b_lo = sp * chunk, b_hi = min(B, b_lo + chunk);
     constexpr int NI = NQ + 1;  // intervals
@@ -443,7 +444,7 @@ rowsum_merge_kernel(const cgpu_rowsum *__restrict__ part, int total, int nsplit,
 static size_t rss_smem(int nq) { return (size_t)(nq + 1) * RS_THREADS * (8 + 8 + 4); }
 
 int launch_rowsum_all_scales(const double *const *d_stat, const int *B, int S, int cm, int nq, const double *d_thr,
-                             cgpu_rowsum *d_part, cgpu_rowsum *d_out, int nsplit, cudaStream_t st, bool edges) {
+                             cgpu_rowsum *d_part, cgpu_rowsum *d_out, int nsplit, cudaStream_t st, bool edges, int row0) {
     if (cm <= 0 || S <= 0) return CGPU_OK;
     if (S > 32 || nq < 1 || nq > RS_MAXQ) {
         set_error(CGPU_EINVAL, "count query with %d scales / %d thresholds", S, nq);
@@ -459,15 +460,15 @@ int launch_rowsum_all_scales(const double *const *d_stat, const int *B, int S, i
     // than one pass of 16 (204 registers)
 #define CGPU_RSM(NQ_)                                                                                                     \
     do {                                                                                                                  \
-        if (edges) rowsum_multi_kernel<NQ_, true><<<grid, RS_THREADS, 0, st>>>(sl, n, q0, nq, nsplit, d_thr, d_part);     \
-        else rowsum_multi_kernel<NQ_, false><<<grid, RS_THREADS, 0, st>>>(sl, n, q0, nq, nsplit, d_thr, d_part);          \
+        if (edges) rowsum_multi_kernel<NQ_, true><<<grid, RS_THREADS, 0, st>>>(sl, row0, n, q0, nq, nsplit, d_thr, d_part);     \
+        else rowsum_multi_kernel<NQ_, false><<<grid, RS_THREADS, 0, st>>>(sl, row0, n, q0, nq, nsplit, d_thr, d_part);          \
     } while (0)
     for (int q0 = 0; q0 < nq; q0 += 8) {
         const int n = std::min(8, nq - q0);
         if (n <= 1) CGPU_RSM(1);
         else if (n <= 2) CGPU_RSM(2);
-        else if (!edges && n <= 4) rowsum_sorted_kernel<4><<<grid, RS_THREADS, rss_smem(4), st>>>(sl, n, q0, nq, nsplit, d_thr, d_part);
-        else if (!edges) rowsum_sorted_kernel<8><<<grid, RS_THREADS, rss_smem(8), st>>>(sl, n, q0, nq, nsplit, d_thr, d_part);
+        else if (!edges && n <= 4) rowsum_sorted_kernel<4><<<grid, RS_THREADS, rss_smem(4), st>>>(sl, row0, n, q0, nq, nsplit, d_thr, d_part);
+        else if (!edges) rowsum_sorted_kernel<8><<<grid, RS_THREADS, rss_smem(8), st>>>(sl, row0, n, q0, nq, nsplit, d_thr, d_part);
         else if (n <= 4) CGPU_RSM(4);
         else CGPU_RSM(8);
     }

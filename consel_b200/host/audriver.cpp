@@ -5,6 +5,7 @@
 #include <atomic>
 #include <condition_variable>
 #include <functional>
+#include <future>
 #include <mutex>
 #include <thread>
 
@@ -103,42 +104,104 @@ static double wall_now() {
     return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
-int run(const Input &in, const aufit::Options &opt, QueryFn query, void *ctx, Output *out) {
+// Two-half lockstep: the items are cut into two row ranges that take turns on the device, so
+// the host fits of one half run while the other half's count query is in flight (the query
+// is issued from a helper thread; the fits never call into the device library).  `prep(h)`
+// fills half h's thresholds and returns how many per row (0 = nothing left to do), `ask(h, nq)`
+// runs the query, `fit(h, nq)` consumes the answers.  With one half everything is sequential.
+template <class Prep, class Ask, class Fit>
+static int lockstep(int nhalf, Prep prep, Ask ask, Fit fit, double *tq, double *tf, int *nround) {
+    int nq[2] = {0, 0};       // thresholds per row of the query being prepared / answered
+    bool pending[2] = {false, false};
+    for (int h = 0; h < nhalf; h++) nq[h] = prep(h);
+    for (;;) {
+        bool any = false;
+        for (int h = 0; h < nhalf; h++) {
+            const int o = nhalf == 2 ? 1 - h : h;  // the half whose answers are fitted meanwhile
+            std::future<int> fut;
+            const bool asked = nq[h] > 0;
+            const double w0 = wall_now();
+            if (asked) {
+                if (nhalf == 2) fut = std::async(std::launch::async, [&, h] { return ask(h, nq[h]); });
+                else if (int rc = ask(h, nq[h])) return rc;
+                (*nround)++;
+            }
+            const double w1 = wall_now();
+            if (nhalf == 2 && pending[o]) {
+                fit(o, nq[o]);
+                pending[o] = false;
+                nq[o] = prep(o);
+            }
+            const double w2 = wall_now();
+            if (asked && nhalf == 2)
+                if (int rc = fut.get()) return rc;
+            const double w3 = wall_now();
+            if (asked) {
+                if (nhalf == 2) {
+                    pending[h] = true;
+                } else {
+                    fit(h, nq[h]);
+                    nq[h] = prep(h);
+                }
+            }
+            *tf += nhalf == 2 ? w2 - w1 : wall_now() - w3;
+            *tq += nhalf == 2 ? w3 - w2 : w1 - w0;  // overlapped: only the part of the query the fits did not hide
+            any = any || asked || pending[0] || pending[1];
+        }
+        if (!any) break;
+    }
+    return 0;
+}
+
+int run(const Input &in, const aufit::Options &opt, QueryFn query, void *ctx, Output *out, QueryRowsFn query_rows) {
     const int cm = in.cm, kk = in.kk;
     static const bool trace = getenv("CHOST_TIMING") != nullptr;  // per-phase wall times on stderr
+    static const bool no_overlap = getenv("CHOST_NO_OVERLAP") != nullptr;
     double tq = 0, tf = 0;
     int nround = 0;
     std::vector<double> bbd(kk);
     for (int k = 0; k < kk; k++) bbd[k] = (double)in.bb[k];
     const double t0 = refio::cpu_seconds();
+    // row ranges of the halves
+    const int nhalf = (query_rows && cm >= 16 && refio::debugmode <= 0 && !no_overlap) ? 2 : 1;
+    const int lo[2] = {0, nhalf == 2 ? cm / 2 : cm}, hi[2] = {nhalf == 2 ? cm / 2 : cm, cm};
+    auto ask_rows = [&](int h, int nq, const double *thr, cgpu_rowsum *rs) {
+        if (nhalf == 1) return query(ctx, nq, thr, rs);
+        return query_rows(ctx, lo[h], hi[h] - lo[h], nq, thr, rs);
+    };
 
-    // ---- vcalpval for every item (src/consel.c:2744-2808), one query per round
+    // ---- vcalpval for every item (src/consel.c:2744-2808), one query per round and half
     std::vector<aufit::VcIter> vc;
     vc.reserve(cm);
     for (int i = 0; i < cm; i++) vc.emplace_back(in.median[i], in.threshold);
     std::vector<double> thr(cm);
     std::vector<cgpu_rowsum> rs((size_t)cm * kk);
-    for (int round = 0; round < opt.vcloopmax; round++) {
-        bool any = false;
-        for (int i = 0; i < cm; i++) {
-            thr[i] = vc[i].x;
-            any = any || !vc[i].done;
-        }
-        if (!any) break;
-        double w0 = wall_now();
-        if (int rc = query(ctx, 1, thr.data(), rs.data())) return rc;
-        double w1 = wall_now();
-        tq += w1 - w0;
-        nround++;
-        parallel_for(cm, [&](int i) {
-            if (vc[i].done) return;
-            std::vector<double> cnts(kk);
-            for (int k = 0; k < kk; k++) cnts[k] = cgpu_smooth_count(&rs[(size_t)i * kk + k], in.bb[k], thr[i]);
-            vc[i].step(cnts.data(), in.rr, bbd.data(), kk, opt);
-        });
-        tf += wall_now() - w1;
+    int vround[2] = {0, 0};
+    {
+        auto prep = [&](int h) {
+            if (vround[h] >= opt.vcloopmax) return 0;
+            bool any = false;
+            for (int i = lo[h]; i < hi[h]; i++) {
+                thr[i] = vc[i].x;
+                any = any || !vc[i].done;
+            }
+            if (!any) return 0;
+            vround[h]++;
+            return 1;
+        };
+        auto ask = [&](int h, int) { return ask_rows(h, 1, thr.data() + lo[h], rs.data() + (size_t)lo[h] * kk); };
+        auto fit = [&](int h, int) {
+            parallel_for(hi[h] - lo[h], [&](int e) {
+                const int i = lo[h] + e;
+                if (vc[i].done) return;
+                std::vector<double> cnts(kk);
+                for (int k = 0; k < kk; k++) cnts[k] = cgpu_smooth_count(&rs[(size_t)i * kk + k], in.bb[k], thr[i]);
+                vc[i].step(cnts.data(), in.rr, bbd.data(), kk, opt);
+            });
+        };
+        if (int rc = lockstep(nhalf, prep, ask, fit, &tq, &tf, &nround)) return rc;
     }
-    if (trace) fprintf(stderr, "[audriver] vcalpval: %d rounds, query %.2f ms, fits %.2f ms\n", nround, tq * 1e3, tf * 1e3);
+    if (trace) fprintf(stderr, "[audriver] vcalpval: %d queries, exposed query %.2f ms, fits %.2f ms\n", nround, tq * 1e3, tf * 1e3);
     tq = tf = 0;
     nround = 0;
     out->pv.assign(cm, 0); out->se.assign(cm, 0); out->pv0.assign(cm, 0); out->se0.assign(cm, 0);
@@ -176,42 +239,67 @@ int run(const Input &in, const aufit::Options &opt, QueryFn query, void *ctx, Ou
     // thresholds are packed to the front (padded with a value above every statistic), so the
     // device pass gets narrower as the round count grows.
     std::vector<int> act((size_t)cm * nq), nact(cm);
-    for (int round = 0; round < opt.ciloopmax; round++) {
-        int nmax = 0;
-        for (int j = 0; j < cm; j++) {
-            int n = 0;
-            for (int q = 0; q < nq; q++)
-                if (!ci[(size_t)j * nq + q].done) act[(size_t)j * nq + n++] = q;
-            nact[j] = n;
-            nmax = std::max(nmax, n);
-        }
-        if (nmax == 0) break;
-        for (int a0 = 0; a0 < nmax; a0 += qchunk) {
-            const int nqc = std::min(qchunk, nmax - a0);
-            cthr.assign((size_t)cm * nqc, 1.0e300);
-            for (int j = 0; j < cm; j++)
-                for (int a = 0; a < nqc && a0 + a < nact[j]; a++)
-                    cthr[(size_t)j * nqc + a] = ci[(size_t)j * nq + act[(size_t)j * nq + a0 + a]].x;
-            crs.resize((size_t)cm * kk * nqc);
-            double w0 = wall_now();
-            if (int rc = query(ctx, nqc, cthr.data(), crs.data())) return rc;
-            double w1 = wall_now();
-            tq += w1 - w0;
-            nround++;
-            parallel_for(cm * nqc, [&](int e) {
-                const int j = e / nqc, a = e % nqc;
-                if (a0 + a >= nact[j]) return;
-                aufit::CiIter &c = ci[(size_t)j * nq + act[(size_t)j * nq + a0 + a]];
+    int cround[2] = {0, 0};
+    {
+        auto prep = [&](int h) {
+            if (cround[h] >= opt.ciloopmax) return 0;
+            int nmax = 0;
+            for (int j = lo[h]; j < hi[h]; j++) {
+                int n = 0;
+                for (int q = 0; q < nq; q++)
+                    if (!ci[(size_t)j * nq + q].done) act[(size_t)j * nq + n++] = q;
+                nact[j] = n;
+                nmax = std::max(nmax, n);
+            }
+            if (nmax == 0) return 0;
+            cround[h]++;
+            return nmax;
+        };
+        // thresholds and answers of half h live at row offset lo[h] of buffers sized for nq per row
+        cthr.assign((size_t)cm * nq, 1.0e300);
+        crs.resize((size_t)cm * kk * nq);
+        auto ask = [&](int h, int nmax) {
+            const int rows = hi[h] - lo[h];
+            double *t = cthr.data() + (size_t)lo[h] * nq;
+            for (int e = 0; e < rows; e++) {
+                const int j = lo[h] + e;
+                for (int a = 0; a < nmax; a++)
+                    t[(size_t)e * nmax + a] = a < nact[j] ? ci[(size_t)j * nq + act[(size_t)j * nq + a]].x : 1.0e300;
+            }
+            cgpu_rowsum *o = crs.data() + (size_t)lo[h] * kk * nq;
+            for (int a0 = 0; a0 < nmax; a0 += qchunk) {  // more than 16 thresholds per row: several queries
+                if (a0 == 0 && nmax <= qchunk) return ask_rows(h, nmax, t, o);
+                // (never taken with the reference's five alphas; kept simple: one query per chunk)
+                const int nqc = std::min(qchunk, nmax - a0);
+                std::vector<double> tt((size_t)rows * nqc);
+                std::vector<cgpu_rowsum> oo((size_t)rows * kk * nqc);
+                for (int e = 0; e < rows; e++)
+                    for (int a = 0; a < nqc; a++) tt[(size_t)e * nqc + a] = t[(size_t)e * nmax + a0 + a];
+                if (int rc = ask_rows(h, nqc, tt.data(), oo.data())) return rc;
+                for (int e = 0; e < rows; e++)
+                    for (int k = 0; k < kk; k++)
+                        for (int a = 0; a < nqc; a++)
+                            o[((size_t)e * kk + k) * nmax + a0 + a] = oo[((size_t)e * kk + k) * nqc + a];
+            }
+            return 0;
+        };
+        auto fit = [&](int h, int nmax) {
+            const int rows = hi[h] - lo[h];
+            const double *t = cthr.data() + (size_t)lo[h] * nq;
+            const cgpu_rowsum *o = crs.data() + (size_t)lo[h] * kk * nq;
+            parallel_for(rows * nmax, [&](int e2) {
+                const int e = e2 / nmax, a = e2 % nmax, j = lo[h] + e;
+                if (a >= nact[j]) return;
+                aufit::CiIter &c = ci[(size_t)j * nq + act[(size_t)j * nq + a]];
                 std::vector<double> cnts(kk);
-                const double t = cthr[(size_t)j * nqc + a];
-                for (int k = 0; k < kk; k++)
-                    cnts[k] = cgpu_smooth_count(&crs[((size_t)j * kk + k) * nqc + a], in.bb[k], t);
+                const double tv = t[(size_t)e * nmax + a];
+                for (int k = 0; k < kk; k++) cnts[k] = cgpu_smooth_count(&o[((size_t)e * kk + k) * nmax + a], in.bb[k], tv);
                 c.step(cnts.data(), in.rr, bbd.data(), kk, opt);
             });
-            tf += wall_now() - w1;
-        }
+        };
+        if (int rc = lockstep(nhalf, prep, ask, fit, &tq, &tf, &nround)) return rc;
     }
-    if (trace) fprintf(stderr, "[audriver] invtpval: %d rounds, query %.2f ms, fits %.2f ms\n", nround, tq * 1e3, tf * 1e3);
+    if (trace) fprintf(stderr, "[audriver] invtpval: %d queries, exposed query %.2f ms, fits %.2f ms\n", nround, tq * 1e3, tf * 1e3);
     const size_t n2 = (size_t)cm * nalpha;
     out->ci.assign(n2, 0); out->cs.assign(n2, 0); out->ei.assign(n2, 0);
     out->ci0.assign(n2, 0); out->cs0.assign(n2, 0); out->ei0.assign(n2, 0);
@@ -234,6 +322,10 @@ int run(const Input &in, const aufit::Options &opt, QueryFn query, void *ctx, Ou
 }  // namespace audriver
 
 // ---- C export for the Python pipeline (consel_b200/pipeline.py)
+// optional row-range query for the next chost_au_run call (same ctx): enables the overlapped schedule
+static audriver::QueryRowsFn g_query_rows = nullptr;
+extern "C" void chost_set_query_rows(audriver::QueryRowsFn fn) { g_query_rows = fn; }
+
 extern "C" int chost_au_run(int cm, int kk, const double *rr, const int *bb, int i0, double threshold,
                             const double *median, const cgpu_rowsum *r0, int nalpha, const double *alpha,
                             int fitmode, double kappa, audriver::QueryFn query, void *ctx,
@@ -246,7 +338,8 @@ extern "C" int chost_au_run(int cm, int kk, const double *rr, const int *bb, int
     opt.fitmode = fitmode;
     opt.kappa = kappa;
     audriver::Output o;
-    int rc = audriver::run(in, opt, query, ctx, &o);
+    int rc = audriver::run(in, opt, query, ctx, &o, g_query_rows);
+    g_query_rows = nullptr;
     if (rc) return rc;
     for (int i = 0; i < cm; i++) {
         pv2[2 * i] = o.pv[i]; pv2[2 * i + 1] = o.pv0[i];

@@ -13,6 +13,8 @@ namespace audriver {
 
 // same shape as cgpu_count_query(const cgpu_reps*, int nq, const double *thr, cgpu_rowsum *out)
 typedef int (*QueryFn)(void *ctx, int nq, const double *thr, cgpu_rowsum *out);
+// same shape as cgpu_count_query_rows: rows [row0, row0+nrows) only (thr nrows x nq, out nrows x S x nq)
+typedef int (*QueryRowsFn)(void *ctx, int row0, int nrows, int nq, const double *thr, cgpu_rowsum *out);
 
 struct Input {
     int cm = 0, kk = 0;
@@ -37,6 +39,8 @@ struct Output {
 };
 
 // returns 0, or the first non-zero code of the query callback
-int run(const Input &in, const aufit::Options &opt, QueryFn query, void *ctx, Output *out);
+// With `query_rows` the items are split into two halves that alternate between the device
+// (count query) and the host (fits); results do not depend on the schedule.
+int run(const Input &in, const aufit::Options &opt, QueryFn query, void *ctx, Output *out, QueryRowsFn query_rows = nullptr);
 
 }  // namespace audriver

@@ -333,7 +333,10 @@ int main(int argc, char **argv) {
         auto query = [](void *ctx, int nq, const double *thr, cgpu_rowsum *out) {
             return cgpu_count_query(static_cast<const cgpu_reps *>(ctx), nq, thr, out);
         };
-        if (audriver::run(ain, opt, query, reps, &ao) != 0) die("%s", cgpu_last_error());
+        auto query_rows = [](void *ctx, int row0, int nrows, int nq, const double *thr, cgpu_rowsum *out) {
+            return cgpu_count_query_rows(static_cast<const cgpu_reps *>(ctx), row0, nrows, nq, thr, out);
+        };
+        if (audriver::run(ain, opt, query, reps, &ao, query_rows) != 0) die("%s", cgpu_last_error());
         for (int i = 0; i < cm; i++) {
             dprint(1, "\n# rank=%d item=%d", i + 1, orderv[i] + 1);
             dprint(1, "\n# ret=%d", ao.ret[i]);

@@ -217,6 +217,10 @@ def consel(reps: api.Reps, datvec, rr, bb, ass=None, alpha=(0.05, 0.10, 0.5, 0.9
         else:
             cb = C.cast(api.load().cgpu_count_query, QUERY_FN)
             ctx = reps._h
+            # row-range queries let the driver fit one half of the items while the device counts for the other
+            lib.chost_set_query_rows.argtypes = [C.c_void_p]
+            lib.chost_set_query_rows.restype = None
+            lib.chost_set_query_rows(C.cast(api.load().cgpu_count_query_rows, C.c_void_p))
         rc = lib.chost_au_run(cm, kk, api._dp(rr), api._ip(bb), i0, C.c_double(threshold), api._dp(med),
                               r0.ctypes.data_as(C.POINTER(api.RowSum)), len(alpha), api._dp(alpha), fitmode,
                               C.c_double(kappa), cb, ctx, api._dp(pv2), api._dp(se2), api._dp(ax7),

@@ -138,6 +138,10 @@ void cgpu_smooth_count_many(const cgpu_rowsum *q, int count, int B, double t, do
  * do_bootrep (src/consel.c:2775-2778, 2845-2848, 1503-1507): nq thresholds per item,
  * thr[i*nq+q]; out[(i*S+s)*nq+q].                                                   */
 int cgpu_count_query(const cgpu_reps *r, int nq, const double *thr, cgpu_rowsum *out);
+/* The same for rows [row0, row0+nrows) only (thr: nrows x nq, out: nrows x S x nq), so a host
+ * driver can fit one half of the items while the device counts for the other half.  The row
+ * edges (min1..max2) come from a cache that the first whole-range query fills.          */
+int cgpu_count_query_rows(const cgpu_reps *r, int row0, int nrows, int nq, const double *thr, cgpu_rowsum *out);
 /* k-th smallest (0-based rank[i]) of stat[s][i][:] for every item — the median and
  * the min/max that vcalpval/invtpval start from (src/consel.c:2765, 2837).         */
 int cgpu_order_stat(const cgpu_reps *r, int s, const int *rank, double *val);
