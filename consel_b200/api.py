@@ -229,6 +229,16 @@ class Reps:
         _check(load().cgpu_count_query(self._h, nq, _dp(thr), out.ctypes.data_as(C.POINTER(RowSum))))
         return out
 
+    def count_query_rows(self, row0: int, thr: np.ndarray) -> np.ndarray:
+        """The same for items row0 .. row0+len(thr)-1 only (after one whole-range query)."""
+        thr = np.ascontiguousarray(thr, dtype=np.float64)
+        thr = thr.reshape(thr.shape[0], -1)
+        nq = thr.shape[1]
+        out = np.zeros((thr.shape[0], self.S, nq), dtype=ROWSUM_DTYPE)
+        _check(load().cgpu_count_query_rows(self._h, int(row0), int(thr.shape[0]), nq, _dp(thr),
+                                            out.ctypes.data_as(C.POINTER(RowSum))))
+        return out
+
     def order_stat(self, s: int, rank) -> np.ndarray:
         rank = np.ascontiguousarray(rank, dtype=np.int32)
         val = np.zeros(self.cm)

@@ -138,3 +138,24 @@ def test_consel_side_rejects_bad_input(cg, orc):
         reps.stats_build(np.array([0, 1]), np.array([9]))  # tree id out of range
     with pytest.raises(cg.CgpuError):
         reps.mctest(0, np.zeros(4), np.array([0, 2]), np.array([1, 1]))  # duplicate association
+
+
+def test_count_query_rows_equals_slices_of_the_whole_query(cg, orc, gold):
+    """cgpu_count_query_rows (the AU driver's half-range query) == the same rows of cgpu_count_query,
+    for 1, 2, 5 and 10 thresholds per item, and it needs one whole-range query first (edge cache)."""
+    rmt, sptr, sidx = _case(orc, gold, "g100")
+    reps = cg.Reps.upload(rmt["reps"])
+    reps.stats_build(sptr, sidx)
+    cm = reps.cm
+    rng = np.random.default_rng(9)
+    with pytest.raises(cg.CgpuError):
+        reps.count_query_rows(1, np.zeros((2, 1)))
+    for nq in (1, 2, 5, 10):
+        thr = rng.normal(0.0, 3.0, size=(cm, nq))
+        thr[:, 0] = 0.0
+        whole = reps.count_query(thr)
+        for row0, rows in ((0, cm // 2), (cm // 2, cm - cm // 2), (1, 1)):
+            part = reps.count_query_rows(row0, thr[row0:row0 + rows])
+            assert part.tobytes() == whole[row0:row0 + rows].tobytes(), (nq, row0)
+    with pytest.raises(cg.CgpuError):
+        reps.count_query_rows(cm - 1, np.zeros((2, 1)))
