@@ -385,19 +385,11 @@ static int scaleboot_core(DevMatrix &m, int S, const int *bn, const int *bb, uns
         }
     } guard{plan};
     // staged index production (see below): one jump tree per stage
-    MtPlan plans[3];
-    PlanGuard sguard0{plans[0]}, sguard1{plans[1]}, sguard2{plans[2]};
-    int nstages = 1, stage_first[3] = {0, 0, 0};
-    cudaEvent_t stage_done[3] = {nullptr, nullptr, nullptr};
-    struct EventGuard {
-        cudaEvent_t *e;
-        ~EventGuard() {
-            cudaStreamSynchronize(G().stream2);  // the aux stream may still use the plans on an error path
-            for (int i = 0; i < 3; i++)
-                if (e[i]) cudaEventDestroy(e[i]);
-        }
-    } eguard{stage_done};
-    for (int i = 1; i < 3; i++) CGPU_CUDA(cudaEventCreateWithFlags(&stage_done[i], cudaEventDisableTiming));
+    constexpr int MAX_STAGES = 4;
+    MtPlan plans[MAX_STAGES];
+    PlanGuard sguard0{plans[0]}, sguard1{plans[1]}, sguard2{plans[2]}, sguard3{plans[3]};
+    int nstages = 1, stage_cut[MAX_STAGES + 1] = {0, 0, 0, 0, 0};
+    std::vector<unsigned long long> st_lo, st_hi;  // kept draw ranges per scale (filled below)
     std::vector<unsigned long long> base(S + 1, 0);
     for (int s = 0; s < S; s++) base[s + 1] = base[s] + (unsigned long long)bb[s] * (unsigned long long)bn[s];
     // When this rank's share of the index stream fits the workspace, ONE draw launch covers
@@ -456,39 +448,30 @@ static int scaleboot_core(DevMatrix &m, int S, const int *bn, const int *bb, uns
             hi[s] = lo[s] + (unsigned long long)reps->nb[s] * (unsigned long long)bn[s];
         }
         // Host-output calls in int8 mode are bound by the device-to-host copy of the replicate
-        // blocks (PCIe), which can only start when the first scale is finished.  The index
-        // stream is therefore produced in three stages of growing size — the first scale
-        // alone with short chunks on the main stream, the rest on the aux stream behind it —
-        // so the copy engine starts early and never waits for the bulk of the draws.
+        // blocks (PCIe, 15 ms at C2 against 10 ms of compute), which can only start when the
+        // first scale is finished.  The index stream is therefore produced in up to four
+        // stages of growing size (about 4 %, 16 %, 45 % and 100 % of the draws, each with its
+        // own jump tree and chunk size), each stage's draw launch queued right before its
+        // first scale: the copy engine starts after ~1 ms and stays busy, at the price of
+        // ~1 ms of extra jumps.  Everything stays on the main stream (the tensor-core GEMM
+        // needs whole SMs, so overlapping long draw CTAs with it only delays it).
         if (idx_whole_run && i8 && host_out && S >= 4 && S <= 32 && G().opt_stage != 0 &&
             (G().opt_stage == 1 || idx_off[S] >= (1ull << 28))) {
-            int g1 = 1, g2 = 2;
-            while (g1 < S - 2 && (double)idx_off[g1] < 0.04 * (double)idx_off[S]) g1++;
-            g2 = g1 + 1;
-            while (g2 < S - 1 && (double)idx_off[g2] < 0.16 * (double)idx_off[S]) g2++;
-            const int cut[4] = {0, g1, g2, S};
-            stage_first[0] = 0;
-            stage_first[1] = g1;
-            stage_first[2] = g2;
-            nstages = 3;
-            for (int g = 0; g < 3; g++)
-                CGPU_TRY(mt_plan(seed, stream_offset, base[S], cut[g + 1] - cut[g], lo.data() + cut[g], hi.data() + cut[g], &plans[g]));
-            CGPU_CUDA(cudaEventRecord(ws.idx_ready, st));  // allocations and memsets are ordered on st
-            CGPU_CUDA(cudaStreamWaitEvent(G().stream2, ws.idx_ready, 0));
-            for (int g = 0; g < 3; g++) {
-                cudaStream_t sg = g == 0 ? st : G().stream2;
-                pt.begin(8, sg);
-                CGPU_TRY(mt_launch(&plans[g], sg));
-                pt.end();
-                pt.begin(9, sg);
-                DrawPlan dp;
-                CGPU_TRY(make_draw_plan(cut[g + 1] - cut[g], lo.data() + cut[g], hi.data() + cut[g], idx_off.data() + cut[g],
-                                        plans[g].chunk_log2, base[S], &dp));
-                CGPU_TRY(resolve_draw_slots(plans[g], &dp));
-                CGPU_TRY(launch_mt_draw(plans[g], dp, (uint32_t)n, ws.d_idx, sg));
-                pt.end();
-                if (g > 0) CGPU_CUDA(cudaEventRecord(stage_done[g], sg));
+            const double frac[MAX_STAGES - 1] = {0.04, 0.16, 0.45};
+            nstages = 0;
+            stage_cut[0] = 0;
+            for (int f = 0; f < MAX_STAGES - 1; f++) {
+                int c = stage_cut[nstages] + 1;
+                while (c < S && (double)idx_off[c] < frac[f] * (double)idx_off[S]) c++;
+                if (c >= S) break;
+                stage_cut[++nstages] = c;
             }
+            stage_cut[++nstages] = S;
+            for (int g = 0; g < nstages; g++)
+                CGPU_TRY(mt_plan(seed, stream_offset, base[S], stage_cut[g + 1] - stage_cut[g], lo.data() + stage_cut[g],
+                                 hi.data() + stage_cut[g], &plans[g]));
+            st_lo = lo;
+            st_hi = hi;
         } else {
         pt.begin(8);
         if (S > 32) {  // more scales than plan ranges: prepare the hull of this rank's draws
@@ -544,8 +527,20 @@ static int scaleboot_core(DevMatrix &m, int S, const int *bn, const int *bb, uns
     int item = 0;
     for (int s = 0; s < S; s++) {
         const double r = (double)bn[s] / (double)n;  // src/makermt.c:48
-        for (int g = 1; g < nstages; g++)
-            if (s == stage_first[g]) CGPU_CUDA(cudaStreamWaitEvent(st, stage_done[g], 0));
+        if (nstages > 1)
+            for (int g = 0; g < nstages; g++)
+                if (s == stage_cut[g]) {  // jump tree and draws of the stage that begins with this scale
+                    pt.begin(8);
+                    CGPU_TRY(mt_launch(&plans[g], st));
+                    pt.end();
+                    pt.begin(9);
+                    DrawPlan dp;
+                    CGPU_TRY(make_draw_plan(stage_cut[g + 1] - stage_cut[g], st_lo.data() + stage_cut[g], st_hi.data() + stage_cut[g],
+                                            idx_off.data() + stage_cut[g], plans[g].chunk_log2, base[S], &dp));
+                    CGPU_TRY(resolve_draw_slots(plans[g], &dp));
+                    CGPU_TRY(launch_mt_draw(plans[g], dp, (uint32_t)n, ws.d_idx, st));
+                    pt.end();
+                }
         for (int a = 0; a < reps->nb[s]; a += batch, item++) {
             const int nbat = std::min(batch, reps->nb[s] - a);
             const int bA = reps->b0[s] + a;  // global replicate index of the batch
