@@ -457,7 +457,8 @@ static int scaleboot_core(DevMatrix &m, int S, const int *bn, const int *bb, uns
         // needs whole SMs, so overlapping long draw CTAs with it only delays it).
         if (idx_whole_run && i8 && host_out && S >= 4 && S <= 32 && G().opt_stage != 0 &&
             (G().opt_stage == 1 || idx_off[S] >= (1ull << 28))) {
-            const double frac[MAX_STAGES - 1] = {0.04, 0.16, 0.45};
+            double frac[MAX_STAGES - 1] = {0.04, 0.16, 0.45};
+            if (const char *e = getenv("CGPU_STAGE_FRACS")) sscanf(e, "%lf,%lf,%lf", &frac[0], &frac[1], &frac[2]);  // measurement
             nstages = 0;
             stage_cut[0] = 0;
             for (int f = 0; f < MAX_STAGES - 1; f++) {
