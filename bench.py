@@ -301,6 +301,19 @@ def run_ours(args) -> None:
               "shared-memory bandwidth bound (~126 us per jump per SM against a 103 us floor at 128 B/clk); "
               "launches_per_step=1 stands for the ~10 levels of the jump tree"),
     ]
+    # the draw kernel is bound by instruction issue, which the hbm|tensor vocabulary cannot express:
+    # add the issue-slot view (warp-instructions per draw from profiles/r01_final_draw_hist_gemm_ncu_full.json)
+    try:
+        prof = json.loads((ROOT / "profiles" / "r01_final_draw_hist_gemm_ncu_full.json").read_text())["launches"][0]
+        wi_per_draw = prof["warp_instructions"] / 3.243e9
+        sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        issue_peak = 4.0 * torch.cuda.get_device_properties(local).multi_processor_count * sm_mhz * 1e6
+        ach = wi_per_draw * draws / (phases["mt_draw"] * 1e-3)
+        kernels[0]["issue_view"] = {"achieved": ach / 1e9, "peak": issue_peak / 1e9, "unit": "G warp-instructions/s",
+                                    "frac": ach / issue_peak, "warp_instructions_per_draw": wi_per_draw,
+                                    "source": "instruction count from the ncu capture, time from this run's CUDA events"}
+    except Exception:
+        pass
     kernels = [e for e in kernels if e["share_of_step"] > 1e-6]  # e.g. fx_combine runs inside the GEMM epilogue when S divides 32
     dominant = max(kernels, key=lambda e: e["share_of_step"])
     roofline = dict(dominant)
