@@ -47,14 +47,15 @@ __device__ __forceinline__ uint32_t shr_mul(uint32_t v, uint32_t pow2_32_minus_s
     return r;
 }
 
-struct DrawConsts { uint32_t p31, p21, p14; };  // 2^(32-1), 2^(32-11), 2^(32-18)
+struct DrawConsts { uint32_t p31, p21, p14, mag; };  // 2^(32-1), 2^(32-11), 2^(32-18), 0x9908b0df (opaque multipliers)
 
 __device__ __forceinline__ uint32_t mt_twist_bal(uint32_t hi, uint32_t lo, const DrawConsts &k) {
-    const uint32_t l1 = shr_mul(lo, k.p31), h1 = shr_mul(hi, k.p31);
-    uint32_t y1;  // (l1 & ~0x40000000) | (h1 & 0x40000000): bit select as ONE lop3 (LUT 0xd8)
-    asm("lop3.b32 %0, %1, %2, 0x40000000, 0xd8;" : "=r"(y1) : "r"(l1), "r"(h1));
-    const uint32_t bit = lo - 2u * l1;  // lo & 1 as a multiply-add
-    return y1 ^ (bit * 0x9908b0dfu);
+    uint32_t y;  // (hi & 0x80000000) | (lo & 0x7fffffff): bit select as ONE lop3 (LUT 0xe4 = mask ? a : b)
+    asm("lop3.b32 %0, %1, %2, 0x80000000, 0xe4;" : "=r"(y) : "r"(hi), "r"(lo));
+    const uint32_t y1 = shr_mul(y, k.p31);  // y >> 1 on the multiplier pipe
+    uint32_t mag;                           // (lo & 1) * 0x9908b0df with the constant in a register: stays a multiply
+    asm("mul.lo.u32 %0, %1, %2;" : "=r"(mag) : "r"(lo & 1u), "r"(k.mag));
+    return y1 ^ mag;
 }
 
 // tempering: left shifts become multiplies on their own, right shifts stay on the logic pipe
@@ -647,7 +648,7 @@ static void mt_draw_launch(const uint32_t *d_states, int chunk_log2, const DrawP
     const int sms = G().sm_count > 0 ? G().sm_count : 148;
     const int nchunks = plan.cum[plan.nintervals];
     const int force = G().opt_draw_nch;
-    const DrawConsts kc = {1u << 31, 1u << 21, 1u << 14};
+    const DrawConsts kc = {1u << 31, 1u << 21, 1u << 14, 0x9908b0dfu};
     // measured: 3 chunks per CTA beats 2 and 1 whenever there are enough chunks to give every SM a CTA
     if (force == 3 || (force < 0 && nchunks >= 3 * sms))
         mt_draw_kernel<PATH, IdxT, 3><<<(nchunks + 2) / 3, DrawCfg<3>::threads, 0, st>>>(d_states, chunk_log2, plan, n, idx, kc);
@@ -750,7 +751,7 @@ int launch_mt_draw_hist(const MtPlan &mt, const DrawPlan &plan, const unsigned i
     }
     hp.NP = NP;
     hp.err = d_err;
-    const DrawConsts kc = {1u << 31, 1u << 21, 1u << 14};
+    const DrawConsts kc = {1u << 31, 1u << 21, 1u << 14, 0x9908b0dfu};
     const int sms = G().sm_count > 0 ? G().sm_count : 148;
     if (nchunks >= 3 * sms) {
         const size_t smem = mt_draw_hist_smem(NP, 3);
