@@ -426,8 +426,10 @@ static int scaleboot_core(DevMatrix &m, int S, const int *bn, const int *bb, uns
     if (!fuse_hist)
         for (int i = 0; i < 2; i++) {
             CGPU_CUDA(scratch_get(1 + i, (size_t)(batch / 8) * NP * 8, reinterpret_cast<void **>(&ws.d_counts[i])));
-            // padding sites and replicates must read as zero counts
-            CGPU_CUDA(cudaMemsetAsync(ws.d_counts[i], 0, (size_t)(batch / 8) * NP * 8, st));
+            // fp64 paths: padding sites and replicates must read as zero counts.  The byte rows of
+            // the tensor-core path need no clearing: the histogram kernels write whole rows
+            // (padding sites included) and the GEMM never stores the columns of padding rows.
+            if (!i8) CGPU_CUDA(cudaMemsetAsync(ws.d_counts[i], 0, (size_t)(batch / 8) * NP * 8, st));
         }
     if (rng_mode == CGPU_RNG_MT19937) {
         for (int s = 0; s < S; s++) idx_off[s + 1] = idx_off[s] + (unsigned long long)reps->nb[s] * (unsigned long long)bn[s];
