@@ -209,13 +209,18 @@ __device__ __forceinline__ void fx_finish_block(const int *tile, int lane, int k
 
 // ------------------------------------------------------------------ tcgen05 GEMM tiles
 constexpr int G8_BM = 128, G8_BN = 256, G8_BK = 128;  // BK in bytes == int8 elements (one 128B swizzle atom)
-constexpr int G8_STAGES = 4;
+constexpr int G8_STAGES = 4;  // one-shot kernel; the persistent kernel is a template over (stages, epilogue warps)
 constexpr int G8_THREADS = 192;  // one-shot kernel: warp0 TMA, warp1 MMA (+TMEM alloc), warps 2-5 epilogue
-constexpr int G8P_EPI_WARPS = 8;  // persistent kernel: two epilogue warps per TMEM lane quarter (columns split)
-constexpr int G8P_THREADS = 64 + 32 * G8P_EPI_WARPS;
+// persistent kernel configurations: (4 stages, 8 epilogue warps) keeps the tensor pipe fed on long
+// tiles; (3 stages, 12 epilogue warps) for short tiles, where the fused epilogue of a tile takes as
+// long as its MMAs and the freed 48 KB hold four more transpose buffers
+template <int STAGES, int EW> struct G8P {
+    static constexpr int threads = 64 + 32 * EW;
+    static constexpr size_t epi_bytes = (size_t)EW * 32 * 33 * 4;  // per epilogue warp a 32 x 32 int32 transpose tile (stride 33)
+    static constexpr size_t smem = STAGES * ((size_t)128 * 128 + (size_t)256 * 128) + 1024 /*align*/ + 256 /*barriers*/ + epi_bytes;
+};
 constexpr size_t G8_A_BYTES = (size_t)G8_BM * G8_BK, G8_B_BYTES = (size_t)G8_BN * G8_BK;
-constexpr size_t G8_EPI_BYTES = G8P_EPI_WARPS * 32 * 33 * 4;  // per epilogue warp a 32 x 32 int32 transpose tile (stride 33)
-constexpr size_t G8_SMEM = G8_STAGES * (G8_A_BYTES + G8_B_BYTES) + 1024 /*align*/ + 256 /*barriers*/ + G8_EPI_BYTES;
+constexpr size_t G8_SMEM = G8_STAGES * (G8_A_BYTES + G8_B_BYTES) + 1024 /*align*/ + 256 /*barriers*/;
 
 __device__ __forceinline__ uint32_t s2u(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mb_init(uint64_t *b, uint32_t n) {
@@ -364,32 +369,33 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 // same time share count rows in L2); the shared-memory ring runs across tiles, and two
 // accumulator stages in tensor memory (2 x 256 columns) let the epilogue of tile i drain
 // while the MMAs of tile i+1 are issued.
-__global__ void __launch_bounds__(G8P_THREADS, 1)
+template <int STAGES, int EW>
+__global__ void __launch_bounds__(64 + 32 * EW, 1)
 gemm_i8_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, int NP,
                           int *__restrict__ P, int ldp, int m_tiles, int n_tiles, FxEpilogue ep) {
     extern __shared__ unsigned char g8_raw[];
     unsigned char *base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(g8_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char *sA = base;
-    unsigned char *sB = base + G8_STAGES * G8_A_BYTES;
-    uint64_t *full = reinterpret_cast<uint64_t *>(base + G8_STAGES * (G8_A_BYTES + G8_B_BYTES));
-    uint64_t *empty = full + G8_STAGES;
-    uint64_t *acc_full = empty + G8_STAGES;  // [2]
+    unsigned char *sB = base + STAGES * G8_A_BYTES;
+    uint64_t *full = reinterpret_cast<uint64_t *>(base + STAGES * (G8_A_BYTES + G8_B_BYTES));
+    uint64_t *empty = full + STAGES;
+    uint64_t *acc_full = empty + STAGES;  // [2]
     uint64_t *acc_empty = acc_full + 2;      // [2]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
-    int *epi = reinterpret_cast<int *>(base + G8_STAGES * (G8_A_BYTES + G8_B_BYTES) + 256);
+    int *epi = reinterpret_cast<int *>(base + STAGES * (G8_A_BYTES + G8_B_BYTES) + 256);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nkb = NP / G8_BK;
     const int total_tiles = m_tiles * n_tiles;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < G8_STAGES; s++) {
+        for (int s = 0; s < STAGES; s++) {
             mb_init(&full[s], 1);
             mb_init(&empty[s], 1);
         }
         for (int a = 0; a < 2; a++) {
             mb_init(&acc_full[a], 1);
-            mb_init(&acc_empty[a], G8P_EPI_WARPS);  // one arrival per epilogue warp
+            mb_init(&acc_empty[a], EW);  // one arrival per epilogue warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -415,8 +421,8 @@ gemm_i8_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
                 const bool pre = NP <= 8192 && nt < total_tiles && nt / m_tiles != tile / m_tiles;
                 const int n0n = (nt / m_tiles) * G8_BN;
                 for (int kb = 0; kb < nkb; kb++, it++) {
-                    const int s = it % G8_STAGES;
-                    mb_wait(&empty[s], ((it / G8_STAGES) & 1) ^ 1);
+                    const int s = it % STAGES;
+                    mb_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
                     mb_expect(&full[s], (uint32_t)(G8_A_BYTES + G8_B_BYTES));
                     tma_load_2d(sA + s * G8_A_BYTES, &mapA, kb * G8_BK, m0, &full[s]);
                     tma_load_2d(sB + s * G8_B_BYTES, &mapB, kb * G8_BK, n0, &full[s]);
@@ -434,8 +440,8 @@ gemm_i8_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t d_tmem = tmem + (uint32_t)(acc * G8_BN);
                 for (int kb = 0; kb < nkb; kb++, it++) {
-                    const int s = it % G8_STAGES;
-                    mb_wait(&full[s], (it / G8_STAGES) & 1);
+                    const int s = it % STAGES;
+                    mb_wait(&full[s], (it / STAGES) & 1);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint64_t ad = umma_desc_sw128(sA + s * G8_A_BYTES), bd = umma_desc_sw128(sB + s * G8_B_BYTES);
 #pragma unroll
@@ -449,7 +455,10 @@ gemm_i8_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
         // epilogue warp: TMEM lane quarter q (= warp % 4, the hardware's access rule), column half h
         const int q = warp & 3;
         const int h = (warp - 2) >> 2;
-        constexpr int COLS = G8_BN / (G8P_EPI_WARPS / 4);
+        // column blocks (32 wide) of this warp: the 8 blocks of a tile are dealt 3 / 3 / 2 to the
+        // three warps of a lane quarter (or 4 / 4 with eight epilogue warps)
+        constexpr int NSPLIT = EW / 4, NBLK = G8_BN / 32;
+        const int blk_lo = h * NBLK / NSPLIT, blk_hi = (h + 1) * NBLK / NSPLIT;
         int *tile_s = epi + (warp - 2) * (32 * 33);
         int tcount = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, tcount++) {
@@ -459,7 +468,7 @@ gemm_i8_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             int *dst = P + (size_t)(m0 + q * 32 + lane) * ldp + n0;
 #pragma unroll 1
-            for (int c = h * COLS; c < (h + 1) * COLS; c += 32) {
+            for (int c = blk_lo * 32; c < blk_hi * 32; c += 32) {
                 uint32_t v[32];
                 const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * G8_BN + c);
                 asm volatile(
@@ -473,7 +482,7 @@ gemm_i8_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
                     : "r"(taddr)
                     : "memory");
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (c + 32 == (h + 1) * COLS) {  // last read of this accumulator by this warp: hand it back
+                if (c + 32 == blk_hi * 32) {  // last read of this accumulator by this warp: hand it back
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s2u(&acc_empty[acc])) : "memory");
@@ -591,7 +600,8 @@ int launch_contract_i8(const DevMatrix &m, const unsigned char *d_counts_rows, i
     static bool attr_done = false;
     if (!attr_done) {
         CGPU_CUDA(cudaFuncSetAttribute(gemm_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G8_SMEM));
-        CGPU_CUDA(cudaFuncSetAttribute(gemm_i8_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G8_SMEM));
+        CGPU_CUDA(cudaFuncSetAttribute(gemm_i8_persistent_kernel<4, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G8P<4, 8>::smem));
+        CGPU_CUDA(cudaFuncSetAttribute(gemm_i8_persistent_kernel<3, 12>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G8P<3, 12>::smem));
         attr_done = true;
     }
     static const bool env_one_shot = getenv("CGPU_I8_ONESHOT") != nullptr;  // development A/B switch
@@ -611,7 +621,11 @@ int launch_contract_i8(const DevMatrix &m, const unsigned char *d_counts_rows, i
         const int grid = std::min(sms, m_tiles * n_tiles);
         FxEpilogue ep{fused ? d_rep : nullptr, r, {(m.fxF > -1000 && m.fxF < 1000) ? std::ldexp(1.0, -m.fxF) : 0.0, m.fxF},
                       m.K, m.fxS, nb, ldrep, col0, G().opt_i8_dbg > 0 ? G().opt_i8_dbg : 0};
-        gemm_i8_persistent_kernel<<<grid, G8P_THREADS, G8_SMEM, st>>>(mapA, mapB, m.NP, d_partial, nb_pad, m_tiles, n_tiles, ep);
+        // short tiles (C2: 27 k-blocks) are epilogue bound, long ones feed bound (measured cross-over ~50)
+        if (fused && m.NP / G8_BK <= 48)
+            gemm_i8_persistent_kernel<3, 12><<<grid, G8P<3, 12>::threads, G8P<3, 12>::smem, st>>>(mapA, mapB, m.NP, d_partial, nb_pad, m_tiles, n_tiles, ep);
+        else
+            gemm_i8_persistent_kernel<4, 8><<<grid, G8P<4, 8>::threads, G8P<4, 8>::smem, st>>>(mapA, mapB, m.NP, d_partial, nb_pad, m_tiles, n_tiles, ep);
     }
     CGPU_LAUNCH_CHECK();
     if (pt) pt->end();
