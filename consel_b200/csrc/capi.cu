@@ -72,9 +72,16 @@ void PhaseTimer::finish(double *ms) {
     cudaEventSynchronize(t1);
     float tot = 0;
     if (cudaEventElapsedTime(&tot, t0, t1) == cudaSuccess) ms[5] = tot;
+    static const bool trace = getenv("CGPU_TRACE") != nullptr;  // development: every span with its start time
     for (int i = 0; i < nspans; i++) {
         Span &sp = spans[i];
         float v = 0;
+        if (trace && sp.ended) {
+            float a = 0, b = 0;
+            if (cudaEventSynchronize(sp.b) == cudaSuccess && cudaEventElapsedTime(&a, t0, sp.a) == cudaSuccess &&
+                cudaEventElapsedTime(&b, t0, sp.b) == cudaSuccess)
+                fprintf(stderr, "[cgpu trace] phase %d: %8.3f -> %8.3f ms\n", sp.phase, a, b);
+        }
         // a span left open by an early error return has no end event: skip it (querying it
         // would leave a stale "invalid resource handle" for the next launch check)
         if (sp.ended && cudaEventSynchronize(sp.b) == cudaSuccess && cudaEventElapsedTime(&v, sp.a, sp.b) == cudaSuccess)
@@ -389,6 +396,15 @@ static int scaleboot_core(DevMatrix &m, int S, const int *bn, const int *bb, uns
     MtPlan plans[MAX_STAGES];
     PlanGuard sguard0{plans[0]}, sguard1{plans[1]}, sguard2{plans[2]}, sguard3{plans[3]};
     int nstages = 1, stage_cut[MAX_STAGES + 1] = {0, 0, 0, 0, 0};
+    cudaEvent_t stage_tree[MAX_STAGES] = {nullptr, nullptr, nullptr, nullptr};
+    struct TreeEvents {
+        cudaEvent_t *e;
+        ~TreeEvents() {
+            cudaStreamSynchronize(G().stream2);  // an error path may leave the aux stream working on the plans
+            for (int i = 0; i < MAX_STAGES; i++)
+                if (e[i]) cudaEventDestroy(e[i]);
+        }
+    } tguard{stage_tree};
     std::vector<unsigned long long> st_lo, st_hi;  // kept draw ranges per scale (filled below)
     std::vector<unsigned long long> base(S + 1, 0);
     for (int s = 0; s < S; s++) base[s + 1] = base[s] + (unsigned long long)bb[s] * (unsigned long long)bn[s];
@@ -475,6 +491,9 @@ static int scaleboot_core(DevMatrix &m, int S, const int *bn, const int *bb, uns
                                  hi.data() + stage_cut[g], &plans[g]));
             st_lo = lo;
             st_hi = hi;
+            for (int g = 1; g < nstages; g++) CGPU_CUDA(cudaEventCreateWithFlags(&stage_tree[g], cudaEventDisableTiming));
+            CGPU_CUDA(cudaEventRecord(ws.idx_ready, st));  // the plans' allocations are ordered on the main stream
+            CGPU_CUDA(cudaStreamWaitEvent(G().stream2, ws.idx_ready, 0));
         } else {
         pt.begin(8);
         if (S > 32) {  // more scales than plan ranges: prepare the hull of this rank's draws
@@ -533,9 +552,13 @@ static int scaleboot_core(DevMatrix &m, int S, const int *bn, const int *bb, uns
         if (nstages > 1)
             for (int g = 0; g < nstages; g++)
                 if (s == stage_cut[g]) {  // jump tree and draws of the stage that begins with this scale
-                    pt.begin(8);
-                    CGPU_TRY(mt_launch(&plans[g], st));
-                    pt.end();
+                    if (g == 0) {
+                        pt.begin(8);
+                        CGPU_TRY(mt_launch(&plans[0], st));
+                        pt.end();
+                    } else {
+                        CGPU_CUDA(cudaStreamWaitEvent(st, stage_tree[g], 0));  // built on the aux stream meanwhile
+                    }
                     pt.begin(9);
                     DrawPlan dp;
                     CGPU_TRY(make_draw_plan(stage_cut[g + 1] - stage_cut[g], st_lo.data() + stage_cut[g], st_hi.data() + stage_cut[g],
@@ -543,6 +566,15 @@ static int scaleboot_core(DevMatrix &m, int S, const int *bn, const int *bb, uns
                     CGPU_TRY(resolve_draw_slots(plans[g], &dp));
                     CGPU_TRY(launch_mt_draw(plans[g], dp, (uint32_t)n, ws.d_idx, st));
                     pt.end();
+                    if (g + 1 < nstages) {
+                        // the next stage's jump tree (latency bound while it is narrow) runs on the aux
+                        // stream under this stage's draws, histograms and GEMMs
+                        cudaStream_t aux2 = G().stream2;
+                        pt.begin(8, aux2);
+                        CGPU_TRY(mt_launch(&plans[g + 1], aux2));
+                        pt.end();
+                        CGPU_CUDA(cudaEventRecord(stage_tree[g + 1], aux2));
+                    }
                 }
         for (int a = 0; a < reps->nb[s]; a += batch, item++) {
             const int nbat = std::min(batch, reps->nb[s] - a);
