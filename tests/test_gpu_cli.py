@@ -104,3 +104,21 @@ def test_in_process_pipeline_matches_reference_pv(gold, orc):
     # the tensor-core sums give the same table to printed precision (catpv prints 3 decimals)
     res8 = pipeline.run(L, rr, rmt["bb"], 7, sum_mode=cg.SUM_INT8)
     assert np.allclose(res8["pv"], ref_pv["pv"], rtol=1e-6, atol=1e-9)
+
+
+def test_makermt_extension_flags(gold, orc, tmp_path):
+    """--sum int8 (tensor-core fixed point): every replicate sum within 1e-9 of the reference's
+    .rmt (north star tolerance; the value is the correctly rounded exact sum), same header;
+    --rng philox: a valid .rmt of the same shape that consel accepts."""
+    shutil.copy(gold / "mam15.lnf", tmp_path / "mam15.lnf")
+    run("makermt", ["-s", "1234", "-b", "0.01", "--paml", "--sum", "int8", "mam15", "i8"], tmp_path)
+    ref, got = orc.read_rmt(gold / "g100.rmt"), orc.read_rmt(tmp_path / "i8.rmt")
+    assert np.array_equal(ref["datvec"], got["datvec"]) and np.array_equal(ref["rr"], got["rr"]) and np.array_equal(ref["bb"], got["bb"])
+    for a, b in zip(ref["reps"], got["reps"]):
+        assert a.shape == b.shape and np.abs(a - b).max() <= 1e-9 * np.abs(a).max()
+    run("makermt", ["-s", "1234", "-b", "0.01", "--paml", "--rng", "philox", "--sum", "int8", "mam15", "ph"], tmp_path)
+    ph = orc.read_rmt(tmp_path / "ph.rmt")
+    assert [r.shape for r in ph["reps"]] == [r.shape for r in ref["reps"]]
+    assert all(np.isfinite(r).all() for r in ph["reps"])
+    out = run("consel", ["ph"], tmp_path)
+    assert "# exit normally" in out and (tmp_path / "ph.pv").exists()
