@@ -94,8 +94,13 @@ static void parallel_for(int n, const std::function<void(int)> &body) {
         return;
     }
     static Pool pool([] {
+        // one process per GPU shares the host: torchrun exports LOCAL_WORLD_SIZE
         unsigned hw = std::thread::hardware_concurrency();
-        return (int)std::max(1u, hw ? hw - 1 : 1u);
+        unsigned share = 1;
+        if (const char *e = getenv("LOCAL_WORLD_SIZE")) share = (unsigned)std::max(1, atoi(e));
+        if (const char *e = getenv("CHOST_THREADS")) return std::max(1, atoi(e));
+        hw = std::max(1u, hw / share);
+        return (int)std::max(1u, hw > 1 ? hw - 1 : 1u);
     }());
     pool.run(n, body);
 }

@@ -207,13 +207,84 @@ def consel(reps: api.Reps, datvec, rr, bb, ass=None, alpha=(0.05, 0.10, 0.5, 0.9
         ret = np.zeros(cm, dtype=np.int32)
         lib = host_lib()
         if dist_mode:
+            # Every rank fits only ITS items (the per-item fits are independent host work; with
+            # one process per GPU the host cores are shared) but counts over its replicate shard
+            # for ALL items.  One protocol round = (1) agree on the threshold count of the round
+            # and on whether anybody is still iterating, (2) all-gather the thresholds of all
+            # items, (3) local count query, (4) all-gather the (count, lo, hi) triples and reduce
+            # them (sum / max / min: exact), (5) every rank takes the rows of its items.  A rank
+            # whose items have converged keeps serving rounds until all ranks are done.
+            import torch
+            import torch.distributed as dist
+            world, rank = dist.get_world_size(), dist.get_rank()
+            dev = cdist._device_for(None)
+            lo_r = [cm * r // world for r in range(world + 1)]
+            my0, my1 = lo_r[rank], lo_r[rank + 1]
+            cml = my1 - my0
+            edges = {f: np.ascontiguousarray(q0[f][:, :, 0]) for f in ("min1", "min2", "max1", "max2")}  # combined once
+            HUGE = 1.0e300
+
+            def protocol_round(nq_loc: int, thr_loc):
+                """thr_loc: (cml, nq_loc) or None.  Returns (active_anywhere, rows for my items or None)."""
+                hdr = torch.tensor([float(nq_loc), 1.0 if nq_loc > 0 else 0.0], dtype=torch.float64, device=dev)
+                dist.all_reduce(hdr, op=dist.ReduceOp.MAX)
+                nq_r = int(hdr[0].item())
+                if hdr[1].item() == 0.0 or nq_r == 0:
+                    return False, None
+                mine = np.full((cml, nq_r), HUGE)
+                if nq_loc > 0:
+                    mine[:, :nq_loc] = thr_loc
+                parts = [torch.empty((lo_r[r + 1] - lo_r[r], nq_r), dtype=torch.float64, device=dev) for r in range(world)]
+                me = torch.from_numpy(mine).to(dev)
+                if len({p.shape for p in parts}) == 1:
+                    dist.all_gather(parts, me)
+                else:
+                    cdist._uneven_gather(parts, me, None)
+                thr_all = torch.cat(parts, dim=0).cpu().numpy()
+                q = reps.count_query(thr_all)  # (cm, S, nq_r) over this rank's replicate columns
+                trip = torch.from_numpy(np.stack([q["cnt"], q["lo"], q["hi"]])).to(dev)  # (3, cm, S, nq_r)
+                gath = [torch.empty_like(trip) for _ in range(world)]
+                dist.all_gather(gath, trip)
+                g = torch.stack(gath)  # (world, 3, cm, S, nq_r)
+                cnt = g[:, 0, my0:my1].sum(dim=0)
+                lo_ = g[:, 1, my0:my1].max(dim=0).values
+                hi_ = g[:, 2, my0:my1].min(dim=0).values
+                if nq_loc == 0:
+                    return True, None
+                rows = np.zeros((cml, kk, nq_r), dtype=api.ROWSUM_DTYPE)
+                rows["cnt"], rows["lo"], rows["hi"] = cnt.cpu().numpy(), lo_.cpu().numpy(), hi_.cpu().numpy()
+                for f in ("min1", "min2", "max1", "max2"):
+                    rows[f] = edges[f][my0:my1, :, None]
+                return True, rows[:, :, :nq_loc]
+
             def py_query(ctx, nq, thr_p, out_p):
-                thr = np.ctypeslib.as_array(thr_p, shape=(cm, nq)).copy()
-                q = cdist.combine_rowsums(reps.count_query(thr))
-                C.memmove(out_p, q.ctypes.data, q.nbytes)
+                thr = np.ctypeslib.as_array(thr_p, shape=(cml, nq)).copy()
+                _, rows = protocol_round(nq, thr)
+                rows = np.ascontiguousarray(rows)
+                C.memmove(out_p, rows.ctypes.data, rows.nbytes)
                 return 0
             cb = QUERY_FN(py_query)
-            ctx = None
+            rc = 0
+            loc = dict(pv2=np.zeros((cml, 2)), se2=np.zeros((cml, 2)), ax7=np.zeros((cml, 7)),
+                       ci6=np.zeros((6, cml, len(alpha))), ret=np.zeros(cml, dtype=np.int32))
+            if cml > 0:
+                med_l = np.ascontiguousarray(med[my0:my1])
+                r0_l = np.ascontiguousarray(r0[my0:my1])
+                rc = lib.chost_au_run(cml, kk, api._dp(rr), api._ip(bb), i0, C.c_double(threshold), api._dp(med_l),
+                                      r0_l.ctypes.data_as(C.POINTER(api.RowSum)), len(alpha), api._dp(alpha), fitmode,
+                                      C.c_double(kappa), cb, None, api._dp(loc["pv2"]), api._dp(loc["se2"]), api._dp(loc["ax7"]),
+                                      api._dp(loc["ci6"]) if confidence else None, api._ip(loc["ret"]))
+            while protocol_round(0, None)[0]:  # serve the ranks that are still iterating
+                pass
+            if rc:
+                raise api.CgpuError(rc, api.load().cgpu_last_error().decode())
+            gathered = [None] * world
+            dist.all_gather_object(gathered, loc)
+            pv2 = np.concatenate([g_["pv2"] for g_ in gathered])
+            se2 = np.concatenate([g_["se2"] for g_ in gathered])
+            ax7 = np.concatenate([g_["ax7"] for g_ in gathered])
+            ci6 = np.concatenate([g_["ci6"] for g_ in gathered], axis=1)
+            ret = np.concatenate([g_["ret"] for g_ in gathered])
         else:
             cb = C.cast(api.load().cgpu_count_query, QUERY_FN)
             ctx = reps._h
@@ -221,12 +292,12 @@ def consel(reps: api.Reps, datvec, rr, bb, ass=None, alpha=(0.05, 0.10, 0.5, 0.9
             lib.chost_set_query_rows.argtypes = [C.c_void_p]
             lib.chost_set_query_rows.restype = None
             lib.chost_set_query_rows(C.cast(api.load().cgpu_count_query_rows, C.c_void_p))
-        rc = lib.chost_au_run(cm, kk, api._dp(rr), api._ip(bb), i0, C.c_double(threshold), api._dp(med),
-                              r0.ctypes.data_as(C.POINTER(api.RowSum)), len(alpha), api._dp(alpha), fitmode,
-                              C.c_double(kappa), cb, ctx, api._dp(pv2), api._dp(se2), api._dp(ax7),
-                              api._dp(ci6) if confidence else None, api._ip(ret))
-        if rc:
-            raise api.CgpuError(rc, api.load().cgpu_last_error().decode())
+            rc = lib.chost_au_run(cm, kk, api._dp(rr), api._ip(bb), i0, C.c_double(threshold), api._dp(med),
+                                  r0.ctypes.data_as(C.POINTER(api.RowSum)), len(alpha), api._dp(alpha), fitmode,
+                                  C.c_double(kappa), cb, ctx, api._dp(pv2), api._dp(se2), api._dp(ax7),
+                                  api._dp(ci6) if confidence else None, api._ip(ret))
+            if rc:
+                raise api.CgpuError(rc, api.load().cgpu_last_error().decode())
         pv[:, 6:8], se[:, 6:8] = pv2, se2
         out.update(ax=ax7, ci=ci6 if confidence else None, alpha=alpha, ret=ret)
         timing["au_s"] = time.perf_counter() - t0
