@@ -242,13 +242,16 @@ def consel(reps: api.Reps, datvec, rr, bb, ass=None, alpha=(0.05, 0.10, 0.5, 0.9
                     cdist._uneven_gather(parts, me, None)
                 thr_all = torch.cat(parts, dim=0).cpu().numpy()
                 q = reps.count_query(thr_all)  # (cm, S, nq_r) over this rank's replicate columns
-                trip = torch.from_numpy(np.stack([q["cnt"], q["lo"], q["hi"]])).to(dev)  # (3, cm, S, nq_r)
-                gath = [torch.empty_like(trip) for _ in range(world)]
-                dist.all_gather(gath, trip)
-                g = torch.stack(gath)  # (world, 3, cm, S, nq_r)
-                cnt = g[:, 0, my0:my1].sum(dim=0)
-                lo_ = g[:, 1, my0:my1].max(dim=0).values
-                hi_ = g[:, 2, my0:my1].min(dim=0).values
+                # all-to-all: rank p receives, from every rank, the triples of ITS items only
+                trip = torch.from_numpy(np.stack([q["cnt"], q["lo"], q["hi"]], axis=1)).to(dev)  # (cm, 3, S, nq_r)
+                width = 3 * kk * nq_r
+                recv = torch.empty((world * cml, width), dtype=torch.float64, device=dev)
+                dist.all_to_all_single(recv, trip.reshape(cm, width), output_split_sizes=[cml] * world,
+                                       input_split_sizes=[lo_r[r + 1] - lo_r[r] for r in range(world)])
+                g = recv.reshape(world, cml, 3, kk, nq_r)
+                cnt = g[:, :, 0].sum(dim=0)
+                lo_ = g[:, :, 1].max(dim=0).values
+                hi_ = g[:, :, 2].min(dim=0).values
                 if nq_loc == 0:
                     return True, None
                 rows = np.zeros((cml, kk, nq_r), dtype=api.ROWSUM_DTYPE)
