@@ -122,7 +122,10 @@ static void wls2(const double *X0, const double *X1, const double *Y, const doub
 static Fit fit_wls(const double *cnts, const double *rr, const double *bb, int kk, double rmin, double rmax,
                    double kappa, double vmat[2][2]) {
     Fit f;
-    std::vector<double> X0(kk), X1(kk), npv(kk), zval(kk), wt(kk);
+    // per-thread scratch: this function runs ~10^4 times per consel call on every pool thread
+    static thread_local std::vector<double> scratch;
+    if ((int)scratch.size() < 5 * kk) scratch.resize(5 * (size_t)kk);
+    double *X0 = scratch.data(), *X1 = X0 + kk, *npv = X1 + kk, *zval = npv + kk, *wt = zval + kk;
     int m = 0;
     for (int i = 0; i < kk; i++) {
         double s = sqrt(1.0 / rr[i]);
@@ -156,7 +159,7 @@ static Fit fit_wls(const double *cnts, const double *rr, const double *bb, int k
         refio::dprint(1, "\n# error in wls");
     } else {
         double beta[2];
-        wls2(X0.data(), X1.data(), zval.data(), wt.data(), kk, beta, &f.rss, vmat);
+        wls2(X0, X1, zval, wt, kk, beta, &f.rss, vmat);
         f.beta[0] = beta[0];
         f.beta[1] = beta[1];
         f.pv = pnorm(-(beta[0] - kappa * beta[1]));
@@ -181,7 +184,10 @@ static double log3(double x) {
 // mlecoef (src/consel.c:2237-2330): Newton-Raphson on the binomial likelihood
 static int fit_mle_coef(const double *cnts, const double *rr, const double *bb, int kk, double coef0[2],
                         double vmat[2][2], double *lrt, double *df, double rmin, double rmax, const Options &opt) {
-    std::vector<double> s(kk), r(kk), c(kk), b(kk), z(kk), p(kk), d(kk), g(kk), h(kk);
+    static thread_local std::vector<double> scratch;
+    if ((int)scratch.size() < 9 * kk) scratch.resize(9 * (size_t)kk);
+    double *s = scratch.data(), *r = s + kk, *c = r + kk, *b = c + kk, *z = b + kk, *p = z + kk, *d = p + kk, *g = d + kk,
+           *h = g + kk;
     int m = 0;
     for (int i = 0; i < kk; i++)
         if (rr[i] >= rmin && rr[i] <= rmax) {
