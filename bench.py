@@ -83,6 +83,22 @@ class ClockSampler(threading.Thread):
         self._halt = threading.Event()
 
     def run(self):
+        # NVML polls in well under a millisecond, so even a 50 ms timed region yields tens of
+        # samples; nvidia-smi (one process per sample) is the fallback
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.idx)
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            bits = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
+            while not self._halt.is_set():
+                sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.rows.append(["nvml", str(sm), str(mx), "", ""] + ["Active" if r & b else "Not Active" for b in bits.values()])
+                self._halt.wait(0.002)
+            return
+        except Exception:
+            pass
         while not self._halt.is_set():
             try:
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
