@@ -198,6 +198,19 @@ class Reps:
         _check(load().cgpu_reps_upload(int(K), len(bb), _ip(bb), C.cast(arr, C.POINTER(C.POINTER(C.c_double))), C.byref(h)))
         return cls(h, int(K), bb)
 
+    @classmethod
+    def upload_stats(cls, stats) -> "Reps":
+        """A handle over statistic blocks that already exist (the payload of a `.rep` file,
+        consel -R): cm x bb[s] each.  No replicate blocks behind it: stats_build / mctest raise."""
+        stats = [np.ascontiguousarray(t, dtype=np.float64) for t in stats]
+        cm = stats[0].shape[0]
+        bb = np.array([t.shape[1] for t in stats], dtype=np.int32)
+        h = C.c_void_p()
+        _check(load().cgpu_stats_upload(cm, len(stats), _ip(bb), _ptr_array(stats), C.byref(h)))
+        r = cls(h, 0, bb)
+        r.cm = cm
+        return r
+
     def _local_cols(self):
         return [shard_range(int(b))[1] - shard_range(int(b))[0] for b in self.bb]
 

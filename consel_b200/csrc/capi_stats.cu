@@ -131,10 +131,67 @@ int cgpu_reps_upload(int K, int S, const int *bb, const double *const *rep, cgpu
     return CGPU_OK;
 }
 
+// Statistics that already exist (a `.rep` file, consel -R: do_repmode src/consel.c:1195-1242):
+// the handle has no replicate blocks, only the cm x B_s statistic rows, and serves the count
+// queries / order statistics / downloads like one built by cgpu_stats_build.
+int cgpu_stats_upload(int cm, int S, const int *bb, const double *const *stat, cgpu_reps **out) {
+    CGPU_TRY(ensure_init());
+    if (cm <= 0 || S <= 0 || !bb || !stat || !out) {
+        set_error(CGPU_EINVAL, "stats_upload: bad arguments");
+        return CGPU_EINVAL;
+    }
+    cudaStream_t st = G().stream;
+    DevReps *r = new DevReps();
+    r->K = 0;
+    r->S = S;
+    r->cm = cm;
+    r->bb = (int *)calloc(S, sizeof(int));
+    r->b0 = (int *)calloc(S, sizeof(int));
+    r->nb = (int *)calloc(S, sizeof(int));
+    r->d_rep = (double **)calloc(S, sizeof(double *));
+    r->d_stat = (double **)calloc(S, sizeof(double *));
+    int rc = CGPU_OK;
+    for (int s = 0; s < S && rc == CGPU_OK; s++) {
+        if (bb[s] < 0 || (bb[s] > 0 && !stat[s])) {
+            set_error(CGPU_EINVAL, "stats_upload: bad block %d", s);
+            rc = CGPU_EINVAL;
+            break;
+        }
+        const int b0 = (int)((long long)bb[s] * G().shard_rank / G().shard_world);
+        const int b1 = (int)((long long)bb[s] * (G().shard_rank + 1) / G().shard_world);
+        r->bb[s] = bb[s];
+        r->b0[s] = b0;
+        r->nb[s] = b1 - b0;
+        cudaError_t e = dev_alloc(&r->d_stat[s], (size_t)cm * std::max(1, b1 - b0) * sizeof(double));
+        if (e == cudaSuccess && b1 > b0)
+            e = cudaMemcpy2DAsync(r->d_stat[s], (size_t)(b1 - b0) * sizeof(double), stat[s] + b0,
+                                  (size_t)bb[s] * sizeof(double), (size_t)(b1 - b0) * sizeof(double), cm,
+                                  cudaMemcpyDefault, st);
+        if (e != cudaSuccess) {
+            set_error(CGPU_ECUDA, "stats_upload scale %d: %s", s, cudaGetErrorString(e));
+            rc = CGPU_ECUDA;
+        }
+    }
+    if (rc == CGPU_OK && cudaStreamSynchronize(st) != cudaSuccess) {
+        set_error(CGPU_ECUDA, "stats_upload: sync failed");
+        rc = CGPU_ECUDA;
+    }
+    if (rc != CGPU_OK) {
+        cgpu_reps_free(reinterpret_cast<cgpu_reps *>(r));
+        return rc;
+    }
+    *out = reinterpret_cast<cgpu_reps *>(r);
+    return CGPU_OK;
+}
+
 int cgpu_stats_build(cgpu_reps *rr, int cm, const int *ass_ptr, const int *ass_idx) {
     CGPU_TRY(ensure_init());
     DevReps *r = reinterpret_cast<DevReps *>(rr);
     if (!r) return CGPU_EINVAL;
+    if (r->K <= 0) {
+        set_error(CGPU_EINVAL, "stats_build: the handle holds uploaded statistics, no replicate blocks");
+        return CGPU_EINVAL;
+    }
     CGPU_TRY(check_csr(r->K, cm, ass_ptr, ass_idx));
     cudaStream_t st = G().stream;
     if (r->d_stat) {
@@ -300,6 +357,10 @@ int cgpu_mctest(const cgpu_reps *rr, int i0, const double *datvec, double varadd
         return CGPU_EINVAL;
     }
     const int K = r->K, B = r->nb[i0];
+    if (K <= 0) {
+        set_error(CGPU_EINVAL, "mctest: the handle holds uploaded statistics, no replicate blocks");
+        return CGPU_EINVAL;
+    }
     CGPU_TRY(check_csr(K, cm, ass_ptr, ass_idx));
     if (B != r->bb[i0]) {
         set_error(CGPU_EINVAL, "mctest needs every replicate of scale %d on this device (row means are sequential sums)", i0);

@@ -7,7 +7,11 @@
 // all items so that one device query per round serves every item; the fits of a round
 // run on all host threads.
 //
-// Not carried by this build (error at the command line): -R/-C input modes, -g multi-gene
+// Rep mode (-R, do_repmode :1195-1242) feeds statistic rows that already exist (a `.rep`
+// file) to the same count queries through cgpu_stats_upload: BP and AU only, like the
+// reference.
+//
+// Not carried by this build (error at the command line): -C input mode, -g multi-gene
 // mode, -f rescaling approximation, --chi* spherical fit, --pdm AIC correction,
 // --quick_mctest.  They are off the hot path (SURVEY 8f "next").
 #include <cmath>
@@ -50,7 +54,7 @@ struct Assoc {
 
 int main(int argc, char **argv) {
     const char *fname_in = nullptr, *fname_out_arg = nullptr, *fname_ass = nullptr, *fname_vt = nullptr;
-    bool outrep = false, outcnt = false, smoothcnt = false, nosort = false;
+    bool outrep = false, outcnt = false, smoothcnt = false, nosort = false, inrep = false;
     bool dobp = true, doba = true, domc = true, doau = true;
     int cm_arg = 0, gpu = -1;
     double threshold = 0.0, varadd = 1.0, bapcoef = 1.0;
@@ -69,6 +73,7 @@ int main(int argc, char **argv) {
             else byebye();
             j++;
         } else if (a == "-r") outrep = true;
+        else if (a == "-R") inrep = true;
         else if (a == "-c") outcnt = true;
         else if (a == "-a") { need(); fname_ass = argv[++i]; }
         else if (a == "-v") { need(); fname_vt = argv[++i]; }
@@ -92,10 +97,10 @@ int main(int argc, char **argv) {
         else if (a == "--mle") opt.fitmode = aufit::FIT_MLE;
         else if (a == "--wls") opt.fitmode = aufit::FIT_WLS;
         else if (a == "--gpu") integer(&gpu);
-        else if (a == "-R" || a == "-C" || a == "-g" || a == "-f" || a == "-p" || a == "--pdm" ||
+        else if (a == "-C" || a == "-g" || a == "-f" || a == "-p" || a == "--pdm" ||
                  a == "--quick_mctest" || a.rfind("--chi", 0) == 0 || a == "--aictype" || a == "--ppn" ||
                  a == "--pmin" || a == "--congbp")
-            die("switch %s is not supported by the B200 build of consel (rmt mode only)", a.c_str());
+            die("switch %s is not supported by the B200 build of consel (rmt and rep modes only)", a.c_str());
         else byebye();
     }
 
@@ -104,12 +109,63 @@ int main(int argc, char **argv) {
     if (fname_out_arg) outbase = strip_extension(fname_out_arg);
     const char *fname_out = fname_out_arg ? outbase.c_str() : nullptr;
 
-    // ---------------- read .rmt (src/consel.c:806-834)
     std::string used;
     std::vector<double> datvec, rr;
     std::vector<int> bb;
     std::vector<std::vector<double>> repmats;
-    int mm = 0, kk = 0;
+    int mm = 0, kk = 0, cm = 0;
+    Assoc ass;
+    std::vector<double> obsvec;
+    std::vector<int> orderv;
+    if (inrep) {
+        // ---------------- read .rep (do_repmode, src/consel.c:1195-1226): the statistic rows
+        // land in `repmats`, cm x B_s each
+        doba = domc = false;
+        std::vector<int> cnt;
+        if (fname_in) {
+            FILE *fp = open_file(fname_in, ".rep", "rb", &used);
+            printf("\n# reading %s", used.c_str());
+            orderv = read_bivec(fp);
+            obsvec = read_bvec(fp);
+            cm = (int)orderv.size();
+            if ((int)obsvec.size() != cm) die("size mismatch in vec");
+            rr = read_bvec(fp);
+            kk = (int)rr.size();
+            bb = read_bivec(fp, kk);
+            if (read_bint(fp) != kk) die("wrong number of matrices");
+            repmats.resize(kk);
+            for (int i = 0; i < kk; i++) {
+                int m = cm, b = bb[i];
+                repmats[i] = read_bmat(fp, &m, &b);
+            }
+            fclose(fp);
+        } else {
+            printf("\n# reading from stdin");
+            orderv = read_ivec(stdin);
+            obsvec = read_vec(stdin);
+            cm = (int)orderv.size();
+            if ((int)obsvec.size() != cm) die("size mismatch in vec");
+            rr = read_vec(stdin);
+            kk = (int)rr.size();
+            bb = read_ivec(stdin, kk);
+            if (read_int(stdin) != kk) die("wrong number of matrices");
+            repmats.resize(kk);
+            for (int i = 0; i < kk; i++) {
+                int m = cm, b = bb[i];
+                repmats[i] = read_mat(stdin, &m, &b);
+                putchar('.');
+                fflush(stdout);
+            }
+        }
+        printf("\n# K:%d", kk);
+        printf("\n# R:");
+        for (int i = 0; i < kk; i++) printf("%g ", rr[i]);
+        printf("\n# B:");
+        for (int i = 0; i < kk; i++) printf("%d ", bb[i]);
+        printf("\n# CM:%d", cm);
+        if (kk < 1 || cm < 1) { printf("\n# exit normally\n"); return 0; }
+    } else {
+    // ---------------- read .rmt (src/consel.c:806-834)
     if (fname_in) {
         FILE *fp = open_file(fname_in, ".rmt", "rb", &used);
         printf("\n# reading %s", used.c_str());
@@ -196,10 +252,10 @@ int main(int argc, char **argv) {
         }
     }
     printf("\n# CM:%d", cm0);
-    int cm = cm_arg;
+    cm = cm_arg;
     if (cm <= 0 || cm > cm0) cm = cm0;
     if (cm < cm0) printf(" -> %d", cm);
-    std::vector<int> orderv(cm0);
+    orderv.resize(cm0);
     if (nosort) {
         for (int i = 0; i < cm0; i++) orderv[i] = i;
     } else {
@@ -222,12 +278,12 @@ int main(int argc, char **argv) {
         dprint(1, "\n# %4d %4d ", i + 1, orderv[i] + 1);
         for (double v : obsv[orderv[i]]) dprint(1, " %6.2f", v);
     }
-    Assoc ass;
-    std::vector<double> obsvec(cm);
+    obsvec.resize(cm);
     for (int i = 0; i < cm; i++) {
         obsvec[i] = obsv[orderv[i]][0];
         ass.push(std::vector<int>(ass0.at(orderv[i]), ass0.at(orderv[i]) + ass0.len(orderv[i])));
     }
+    }  // rmt mode
 
     // ---------------- alphas (read_alpha, src/consel.c:543-560)
     std::vector<double> alphavec = {0.05, 0.10, 0.5, 0.90, 0.95};
@@ -262,7 +318,8 @@ int main(int argc, char **argv) {
     {
         std::vector<const double *> ptrs(kk);
         for (int i = 0; i < kk; i++) ptrs[i] = repmats[i].data();
-        CG(cgpu_reps_upload(mm, kk, bb.data(), ptrs.data(), &reps));
+        if (inrep) CG(cgpu_stats_upload(cm, kk, bb.data(), ptrs.data(), &reps));
+        else CG(cgpu_reps_upload(mm, kk, bb.data(), ptrs.data(), &reps));
     }
     int i0 = 0;  // scale closest to r = 1 (find_i0, src/consel.c:1778-1789)
     for (int i = 1; i < kk; i++)
@@ -291,9 +348,11 @@ int main(int argc, char **argv) {
     std::vector<double> cimat, csmat, eimat, ci0mat, cs0mat, ei0mat, cntmat;
     std::vector<cgpu_rowsum> r0;
     if (doau || dobp || outrep || outcnt) {
-        printf("\n# calculate replicates of the statistics");
-        CG(cgpu_stats_build(reps, cm, ass.ptr.data(), ass.idx.data()));
-        dots(kk);
+        if (!inrep) {
+            printf("\n# calculate replicates of the statistics");
+            CG(cgpu_stats_build(reps, cm, ass.ptr.data(), ass.idx.data()));
+            dots(kk);
+        }
         // one query at the region threshold serves BP, the .cnt file and the row extremes
         std::vector<double> thr(cm, threshold);
         r0.resize((size_t)cm * kk);
@@ -373,6 +432,7 @@ int main(int argc, char **argv) {
         printf("\n# AU-TEST DONE");
     }
 
+    if (inrep && !doau) outrep = outcnt = false;  // do_repmode writes them only after the AU test (:1236-1240)
     if (outcnt && (doau || dobp)) {
         cntmat.resize((size_t)cm * kk);
         for (int i = 0; i < cm; i++)
@@ -457,8 +517,9 @@ int main(int argc, char **argv) {
         // the reference writes the rows after do_bootrep/do_bptest sorted them in place
         const bool sorted = doau || dobp;
         CG(cgpu_stats_download(reps, sorted ? 1 : 0, ptrs.data()));
+        const std::string repbase = (inrep && fname_in) ? std::string(fname_in) : outbase;  // fname_rep (:438, :443)
         if (fname_out) {
-            FILE *fp = open_file(fname_out, ".rep", "wb", &used);
+            FILE *fp = open_file(repbase.c_str(), ".rep", "wb", &used);
             printf("\n# writing %s", used.c_str());
             write_bivec(fp, orderv.data(), cm);
             write_bvec(fp, obsvec.data(), cm);

@@ -116,6 +116,12 @@ int cgpu_reps_upload(int K, int S, const int *bb, const double *const *rep, cgpu
  * min_{i in A_e} ( max_{j != i} rep[j][b] - rep[i][b] ).  Associations in CSR form,
  * already permuted into the output item order (orderv, src/consel.c:514-530).     */
 int cgpu_stats_build(cgpu_reps *r, int cm, const int *ass_ptr, const int *ass_idx);
+/* Replaces the fread_blmat'ed statmats of rep mode (consel -R, do_repmode
+ * src/consel.c:1195-1212): a handle over statistic blocks that already exist
+ * (stat[s] = cm x bb[s] doubles row-major, sorted or not).  It has no replicate blocks:
+ * count queries, order statistics and downloads work, cgpu_stats_build and cgpu_mctest
+ * return CGPU_EINVAL.                                                                */
+int cgpu_stats_upload(int cm, int S, const int *bb, const double *const *stat, cgpu_reps **out);
 /* stat_out[s] = cm x nb[s] doubles row-major (nb[s] = bb[s] unless sharded); sorted != 0
  * sorts every row ascending like sort_vec (src/consel.c:1466-1471) — the payload of
  * `.rep` (unsharded only).                                                           */

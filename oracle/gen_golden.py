@@ -9,6 +9,7 @@ Fixtures
   mam15.lnf                 reference example input (example/mam15.lnf), config C1
   g100.{rmt,vt,pv,ci,cnt,rep,txt}   makermt -s 1234 -b 0.01 --paml mam15 ; consel -r -c ; catpv
   g100e.{pv,ci,cnt,rep,txt} + mam15.ass   treeass mam15 ; consel -a (edge associations)
+  g100R / g100eR .{pv,ci,cnt}             consel -R on the two .rep files above (rep mode)
   tiny.{mt,pa,rmt,vt,...}   synthetic K=6 n=40, ragged scales/replicate counts
   MANIFEST.json             md5 of every fixture + md5s of the full-size seeded runs
 """
@@ -57,6 +58,11 @@ def main() -> None:
     orc.run_ref("consel", ["-a", "mam15", "-r", "-c", "g100", "g100e"], work)
     (work / "g100e.txt").write_text(orc.run_ref("catpv", ["g100e"], work))
     keep += ["mam15.ass"] + [f"g100e.{e}" for e in ("pv", "ci", "cnt", "rep", "txt")]
+
+    # --- rep mode (consel -R): BP/AU from the statistic rows of a .rep file
+    for case in ("g100", "g100e"):
+        orc.run_ref("consel", ["-R", "-c", case, case + "R"], work)
+        keep += [f"{case}R.{e}" for e in ("pv", "ci", "cnt")]
 
     # --- tiny: synthetic ragged case (different r and B per scale, bn < n and > n)
     rng = np.random.Generator(np.random.PCG64(20261019))

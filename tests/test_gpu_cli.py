@@ -57,6 +57,26 @@ def test_consel_with_edge_associations(gold, orc, tmp_path):
     assert run("catpv", ["g100e"], tmp_path) == (gold / "g100e.txt").read_text()
 
 
+@pytest.mark.parametrize("case", ["g100", "g100e"])
+def test_consel_rep_mode(case, gold, orc, tmp_path):
+    """consel -R (do_repmode, src/consel.c:1195-1242): BP and AU from the rows of a .rep file,
+    against what the reference wrote for the same file."""
+    shutil.copy(gold / f"{case}.rep", tmp_path / f"{case}.rep")
+    out = run("consel", ["-R", "-c", case, case + "R"], tmp_path)
+    assert "# exit normally" in out and "MC-TEST" not in out
+    assert (tmp_path / f"{case}R.cnt").read_bytes() == (gold / f"{case}R.cnt").read_bytes()
+    same_numbers(tmp_path / f"{case}R.pv", gold / f"{case}R.pv", orc)
+    same_numbers(tmp_path / f"{case}R.ci", gold / f"{case}R.ci", orc)
+    # -r in rep mode rewrites the INPUT file name (fname_rep), rows sorted: a .rep written by consel is a fixed point
+    before = (tmp_path / f"{case}.rep").read_bytes()
+    run("consel", ["-R", "-r", case, case + "R2"], tmp_path)
+    assert (tmp_path / f"{case}.rep").read_bytes() == before
+    assert not (tmp_path / f"{case}R2.rep").exists()
+    # without the AU test nothing but the .pv is written (:1236-1240)
+    run("consel", ["-R", "-c", "--no_au", case, case + "R3"], tmp_path)
+    assert (tmp_path / f"{case}R3.pv").exists() and not (tmp_path / f"{case}R3.cnt").exists()
+
+
 def test_cli_error_protocol(tmp_path):
     r = subprocess.run([str(BIN / "makermt"), "--bogus"], cwd=tmp_path, capture_output=True, text=True)
     assert r.returncode == 1 and "#! Terminated: error in command line." in r.stdout

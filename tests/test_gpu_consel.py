@@ -159,3 +159,30 @@ def test_count_query_rows_equals_slices_of_the_whole_query(cg, orc, gold):
             assert part.tobytes() == whole[row0:row0 + rows].tobytes(), (nq, row0)
     with pytest.raises(cg.CgpuError):
         reps.count_query_rows(cm - 1, np.zeros((2, 1)))
+
+
+@pytest.mark.parametrize("name", ["g100e", "tiny"])
+def test_uploaded_statistics_serve_the_same_queries(cg, orc, gold, name):
+    """cgpu_stats_upload (rep mode, src/consel.c:1195-1212): a handle over the rows of a .rep file
+    answers count queries / order statistics exactly like one built from the replicates."""
+    rmt, sptr, sidx = _case(orc, gold, name)
+    rep = orc.read_rep(gold / f"{name}.rep")
+    built = cg.Reps.upload(rmt["reps"])
+    built.stats_build(sptr, sidx)
+    up = cg.Reps.upload_stats(rep["stats"])
+    assert up.cm == built.cm and up.S == built.S
+    rng = np.random.default_rng(11)
+    i0 = orc.find_i0(rmt["rr"])
+    row0 = rep["stats"][i0]
+    thr = np.stack([np.zeros(up.cm), row0[:, 0], row0[:, -1], rng.uniform(row0[:, 0], row0[:, -1])], axis=1)
+    a, b = built.count_query(thr), up.count_query(thr)
+    for f in a.dtype.names:
+        assert np.array_equal(a[f], b[f]), f
+    B = int(rmt["bb"][i0])
+    rank = np.full(up.cm, B // 2)
+    assert np.array_equal(up.order_stat(i0, rank), row0[:, B // 2])
+    got = up.stats_download(sorted_rows=True)
+    for s in range(up.S):
+        assert np.array_equal(got[s], rep["stats"][s])
+    with pytest.raises(cg.CgpuError):
+        up.stats_build(sptr, sidx)
