@@ -226,6 +226,18 @@ class Reps:
         self.cm = len(ass_ptr) - 1
         _check(load().cgpu_stats_build(self._h, self.cm, _ip(ass_ptr), _ip(ass_idx)))
 
+    def stats_build_rescaled(self, i0: int, rs, ass_ptr, ass_idx) -> "Reps":
+        """consel -f: statistics of len(rs) target scales derived from scale i0 (cgpu_stats_build_rescaled)."""
+        rs = np.ascontiguousarray(rs, dtype=np.float64)
+        ass_ptr = np.ascontiguousarray(ass_ptr, dtype=np.int32)
+        ass_idx = np.ascontiguousarray(ass_idx, dtype=np.int32)
+        h = C.c_void_p()
+        _check(load().cgpu_stats_build_rescaled(self._h, int(i0), len(rs), _dp(rs), len(ass_ptr) - 1, _ip(ass_ptr),
+                                                _ip(ass_idx), C.byref(h)))
+        r = Reps(h, 0, np.full(len(rs), int(self.bb[i0]), dtype=np.int32))
+        r.cm = len(ass_ptr) - 1
+        return r
+
     def stats_download(self, sorted_rows: bool = False):
         out = [np.zeros((self.cm, nb), dtype=np.float64) for nb in self._local_cols()]
         _check(load().cgpu_stats_download(self._h, int(sorted_rows), _ptr_array(out)))

@@ -225,6 +225,66 @@ int cgpu_stats_build(cgpu_reps *rr, int cm, const int *ass_ptr, const int *ass_i
     return CGPU_OK;
 }
 
+// consel -f (genrep's rescaling branch, src/consel.c:757-771, repminmaxsrs :1961-1984): the
+// statistics of S1 target scales, all derived from the replicates of scale i0 pulled towards
+// their row means by rs[s] = sqrt(rr[i0]/rr1[s]) (computed by the caller, like the reference).
+int cgpu_stats_build_rescaled(const cgpu_reps *src, int i0, int S1, const double *rs, int cm, const int *ass_ptr,
+                              const int *ass_idx, cgpu_reps **out) {
+    CGPU_TRY(ensure_init());
+    const DevReps *q = reinterpret_cast<const DevReps *>(src);
+    if (!q || q->K <= 0 || i0 < 0 || i0 >= q->S || S1 <= 0 || !rs || !out) {
+        set_error(CGPU_EINVAL, "stats_build_rescaled: bad arguments");
+        return CGPU_EINVAL;
+    }
+    const int K = q->K, B = q->nb[i0];
+    CGPU_TRY(check_csr(K, cm, ass_ptr, ass_idx));
+    if (B != q->bb[i0] || B <= 0) {
+        set_error(CGPU_EINVAL, "stats_build_rescaled needs every replicate of scale %d on this device (row means are sequential sums)", i0);
+        return CGPU_EINVAL;
+    }
+    cudaStream_t st = G().stream;
+    DevReps *r = new DevReps();
+    r->K = 0;
+    r->S = S1;
+    r->cm = cm;
+    r->bb = (int *)calloc(S1, sizeof(int));
+    r->b0 = (int *)calloc(S1, sizeof(int));
+    r->nb = (int *)calloc(S1, sizeof(int));
+    r->d_rep = (double **)calloc(S1, sizeof(double *));
+    r->d_stat = (double **)calloc(S1, sizeof(double *));
+    auto fail = [&](int rc) {
+        cgpu_reps_free(reinterpret_cast<cgpu_reps *>(r));
+        return rc;
+    };
+    DevBuf xs, m1, m2, a1, d_ptr, d_idx;
+    int rc = xs.alloc((size_t)K * B * 8);
+    if (rc == CGPU_OK) rc = m1.alloc((size_t)B * 8);
+    if (rc == CGPU_OK) rc = m2.alloc((size_t)B * 8);
+    if (rc == CGPU_OK) rc = a1.alloc((size_t)B * 4);
+    if (rc == CGPU_OK) rc = d_ptr.upload(ass_ptr, (size_t)(cm + 1), st);
+    if (rc == CGPU_OK) rc = d_idx.upload(ass_idx, (size_t)std::max(1, ass_ptr[cm]), st);
+    if (rc != CGPU_OK) return fail(rc);
+    for (int s = 0; s < S1; s++) {
+        r->bb[s] = r->nb[s] = B;
+        if (dev_alloc(&r->d_stat[s], (size_t)cm * B * sizeof(double)) != cudaSuccess) {
+            set_error(CGPU_ENOMEM, "stats_build_rescaled: device allocation for scale %d", s);
+            return fail(CGPU_ENOMEM);
+        }
+        rc = launch_center(q->d_rep[i0], K, B, B, xs.as<double>(), st, true, rs[s]);
+        if (rc == CGPU_OK) rc = launch_col_top2(xs.as<double>(), K, B, B, m1.as<double>(), m2.as<double>(), a1.as<int>(), st);
+        if (rc == CGPU_OK)
+            rc = launch_stat_build(xs.as<double>(), K, B, B, m1.as<double>(), m2.as<double>(), a1.as<int>(), cm,
+                                   d_ptr.as<int>(), d_idx.as<int>(), r->d_stat[s], st);
+        if (rc != CGPU_OK) return fail(rc);
+    }
+    if (cudaStreamSynchronize(st) != cudaSuccess) {
+        set_error(CGPU_ECUDA, "stats_build_rescaled: sync failed");
+        return fail(CGPU_ECUDA);
+    }
+    *out = reinterpret_cast<cgpu_reps *>(r);
+    return CGPU_OK;
+}
+
 int cgpu_stats_download(const cgpu_reps *rr, int sorted, double *const *stat_out) {
     CGPU_TRY(ensure_init());
     const DevReps *r = reinterpret_cast<const DevReps *>(rr);

@@ -240,7 +240,9 @@ int launch_order_stat(const double *d_stat, int rows, int B, int ld, const int *
 int launch_col_top2(const double *x, int K, int B, int ld, double *m1, double *m2, int *a1, cudaStream_t st);
 int launch_stat_build(const double *x, int K, int B, int ld, const double *m1, const double *m2, const int *a1,
                       int cm, const int *ass_ptr, const int *ass_idx, double *stat, cudaStream_t st);
-int launch_center(const double *x, int K, int B, int ld, double *xc, cudaStream_t st);
+// xc = x - rowmean (rescale == false) or rs*(x - rowmean) + rowmean (consel -f); rowmean = sequential sum / B
+int launch_center(const double *x, int K, int B, int ld, double *xc, cudaStream_t st, bool rescale = false,
+                  double rs = 1.0);
 int launch_pair_weight(const double *xc, int K, int B, int ld, double varadd, double *wt, int *nsmall, cudaStream_t st);
 int launch_sh_rows(bool weighted, const double *x, int K, int B, int ld, const double *wt, int nmem,
                    const int *mem_item, const int *mem_tree, const int *cass_ptr, const int *cass_idx, double *out,

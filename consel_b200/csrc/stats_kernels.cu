@@ -548,7 +548,7 @@ int launch_order_stat(const double *d_stat, int rows, int B, int ld, const int *
 // consecutive values, every lane replays the 32 adds through shuffles.
 constexpr int CR_CHUNK = 256;  // elements staged per warp and step
 __global__ void __launch_bounds__(128)
-center_rows_kernel(const double *__restrict__ x, int K, int B, int ld, double *__restrict__ xc) {
+center_rows_kernel(const double *__restrict__ x, int K, int B, int ld, double *__restrict__ xc, bool rescale, double rs) {
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + w;
     __shared__ double stage[4][CR_CHUNK];
@@ -585,7 +585,11 @@ center_rows_kernel(const double *__restrict__ x, int K, int B, int ld, double *_
     }
     const double mean = __ddiv_rn(s, (double)B);
     double *dst = xc + (size_t)row * ld;
-    for (int b = lane; b < B; b += 32) dst[b] = __dsub_rn(src[b], mean);
+    if (rescale) {  // repminmaxsrs (src/consel.c:1978): rs*(x - mean) + mean, three roundings
+        for (int b = lane; b < B; b += 32) dst[b] = __dadd_rn(__dmul_rn(rs, __dsub_rn(src[b], mean)), mean);
+    } else {
+        for (int b = lane; b < B; b += 32) dst[b] = __dsub_rn(src[b], mean);
+    }
 }
 
 // pairwise variances -> weights (src/consel.c:1404-1415):
@@ -726,8 +730,8 @@ int launch_stat_build(const double *x, int K, int B, int ld, const double *m1, c
     CGPU_LAUNCH_CHECK();
     return CGPU_OK;
 }
-int launch_center(const double *x, int K, int B, int ld, double *xc, cudaStream_t st) {
-    center_rows_kernel<<<(K + 3) / 4, 128, 0, st>>>(x, K, B, ld, xc);
+int launch_center(const double *x, int K, int B, int ld, double *xc, cudaStream_t st, bool rescale, double rs) {
+    center_rows_kernel<<<(K + 3) / 4, 128, 0, st>>>(x, K, B, ld, xc, rescale, rs);
     CGPU_LAUNCH_CHECK();
     return CGPU_OK;
 }

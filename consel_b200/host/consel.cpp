@@ -11,8 +11,12 @@
 // file) to the same count queries through cgpu_stats_upload: BP and AU only, like the
 // reference.
 //
+// The rescaling approximation (-f [-p scales.pa], genrep :757-771) derives the statistics of
+// every target scale from the replicates of the scale nearest r=1 on the device
+// (cgpu_stats_build_rescaled).
+//
 // Not carried by this build (error at the command line): -C input mode, -g multi-gene
-// mode, -f rescaling approximation, --chi* spherical fit, --pdm AIC correction,
+// mode, --chi* spherical fit, --pdm AIC correction,
 // --quick_mctest.  They are off the hot path (SURVEY 8f "next").
 #include <cmath>
 #include <cstdio>
@@ -53,7 +57,8 @@ struct Assoc {
 };
 
 int main(int argc, char **argv) {
-    const char *fname_in = nullptr, *fname_out_arg = nullptr, *fname_ass = nullptr, *fname_vt = nullptr;
+    const char *fname_in = nullptr, *fname_out_arg = nullptr, *fname_ass = nullptr, *fname_vt = nullptr, *fname_pa = nullptr;
+    bool fastrep = false;
     bool outrep = false, outcnt = false, smoothcnt = false, nosort = false, inrep = false;
     bool dobp = true, doba = true, domc = true, doau = true;
     int cm_arg = 0, gpu = -1;
@@ -74,6 +79,8 @@ int main(int argc, char **argv) {
             j++;
         } else if (a == "-r") outrep = true;
         else if (a == "-R") inrep = true;
+        else if (a == "-f") fastrep = true;
+        else if (a == "-p") { need(); fname_pa = argv[++i]; }
         else if (a == "-c") outcnt = true;
         else if (a == "-a") { need(); fname_ass = argv[++i]; }
         else if (a == "-v") { need(); fname_vt = argv[++i]; }
@@ -97,7 +104,7 @@ int main(int argc, char **argv) {
         else if (a == "--mle") opt.fitmode = aufit::FIT_MLE;
         else if (a == "--wls") opt.fitmode = aufit::FIT_WLS;
         else if (a == "--gpu") integer(&gpu);
-        else if (a == "-C" || a == "-g" || a == "-f" || a == "-p" || a == "--pdm" ||
+        else if (a == "-C" || a == "-g" || a == "--pdm" ||
                  a == "--quick_mctest" || a.rfind("--chi", 0) == 0 || a == "--aictype" || a == "--ppn" ||
                  a == "--pmin" || a == "--congbp")
             die("switch %s is not supported by the B200 build of consel (rmt and rep modes only)", a.c_str());
@@ -294,6 +301,19 @@ int main(int argc, char **argv) {
         fclose(fp);
     }
     const int nalpha = (int)alphavec.size();
+    std::vector<double> rr1 = {0.5, 0.6, 0.7, 0.8, 0.9, 1.0, 1.1, 1.2, 1.3, 1.4};  // rr0, src/consel.c:162-163
+    if (fastrep && !inrep) {  // read_scale, src/consel.c:562-582
+        if (fname_pa) {
+            FILE *fp = open_file(fname_pa, ".pa", "r", &used);
+            printf("\n# reading %s", used.c_str());
+            rr1 = read_vec(fp);
+            fclose(fp);
+        }
+        printf("\n# RESCALING");
+        printf("\n# K:%d", (int)rr1.size());
+        printf("\n# R:");
+        for (double r : rr1) printf("%g ", r);
+    }
 
     // ---------------- Bayesian posterior (do_batest, src/consel.c:1311-1340)
     std::vector<double> bapvec(cm, 0.0);
@@ -348,7 +368,23 @@ int main(int argc, char **argv) {
     std::vector<double> cimat, csmat, eimat, ci0mat, cs0mat, ei0mat, cntmat;
     std::vector<cgpu_rowsum> r0;
     if (doau || dobp || outrep || outcnt) {
-        if (!inrep) {
+        if (!inrep && fastrep) {  // genrep's rescaling branch (src/consel.c:757-771)
+            printf("\n# calculate replicates of the statistics");
+            const int kk1 = (int)rr1.size();
+            std::vector<double> rs(kk1);
+            for (int i = 0; i < kk1; i++) rs[i] = sqrt(rr[i0] / rr1[i]);
+            cgpu_reps *scaled = nullptr;
+            CG(cgpu_stats_build_rescaled(reps, i0, kk1, rs.data(), cm, ass.ptr.data(), ass.idx.data(), &scaled));
+            dots(kk1);
+            cgpu_reps_free(reps);  // the KH/SH tests are done; everything below reads the statistics only
+            reps = scaled;
+            bb.assign(kk1, nb0);
+            rr = rr1;
+            kk = kk1;
+            i0 = 0;  // find_i0 again on the new scales (do_bptest :1293, do_bootrep :1463)
+            for (int i = 1; i < kk; i++)
+                if (fabs(rr[i] - 1.0) < fabs(rr[i0] - 1.0)) i0 = i;
+        } else if (!inrep) {
             printf("\n# calculate replicates of the statistics");
             CG(cgpu_stats_build(reps, cm, ass.ptr.data(), ass.idx.data()));
             dots(kk);

@@ -122,6 +122,14 @@ int cgpu_stats_build(cgpu_reps *r, int cm, const int *ass_ptr, const int *ass_id
  * count queries, order statistics and downloads work, cgpu_stats_build and cgpu_mctest
  * return CGPU_EINVAL.                                                                */
 int cgpu_stats_upload(int cm, int S, const int *bb, const double *const *stat, cgpu_reps **out);
+/* Replaces the rescaling branch of genrep (consel -f, src/consel.c:757-771) with
+ * repminmaxsrs (:1961-1984): statistic blocks of S1 target scales, all from the replicates
+ * of scale i0 of `src`: x' = rs[s]*(x - mean) + mean per tree row (mean = sequential sum / B,
+ * three rounded operations), then the statistics of cgpu_stats_build.  rs[s] =
+ * sqrt(rr[i0]/rr1[s]) is computed by the caller.  `out` is a statistics-only handle (like
+ * cgpu_stats_upload) with S1 scales of bb[i0] replicates; `src` stays valid for cgpu_mctest. */
+int cgpu_stats_build_rescaled(const cgpu_reps *src, int i0, int S1, const double *rs, int cm,
+                              const int *ass_ptr, const int *ass_idx, cgpu_reps **out);
 /* stat_out[s] = cm x nb[s] doubles row-major (nb[s] = bb[s] unless sharded); sorted != 0
  * sorts every row ascending like sort_vec (src/consel.c:1466-1471) — the payload of
  * `.rep` (unsharded only).                                                           */

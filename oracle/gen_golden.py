@@ -10,6 +10,7 @@ Fixtures
   g100.{rmt,vt,pv,ci,cnt,rep,txt}   makermt -s 1234 -b 0.01 --paml mam15 ; consel -r -c ; catpv
   g100e.{pv,ci,cnt,rep,txt} + mam15.ass   treeass mam15 ; consel -a (edge associations)
   g100R / g100eR .{pv,ci,cnt}             consel -R on the two .rep files above (rep mode)
+  g100f / g100fe .{pv,ci,cnt,rep} + fscale.pa   consel -f [-p fscale -a mam15] (rescaling approximation)
   tiny.{mt,pa,rmt,vt,...}   synthetic K=6 n=40, ragged scales/replicate counts
   MANIFEST.json             md5 of every fixture + md5s of the full-size seeded runs
 """
@@ -63,6 +64,12 @@ def main() -> None:
     for case in ("g100", "g100e"):
         orc.run_ref("consel", ["-R", "-c", case, case + "R"], work)
         keep += [f"{case}R.{e}" for e in ("pv", "ci", "cnt")]
+
+    # --- rescaling approximation (consel -f): default target scales, and scales from a .pa file
+    orc.run_ref("consel", ["-f", "-r", "-c", "g100", "g100f"], work)
+    orc.write_pa(work / "fscale.pa", [0.4, 0.75, 1.0, 1.6], [1, 1, 1, 1])
+    orc.run_ref("consel", ["-f", "-p", "fscale", "-a", "mam15", "-r", "-c", "g100", "g100fe"], work)
+    keep += ["fscale.pa"] + [f"{c}.{e}" for c in ("g100f", "g100fe") for e in ("pv", "ci", "cnt", "rep")]
 
     # --- tiny: synthetic ragged case (different r and B per scale, bn < n and > n)
     rng = np.random.Generator(np.random.PCG64(20261019))

@@ -140,6 +140,17 @@ def repminmaxs(rep: np.ndarray, ass_ptr, ass_idx) -> np.ndarray:
     return stat
 
 
+def repminmaxs_rescaled(rep: np.ndarray, ass_ptr, ass_idx, rs: float) -> np.ndarray:
+    """consel -f: genrep's rescaling branch (src/consel.c:762-769) + repminmaxsrs (:1961-1984).
+    Row mean = left-to-right sum / B (cumsum is that chain), x' = rs*(x - mean) + mean with
+    every operation rounded on its own, then the ordinary statistics."""
+    rep = np.ascontiguousarray(rep, dtype=np.float64)
+    mean = (np.cumsum(rep, axis=1)[:, -1] / rep.shape[1])[:, None]
+    d = rep - mean
+    d = rs * d
+    return repminmaxs(d + mean, ass_ptr, ass_idx)
+
+
 def obs_stat(datvec, ass_ptr, ass_idx) -> np.ndarray:
     datvec = np.ascontiguousarray(datvec, dtype=np.float64)
     ass_ptr = np.ascontiguousarray(ass_ptr, dtype=np.int32)

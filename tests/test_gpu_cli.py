@@ -77,6 +77,24 @@ def test_consel_rep_mode(case, gold, orc, tmp_path):
     assert (tmp_path / f"{case}R3.pv").exists() and not (tmp_path / f"{case}R3.cnt").exists()
 
 
+@pytest.mark.parametrize("case", ["g100f", "g100fe"])
+def test_consel_rescaling_approximation(case, gold, orc, tmp_path):
+    """consel -f [-p scales] (genrep's rescaling branch, src/consel.c:757-771): all target scales
+    from the replicates of the scale nearest r=1, against the reference's own -f run."""
+    shutil.copy(gold / "g100.rmt", tmp_path / "g100.rmt")
+    args = ["-f", "-r", "-c", "g100", case]
+    if case == "g100fe":
+        shutil.copy(gold / "mam15.ass", tmp_path / "mam15.ass")
+        shutil.copy(gold / "fscale.pa", tmp_path / "fscale.pa")
+        args = ["-f", "-p", "fscale", "-a", "mam15", "-r", "-c", "g100", case]
+    out = run("consel", args, tmp_path)
+    assert "# RESCALING" in out and "# exit normally" in out
+    assert (tmp_path / f"{case}.rep").read_bytes() == (gold / f"{case}.rep").read_bytes()
+    assert (tmp_path / f"{case}.cnt").read_bytes() == (gold / f"{case}.cnt").read_bytes()
+    same_numbers(tmp_path / f"{case}.pv", gold / f"{case}.pv", orc)
+    same_numbers(tmp_path / f"{case}.ci", gold / f"{case}.ci", orc)
+
+
 def test_cli_error_protocol(tmp_path):
     r = subprocess.run([str(BIN / "makermt"), "--bogus"], cwd=tmp_path, capture_output=True, text=True)
     assert r.returncode == 1 and "#! Terminated: error in command line." in r.stdout

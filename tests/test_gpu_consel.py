@@ -186,3 +186,34 @@ def test_uploaded_statistics_serve_the_same_queries(cg, orc, gold, name):
         assert np.array_equal(got[s], rep["stats"][s])
     with pytest.raises(cg.CgpuError):
         up.stats_build(sptr, sidx)
+
+
+@pytest.mark.parametrize("name", ["g100", "g100e", "tiny"])
+def test_rescaled_statistics_bit_exact(cg, orc, gold, name):
+    """cgpu_stats_build_rescaled (consel -f, repminmaxsrs src/consel.c:1961-1984) against the oracle:
+    sequential row mean, three rounded operations per element, then the ordinary statistics."""
+    rmt, sptr, sidx = _case(orc, gold, name)
+    i0 = orc.find_i0(rmt["rr"])
+    rs = np.sqrt(rmt["rr"][i0] / np.array([0.3, 0.75, 1.0, 1.9, 4.0]))
+    reps = cg.Reps.upload(rmt["reps"])
+    scaled = reps.stats_build_rescaled(i0, rs, sptr, sidx)
+    assert scaled.S == len(rs) and scaled.cm == len(sptr) - 1
+    got = scaled.stats_download()
+    for s in range(len(rs)):
+        assert np.array_equal(got[s], orc.repminmaxs_rescaled(rmt["reps"][i0], sptr, sidx, float(rs[s]))), s
+    # the source handle is untouched and still serves the ordinary build
+    reps.stats_build(sptr, sidx)
+    assert np.array_equal(reps.stats_download()[i0], orc.repminmaxs(rmt["reps"][i0], sptr, sidx))
+
+
+def test_rescaled_statistics_long_rows(cg, orc):
+    """Row means over more than one staging chunk per warp and a ragged tail (B = 1000 + 37)."""
+    rng = np.random.default_rng(5)
+    K, B = 23, 1037
+    rep = -3000.0 + 40.0 * rng.standard_normal((K, B))
+    ptr, idx = orc.identity_assoc(K)
+    reps = cg.Reps.upload([rep])
+    scaled = reps.stats_build_rescaled(0, np.array([1.25, 0.8]), ptr, idx)
+    got = scaled.stats_download()
+    for s, r in enumerate((1.25, 0.8)):
+        assert np.array_equal(got[s], orc.repminmaxs_rescaled(rep, ptr, idx, r)), s
