@@ -12,6 +12,7 @@ Fixtures
   g100R / g100eR .{pv,ci,cnt}             consel -R on the two .rep files above (rep mode)
   g100f / g100fe .{pv,ci,cnt,rep} + fscale.pa   consel -f [-p fscale -a mam15] (rescaling approximation)
   tiny.{mt,pa,rmt,vt,...}   synthetic K=6 n=40, ragged scales/replicate counts
+  mr100e.rep, tinymr.rep + mr.pa   makerep -s 1234 -p mr -a mam15 --paml mam15 ; makerep -s 7 -p tiny tiny
   MANIFEST.json             md5 of every fixture + md5s of the full-size seeded runs
 """
 from __future__ import annotations
@@ -82,6 +83,12 @@ def main() -> None:
     orc.run_ref("consel", ["-r", "-c", "tiny"], work)
     (work / "tiny.txt").write_text(orc.run_ref("catpv", ["tiny"], work))
     keep += [f"tiny.{e}" for e in ("mt", "pa", "rmt", "vt", "pv", "ci", "cnt", "rep", "txt")]
+
+    # --- makerep: resampling + statistics in one process (rows unsorted), same seeds as above
+    orc.write_pa(work / "mr.pa", [0.5, 0.6, 0.7, 0.8, 0.9, 1.0, 1.1, 1.2, 1.3, 1.4], [100] * 10)
+    orc.run_ref("makerep", ["-s", "1234", "-p", "mr", "-a", "mam15", "--paml", "mam15", "mr100e"], work)
+    orc.run_ref("makerep", ["-s", "7", "-p", "tiny", "tiny", "tinymr"], work)
+    keep += ["mr.pa", "mr100e.rep", "tinymr.rep"]
 
     for name in keep:
         shutil.copy(work / name, GOLD / name)

@@ -95,6 +95,28 @@ def test_consel_rescaling_approximation(case, gold, orc, tmp_path):
     same_numbers(tmp_path / f"{case}.ci", gold / f"{case}.ci", orc)
 
 
+def test_makerep_matches_reference(gold, orc, tmp_path):
+    """makerep (src/makerep.c:304-331): resampling + statistics in one process; the .rep files
+    (rows unsorted) byte-equal to the ones the reference's makerep wrote for the same seeds, and
+    consel -R on them gives the reference's BP/AU numbers."""
+    for f in ("mam15.lnf", "mam15.ass", "mr.pa", "tiny.mt", "tiny.pa"):
+        shutil.copy(gold / f, tmp_path / f)
+    out = run("makerep", ["-s", "1234", "-p", "mr", "-a", "mam15", "--paml", "mam15", "mr100e"], tmp_path)
+    assert "# exit normally" in out and "# CM:10" in out
+    assert (tmp_path / "mr100e.rep").read_bytes() == (gold / "mr100e.rep").read_bytes()
+    run("makerep", ["-s", "7", "-p", "tiny", "tiny", "tinymr"], tmp_path)
+    assert (tmp_path / "tinymr.rep").read_bytes() == (gold / "tinymr.rep").read_bytes()
+    # same replicates as makermt | consel -a: rep mode on makerep's file reproduces that run's BP/AU
+    run("consel", ["-R", "-c", "mr100e", "mr100eR"], tmp_path)
+    assert (tmp_path / "mr100eR.cnt").read_bytes() == (gold / "g100eR.cnt").read_bytes()
+    same_numbers(tmp_path / "mr100eR.pv", gold / "g100eR.pv", orc)
+    # int8 sums: exact sums correctly rounded, statistics within 1e-9 of the strict ones
+    run("makerep", ["-s", "1234", "-p", "mr", "-a", "mam15", "--paml", "mam15", "--sum", "int8", "mr100i"], tmp_path)
+    a, b = orc.read_rep(tmp_path / "mr100i.rep"), orc.read_rep(gold / "mr100e.rep")
+    for x, y in zip(a["stats"], b["stats"]):
+        assert np.allclose(x, y, rtol=0, atol=1e-9)
+
+
 def test_cli_error_protocol(tmp_path):
     r = subprocess.run([str(BIN / "makermt"), "--bogus"], cwd=tmp_path, capture_output=True, text=True)
     assert r.returncode == 1 and "#! Terminated: error in command line." in r.stdout
