@@ -15,9 +15,12 @@
 // every target scale from the replicates of the scale nearest r=1 on the device
 // (cgpu_stats_build_rescaled).
 //
-// Not carried by this build (error at the command line): -C input mode, -g multi-gene
-// mode, --chi* spherical fit, --pdm AIC correction,
+// Cnt mode (-C, do_cntmode :1244-1283) is host arithmetic only in the reference too: the AU
+// fit from the counts of a `.cnt` file, no replicates involved.
+//
+// Not carried by this build (error at the command line): -g multi-gene mode, --chi* spherical fit, --pdm AIC correction,
 // --quick_mctest.  They are off the hot path (SURVEY 8f "next").
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -46,10 +49,121 @@ static void dots(int n) {
 
 
 
+// ---------------------------------------------------------------- cnt mode (consel -C)
+// do_cntmode (src/consel.c:1244-1283) + do_bootcnt (:1540-1592): BP and the AU fit from the
+// count matrix of a `.cnt` file.  No replicates, no device: the reference's path is the
+// same host arithmetic.  rcalpval (:2703-2737) with its default pfmin = 0 makes exactly one
+// calcpval call, on the scales from the smallest r >= rmin that is below 1 upwards, and
+// reports "degenerated" without fitting when there is no scale in [rmin, 1).
+static void run_cntmode(const char *fname_in, const char *fname_out, bool dobp, bool doau, double threshold,
+                        const aufit::Options &opt) {
+    std::string used;
+    FILE *fp = stdin;
+    if (fname_in) {
+        fp = open_file(fname_in, ".cnt", "r", &used);
+        printf("\n# reading %s", used.c_str());
+    } else {
+        printf("\n# reading from stdin");
+    }
+    std::vector<int> orderv = read_ivec(fp);
+    int cm = (int)orderv.size(), kk = 0;
+    std::vector<double> obsvec = read_vec(fp, cm);
+    std::vector<double> rrmat = read_mat(fp, &cm, &kk), bbmat = read_mat(fp, &cm, &kk), cntmat = read_mat(fp, &cm, &kk);
+    if (fname_in) fclose(fp);
+    printf("\n# CM:%d", cm);
+    printf("\n# K:%d", kk);
+
+    std::vector<double> npvec(cm), nsvec(cm), pvvec(cm), sevec(cm), pv0vec(cm), se0vec(cm), rssvec(cm), dfvec(cm),
+        pfvec(cm), thvec(cm), beta(3 * (size_t)cm, 0.0);
+    if (dobp) {
+        for (int j = 0; j < cm; j++) {
+            const double *rr = &rrmat[(size_t)j * kk];
+            int i0 = 0;
+            for (int i = 1; i < kk; i++)
+                if (fabs(rr[i] - 1.0) < fabs(rr[i0] - 1.0)) i0 = i;
+            const double b = bbmat[(size_t)j * kk + i0];
+            npvec[j] = cntmat[(size_t)j * kk + i0] / b;
+            nsvec[j] = sqrt(npvec[j] * (1.0 - npvec[j]) / b);
+        }
+    }
+    if (doau) {
+        printf("\n# AU-TEST STARTS");
+        printf("\n# calculating approximately unbiased p-values by ");
+        printf(opt.fitmode == aufit::FIT_WLS ? "WLS (very fast)" : "MLE (fast)");
+        printf(" fitting");
+        fflush(stdout);
+        const double t0 = cpu_seconds();
+        for (int i = 0; i < cm; i++) {
+            const double *rr = &rrmat[(size_t)i * kk];
+            std::vector<double> rs(rr, rr + kk);
+            std::sort(rs.begin(), rs.end());
+            int i1 = 0;
+            while (i1 < kk && rs[i1] < opt.rrmin) i1++;
+            int i2 = i1;
+            while (i2 < kk && rs[i2] < 1.0) i2++;
+            aufit::Fit f;
+            int j = 1;
+            if (i1 < i2) {
+                f = aufit::calcpval(&cntmat[(size_t)i * kk], rr, &bbmat[(size_t)i * kk], kk, rs[i1], opt.rrmax, opt.kappa, opt);
+                j = f.rc;
+            }
+            pvvec[i] = f.pv; sevec[i] = f.se; pv0vec[i] = f.pv0;
+            if (cm > 1) se0vec[1] = f.se0;  // the reference passes `se0vec+1` for every item (:1567)
+            rssvec[i] = f.rss; dfvec[i] = f.df;
+            thvec[i] = threshold;  // unused in cnt mode
+            dprint(1, "\n# rank=%d item=%d", i + 1, orderv[i] + 1);
+            dprint(1, "\n# ret=%d", j);
+            if (j) {
+                pfvec[i] = 0.0;
+                warn("regression degenerated: df[%d]=%g", i + 1, dfvec[i]);
+            } else {
+                pfvec[i] = specfun::pochisq(rssvec[i], (int)dfvec[i]);
+                if (pfvec[i] < 0.01) warn("theory does not fit well: pfit[%d]=%.4f", i + 1, pfvec[i]);
+                for (int c = 0; c < 3; c++) beta[3 * (size_t)i + c] = f.beta[c];
+            }
+            putchar('.');
+            fflush(stdout);
+        }
+        printf("\n# time elapsed for AU test is t=%g sec", cpu_seconds() - t0);
+        printf("\n# AU-TEST DONE");
+    }
+    if (!(dobp || doau)) return;
+    // write_pv(sw_dobp,0,0,sw_doau) (src/consel.c:1611-1683)
+    fp = stdout;
+    if (fname_out) {
+        fp = open_file(fname_out, ".pv", "w", &used);
+        printf("\n# writing %s", used.c_str());
+    } else {
+        printf("\n# writing to stdout\n");
+    }
+    const int outbit = (dobp ? 1 : 0) + (doau ? 8 : 0), pvnum = (dobp ? 1 : 0) + (doau ? 2 : 0), auxnum = doau ? 7 : 0;
+    fprintf(fp, "\n# ID:\n%d\n", 1);
+    fprintf(fp, "\n# ITEM:\n"); write_ivec(fp, orderv.data(), cm);
+    fprintf(fp, "\n# STAT:\n"); write_vec(fp, obsvec.data(), cm);
+    fprintf(fp, "\n# BIT:\n%d\n", outbit);
+    std::vector<double> pvmat((size_t)cm * pvnum), semat((size_t)cm * pvnum), auxmat((size_t)cm * auxnum);
+    for (int i = 0; i < cm; i++) {
+        int j = 0;
+        if (dobp) { pvmat[(size_t)i * pvnum + j] = npvec[i]; semat[(size_t)i * pvnum + j] = nsvec[i]; j++; }
+        if (doau) {
+            pvmat[(size_t)i * pvnum + j] = pvvec[i]; semat[(size_t)i * pvnum + j] = sevec[i]; j++;
+            pvmat[(size_t)i * pvnum + j] = pv0vec[i]; semat[(size_t)i * pvnum + j] = se0vec[i]; j++;
+            double *ax = &auxmat[(size_t)i * auxnum];
+            ax[0] = pfvec[i]; ax[1] = rssvec[i]; ax[2] = dfvec[i];
+            ax[3] = beta[3 * (size_t)i]; ax[4] = beta[3 * (size_t)i + 1];
+            ax[5] = thvec[i]; ax[6] = beta[3 * (size_t)i + 2];
+        }
+    }
+    fprintf(fp, "\n# PV:\n"); write_mat(fp, pvmat.data(), cm, pvnum);
+    fprintf(fp, "\n# SE:\n"); write_mat(fp, semat.data(), cm, pvnum);
+    fprintf(fp, "\n# AX:\n"); write_mat(fp, auxnum ? auxmat.data() : pvmat.data(), cm, auxnum);
+    if (fname_out) fclose(fp);
+}
+
 int main(int argc, char **argv) {
     const char *fname_in = nullptr, *fname_out_arg = nullptr, *fname_ass = nullptr, *fname_vt = nullptr, *fname_pa = nullptr;
     bool fastrep = false;
-    bool outrep = false, outcnt = false, smoothcnt = false, nosort = false, inrep = false;
+    bool outrep = false, outcnt = false, smoothcnt = false, nosort = false, inrep = false, incnt = false;
     bool dobp = true, doba = true, domc = true, doau = true;
     int cm_arg = 0, gpu = -1;
     double threshold = 0.0, varadd = 1.0, bapcoef = 1.0;
@@ -69,6 +183,7 @@ int main(int argc, char **argv) {
             j++;
         } else if (a == "-r") outrep = true;
         else if (a == "-R") inrep = true;
+        else if (a == "-C") incnt = true;
         else if (a == "-f") fastrep = true;
         else if (a == "-p") { need(); fname_pa = argv[++i]; }
         else if (a == "-c") outcnt = true;
@@ -94,10 +209,10 @@ int main(int argc, char **argv) {
         else if (a == "--mle") opt.fitmode = aufit::FIT_MLE;
         else if (a == "--wls") opt.fitmode = aufit::FIT_WLS;
         else if (a == "--gpu") integer(&gpu);
-        else if (a == "-C" || a == "-g" || a == "--pdm" ||
+        else if (a == "-g" || a == "--pdm" ||
                  a == "--quick_mctest" || a.rfind("--chi", 0) == 0 || a == "--aictype" || a == "--ppn" ||
                  a == "--pmin" || a == "--congbp")
-            die("switch %s is not supported by the B200 build of consel (rmt and rep modes only)", a.c_str());
+            die("switch %s is not supported by the B200 build of consel (rmt, rep and cnt modes only)", a.c_str());
         else byebye();
     }
 
@@ -105,6 +220,13 @@ int main(int argc, char **argv) {
     if (fname_in && !fname_out_arg) fname_out_arg = fname_in;
     if (fname_out_arg) outbase = strip_extension(fname_out_arg);
     const char *fname_out = fname_out_arg ? outbase.c_str() : nullptr;
+
+    if (incnt && inrep) die("only one of -C and -R can be specified");
+    if (incnt) {
+        run_cntmode(fname_in, fname_out, dobp, doau, threshold, opt);
+        printf("\n# exit normally\n");
+        return 0;
+    }
 
     std::string used;
     std::vector<double> datvec, rr;

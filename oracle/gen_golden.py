@@ -13,6 +13,7 @@ Fixtures
   g100f / g100fe .{pv,ci,cnt,rep} + fscale.pa   consel -f [-p fscale -a mam15] (rescaling approximation)
   tiny.{mt,pa,rmt,vt,...}   synthetic K=6 n=40, ragged scales/replicate counts
   mr100e.rep, tinymr.rep + mr.pa   makerep -s 1234 -p mr -a mam15 --paml mam15 ; makerep -s 7 -p tiny tiny
+  {g100,g100e,tiny,g100fe}C.pv   consel -C on the .cnt files above (cnt mode)
   MANIFEST.json             md5 of every fixture + md5s of the full-size seeded runs
 """
 from __future__ import annotations
@@ -89,6 +90,11 @@ def main() -> None:
     orc.run_ref("makerep", ["-s", "1234", "-p", "mr", "-a", "mam15", "--paml", "mam15", "mr100e"], work)
     orc.run_ref("makerep", ["-s", "7", "-p", "tiny", "tiny", "tinymr"], work)
     keep += ["mr.pa", "mr100e.rep", "tinymr.rep"]
+
+    # --- cnt mode (consel -C): the AU fit from the counts alone
+    for case in ("g100", "g100e", "tiny", "g100fe"):
+        orc.run_ref("consel", ["-C", case, case + "C"], work)
+        keep.append(case + "C.pv")
 
     for name in keep:
         shutil.copy(work / name, GOLD / name)

@@ -154,3 +154,19 @@ def test_parallel_matrix_reader_equals_token_reader(tmp_path):
         assert (mm.value, nn.value) == (m, n)
         assert np.array_equal(out.view(np.uint64), a.ravel().view(np.uint64))
         assert word.value == b"TRAILER"
+
+
+@pytest.mark.parametrize("case", ["g100", "g100e", "tiny", "g100fe"])
+def test_consel_cnt_mode_cli(case, gold, tmp_path):
+    """consel -C (do_cntmode / do_bootcnt, src/consel.c:1244-1283, 1540-1592): host arithmetic only in
+    the reference too - the .pv is byte-equal to the reference's, degenerate items included."""
+    import shutil
+    import subprocess
+    from pathlib import Path
+    exe = Path(__file__).resolve().parent.parent / "consel_b200" / "bin" / "consel"
+    shutil.copy(gold / f"{case}.cnt", tmp_path / f"{case}.cnt")
+    r = subprocess.run([str(exe), "-C", case, case + "C"], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0 and "# exit normally" in r.stdout, r.stdout + r.stderr
+    assert (tmp_path / f"{case}C.pv").read_bytes() == (gold / f"{case}C.pv").read_bytes()
+    r = subprocess.run([str(exe), "-C", "-R", case], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 1 and "only one of -C and -R can be specified" in r.stdout
