@@ -18,7 +18,10 @@
 // Cnt mode (-C, do_cntmode :1244-1283) is host arithmetic only in the reference too: the AU
 // fit from the counts of a `.cnt` file, no replicates involved.
 //
-// Not carried by this build (error at the command line): -g multi-gene mode, --chi* spherical fit, --pdm AIC correction,
+// Multi-gene mode (-g, do_rmtmultimode :1056-1192): per gene the statistics and one count
+// query on the device, then congcnt and the count-matrix fit on the host.
+//
+// Not carried by this build (error at the command line): --chi* spherical fit, --pdm AIC correction,
 // --quick_mctest.  They are off the hot path (SURVEY 8f "next").
 #include <algorithm>
 #include <cmath>
@@ -49,12 +52,123 @@ static void dots(int n) {
 
 
 
-// ---------------------------------------------------------------- cnt mode (consel -C)
-// do_cntmode (src/consel.c:1244-1283) + do_bootcnt (:1540-1592): BP and the AU fit from the
-// count matrix of a `.cnt` file.  No replicates, no device: the reference's path is the
-// same host arithmetic.  rcalpval (:2703-2737) with its default pfmin = 0 makes exactly one
-// calcpval call, on the scales from the smallest r >= rmin that is below 1 upwards, and
-// reports "degenerated" without fitting when there is no scale in [rmin, 1).
+// ---------------------------------------------------------------- count-matrix modes
+// State shared by cnt mode (-C) and multi-gene mode (-g): per-item scale, replicate-count and
+// count matrices (cm x kk each) and what do_bootcnt / write_pv derive from them.
+struct CntWork {
+    int cm = 0, kk = 0;
+    std::vector<int> orderv;
+    std::vector<double> obsvec, rrmat, bbmat, cntmat;
+    std::vector<double> npvec, nsvec, bapvec, pvvec, sevec, pv0vec, se0vec, rssvec, dfvec, pfvec, thvec, beta;
+};
+
+// BP from the counts of the scale nearest r=1 (src/consel.c:1268-1275, :1168-1175)
+static void cnt_bptest(CntWork &w) {
+    w.npvec.assign(w.cm, 0.0);
+    w.nsvec.assign(w.cm, 0.0);
+    for (int j = 0; j < w.cm; j++) {
+        const double *rr = &w.rrmat[(size_t)j * w.kk];
+        int i0 = 0;
+        for (int i = 1; i < w.kk; i++)
+            if (fabs(rr[i] - 1.0) < fabs(rr[i0] - 1.0)) i0 = i;
+        const double b = w.bbmat[(size_t)j * w.kk + i0];
+        w.npvec[j] = w.cntmat[(size_t)j * w.kk + i0] / b;
+        w.nsvec[j] = sqrt(w.npvec[j] * (1.0 - w.npvec[j]) / b);
+    }
+}
+
+// do_bootcnt (src/consel.c:1540-1592).  rcalpval (:2703-2737) with its default pfmin = 0 makes
+// exactly one calcpval call, on the scales from the smallest r >= rmin that is below 1
+// upwards, and reports "degenerated" without fitting when there is no scale in [rmin, 1).
+static void cnt_bootcnt(CntWork &w, double threshold, const aufit::Options &opt) {
+    const int cm = w.cm, kk = w.kk;
+    for (auto *v : {&w.pvvec, &w.sevec, &w.pv0vec, &w.se0vec, &w.rssvec, &w.dfvec, &w.pfvec, &w.thvec}) v->assign(cm, 0.0);
+    w.beta.assign(3 * (size_t)cm, 0.0);
+    printf("\n# AU-TEST STARTS");
+    printf("\n# calculating approximately unbiased p-values by ");
+    printf(opt.fitmode == aufit::FIT_WLS ? "WLS (very fast)" : "MLE (fast)");
+    printf(" fitting");
+    fflush(stdout);
+    const double t0 = cpu_seconds();
+    for (int i = 0; i < cm; i++) {
+        const double *rr = &w.rrmat[(size_t)i * kk];
+        std::vector<double> rs(rr, rr + kk);
+        std::sort(rs.begin(), rs.end());
+        int i1 = 0;
+        while (i1 < kk && rs[i1] < opt.rrmin) i1++;
+        int i2 = i1;
+        while (i2 < kk && rs[i2] < 1.0) i2++;
+        aufit::Fit f;
+        int j = 1;
+        if (i1 < i2) {
+            f = aufit::calcpval(&w.cntmat[(size_t)i * kk], rr, &w.bbmat[(size_t)i * kk], kk, rs[i1], opt.rrmax, opt.kappa, opt);
+            j = f.rc;
+        }
+        w.pvvec[i] = f.pv; w.sevec[i] = f.se; w.pv0vec[i] = f.pv0;
+        if (cm > 1) w.se0vec[1] = f.se0;  // the reference passes `se0vec+1` for every item (:1567)
+        w.rssvec[i] = f.rss; w.dfvec[i] = f.df;
+        w.thvec[i] = threshold;  // unused in the count-matrix modes
+        dprint(1, "\n# rank=%d item=%d", i + 1, w.orderv[i] + 1);
+        dprint(1, "\n# ret=%d", j);
+        if (j) {
+            w.pfvec[i] = 0.0;
+            warn("regression degenerated: df[%d]=%g", i + 1, w.dfvec[i]);
+        } else {
+            w.pfvec[i] = specfun::pochisq(w.rssvec[i], (int)w.dfvec[i]);
+            if (w.pfvec[i] < 0.01) warn("theory does not fit well: pfit[%d]=%.4f", i + 1, w.pfvec[i]);
+            for (int c = 0; c < 3; c++) w.beta[3 * (size_t)i + c] = f.beta[c];
+        }
+        putchar('.');
+        fflush(stdout);
+    }
+    printf("\n# time elapsed for AU test is t=%g sec", cpu_seconds() - t0);
+    printf("\n# AU-TEST DONE");
+}
+
+// write_pv(sw_bp, sw_ba, 0, sw_au) (src/consel.c:1611-1683)
+static void cnt_write_pv(const CntWork &w, const char *fname_out, bool dobp, bool doba, bool doau) {
+    std::string used;
+    FILE *fp = stdout;
+    if (fname_out) {
+        fp = open_file(fname_out, ".pv", "w", &used);
+        printf("\n# writing %s", used.c_str());
+    } else {
+        printf("\n# writing to stdout\n");
+    }
+    const int cm = w.cm;
+    const int outbit = (dobp ? 1 : 0) + (doba ? 2 : 0) + (doau ? 8 : 0);
+    const int pvnum = (dobp ? 1 : 0) + (doba ? 1 : 0) + (doau ? 2 : 0), auxnum = doau ? 7 : 0;
+    fprintf(fp, "\n# ID:\n%d\n", 1);
+    fprintf(fp, "\n# ITEM:\n"); write_ivec(fp, w.orderv.data(), cm);
+    fprintf(fp, "\n# STAT:\n"); write_vec(fp, w.obsvec.data(), cm);
+    fprintf(fp, "\n# BIT:\n%d\n", outbit);
+    std::vector<double> pvmat((size_t)cm * pvnum), semat((size_t)cm * pvnum), auxmat((size_t)cm * auxnum);
+    for (int i = 0; i < cm; i++) {
+        int j = 0;
+        auto put = [&](double p, double se) {
+            pvmat[(size_t)i * pvnum + j] = p;
+            semat[(size_t)i * pvnum + j] = se;
+            j++;
+        };
+        if (dobp) put(w.npvec[i], w.nsvec[i]);
+        if (doba) put(w.bapvec[i], 0.0);
+        if (doau) {
+            put(w.pvvec[i], w.sevec[i]);
+            put(w.pv0vec[i], w.se0vec[i]);
+            double *ax = &auxmat[(size_t)i * auxnum];
+            ax[0] = w.pfvec[i]; ax[1] = w.rssvec[i]; ax[2] = w.dfvec[i];
+            ax[3] = w.beta[3 * (size_t)i]; ax[4] = w.beta[3 * (size_t)i + 1];
+            ax[5] = w.thvec[i]; ax[6] = w.beta[3 * (size_t)i + 2];
+        }
+    }
+    fprintf(fp, "\n# PV:\n"); write_mat(fp, pvmat.data(), cm, pvnum);
+    fprintf(fp, "\n# SE:\n"); write_mat(fp, semat.data(), cm, pvnum);
+    fprintf(fp, "\n# AX:\n"); write_mat(fp, auxnum ? auxmat.data() : pvmat.data(), cm, auxnum);
+    if (fname_out) fclose(fp);
+}
+
+// cnt mode (consel -C): do_cntmode (src/consel.c:1244-1283).  No replicates, no device: the
+// reference's path is the same host arithmetic.
 static void run_cntmode(const char *fname_in, const char *fname_out, bool dobp, bool doau, double threshold,
                         const aufit::Options &opt) {
     std::string used;
@@ -65,105 +179,287 @@ static void run_cntmode(const char *fname_in, const char *fname_out, bool dobp, 
     } else {
         printf("\n# reading from stdin");
     }
-    std::vector<int> orderv = read_ivec(fp);
-    int cm = (int)orderv.size(), kk = 0;
-    std::vector<double> obsvec = read_vec(fp, cm);
-    std::vector<double> rrmat = read_mat(fp, &cm, &kk), bbmat = read_mat(fp, &cm, &kk), cntmat = read_mat(fp, &cm, &kk);
+    CntWork w;
+    w.orderv = read_ivec(fp);
+    w.cm = (int)w.orderv.size();
+    w.obsvec = read_vec(fp, w.cm);
+    w.rrmat = read_mat(fp, &w.cm, &w.kk);
+    w.bbmat = read_mat(fp, &w.cm, &w.kk);
+    w.cntmat = read_mat(fp, &w.cm, &w.kk);
     if (fname_in) fclose(fp);
-    printf("\n# CM:%d", cm);
-    printf("\n# K:%d", kk);
+    printf("\n# CM:%d", w.cm);
+    printf("\n# K:%d", w.kk);
+    if (dobp) cnt_bptest(w);
+    if (doau) cnt_bootcnt(w, threshold, opt);
+    if (dobp || doau) cnt_write_pv(w, fname_out, dobp, false, doau);
+}
 
-    std::vector<double> npvec(cm), nsvec(cm), pvvec(cm), sevec(cm), pv0vec(cm), se0vec(cm), rssvec(cm), dfvec(cm),
-        pfvec(cm), thvec(cm), beta(3 * (size_t)cm, 0.0);
-    if (dobp) {
-        for (int j = 0; j < cm; j++) {
-            const double *rr = &rrmat[(size_t)j * kk];
+// ---------------------------------------------------------------- multi-gene mode (consel -g)
+// do_rmtmultimode (src/consel.c:1056-1192): one .rmt per gene, the items' counts of every gene
+// (gencnt :892-951, here cgpu_stats_build[_rescaled] + one count query per gene on the device),
+// combined into effective counts / replicate numbers by congcnt (:961-1043), then the
+// count-matrix BP and AU fit above.  The reference marks the mode experimental; its quirks are
+// kept (the congruence row sums the first MF posterior entries, :1146).
+struct MultiArgs {
+    const char *fname_in, *fname_out, *fname_ass, *fname_vt, *fname_pa;
+    bool dobp, doba, doau, outcnt, smoothcnt, nosort, fastrep;
+    int cm_arg, gpu;
+    double threshold, bapcoef, congbpadd;
+};
+
+static void run_multimode(const MultiArgs &A, const aufit::Options &opt) {
+    std::string used;
+    FILE *fp = A.fname_in ? open_file(A.fname_in, ".svt", "r", &used) : stdin;
+    const std::vector<std::string> infiles = read_svec(fp);
+    if (A.fname_in) fclose(fp);
+    const int mf = (int)infiles.size();
+    printf("\n# MF:%d", mf);
+
+    int mm = 0, kk = 0;
+    std::vector<std::vector<double>> datvecm(mf), rrm(mf);
+    std::vector<std::vector<int>> bbm(mf);
+    for (int f = 0; f < mf; f++) {  // :1080-1093
+        fp = open_file(infiles[f].c_str(), ".rmt", "rb", &used);
+        printf("\n# checking %s", used.c_str());
+        datvecm[f] = read_bvec(fp, mm);
+        mm = (int)datvecm[f].size();
+        rrm[f] = read_bvec(fp, kk);
+        kk = (int)rrm[f].size();
+        bbm[f] = read_bivec(fp, kk);
+        printf("\n# R:");
+        for (int i = 0; i < kk; i++) printf("%6.2f ", rrm[f][i]);
+        printf("\n# B:");
+        for (int i = 0; i < kk; i++) printf("%6d ", bbm[f][i]);
+        for (int i = 0; i < kk; i++)
+            if (fabs(rrm[f][i] - rrm[0][i]) > rrm[0][i] * 0.1) die("rr mismatch");
+        if (read_bint(fp) != kk) die("wrong size in rmt");
+        fclose(fp);
+    }
+    printf("\n# K:%d", kk);
+    printf("\n# M:%d", mm);
+    if (kk < 1 || mf < 1) return;
+
+    std::vector<double> datvec0(mm);
+    for (int i = 0; i < mm; i++) {  // total log-likelihood, :1101-1105
+        double x = 0.0;
+        for (int f = 0; f < mf; f++) x += datvecm[f][i];
+        datvec0[i] = x;
+    }
+    Assoc ass;
+    CntWork w;
+    int cm = read_assoc_and_order(A.fname_ass, datvec0, A.cm_arg, A.nosort, &ass, &w.obsvec, &w.orderv);
+
+    bool cong = true;  // sw_cong, :230; dropped when the associations overlap (:1112-1119)
+    {
+        std::vector<int> hits(mm, 0);
+        for (int i = 0; i < cm; i++)
+            for (int q = 0; q < ass.len(i); q++) hits[ass.at(i)[q]]++;
+        for (int i = 0; i < mm; i++)
+            if (hits[i] > 1) {
+                printf("\n# non-disjoint");
+                cong = false;
+                break;
+            }
+    }
+    const int cm2 = cm + (cong ? 1 : 0);
+    w.obsvec.resize(cm2);
+    w.orderv.resize(cm2);
+    if (cong) {
+        w.obsvec[cm] = 0.0;
+        w.orderv[cm] = cm;
+    }
+
+    if (A.fname_vt) {  // read_alpha: the alphas are read (and announced) but unused in this mode
+        fp = open_file(A.fname_vt, ".vt", "r", &used);
+        printf("\n# reading %s", used.c_str());
+        read_vec(fp);
+        fclose(fp);
+    }
+    std::vector<double> rr1 = {0.5, 0.6, 0.7, 0.8, 0.9, 1.0, 1.1, 1.2, 1.3, 1.4};
+    if (A.fastrep) {  // read_scale, :562-582
+        if (A.fname_pa) {
+            fp = open_file(A.fname_pa, ".pa", "r", &used);
+            printf("\n# reading %s", used.c_str());
+            rr1 = read_vec(fp);
+            fclose(fp);
+        }
+        printf("\n# RESCALING");
+        printf("\n# K:%d", (int)rr1.size());
+        printf("\n# R:");
+        for (double r : rr1) printf("%g ", r);
+    }
+
+    if (A.doba) {  // per-gene posteriors multiplied (:1133-1151)
+        w.bapvec.assign(cm2, 0.0);
+        std::vector<double> prod(cm, 1.0);
+        for (int f = 0; f < mf; f++) {
+            const std::vector<double> &dv = datvecm[f];
+            double x = -kHuge;
+            for (int i = 0; i < mm; i++)
+                if (dv[i] > x) x = dv[i];
+            std::vector<double> p(mm);
+            double y = 0.0;
+            for (int i = 0; i < mm; i++) y += p[i] = exp(A.bapcoef * (dv[i] - x));
+            for (int i = 0; i < mm; i++) p[i] = p[i] / y;
+            for (int i = 0; i < cm; i++) {
+                double t = 0.0;
+                for (int q = 0; q < ass.len(i); q++) t += p[ass.at(i)[q]];
+                prod[i] *= t;
+            }
+        }
+        for (int i = 0; i < cm; i++) w.bapvec[i] = prod[i];
+        if (cong) {
+            double x = 0.0;
+            for (int i = 0; i < mf && i < cm2; i++) x += w.bapvec[i];  // `i<mf` as in the reference (:1146)
+            w.bapvec[cm] = x;
+        }
+    }
+
+    if (A.doau || A.dobp || A.outcnt) {
+        CG(cgpu_init(A.gpu));
+        std::vector<std::vector<double>> cntm(mf);  // cm x kk per gene
+        for (int f = 0; f < mf; f++) {  // gencnt
+            fp = open_file(infiles[f].c_str(), ".rmt", "rb", &used);
+            printf("\n# reading %s", used.c_str());
+            std::vector<double> dv = read_bvec(fp, mm);
+            std::vector<double> rr = read_bvec(fp);
+            int k0 = (int)rr.size();
+            std::vector<int> bb = read_bivec(fp, k0);
+            if (read_bint(fp) != k0) die("wrong size in rmt");
+            std::vector<std::vector<double>> repmats(k0);
             int i0 = 0;
-            for (int i = 1; i < kk; i++)
+            for (int i = 1; i < k0; i++)
                 if (fabs(rr[i] - 1.0) < fabs(rr[i0] - 1.0)) i0 = i;
-            const double b = bbmat[(size_t)j * kk + i0];
-            npvec[j] = cntmat[(size_t)j * kk + i0] / b;
-            nsvec[j] = sqrt(npvec[j] * (1.0 - npvec[j]) / b);
-        }
-    }
-    if (doau) {
-        printf("\n# AU-TEST STARTS");
-        printf("\n# calculating approximately unbiased p-values by ");
-        printf(opt.fitmode == aufit::FIT_WLS ? "WLS (very fast)" : "MLE (fast)");
-        printf(" fitting");
-        fflush(stdout);
-        const double t0 = cpu_seconds();
-        for (int i = 0; i < cm; i++) {
-            const double *rr = &rrmat[(size_t)i * kk];
-            std::vector<double> rs(rr, rr + kk);
-            std::sort(rs.begin(), rs.end());
-            int i1 = 0;
-            while (i1 < kk && rs[i1] < opt.rrmin) i1++;
-            int i2 = i1;
-            while (i2 < kk && rs[i2] < 1.0) i2++;
-            aufit::Fit f;
-            int j = 1;
-            if (i1 < i2) {
-                f = aufit::calcpval(&cntmat[(size_t)i * kk], rr, &bbmat[(size_t)i * kk], kk, rs[i1], opt.rrmax, opt.kappa, opt);
-                j = f.rc;
+            const int nread = A.fastrep ? i0 + 1 : k0;  // the rescaling branch stops reading at scale i0 (:908-912)
+            for (int i = 0; i < nread; i++) {
+                int m = mm, b = bb[i];
+                repmats[i] = read_bmat(fp, &m, &b);
             }
-            pvvec[i] = f.pv; sevec[i] = f.se; pv0vec[i] = f.pv0;
-            if (cm > 1) se0vec[1] = f.se0;  // the reference passes `se0vec+1` for every item (:1567)
-            rssvec[i] = f.rss; dfvec[i] = f.df;
-            thvec[i] = threshold;  // unused in cnt mode
-            dprint(1, "\n# rank=%d item=%d", i + 1, orderv[i] + 1);
-            dprint(1, "\n# ret=%d", j);
-            if (j) {
-                pfvec[i] = 0.0;
-                warn("regression degenerated: df[%d]=%g", i + 1, dfvec[i]);
+            fclose(fp);
+            cgpu_reps *reps = nullptr, *stats = nullptr;
+            if (A.fastrep) {
+                std::vector<const double *> ptrs{repmats[i0].data()};
+                CG(cgpu_reps_upload(mm, 1, &bb[i0], ptrs.data(), &reps));
+                const int kk1 = (int)rr1.size();
+                std::vector<double> rs(kk1);
+                for (int i = 0; i < kk1; i++) rs[i] = sqrt(rr[i0] / rr1[i]);
+                CG(cgpu_stats_build_rescaled(reps, 0, kk1, rs.data(), cm, ass.ptr.data(), ass.idx.data(), &stats));
+                bb.assign(kk1, bb[i0]);
+                rr = rr1;
             } else {
-                pfvec[i] = specfun::pochisq(rssvec[i], (int)dfvec[i]);
-                if (pfvec[i] < 0.01) warn("theory does not fit well: pfit[%d]=%.4f", i + 1, pfvec[i]);
-                for (int c = 0; c < 3; c++) beta[3 * (size_t)i + c] = f.beta[c];
+                std::vector<const double *> ptrs(k0);
+                for (int i = 0; i < k0; i++) ptrs[i] = repmats[i].data();
+                CG(cgpu_reps_upload(mm, k0, bb.data(), ptrs.data(), &reps));
+                CG(cgpu_stats_build(reps, cm, ass.ptr.data(), ass.idx.data()));
             }
-            putchar('.');
-            fflush(stdout);
+            const int kf = (int)rr.size();
+            if (f > 0 && kf != kk) die("size mismatch in vec");
+            kk = kf;
+            dots(kk);
+            std::vector<double> thr(cm, A.threshold);
+            std::vector<cgpu_rowsum> q((size_t)cm * kk);
+            CG(cgpu_count_query(stats ? stats : reps, 1, thr.data(), q.data()));
+            cntm[f].resize((size_t)cm * kk);
+            for (int j = 0; j < cm; j++)
+                for (int i = 0; i < kk; i++) {
+                    const cgpu_rowsum &e = q[(size_t)j * kk + i];
+                    cntm[f][(size_t)j * kk + i] = A.smoothcnt ? cgpu_smooth_count(&e, bb[i], A.threshold) : e.cnt;
+                }
+            if (stats) cgpu_reps_free(stats);
+            cgpu_reps_free(reps);
+            bbm[f] = bb;
+            rrm[f] = rr;
         }
-        printf("\n# time elapsed for AU test is t=%g sec", cpu_seconds() - t0);
-        printf("\n# AU-TEST DONE");
-    }
-    if (!(dobp || doau)) return;
-    // write_pv(sw_dobp,0,0,sw_doau) (src/consel.c:1611-1683)
-    fp = stdout;
-    if (fname_out) {
-        fp = open_file(fname_out, ".pv", "w", &used);
-        printf("\n# writing %s", used.c_str());
-    } else {
-        printf("\n# writing to stdout\n");
-    }
-    const int outbit = (dobp ? 1 : 0) + (doau ? 8 : 0), pvnum = (dobp ? 1 : 0) + (doau ? 2 : 0), auxnum = doau ? 7 : 0;
-    fprintf(fp, "\n# ID:\n%d\n", 1);
-    fprintf(fp, "\n# ITEM:\n"); write_ivec(fp, orderv.data(), cm);
-    fprintf(fp, "\n# STAT:\n"); write_vec(fp, obsvec.data(), cm);
-    fprintf(fp, "\n# BIT:\n%d\n", outbit);
-    std::vector<double> pvmat((size_t)cm * pvnum), semat((size_t)cm * pvnum), auxmat((size_t)cm * auxnum);
-    for (int i = 0; i < cm; i++) {
-        int j = 0;
-        if (dobp) { pvmat[(size_t)i * pvnum + j] = npvec[i]; semat[(size_t)i * pvnum + j] = nsvec[i]; j++; }
-        if (doau) {
-            pvmat[(size_t)i * pvnum + j] = pvvec[i]; semat[(size_t)i * pvnum + j] = sevec[i]; j++;
-            pvmat[(size_t)i * pvnum + j] = pv0vec[i]; semat[(size_t)i * pvnum + j] = se0vec[i]; j++;
-            double *ax = &auxmat[(size_t)i * auxnum];
-            ax[0] = pfvec[i]; ax[1] = rssvec[i]; ax[2] = dfvec[i];
-            ax[3] = beta[3 * (size_t)i]; ax[4] = beta[3 * (size_t)i + 1];
-            ax[5] = thvec[i]; ax[6] = beta[3 * (size_t)i + 2];
+        w.cm = cm2;
+        w.kk = kk;
+        w.rrmat.assign((size_t)cm2 * kk, 0.0);
+        for (int i = 0; i < kk; i++) {  // averaged scales, :1161-1165
+            double x = 0.0;
+            for (int f = 0; f < mf; f++) x += rrm[f][i];
+            x = x / mf;
+            for (int j = 0; j < cm2; j++) w.rrmat[(size_t)j * kk + i] = x;
         }
+
+        // ---- congcnt (:961-1043)
+        auto at = [kk](std::vector<double> &m, int i, int j) -> double & { return m[(size_t)i * kk + j]; };
+        std::vector<std::vector<double>> pm(mf, std::vector<double>((size_t)cm * kk));
+        std::vector<double> pv((size_t)cm2 * kk, 0.0), va((size_t)cm2 * kk, 0.0);
+        w.cntmat.assign((size_t)cm2 * kk, 0.0);
+        w.bbmat.assign((size_t)cm2 * kk, 0.0);
+        auto combine = [&]() {  // product over genes, congruence row = sum over items
+            for (int j = 0; j < kk; j++)
+                for (int i = 0; i < cm; i++) {
+                    double x = 1.0;
+                    for (int f = 0; f < mf; f++) x *= at(pm[f], i, j);
+                    at(pv, i, j) = x;
+                }
+            if (cong)
+                for (int j = 0; j < kk; j++) {
+                    double x = 0.0;
+                    for (int i = 0; i < cm; i++) x += at(pv, i, j);
+                    at(pv, cm, j) = x;
+                }
+        };
+        for (int f = 0; f < mf; f++)  // bootstrap probabilities pulled towards 1/2 by congbpadd counts
+            for (int j = 0; j < kk; j++)
+                for (int i = 0; i < cm; i++) {
+                    const double x = at(cntm[f], i, j), y = bbm[f][j];
+                    const double z = y * 0.5 + ((y - 2.0 * A.congbpadd) / y) * (x - y * 0.5);
+                    at(pm[f], i, j) = z / y;
+                }
+        combine();
+        for (int j = 0; j < kk; j++) {  // delta-method variance of the product
+            double z = 0.0, y = 0.0;
+            for (int f = 0; f < mf; f++) y += 1.0 / bbm[f][j];
+            for (int i = 0; i < cm; i++) {
+                double x = 0.0;
+                if (at(pv, i, j) > 0.0)
+                    for (int f = 0; f < mf; f++) x += 1.0 / (bbm[f][j] * at(pm[f], i, j));
+                x *= at(pv, i, j) * at(pv, i, j);
+                z += x;
+                at(va, i, j) = x - y * (at(pv, i, j) * at(pv, i, j));
+            }
+            if (cong) at(va, cm, j) = z - y * (at(pv, cm, j) * at(pv, cm, j));
+        }
+        for (int j = 0; j < kk; j++)  // effective number of replicates
+            for (int i = 0; i < cm2; i++) {
+                const double x = at(pv, i, j);
+                at(w.bbmat, i, j) = x * (1.0 - x) / at(va, i, j);
+            }
+        for (int f = 0; f < mf; f++)  // uncorrected probabilities
+            for (int j = 0; j < kk; j++)
+                for (int i = 0; i < cm; i++) at(pm[f], i, j) = at(cntm[f], i, j) / bbm[f][j];
+        combine();
+        for (int j = 0; j < kk; j++)
+            for (int i = 0; i < cm2; i++) at(w.cntmat, i, j) = at(w.bbmat, i, j) * at(pv, i, j);
     }
-    fprintf(fp, "\n# PV:\n"); write_mat(fp, pvmat.data(), cm, pvnum);
-    fprintf(fp, "\n# SE:\n"); write_mat(fp, semat.data(), cm, pvnum);
-    fprintf(fp, "\n# AX:\n"); write_mat(fp, auxnum ? auxmat.data() : pvmat.data(), cm, auxnum);
-    if (fname_out) fclose(fp);
+    w.cm = cm2;
+    if (A.dobp) cnt_bptest(w);
+    if (A.doau) cnt_bootcnt(w, A.threshold, opt);
+    if (A.dobp || A.doau || A.doba) cnt_write_pv(w, A.fname_out, A.dobp, A.doba, A.doau);
+    if (A.outcnt) {  // write_cnt2
+        fp = stdout;
+        if (A.fname_out) {
+            fp = open_file(A.fname_out, ".cnt", "w", &used);
+            printf("\n# writing %s", used.c_str());
+        } else {
+            printf("\n# writing to stdout\n");
+        }
+        fprintf(fp, "\n# ITEM:\n"); write_ivec(fp, w.orderv.data(), w.cm);
+        fprintf(fp, "\n# STAT:\n"); write_vec(fp, w.obsvec.data(), w.cm);
+        fprintf(fp, "\n# R:\n"); write_mat(fp, w.rrmat.data(), w.cm, w.kk);
+        fprintf(fp, "\n# B:\n"); write_mat(fp, w.bbmat.data(), w.cm, w.kk);
+        fprintf(fp, "\n# CNT:\n"); write_mat(fp, w.cntmat.data(), w.cm, w.kk);
+        if (A.fname_out) fclose(fp);
+    }
+    if (A.doau || A.dobp || A.outcnt) cgpu_shutdown();
 }
 
 int main(int argc, char **argv) {
     const char *fname_in = nullptr, *fname_out_arg = nullptr, *fname_ass = nullptr, *fname_vt = nullptr, *fname_pa = nullptr;
     bool fastrep = false;
-    bool outrep = false, outcnt = false, smoothcnt = false, nosort = false, inrep = false, incnt = false;
+    bool outrep = false, outcnt = false, smoothcnt = false, nosort = false, inrep = false, incnt = false, multi = false;
+    double congbpadd = 1.0;  // src/consel.c:960
     bool dobp = true, doba = true, domc = true, doau = true;
     int cm_arg = 0, gpu = -1;
     double threshold = 0.0, varadd = 1.0, bapcoef = 1.0;
@@ -184,6 +480,8 @@ int main(int argc, char **argv) {
         } else if (a == "-r") outrep = true;
         else if (a == "-R") inrep = true;
         else if (a == "-C") incnt = true;
+        else if (a == "-g") multi = true;
+        else if (a == "--congbp") dbl(&congbpadd);
         else if (a == "-f") fastrep = true;
         else if (a == "-p") { need(); fname_pa = argv[++i]; }
         else if (a == "-c") outcnt = true;
@@ -209,9 +507,9 @@ int main(int argc, char **argv) {
         else if (a == "--mle") opt.fitmode = aufit::FIT_MLE;
         else if (a == "--wls") opt.fitmode = aufit::FIT_WLS;
         else if (a == "--gpu") integer(&gpu);
-        else if (a == "-g" || a == "--pdm" ||
+        else if (a == "--pdm" ||
                  a == "--quick_mctest" || a.rfind("--chi", 0) == 0 || a == "--aictype" || a == "--ppn" ||
-                 a == "--pmin" || a == "--congbp")
+                 a == "--pmin")
             die("switch %s is not supported by the B200 build of consel (rmt, rep and cnt modes only)", a.c_str());
         else byebye();
     }
@@ -224,6 +522,14 @@ int main(int argc, char **argv) {
     if (incnt && inrep) die("only one of -C and -R can be specified");
     if (incnt) {
         run_cntmode(fname_in, fname_out, dobp, doau, threshold, opt);
+        printf("\n# exit normally\n");
+        return 0;
+    }
+
+    if (multi && !inrep) {  // rmt mode only (src/consel.c:439-440)
+        const MultiArgs A{fname_in, fname_out, fname_ass, fname_vt, fname_pa, dobp, doba, doau, outcnt, smoothcnt, nosort,
+                          fastrep, cm_arg, gpu, threshold, bapcoef, congbpadd};
+        run_multimode(A, opt);
         printf("\n# exit normally\n");
         return 0;
     }

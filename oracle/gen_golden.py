@@ -14,6 +14,7 @@ Fixtures
   tiny.{mt,pa,rmt,vt,...}   synthetic K=6 n=40, ragged scales/replicate counts
   mr100e.rep, tinymr.rep + mr.pa   makerep -s 1234 -p mr -a mam15 --paml mam15 ; makerep -s 7 -p tiny tiny
   {g100,g100e,tiny,g100fe}C.pv   consel -C on the .cnt files above (cnt mode)
+  ga/gb/gc.mt genes.svt pairs.ass mg.pa mgout* mgoutf*   makermt -s 11 -p mg -g genes ; consel -g (multi-gene mode)
   MANIFEST.json             md5 of every fixture + md5s of the full-size seeded runs
 """
 from __future__ import annotations
@@ -90,6 +91,20 @@ def main() -> None:
     orc.run_ref("makerep", ["-s", "1234", "-p", "mr", "-a", "mam15", "--paml", "mam15", "mr100e"], work)
     orc.run_ref("makerep", ["-s", "7", "-p", "tiny", "tiny", "tinymr"], work)
     keep += ["mr.pa", "mr100e.rep", "tinymr.rep"]
+
+    # --- multi-gene mode (makermt -g ; consel -g): three synthetic genes of different lengths
+    rng = np.random.Generator(np.random.PCG64(77))
+    for gname, gn in (("ga", 60), ("gb", 85), ("gc", 47)):
+        gbase = -2.3 - 4.07 * rng.exponential(size=gn)
+        gL = gbase[None, :] + 0.25 * rng.standard_normal((6, gn)) - 0.9 * np.arange(6)[:, None] / gn
+        orc.write_mt(work / f"{gname}.mt", gL)
+    (work / "genes.svt").write_text("3\nga gb gc\n")
+    (work / "pairs.ass").write_text("3\n2 0 1\n2 2 3\n2 4 5\n")
+    orc.write_pa(work / "mg.pa", [0.5, 0.7, 0.85, 1.0, 1.2, 1.4], [300] * 6)
+    orc.run_ref("makermt", ["-s", "11", "-p", "mg", "-g", "genes"], work)
+    orc.run_ref("consel", ["-g", "-c", "genes", "mgout"], work)
+    orc.run_ref("consel", ["-g", "-f", "-p", "fscale", "-a", "pairs", "--smooth_cnt", "-c", "genes", "mgoutf"], work)
+    keep += ["ga.mt", "gb.mt", "gc.mt", "genes.svt", "pairs.ass", "mg.pa", "mgout.pv", "mgout.cnt", "mgoutf.pv", "mgoutf.cnt"]
 
     # --- cnt mode (consel -C): the AU fit from the counts alone
     for case in ("g100", "g100e", "tiny", "g100fe"):

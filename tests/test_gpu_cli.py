@@ -117,6 +117,22 @@ def test_makerep_matches_reference(gold, orc, tmp_path):
         assert np.allclose(x, y, rtol=0, atol=1e-9)
 
 
+def test_multi_gene_mode(gold, orc, tmp_path):
+    """makermt -g ; consel -g (do_rmtmultimode, src/consel.c:1056-1192): per-gene statistics and counts
+    on the device, congcnt + count-matrix fit on the host, against the reference's own run."""
+    for f in ("ga.mt", "gb.mt", "gc.mt", "genes.svt", "pairs.ass", "mg.pa", "fscale.pa"):
+        shutil.copy(gold / f, tmp_path / f)
+    run("makermt", ["-s", "11", "-p", "mg", "-g", "genes"], tmp_path)
+    out = run("consel", ["-g", "-c", "genes", "mgout"], tmp_path)
+    assert "# MF:3" in out and "# exit normally" in out
+    assert (tmp_path / "mgout.cnt").read_bytes() == (gold / "mgout.cnt").read_bytes()
+    same_numbers(tmp_path / "mgout.pv", gold / "mgout.pv", orc)
+    out = run("consel", ["-g", "-f", "-p", "fscale", "-a", "pairs", "--smooth_cnt", "-c", "genes", "mgoutf"], tmp_path)
+    assert "# RESCALING" in out
+    same_numbers(tmp_path / "mgoutf.cnt", gold / "mgoutf.cnt", orc)
+    same_numbers(tmp_path / "mgoutf.pv", gold / "mgoutf.pv", orc)
+
+
 def test_cli_error_protocol(tmp_path):
     r = subprocess.run([str(BIN / "makermt"), "--bogus"], cwd=tmp_path, capture_output=True, text=True)
     assert r.returncode == 1 and "#! Terminated: error in command line." in r.stdout
