@@ -832,6 +832,7 @@ int cgpu_set_option(const char *name, int value) {
     else if (!strcmp(name, "draw_fuse")) g.opt_draw_fuse = value;
     else if (!strcmp(name, "stage")) g.opt_stage = value;
     else if (!strcmp(name, "i8_dbg")) g.opt_i8_dbg = value;
+    else if (!strcmp(name, "mc_smooth")) g.opt_mc_smooth = value;
     else if (!strcmp(name, "chunk_log2")) g.opt_chunk_log2 = value;
     else {
         set_error(CGPU_EINVAL, "unknown option %s", name);

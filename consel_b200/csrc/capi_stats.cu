@@ -511,7 +511,10 @@ int cgpu_mctest(const cgpu_reps *rr, int i0, const double *datvec, double varadd
         CGPU_CUDA(cudaStreamSynchronize(st));
         return CGPU_OK;
     };
-    auto pval = [&](const cgpu_rowsum &q, double t) { return 1.0 - smooth_count(q, B, t) / B; };  // pvaldist :1876-1884
+    const bool smooth = G().opt_mc_smooth != 0;  // sw_pvaldist; 0 = --quick_mctest
+    auto pval = [&](const cgpu_rowsum &q, double t) {  // pvaldist :1876-1884
+        return 1.0 - (smooth ? smooth_count(q, B, t) : q.cnt) / B;
+    };
 
     {  // KH
         RowSrc src{xc.as<double>(), B, d_ia.as<int>(), d_ja.as<int>(), nullptr, nullptr, nullptr};

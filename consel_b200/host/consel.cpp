@@ -21,8 +21,8 @@
 // Multi-gene mode (-g, do_rmtmultimode :1056-1192): per gene the statistics and one count
 // query on the device, then congcnt and the count-matrix fit on the host.
 //
-// Not carried by this build (error at the command line): --chi* spherical fit, --pdm AIC correction,
-// --quick_mctest.  They are off the hot path (SURVEY 8f "next").
+// Not carried by this build (error at the command line): --chi* spherical fit, --pdm AIC
+// correction.  They are off the hot path (SURVEY 8f "next").
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -458,7 +458,7 @@ static void run_multimode(const MultiArgs &A, const aufit::Options &opt) {
 int main(int argc, char **argv) {
     const char *fname_in = nullptr, *fname_out_arg = nullptr, *fname_ass = nullptr, *fname_vt = nullptr, *fname_pa = nullptr;
     bool fastrep = false;
-    bool outrep = false, outcnt = false, smoothcnt = false, nosort = false, inrep = false, incnt = false, multi = false;
+    bool outrep = false, outcnt = false, smoothcnt = false, nosort = false, inrep = false, incnt = false, multi = false, quickmc = false;
     double congbpadd = 1.0;  // src/consel.c:960
     bool dobp = true, doba = true, domc = true, doau = true;
     int cm_arg = 0, gpu = -1;
@@ -495,6 +495,7 @@ int main(int argc, char **argv) {
         else if (a == "--no_sh") domc = false;
         else if (a == "--no_au") doau = false;
         else if (a == "--smooth_cnt") smoothcnt = true;
+        else if (a == "--quick_mctest") quickmc = true;
         else if (a == "--th") dbl(&threshold);
         else if (a == "--kappa") dbl(&opt.kappa);
         else if (a == "--ppcoef") dbl(&bapcoef);
@@ -508,7 +509,7 @@ int main(int argc, char **argv) {
         else if (a == "--wls") opt.fitmode = aufit::FIT_WLS;
         else if (a == "--gpu") integer(&gpu);
         else if (a == "--pdm" ||
-                 a == "--quick_mctest" || a.rfind("--chi", 0) == 0 || a == "--aictype" || a == "--ppn" ||
+                 a.rfind("--chi", 0) == 0 || a == "--aictype" || a == "--ppn" ||
                  a == "--pmin")
             die("switch %s is not supported by the B200 build of consel (rmt, rep and cnt modes only)", a.c_str());
         else byebye();
@@ -698,6 +699,7 @@ int main(int argc, char **argv) {
     // ---------------- KH / SH tests (do_mctest)
     std::vector<double> khp(cm), mcp(cm), khwp(cm), mcwp(cm);
     if (domc) {
+        if (quickmc) CG(cgpu_set_option("mc_smooth", 0));  // sw_pvaldist=0: plain counts, no smoothing
         printf("\n# MC-TEST STARTS");
         printf("\n# centering the replicates");
         CG(cgpu_mctest(reps, i0, datvec.data(), varadd, cm, ass.ptr.data(), ass.idx.data(), khp.data(), mcp.data(),
@@ -747,7 +749,8 @@ int main(int argc, char **argv) {
     if (dobp) {  // do_bptest
         printf("\n# BP-TEST STARTS");
         for (int jx = 0; jx < cm; jx++) {
-            double x = cgpu_smooth_count(&r0[(size_t)jx * kk + i0], nb0, threshold);
+            const cgpu_rowsum &q0 = r0[(size_t)jx * kk + i0];
+            double x = quickmc ? q0.cnt : cgpu_smooth_count(&q0, nb0, threshold);  // pvaldist honours sw_pvaldist (:1298)
             npvec[jx] = 1.0 - (1.0 - x / nb0);
         }
         printf(" - DONE");

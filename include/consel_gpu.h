@@ -182,7 +182,9 @@ int cgpu_last_timing_ex(double *ms, int n);
  * "draw_fuse" 0|1 (draws + histograms in one kernel, int8 mode, opt-in), "stage" 0|1 (staged
  * index production of host-output int8 calls: 0 off, 1 always, default by size),
  * "chunk_log2" 10..30, "i8_dbg" 0..3 (switches parts of the GEMM epilogue off: timing only,
- * results are wrong).  A negative value restores the default.  Returns CGPU_EINVAL for an
+ * results are wrong), "mc_smooth" 0|1 (0 = consel --quick_mctest: the KH/SH p-values of
+ * cgpu_mctest use the plain count #{v<=t} instead of the smoothed one, sw_pvaldist
+ * src/consel.c:1875-1884).  A negative value restores the default.  Returns CGPU_EINVAL for an
  * unknown name.  Environment (development): CGPU_TRACE=1 prints every timed span of a
  * resampling call, CGPU_STAGE_FRACS=a,b,c overrides the stage sizes.                    */
 int cgpu_set_option(const char *name, int value);

@@ -106,6 +106,10 @@ def main() -> None:
     orc.run_ref("consel", ["-g", "-f", "-p", "fscale", "-a", "pairs", "--smooth_cnt", "-c", "genes", "mgoutf"], work)
     keep += ["ga.mt", "gb.mt", "gc.mt", "genes.svt", "pairs.ass", "mg.pa", "mgout.pv", "mgout.cnt", "mgoutf.pv", "mgoutf.cnt"]
 
+    # --- --quick_mctest: KH/SH p-values from plain counts
+    orc.run_ref("consel", ["--quick_mctest", "--no_au", "-a", "mam15", "g100", "g100q"], work)
+    keep.append("g100q.pv")
+
     # --- cnt mode (consel -C): the AU fit from the counts alone
     for case in ("g100", "g100e", "tiny", "g100fe"):
         orc.run_ref("consel", ["-C", case, case + "C"], work)

@@ -133,6 +133,16 @@ def test_multi_gene_mode(gold, orc, tmp_path):
     same_numbers(tmp_path / "mgoutf.pv", gold / "mgoutf.pv", orc)
 
 
+def test_quick_mctest(gold, orc, tmp_path):
+    """--quick_mctest (sw_pvaldist=0, src/consel.c:1875-1884): KH/SH/wKH/wSH p-values from plain counts."""
+    shutil.copy(gold / "g100.rmt", tmp_path / "g100.rmt")
+    shutil.copy(gold / "mam15.ass", tmp_path / "mam15.ass")
+    run("consel", ["--quick_mctest", "--no_au", "-a", "mam15", "g100", "g100q"], tmp_path)
+    same_numbers(tmp_path / "g100q.pv", gold / "g100q.pv", orc)
+    a, b = orc.read_text_blocks(gold / "g100q.pv"), orc.read_text_blocks(gold / "g100e.pv")
+    assert len(a) != len(b) or not np.allclose(a, b)  # the switch does change the numbers
+
+
 def test_cli_error_protocol(tmp_path):
     r = subprocess.run([str(BIN / "makermt"), "--bogus"], cwd=tmp_path, capture_output=True, text=True)
     assert r.returncode == 1 and "#! Terminated: error in command line." in r.stdout
