@@ -21,8 +21,8 @@
 // Multi-gene mode (-g, do_rmtmultimode :1056-1192): per gene the statistics and one count
 // query on the device, then congcnt and the count-matrix fit on the host.
 //
-// Not carried by this build (error at the command line): --chi* spherical fit, --pdm AIC
-// correction.  They are off the hot path (SURVEY 8f "next").
+// Not carried by this build (error at the command line): the --chi* spherical fit (off the
+// hot path, SURVEY 8f "next").
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -77,10 +77,11 @@ static void cnt_bptest(CntWork &w) {
     }
 }
 
-// do_bootcnt (src/consel.c:1540-1592).  rcalpval (:2703-2737) with its default pfmin = 0 makes
-// exactly one calcpval call, on the scales from the smallest r >= rmin that is below 1
-// upwards, and reports "degenerated" without fitting when there is no scale in [rmin, 1).
-static void cnt_bootcnt(CntWork &w, double threshold, const aufit::Options &opt) {
+// do_bootcnt (src/consel.c:1540-1592).  rcalpval (:2703-2737) fits on the scales from the
+// smallest r >= rmin that is below 1 upwards, drops the smallest scale and fits again while
+// the fit's p-value is below pfmin (--pmin; the default 0 accepts the first fit), and reports
+// "degenerated" without fitting when there is no scale in [rmin, 1).
+static void cnt_bootcnt(CntWork &w, double threshold, const aufit::Options &opt, double pfmin) {
     const int cm = w.cm, kk = w.kk;
     for (auto *v : {&w.pvvec, &w.sevec, &w.pv0vec, &w.se0vec, &w.rssvec, &w.dfvec, &w.pfvec, &w.thvec}) v->assign(cm, 0.0);
     w.beta.assign(3 * (size_t)cm, 0.0);
@@ -100,9 +101,11 @@ static void cnt_bootcnt(CntWork &w, double threshold, const aufit::Options &opt)
         while (i2 < kk && rs[i2] < 1.0) i2++;
         aufit::Fit f;
         int j = 1;
-        if (i1 < i2) {
-            f = aufit::calcpval(&w.cntmat[(size_t)i * kk], rr, &w.bbmat[(size_t)i * kk], kk, rs[i1], opt.rrmax, opt.kappa, opt);
+        for (int t = i1; t < i2; t++) {  // raise rmin until the fit is acceptable (--pmin; default 0 = first fit)
+            f = aufit::calcpval(&w.cntmat[(size_t)i * kk], rr, &w.bbmat[(size_t)i * kk], kk, rs[t], opt.rrmax, opt.kappa, opt);
             j = f.rc;
+            if (j) break;
+            if (specfun::pochisq(f.rss, (int)f.df) >= pfmin) break;
         }
         w.pvvec[i] = f.pv; w.sevec[i] = f.se; w.pv0vec[i] = f.pv0;
         if (cm > 1) w.se0vec[1] = f.se0;  // the reference passes `se0vec+1` for every item (:1567)
@@ -170,7 +173,7 @@ static void cnt_write_pv(const CntWork &w, const char *fname_out, bool dobp, boo
 // cnt mode (consel -C): do_cntmode (src/consel.c:1244-1283).  No replicates, no device: the
 // reference's path is the same host arithmetic.
 static void run_cntmode(const char *fname_in, const char *fname_out, bool dobp, bool doau, double threshold,
-                        const aufit::Options &opt) {
+                        const aufit::Options &opt, double pfmin) {
     std::string used;
     FILE *fp = stdin;
     if (fname_in) {
@@ -190,7 +193,7 @@ static void run_cntmode(const char *fname_in, const char *fname_out, bool dobp, 
     printf("\n# CM:%d", w.cm);
     printf("\n# K:%d", w.kk);
     if (dobp) cnt_bptest(w);
-    if (doau) cnt_bootcnt(w, threshold, opt);
+    if (doau) cnt_bootcnt(w, threshold, opt, pfmin);
     if (dobp || doau) cnt_write_pv(w, fname_out, dobp, false, doau);
 }
 
@@ -204,7 +207,7 @@ struct MultiArgs {
     const char *fname_in, *fname_out, *fname_ass, *fname_vt, *fname_pa;
     bool dobp, doba, doau, outcnt, smoothcnt, nosort, fastrep;
     int cm_arg, gpu;
-    double threshold, bapcoef, congbpadd;
+    double threshold, bapcoef, congbpadd, pfmin;
 };
 
 static void run_multimode(const MultiArgs &A, const aufit::Options &opt) {
@@ -435,7 +438,7 @@ static void run_multimode(const MultiArgs &A, const aufit::Options &opt) {
     }
     w.cm = cm2;
     if (A.dobp) cnt_bptest(w);
-    if (A.doau) cnt_bootcnt(w, A.threshold, opt);
+    if (A.doau) cnt_bootcnt(w, A.threshold, opt, A.pfmin);
     if (A.dobp || A.doau || A.doba) cnt_write_pv(w, A.fname_out, A.dobp, A.doba, A.doau);
     if (A.outcnt) {  // write_cnt2
         fp = stdout;
@@ -460,6 +463,9 @@ int main(int argc, char **argv) {
     bool fastrep = false;
     bool outrep = false, outcnt = false, smoothcnt = false, nosort = false, inrep = false, incnt = false, multi = false, quickmc = false;
     double congbpadd = 1.0;  // src/consel.c:960
+    const char *fname_pdm = nullptr;  // --pdm: parameters per item for the AIC correction (:584-744)
+    int aictype = 2;                  // :239
+    double bapn = 1.0, pfmin = 0.0;   // :182, :2700
     bool dobp = true, doba = true, domc = true, doau = true;
     int cm_arg = 0, gpu = -1;
     double threshold = 0.0, varadd = 1.0, bapcoef = 1.0;
@@ -508,10 +514,12 @@ int main(int argc, char **argv) {
         else if (a == "--mle") opt.fitmode = aufit::FIT_MLE;
         else if (a == "--wls") opt.fitmode = aufit::FIT_WLS;
         else if (a == "--gpu") integer(&gpu);
-        else if (a == "--pdm" ||
-                 a.rfind("--chi", 0) == 0 || a == "--aictype" || a == "--ppn" ||
-                 a == "--pmin")
-            die("switch %s is not supported by the B200 build of consel (rmt, rep and cnt modes only)", a.c_str());
+        else if (a == "--pdm") { need(); fname_pdm = argv[++i]; }
+        else if (a == "--aictype") integer(&aictype);
+        else if (a == "--ppn") dbl(&bapn);
+        else if (a == "--pmin") dbl(&pfmin);
+        else if (a.rfind("--chi", 0) == 0)
+            die("switch %s is not supported by the B200 build of consel (the spherical fit is not carried)", a.c_str());
         else byebye();
     }
 
@@ -522,14 +530,14 @@ int main(int argc, char **argv) {
 
     if (incnt && inrep) die("only one of -C and -R can be specified");
     if (incnt) {
-        run_cntmode(fname_in, fname_out, dobp, doau, threshold, opt);
+        run_cntmode(fname_in, fname_out, dobp, doau, threshold, opt, pfmin);
         printf("\n# exit normally\n");
         return 0;
     }
 
     if (multi && !inrep) {  // rmt mode only (src/consel.c:439-440)
         const MultiArgs A{fname_in, fname_out, fname_ass, fname_vt, fname_pa, dobp, doba, doau, outcnt, smoothcnt, nosort,
-                          fastrep, cm_arg, gpu, threshold, bapcoef, congbpadd};
+                          fastrep, cm_arg, gpu, threshold, bapcoef, congbpadd, pfmin};
         run_multimode(A, opt);
         printf("\n# exit normally\n");
         return 0;
@@ -541,7 +549,7 @@ int main(int argc, char **argv) {
     std::vector<std::vector<double>> repmats;
     int mm = 0, kk = 0, cm = 0;
     Assoc ass;
-    std::vector<double> obsvec;
+    std::vector<double> obsvec, datvec00, pdmvec;
     std::vector<int> orderv;
     if (inrep) {
         // ---------------- read .rep (do_repmode, src/consel.c:1195-1226): the statistic rows
@@ -638,6 +646,41 @@ int main(int argc, char **argv) {
         return 0;
     }
 
+    // ---------------- AIC correction (read_pdm / do_pdm, src/consel.c:675-744): a constant per tree
+    // added to the observed log-likelihoods and to every replicate, on the host before the
+    // upload (one rounded add per element, as in the reference)
+    datvec00 = datvec;
+    if (fname_pdm) {
+        FILE *fp = open_file(fname_pdm, ".vt", "r", &used);
+        printf("\n# reading %s", used.c_str());
+        pdmvec = read_vec(fp);
+        fclose(fp);
+        printf("\n# pdm:");
+        for (double v : pdmvec) printf("%g ", v);
+        printf("\n# aictype:%d", aictype);
+    }
+    if (!pdmvec.empty()) {
+        if ((int)pdmvec.size() != mm) die("size of pdm should be M");
+        if (aictype != 0) {
+            for (int i = 0; i < mm; i++) {
+                double x = 0.0;  // an aictype outside 1..4 leaves x as it was in the reference (uninitialised); 0 here
+                if (aictype == 1 || aictype == 4) x = -1.0 * pdmvec[i];
+                else if (aictype == 2 || aictype == 3) x = -0.5 * pdmvec[i];
+                datvec[i] += x;
+            }
+            for (int k = 0; k < kk; k++)
+                for (int i = 0; i < mm; i++) {
+                    double x = 0.0;
+                    if (aictype == 1) x = -1.0 * pdmvec[i] / rr[k];
+                    else if (aictype == 2) x = -0.5 * pdmvec[i];
+                    else if (aictype == 3) x = -0.5 * pdmvec[i] * (1.0 - 1.0 / rr[k]);
+                    else if (aictype == 4) x = -1.0 * pdmvec[i];
+                    double *row = &repmats[k][(size_t)i * bb[k]];
+                    for (int j = 0; j < bb[k]; j++) row[j] += x;
+                }
+        }
+    }
+
     cm = read_assoc_and_order(fname_ass, datvec, cm_arg, nosort, &ass, &obsvec, &orderv);
     }  // rmt mode
 
@@ -667,12 +710,19 @@ int main(int argc, char **argv) {
     // ---------------- Bayesian posterior (do_batest, src/consel.c:1311-1340)
     std::vector<double> bapvec(cm, 0.0);
     if (doba) {
-        double x = -kHuge;
-        for (int i = 0; i < mm; i++)
-            if (datvec[i] > x) x = datvec[i];
         std::vector<double> w(mm);
-        double y = 0.0;
-        for (int i = 0; i < mm; i++) y += w[i] = exp(bapcoef * (datvec[i] - x));
+        double x = -kHuge, y = 0.0;
+        if ((int)pdmvec.size() != mm) {
+            for (int i = 0; i < mm; i++)
+                if (datvec[i] > x) x = datvec[i];
+            for (int i = 0; i < mm; i++) y += w[i] = exp(bapcoef * (datvec[i] - x));
+        } else {  // BIC correction: P = const*exp{bapcoef*logL - 0.5*pdm*log(n)} on the uncorrected logL (:1325-1332)
+            printf("\n# ppn:%g", bapn);
+            for (int i = 0; i < mm; i++) w[i] = bapcoef * datvec00[i] - 0.5 * pdmvec[i] * log(bapn);
+            for (int i = 0; i < mm; i++)
+                if (w[i] > x) x = w[i];
+            for (int i = 0; i < mm; i++) y += w[i] = exp(w[i] - x);
+        }
         for (int i = 0; i < mm; i++) w[i] = w[i] / y;
         for (int i = 0; i < cm; i++) {
             double s = 0.0;

@@ -110,6 +110,13 @@ def main() -> None:
     orc.run_ref("consel", ["--quick_mctest", "--no_au", "-a", "mam15", "g100", "g100q"], work)
     keep.append("g100q.pv")
 
+    # --- AIC correction (--pdm), default aictype 2 and aictype 3 with --ppn; --pmin in cnt mode
+    (work / "pdm.vt").write_text("15\n" + " ".join(str(v) for v in [3, 5, 2, 8, 4, 6, 1, 7, 3, 2, 9, 4, 5, 6, 2]) + "\n")
+    orc.run_ref("consel", ["--pdm", "pdm", "g100", "g100p"], work)
+    orc.run_ref("consel", ["--pdm", "pdm", "--aictype", "3", "--ppn", "3414", "-r", "-c", "g100", "g100p3"], work)
+    orc.run_ref("consel", ["-C", "--pmin", "0.5", "g100", "g100Cp"], work)
+    keep += ["pdm.vt", "g100p.pv", "g100p.ci", "g100p3.pv", "g100p3.rep", "g100p3.cnt", "g100Cp.pv"]
+
     # --- cnt mode (consel -C): the AU fit from the counts alone
     for case in ("g100", "g100e", "tiny", "g100fe"):
         orc.run_ref("consel", ["-C", case, case + "C"], work)

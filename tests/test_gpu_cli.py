@@ -143,6 +143,20 @@ def test_quick_mctest(gold, orc, tmp_path):
     assert len(a) != len(b) or not np.allclose(a, b)  # the switch does change the numbers
 
 
+def test_pdm_aic_correction(gold, orc, tmp_path):
+    """--pdm / --aictype / --ppn (read_pdm, do_pdm, BIC branch of do_batest: src/consel.c:675-744, 1325-1332)."""
+    shutil.copy(gold / "g100.rmt", tmp_path / "g100.rmt")
+    shutil.copy(gold / "pdm.vt", tmp_path / "pdm.vt")
+    out = run("consel", ["--pdm", "pdm", "g100", "g100p"], tmp_path)
+    assert "# aictype:2" in out and "# ppn:1" in out
+    same_numbers(tmp_path / "g100p.pv", gold / "g100p.pv", orc)
+    same_numbers(tmp_path / "g100p.ci", gold / "g100p.ci", orc)
+    run("consel", ["--pdm", "pdm", "--aictype", "3", "--ppn", "3414", "-r", "-c", "g100", "g100p3"], tmp_path)
+    assert (tmp_path / "g100p3.rep").read_bytes() == (gold / "g100p3.rep").read_bytes()
+    assert (tmp_path / "g100p3.cnt").read_bytes() == (gold / "g100p3.cnt").read_bytes()
+    same_numbers(tmp_path / "g100p3.pv", gold / "g100p3.pv", orc)
+
+
 def test_cli_error_protocol(tmp_path):
     r = subprocess.run([str(BIN / "makermt"), "--bogus"], cwd=tmp_path, capture_output=True, text=True)
     assert r.returncode == 1 and "#! Terminated: error in command line." in r.stdout

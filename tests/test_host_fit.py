@@ -170,3 +170,16 @@ def test_consel_cnt_mode_cli(case, gold, tmp_path):
     assert (tmp_path / f"{case}C.pv").read_bytes() == (gold / f"{case}C.pv").read_bytes()
     r = subprocess.run([str(exe), "-C", "-R", case], cwd=tmp_path, capture_output=True, text=True)
     assert r.returncode == 1 and "only one of -C and -R can be specified" in r.stdout
+
+
+def test_consel_cnt_mode_pmin(gold, tmp_path):
+    """--pmin (rcalpval, src/consel.c:2727-2734): refit on fewer scales while the fit's p-value is too small."""
+    import shutil
+    import subprocess
+    from pathlib import Path
+    exe = Path(__file__).resolve().parent.parent / "consel_b200" / "bin" / "consel"
+    shutil.copy(gold / "g100.cnt", tmp_path / "g100.cnt")
+    r = subprocess.run([str(exe), "-C", "--pmin", "0.5", "g100", "g100Cp"], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert (tmp_path / "g100Cp.pv").read_bytes() == (gold / "g100Cp.pv").read_bytes()
+    assert (gold / "g100Cp.pv").read_bytes() != (gold / "g100C.pv").read_bytes()
