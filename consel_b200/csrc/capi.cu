@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <thread>
+#include <map>
 #include <vector>
 
 #include "cgpu_internal.h"
@@ -163,31 +164,130 @@ static int alloc_reps(int K, int S, const int *bb, DevReps **out) {
     return CGPU_OK;
 }
 
-// Chunk size (log2 draws) of the MT19937 jump tree, from a cost model measured on B200:
-// a jump costs ~0.75 us of whole-GPU time (126 us on one SM), a tree level ~20 us of
-// latency, and a draw CTA slot (6 chunks resident per SM) produces one draw per ~1.0 ns;
-// the draw launch runs in whole waves of 6 x SMs chunks.
-static int pick_chunk_log2(unsigned long long needed_draws, unsigned long long stream_end, int nranges) {
-    if (G().opt_chunk_log2 >= 10 && G().opt_chunk_log2 <= 30) return G().opt_chunk_log2;
+// Chunk length (draws) of the MT19937 jump tree, from a cost model measured on B200: a jump
+// costs ~0.75 us of whole-GPU time (126 us on one SM), a tree level ~20 us of latency, and
+// a draw CTA slot (6 chunks resident per SM) produces one draw per ~1.0 ns; the draw launch
+// runs in whole waves of 6 x SMs chunks.  Candidates: the powers of two (their jump
+// polynomials x^(2^i) are tabulated at init) and, per wave count, the EQUAL-FILL length that
+// makes the chunks of this call just fill the slots (774 chunks of 2^22 draws leave 13 % of
+// the slots of a C2 launch idle for its whole duration); its polynomials x^(len*2^r) are
+// computed on first use and cached.
+static unsigned long long pick_chunk_len(unsigned long long needed_draws, unsigned long long stream_end, int nranges,
+                                         const unsigned long long *lo, const unsigned long long *hi) {
+    if (G().opt_chunk_log2 >= 10 && G().opt_chunk_log2 <= 30) return 1ull << G().opt_chunk_log2;
     const int sms = G().sm_count > 0 ? G().sm_count : 148;
     const double slots = 6.0 * sms;
-    int best = 12;
+    unsigned long long best = 1ull << 12;
     double best_cost = 1e300;
+    auto levels = [&](unsigned long long len) {
+        int top = 0;
+        while ((stream_end + len - 1) / len > (1ull << top)) top++;
+        return top;
+    };
     for (int m = 12; m <= 24; m++) {
         const double chunk = (double)(1ull << m);
         const double pn = std::ceil((double)needed_draws / chunk) + nranges;
-        int top = 0;
-        while (((stream_end + (1ull << m) - 1) >> m) > (1ull << top)) top++;
+        const int top = levels(1ull << m);
         if (m + top > MT_MAXLOG) continue;
         const double waves = std::ceil(pn / slots);
         const double cost = pn * 0.75e-6 + top * 20e-6 + waves * chunk * 1.0e-9;
         if (cost < best_cost) {
             best_cost = cost;
-            best = m;
+            best = 1ull << m;
         }
     }
-    return best;
+    const bool force_fill = G().opt_chunk_fill == 2;  // tests: equal-fill whatever the model says
+    if (G().opt_chunk_fill == 0 || nranges > 32 || (!force_fill && needed_draws < (1ull << 22))) return best;
+    constexpr unsigned long long ALIGN = 4 * MT_N;  // whole groups of four blocks (the branch-free body of the draw kernel)
+    std::vector<unsigned long long> off(nranges, 0);
+    unsigned long long pick = best;
+    for (int w = 1; w <= 4; w++) {
+        const long long cap = (long long)(w * slots);
+        if (cap <= nranges + 1) continue;
+        unsigned long long len = (needed_draws + (unsigned long long)(cap - nranges) - 1) / (unsigned long long)(cap - nranges);
+        len = (len + ALIGN - 1) / ALIGN * ALIGN;
+        int count = 0;
+        for (int tries = 0; tries < 8; tries++) {  // the estimate ignores how the ranges sit on the chunk grid
+            DrawPlan dp;
+            if (make_draw_plan(nranges, lo, hi, off.data(), len, stream_end, &dp) != CGPU_OK) return best;
+            count = dp.cum[dp.nintervals];
+            if (count <= cap) break;
+            len = (len + len / 128 + ALIGN - 1) / ALIGN * ALIGN;
+        }
+        if (count > cap || (len < 4096 && !force_fill)) continue;
+        const int top = levels(len);
+        if (top > 40 || (len >> (62 - top)) != 0) continue;  // len * 2^top must stay a 64-bit exponent
+        const double cost = count * 0.75e-6 + top * 20e-6 + w * (double)len * 1.0e-9;
+        if (cost < 0.98 * best_cost || (force_fill && pick == best)) {
+            best_cost = cost;
+            pick = len;
+        }
+    }
+    return pick;
 }
+
+// Position lists of the jump polynomials x^(len * 2^r) mod phi, r = 0 .. levels-1, for a chunk
+// length that is not a power of two: built on the host on first use (a few squarings each),
+// kept on the device.  Entries are never freed while a plan may still reference them; the
+// cache is bounded by rebuilding from scratch (after a device synchronize) when it is full.
+struct JumpPolys {
+    uint32_t *d_pos = nullptr;
+    int levels = 0;
+    int nquads[64];
+};
+static std::map<unsigned long long, JumpPolys> &jump_cache() {
+    static std::map<unsigned long long, JumpPolys> c;  // (node-based: addresses of live entries are stable)
+    return c;
+}
+static std::vector<uint32_t *> &jump_graveyard() {
+    static std::vector<uint32_t *> g;
+    return g;
+}
+static void jump_cache_clear() {
+    for (auto &kv : jump_cache()) cudaFree(kv.second.d_pos);
+    for (uint32_t *p : jump_graveyard()) cudaFree(p);
+    jump_cache().clear();
+    jump_graveyard().clear();
+}
+// called at the start of a resampling call, when no plan references the cache
+static int jump_cache_trim() {
+    if (jump_cache().size() < 20 && jump_graveyard().empty()) return CGPU_OK;
+    CGPU_CUDA(cudaDeviceSynchronize());
+    if (jump_cache().size() >= 20) jump_cache_clear();
+    for (uint32_t *p : jump_graveyard()) cudaFree(p);
+    jump_graveyard().clear();
+    return CGPU_OK;
+}
+static int jump_polys_for(unsigned long long len, int levels, const uint32_t **d_pos, const int **nquads) {
+    auto &cache = jump_cache();
+    auto it = cache.find(len);
+    if (it != cache.end() && it->second.levels >= levels) {
+        *d_pos = it->second.d_pos;
+        *nquads = it->second.nquads;
+        return CGPU_OK;
+    }
+    if (it != cache.end()) {  // too few levels: an earlier plan of this call may still use the old lists
+        jump_graveyard().push_back(it->second.d_pos);
+        cache.erase(it);
+    }
+    JumpPolys jp;
+    jp.levels = std::max(levels, 12);
+    while (jp.levels > levels && (len >> (62 - jp.levels)) != 0) jp.levels--;
+    std::vector<uint32_t> pos((size_t)jp.levels * MT_POS_STRIDE, 0u);
+    for (int r = 0; r < jp.levels; r++) {
+        Gf2Poly g;
+        mt_poly_xpow(len << r, &g);
+        jp.nquads[r] = mt_poly_positions(&g, pos.data() + (size_t)r * MT_POS_STRIDE);
+    }
+    CGPU_CUDA(cudaMalloc(&jp.d_pos, pos.size() * sizeof(uint32_t)));
+    CGPU_CUDA(cudaMemcpy(jp.d_pos, pos.data(), pos.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    auto ins = cache.emplace(len, jp).first;
+    *d_pos = ins->second.d_pos;
+    *nquads = ins->second.nquads;
+    return CGPU_OK;
+}
+
+static unsigned long long g_last_chunk_len = 0;
 
 // Chunk start states W_{offset + c*2^m} for the chunks c that cover the kept ranges, by a
 // binary jump tree walked from the top bit down: at bit r every live node a (a multiple of
@@ -197,12 +297,16 @@ static int mt_plan(unsigned long seed, unsigned long long stream_offset, unsigne
                    const unsigned long long *lo, const unsigned long long *hi, MtPlan *plan) {
     unsigned long long needed = 0;
     for (int r = 0; r < nranges; r++) needed += hi[r] > lo[r] ? hi[r] - lo[r] : 0;
-    plan->chunk_log2 = pick_chunk_log2(needed, stream_end, nranges);
-    const int m = plan->chunk_log2;
+    plan->chunk_len = pick_chunk_len(needed, stream_end, nranges, lo, hi);
+    g_last_chunk_len = plan->chunk_len;
+    const unsigned long long clen = plan->chunk_len;
+    const bool pow2 = (clen & (clen - 1)) == 0;
+    int m = 0;  // log2 of a power-of-two chunk length
+    while (pow2 && (1ull << m) < clen) m++;
     DrawPlan dp;
     {
         std::vector<unsigned long long> off(nranges, 0);
-        CGPU_TRY(make_draw_plan(nranges, lo, hi, off.data(), m, stream_end, &dp));
+        CGPU_TRY(make_draw_plan(nranges, lo, hi, off.data(), clen, stream_end, &dp));
     }
     plan->nintervals = dp.nintervals;
     for (int i = 0; i < dp.nintervals; i++) {
@@ -215,9 +319,15 @@ static int mt_plan(unsigned long seed, unsigned long long stream_offset, unsigne
     const unsigned long long maxchunk = plan->first[plan->nintervals - 1] + (unsigned long long)(plan->count[plan->nintervals - 1] - 1);
     int top = 0;
     while (top < 63 && (maxchunk >> top) != 0) top++;
-    if (top > 0 && m + top - 1 > MT_MAXLOG) {
+    if (top > 0 && (pow2 ? m + top - 1 > MT_MAXLOG : (top > 40 || (clen >> (62 - top)) != 0))) {
         set_error(CGPU_EINVAL, "stream of %llu draws exceeds the jump table", stream_end);
         return CGPU_EINVAL;
+    }
+    if (pow2) {
+        plan->d_pos = G().d_jump_table + (size_t)m * MT_POS_STRIDE;
+        plan->nquads = G().jump_nquads + m;
+    } else {
+        CGPU_TRY(jump_polys_for(clen, top, &plan->d_pos, &plan->nquads));
     }
     auto wanted = [&](unsigned long long a, unsigned long long b) {  // any wanted chunk in [a, b]?
         for (int i = 0; i < plan->nintervals; i++)
@@ -280,7 +390,6 @@ static int mt_plan(unsigned long seed, unsigned long long stream_offset, unsigne
 static int mt_launch(MtPlan *plan, cudaStream_t st) {
     Globals &g = G();
     if (plan->nslots == 0) return CGPU_OK;
-    const int m = plan->chunk_log2;
     CGPU_CUDA(cudaMemsetAsync(plan->d_states, 0, (size_t)plan->nslots * MT_N * sizeof(uint32_t), st));
     CGPU_CUDA(cudaMemcpyAsync(plan->d_states + (size_t)plan->root * MT_N, plan->h_stage.data(), MT_N * sizeof(uint32_t),
                               cudaMemcpyHostToDevice, st));
@@ -290,8 +399,8 @@ static int mt_launch(MtPlan *plan, cudaStream_t st) {
     for (int r = (int)plan->level_cnt.size() - 1; r >= 0; r--) {
         const int cnt = plan->level_cnt[r];
         if (!cnt) continue;
-        CGPU_TRY(launch_mt_jump(plan->d_states, plan->d_pairs + done, g.d_jump_table + (size_t)(m + r) * MT_POS_STRIDE,
-                                g.jump_nquads[m + r], cnt, st));
+        CGPU_TRY(launch_mt_jump(plan->d_states, plan->d_pairs + done, plan->d_pos + (size_t)r * MT_POS_STRIDE,
+                                plan->nquads[r], cnt, st));
         done += cnt;
     }
     return CGPU_OK;
@@ -346,6 +455,7 @@ static int scaleboot_core(DevMatrix &m, int S, const int *bn, const int *bb, uns
         set_error(CGPU_EINVAL, "unknown rng_mode %d", rng_mode);
         return CGPU_EINVAL;
     }
+    CGPU_TRY(jump_cache_trim());  // no jump plan is alive here
     for (int s = 0; s < S; s++)
         if (bn[s] <= 0 || bb[s] < 0) {
             set_error(CGPU_EINVAL, "scale %d: bn=%d bb=%d", s, bn[s], bb[s]);
@@ -518,13 +628,13 @@ static int scaleboot_core(DevMatrix &m, int S, const int *bn, const int *bb, uns
             }
             if (!flo.empty()) {
                 DrawPlan dp;
-                CGPU_TRY(make_draw_plan((int)flo.size(), flo.data(), fhi.data(), foff.data(), plan.chunk_log2, base[S], &dp));
+                CGPU_TRY(make_draw_plan((int)flo.size(), flo.data(), fhi.data(), foff.data(), plan.chunk_len, base[S], &dp));
                 CGPU_TRY(resolve_draw_slots(plan, &dp));
                 CGPU_TRY(launch_mt_draw_hist(plan, dp, fbn.data(), frow.data(), NP, (uint32_t)n, ws.d_err, st));
             }
         } else if (idx_whole_run) {
             DrawPlan dp;
-            CGPU_TRY(make_draw_plan(S, lo.data(), hi.data(), idx_off.data(), plan.chunk_log2, base[S], &dp));
+            CGPU_TRY(make_draw_plan(S, lo.data(), hi.data(), idx_off.data(), plan.chunk_len, base[S], &dp));
             CGPU_TRY(resolve_draw_slots(plan, &dp));
             CGPU_TRY(launch_mt_draw(plan, dp, (uint32_t)n, ws.d_idx, st));
         }
@@ -562,7 +672,7 @@ static int scaleboot_core(DevMatrix &m, int S, const int *bn, const int *bb, uns
                     pt.begin(9);
                     DrawPlan dp;
                     CGPU_TRY(make_draw_plan(stage_cut[g + 1] - stage_cut[g], st_lo.data() + stage_cut[g], st_hi.data() + stage_cut[g],
-                                            idx_off.data() + stage_cut[g], plans[g].chunk_log2, base[S], &dp));
+                                            idx_off.data() + stage_cut[g], plans[g].chunk_len, base[S], &dp));
                     CGPU_TRY(resolve_draw_slots(plans[g], &dp));
                     CGPU_TRY(launch_mt_draw(plans[g], dp, (uint32_t)n, ws.d_idx, st));
                     pt.end();
@@ -787,6 +897,7 @@ void cgpu_shutdown(void) {
     if (!g.inited) return;
     cudaStreamSynchronize(g.stream);
     dev_free(g.d_jump_table);
+    jump_cache_clear();
     for (int i = 0; i < 4; i++) {
         dev_free(g.scratch[i]);
         g.scratch[i] = nullptr;
@@ -834,6 +945,7 @@ int cgpu_set_option(const char *name, int value) {
     else if (!strcmp(name, "i8_dbg")) g.opt_i8_dbg = value;
     else if (!strcmp(name, "mc_smooth")) g.opt_mc_smooth = value;
     else if (!strcmp(name, "chunk_log2")) g.opt_chunk_log2 = value;
+    else if (!strcmp(name, "chunk_fill")) g.opt_chunk_fill = value;
     else {
         set_error(CGPU_EINVAL, "unknown option %s", name);
         return CGPU_EINVAL;
@@ -899,6 +1011,8 @@ int cgpu_reps_download(const cgpu_reps *rr, double *const *rep_out) {
     if (!r || !rep_out) return CGPU_EINVAL;
     return reps_download(r, rep_out, G().stream);
 }
+
+unsigned long long cgpu_last_chunk_len(void) { return g_last_chunk_len; }
 
 void cgpu_reps_free(cgpu_reps *rr) { free_reps(reinterpret_cast<DevReps *>(rr)); }
 

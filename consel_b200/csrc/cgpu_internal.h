@@ -84,7 +84,7 @@ struct Globals {
     void *scratch[4] = {nullptr, nullptr, nullptr, nullptr};
     size_t scratch_cap[4] = {0, 0, 0, 0};
     // tuning switches (cgpu_set_option); -1 = built-in default
-    int opt_overlap = -1, opt_hist_algo = -1, opt_contract_algo = -1, opt_i8_oneshot = -1, opt_draw_nch = -1, opt_chunk_log2 = -1, opt_i8_fuse = -1, opt_draw_fuse = -1, opt_stage = -1, opt_i8_dbg = -1, opt_mc_smooth = -1;
+    int opt_overlap = -1, opt_hist_algo = -1, opt_contract_algo = -1, opt_i8_oneshot = -1, opt_draw_nch = -1, opt_chunk_log2 = -1, opt_i8_fuse = -1, opt_draw_fuse = -1, opt_stage = -1, opt_i8_dbg = -1, opt_mc_smooth = -1, opt_chunk_fill = -1;
 };
 Globals &G();
 int ensure_init();
@@ -154,7 +154,10 @@ struct DrawPlan {
 struct MtPlan {
     uint32_t *d_states = nullptr;  // nslots x 624 words
     int2 *d_pairs = nullptr;       // (src slot, dst slot) of every jump, level by level
-    int chunk_log2 = 0;
+    unsigned long long chunk_len = 0;  // draws per chunk: a power of two (tabulated jump polynomials) or an
+                                       // equal-fill length with its own cached polynomials x^(chunk_len*2^r)
+    const uint32_t *d_pos = nullptr;   // device position lists of the jump polynomials, level r at r*MT_POS_STRIDE
+    const int *nquads = nullptr;       // host: 8-position groups per level
     int nintervals = 0;
     unsigned long long first[32];
     int count[32], slot[32];
@@ -169,7 +172,7 @@ struct MtPlan {
     }
 };
 int make_draw_plan(int nranges, const unsigned long long *lo, const unsigned long long *hi,
-                   const unsigned long long *off, int chunk_log2, unsigned long long stream_end, DrawPlan *plan);
+                   const unsigned long long *off, unsigned long long chunk_len, unsigned long long stream_end, DrawPlan *plan);
 int resolve_draw_slots(const MtPlan &mt, DrawPlan *plan);
 // fused draws + site histograms (byte rows of NP sites; needs bn >= 1248 and NP small enough for shared memory)
 bool mt_draw_hist_fits(int NP);

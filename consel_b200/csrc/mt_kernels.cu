@@ -334,14 +334,14 @@ __device__ __forceinline__ void draw_step(DrawLane<PATH, IdxT> &L, uint32_t *bt,
 
 template <int PATH, typename IdxT, int CPC>
 __global__ void __launch_bounds__(DrawCfg<CPC>::threads, DrawCfg<CPC>::ctas)
-mt_draw_kernel(const uint32_t *__restrict__ states, int chunk_log2, DrawPlan plan, uint32_t n, IdxT *__restrict__ idx,
+mt_draw_kernel(const uint32_t *__restrict__ states, unsigned long long chunk_len, DrawPlan plan, uint32_t n, IdxT *__restrict__ idx,
                DrawConsts kc) {
     __shared__ uint32_t buf[CPC + 1][2][MT_N];  // +1: the padding lanes of the last warp index a dummy slot
     __shared__ unsigned long long s_begin[CPC + 1], s_end[CPC + 1];  // read on the slow path only
     constexpr int H = DRAW_H;
     const int c = threadIdx.x / H, t = threadIdx.x - c * H;
     const double dn = (double)n;
-    const unsigned int steps = (unsigned int)(((1ull << chunk_log2) + MT_N - 1) / MT_N);
+    const unsigned int steps = (unsigned int)((chunk_len + MT_N - 1) / MT_N);
 
     DrawLane<PATH, IdxT> L;
     L.r0 = L.r1 = L.r2 = 0;
@@ -358,8 +358,8 @@ mt_draw_kernel(const uint32_t *__restrict__ states, int chunk_log2, DrawPlan pla
             int iv = 0;
             while (ci >= plan.cum[iv + 1]) iv++;
             const unsigned long long chunk = plan.first[iv] + (unsigned long long)(ci - plan.cum[iv]);
-            d_begin = chunk << chunk_log2;
-            d_end = d_begin + (1ull << chunk_log2);
+            d_begin = chunk * chunk_len;
+            d_end = d_begin + chunk_len;
             if (d_end > plan.stream_end) d_end = plan.stream_end;
             if (d_end > d_begin) {
                 const uint32_t *w = states + (size_t)(plan.slot[iv] + (ci - plan.cum[iv])) * MT_N + t;
@@ -435,7 +435,7 @@ struct HistPlan {
 
 template <int CPC>
 __global__ void __launch_bounds__(DrawCfg<CPC>::threads, DrawCfg<CPC>::ctas)
-mt_draw_hist_kernel(const uint32_t *__restrict__ states, int chunk_log2, DrawPlan plan, HistPlan hp, uint32_t n,
+mt_draw_hist_kernel(const uint32_t *__restrict__ states, unsigned long long chunk_len, DrawPlan plan, HistPlan hp, uint32_t n,
                     DrawConsts kc) {
     extern __shared__ __align__(16) uint32_t dh_smem[];
     constexpr int H = DRAW_H;
@@ -444,7 +444,7 @@ mt_draw_hist_kernel(const uint32_t *__restrict__ states, int chunk_log2, DrawPla
     uint32_t *hist_base = dh_smem + (CPC + 1) * 2 * MT_N;       // [CPC][2][NP]; the padding lanes alias group 0 (they only zero it)
     const int c = threadIdx.x / H, t = threadIdx.x - c * H;
     const bool third = t < MT_N - 2 * H;
-    const unsigned int steps = (unsigned int)(((1ull << chunk_log2) + MT_N - 1) / MT_N);
+    const unsigned int steps = (unsigned int)((chunk_len + MT_N - 1) / MT_N);
     uint32_t *bt = buf_base + (size_t)c * 2 * MT_N + t;
     uint32_t *hist = hist_base + (size_t)(c < CPC ? c : 0) * 2 * NP;
 
@@ -456,8 +456,8 @@ mt_draw_hist_kernel(const uint32_t *__restrict__ states, int chunk_log2, DrawPla
             int iv = 0;
             while (ci >= plan.cum[iv + 1]) iv++;
             const unsigned long long chunk = plan.first[iv] + (unsigned long long)(ci - plan.cum[iv]);
-            d_begin = chunk << chunk_log2;
-            d_end = d_begin + (1ull << chunk_log2);
+            d_begin = chunk * chunk_len;
+            d_end = d_begin + chunk_len;
             if (d_end > plan.stream_end) d_end = plan.stream_end;
             if (d_end > d_begin) {
                 const uint32_t *w = states + (size_t)(plan.slot[iv] + (ci - plan.cum[iv])) * MT_N + t;
@@ -643,7 +643,7 @@ mt_draw_hist_kernel(const uint32_t *__restrict__ states, int chunk_log2, DrawPla
 }
 
 template <int PATH, typename IdxT>
-static void mt_draw_launch(const uint32_t *d_states, int chunk_log2, const DrawPlan &plan, uint32_t n, IdxT *idx,
+static void mt_draw_launch(const uint32_t *d_states, unsigned long long chunk_len, const DrawPlan &plan, uint32_t n, IdxT *idx,
                            cudaStream_t st) {
     const int sms = G().sm_count > 0 ? G().sm_count : 148;
     const int nchunks = plan.cum[plan.nintervals];
@@ -651,16 +651,16 @@ static void mt_draw_launch(const uint32_t *d_states, int chunk_log2, const DrawP
     const DrawConsts kc = {1u << 31, 1u << 21, 1u << 14, 0x9908b0dfu};
     // measured: 3 chunks per CTA beats 2 and 1 whenever there are enough chunks to give every SM a CTA
     if (force == 3 || (force < 0 && nchunks >= 3 * sms))
-        mt_draw_kernel<PATH, IdxT, 3><<<(nchunks + 2) / 3, DrawCfg<3>::threads, 0, st>>>(d_states, chunk_log2, plan, n, idx, kc);
+        mt_draw_kernel<PATH, IdxT, 3><<<(nchunks + 2) / 3, DrawCfg<3>::threads, 0, st>>>(d_states, chunk_len, plan, n, idx, kc);
     else if (force == 2)
-        mt_draw_kernel<PATH, IdxT, 2><<<(nchunks + 1) / 2, DrawCfg<2>::threads, 0, st>>>(d_states, chunk_log2, plan, n, idx, kc);
+        mt_draw_kernel<PATH, IdxT, 2><<<(nchunks + 1) / 2, DrawCfg<2>::threads, 0, st>>>(d_states, chunk_len, plan, n, idx, kc);
     else
-        mt_draw_kernel<PATH, IdxT, 1><<<nchunks, DrawCfg<1>::threads, 0, st>>>(d_states, chunk_log2, plan, n, idx, kc);
+        mt_draw_kernel<PATH, IdxT, 1><<<nchunks, DrawCfg<1>::threads, 0, st>>>(d_states, chunk_len, plan, n, idx, kc);
 }
 
 // plan for `nranges` disjoint, ascending stream ranges; off[r] = index-buffer offset of range r
 int make_draw_plan(int nranges, const unsigned long long *lo, const unsigned long long *hi,
-                   const unsigned long long *off, int chunk_log2, unsigned long long stream_end, DrawPlan *plan) {
+                   const unsigned long long *off, unsigned long long chunk_len, unsigned long long stream_end, DrawPlan *plan) {
     if (nranges < 1 || nranges > 32) {
         set_error(CGPU_EINVAL, "draw plan with %d ranges (1..32)", nranges);
         return CGPU_EINVAL;
@@ -675,7 +675,7 @@ int make_draw_plan(int nranges, const unsigned long long *lo, const unsigned lon
         plan->lo[k] = lo[r];
         plan->hi[k] = hi[r];
         plan->off[k] = off[r];
-        unsigned long long c0 = lo[r] >> chunk_log2, c1 = (hi[r] - 1) >> chunk_log2;
+        unsigned long long c0 = lo[r] / chunk_len, c1 = (hi[r] - 1) / chunk_len;
         if (plan->nintervals > 0) {
             const int p = plan->nintervals - 1;
             const unsigned long long last = plan->first[p] + (unsigned long long)(plan->cum[p + 1] - plan->cum[p]) - 1;
@@ -709,13 +709,13 @@ int resolve_draw_slots(const MtPlan &mt, DrawPlan *plan) {
 int launch_mt_draw(const MtPlan &mt, const DrawPlan &plan, uint32_t n, void *d_idx, cudaStream_t st) {
     if (plan.nranges <= 0 || plan.cum[plan.nintervals] <= 0) return CGPU_OK;
     const uint32_t *d_states = mt.d_states;
-    const int chunk_log2 = mt.chunk_log2;
+    const unsigned long long chunk_len = mt.chunk_len;
     uint32_t *i32 = static_cast<uint32_t *>(d_idx);
     uint16_t *i16 = static_cast<uint16_t *>(d_idx);
-    if (n == 0) mt_draw_launch<2, uint32_t>(d_states, chunk_log2, plan, n, i32, st);
-    else if (idx_is16(n)) mt_draw_launch<0, uint16_t>(d_states, chunk_log2, plan, n, i16, st);
-    else if (n < (1u << 21)) mt_draw_launch<0, uint32_t>(d_states, chunk_log2, plan, n, i32, st);
-    else mt_draw_launch<1, uint32_t>(d_states, chunk_log2, plan, n, i32, st);
+    if (n == 0) mt_draw_launch<2, uint32_t>(d_states, chunk_len, plan, n, i32, st);
+    else if (idx_is16(n)) mt_draw_launch<0, uint16_t>(d_states, chunk_len, plan, n, i16, st);
+    else if (n < (1u << 21)) mt_draw_launch<0, uint32_t>(d_states, chunk_len, plan, n, i32, st);
+    else mt_draw_launch<1, uint32_t>(d_states, chunk_len, plan, n, i32, st);
     CGPU_LAUNCH_CHECK();
     return CGPU_OK;
 }
@@ -726,7 +726,7 @@ int launch_mt_draw_range(const MtPlan &mt, unsigned long long lo, unsigned long 
     if (hi <= lo) return CGPU_OK;
     DrawPlan plan;
     const unsigned long long off = 0;
-    CGPU_TRY(make_draw_plan(1, &lo, &hi, &off, mt.chunk_log2, hi, &plan));
+    CGPU_TRY(make_draw_plan(1, &lo, &hi, &off, mt.chunk_len, hi, &plan));
     CGPU_TRY(resolve_draw_slots(mt, &plan));
     return launch_mt_draw(mt, plan, n, d_idx, st);
 }
@@ -760,7 +760,7 @@ int launch_mt_draw_hist(const MtPlan &mt, const DrawPlan &plan, const unsigned i
             CGPU_CUDA(cudaFuncSetAttribute(mt_draw_hist_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
             attr3 = true;
         }
-        mt_draw_hist_kernel<3><<<(nchunks + 2) / 3, DrawCfg<3>::threads, smem, st>>>(mt.d_states, mt.chunk_log2, plan, hp, n, kc);
+        mt_draw_hist_kernel<3><<<(nchunks + 2) / 3, DrawCfg<3>::threads, smem, st>>>(mt.d_states, mt.chunk_len, plan, hp, n, kc);
     } else {
         const size_t smem = mt_draw_hist_smem(NP, 1);
         static bool attr1 = false;
@@ -768,7 +768,7 @@ int launch_mt_draw_hist(const MtPlan &mt, const DrawPlan &plan, const unsigned i
             CGPU_CUDA(cudaFuncSetAttribute(mt_draw_hist_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
             attr1 = true;
         }
-        mt_draw_hist_kernel<1><<<nchunks, DrawCfg<1>::threads, smem, st>>>(mt.d_states, mt.chunk_log2, plan, hp, n, kc);
+        mt_draw_hist_kernel<1><<<nchunks, DrawCfg<1>::threads, smem, st>>>(mt.d_states, mt.chunk_len, plan, hp, n, kc);
     }
     CGPU_LAUNCH_CHECK();
     return CGPU_OK;

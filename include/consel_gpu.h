@@ -181,13 +181,16 @@ int cgpu_last_timing_ex(double *ms, int n);
  * "i8_oneshot" 0|1, "i8_fuse" 0|1 (recombination in the GEMM epilogue), "draw_nch" 1|2|3,
  * "draw_fuse" 0|1 (draws + histograms in one kernel, int8 mode, opt-in), "stage" 0|1 (staged
  * index production of host-output int8 calls: 0 off, 1 always, default by size),
- * "chunk_log2" 10..30, "i8_dbg" 0..3 (switches parts of the GEMM epilogue off: timing only,
+ * "chunk_log2" 10..30 (force a power-of-two chunk of the MT19937 jump tree), "chunk_fill" 0|1|2
+ * (equal-fill chunk lengths that are not powers of two: off, by cost model (default), forced), "i8_dbg" 0..3 (switches parts of the GEMM epilogue off: timing only,
  * results are wrong), "mc_smooth" 0|1 (0 = consel --quick_mctest: the KH/SH p-values of
  * cgpu_mctest use the plain count #{v<=t} instead of the smoothed one, sw_pvaldist
  * src/consel.c:1875-1884).  A negative value restores the default.  Returns CGPU_EINVAL for an
  * unknown name.  Environment (development): CGPU_TRACE=1 prints every timed span of a
  * resampling call, CGPU_STAGE_FRACS=a,b,c overrides the stage sizes.                    */
 int cgpu_set_option(const char *name, int value);
+/* draws per chunk of the most recent MT19937 jump plan (diagnostics / tests) */
+unsigned long long cgpu_last_chunk_len(void);
 /* number of kernels launched by this library since cgpu_init (bench `gpu_launches`) */
 long long cgpu_launch_count(void);
 /* raw device pointer + shape of a replicate block, so a host framework can wrap it

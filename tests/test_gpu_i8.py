@@ -194,3 +194,54 @@ def test_int8_long_alignments_shared_histograms(cg, orc, n):
     ref = cg.scaleboot_all(L, bn, bb, 31, rng_mode=cg.RNG_PHILOX, sum_mode=cg.SUM_FAST)
     for s in range(len(bb)):
         assert np.abs(ph[s] - ref[s]).max() <= 1e-9 * np.abs(ref[s]).max()
+
+
+def test_equal_fill_chunks_same_result(cg, orc):
+    """Chunk lengths that are not powers of two (equal-fill, jump polynomials x^(len*2^r) built on
+    first use): the same blocks as with tabulated power-of-two chunks, strict mode == oracle,
+    shards == slices, staged == unstaged."""
+    import ctypes as C
+    from consel_b200.api import load
+    lib = load()
+    lib.cgpu_last_chunk_len.restype = C.c_ulonglong
+    K, n = 7, 1300
+    L = synth(K, n, seed=21)
+    rr = [0.5, 0.8, 1.0, 1.3]
+    bb = [300, 211, 150, 97]
+    _, bn, _ = orc.scale_setup(L, rr)
+    try:
+        cg.set_option("chunk_fill", 0)
+        ref8 = cg.scaleboot_all(L, bn, bb, 5, sum_mode=cg.SUM_INT8)
+        assert lib.cgpu_last_chunk_len() & (lib.cgpu_last_chunk_len() - 1) == 0
+        cg.set_option("chunk_fill", 2)
+        got8 = cg.scaleboot_all(L, bn, bb, 5, sum_mode=cg.SUM_INT8)
+        clen = lib.cgpu_last_chunk_len()
+        assert clen & (clen - 1) != 0, clen  # really not a power of two
+        for s in range(len(bb)):
+            assert np.array_equal(got8[s], ref8[s]), s
+        strict = cg.scaleboot_all(L, bn, bb, 5, sum_mode=cg.SUM_STRICT)
+        want = orc.makermt(L, bn, bb, 5)
+        for s in range(len(bb)):
+            assert np.array_equal(strict[s], want[s]), s
+        cg.set_option("stage", 1)
+        staged = cg.scaleboot_all(L, bn, bb, 5, sum_mode=cg.SUM_INT8)
+        cg.set_option("stage", -1)
+        for s in range(len(bb)):
+            assert np.array_equal(staged[s], ref8[s]), s
+        for rank in range(3):
+            cg.set_shard(rank, 3)
+            loc = cg.scaleboot_all(L, bn, bb, 5, sum_mode=cg.SUM_INT8)
+            for s in range(len(bb)):
+                b0, b1 = cg.shard_range(bb[s])
+                assert np.array_equal(loc[s], ref8[s][:, b0:b1]), (rank, s)
+        cg.set_shard(0, 1)
+        # a non-zero stream offset (makermt -g continues the stream across files)
+        a = cg.scaleboot_all(L, bn, bb, 5, sum_mode=cg.SUM_INT8, stream_offset=123457)
+        cg.set_option("chunk_fill", 0)
+        b = cg.scaleboot_all(L, bn, bb, 5, sum_mode=cg.SUM_INT8, stream_offset=123457)
+        for s in range(len(bb)):
+            assert np.array_equal(a[s], b[s]), s
+    finally:
+        cg.set_shard(0, 1)
+        cg.set_option("stage", -1)
+        cg.set_option("chunk_fill", -1)

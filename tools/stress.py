@@ -27,7 +27,8 @@ for case in range(ncase):
     if min(bn) < 1:
         continue
     opts = {"chunk_log2": int(rng.choice([-1, 12, 14, 17, 20])), "stage": int(rng.choice([-1, 0, 1])),
-            "i8_fuse": int(rng.choice([-1, 0])), "draw_fuse": int(rng.choice([-1, 1]))}
+            "i8_fuse": int(rng.choice([-1, 0])), "draw_fuse": int(rng.choice([-1, 1])),
+            "chunk_fill": int(rng.choice([-1, 0, 2, 2]))}
     for k, v in opts.items():
         cg.set_option(k, v)
     world = int(rng.integers(1, 4))
