@@ -297,7 +297,7 @@ def run_ours(args) -> None:
         entry("mt_draw_kernel", "mt_draw_kernel<int path, uint16, 3 chunks/CTA> (MT19937 block regeneration + tempering + site index)",
               phases["mt_draw"], 1, "hbm", idx_b * draws, hbm_peak, "GB/s",
               "2 B written per draw (uint16 site index), all scales of the step in one launch",
-              "integer-issue bound, not HBM bound: ~1.0 warp-instruction per draw at ~70 % of the issue slots "
+              "integer-issue bound, not HBM bound: ~0.82 warp-instruction per draw at ~64 % of the issue slots "
               "(profiles/); the HBM fraction is reported because the contract asks for one of hbm|tensor"),
         entry("hist_group_kernel", "hist_group_kernel<uint16 idx, smem atomics, byte rows>", phases["resample"], nS, "hbm",
               (idx_b * draws + float(NP) * b_loc * nS) / nS, hbm_peak, "GB/s",
@@ -318,9 +318,9 @@ def run_ours(args) -> None:
               "launches_per_step=1 stands for the ~10 levels of the jump tree"),
     ]
     # the draw kernel is bound by instruction issue, which the hbm|tensor vocabulary cannot express:
-    # add the issue-slot view (warp-instructions per draw from profiles/r01_final_draw_hist_gemm_ncu_full.json)
+    # add the issue-slot view (warp-instructions per draw from profiles/r01_final_draw_equalfill_ncu_full.json)
     try:
-        prof = json.loads((ROOT / "profiles" / "r01_final_draw_hist_gemm_ncu_full.json").read_text())["launches"][0]
+        prof = json.loads((ROOT / "profiles" / "r01_final_draw_equalfill_ncu_full.json").read_text())["launches"][0]
         wi_per_draw = prof["warp_instructions"] / 3.243e9
         sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
         issue_peak = 4.0 * torch.cuda.get_device_properties(local).multi_processor_count * sm_mhz * 1e6
