@@ -19,7 +19,18 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters, 
     if (s == 123.456) out[0] = s;  // keep the loop alive
 }
 
+int bench_i8_peak(double *tops, cudaStream_t st);  // i8_kernels.cu
+
 }  // namespace cgpu
+
+// dense int8 tensor-core issue rate (TOP/s) of tcgen05.mma kind::i8 from shared-memory-resident
+// operands, measured on this device: the denominator of the GEMM's roofline fraction
+extern "C" int cgpu_bench_i8_peak(double *tops) {
+    using namespace cgpu;
+    CGPU_TRY(ensure_init());
+    if (!tops) return CGPU_EINVAL;
+    return bench_i8_peak(tops, G().stream);
+}
 
 extern "C" int cgpu_bench_fp64_peak(double *tflops) {
     using namespace cgpu;

@@ -8,16 +8,21 @@
 #include <algorithm>
 #include <thread>
 #include <map>
+#include <mutex>
 #include <vector>
 
 #include "cgpu_internal.h"
 
 namespace cgpu {
 
-static thread_local char t_err[512] = "no error";
+// one process-wide message: the AU driver issues count queries from a helper thread, and the
+// program that reports the failure (`#! Terminated: ...`) runs on the main thread
+static char t_err[512] = "no error";
+static std::mutex g_err_mu;
 std::atomic<long long> g_launches{0};
 
 void set_error(int code, const char *fmt, ...) {
+    std::lock_guard<std::mutex> lk(g_err_mu);
     va_list ap;
     va_start(ap, fmt);
     int off = snprintf(t_err, sizeof(t_err), "cgpu error %d: ", code);
@@ -90,6 +95,29 @@ void PhaseTimer::finish(double *ms) {
     }
     ms[1] += ms[8] + ms[9];
     (void)cudaGetLastError();
+}
+
+// ---- per-kernel timing registry (KT)
+struct KSpan {
+    std::string name;
+    cudaEvent_t a, b;
+};
+static std::vector<KSpan> &kspans() {
+    static std::vector<KSpan> v;
+    return v;
+}
+KT::KT(const char *name, cudaStream_t s) : st(s) {
+    if (G().opt_ktime != 1) return;
+    KSpan sp;
+    sp.name = name;
+    cudaEventCreate(&sp.a);
+    cudaEventCreate(&sp.b);
+    cudaEventRecord(sp.a, st);
+    kspans().push_back(sp);
+    slot = (int)kspans().size() - 1;
+}
+KT::~KT() {
+    if (slot >= 0 && slot < (int)kspans().size()) cudaEventRecord(kspans()[slot].b, st);
 }
 
 static void shard_range(int bb, int *b0, int *b1) {
@@ -467,7 +495,14 @@ static int scaleboot_core(DevMatrix &m, int S, const int *bn, const int *bb, uns
     const size_t budget = (size_t)4 << 30;
     int max_bn = 1;
     for (int s = 0; s < S; s++) max_bn = std::max(max_bn, bn[s]);
-    long long cap = std::min<long long>((long long)(budget / ((size_t)max_bn * 4)), (long long)(budget / (size_t)NP));
+    // (the index term only matters when the indices are produced batch by batch: an MT19937 call
+    // whose whole index stream does not fit the workspace, see idx_whole_run below)
+    unsigned long long total_draws = 0;
+    for (int s = 0; s < S; s++) total_draws += (unsigned long long)reps->nb[s] * (unsigned long long)bn[s];
+    const bool idx_per_batch = rng_mode == CGPU_RNG_MT19937 &&
+                               (S > 32 || total_draws * idx_bytes((uint32_t)n) > ((unsigned long long)64 << 30));
+    long long cap = (long long)(budget / (size_t)NP);
+    if (idx_per_batch) cap = std::min<long long>(cap, (long long)(budget / ((size_t)max_bn * 4)));
     cap = std::max<long long>(64, cap / 64 * 64);
     int max_nb = 0;
     for (int s = 0; s < S; s++) max_nb = std::max(max_nb, reps->nb[s]);
@@ -709,7 +744,7 @@ static int scaleboot_core(DevMatrix &m, int S, const int *bn, const int *bb, uns
                 pt.end();
             } else {
                 pt.begin(2, aux);
-                CGPU_TRY(launch_hist_philox((unsigned long long)seed, s, bA, n, NP, bn[s], nbat, ws.d_counts[buf], ws.d_err, aux, i8));
+                CGPU_TRY(launch_hist_philox((unsigned long long)seed, s, bA, n, NP, bn[s], nbat, ws.d_counts[buf], ws.d_err, aux, i8, stream_offset));
                 pt.end();
             }
             if (overlap) {
@@ -946,10 +981,51 @@ int cgpu_set_option(const char *name, int value) {
     else if (!strcmp(name, "mc_smooth")) g.opt_mc_smooth = value;
     else if (!strcmp(name, "chunk_log2")) g.opt_chunk_log2 = value;
     else if (!strcmp(name, "chunk_fill")) g.opt_chunk_fill = value;
+    else if (!strcmp(name, "ktime")) g.opt_ktime = value;
+    else if (!strcmp(name, "hist_wide")) g.opt_hist_wide = value;
     else {
         set_error(CGPU_EINVAL, "unknown option %s", name);
         return CGPU_EINVAL;
     }
+    return CGPU_OK;
+}
+
+int cgpu_kernel_times(char *buf, int len) {
+    if (!buf || len <= 0) return CGPU_EINVAL;
+    cudaDeviceSynchronize();
+    std::map<std::string, std::pair<int, double>> agg;
+    std::vector<std::string> order;
+    for (auto &sp : kspans()) {
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, sp.a, sp.b) == cudaSuccess) {
+            if (!agg.count(sp.name)) order.push_back(sp.name);
+            agg[sp.name].first++;
+            agg[sp.name].second += ms;
+        }
+        cudaEventDestroy(sp.a);
+        cudaEventDestroy(sp.b);
+    }
+    kspans().clear();
+    (void)cudaGetLastError();
+    int off = 0;
+    buf[0] = 0;
+    for (auto &n : order) {
+        int w = snprintf(buf + off, (size_t)(len - off), "%s %d %.6f\n", n.c_str(), agg[n].first, agg[n].second);
+        if (w < 0 || w >= len - off) break;
+        off += w;
+    }
+    return CGPU_OK;
+}
+
+int cgpu_matrix_info(const cgpu_matrix *mm, int *K, int *n, int *NP, int *slices, int *frac_bits, long long *mpad) {
+    const DevMatrix *m = reinterpret_cast<const DevMatrix *>(mm);
+    if (!m) return CGPU_EINVAL;
+    if (K) *K = m->K;
+    if (n) *n = m->n;
+    if (NP) *NP = m->NP;
+    if (slices) *slices = m->fxS;
+    if (frac_bits) *frac_bits = m->fxF;
+    if (mpad) *mpad = (long long)m->fxMpad;
     return CGPU_OK;
 }
 
@@ -1088,7 +1164,7 @@ int cgpu_resample_counts(int n, int S, const int *bn, const int *bb, unsigned lo
         CGPU_TRY(launch_mt_draw_range(plan, lo, hi, (uint32_t)n, ws.d_idx, st));
         CGPU_TRY(launch_hist_from_idx(ws.d_idx, n, NP, bn[s], nb, ws.d_counts[0], ws.d_err, st));
     } else if (rng_mode == CGPU_RNG_PHILOX) {
-        CGPU_TRY(launch_hist_philox((unsigned long long)seed, s, b0, n, NP, bn[s], nb, ws.d_counts[0], ws.d_err, st));
+        CGPU_TRY(launch_hist_philox((unsigned long long)seed, s, b0, n, NP, bn[s], nb, ws.d_counts[0], ws.d_err, st, false, stream_offset));
     } else {
         set_error(CGPU_EINVAL, "unknown rng_mode %d", rng_mode);
         return CGPU_EINVAL;

@@ -84,7 +84,7 @@ struct Globals {
     void *scratch[4] = {nullptr, nullptr, nullptr, nullptr};
     size_t scratch_cap[4] = {0, 0, 0, 0};
     // tuning switches (cgpu_set_option); -1 = built-in default
-    int opt_overlap = -1, opt_hist_algo = -1, opt_contract_algo = -1, opt_i8_oneshot = -1, opt_draw_nch = -1, opt_chunk_log2 = -1, opt_i8_fuse = -1, opt_draw_fuse = -1, opt_stage = -1, opt_i8_dbg = -1, opt_mc_smooth = -1, opt_chunk_fill = -1;
+    int opt_overlap = -1, opt_hist_algo = -1, opt_contract_algo = -1, opt_i8_oneshot = -1, opt_draw_nch = -1, opt_chunk_log2 = -1, opt_i8_fuse = -1, opt_draw_fuse = -1, opt_stage = -1, opt_i8_dbg = -1, opt_mc_smooth = -1, opt_chunk_fill = -1, opt_ktime = -1, opt_hist_wide = -1;
 };
 Globals &G();
 int ensure_init();
@@ -187,7 +187,8 @@ int launch_mt_draw_range(const MtPlan &mt, unsigned long long lo, unsigned long 
 int launch_hist_from_idx(const void *d_idx, int n, int NP, int bn, int nb,
                          unsigned long long *d_counts, int *d_err, cudaStream_t st, bool rows = false);
 int launch_hist_philox(unsigned long long seed, int scale, int b_first, int n, int NP, int bn, int nb,
-                       unsigned long long *d_counts, int *d_err, cudaStream_t st, bool rows = false);
+                       unsigned long long *d_counts, int *d_err, cudaStream_t st, bool rows = false,
+                       unsigned long long stream_offset = 0);
 int launch_counts_unpack(const unsigned long long *d_counts, int n, int NP, int nb,
                          unsigned char *d_out, cudaStream_t st);
 // contract_kernels.cu
@@ -222,6 +223,26 @@ struct PhaseTimer {
     void finish(double *ms);  // call after the streams have been synchronised
 };
 
+// comm.cu: the library's NCCL communicator (one process per GPU); every helper degenerates to a
+// local copy when no communicator exists
+int comm_world();
+int comm_rank();
+int comm_group_start();
+int comm_group_end();
+int comm_allgather_f64(const double *send, double *recv, size_t count_per_rank, cudaStream_t st);
+int comm_allreduce_f64(const double *send, double *recv, size_t count, int op /*0 sum, 1 max, 2 min*/, cudaStream_t st);
+int comm_reduce_scatter_f64(const double *send, double *recv, size_t recvcount, int op, cudaStream_t st);
+
+// Per-kernel device times of the consel side (cgpu_set_option("ktime", 1); read and cleared by
+// cgpu_kernel_times): a launcher brackets its launch with a KT object.  Off by default: no
+// events are created and nothing is recorded.
+struct KT {
+    int slot = -1;
+    cudaStream_t st;
+    KT(const char *name, cudaStream_t s);
+    ~KT();
+};
+
 // stats_kernels.cu
 // Row definitions for the row-summary kernel:
 //  mode 0: plain row            v = x[row*ld + b]
@@ -239,6 +260,8 @@ int launch_rowsum(int mode, const RowSrc &src, int rows, int B, int nq, const do
 int launch_rowsum_all_scales(const double *const *d_stat, const int *B, int S, int cm, int nq, const double *d_thr,
                              cgpu_rowsum *d_part, cgpu_rowsum *d_out, int nsplit, cudaStream_t st, bool edges = true,
                              int row0 = 0 /* cm = number of rows queried, starting at this row of the blocks */);
+int launch_rowsum_planes(const cgpu_rowsum *d_q, size_t n, size_t padded, double *d_planes, cudaStream_t st);
+int launch_rowsum_edges(const cgpu_rowsum *d_q, size_t nrs, int nq, double *d_edges, cudaStream_t st);
 int launch_order_stat(const double *d_stat, int rows, int B, int ld, const int *d_rank, double *d_val, cudaStream_t st);
 int launch_col_top2(const double *x, int K, int B, int ld, double *m1, double *m2, int *a1, cudaStream_t st);
 int launch_stat_build(const double *x, int K, int B, int ld, const double *m1, const double *m2, const int *a1,
@@ -246,7 +269,10 @@ int launch_stat_build(const double *x, int K, int B, int ld, const double *m1, c
 // xc = x - rowmean (rescale == false) or rs*(x - rowmean) + rowmean (consel -f); rowmean = sequential sum / B
 int launch_center(const double *x, int K, int B, int ld, double *xc, cudaStream_t st, bool rescale = false,
                   double rs = 1.0);
-int launch_pair_weight(const double *xc, int K, int B, int ld, double varadd, double *wt, int *nsmall, cudaStream_t st);
+int launch_pair_weight(const double *xc, int K, int B, int ld, double varadd, double *wt, int *nsmall, cudaStream_t st,
+                       const int *d_rows = nullptr /* only these weight rows (device list) */, int nrows = 0);
+int launch_wsh_single(const double *x, int K, int B, int ld, const double *wt, const int *mem_tree, int nmem, double *out,
+                      cudaStream_t st);
 int launch_sh_rows(bool weighted, const double *x, int K, int B, int ld, const double *wt, int nmem,
                    const int *mem_item, const int *mem_tree, const int *cass_ptr, const int *cass_idx, double *out,
                    cudaStream_t st);

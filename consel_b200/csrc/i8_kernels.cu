@@ -518,6 +518,76 @@ gemm_i8_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * G8_BN) : "memory");
 }
 
+// ------------------------------------------------------------------ measured int8 tensor peak
+// The bare issue rate of tcgen05.mma kind::i8 (M=128, N=256, K=32 per instruction) from operands
+// that already sit in shared memory: no TMA, no epilogue, two accumulator stages alternating like
+// the GEMM above.  One CTA per SM; `iters` k-blocks of four instructions each.  This is the
+// roofline denominator bench.py grades gemm_i8_persistent_kernel against (MEASURED_PEAKS.json
+// carries bf16 only).
+__global__ void __launch_bounds__(64, 1) i8_peak_kernel(int iters) {
+    extern __shared__ unsigned char g8_raw[];
+    unsigned char *base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(g8_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char *sA = base, *sB = base + 2 * G8_A_BYTES;
+    uint64_t *done = reinterpret_cast<uint64_t *>(base + 2 * (G8_A_BYTES + G8_B_BYTES));
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(done + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (size_t i = threadIdx.x; i < 2 * (G8_A_BYTES + G8_B_BYTES) / 16; i += blockDim.x)
+        reinterpret_cast<uint4 *>(base)[i] = make_uint4(0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u);
+    if (threadIdx.x == 0) {
+        mb_init(done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the MMA's async proxy
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s2u(tmem_slot)), "n"(2 * G8_BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
+    if (warp == 1 && lane == 0) {
+        const uint32_t idesc = (2u << 4) | (1u << 7) | (0u << 10) | ((uint32_t)(G8_BN >> 3) << 17) | ((uint32_t)(G8_BM >> 4) << 24);
+        for (int it = 0; it < iters; it++) {
+            const int s = it & 1;  // two operand stages and two accumulators, like the pipelined kernel
+            const uint64_t ad = umma_desc_sw128(sA + s * G8_A_BYTES), bd = umma_desc_sw128(sB + s * G8_B_BYTES);
+            const uint32_t d_tmem = tmem + (uint32_t)(((it >> 5) & 1) * G8_BN);
+#pragma unroll
+            for (int k = 0; k < G8_BK / 32; k++) umma_i8(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (it & 31) | k ? 1u : 0u);
+        }
+        umma_commit(done);
+        mb_wait(done, 0);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * G8_BN) : "memory");
+}
+
+int bench_i8_peak(double *tops, cudaStream_t st) {
+    const size_t smem = 2 * (G8_A_BYTES + G8_B_BYTES) + 1024 + 64;
+    CGPU_CUDA(cudaFuncSetAttribute(i8_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int sms = G().sm_count > 0 ? G().sm_count : 148;
+    const int iters = 1 << 15;  // 32768 k-blocks of 128x256x128: ~2.5 ms at the datasheet rate
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+        cudaEventRecord(a, st);
+        i8_peak_kernel<<<sms, 64, smem, st>>>(iters);
+        cudaEventRecord(b, st);
+        cudaEventSynchronize(b);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, a, b);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    CGPU_LAUNCH_CHECK();
+    *tops = 2.0 * G8_BM * G8_BN * G8_BK * (double)iters * sms / (best * 1e-3) / 1e12;
+    return CGPU_OK;
+}
+
 // ------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,

@@ -100,7 +100,7 @@ template <int SRC, int HALGO, bool ROWS, int RPC>
 __global__ void __launch_bounds__(HIST_THREADS)
 hist_group_kernel(const void *__restrict__ idx_v, int n, int NP, int bn, int nb,
                   unsigned long long *__restrict__ counts, int *__restrict__ err,
-                  uint32_t key0, uint32_t key1, uint32_t scale, uint32_t b_first) {
+                  uint32_t key0, uint32_t key1, uint32_t scale, uint32_t b_first, uint32_t ctr3) {
     extern __shared__ unsigned char hsm[];  // RPC histograms of NP bytes (+ 8 tag arrays for HALGO 2)
     static_assert(RPC == 8 || (ROWS && HALGO == 1), "shared histograms need the atomic update and the row layout");
     constexpr int WPR = 8 / RPC;  // warps per replicate
@@ -161,11 +161,11 @@ hist_group_kernel(const void *__restrict__ idx_v, int n, int NP, int bn, int nb,
                     }
                 }
             } else {
-                // draw i of replicate b is word (i & 3) of Philox(counter = (i >> 2, b, scale, 0))
+                // draw i of replicate b is word (i & 3) of Philox(counter = (i >> 2, b, scale, stream id))
                 const uint32_t b = b_first + (uint32_t)r;
                 for (int i0 = sub * 128; i0 < bn; i0 += WPR * 128) {
                     int q = (i0 >> 2) + lane;
-                    Philox4 p = philox4x32_10((uint32_t)q, b, scale, 0u, key0, key1);
+                    Philox4 p = philox4x32_10((uint32_t)q, b, scale, ctr3, key0, key1);
 #pragma unroll
                     for (int u = 0; u < 4; u++) {
                         bool valid = q * 4 + u < bn;
@@ -228,7 +228,7 @@ template <int SRC, bool ROWS>
 __global__ void __launch_bounds__(256)
 hist_global_kernel(const void *__restrict__ idx_v, int n, int NP, int bn, int nb,
                    unsigned int *__restrict__ counts32, uint32_t key0, uint32_t key1, uint32_t scale,
-                   uint32_t b_first) {
+                   uint32_t b_first, uint32_t ctr3) {
     const unsigned long long total = SRC != 1 ? (unsigned long long)nb * bn
                                               : (unsigned long long)nb * ((bn + 3) / 4);
     for (unsigned long long d = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; d < total;
@@ -245,7 +245,7 @@ hist_global_kernel(const void *__restrict__ idx_v, int n, int NP, int bn, int nb
         } else {
             uint32_t qn = (uint32_t)((bn + 3) / 4);
             uint32_t r = (uint32_t)(d / qn), q = (uint32_t)(d % qn);
-            Philox4 p = philox4x32_10(q, b_first + r, scale, 0u, key0, key1);
+            Philox4 p = philox4x32_10(q, b_first + r, scale, ctr3, key0, key1);
 #pragma unroll
             for (int u = 0; u < 4; u++) {
                 if ((int)(q * 4 + u) < bn) {
@@ -262,6 +262,114 @@ hist_global_kernel(const void *__restrict__ idx_v, int n, int NP, int bn, int nb
     }
 }
 
+// Long alignments, byte rows: ONE replicate per CTA and TH/32 warps on its single shared
+// histogram.  The shared-memory footprint is the histogram alone (NP bytes), so an SM holds
+// floor(220 KB / NP) CTAs and the warp count per SM stays at 32-64 whatever the site count is
+// (n = 100000: two CTAs of 32 warps; the 8-warp CTAs of hist_group_kernel leave 8 warps per SM
+// there, and the kernel is bound by the latency of the index loads and the shared atomics).
+// Every warp owns a contiguous segment of the replicate's draws and reads it with 16-byte loads,
+// the next one in flight while the current indices are counted.
+template <int SRC, int TH>
+__global__ void __launch_bounds__(TH)
+hist_wide_kernel(const void *__restrict__ idx_v, int n, int NP, int bn, int nb, unsigned char *__restrict__ rows,
+                 int *__restrict__ err, uint32_t key0, uint32_t key1, uint32_t scale, uint32_t b_first, uint32_t ctr3) {
+    extern __shared__ __align__(16) unsigned char hsm[];
+    __shared__ unsigned int s_sum[TH / 32];
+    constexpr int NW = TH / 32;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    unsigned *h32 = reinterpret_cast<unsigned *>(hsm);
+    auto add = [&](uint32_t k) { atomicAdd(h32 + (k >> 2), 1u << ((k & 3u) * 8u)); };
+    for (int r = blockIdx.x; r < nb; r += gridDim.x) {
+        for (int i = tid; i < NP / 16; i += TH) reinterpret_cast<uint4 *>(hsm)[i] = make_uint4(0, 0, 0, 0);
+        __syncthreads();
+        if (SRC == 1) {
+            const uint32_t b = b_first + (uint32_t)r;
+            const int nquad = (bn + 3) >> 2;
+            for (int q = tid; q < nquad; q += TH) {
+                Philox4 p = philox4x32_10((uint32_t)q, b, scale, ctr3, key0, key1);
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    if (q * 4 + u < bn) add(__umulhi(p.v[u], (uint32_t)n));
+            }
+        } else {
+            constexpr int PER = SRC == 2 ? 8 : 4;  // indices per 16-byte load
+            const uint16_t *src16 = static_cast<const uint16_t *>(idx_v) + (size_t)r * bn;
+            const uint32_t *src32 = static_cast<const uint32_t *>(idx_v) + (size_t)r * bn;
+            auto at = [&](int i) -> uint32_t { return SRC == 2 ? (uint32_t)src16[i] : src32[i]; };
+            const uintptr_t base = SRC == 2 ? reinterpret_cast<uintptr_t>(src16) : reinterpret_cast<uintptr_t>(src32);
+            const int seg = (bn + NW - 1) / NW;
+            int i = wid * seg;
+            const int hi = min(bn, i + seg);
+            if (i < hi) {
+                const int esz = SRC == 2 ? 2 : 4;
+                const int head = min(hi - i, (int)(((16 - ((base + (size_t)i * esz) & 15)) & 15) / esz));
+                if (lane < head) add(at(i + lane));
+                i += head;
+                constexpr int STEP = 32 * PER;
+                if (i + STEP <= hi) {
+                    const uint4 *p4 = reinterpret_cast<const uint4 *>(base + (size_t)i * esz);
+                    uint4 v = __ldg(p4 + lane);
+                    for (; i + STEP <= hi; i += STEP, p4 += 32) {
+                        uint4 nx = v;
+                        if (i + 2 * STEP <= hi) nx = __ldg(p4 + 32 + lane);
+                        if (SRC == 2) {
+                            add(v.x & 0xffffu); add(v.x >> 16);
+                            add(v.y & 0xffffu); add(v.y >> 16);
+                            add(v.z & 0xffffu); add(v.z >> 16);
+                            add(v.w & 0xffffu); add(v.w >> 16);
+                        } else {
+                            add(v.x); add(v.y); add(v.z); add(v.w);
+                        }
+                        v = nx;
+                    }
+                }
+                for (int j = i + lane; j < hi; j += 32) add(at(j));
+            }
+        }
+        __syncthreads();
+        // checksum (a byte that wrapped past 255 changes the sum) while the row is copied out
+        unsigned int sum = 0;
+        uint4 *dst4 = reinterpret_cast<uint4 *>(rows + (size_t)r * NP);
+        for (int i = tid; i < NP / 16; i += TH) {
+            const uint4 v = reinterpret_cast<const uint4 *>(hsm)[i];
+            sum = __dp4a(v.x, 0x01010101u, sum);
+            sum = __dp4a(v.y, 0x01010101u, sum);
+            sum = __dp4a(v.z, 0x01010101u, sum);
+            sum = __dp4a(v.w, 0x01010101u, sum);
+            dst4[i] = v;
+        }
+#pragma unroll
+        for (int off = 16; off; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+        if (lane == 0) s_sum[wid] = sum;
+        __syncthreads();
+        if (tid == 0) {
+            unsigned int tot = 0;
+            for (int w = 0; w < NW; w++) tot += s_sum[w];
+            if (tot != (unsigned int)bn) atomicExch(err, 1);
+        }
+        // (the next iteration's zeroing is ordered behind the copy by the barrier above; s_sum is
+        // rewritten only after the next two barriers)
+    }
+}
+
+template <int SRC, int TH>
+static int hist_wide_launch(const void *d_idx, int n, int NP, int bn, int nb, unsigned long long *d_counts, int *d_err,
+                            uint32_t k0, uint32_t k1, uint32_t scale, uint32_t b_first, uint32_t ctr3, cudaStream_t st) {
+    auto kern = hist_wide_kernel<SRC, TH>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        CGPU_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * HIST_SMEM_SITES));
+        attr_done = true;
+    }
+    const int sms = G().sm_count > 0 ? G().sm_count : 148;
+    const int per_sm = std::max(1, std::min(2048 / TH, (int)((size_t)(224 * 1024) / ((size_t)NP + 1024))));
+    const int grid = std::min(nb, sms * per_sm);
+    kern<<<grid, TH, (size_t)NP, st>>>(d_idx, n, NP, bn, nb, reinterpret_cast<unsigned char *>(d_counts), d_err, k0, k1, scale,
+                                       b_first, ctr3);
+    CGPU_LAUNCH_CHECK();
+    return CGPU_OK;
+}
+
 // CGPU_HIST_ALGO selects the in-warp conflict scheme (development A/B switch)
 static int hist_algo() {
     static int v = [] {
@@ -273,7 +381,7 @@ static int hist_algo() {
 
 template <int SRC, int HALGO, bool ROWS, int RPC = 8>
 static int hist_group_launch(const void *d_idx, int n, int NP, int bn, int nb, unsigned long long *d_counts,
-                             int *d_err, uint32_t k0, uint32_t k1, uint32_t scale, uint32_t b_first, cudaStream_t st) {
+                             int *d_err, uint32_t k0, uint32_t k1, uint32_t scale, uint32_t b_first, uint32_t ctr3, cudaStream_t st) {
     auto kern = hist_group_kernel<SRC, HALGO, ROWS, RPC>;
     static bool attr_done = false;
     if (!attr_done) {
@@ -286,23 +394,33 @@ static int hist_group_launch(const void *d_idx, int n, int NP, int bn, int nb, u
     int per_sm = (int)std::min<size_t>(8, (220 * 1024) / smem);
     if (per_sm < 1) per_sm = 1;
     const int grid = std::min(ngroups, sms * per_sm);
-    kern<<<grid, HIST_THREADS, smem, st>>>(d_idx, n, NP, bn, nb, d_counts, d_err, k0, k1, scale, b_first);
+    kern<<<grid, HIST_THREADS, smem, st>>>(d_idx, n, NP, bn, nb, d_counts, d_err, k0, k1, scale, b_first, ctr3);
     CGPU_LAUNCH_CHECK();
     return CGPU_OK;
 }
 
 static int hist_dispatch(int src, const void *d_idx, int n, int NP, int bn, int nb,
                          unsigned long long *d_counts, int *d_err, uint32_t k0, uint32_t k1, uint32_t scale,
-                         uint32_t b_first, cudaStream_t st, bool rows) {
+                         uint32_t b_first, uint32_t ctr3, cudaStream_t st, bool rows) {
     if (nb <= 0) return CGPU_OK;
     const int ngroups = (nb + 7) / 8;
     int algo = hist_algo();
     if (algo == 2 && 2 * NP > HIST_SMEM_SITES) algo = 0;  // tag arrays double the footprint
+    if (rows && algo == 1 && NP > HIST_SMEM_SITES / 2 && NP <= 8 * HIST_SMEM_SITES && G().opt_hist_wide != 0) {
+        // 16 warps per replicate while four or more histograms fit an SM, 32 warps above that
+        const bool th512 = (size_t)4 * ((size_t)NP + 1024) <= (size_t)224 * 1024;
+#define CGPU_HISTWIDE_CASE(S)                                                                                              \
+    if (src == S)                                                                                                          \
+        return th512 ? hist_wide_launch<S, 512>(d_idx, n, NP, bn, nb, d_counts, d_err, k0, k1, scale, b_first, ctr3, st)    \
+                     : hist_wide_launch<S, 1024>(d_idx, n, NP, bn, nb, d_counts, d_err, k0, k1, scale, b_first, ctr3, st);
+        CGPU_HISTWIDE_CASE(0) CGPU_HISTWIDE_CASE(1) CGPU_HISTWIDE_CASE(2)
+#undef CGPU_HISTWIDE_CASE
+    }
     if (NP <= HIST_SMEM_SITES) {
 #define CGPU_HIST_CASE(S, A)                                                                                     \
     if (src == S && algo == A)                                                                                    \
-        return rows ? hist_group_launch<S, A, true>(d_idx, n, NP, bn, nb, d_counts, d_err, k0, k1, scale, b_first, st) \
-                    : hist_group_launch<S, A, false>(d_idx, n, NP, bn, nb, d_counts, d_err, k0, k1, scale, b_first, st);
+        return rows ? hist_group_launch<S, A, true>(d_idx, n, NP, bn, nb, d_counts, d_err, k0, k1, scale, b_first, ctr3, st) \
+                    : hist_group_launch<S, A, false>(d_idx, n, NP, bn, nb, d_counts, d_err, k0, k1, scale, b_first, ctr3, st);
         CGPU_HIST_CASE(0, 0) CGPU_HIST_CASE(0, 1) CGPU_HIST_CASE(0, 2)
         CGPU_HIST_CASE(1, 0) CGPU_HIST_CASE(1, 1) CGPU_HIST_CASE(1, 2)
         CGPU_HIST_CASE(2, 0) CGPU_HIST_CASE(2, 1) CGPU_HIST_CASE(2, 2)
@@ -313,9 +431,9 @@ static int hist_dispatch(int src, const void *d_idx, int n, int NP, int bn, int 
         // byte rows of a long alignment: 4, 2 or 1 replicates per CTA share the 8 warps
 #define CGPU_HISTW_CASE(S)                                                                                               \
     if (src == S) {                                                                                                       \
-        if (NP <= 2 * HIST_SMEM_SITES) return hist_group_launch<S, 1, true, 4>(d_idx, n, NP, bn, nb, d_counts, d_err, k0, k1, scale, b_first, st); \
-        if (NP <= 4 * HIST_SMEM_SITES) return hist_group_launch<S, 1, true, 2>(d_idx, n, NP, bn, nb, d_counts, d_err, k0, k1, scale, b_first, st); \
-        return hist_group_launch<S, 1, true, 1>(d_idx, n, NP, bn, nb, d_counts, d_err, k0, k1, scale, b_first, st);      \
+        if (NP <= 2 * HIST_SMEM_SITES) return hist_group_launch<S, 1, true, 4>(d_idx, n, NP, bn, nb, d_counts, d_err, k0, k1, scale, b_first, ctr3, st); \
+        if (NP <= 4 * HIST_SMEM_SITES) return hist_group_launch<S, 1, true, 2>(d_idx, n, NP, bn, nb, d_counts, d_err, k0, k1, scale, b_first, ctr3, st); \
+        return hist_group_launch<S, 1, true, 1>(d_idx, n, NP, bn, nb, d_counts, d_err, k0, k1, scale, b_first, ctr3, st);      \
     }
         CGPU_HISTW_CASE(0) CGPU_HISTW_CASE(1) CGPU_HISTW_CASE(2)
 #undef CGPU_HISTW_CASE
@@ -328,7 +446,7 @@ static int hist_dispatch(int src, const void *d_idx, int n, int NP, int bn, int 
         unsigned int *c32 = reinterpret_cast<unsigned int *>(d_counts);
 #define CGPU_HISTG_CASE(S, R)                                                                                 \
     if (src == S && rows == R)                                                                                 \
-        hist_global_kernel<S, R><<<grid, 256, 0, st>>>(d_idx, n, NP, bn, nb, c32, k0, k1, scale, b_first);
+        hist_global_kernel<S, R><<<grid, 256, 0, st>>>(d_idx, n, NP, bn, nb, c32, k0, k1, scale, b_first, ctr3);
         CGPU_HISTG_CASE(0, false) CGPU_HISTG_CASE(0, true) CGPU_HISTG_CASE(1, false) CGPU_HISTG_CASE(1, true)
         CGPU_HISTG_CASE(2, false) CGPU_HISTG_CASE(2, true)
 #undef CGPU_HISTG_CASE
@@ -339,13 +457,25 @@ static int hist_dispatch(int src, const void *d_idx, int n, int NP, int bn, int 
 
 int launch_hist_from_idx(const void *d_idx, int n, int NP, int bn, int nb,
                          unsigned long long *d_counts, int *d_err, cudaStream_t st, bool rows) {
-    return hist_dispatch(idx_is16((uint32_t)n) ? 2 : 0, d_idx, n, NP, bn, nb, d_counts, d_err, 0, 0, 0, 0, st, rows);
+    return hist_dispatch(idx_is16((uint32_t)n) ? 2 : 0, d_idx, n, NP, bn, nb, d_counts, d_err, 0, 0, 0, 0, 0, st, rows);
 }
 
 int launch_hist_philox(unsigned long long seed, int scale, int b_first, int n, int NP, int bn, int nb,
-                       unsigned long long *d_counts, int *d_err, cudaStream_t st, bool rows) {
+                       unsigned long long *d_counts, int *d_err, cudaStream_t st, bool rows, unsigned long long stream_offset) {
+    // The counter-based generator has no stream position; calls that continue one logical stream
+    // (makermt -g: one call per gene file, stream_offset = draws consumed so far) must still draw
+    // independent replicates, so the offset is hashed (splitmix64 finaliser) into the fourth
+    // counter word.  Offset 0 keeps the word 0.
+    unsigned long long z = stream_offset;
+    if (z) {
+        z += 0x9E3779B97F4A7C15ull;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        z ^= z >> 31;
+        z = (z & 0xffffffffull) ? z : 1;
+    }
     return hist_dispatch(1, nullptr, n, NP, bn, nb, d_counts, d_err, (uint32_t)seed, (uint32_t)(seed >> 32),
-                         (uint32_t)scale, (uint32_t)b_first, st, rows);
+                         (uint32_t)scale, (uint32_t)b_first, (uint32_t)z, st, rows);
 }
 
 // BJ8 -> plain counts[b*n + j] bytes (test seam: cgpu_resample_counts)

@@ -25,21 +25,58 @@ namespace cgpu {
 // For column b: m1 = max_k x, a1 = first index attaining it, m2 = max_{k != a1} x, all
 // with the reference's -1e30 floor, so max_{j != i} x_j == (i == a1 ? m2 : m1) exactly
 // as the prefix/suffix scan of calcmaxs (src/consel.c:1894-1916) yields it.
+// The K rows are cut into `ks` ranges (grid.y) so that a block of few replicates (B = 10^4 gives
+// only 79 column tiles) still fills the SMs; every thread keeps four row loads in flight.  The
+// partial triples are merged in row order by col_top2_merge_kernel, which keeps the "first index
+// attaining the maximum" rule of the sequential scan (a later range only wins with v > m1).
 __global__ void __launch_bounds__(128)
-col_top2_kernel(const double *__restrict__ x, int K, int B, int ld, double *__restrict__ m1o,
+col_top2_kernel(const double *__restrict__ x, int K, int B, int ld, int rows_per, double *__restrict__ m1o,
                 double *__restrict__ m2o, int *__restrict__ a1o) {
-    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
+    const int k0 = blockIdx.y * rows_per, k1 = min(K, k0 + rows_per);
     double m1 = -CG_HUGE, m2 = -CG_HUGE;
     int a1 = -1;
-    for (int k = 0; k < K; k++) {
-        double v = x[(size_t)k * ld + b];
+    auto take = [&](double v, int k) {
         if (v > m1) {
             m2 = m1;
             m1 = v;
             a1 = k;
         } else if (v > m2) {
             m2 = v;
+        }
+    };
+    int k = k0;
+    for (; k + 4 <= k1; k += 4) {
+        const double v0 = x[(size_t)k * ld + b], v1 = x[(size_t)(k + 1) * ld + b];
+        const double v2 = x[(size_t)(k + 2) * ld + b], v3 = x[(size_t)(k + 3) * ld + b];
+        take(v0, k);
+        take(v1, k + 1);
+        take(v2, k + 2);
+        take(v3, k + 3);
+    }
+    for (; k < k1; k++) take(x[(size_t)k * ld + b], k);
+    const size_t o = (size_t)blockIdx.y * B + b;
+    m1o[o] = m1;
+    m2o[o] = m2;
+    a1o[o] = a1;
+}
+
+__global__ void __launch_bounds__(128)
+col_top2_merge_kernel(const double *__restrict__ pm1, const double *__restrict__ pm2, const int *__restrict__ pa1, int ks,
+                      int B, double *__restrict__ m1o, double *__restrict__ m2o, int *__restrict__ a1o) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double m1 = pm1[b], m2 = pm2[b];
+    int a1 = pa1[b];
+    for (int p = 1; p < ks; p++) {
+        const double q1 = pm1[(size_t)p * B + b], q2 = pm2[(size_t)p * B + b];
+        if (q1 > m1) {  // strictly greater: an equal maximum in a later range keeps the earlier index
+            m2 = m1 > q2 ? m1 : q2;
+            m1 = q1;
+            a1 = pa1[(size_t)p * B + b];
+        } else {
+            m2 = m2 > q1 ? m2 : q1;
         }
     }
     m1o[b] = m1;
@@ -441,6 +478,46 @@ rowsum_merge_kernel(const cgpu_rowsum *__restrict__ part, int total, int nsplit,
     out[e] = r;
 }
 
+// row summaries -> three planar arrays (count | lo | hi) of `padded` entries each, the layout the
+// NCCL reductions (sum | max | min) of a sharded count query want; padding entries are neutral
+__global__ void __launch_bounds__(256)
+rowsum_planes_kernel(const cgpu_rowsum *__restrict__ q, size_t n, size_t padded, double *__restrict__ planes) {
+    const size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (e >= padded) return;
+    double c = 0.0, lo = -CG_HUGE, hi = CG_HUGE;
+    if (e < n) {
+        c = q[e].cnt;
+        lo = q[e].lo;
+        hi = q[e].hi;
+    }
+    planes[e] = c;
+    planes[padded + e] = lo;
+    planes[2 * padded + e] = hi;
+}
+// (min1, min2, max1, max2) of every (row, scale), taken from the first threshold's summary
+__global__ void __launch_bounds__(256)
+rowsum_edges_kernel(const cgpu_rowsum *__restrict__ q, size_t nrs, int nq, double *__restrict__ edges) {
+    const size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (e >= nrs) return;
+    const cgpu_rowsum r = q[e * nq];
+    edges[4 * e] = r.min1;
+    edges[4 * e + 1] = r.min2;
+    edges[4 * e + 2] = r.max1;
+    edges[4 * e + 3] = r.max2;
+}
+int launch_rowsum_planes(const cgpu_rowsum *d_q, size_t n, size_t padded, double *d_planes, cudaStream_t st) {
+    if (padded == 0) return CGPU_OK;
+    rowsum_planes_kernel<<<(unsigned)((padded + 255) / 256), 256, 0, st>>>(d_q, n, padded, d_planes);
+    CGPU_LAUNCH_CHECK();
+    return CGPU_OK;
+}
+int launch_rowsum_edges(const cgpu_rowsum *d_q, size_t nrs, int nq, double *d_edges, cudaStream_t st) {
+    if (nrs == 0) return CGPU_OK;
+    rowsum_edges_kernel<<<(unsigned)((nrs + 255) / 256), 256, 0, st>>>(d_q, nrs, nq, d_edges);
+    CGPU_LAUNCH_CHECK();
+    return CGPU_OK;
+}
+
 static size_t rss_smem(int nq) { return (size_t)(nq + 1) * RS_THREADS * (8 + 8 + 4); }
 
 int launch_rowsum_all_scales(const double *const *d_stat, const int *B, int S, int cm, int nq, const double *d_thr,
@@ -456,6 +533,7 @@ int launch_rowsum_all_scales(const double *const *d_stat, const int *B, int S, i
         sl.B[s] = B[s];
     }
     const dim3 grid(cm, S, nsplit);
+    KT kt(nq == 1 ? "rowsum_multi_kernel<1>" : "rowsum_multi/sorted_kernel", st);
     // more than 8 thresholds per row: two passes of <= 8 (64 registers, 3 CTAs/SM) stream faster
     // than one pass of 16 (204 registers)
 #define CGPU_RSM(NQ_)                                                                                                     \
@@ -487,6 +565,7 @@ int launch_rowsum(int mode, const RowSrc &src, int rows, int B, int nq, const do
         set_error(CGPU_EINVAL, "nq=%d (1..%d)", nq, RS_MAXQ);
         return CGPU_EINVAL;
     }
+    KT kt(mode == 0 ? "rowsum_kernel<plain>" : mode == 1 ? "rowsum_kernel<kh>" : "rowsum_kernel<sh>", st);
     if (mode == 0) rowsum_kernel<0><<<rows, RS_THREADS, 0, st>>>(src, B, nq, d_thr, d_out, out_stride, out_off);
     else if (mode == 1) rowsum_kernel<1><<<rows, RS_THREADS, 0, st>>>(src, B, nq, d_thr, d_out, out_stride, out_off);
     else rowsum_kernel<2><<<rows, RS_THREADS, 0, st>>>(src, B, nq, d_thr, d_out, out_stride, out_off);
@@ -495,8 +574,7 @@ int launch_rowsum(int mode, const RowSrc &src, int rows, int B, int nq, const do
 }
 
 // ------------------------------------------------------------------ order statistic
-// k-th smallest (0-based) of each row by bisection on the bits of the order-preserving
-// integer image of a double: 64 counting passes over a row that stays in L1/L2.
+// k-th smallest (0-based) of each row on the order-preserving integer image of a double.
 __device__ __forceinline__ unsigned long long dkey(double v) {
     unsigned long long u = (unsigned long long)__double_as_longlong(v);
     return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
@@ -506,37 +584,52 @@ __device__ __forceinline__ double dunkey(unsigned long long k) {
     return __longlong_as_double((long long)u);
 }
 
+// Radix select, most significant byte first: eight passes, each a 256-bin shared-memory
+// histogram of the current byte over the elements that match the prefix found so far, then a
+// scan of the bins for the one that holds rank k (rows stay in L1/L2 between the passes).
 __global__ void __launch_bounds__(256)
 order_stat_kernel(const double *__restrict__ stat, int B, int ld, const int *__restrict__ rank,
                   double *__restrict__ val) {
     const int row = blockIdx.x, tid = threadIdx.x;
     const double *v = stat + (size_t)row * ld;
-    const unsigned int k = (unsigned int)rank[row];
-    __shared__ unsigned int s_cnt[8];
-    __shared__ unsigned long long s_res;
-    if (tid == 0) s_res = 0;
-    __syncthreads();
-    for (int bit = 63; bit >= 0; bit--) {
-        const unsigned long long cand = s_res | (1ull << bit);
-        unsigned int c = 0;
-        for (int b = tid; b < B; b += 256) c += dkey(v[b]) < cand;
-#pragma unroll
-        for (int off = 16; off; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
-        if ((tid & 31) == 0) s_cnt[tid >> 5] = c;
+    __shared__ unsigned int s_hist[256];
+    __shared__ unsigned long long s_prefix;
+    __shared__ unsigned int s_k;
+    if (tid == 0) {
+        s_prefix = 0;
+        s_k = (unsigned int)rank[row];
+    }
+    for (int pass = 0; pass < 8; pass++) {
+        const int shift = 56 - 8 * pass;
+        s_hist[tid] = 0;
+        __syncthreads();
+        const unsigned long long prefix = s_prefix;
+        const unsigned long long mask = pass == 0 ? 0ull : (~0ull << (shift + 8));
+        for (int b = tid; b < B; b += 256) {
+            const unsigned long long key = dkey(v[b]);
+            if ((key & mask) == prefix) atomicAdd(&s_hist[(unsigned int)(key >> shift) & 0xffu], 1u);
+        }
         __syncthreads();
         if (tid == 0) {
-            unsigned int tot = 0;
-            for (int w = 0; w < 8; w++) tot += s_cnt[w];
-            if (tot <= k) s_res = cand;
+            unsigned int k = s_k, c = 0;
+            int bin = 0;
+            for (; bin < 255; bin++) {
+                c = s_hist[bin];
+                if (k < c) break;
+                k -= c;
+            }
+            s_k = k;
+            s_prefix = prefix | ((unsigned long long)bin << shift);
         }
         __syncthreads();
     }
-    if (tid == 0) val[row] = dunkey(s_res);
+    if (tid == 0) val[row] = dunkey(s_prefix);
 }
 
 int launch_order_stat(const double *d_stat, int rows, int B, int ld, const int *d_rank, double *d_val,
                       cudaStream_t st) {
     if (rows <= 0) return CGPU_OK;
+    KT kt("order_stat_kernel", st);
     order_stat_kernel<<<rows, 256, 0, st>>>(d_stat, B, ld, d_rank, d_val);
     CGPU_LAUNCH_CHECK();
     return CGPU_OK;
@@ -596,14 +689,24 @@ center_rows_kernel(const double *__restrict__ x, int K, int B, int ld, double *_
 //   wt[i][j] = 1/sqrt((sum_b (x_i - x_j)^2 + varadd)/(B-1)), sum in replicate order.
 // 16x16 pairs per CTA, one pair per thread, replicates staged through shared memory.
 constexpr int PV_T = 16, PV_BC = 64;
+// rows == nullptr: all pairs, lower triangle computed once and mirrored (grid t x t).
+// rows != nullptr: only the weight rows i = rows[0..nrows) against every j (grid t x ceil(nrows/16)):
+// a rank of a sharded run needs the rows of its own members only.  (x_i - x_j)^2 is the same
+// value whichever of the two is "i", so both forms give bit-identical weights.
 __global__ void __launch_bounds__(PV_T * PV_T)
 pair_weight_kernel(const double *__restrict__ xc, int K, int B, int ld, double varadd, double *__restrict__ wt,
-                   int *__restrict__ nsmall) {
+                   int *__restrict__ nsmall, const int *__restrict__ rows, int nrows) {
     const int ti = blockIdx.y, tj = blockIdx.x;
-    if (tj > ti) return;
+    if (!rows && tj > ti) return;
     __shared__ double si[PV_T][PV_BC + 1], sj[PV_T][PV_BC + 1];
-    const int tx = threadIdx.x % PV_T, ty = threadIdx.x / PV_T;  // pair (i = ti*16+ty, j = tj*16+tx)
-    const int i = ti * PV_T + ty, j = tj * PV_T + tx;
+    __shared__ int s_row[PV_T];
+    const int tx = threadIdx.x % PV_T, ty = threadIdx.x / PV_T;  // pair (i = row ty of tile ti, j = tj*16+tx)
+    if (threadIdx.x < PV_T) {
+        const int r = ti * PV_T + threadIdx.x;
+        s_row[threadIdx.x] = rows ? (r < nrows ? rows[r] : -1) : (r < K ? r : -1);
+    }
+    __syncthreads();
+    const int i = s_row[ty], j = tj * PV_T + tx;
     // staging: thread e loads rows r = e/64 (+4, +8, +12) at column e%64 of both tiles; the next
     // chunk is fetched into registers while the current one is consumed from shared memory
     constexpr int PER = PV_T * PV_BC / (PV_T * PV_T);  // 4 elements per thread and tile
@@ -614,8 +717,8 @@ pair_weight_kernel(const double *__restrict__ xc, int K, int B, int ld, double v
         for (int u = 0; u < PER; u++) {
             const int r = lr + u * (PV_T * PV_T / PV_BC);
             const int b = b0 + lc;
-            const int gi = ti * PV_T + r, gj = tj * PV_T + r;
-            ni[u] = (gi < K && b < B) ? xc[(size_t)gi * ld + b] : 0.0;
+            const int gi = s_row[r], gj = tj * PV_T + r;
+            ni[u] = (gi >= 0 && b < B) ? xc[(size_t)gi * ld + b] : 0.0;
             nj[u] = (gj < K && b < B) ? xc[(size_t)gj * ld + b] : 0.0;
         }
     };
@@ -652,13 +755,19 @@ pair_weight_kernel(const double *__restrict__ xc, int K, int B, int ld, double v
         }
         __syncthreads();
     }
-    if (i < K && j < i) {
-        if (acc < varadd * 100.0) atomicAdd(nsmall, 1);  // VARADDWARN, src/consel.c:154,1409
-        double w = __ddiv_rn(1.0, __dsqrt_rn(__ddiv_rn(__dadd_rn(acc, varadd), (double)(B - 1))));
-        wt[(size_t)i * K + j] = w;
-        wt[(size_t)j * K + i] = w;
+    if (i < 0 || j >= K) return;
+    if (i == j) {
+        wt[(size_t)i * K + i] = 0.0;
+        return;
     }
-    if (i < K && i == j) wt[(size_t)i * K + i] = 0.0;
+    if (!rows && j > i) return;
+    // VARADDWARN (src/consel.c:154,1409) counts every pair once: in the row-subset form the pair is
+    // counted by the row with the larger tree index when both rows are present -- the caller only
+    // uses the count on single-device runs
+    if (acc < varadd * 100.0 && (!rows || j < i)) atomicAdd(nsmall, 1);
+    double w = __ddiv_rn(1.0, __dsqrt_rn(__ddiv_rn(__dadd_rn(acc, varadd), (double)(B - 1))));
+    wt[(size_t)i * K + j] = w;
+    if (!rows) wt[(size_t)j * K + i] = w;
 }
 
 // SH statistic rows for general association sets (src/consel.c:2026-2030, 2017-2024):
@@ -693,6 +802,64 @@ sh_rows_kernel(const double *__restrict__ x, int K, int B, int ld, const double 
     }
 }
 
+// Weighted SH rows when every item is a single tree (the default identity association): the
+// complement of member i is "every j != i", so no index list is needed, and a CTA finishes
+// WS_MI members for 128 replicates at once -- x[j][b] is loaded once per j and used by all of its
+// members, the weights wt[i_m][j] of a chunk of j sit in shared memory.  Per (member, j, b) one
+// rounded subtract, one rounded multiply and a compare, exactly the operations (and the ascending
+// j order) of calcmaxass with weights (src/consel.c:2017-2024); the FP64 pipe is the bound.
+constexpr int WS_MI = 8, WS_JC = 128;
+__global__ void __launch_bounds__(128)
+wsh_single_kernel(const double *__restrict__ x, int K, int B, int ld, const double *__restrict__ wt,
+                  const int *__restrict__ mem_tree, int nmem, double *__restrict__ out) {
+    const int b = blockIdx.x * 128 + threadIdx.x;
+    const int q0 = blockIdx.y * WS_MI;
+    __shared__ __align__(16) double s_w[WS_JC][WS_MI];  // the WS_MI weights of one j are contiguous: 128-bit shared loads
+    __shared__ int s_tree[WS_MI];
+    if (threadIdx.x < WS_MI) s_tree[threadIdx.x] = q0 + threadIdx.x < nmem ? mem_tree[q0 + threadIdx.x] : -1;
+    __syncthreads();
+    const bool live = b < B;
+    double x0[WS_MI], mx[WS_MI];
+#pragma unroll
+    for (int m = 0; m < WS_MI; m++) {
+        const int t = s_tree[m];
+        x0[m] = (live && t >= 0) ? x[(size_t)t * ld + b] : 0.0;
+        mx[m] = -CG_HUGE;
+    }
+    for (int j0 = 0; j0 < K; j0 += WS_JC) {
+        const int jn = min(WS_JC, K - j0);
+        __syncthreads();
+        for (int e = threadIdx.x; e < WS_MI * WS_JC; e += 128) {
+            const int m = e / WS_JC, jj = e % WS_JC, t = s_tree[m];
+            // the member's own tree is not in its complement: a NaN weight fails every compare
+            s_w[jj][m] = (t >= 0 && jj < jn && j0 + jj != t) ? wt[(size_t)t * K + j0 + jj] : __longlong_as_double(0x7ff8000000000000ll);
+        }
+        __syncthreads();
+        if (!live) continue;
+        double xn = x[(size_t)j0 * ld + b];
+        for (int jj = 0; jj < jn; jj++) {
+            const double xj = xn;
+            if (jj + 1 < jn) xn = x[(size_t)(j0 + jj + 1) * ld + b];
+            double w[WS_MI];
+#pragma unroll
+            for (int m = 0; m < WS_MI; m += 2) {
+                const double2 w2 = *reinterpret_cast<const double2 *>(&s_w[jj][m]);
+                w[m] = w2.x;
+                w[m + 1] = w2.y;
+            }
+#pragma unroll
+            for (int m = 0; m < WS_MI; m++) {
+                const double y = __dmul_rn(w[m], __dsub_rn(xj, x0[m]));
+                if (y > mx[m]) mx[m] = y;
+            }
+        }
+    }
+    if (!live) return;
+#pragma unroll
+    for (int m = 0; m < WS_MI; m++)
+        if (q0 + m < nmem) out[(size_t)(q0 + m) * ld + b] = mx[m];
+}
+
 // observed statistics and KH contrasts that depend on the weights (src/consel.c:2121-2134,
 // 2017-2024 applied to datvec): one thread per member.
 __global__ void __launch_bounds__(128)
@@ -702,43 +869,92 @@ weighted_obs_kernel(const double *__restrict__ dat, int K, const double *__restr
                     double *__restrict__ obs, int *__restrict__ argj) {
     const int q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nmem) return;
-    const int e = mem_item[q], i = mem_tree[q];
+    const int i = mem_tree[q];
     const double x0 = dat[i];
     const double *wp = wt + (size_t)i * K;
     double mx = -CG_HUGE;
-    int jj = 0;
-    for (int p = cass_ptr[e]; p < cass_ptr[e + 1]; p++) {
-        int j = cass_idx[p];
-        double y = __dmul_rn(wp[j], __dsub_rn(dat[j], x0));
-        if (y > mx) { mx = y; jj = p - cass_ptr[e]; }
+    int jj = -1;
+    if (cass_ptr) {
+        const int e = mem_item[q];
+        jj = cass_idx[cass_ptr[e]];
+        for (int p = cass_ptr[e]; p < cass_ptr[e + 1]; p++) {
+            int j = cass_idx[p];
+            double y = __dmul_rn(wp[j], __dsub_rn(dat[j], x0));
+            if (y > mx) { mx = y; jj = j; }
+        }
+    } else {  // singleton item: the complement is every other tree, ascending
+        jj = i == 0 ? 1 : 0;
+        for (int j = 0; j < K; j++) {
+            if (j == i) continue;
+            double y = __dmul_rn(wp[j], __dsub_rn(dat[j], x0));
+            if (y > mx) { mx = y; jj = j; }
+        }
     }
     obs[q] = mx;
-    argj[q] = jj;
+    argj[q] = jj;  // the TREE that attains the maximum (first one in complement order)
 }
 
 int launch_col_top2(const double *x, int K, int B, int ld, double *m1, double *m2, int *a1, cudaStream_t st) {
     if (B <= 0) return CGPU_OK;
-    col_top2_kernel<<<(B + 127) / 128, 128, 0, st>>>(x, K, B, ld, m1, m2, a1);
-    CGPU_LAUNCH_CHECK();
+    const int tiles = (B + 127) / 128;
+    const int sms = G().sm_count > 0 ? G().sm_count : 148;
+    int ks = std::max(1, std::min({(8 * sms + tiles - 1) / tiles, (K + 15) / 16, 64}));
+    const int rows_per = (K + ks - 1) / ks;
+    ks = (K + rows_per - 1) / rows_per;
+    if (ks == 1) {
+        KT kt("col_top2_kernel", st);
+        col_top2_kernel<<<dim3(tiles, 1), 128, 0, st>>>(x, K, B, ld, rows_per, m1, m2, a1);
+        CGPU_LAUNCH_CHECK();
+        return CGPU_OK;
+    }
+    double *pm = nullptr;
+    int *pa = nullptr;
+    CGPU_CUDA(dev_alloc(&pm, (size_t)2 * ks * B * sizeof(double)));
+    CGPU_CUDA(dev_alloc(&pa, (size_t)ks * B * sizeof(int)));
+    {
+        KT kt("col_top2_kernel", st);
+        col_top2_kernel<<<dim3(tiles, ks), 128, 0, st>>>(x, K, B, ld, rows_per, pm, pm + (size_t)ks * B, pa);
+        CGPU_LAUNCH_CHECK();
+    }
+    {
+        KT kt("col_top2_merge_kernel", st);
+        col_top2_merge_kernel<<<tiles, 128, 0, st>>>(pm, pm + (size_t)ks * B, pa, ks, B, m1, m2, a1);
+        CGPU_LAUNCH_CHECK();
+    }
+    dev_free(pm);
+    dev_free(pa);
     return CGPU_OK;
 }
 int launch_stat_build(const double *x, int K, int B, int ld, const double *m1, const double *m2, const int *a1,
                       int cm, const int *ass_ptr, const int *ass_idx, double *stat, cudaStream_t st) {
     if (B <= 0 || cm <= 0) return CGPU_OK;
     int gy = std::min(cm, 64);
+    KT kt("stat_build_kernel", st);
     stat_build_kernel<<<dim3((B + 127) / 128, gy), 128, 0, st>>>(x, K, B, ld, m1, m2, a1, cm, ass_ptr, ass_idx, stat);
     CGPU_LAUNCH_CHECK();
     return CGPU_OK;
 }
 int launch_center(const double *x, int K, int B, int ld, double *xc, cudaStream_t st, bool rescale, double rs) {
+    KT kt("center_rows_kernel", st);
     center_rows_kernel<<<(K + 3) / 4, 128, 0, st>>>(x, K, B, ld, xc, rescale, rs);
     CGPU_LAUNCH_CHECK();
     return CGPU_OK;
 }
 int launch_pair_weight(const double *xc, int K, int B, int ld, double varadd, double *wt, int *nsmall,
-                       cudaStream_t st) {
+                       cudaStream_t st, const int *d_rows, int nrows) {
     int t = (K + PV_T - 1) / PV_T;
-    pair_weight_kernel<<<dim3(t, t), PV_T * PV_T, 0, st>>>(xc, K, B, ld, varadd, wt, nsmall);
+    const int ty = d_rows ? (nrows + PV_T - 1) / PV_T : t;
+    if (ty <= 0) return CGPU_OK;
+    KT kt("pair_weight_kernel", st);
+    pair_weight_kernel<<<dim3(t, ty), PV_T * PV_T, 0, st>>>(xc, K, B, ld, varadd, wt, nsmall, d_rows, nrows);
+    CGPU_LAUNCH_CHECK();
+    return CGPU_OK;
+}
+int launch_wsh_single(const double *x, int K, int B, int ld, const double *wt, const int *mem_tree, int nmem, double *out,
+                      cudaStream_t st) {
+    if (nmem <= 0 || B <= 0) return CGPU_OK;
+    KT kt("wsh_single_kernel", st);
+    wsh_single_kernel<<<dim3((B + 127) / 128, (nmem + WS_MI - 1) / WS_MI), 128, 0, st>>>(x, K, B, ld, wt, mem_tree, nmem, out);
     CGPU_LAUNCH_CHECK();
     return CGPU_OK;
 }
@@ -747,6 +963,7 @@ int launch_sh_rows(bool weighted, const double *x, int K, int B, int ld, const d
                    cudaStream_t st) {
     if (nmem <= 0 || B <= 0) return CGPU_OK;
     dim3 grid((B + 127) / 128, nmem);
+    KT kt(weighted ? "sh_rows_kernel<weighted>" : "sh_rows_kernel", st);
     if (weighted) sh_rows_kernel<true><<<grid, 128, 0, st>>>(x, K, B, ld, wt, mem_item, mem_tree, cass_ptr, cass_idx, out);
     else sh_rows_kernel<false><<<grid, 128, 0, st>>>(x, K, B, ld, wt, mem_item, mem_tree, cass_ptr, cass_idx, out);
     CGPU_LAUNCH_CHECK();
@@ -756,6 +973,7 @@ int launch_weighted_obs(const double *dat, int K, const double *wt, int nmem, co
                         const int *mem_tree, const int *cass_ptr, const int *cass_idx, double *obs, int *argj,
                         cudaStream_t st) {
     if (nmem <= 0) return CGPU_OK;
+    KT kt("weighted_obs_kernel", st);
     weighted_obs_kernel<<<(nmem + 127) / 128, 128, 0, st>>>(dat, K, wt, nmem, mem_item, mem_tree, cass_ptr, cass_idx, obs, argj);
     CGPU_LAUNCH_CHECK();
     return CGPU_OK;

@@ -158,7 +158,26 @@ static int lockstep(int nhalf, Prep prep, Ask ask, Fit fit, double *tq, double *
     return 0;
 }
 
-int run(const Input &in, const aufit::Options &opt, QueryFn query, void *ctx, Output *out, QueryRowsFn query_rows) {
+// Sharded runs: one half, every round is a collective; the loop ends when NO rank is active.
+template <class Prep, class Ask, class Fit>
+static int lockstep_dist(Prep prep, Ask ask, Fit fit, double *tq, double *tf, int *nround) {
+    for (;;) {
+        const int nq = prep(0);  // 0: this rank's items are done (it still serves the round)
+        int any = 0;
+        const double w0 = wall_now();
+        if (int rc = ask(nq, &any)) return rc;
+        const double w1 = wall_now();
+        (*nround)++;
+        *tq += w1 - w0;
+        if (!any) break;
+        if (nq > 0) fit(0, nq);
+        *tf += wall_now() - w1;
+    }
+    return 0;
+}
+
+int run(const Input &in, const aufit::Options &opt, QueryFn query, void *ctx, Output *out, QueryRowsFn query_rows,
+        DistQueryFn dist_query) {
     const int cm = in.cm, kk = in.kk;
     static const bool trace = getenv("CHOST_TIMING") != nullptr;  // per-phase wall times on stderr
     static const bool no_overlap = getenv("CHOST_NO_OVERLAP") != nullptr;
@@ -168,7 +187,7 @@ int run(const Input &in, const aufit::Options &opt, QueryFn query, void *ctx, Ou
     for (int k = 0; k < kk; k++) bbd[k] = (double)in.bb[k];
     const double t0 = refio::cpu_seconds();
     // row ranges of the halves
-    const int nhalf = (query_rows && cm >= 16 && refio::debugmode <= 0 && !no_overlap) ? 2 : 1;
+    const int nhalf = (!dist_query && query_rows && cm >= 16 && refio::debugmode <= 0 && !no_overlap) ? 2 : 1;
     const int lo[2] = {0, nhalf == 2 ? cm / 2 : cm}, hi[2] = {nhalf == 2 ? cm / 2 : cm, cm};
     auto ask_rows = [&](int h, int nq, const double *thr, cgpu_rowsum *rs) {
         if (nhalf == 1) return query(ctx, nq, thr, rs);
@@ -179,8 +198,8 @@ int run(const Input &in, const aufit::Options &opt, QueryFn query, void *ctx, Ou
     std::vector<aufit::VcIter> vc;
     vc.reserve(cm);
     for (int i = 0; i < cm; i++) vc.emplace_back(in.median[i], in.threshold);
-    std::vector<double> thr(cm);
-    std::vector<cgpu_rowsum> rs((size_t)cm * kk);
+    std::vector<double> thr(std::max(cm, 1), 1.0e300);
+    std::vector<cgpu_rowsum> rs((size_t)std::max(cm, 1) * kk);
     int vround[2] = {0, 0};
     {
         auto prep = [&](int h) {
@@ -204,7 +223,10 @@ int run(const Input &in, const aufit::Options &opt, QueryFn query, void *ctx, Ou
                 vc[i].step(cnts.data(), in.rr, bbd.data(), kk, opt);
             });
         };
-        if (int rc = lockstep(nhalf, prep, ask, fit, &tq, &tf, &nround)) return rc;
+        if (dist_query) {
+            auto dask = [&](int nq1, int *any) { return dist_query(ctx, 1, thr.data(), rs.data(), nq1 > 0, any); };
+            if (int rc = lockstep_dist(prep, dask, fit, &tq, &tf, &nround)) return rc;
+        } else if (int rc = lockstep(nhalf, prep, ask, fit, &tq, &tf, &nround)) return rc;
     }
     if (trace) fprintf(stderr, "[audriver] vcalpval: %d queries, exposed query %.2f ms, fits %.2f ms\n", nround, tq * 1e3, tf * 1e3);
     tq = tf = 0;
@@ -261,8 +283,8 @@ int run(const Input &in, const aufit::Options &opt, QueryFn query, void *ctx, Ou
             return nmax;
         };
         // thresholds and answers of half h live at row offset lo[h] of buffers sized for nq per row
-        cthr.assign((size_t)cm * nq, 1.0e300);
-        crs.resize((size_t)cm * kk * nq);
+        cthr.assign((size_t)std::max(cm, 1) * nq, 1.0e300);
+        crs.resize((size_t)std::max(cm, 1) * kk * nq);
         auto ask = [&](int h, int nmax) {
             const int rows = hi[h] - lo[h];
             double *t = cthr.data() + (size_t)lo[h] * nq;
@@ -302,7 +324,38 @@ int run(const Input &in, const aufit::Options &opt, QueryFn query, void *ctx, Ou
                 c.step(cnts.data(), in.rr, bbd.data(), kk, opt);
             });
         };
-        if (int rc = lockstep(nhalf, prep, ask, fit, &tq, &tf, &nround)) return rc;
+        if (dist_query) {
+            // fixed width on every rank: all nq searches of an item, qchunk at a time (converged
+            // searches and finished ranks send a threshold above every statistic)
+            const int nfix = std::min(nq, qchunk);
+            auto dprep = [&](int h) { return prep(h) > 0 ? nq : 0; };
+            auto dask = [&](int nloc, int *any) {
+                const int rows = cm;
+                double *t = cthr.data();
+                for (int e = 0; e < rows; e++)
+                    for (int a = 0; a < nq; a++)
+                        t[(size_t)e * nq + a] = (nloc > 0 && a < nact[e]) ? ci[(size_t)e * nq + act[(size_t)e * nq + a]].x : 1.0e300;
+                cgpu_rowsum *o = crs.data();
+                *any = 0;
+                if (nq <= qchunk) return dist_query(ctx, nq, t, o, nloc > 0, any);
+                for (int a0 = 0; a0 < nq; a0 += nfix) {  // more than 16 searches per item: fixed-size chunks
+                    std::vector<double> tt((size_t)std::max(rows, 1) * nfix, 1.0e300);
+                    std::vector<cgpu_rowsum> oo((size_t)std::max(rows, 1) * kk * nfix);
+                    const int nqc = std::min(nfix, nq - a0);
+                    for (int e = 0; e < rows; e++)
+                        for (int a = 0; a < nqc; a++) tt[(size_t)e * nfix + a] = t[(size_t)e * nq + a0 + a];
+                    int any1 = 0;
+                    if (int rc = dist_query(ctx, nfix, tt.data(), oo.data(), nloc > 0, &any1)) return rc;
+                    *any |= any1;
+                    for (int e = 0; e < rows; e++)
+                        for (int k = 0; k < kk; k++)
+                            for (int a = 0; a < nqc; a++)
+                                o[((size_t)e * kk + k) * nq + a0 + a] = oo[((size_t)e * kk + k) * nfix + a];
+                }
+                return 0;
+            };
+            if (int rc = lockstep_dist(dprep, dask, fit, &tq, &tf, &nround)) return rc;
+        } else if (int rc = lockstep(nhalf, prep, ask, fit, &tq, &tf, &nround)) return rc;
     }
     if (trace) fprintf(stderr, "[audriver] invtpval: %d queries, exposed query %.2f ms, fits %.2f ms\n", nround, tq * 1e3, tf * 1e3);
     const size_t n2 = (size_t)cm * nalpha;

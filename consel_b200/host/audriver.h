@@ -16,6 +16,14 @@ typedef int (*QueryFn)(void *ctx, int nq, const double *thr, cgpu_rowsum *out);
 // same shape as cgpu_count_query_rows: rows [row0, row0+nrows) only (thr nrows x nq, out nrows x S x nq)
 typedef int (*QueryRowsFn)(void *ctx, int row0, int nrows, int nq, const double *thr, cgpu_rowsum *out);
 
+// Sharded runs (one process per GPU): `in` describes THIS rank's items only and every query is a
+// collective that all ranks enter together -- same shape as cgpu_count_query_dist(reps, 0, ...):
+// thr = cm x nq thresholds of the rank's items, out = cm x kk x nq summaries over ALL replicates,
+// `active` = this rank still iterates, *any_active = some rank does.  nq is the same on every
+// rank in every round (1 in the vcalpval phase, min(2*nalpha, 16) per chunk in the invtpval phase),
+// and a rank whose items have converged keeps entering rounds until nobody is active.
+typedef int (*DistQueryFn)(void *ctx, int nq, const double *thr, cgpu_rowsum *out, int active, int *any_active);
+
 struct Input {
     int cm = 0, kk = 0;
     const double *rr = nullptr;   // kk scales
@@ -41,6 +49,7 @@ struct Output {
 // returns 0, or the first non-zero code of the query callback
 // With `query_rows` the items are split into two halves that alternate between the device
 // (count query) and the host (fits); results do not depend on the schedule.
-int run(const Input &in, const aufit::Options &opt, QueryFn query, void *ctx, Output *out, QueryRowsFn query_rows = nullptr);
+int run(const Input &in, const aufit::Options &opt, QueryFn query, void *ctx, Output *out, QueryRowsFn query_rows = nullptr,
+        DistQueryFn dist_query = nullptr);
 
 }  // namespace audriver

@@ -14,7 +14,8 @@
  *     reference's, matrices are caller-owned HOST memory unless the name says
  *     "dev"; the library owns all device memory behind opaque handles.
  *   - return 0 on success, a negative CGPU_E* code on failure;
- *     cgpu_last_error() then returns a static, thread-local message.  The host
+ *     cgpu_last_error() then returns the process-wide message of the most
+ *     recent failure (whichever thread it happened on).  The host
  *     programs turn a failure into the reference's `#! Terminated: ...` + exit(1)
  *     (src/misc.c:40-49).  There is NO CPU fallback: without a CUDA device every
  *     compute entry point fails with CGPU_ENODEV.
@@ -167,6 +168,55 @@ int cgpu_mctest(const cgpu_reps *r, int i0, const double *datvec, double varadd,
                 const int *ass_ptr, const int *ass_idx, double *kh, double *sh, double *wkh,
                 double *wsh);
 
+/* ------------------------------------------------------ multi-GPU */
+/* One process per GPU.  The reference's only parallel recipe is one makermt process per scale
+ * plus catrep (src/program.tex:1089-1109); here replicates (columns) are sharded over the
+ * ranks and the consel side combines per-rank results over the library's own NCCL
+ * communicator.  cgpu_comm_init also does cgpu_set_shard(rank, world).  The 128-byte id comes
+ * from rank 0's cgpu_comm_unique_id and reaches the other ranks through the launcher, or
+ * cgpu_comm_init_env does it all from RANK / WORLD_SIZE / MASTER_ADDR / MASTER_PORT (TCP on
+ * MASTER_PORT+17, or CGPU_COMM_PORT).  With no communicator every call below is local.      */
+int cgpu_comm_unique_id(char *id128);
+int cgpu_comm_init(int rank, int world, const char *id128);
+int cgpu_comm_init_env(void);
+void cgpu_comm_destroy(void);
+int cgpu_comm_info(int *rank, int *world);
+/* items (rows of the statistic blocks) are owned in equal contiguous ranges of
+ * ceil(cm/world) rows: this rank fits rows [row0, row0+nrows)                               */
+int cgpu_comm_item_range(int cm, int *row0, int *nrows);
+/* small host-buffer collectives for the results (staged through device memory):
+ * recv = world x bytes; op 0 sum, 1 max, 2 min, in place                                    */
+int cgpu_comm_allgather_host(const void *send, void *recv, long long bytes);
+int cgpu_comm_allreduce_host(double *buf, long long count, int op);
+int cgpu_comm_barrier(void);
+
+/* COLLECTIVE.  All-gather of the rank-local column blocks of scale s into one K x bb[s] block on
+ * every rank (NCCL all-gather + strided device copies): a new single-scale, unsharded handle.
+ * The KH/SH tests and the median of the AU start value need that scale whole
+ * (src/consel.c:1374-1415: sequential row sums over all replicates).                        */
+int cgpu_reps_gather_scale(const cgpu_reps *r, int s, cgpu_reps **whole);
+
+/* cgpu_mctest for the items [e0, e1) only (the other entries of kh/sh/wkh/wsh are left
+ * untouched): the O(K^2 B) loops shard over items when every rank holds the whole scale.
+ * cgpu_mctest itself, called on a column-sharded handle with a communicator, does
+ * gather + item range + all-reduce of the four vectors (COLLECTIVE in that case).            */
+int cgpu_mctest_rows(const cgpu_reps *r, int i0, const double *datvec, double varadd, int cm,
+                     const int *ass_ptr, const int *ass_idx, int e0, int e1, double *kh, double *sh,
+                     double *wkh, double *wsh);
+
+/* COLLECTIVE count query over column-sharded statistic blocks (one fit round of the AU test):
+ *   all_rows != 0: thr is cm x nq, identical on every rank; out = cm x S x nq on every rank.
+ *   all_rows == 0: thr is nrows x nq for THIS rank's items (cgpu_comm_item_range); out =
+ *                  nrows x S x nq: the summaries of its items over ALL replicates.
+ * nq must be the same on every rank.  Each rank counts every item over its own columns
+ * (thresholds all-gathered on the device), the integer counts add, lo is a max, hi a min
+ * (one grouped NCCL reduce[-scatter]): exact and order independent, hence bit-identical to
+ * the single-device result.  `active` is this rank's "I still iterate" flag; *any_active
+ * returns the OR over all ranks from the same exchange, so converged ranks know how long to
+ * keep serving rounds.  Without a communicator this is cgpu_count_query.                     */
+int cgpu_count_query_dist(const cgpu_reps *r, int all_rows, int nq, const double *thr, cgpu_rowsum *out,
+                          int active, int *any_active);
+
 /* -------------------------------------------------------------- introspection */
 /* Device time (ms, CUDA events on the library's streams) of the last cgpu_scaleboot_*
  * call: [0] upload, [1] rng/jump, [2] resample, [3] contraction (all kernels),
@@ -189,6 +239,19 @@ int cgpu_last_timing_ex(double *ms, int n);
  * unknown name.  Environment (development): CGPU_TRACE=1 prints every timed span of a
  * resampling call, CGPU_STAGE_FRACS=a,b,c overrides the stage sizes.                    */
 int cgpu_set_option(const char *name, int value);
+/* With cgpu_set_option("ktime", 1) every kernel launch of the consel side (statistics, count
+ * queries, order statistics, KH/SH tests) is bracketed by CUDA events; this call synchronises the
+ * device, writes one line "kernel_name launches total_ms" per kernel into buf and clears the
+ * record (bench.py's per-kernel rooflines).                                              */
+int cgpu_kernel_times(char *buf, int len);
+/* shape of an uploaded matrix; slices/frac_bits/mpad describe the fixed-point split of
+ * CGPU_SUM_INT8 (0 before the first int8 call): L = M * 2^-frac_bits, M in `slices` signed
+ * base-256 digits, mpad = GEMM rows (slices*K rounded up to 128).  Any pointer may be NULL. */
+int cgpu_matrix_info(const cgpu_matrix *m, int *K, int *n, int *NP, int *slices, int *frac_bits, long long *mpad);
+/* measured roofline denominators (MEASURED_PEAKS.json carries HBM and bf16 only): dense int8
+ * tcgen05.mma issue rate from shared-memory-resident operands (TOP/s), FP64 DFMA rate (TFLOP/s) */
+int cgpu_bench_i8_peak(double *tops);
+int cgpu_bench_fp64_peak(double *tflops);
 /* draws per chunk of the most recent MT19937 jump plan (diagnostics / tests) */
 unsigned long long cgpu_last_chunk_len(void);
 /* number of kernels launched by this library since cgpu_init (bench `gpu_launches`) */

@@ -12,7 +12,7 @@ def synth(K, n, seed=20261019):
 
 cg.init()
 RR = [0.5, 0.6, 0.7, 0.8, 0.9, 1.0, 1.1, 1.2, 1.3, 1.4]
-cfgs = {"C1": (15, 3414, 10000), "C2": (105, 3414, 100000), "C3": (1000, 100000, 10000), "C3s": (1000, 100000, 2000)}
+cfgs = {"C1": (15, 3414, 10000), "C2": (105, 3414, 100000), "C3": (1000, 100000, 10000), "C3s": (1000, 100000, 2000), "C5": (10000, 50000, 10000), "C5s": (10000, 50000, 1000)}
 for name in sys.argv[1:]:
     K, n, B = cfgs[name]
     L = synth(K, n)
