@@ -1,33 +1,48 @@
 #!/usr/bin/env python
-"""bench.py — tree-site accumulations per second of the multiscale RELL bootstrap.
+"""bench.py — tree-site accumulations per second of the multiscale RELL bootstrap, and the
+makermt+consel wall time, on the configurations BASELINE.json names.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config C1|C2|C3|C4|C5] [--impl ours|reference]
 
-Metric (BASELINE.json): acc/s = K*n*sum_s(B_s) / t, where one "step" is one full
-makermt resampling pass (all scales) over one synthetic site-log-likelihood matrix.
-Workload = BASELINE.json configs[1] ("C2"): K=105 trees x n=3414 sites, 10 scales
-r=0.5..1.4, 100000 replicates per scale PER GPU (replicates are sharded over ranks with
-no data-path collective, so N GPUs resample N x 100000 replicates per scale: weak
-scaling).  Headline mode = the north star's parity contract: the reference's own seeded
-MT19937 index stream (site counts bit-exact) + exact fixed-point sums on the tcgen05 int8
-tensor cores (replicate sums = the correctly rounded exact sums, <= 1e-12 relative to
-`makermt -s 7`).  The line also carries `modes`: the bit-identical strict fp64 mode, the
-fast fp64 mode and the counter-based (Philox) resampler, each timed the same way.
+Metric (BASELINE.json): acc/s = K*n*sum_s(B_s) / t, one "step" = one full makermt resampling pass
+(all ten scales) over one site-log-likelihood matrix.  Workloads:
 
-  value  device-resident: L already in HBM, replicate blocks left in HBM
-         (cgpu_scaleboot_dev), timed with CUDA events on the library's stream.
-  e2e    through the drop-in C-ABI call cgpu_scaleboot_all with HOST buffers:
-         H2D of L, compute, D2H of the replicate blocks, all inside the timed region.
+    C1  example/mam15.lnf (real data): K=15 x n=3414, 10 x 10^4 replicates
+    C2  synthetic K=105 x n=3414, 10 x 10^5 replicates PER GPU (weak scaling: the r01 headline)
+    C3  synthetic K=1000 x n=10^5, 10 x 10^4 replicates, sharded over the ranks (strong scaling)
+        -- the DEFAULT: the configuration the north star is quoted on, and it fits one GPU
+    C4  synthetic K=100 x n=10^7, 10 x 10^4 replicates over 8 GPUs; with N < 8 ranks the run keeps
+        the per-GPU share of the 8-GPU job (10^4 * N/8 replicates per scale) and says so
+    C5  synthetic K=10^4 x n=5*10^4, 10 x 10^4 replicates (consel-kernel stress), strong scaling
 
---impl reference times the UNMODIFIED reference program (oracle/_ref/makermt, built
-from /root/reference/src by oracle/Makefile) on the host cores with the reference's
-own parallel recipe (one process per scale, doc: src/program.tex:1089-1109), on a
-bounded sample of the same workload.
+Headline mode = the north star's parity contract: the reference's own seeded MT19937 index stream
+(site counts bit-exact) + exact fixed-point sums on the tcgen05 int8 tensor cores (the correctly
+rounded exact sums).  A few replicate columns of the timed run are checked in-run against the CPU
+oracle (`spot_check`).
+
+  value      device-resident: L already in HBM, replicate blocks left in HBM (cgpu_scaleboot_dev),
+             CUDA events on the library's stream, max over ranks.
+  e2e        through the drop-in C-ABI call cgpu_scaleboot_all with HOST buffers: H2D of L, compute,
+             D2H of this rank's replicate blocks, all inside the timed region.
+  pipeline   the metric's second half: makermt+consel wall time in one process (chost_consel_run:
+             KH/SH/wKH/wSH, BP, AU + confidence limits for every item), p-value table on the host;
+             sharded over the ranks through the library's NCCL communicator when N > 1.
+  roofline   the kernel with the largest share of the step, `roofline.kernels` every kernel of the
+             makermt AND consel sides with its own bound, `roofline.step` the whole step against
+             SURVEY 8(d)'s floor (2*S*K*n*sum(B) int8-ops at the int8 peak MEASURED in this run).
+
+--impl reference times the reference's own CPU code on the host cores: the unmodified makermt
+binary (one process per scale and part, src/program.tex:1089-1109) when the matrix is small enough
+to pass as a .mt text file, else the reference's scaleboot() compiled unmodified from
+/root/reference/src/makermt.c into oracle/_ref/libmakermt_ref.so and called in-process (a C3 .mt
+file is 2.4 GB of text that every one of the processes would parse for minutes); plus the
+reference consel binary on the .rmt those replicates make (`pipeline`).
 """
 from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import statistics
 import subprocess
@@ -45,32 +60,87 @@ sys.path.insert(0, str(ROOT))
 METRIC = "bootstrap tree-site accumulations/sec (K*n*B)"
 UNIT = "acc/s"
 RR = [0.5, 0.6, 0.7, 0.8, 0.9, 1.0, 1.1, 1.2, 1.3, 1.4]
-K, N_SITES, B_PER_SCALE = 105, 3414, 100000
+CONFIGS = {
+    "C1": dict(K=15, n=3414, B=10000, scaling="strong", what="example/mam15.lnf (real data, BASELINE.json configs[0])"),
+    "C2": dict(K=105, n=3414, B=100000, scaling="weak", what="synthetic mam105-style, replicate-heavy (BASELINE.json configs[1])"),
+    "C3": dict(K=1000, n=100000, B=10000, scaling="strong", what="synthetic phylogenomic (BASELINE.json configs[2])"),
+    "C4": dict(K=100, n=10000000, B=10000, scaling="strong", what="synthetic genome-scale (BASELINE.json configs[3], an 8-GPU job)"),
+    "C5": dict(K=10000, n=50000, B=10000, scaling="strong", what="synthetic many-trees, consel-kernel stress (BASELINE.json configs[4])"),
+}
+DEFAULT_CONFIG = "C3"
 
 
 def synth_matrix(k: int, n: int, seed: int = 20261019) -> np.ndarray:
-    """mam15-like site log-likelihoods."""
+    """mam15-like site log-likelihoods (row blocks keep the peak host memory at one copy)."""
     rng = np.random.Generator(np.random.PCG64(seed))
     base = -2.3 - 4.07 * rng.exponential(size=n)
-    return np.ascontiguousarray(base[None, :] + 0.106 * rng.standard_normal((k, n)) - 0.5 * np.arange(k)[:, None] / n)
+    L = np.empty((k, n))
+    step = max(1, (1 << 24) // n)
+    for k0 in range(0, k, step):
+        k1 = min(k, k0 + step)
+        L[k0:k1] = base[None, :] + 0.106 * rng.standard_normal((k1 - k0, n)) - 0.5 * np.arange(k0, k1)[:, None] / n
+    return L
 
 
-def config(world: int) -> dict:
-    return {
-        "workload": "C2 (BASELINE.json configs[1]): synthetic K=105 trees x n=3414 sites, 10 scales "
-                    "r=0.5..1.4 x 100000 replicates per scale per GPU",
-        "K": K, "n": N_SITES, "scales": len(RR), "replicates_per_scale_per_gpu": B_PER_SCALE,
-        "replicates_per_scale_total": B_PER_SCALE * world,
+def read_paml_lnf(path: Path) -> np.ndarray:
+    """PAML .lnf (the makermt --paml input, src/freadmat.c:110-154): `m n p`, per tree an id line and p
+    pattern lines `idx count lnL ...`; every pattern's lnL is repeated `count` times."""
+    rows = [t.split() for t in path.read_text().splitlines() if t.strip()]
+    m, n, npat = (int(x) for x in rows[0][:3])
+    L = np.empty((m, n))
+    p = 1
+    for i in range(m):
+        p += 1
+        col = 0
+        for _ in range(npat):
+            cnt = int(rows[p][1])
+            L[i, col:col + cnt] = float(rows[p][2])
+            col += cnt
+            p += 1
+    return L
+
+
+def workload(name: str, world: int) -> dict:
+    c = dict(CONFIGS[name])
+    if name == "C4" and world < 8:
+        c["B_total"] = max(8, c["B"] * world // 8)
+        c["note"] = (f"C4 is an 8-GPU job (9.5e11 draws): with {world} rank(s) the run keeps the per-GPU share of it, "
+                     f"{c['B_total']} replicates per scale in total")
+    else:
+        c["B_total"] = c["B"] * world if c["scaling"] == "weak" else c["B"]
+    return c
+
+
+def make_matrix(name: str, c: dict) -> np.ndarray:
+    if name == "C1":
+        return read_paml_lnf(ROOT / "tests" / "golden" / "mam15.lnf")
+    return synth_matrix(c["K"], c["n"])
+
+
+def config_json(name: str, c: dict, world: int) -> dict:
+    K, n = c["K"], c["n"]
+    NP = (n + 127) // 128 * 128
+    idx_b = 2 if n <= 65536 else 4
+    per_scale = c["B_total"] // world
+    ws = (idx_b * n * per_scale + NP * per_scale + 8 * K * per_scale) / 1e9
+    out = {
+        "workload": f"{name}: {c['what']}: K={K} trees x n={n} sites, 10 scales r=0.5..1.4 x {c['B_total']} replicates per scale"
+                    + (" in total (sharded over the ranks)" if c["scaling"] == "strong" else f" ({c['B']} per GPU)"),
+        "K": K, "n": n, "scales": len(RR), "replicates_per_scale_total": c["B_total"],
+        "replicates_per_scale_per_gpu": per_scale,
         "rng_mode": "mt19937 reference stream (seed 7), device jump-ahead: site counts bit-exact",
-        "sum_mode": "int8: exact fixed-point sums on tcgen05 tensor cores, one rounding (<=1e-12 rel. to the "
-                    "reference; `modes.strict_mt` is the bit-identical fp64 mode)",
-        "l2": "per-scale working set (index buffer 1.9 GB + counts 0.35 GB + replicate block 84 MB) "
-              "exceeds the 126 MB L2; a 256 MB buffer is also written between timed steps",
+        "sum_mode": "int8: exact fixed-point sums on tcgen05 tensor cores, one rounding (<=1e-12 rel. to the reference; "
+                    "`modes.strict_mt` is the bit-identical fp64 mode)",
+        "l2": f"inputs larger than L2: a scale's working set (indices + count rows + replicate block) is ~{ws:.2f} GB "
+              "per rank against the 126 MB L2; a 256 MB buffer is also written between timed steps",
     }
+    if "note" in c:
+        out["note"] = c["note"]
+    return out
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    """NVML clocks / throttle reasons DURING the timed region (B200_PROFILING.md); nvidia-smi fallback."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -81,10 +151,10 @@ class ClockSampler(threading.Thread):
         self.idx = gpu_index
         self.rows = []
         self._halt = threading.Event()
+        # NVML queries take a driver lock; polled too often they delay the library's own launches
+        self.period = float(os.environ.get("BENCH_SAMPLER_MS", "25")) * 1e-3
 
     def run(self):
-        # NVML polls in well under a millisecond, so even a 50 ms timed region yields tens of
-        # samples; nvidia-smi (one process per sample) is the fallback
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -95,7 +165,7 @@ class ClockSampler(threading.Thread):
                 sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
                 r = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
                 self.rows.append(["nvml", str(sm), str(mx), "", ""] + ["Active" if r & b else "Not Active" for b in bits.values()])
-                self._halt.wait(0.002)
+                self._halt.wait(self.period)
             return
         except Exception:
             pass
@@ -125,10 +195,18 @@ class ClockSampler(threading.Thread):
 
 
 def dist_env():
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    return rank, world, local
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+
+
+def exact_sums(Lrows: np.ndarray, counts: np.ndarray, r: float) -> np.ndarray:
+    """Correctly rounded exact sums sum_j c[b,j]*L[k,j] (math.fsum over the drawn multiset), then /r:
+    what CGPU_SUM_INT8 must return bit for bit (checker side of the in-run spot check)."""
+    out = np.empty((Lrows.shape[0], counts.shape[0]))
+    for b in range(counts.shape[0]):
+        c = counts[b].astype(np.int64)
+        for k in range(Lrows.shape[0]):
+            out[k, b] = math.fsum(np.repeat(Lrows[k], c)) / np.float64(r)
+    return out
 
 
 # ----------------------------------------------------------------------------- ours
@@ -137,6 +215,7 @@ def run_ours(args) -> None:
     import torch.distributed as dist
 
     import consel_b200 as cg
+    from consel_b200 import pipeline
 
     rank, world, local = dist_env()
     if world != args.gpus and world > 1:
@@ -146,11 +225,17 @@ def run_ours(args) -> None:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     cg.init(local)
-    cg.set_shard(rank, world)
+    if world > 1:
+        pipeline.comm_init_from_torch()  # the library's own NCCL communicator (sets the shard too)
+    else:
+        cg.set_shard(0, 1)
 
-    L = synth_matrix(K, N_SITES)
+    name = args.config
+    c = workload(name, world)
+    K, N_SITES = c["K"], c["n"]
+    L = make_matrix(name, c)
     _, bn, _ = cg.scale_setup(L, RR)
-    bb = np.full(len(RR), B_PER_SCALE * world, dtype=np.int32)
+    bb = np.full(len(RR), c["B_total"], dtype=np.int32)
     acc_per_step_total = float(K) * N_SITES * float(bb.sum())
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
@@ -169,8 +254,9 @@ def run_ours(args) -> None:
     # ---- device-resident arm
     mat = cg.Matrix(L)
     flush_ctr = [0]
+    keep = {}
 
-    def timed_steps(rng_mode, sum_mode, steps, warmup):
+    def timed_steps(rng_mode, sum_mode, steps, warmup, keep_last=False):
         for w in range(warmup):
             mat.scaleboot(bn, bb, 7, rng_mode=rng_mode, sum_mode=sum_mode).free()
         dev, wall, ph = 0.0, 0.0, {}
@@ -186,7 +272,10 @@ def run_ours(args) -> None:
             dev += tm["total"]
             for k_, v in tm.items():
                 ph[k_] = ph.get(k_, 0.0) + v / steps
-            reps.free()
+            if keep_last and step == steps - 1:
+                keep["reps"] = reps
+            else:
+                reps.free()
         barrier()
         return max_over_ranks(dev), max_over_ranks(wall), ph
 
@@ -196,34 +285,74 @@ def run_ours(args) -> None:
     if rank == 0:
         sampler.start()
     launches0 = cg.launch_count()
-    dev_ms, wall_ms, phases = timed_steps(*HEAD, args.steps, 0)
+    dev_ms, wall_ms, phases = timed_steps(*HEAD, args.steps, 0, keep_last=True)
     launches = cg.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
-    modes = {}
-    side_steps = max(1, min(args.steps, 3))
-    for name, rm, sm in (("strict_mt", cg.RNG_MT19937, cg.SUM_STRICT), ("fast_mt", cg.RNG_MT19937, cg.SUM_FAST),
-                         ("int8_philox", cg.RNG_PHILOX, cg.SUM_INT8)):
-        d, w_, ph = timed_steps(rm, sm, side_steps, 2)
-        modes[name] = {"ms_per_step": d / side_steps, "value": acc_per_step_total * side_steps / (d * 1e-3),
-                       "phases_ms_per_step": ph}
 
-    # ---- the metric's second half: makermt+consel wall time, in one process (no .rmt round trip),
-    # same workload; sharded over the ranks when N>1 (row summaries combined over NCCL)
-    from consel_b200 import pipeline
+    # ---- in-run spot check of the timed run's own output against the CPU oracle (rank 0: the first
+    # two replicates of scales 0 and 1 -- scale 1 starts bb[0]*bn[0] draws into the MT19937 stream)
+    spot = None
+    if rank == 0:
+        from oracle import oracle as orc
+        t0 = time.perf_counter()
+        ok_counts, ok_exact, worst_rel = True, True, 0.0
+        ktrees = np.unique(np.linspace(0, K - 1, 3).astype(int))
+        skip = 0
+        for s in (0, 1):
+            nrep = 2
+            y = orc.mt_stream(7, skip, nrep * int(bn[s]))
+            idx = orc.site_indices(y, N_SITES).reshape(nrep, int(bn[s]))
+            counts = np.stack([np.bincount(idx[b], minlength=N_SITES) for b in range(nrep)])
+            got = keep["reps"].download_cols(s, 0, nrep)
+            r_s = float(bn[s]) / float(N_SITES)
+            want = exact_sums(L[ktrees], counts, r_s)
+            ok_exact = ok_exact and bool(np.array_equal(got[ktrees], want))
+            seq = orc.contract_counts(L[ktrees], counts, r_s)  # the reference's sequentially rounded sums
+            worst_rel = max(worst_rel, float(np.max(np.abs(got[ktrees] - seq) / np.abs(seq))))
+            skip += int(bb[s]) * int(bn[s])
+            if skip > 3_000_000_000:
+                break
+        spot = {"ok": bool(ok_exact and worst_rel <= 1e-9), "bit_equal_to_exact_rounded_sums": ok_exact,
+                "max_rel_diff_to_reference_sequential_sums": worst_rel,
+                "what": f"replicates 0,1 of scales 0 and 1 of the LAST timed step, trees {ktrees.tolist()}: MT19937 draws and site "
+                        "indices by the oracle (oracle/oracle.c), exact sums by math.fsum", "seconds": time.perf_counter() - t0}
+    keep.pop("reps").free()
+
+    modes = {}
+    heavy = acc_per_step_total / world > 2e12
+    side = [("int8_philox", cg.RNG_PHILOX, cg.SUM_INT8)]
+    if acc_per_step_total / world <= 2e13:
+        side = [("strict_mt", cg.RNG_MT19937, cg.SUM_STRICT), ("fast_mt", cg.RNG_MT19937, cg.SUM_FAST)] + side
+    for mname, rm, sm in side:
+        is_fp64 = sm != cg.SUM_INT8
+        st_ = 1 if (heavy and is_fp64) else max(1, min(args.steps, 3))
+        d, w_, ph = timed_steps(rm, sm, st_, 1 if (heavy and is_fp64) else 2)
+        modes[mname] = {"ms_per_step": d / st_, "value": acc_per_step_total * st_ / (d * 1e-3), "steps": st_,
+                        "phases_ms_per_step": ph}
+
+    # ---- the metric's second half: makermt+consel wall time in one process, same workload
     pipe = None
+    ktimes = {}
     try:
         pipeline.run(L, RR, bb, 7, sum_mode=cg.SUM_INT8, matrix=mat)  # warm-up: host pool, stat buffers
-        pw = []
+        pw, res = [], None
         for _ in range(3):
             barrier()
             t0 = time.perf_counter()
             res = pipeline.run(L, RR, bb, 7, sum_mode=cg.SUM_INT8, matrix=mat)
             pw.append((time.perf_counter() - t0) * 1e3)
         barrier()
+        cg.set_option("ktime", 1)  # one more pass with per-kernel CUDA events on the consel side
+        pipeline.run(L, RR, bb, 7, sum_mode=cg.SUM_INT8, matrix=mat)
+        ktimes = cg.kernel_times()
+        cg.set_option("ktime", 0)
         pipe = {"makermt_consel_wall_ms": max_over_ranks(float(np.median(pw))),
                 "phases_ms": {k_: round(v * 1e3, 2) for k_, v in res["timing"].items() if isinstance(v, float)},
-                "what": "pipeline.run: MT19937 + int8 resampling, KH/SH/wKH/wSH tests, BP, AU fit and confidence "
-                        "limits for all K items; replicate blocks stay on the device"}
+                "items": int(len(res["item"])), "au_first3": [float(x) for x in res["pv"][:3, 6]],
+                "what": "pipeline.run -> chost_consel_run: MT19937 + int8 resampling, KH/SH/wKH/wSH tests, BP, AU fit and "
+                        "confidence limits for all K items; replicate blocks never leave the device, the p-value table is "
+                        "returned to the host" + (f"; replicates sharded over {world} ranks, collectives issued by the "
+                                                  "library's NCCL communicator" if world > 1 else "")}
     except Exception as e:  # the headline line must still be printed
         pipe = {"error": f"{type(e).__name__}: {e}"}
 
@@ -238,6 +367,7 @@ def run_ours(args) -> None:
     e2e_steps = max(1, min(args.steps, 3))
     cg.scaleboot_all(Lh.numpy(), bn, bb, 7, sum_mode=cg.SUM_INT8, out=outs)  # warm-up (page-locks, pool growth)
     e2e_ms = 0.0
+    checksum = 0.0
     for step in range(e2e_steps):
         flush.fill_(step & 0xFF)
         barrier()
@@ -254,93 +384,123 @@ def run_ours(args) -> None:
             dist.destroy_process_group()
         return
 
-    # ---- rooflines, measured live: every kernel of the step with its own bound; the top-level
-    # `roofline` object is the kernel with the largest share of the step
-    import ctypes as C
-    tf = C.c_double()
-    cg.api._check(cg.load().cgpu_bench_fp64_peak(C.byref(tf)))
+    # ---- rooflines, measured live: every kernel of the step with its own bound
+    live = cg.bench_peaks()
     peaks = {}
     try:
         peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
     except Exception:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    bf16_peak = peaks.get("bf16_tflops", 1590.0)
     peak_src = "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"
+    i8_peak = live["int8_tops"]
+    fp64_peak = live["fp64_tflops"]
     traffic_db = {}
     tp = ROOT / "profiles" / "kernel_traffic.json"
     if tp.exists():
         try:
-            traffic_db = json.loads(tp.read_text())
+            traffic_db = json.loads(tp.read_text()).get(name, {})
         except Exception:
             traffic_db = {}
+    info = mat.info()
     b_loc = b1 - b0
-    S_SLICES = 8   # fixed-point slices of this matrix (57-bit data: see DESIGN.md 4.4)
-    M_PAD = (S_SLICES * K + 127) // 128 * 128
-    NP = (N_SITES + 127) // 128 * 128
+    S_SLICES = info["slices"]
+    M_PAD = info["mpad"]
+    NP = info["NP"]
     draws = float(sum(int(x) for x in bn)) * b_loc       # this rank's draws per step
     idx_b = 2.0 if N_SITES <= 65536 else 4.0
     nS = len(RR)
+    total_ms = max(phases["total"], 1e-9)
 
-    def entry(name, kernel, ms_step, launches, bound, alg_per_launch, peak, unit, algorithmic, note=None):
-        t_launch = max(ms_step, 1e-9) / launches * 1e-3
-        ach = alg_per_launch / t_launch / (1e12 if bound == "tensor" else 1e9)
+    def entry(kname, kernel, ms_step, nlaunch, bound, alg_per_launch, peak, unit, algorithmic, note=None, base_ms=total_ms):
+        t_launch = max(ms_step, 1e-9) / max(nlaunch, 1) * 1e-3
+        scale = 1e12 if bound != "hbm" else 1e9
+        ach = alg_per_launch / t_launch / scale
         e = {"kernel": kernel, "bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
-             "launches_per_step": launches, "us_per_launch": t_launch * 1e6, "algorithmic": algorithmic,
-             "share_of_step": ms_step / max(phases["total"], 1e-9),
-             "traffic": traffic_db.get(name)}
+             "launches_per_step": nlaunch, "us_per_launch": t_launch * 1e6, "algorithmic": algorithmic,
+             "share_of_step": ms_step / base_ms, "traffic": traffic_db.get(kname)}
         if note:
             e["note"] = note
         return e
 
+    if NP <= 14080:
+        hist_name = "hist_group_kernel<smem atomics, byte rows, one warp per replicate>"
+    elif NP <= 225280:
+        hist_name = "hist_wide_kernel<one replicate per CTA, 16-32 warps on one shared byte histogram>"
+    else:
+        hist_name = "hist_global_kernel<global atomics>"
+    gemm_launches = max(1, int(round(phases.get("n_gemm", nS))))
+    hist_launches = max(1, int(round(phases.get("n_hist", nS))))
     kernels = [
-        entry("mt_draw_kernel", "mt_draw_kernel<int path, uint16, 3 chunks/CTA> (MT19937 block regeneration + tempering + site index)",
+        entry("mt_draw_kernel", f"mt_draw_kernel<{'uint16' if idx_b == 2 else 'uint32'} indices, 3 chunks/CTA> (MT19937 block regeneration + tempering + site index)",
               phases["mt_draw"], 1, "hbm", idx_b * draws, hbm_peak, "GB/s",
-              "2 B written per draw (uint16 site index), all scales of the step in one launch",
-              "integer-issue bound, not HBM bound: ~0.82 warp-instruction per draw at ~64 % of the issue slots "
-              "(profiles/); the HBM fraction is reported because the contract asks for one of hbm|tensor"),
-        entry("hist_group_kernel", "hist_group_kernel<uint16 idx, smem atomics, byte rows>", phases["resample"], nS, "hbm",
-              (idx_b * draws + float(NP) * b_loc * nS) / nS, hbm_peak, "GB/s",
-              "2 B read per draw + NP count bytes written per replicate, one launch per scale",
+              f"{int(idx_b)} B written per draw (site index), all scales of the step in one launch",
+              "integer-issue bound, not HBM bound (~0.8 warp-instruction per draw, profiles/); the HBM fraction is reported "
+              "because the contract asks for one of hbm|tensor"),
+        entry("hist_kernel", hist_name, phases["resample"], hist_launches, "hbm",
+              (idx_b * draws + float(NP) * b_loc * nS) / hist_launches, hbm_peak, "GB/s",
+              f"{int(idx_b)} B read per draw + NP count bytes written per replicate, one launch per (scale, batch)",
               "shared-memory atomic bound (one atomic per draw)"),
-        entry("gemm_i8_persistent_kernel", "gemm_i8_persistent_kernel (tcgen05.mma kind::i8, 128x256x128 tiles, TMA SW128 ring, "
-              "2 TMEM accumulator stages, exact int128 recombination + rounding + /r fused into the epilogue)", phases["gemm_i8"], nS, "tensor", 2.0 * S_SLICES * K * N_SITES * b_loc,
-              2.0 * bf16_peak, "TOP/s (int8)",
-              "2*S int8-ops per tree-site accumulation (SURVEY 8d), S=8 slices, x K*n*B_s per launch",
-              "peak = 2 x bf16_tflops of MEASURED_PEAKS.json (dense int8 issues at twice the bf16 rate on B200; the file has no int8 figure)"),
+        entry("gemm_i8_persistent_kernel", "gemm_i8 kernel (tcgen05.mma kind::i8, TMA SW128 ring, TMEM accumulator stages, exact "
+              "recombination + rounding + /r fused into the epilogue)", phases["gemm_i8"], gemm_launches, "tensor",
+              2.0 * S_SLICES * K * N_SITES * b_loc * nS / gemm_launches, i8_peak, "TOP/s (int8)",
+              f"2*S int8-ops per tree-site accumulation (SURVEY 8d), S={S_SLICES} slices, x K*n*B_s per launch",
+              "peak = cgpu_bench_i8_peak: tcgen05.mma kind::i8 issue rate from smem-resident operands, measured in this run "
+              "(a burst figure at full clocks)"),
         entry("fx_combine_kernel", "fx_combine_kernel (exact int128 recombination of the S slice sums, one rounding, /r)",
               phases["fx_combine"], nS, "hbm", 4.0 * M_PAD * b_loc + 8.0 * K * b_loc, hbm_peak, "GB/s",
               "4 B x Mpad int32 partial sums read + 8 B x K doubles written per replicate"),
         entry("mt_jump_kernel", "mt_jump_kernel (x^J mod phi applied to a 624-word window; position list in smem)",
               phases["mt_jump"], 1, "hbm", 2.0 * 2496.0 * draws / 2 ** 22, hbm_peak, "GB/s",
               "2.5 KB read + 2.5 KB written per chunk state; the work is 624 x ~10^4 shared-memory word reads per jump",
-              "shared-memory bandwidth bound (~126 us per jump per SM against a 103 us floor at 128 B/clk); "
-              "launches_per_step=1 stands for the ~10 levels of the jump tree"),
+              "shared-memory bandwidth bound; launches_per_step=1 stands for the ~10 levels of the jump tree"),
     ]
-    # the draw kernel is bound by instruction issue, which the hbm|tensor vocabulary cannot express:
-    # add the issue-slot view (warp-instructions per draw from profiles/r01_final_draw_equalfill_ncu_full.json)
-    try:
-        prof = json.loads((ROOT / "profiles" / "r01_final_draw_equalfill_ncu_full.json").read_text())["launches"][0]
-        wi_per_draw = prof["warp_instructions"] / 3.243e9
-        sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
-        issue_peak = 4.0 * torch.cuda.get_device_properties(local).multi_processor_count * sm_mhz * 1e6
-        ach = wi_per_draw * draws / (phases["mt_draw"] * 1e-3)
-        kernels[0]["issue_view"] = {"achieved": ach / 1e9, "peak": issue_peak / 1e9, "unit": "G warp-instructions/s",
-                                    "frac": ach / issue_peak, "warp_instructions_per_draw": wi_per_draw,
-                                    "source": "instruction count from the ncu capture, time from this run's CUDA events"}
-    except Exception:
-        pass
-    kernels = [e for e in kernels if e["share_of_step"] > 1e-6]  # e.g. fx_combine runs inside the GEMM epilogue when S divides 32
-    dominant = max(kernels, key=lambda e: e["share_of_step"])
+    kernels = [e for e in kernels if e["share_of_step"] > 1e-6]  # e.g. fx_combine runs inside the GEMM epilogue when S divides 8
+    # consel side: per-kernel CUDA-event times of one pipeline pass (cgpu_kernel_times)
+    consel_alg = {  # kernel -> (bound, what the library's per-launch work figure counts)
+        "col_top2_kernel": ("hbm", "8 B x K x B_s read per scale (one pass over the replicate block)"),
+        "stat_build_kernel": ("hbm", "8 B x K x B_s read + 8 B x cm x B_s written per scale"),
+        "rowsum_multi_kernel<1>": ("hbm", "8 B per (queried item, replicate) over all scales per one-threshold query"),
+        "rowsum_multi/sorted_kernel": ("hbm", "8 B per (queried item, replicate) over all scales per pass of <= 8 thresholds"),
+        "center_rows_kernel": ("hbm", "8 B read + 8 B written per (tree, replicate) of scale i0; the row mean is a sequential chain of B rounded adds"),
+        "pair_weight_kernel": ("fp64", "pairs x B x (sub, mul, add) fp64 instructions"),
+        "wsh_single_kernel": ("fp64", "members x (K-1) x B x (sub, mul, compare) fp64 instructions"),
+        "order_stat_kernel": ("hbm", "8 B per element of the scale-i0 statistic rows (8 radix passes from L1/L2)"),
+        "rowsum_kernel<kh>": ("hbm", "two replicate rows read per item"),
+        "rowsum_kernel<sh>": ("hbm", "one replicate row read per member"),
+        "rowsum_kernel<plain>": ("hbm", "one statistic row read per member"),
+    }
+    pipe_ms = (pipe or {}).get("makermt_consel_wall_ms") or 1e9
+    for kname, (cnt, ms, work) in ktimes.items():
+        if kname not in consel_alg or cnt == 0:
+            continue
+        bound, what = consel_alg[kname]
+        alg = work / cnt
+        if bound == "hbm":
+            kernels.append(entry(kname, kname + " (consel side)", ms, cnt, "hbm", alg, hbm_peak, "GB/s", what,
+                                 "share_of_step is the share of the makermt+consel pipeline wall time", base_ms=pipe_ms))
+        else:
+            e = entry(kname, kname + " (consel side)", ms, cnt, "tensor", alg, fp64_peak / 2.0, "T fp64-instr/s", what,
+                      "FP64-pipe bound: peak = measured DFMA rate / 2 flops per instruction; `bound` says tensor only because "
+                      "the contract's vocabulary is hbm|tensor", base_ms=pipe_ms)
+            e["bound_detail"] = "fp64"
+            kernels.append(e)
+    step_kernels = [e for e in kernels if "(consel side)" not in e["kernel"]]
+    dominant = max(step_kernels, key=lambda e: e["share_of_step"])
     roofline = dict(dominant)
-    roofline["peak_source"] = peak_src
-    roofline["step_shares"] = {k_: v / max(phases["total"], 1e-9) for k_, v in phases.items() if k_ not in ("total", "rng")}
-    roofline["fp64_dfma_peak_tflops_measured_live"] = tf.value
+    roofline["peak_source"] = peak_src + " (HBM); int8 and fp64 peaks measured live by cgpu_bench_i8_peak / cgpu_bench_fp64_peak"
+    roofline["step_shares"] = {k_: v / total_ms for k_, v in phases.items() if k_ not in ("total", "rng")}
+    roofline["int8_peak_tops_measured_live"] = i8_peak
+    roofline["fp64_dfma_peak_tflops_measured_live"] = fp64_peak
+    floor_ms = 2.0 * S_SLICES * K * N_SITES * b_loc * nS / (i8_peak * 1e12) * 1e3
+    roofline["step"] = {"floor_ms": floor_ms, "ms_per_step": dev_ms / args.steps, "frac": floor_ms / (dev_ms / args.steps),
+                        "what": "SURVEY 8(d): 2*S*K*n*sum(B) int8-ops per rank at the measured int8 peak, against the whole "
+                                "device-resident step (draws + histograms + GEMMs)"}
     roofline["kernels"] = kernels
 
-    # ---- CPU baseline: the oracle port, single thread, bounded sample
+    # ---- CPU baseline: the oracle port, single thread, bounded sample (~10-20 s)
     from oracle import oracle as orc
-    b_cpu = 3000
+    b_cpu = max(1, int(2.4e10 / (K * N_SITES * len(RR))))
     t0 = time.perf_counter()
     orc.makermt(L, bn, [b_cpu] * len(RR), 7)
     t_cpu = time.perf_counter() - t0
@@ -350,48 +510,75 @@ def run_ours(args) -> None:
     line = {
         "metric": METRIC, "value": acc_per_step_total * args.steps / (dev_ms * 1e-3), "unit": UNIT,
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": config(world),
+        "higher_is_better": True, "scaling": c["scaling"], "vs_baseline": None, "dtype": "f64", "data": "synthetic" if name != "C1" else "example/mam15.lnf",
+        "config": config_json(name, c, world),
         "timing": "CUDA events on the library stream, first to last event of each step, max over ranks",
         "wall_ms_per_step": wall_ms / args.steps, "phases_ms_per_step": phases,
         "e2e": {"value": acc_per_step_total * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
-                "api": "cgpu_scaleboot_all(CGPU_RNG_MT19937, CGPU_SUM_INT8): pinned host L in, pinned host replicate blocks out"},
+                "api": "cgpu_scaleboot_all(CGPU_RNG_MT19937, CGPU_SUM_INT8): pinned host L in, this rank's pinned host replicate blocks out"},
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
-        "modes": modes, "pipeline": pipe,
+        "spot_check": spot, "modes": modes, "pipeline": pipe,
     }
     print(json.dumps(line))
     if world > 1:
+        cg.load().cgpu_comm_destroy()
         dist.destroy_process_group()
 
 
 # ------------------------------------------------------------------------ reference
+def _ref_worker(args):
+    """one host process of the in-process reference arm: scaleboot() of the unmodified makermt.c"""
+    import ctypes as C
+    so, shm_name, K, n, bn, b_each, seed = args
+    from multiprocessing import shared_memory
+    lib = C.CDLL(so)
+    shm = shared_memory.SharedMemory(name=shm_name)
+    L = np.ndarray((K, n), dtype=np.float64, buffer=shm.buf)
+    rows = (C.POINTER(C.c_double) * K)(*[C.cast(L.ctypes.data + 8 * n * k, C.POINTER(C.c_double)) for k in range(K)])
+    out = np.zeros((K, b_each))
+    orow = (C.POINTER(C.c_double) * K)(*[C.cast(out.ctypes.data + 8 * b_each * k, C.POINTER(C.c_double)) for k in range(K)])
+    lib.smrand.argtypes = [C.c_ulong]
+    lib.scaleboot.restype = C.c_void_p
+    lib.smrand(int(seed))
+    t0 = time.perf_counter()
+    lib.scaleboot(rows, orow, K, n, int(bn), int(b_each))
+    dt = time.perf_counter() - t0
+    del L
+    shm.close()
+    return dt, out
+
+
 def run_reference(args) -> None:
     rank, world, _ = dist_env()
     if rank != 0:
         return
     from oracle import oracle as orc
+    name = args.config
+    c = workload(name, max(world, args.gpus))
+    K, N_SITES = c["K"], c["n"]
     exe = orc.ref_bin("makermt")
-    if exe is None:
+    so = orc.REF_DIR / "libmakermt_ref.so"
+    if exe is None or not so.exists():
         try:
             orc.build(ref=True)
         except Exception:
             pass
         exe = orc.ref_bin("makermt")
-    L = synth_matrix(K, N_SITES)
+    L = make_matrix(name, c)
     cores = os.cpu_count() or 1
-    # the reference's parallel recipe is one process per scale; to use every host core each
-    # scale is further split into `parts` independent processes (own seed), and the
-    # 10*parts jobs run through a pool of `cores` concurrent processes
+    cfg = config_json(name, c, max(world, args.gpus))
+    _, bn, rr1 = orc.scale_setup(L, RR)
+    use_cli = exe is not None and K * N_SITES <= 2_000_000
+    # one job ~ 6-10 s of one core at ~1.5e9 acc/s
     parts = max(1, -(-2 * cores // len(RR))) if cores > len(RR) else 1
     nproc = len(RR) * parts
-    # ~10 s per job at ~1.5e9 acc/s per core
-    b_each = max(50, int(9e9 / (K * N_SITES)))
-    cfg = config(world)
+    b_each = max(2, int(9e9 / (K * N_SITES)))
+    pipe_ref = None
     with tempfile.TemporaryDirectory(prefix="consel_ref_") as td:
         td = Path(td)
-        kind = "reference"
-        if exe is not None:
+        if use_cli:
+            kind = "reference"
             orc.write_mt(td / "in.mt", L)
             for s, r in enumerate(RR):
                 for p in range(parts):
@@ -415,32 +602,77 @@ def run_reference(args) -> None:
                             raise RuntimeError("reference makermt failed")
                     running = still
                     time.sleep(0.005)
-            total_b = b_each * nproc
+                return None
+            sample = (f"{nproc} `makermt -s SEED -p one_scale.pa` processes, at most {cores} at a time (unmodified reference binary, -O2), "
+                      f"{b_each} replicates each, same matrix read from a 17-digit .mt text file; wall clock includes process start and text parse")
+        elif so.exists():
+            kind = "reference"
+            from multiprocessing import get_context, shared_memory
+            shm = shared_memory.SharedMemory(create=True, size=L.nbytes)
+            np.ndarray(L.shape, dtype=np.float64, buffer=shm.buf)[:] = L
+            ctx = get_context("fork")
+            pool = ctx.Pool(min(cores, nproc))
+            keep = {}
+
+            def step():
+                jobs = [(str(so), shm.name, K, N_SITES, int(bn[s]), b_each, 151 + s * parts + p) for s in range(len(RR)) for p in range(parts)]
+                res = pool.map(_ref_worker, jobs, chunksize=1)
+                keep["reps"] = [np.concatenate([res[s * parts + p][1] for p in range(parts)], axis=1) for s in range(len(RR))]
+                return None
+            sample = (f"{nproc} calls of scaleboot() (unmodified /root/reference/src/makermt.c:35-75 compiled -O2 into "
+                      f"oracle/_ref/libmakermt_ref.so), one per (scale, part), at most {cores} host processes at a time, {b_each} replicates "
+                      "each, matrix in shared memory (no .mt text parse: the file would be "
+                      f"{K * N_SITES * 24 / 1e9:.1f} GB per process)")
         else:
             kind = "port"
-            _, bn, _ = orc.scale_setup(L, RR)
+            nproc = 1
+            parts = 1
 
             def step():
                 orc.makermt(L, bn, [b_each] * len(RR), 7)
-            total_b = b_each * len(RR)
-            nproc = 1
+            sample = f"oracle port (oracle/oracle.c), 1 thread, {b_each} replicates per scale"
+        total_b = b_each * (nproc if kind == "reference" else len(RR))
         for _ in range(min(args.warmup, 1)):
             step()
         t0 = time.perf_counter()
         for _ in range(args.steps):
             step()
         t = time.perf_counter() - t0
-    value = K * N_SITES * total_b * args.steps / t
-    sample = (f"{nproc} `makermt -s SEED -p one_scale.pa` processes, at most {cores} at a time (reference binary, -O2), "
-              f"{b_each} replicates each, same matrix read from a 17-digit .mt text file; wall clock "
-              f"includes process start and text parse") if kind == "reference" else \
-             f"oracle port, 1 thread, {b_each} replicates per scale"
+        value = K * N_SITES * total_b * args.steps / t
+        # ---- the reference's consel on the replicates the sample made (the metric's second half)
+        cexe = orc.ref_bin("consel")
+        try:
+            if cexe is not None and kind == "reference":
+                if use_cli:
+                    subprocess.run([str(orc.ref_bin("catrep") or "catrep"), "--no_sort", "-m"] +
+                                   [f"o{s}_0" for s in range(len(RR))] + ["all"], cwd=td, stdout=subprocess.DEVNULL, check=True)
+                    bsamp = b_each
+                else:
+                    datvec, _, _ = orc.scale_setup(L, RR)
+                    bsamp = keep["reps"][0].shape[1]
+                    orc.write_rmt(td / "all.rmt", datvec, rr1, [bsamp] * len(RR), keep["reps"])
+                t0 = time.perf_counter()
+                subprocess.run([str(cexe), "all"], cwd=td, stdout=subprocess.DEVNULL, check=True, timeout=1500)
+                t_consel = time.perf_counter() - t0
+                t_makermt_full = K * N_SITES * float(c["B_total"]) * len(RR) / value
+                pipe_ref = {"consel_wall_s_at_sample": t_consel, "replicates_per_scale_in_sample": int(bsamp),
+                            "makermt_wall_s_full_size_on_all_cores": t_makermt_full,
+                            "makermt_consel_wall_ms_extrapolated": (t_makermt_full + t_consel * c["B_total"] / bsamp) * 1e3,
+                            "what": "unmodified reference consel (single-threaded, as shipped) on a .rmt of the sampled replicates; "
+                                    "the full-size figure scales both parts linearly in the replicate count (SURVEY 8d)"}
+        except Exception as e:
+            pipe_ref = {"error": f"{type(e).__name__}: {e}"}
+        if not use_cli and kind == "reference":
+            pool.close()
+            shm.close()
+            shm.unlink()
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": t / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+        "warmup": args.warmup, "ms_per_step": t / args.steps * 1e3, "higher_is_better": True, "scaling": c["scaling"],
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic" if name != "C1" else "example/mam15.lnf", "config": cfg,
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": min(cores, nproc) if kind == "reference" else 1, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "pipeline": pipe_ref,
     }))
 
 
@@ -450,6 +682,7 @@ def main() -> None:
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default=DEFAULT_CONFIG, choices=sorted(CONFIGS))
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -18,7 +18,9 @@ from .api import (  # noqa: F401
     SUM_FAST,
     SUM_INT8,
     SUM_STRICT,
+    bench_peaks,
     exported_symbols,
+    kernel_times,
     init,
     last_timing,
     launch_count,

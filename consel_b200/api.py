@@ -100,9 +100,10 @@ def launch_count() -> int:
 
 
 def last_timing() -> dict:
-    ms = (C.c_double * 10)()
-    _check(load().cgpu_last_timing_ex(ms, 10))
-    keys = ("upload", "rng", "resample", "contract", "download", "total", "gemm_i8", "fx_combine", "mt_jump", "mt_draw")
+    ms = (C.c_double * 12)()
+    _check(load().cgpu_last_timing_ex(ms, 12))
+    keys = ("upload", "rng", "resample", "contract", "download", "total", "gemm_i8", "fx_combine", "mt_jump", "mt_draw",
+            "n_gemm", "n_hist")
     return dict(zip(keys, [float(x) for x in ms]))
 
 
@@ -156,6 +157,12 @@ class Matrix:
         _check(load().cgpu_scaleboot_dev(self._h, len(bn), _ip(bn), _ip(bb), C.c_ulong(seed),
                                          C.c_ulonglong(stream_offset), rng_mode, sum_mode, C.byref(h)))
         return Reps(h, self.K, bb)
+
+    def info(self) -> dict:
+        K, n, NP, S, F = (C.c_int() for _ in range(5))
+        mp = C.c_longlong()
+        _check(load().cgpu_matrix_info(self._h, C.byref(K), C.byref(n), C.byref(NP), C.byref(S), C.byref(F), C.byref(mp)))
+        return dict(K=K.value, n=n.value, NP=NP.value, slices=S.value, frac_bits=F.value, mpad=mp.value)
 
     def free(self):
         if self._h:
@@ -218,6 +225,11 @@ class Reps:
         if out is None:
             out = [np.zeros((self.K, nb), dtype=np.float64) for nb in self._local_cols()]
         _check(load().cgpu_reps_download(self._h, _ptr_array(out)))
+        return out
+
+    def download_cols(self, s: int, col0: int, ncols: int) -> np.ndarray:
+        out = np.zeros((self.K, ncols), dtype=np.float64)
+        _check(load().cgpu_reps_download_cols(self._h, int(s), int(col0), int(ncols), _dp(out)))
         return out
 
     def stats_build(self, ass_ptr, ass_idx) -> None:
@@ -296,6 +308,25 @@ class Reps:
             self.free()
         except Exception:
             pass
+
+
+def kernel_times() -> dict:
+    """{kernel: (launches, total_ms, algorithmic work)} recorded since the last call (needs set_option("ktime", 1))."""
+    buf = C.create_string_buffer(1 << 16)
+    _check(load().cgpu_kernel_times(buf, len(buf)))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, cnt, ms, work = line.rsplit(" ", 3)
+        out[name] = (int(cnt), float(ms), float(work))
+    return out
+
+
+def bench_peaks() -> dict:
+    """roofline denominators measured on this device: int8 tcgen05 issue rate, FP64 DFMA rate"""
+    a, b = C.c_double(), C.c_double()
+    _check(load().cgpu_bench_i8_peak(C.byref(a)))
+    _check(load().cgpu_bench_fp64_peak(C.byref(b)))
+    return {"int8_tops": a.value, "fp64_tflops": b.value}
 
 
 def smooth_count(rowsum, B: int, t: float) -> float:

@@ -94,6 +94,12 @@ void PhaseTimer::finish(double *ms) {
             ms[sp.phase] += v;
     }
     ms[1] += ms[8] + ms[9];
+    // slots 10 / 11: how many tensor-core GEMM / histogram launches the call made (bench rooflines)
+    ms[10] = ms[11] = 0;
+    for (int i = 0; i < nspans; i++) {
+        if (spans[i].phase == 6) ms[10] += 1;
+        if (spans[i].phase == 2) ms[11] += 1;
+    }
     (void)cudaGetLastError();
 }
 
@@ -101,15 +107,17 @@ void PhaseTimer::finish(double *ms) {
 struct KSpan {
     std::string name;
     cudaEvent_t a, b;
+    double work;
 };
 static std::vector<KSpan> &kspans() {
     static std::vector<KSpan> v;
     return v;
 }
-KT::KT(const char *name, cudaStream_t s) : st(s) {
+KT::KT(const char *name, cudaStream_t s, double work) : st(s) {
     if (G().opt_ktime != 1) return;
     KSpan sp;
     sp.name = name;
+    sp.work = work;
     cudaEventCreate(&sp.a);
     cudaEventCreate(&sp.b);
     cudaEventRecord(sp.a, st);
@@ -148,6 +156,8 @@ static cudaError_t scratch_get(int slot, size_t bytes, void **out) {
     *out = g.scratch[slot];
     return cudaSuccess;
 }
+
+int lt_prepare(DevMatrix &m, cudaStream_t st);
 
 static void free_reps(DevReps *r) {
     if (!r) return;
@@ -509,19 +519,31 @@ static int scaleboot_core(DevMatrix &m, int S, const int *bn, const int *bb, uns
     int *d_partial = nullptr;  // int32 partial sums of the tensor-core path
 
     if (i8) {
-        pt.begin(0);
-        CGPU_TRY(fx_prepare(m, st));
-        pt.end();
         if ((long long)max_bn * 128 >= (1ll << 31)) {
             set_error(CGPU_ERANGE, "CGPU_SUM_INT8: %d draws per replicate can overflow the int32 accumulators", max_bn);
             return CGPU_ERANGE;
         }
-        cap = std::min<long long>(cap, (long long)(budget / (m.fxMpad * 4)));
         cap = std::max<long long>(256, cap / 256 * 256);
+    } else {
+        CGPU_TRY(lt_prepare(m, st));
     }
     const int align = i8 ? 256 : 64;
+    if (G().opt_batch > 0) cap = std::max<long long>(align, (long long)G().opt_batch / align * align);  // tests: force several batches per scale
     const int batch = (int)std::min<long long>(cap, std::max(align, (max_nb + align - 1) / align * align));
-    if (i8) CGPU_CUDA(scratch_get(3, m.fxMpad * (size_t)batch * sizeof(int), reinterpret_cast<void **>(&d_partial)));
+    // The fixed-point slices of L (and the partial-sum buffer of an unfused recombination) are
+    // prepared right before the FIRST GEMM: the jump tree, the draws and the first histogram do
+    // not read L, so on a host-buffer call they run under the upload of L (copy stream)
+    bool fx_ready = !i8;
+    auto ensure_fx = [&]() -> int {
+        if (fx_ready) return CGPU_OK;
+        pt.begin(0);
+        CGPU_TRY(fx_prepare(m, st));
+        pt.end();
+        if (fx_needs_partial(m, max_bn))
+            CGPU_CUDA(scratch_get(3, m.fxMpad * (size_t)batch * sizeof(int), reinterpret_cast<void **>(&d_partial)));
+        fx_ready = true;
+        return CGPU_OK;
+    };
 
     Workspace ws;
     ws.borrowed = true;
@@ -597,7 +619,10 @@ static int scaleboot_core(DevMatrix &m, int S, const int *bn, const int *bb, uns
         // index stream of the whole call in one buffer when it fits 64 GB and half of the free
         // device memory (C3: 38 GB of uint32 indices); otherwise batch by batch
         unsigned long long idx_budget = (unsigned long long)64 << 30;
-        if (idx_off[S] * idx_bytes((uint32_t)n) > ((unsigned long long)16 << 30)) {  // the query costs ~1 ms: large requests only
+        // (the query takes a driver lock -- a concurrent NVML poller stretches it to milliseconds -- so it is
+        // only made when the index buffer would have to GROW past 16 GB; a buffer that already exists fits)
+        if (idx_off[S] * idx_bytes((uint32_t)n) > ((unsigned long long)16 << 30) &&
+            idx_off[S] * idx_bytes((uint32_t)n) > G().scratch_cap[0]) {
             size_t free_b = 0, total_b = 0;
             if (cudaMemGetInfo(&free_b, &total_b) == cudaSuccess)
                 idx_budget = std::min<unsigned long long>(idx_budget, (free_b + G().scratch_cap[0]) / 2);
@@ -751,6 +776,7 @@ static int scaleboot_core(DevMatrix &m, int S, const int *bn, const int *bb, uns
                 CGPU_CUDA(cudaEventRecord(ws.hist_done[buf], aux));
                 CGPU_CUDA(cudaStreamWaitEvent(st, ws.hist_done[buf], 0));
             }
+            CGPU_TRY(ensure_fx());
             pt.begin(3);
             if (i8)
                 CGPU_TRY(launch_contract_i8(m, fuse_hist ? d_cnt_all + cnt_off[s] : reinterpret_cast<const unsigned char *>(ws.d_counts[buf]), nbat,
@@ -788,7 +814,12 @@ static int scaleboot_core(DevMatrix &m, int S, const int *bn, const int *bb, uns
     return CGPU_OK;
 }
 
-static int matrix_upload(const double *L, int K, int n, DevMatrix **out, cudaStream_t st) {
+// d_L <- L on stream `st`, no host synchronisation (the caller keeps L alive until the stream has
+// passed m->ready).  With a communicator and `collective` set every rank copies only its share of
+// the rows from the host and the ranks all-gather over NVLink: N ranks of one box then pull K*n*8
+// bytes through the host's memory system once, not N times.  The fp64 tile layout (LT) and the
+// fixed-point slices are derived lazily by the modes that need them (lt_prepare / fx_prepare).
+static int matrix_upload(const double *L, int K, int n, DevMatrix **out, cudaStream_t st, bool collective = false) {
     if (!L || K <= 0 || n <= 0) {
         set_error(CGPU_EINVAL, "matrix_upload: K=%d n=%d", K, n);
         return CGPU_EINVAL;
@@ -800,31 +831,61 @@ static int matrix_upload(const double *L, int K, int n, DevMatrix **out, cudaStr
     m->TK = pick_tk(K);
     m->KT = 32 * m->TK;
     m->ktiles = (K + m->KT - 1) / m->KT;
-    int *d_flag = nullptr;
+    const int world = collective && G().opt_dist_upload != 0 ? comm_world() : 1, rank = comm_rank();
+    const int rows_per = (K + world - 1) / world;
     int rc = CGPU_OK;
     auto fail = [&](cudaError_t e, const char *what) {
         set_error(CGPU_ECUDA, "matrix_upload %s: %s", what, cudaGetErrorString(e));
         rc = e == cudaErrorMemoryAllocation ? CGPU_ENOMEM : CGPU_ECUDA;
     };
     cudaError_t e;
-    if ((e = dev_alloc(&m->d_L, (size_t)K * n * sizeof(double))) != cudaSuccess) fail(e, "alloc L");
-    if (!rc && (e = dev_alloc(&m->d_LT, (size_t)m->ktiles * m->NP * m->KT * sizeof(double))) != cudaSuccess) fail(e, "alloc LT");
-    if (!rc && (e = dev_alloc(&d_flag, sizeof(int))) != cudaSuccess) fail(e, "alloc flag");
-    if (!rc && (e = cudaMemsetAsync(d_flag, 0, sizeof(int), st)) != cudaSuccess) fail(e, "memset");
-    if (!rc && (e = cudaMemcpyAsync(m->d_L, L, (size_t)K * n * sizeof(double), cudaMemcpyHostToDevice, st)) != cudaSuccess) fail(e, "H2D");
-    if (!rc) rc = launch_transpose_L(m->d_L, K, n, m->NP, m->TK, m->d_LT, d_flag, st);
-    int h_flag = 0;
-    if (!rc && (e = cudaMemcpyAsync(&h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st)) != cudaSuccess) fail(e, "D2H flag");
-    if (!rc && (e = cudaStreamSynchronize(st)) != cudaSuccess) fail(e, "sync");
-    dev_free(d_flag);
+    if ((e = dev_alloc(&m->d_L, (size_t)rows_per * world * n * sizeof(double))) != cudaSuccess) fail(e, "alloc L");
+    if (!rc && (e = cudaEventCreateWithFlags(&m->ready, cudaEventDisableTiming)) != cudaSuccess) fail(e, "event");
+    if (!rc && st != G().stream) {  // the allocation is ordered on the library stream
+        cudaEvent_t ev;
+        if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) fail(e, "event");
+        if (!rc) {
+            cudaEventRecord(ev, G().stream);
+            cudaStreamWaitEvent(st, ev, 0);
+            cudaEventDestroy(ev);
+        }
+    }
+    if (!rc) {
+        if (world == 1) {
+            if ((e = cudaMemcpyAsync(m->d_L, L, (size_t)K * n * sizeof(double), cudaMemcpyHostToDevice, st)) != cudaSuccess) fail(e, "H2D");
+        } else {
+            const int r0 = std::min(K, rank * rows_per), r1 = std::min(K, r0 + rows_per);
+            double *mine = m->d_L + (size_t)rank * rows_per * n;
+            if (r1 > r0 && (e = cudaMemcpyAsync(mine, L + (size_t)r0 * n, (size_t)(r1 - r0) * n * sizeof(double), cudaMemcpyHostToDevice, st)) != cudaSuccess)
+                fail(e, "H2D");
+            if (!rc) rc = comm_allgather_f64(mine, m->d_L, (size_t)rows_per * n, st);  // in place: rank p's rows land at p*rows_per
+        }
+    }
+    if (!rc && (e = cudaEventRecord(m->ready, st)) != cudaSuccess) fail(e, "record");
     if (rc) {
         dev_free(m->d_L);
-        dev_free(m->d_LT);
+        if (m->ready) cudaEventDestroy(m->ready);
         delete m;
         return rc;
     }
-    m->finite = !h_flag;
     *out = m;
+    return CGPU_OK;
+}
+
+// the fp64 contraction's tile layout of L and the "every entry is finite" flag, on first use
+int lt_prepare(DevMatrix &m, cudaStream_t st) {
+    if (m.d_LT) return CGPU_OK;
+    if (m.ready) CGPU_CUDA(cudaStreamWaitEvent(st, m.ready, 0));
+    int *d_flag = nullptr;
+    CGPU_CUDA(dev_alloc(&m.d_LT, (size_t)m.ktiles * m.NP * m.KT * sizeof(double)));
+    CGPU_CUDA(dev_alloc(&d_flag, sizeof(int)));
+    CGPU_CUDA(cudaMemsetAsync(d_flag, 0, sizeof(int), st));
+    CGPU_TRY(launch_transpose_L(m.d_L, m.K, m.n, m.NP, m.TK, m.d_LT, d_flag, st));
+    int h_flag = 0;
+    CGPU_CUDA(cudaMemcpyAsync(&h_flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CGPU_CUDA(cudaStreamSynchronize(st));
+    dev_free(d_flag);
+    m.finite = !h_flag;
     return CGPU_OK;
 }
 
@@ -983,6 +1044,9 @@ int cgpu_set_option(const char *name, int value) {
     else if (!strcmp(name, "chunk_fill")) g.opt_chunk_fill = value;
     else if (!strcmp(name, "ktime")) g.opt_ktime = value;
     else if (!strcmp(name, "hist_wide")) g.opt_hist_wide = value;
+    else if (!strcmp(name, "i8_2cta")) g.opt_i8_2cta = value;
+    else if (!strcmp(name, "batch")) g.opt_batch = value;
+    else if (!strcmp(name, "dist_upload")) g.opt_dist_upload = value;
     else {
         set_error(CGPU_EINVAL, "unknown option %s", name);
         return CGPU_EINVAL;
@@ -993,7 +1057,11 @@ int cgpu_set_option(const char *name, int value) {
 int cgpu_kernel_times(char *buf, int len) {
     if (!buf || len <= 0) return CGPU_EINVAL;
     cudaDeviceSynchronize();
-    std::map<std::string, std::pair<int, double>> agg;
+    struct Agg {
+        int first = 0;
+        double second = 0, work = 0;
+    };
+    std::map<std::string, Agg> agg;
     std::vector<std::string> order;
     for (auto &sp : kspans()) {
         float ms = 0;
@@ -1001,6 +1069,7 @@ int cgpu_kernel_times(char *buf, int len) {
             if (!agg.count(sp.name)) order.push_back(sp.name);
             agg[sp.name].first++;
             agg[sp.name].second += ms;
+            agg[sp.name].work += sp.work;
         }
         cudaEventDestroy(sp.a);
         cudaEventDestroy(sp.b);
@@ -1010,7 +1079,7 @@ int cgpu_kernel_times(char *buf, int len) {
     int off = 0;
     buf[0] = 0;
     for (auto &n : order) {
-        int w = snprintf(buf + off, (size_t)(len - off), "%s %d %.6f\n", n.c_str(), agg[n].first, agg[n].second);
+        int w = snprintf(buf + off, (size_t)(len - off), "%s %d %.6f %.6e\n", n.c_str(), agg[n].first, agg[n].second, agg[n].work);
         if (w < 0 || w >= len - off) break;
         off += w;
     }
@@ -1046,6 +1115,7 @@ int cgpu_matrix_upload(const double *L, int K, int n, cgpu_matrix **out) {
     if (!out) return CGPU_EINVAL;
     DevMatrix *m = nullptr;
     CGPU_TRY(matrix_upload(L, K, n, &m, G().stream));
+    CGPU_CUDA(cudaStreamSynchronize(G().stream));  // L belongs to the caller again when this returns
     *out = reinterpret_cast<cgpu_matrix *>(m);
     return CGPU_OK;
 }
@@ -1056,6 +1126,7 @@ void cgpu_matrix_free(cgpu_matrix *mm) {
     dev_free(m->d_L);
     dev_free(m->d_LT);
     dev_free(m->d_A8);
+    if (m->ready) cudaEventDestroy(m->ready);
     delete m;
 }
 
@@ -1088,6 +1159,20 @@ int cgpu_reps_download(const cgpu_reps *rr, double *const *rep_out) {
     return reps_download(r, rep_out, G().stream);
 }
 
+int cgpu_reps_download_cols(const cgpu_reps *rr, int s, int col0, int ncols, double *out) {
+    CGPU_TRY(ensure_init());
+    const DevReps *r = reinterpret_cast<const DevReps *>(rr);
+    if (!r || !out || s < 0 || s >= r->S || !r->d_rep || col0 < 0 || ncols < 0 || col0 + ncols > r->nb[s]) {
+        set_error(CGPU_EINVAL, "reps_download_cols: bad arguments");
+        return CGPU_EINVAL;
+    }
+    if (ncols == 0) return CGPU_OK;
+    CGPU_CUDA(cudaMemcpy2DAsync(out, (size_t)ncols * 8, r->d_rep[s] + col0, (size_t)r->nb[s] * 8, (size_t)ncols * 8, r->K,
+                                cudaMemcpyDeviceToHost, G().stream));
+    CGPU_CUDA(cudaStreamSynchronize(G().stream));
+    return CGPU_OK;
+}
+
 unsigned long long cgpu_last_chunk_len(void) { return g_last_chunk_len; }
 
 void cgpu_reps_free(cgpu_reps *rr) { free_reps(reinterpret_cast<DevReps *>(rr)); }
@@ -1112,13 +1197,19 @@ int cgpu_scaleboot_all(const double *L, int K, int n, int S, const int *bn, cons
     cudaStream_t st = G().stream;
     PhaseTimer pt(st);
     DevMatrix *m = nullptr;
-    pt.begin(0);
-    int rc = matrix_upload(L, K, n, &m, st);
+    // int8 mode: the upload runs on the copy stream under the jump tree, the draws and the first
+    // histogram (none of them reads L); with a communicator the ranks share the upload (collective)
+    cudaStream_t up = sum_mode == CGPU_SUM_INT8 ? G().stream3 : st;
+    pt.begin(0, up);
+    int rc = matrix_upload(L, K, n, &m, up, true);
     pt.end();
     DevReps *r = nullptr;
     if (rc == CGPU_OK) rc = alloc_reps(K, S, bb, &r);
     if (rc == CGPU_OK) rc = scaleboot_core(*m, S, bn, bb, seed, stream_offset, rng_mode, sum_mode, r, pt, st, rep_out);
     cudaStreamSynchronize(st);
+    // every exit path: the upload and the device-to-host copies of the copy stream are finished
+    // before the blocks they touch are freed and before the caller gets its buffers back
+    cudaStreamSynchronize(G().stream3);
     pt.finish(G().last_ms);
     free_reps(r);
     cgpu_matrix_free(reinterpret_cast<cgpu_matrix *>(m));

@@ -84,7 +84,7 @@ struct Globals {
     void *scratch[4] = {nullptr, nullptr, nullptr, nullptr};
     size_t scratch_cap[4] = {0, 0, 0, 0};
     // tuning switches (cgpu_set_option); -1 = built-in default
-    int opt_overlap = -1, opt_hist_algo = -1, opt_contract_algo = -1, opt_i8_oneshot = -1, opt_draw_nch = -1, opt_chunk_log2 = -1, opt_i8_fuse = -1, opt_draw_fuse = -1, opt_stage = -1, opt_i8_dbg = -1, opt_mc_smooth = -1, opt_chunk_fill = -1, opt_ktime = -1, opt_hist_wide = -1;
+    int opt_overlap = -1, opt_hist_algo = -1, opt_contract_algo = -1, opt_i8_oneshot = -1, opt_draw_nch = -1, opt_chunk_log2 = -1, opt_i8_fuse = -1, opt_draw_fuse = -1, opt_stage = -1, opt_i8_dbg = -1, opt_mc_smooth = -1, opt_chunk_fill = -1, opt_ktime = -1, opt_hist_wide = -1, opt_i8_2cta = -1, opt_batch = -1, opt_dist_upload = -1;
 };
 Globals &G();
 int ensure_init();
@@ -108,7 +108,8 @@ struct DevMatrix {  // cgpu_matrix
     int K = 0, n = 0, NP = 0, TK = 0, KT = 0, ktiles = 0;
     bool finite = true;
     double *d_L = nullptr;   // K x n row-major (as uploaded)
-    double *d_LT = nullptr;  // [ktiles][NP][KT] site-major tiles, zero padded
+    double *d_LT = nullptr;  // [ktiles][NP][KT] site-major tiles, zero padded (fp64 paths; built on first use)
+    cudaEvent_t ready = nullptr;  // recorded behind the upload of d_L: streams that read it wait on this first
     // CGPU_SUM_INT8 (built lazily by fx_prepare): L = M * 2^-fxF, M = sum_s digit_s * 256^s
     signed char *d_A8 = nullptr;  // [fxMpad][NP] int8 digits, row k*fxS+s
     int fxS = 0, fxF = 0;
@@ -198,6 +199,8 @@ int launch_contract(const DevMatrix &m, const unsigned long long *d_counts, int 
                     double *d_rep, int ldrep, int col0, int sum_mode, cudaStream_t st);
 // i8_kernels.cu
 int fx_prepare(DevMatrix &m, cudaStream_t st);
+// does the tensor-core path need the int32 partial-sum buffer (recombination outside the GEMM epilogue)?
+bool fx_needs_partial(const DevMatrix &m, int max_draws);
 struct PhaseTimer;
 int launch_contract_i8(const DevMatrix &m, const unsigned char *d_counts_rows, int nb, int nb_pad, int *d_partial,
                        double r, double *d_rep, int ldrep, int col0, cudaStream_t st, PhaseTimer *pt = nullptr,
@@ -239,7 +242,8 @@ int comm_reduce_scatter_f64(const double *send, double *recv, size_t recvcount, 
 struct KT {
     int slot = -1;
     cudaStream_t st;
-    KT(const char *name, cudaStream_t s);
+    // work: the launch's ALGORITHMIC bytes (HBM-bound kernels) or fp64 instructions (FP64-bound ones)
+    KT(const char *name, cudaStream_t s, double work = 0.0);
     ~KT();
 };
 

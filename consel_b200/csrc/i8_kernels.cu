@@ -518,6 +518,238 @@ gemm_i8_persistent_kernel(const __grid_constant__ CUtensorMap mapA, const __grid
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * G8_BN) : "memory");
 }
 
+// ------------------------------------------------------------------ 2-CTA GEMM (cta_group::2)
+// The one-CTA kernel above is bound by shared-memory bandwidth, not by the tensor pipe: a
+// 128x256x32 instruction reads 12 KB of operands while TMA writes the next 12 KB, 184 B/clk
+// against the 128 B/clk an SM's shared memory moves, which caps it near 70 % of the int8 issue
+// rate (measured: 0.68).  Here two CTAs of a cluster (one TPC) issue ONE 256x256x32 instruction
+// per step: each CTA stages only its own 128 replicate rows and HALF of the digit rows
+// (16 KB + 16 KB per 128-byte k-block instead of 16 + 32), the hardware shares the digit halves
+// between the two tensor cores.
+//
+// Roles are also swapped with respect to the kernel above: the REPLICATES are the M side (TMEM
+// lanes) and the (tree, digit) rows the N side (TMEM columns), so an epilogue thread owns one
+// replicate and reads the S digits of a tree from consecutive registers -- the exact fold, the
+// single rounding and the division need no shared-memory transpose, and a warp stores 32
+// consecutive replicates of a tree with one coalesced 256-byte store.
+//
+// Protocol (both CTAs run the same code; rank 0 of the cluster is the leader):
+//   producers   each CTA's warp 0 waits on its own empty[s], then issues its two TMA loads with
+//               cta_group::2 completing on the LEADER's full[s]; the leader alone arms full[s]
+//               with the bytes of both CTAs
+//   MMA         the leader's warp 1 issues tcgen05.mma.cta_group::2 and commits (multicast) to
+//               empty[s] of both CTAs, and to acc_full[a] of both CTAs after a tile
+//   epilogue    every epilogue warp of both CTAs drains its own TMEM lanes and arrives on the
+//               LEADER's acc_empty[a] (count 2 x EW)
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address: rank 0's copy
+constexpr size_t G2_OP_BYTES = (size_t)128 * G8_BK;  // one operand tile of a CTA: 128 rows x 128 bytes
+
+template <int STAGES, int EW> struct G2P {
+    static constexpr int threads = 64 + 32 * EW;
+    static constexpr size_t smem = STAGES * 2 * G2_OP_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_2sm(void *dst, const CUtensorMap *map, int c0, int c1, uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            s2u(dst)),
+        "l"(map), "r"(s2u(bar) & PEER_BIT_MASK), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_i8_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t *bar) {  // arrives on `bar` of BOTH CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(s2u(bar)),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ void mb_arrive_leader(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(s2u(bar) & PEER_BIT_MASK) : "memory");
+}
+
+// this thread's replicate b, 32/S trees starting at k0: digits in consecutive registers
+template <int S>
+__device__ __forceinline__ void fx_finish_regs(const uint32_t (&v)[32], int k0, int b, const FxEpilogue &ep) {
+    static_assert(S <= 8, "the fused recombination folds at most two 64-bit groups");
+    constexpr int TREES = 32 / S;
+    double x[TREES];
+#pragma unroll
+    for (int j = 0; j < TREES; j++) {
+        long long g0 = 0, g1 = 0;
+#pragma unroll
+        for (int sdig = (S < 4 ? S : 4) - 1; sdig >= 0; sdig--) g0 = g0 * 256 + (long long)(int)v[j * S + sdig];
+        if (S <= 4) {
+            x[j] = (double)g0 * ep.sc.mul;
+        } else {
+#pragma unroll
+            for (int sdig = S - 1; sdig >= 4; sdig--) g1 = g1 * 256 + (long long)(int)v[j * S + sdig];
+            x[j] = __fma_rn((double)g1, 4294967296.0, (double)g0) * ep.sc.mul;
+        }
+    }
+    if (ep.dbg != 1) {
+#pragma unroll
+        for (int j = 0; j < TREES; j++) x[j] = __ddiv_rn(x[j], ep.r);
+    }
+    if (b < ep.nb) {
+#pragma unroll
+        for (int j = 0; j < TREES; j++)
+            if (k0 + j < ep.K) ep.rep[(size_t)(k0 + j) * ep.ldrep + ep.col0 + b] = x[j];
+    }
+}
+
+// mapC: count rows [nb_pad][NP] (uint8), box 128 rows; mapD: digit rows [Mpad][NP] (int8), box 128 rows.
+// A pair's tile: 256 replicates (ct) x 256 digit rows (dt); digit tiles run fastest so that pairs
+// working at the same time share count rows in L2.  P (unfused path): [p_rows][ldp] int32.
+template <int STAGES, int EW>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EW, 1)
+gemm_i8_2cta_kernel(const __grid_constant__ CUtensorMap mapC, const __grid_constant__ CUtensorMap mapD, int NP,
+                    int *__restrict__ P, int ldp, int p_rows, int c_tiles, int d_tiles, FxEpilogue ep) {
+    extern __shared__ unsigned char g8_raw[];
+    unsigned char *base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(g8_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char *sC = base;
+    unsigned char *sD = base + STAGES * G2_OP_BYTES;
+    uint64_t *full = reinterpret_cast<uint64_t *>(base + STAGES * 2 * G2_OP_BYTES);
+    uint64_t *empty = full + STAGES;
+    uint64_t *acc_full = empty + STAGES;  // [2]
+    uint64_t *acc_empty = acc_full + 2;   // [2] (the leader's copy is the one in use)
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    const int nkb = NP / G8_BK;
+    const int total_tiles = c_tiles * d_tiles;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; s++) {
+            mb_init(&full[s], 1);
+            mb_init(&empty[s], 1);
+        }
+        for (int a = 0; a < 2; a++) {
+            mb_init(&acc_full[a], 1);
+            mb_init(&acc_empty[a], 2 * EW);  // one arrival per epilogue warp of both CTAs
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {  // the same warp of both CTAs allocates the pair's accumulator columns
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s2u(tmem_slot)), "n"(2 * G8_BN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster_sync_all();  // barriers of both CTAs are initialised before anybody signals them
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            int it = 0;  // k-block counter across tiles
+            for (int tile = pair; tile < total_tiles; tile += npairs) {
+                const int row_c = (tile / d_tiles) * 256 + (int)rank * 128;
+                const int row_d = (tile % d_tiles) * 256 + (int)rank * 128;
+                for (int kb = 0; kb < nkb; kb++, it++) {
+                    const int s = it % STAGES;
+                    mb_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
+                    if (leader) mb_expect(&full[s], (uint32_t)(4 * G2_OP_BYTES));  // both operands of both CTAs
+                    tma_load_2d_2sm(sC + s * G2_OP_BYTES, &mapC, kb * G8_BK, row_c, &full[s]);
+                    tma_load_2d_2sm(sD + s * G2_OP_BYTES, &mapD, kb * G8_BK, row_d, &full[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0 && leader) {
+            // instruction descriptor: D=S32, A=unsigned 8 bit (counts), B=signed 8 bit (digits), both K-major, N=256, M=256
+            const uint32_t idesc = (2u << 4) | (0u << 7) | (1u << 10) | ((uint32_t)(256 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+            int it = 0, tcount = 0;
+            for (int tile = pair; tile < total_tiles; tile += npairs, tcount++) {
+                const int acc = tcount & 1;
+                mb_wait(&acc_empty[acc], ((tcount >> 1) & 1) ^ 1);  // both epilogues have drained this accumulator
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t d_tmem = tmem + (uint32_t)(acc * G8_BN);
+                for (int kb = 0; kb < nkb; kb++, it++) {
+                    const int s = it % STAGES;
+                    mb_wait(&full[s], (it / STAGES) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint64_t ad = umma_desc_sw128(sC + s * G2_OP_BYTES), bd = umma_desc_sw128(sD + s * G2_OP_BYTES);
+#pragma unroll
+                    for (int k = 0; k < G8_BK / 32; k++) umma_i8_2sm(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                    umma_commit_2sm(&empty[s]);
+                }
+                umma_commit_2sm(&acc_full[acc]);
+            }
+        }
+    } else {
+        // epilogue warp: TMEM lane quarter q (= warp % 4), column range h of NSPLIT
+        const int q = warp & 3;
+        const int h = (warp - 2) >> 2;
+        constexpr int NSPLIT = EW / 4, NBLK = G8_BN / 32;
+        const int blk_lo = h * NBLK / NSPLIT, blk_hi = (h + 1) * NBLK / NSPLIT;
+        int tcount = 0;
+        for (int tile = pair; tile < total_tiles; tile += npairs, tcount++) {
+            const int acc = tcount & 1;
+            const int b = (tile / d_tiles) * 256 + (int)rank * 128 + q * 32 + lane;  // this thread's replicate (column of the batch)
+            const int n_base = (tile % d_tiles) * 256;                               // first digit row of the tile
+            mb_wait(&acc_full[acc], (tcount >> 1) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+            for (int c = blk_lo * 32; c < blk_hi * 32; c += 32) {
+                uint32_t v[32];
+                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * G8_BN + c);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                      "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                      "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                    : "r"(taddr)
+                    : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (c + 32 == blk_hi * 32) {  // last read of this accumulator by this warp: hand it back to the leader
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) mb_arrive_leader(&acc_empty[acc]);
+                }
+                const int n0 = n_base + c;
+                if (ep.rep == nullptr) {
+                    if (b < ldp) {
+#pragma unroll
+                        for (int i = 0; i < 32; i++)
+                            if (n0 + i < p_rows) P[(size_t)(n0 + i) * ldp + b] = (int)v[i];
+                    }
+                    continue;
+                }
+                if (ep.dbg >= 2) continue;
+                const int k0 = n0 / ep.S;
+                switch (ep.S) {
+                    case 1: fx_finish_regs<1>(v, k0, b, ep); break;
+                    case 2: fx_finish_regs<2>(v, k0, b, ep); break;
+                    case 4: fx_finish_regs<4>(v, k0, b, ep); break;
+                    default: fx_finish_regs<8>(v, k0, b, ep); break;
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster_sync_all();  // the peer may still be reading operands / signalling barriers of this CTA
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * G8_BN) : "memory");
+}
+
 // ------------------------------------------------------------------ measured int8 tensor peak
 // The bare issue rate of tcgen05.mma kind::i8 (M=128, N=256, K=32 per instruction) from operands
 // that already sit in shared memory: no TMA, no epilogue, two accumulator stages alternating like
@@ -624,8 +856,19 @@ static int make_map(CUtensorMap *map, const void *ptr, size_t rows, int NP, int 
     return CGPU_OK;
 }
 
+static bool fx_can_fuse(const DevMatrix &m, int max_draws) {
+    // S <= 8 dividing 8, a scale 2^-F that is a normal double, and group sums that are exact in fp64
+    return m.fxS <= 8 && 8 % m.fxS == 0 && G().opt_i8_fuse != 0 && m.fxF > -1000 && m.fxF < 1000 && max_draws < (1 << 21);
+}
+bool fx_needs_partial(const DevMatrix &m, int max_draws) {
+    static const bool env_one_shot = getenv("CGPU_I8_ONESHOT") != nullptr;
+    const bool one_shot = G().opt_i8_oneshot >= 0 ? G().opt_i8_oneshot != 0 : env_one_shot;
+    return one_shot || !fx_can_fuse(m, max_draws);
+}
+
 int fx_prepare(DevMatrix &m, cudaStream_t st) {
     if (m.d_A8) return CGPU_OK;
+    if (m.ready) CGPU_CUDA(cudaStreamWaitEvent(st, m.ready, 0));  // the upload may still be in flight on the copy stream
     int *d_rng = nullptr;
     CGPU_CUDA(dev_alloc(&d_rng, 3 * sizeof(int)));
     const int init[3] = {1 << 30, -(1 << 30), 0};
@@ -679,11 +922,35 @@ int launch_contract_i8(const DevMatrix &m, const unsigned char *d_counts_rows, i
     // the recombination runs in the GEMM epilogue when the digits of a tree stay inside one
     // 32-row epilogue slab ("i8_fuse" 0 keeps the two-kernel form for measurements)
     // (S <= 8, a scale 2^-F that is a normal double, and group sums that are exact in fp64)
-    const bool fused = !one_shot && m.fxS <= 8 && 8 % m.fxS == 0 && G().opt_i8_fuse != 0 && m.fxF > -1000 && m.fxF < 1000 &&
-                       max_draws < (1 << 21);
+    const bool fused = !one_shot && fx_can_fuse(m, max_draws);
+    if (!fused && !d_partial) {
+        set_error(CGPU_EINVAL, "launch_contract_i8: no partial-sum buffer for the unfused recombination");
+        return CGPU_EINVAL;
+    }
     if (pt) pt->begin(6, st);
     const int m_tiles = (int)(m.fxMpad / G8_BM), n_tiles = nb_pad / G8_BN;
-    if (one_shot) {
+    // cta_group::2 pairs for long tiles; short tiles (C2: 27 k-blocks) are bound by the epilogue's
+    // divisions, where the one-CTA kernel with twelve epilogue warps is faster (measured 2.2 vs 3.0 ms)
+    const bool two_cta = !one_shot && (G().opt_i8_2cta == 1 || (G().opt_i8_2cta != 0 && m.NP / G8_BK > 48)) &&
+                         (G().sm_count % 2 == 0 || G().sm_count <= 0);
+    if (two_cta) {
+        // cta_group::2: replicates on the M side (count rows are operand A), digit rows on N
+        CUtensorMap mapC, mapD;
+        CGPU_TRY(make_map(&mapC, d_counts_rows, (size_t)nb_pad, m.NP, 128));
+        CGPU_TRY(make_map(&mapD, m.d_A8, m.fxMpad, m.NP, 128));
+        static bool attr2_done = false;
+        if (!attr2_done) {
+            CGPU_CUDA(cudaFuncSetAttribute(gemm_i8_2cta_kernel<6, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G2P<6, 8>::smem));
+            attr2_done = true;
+        }
+        const int c_tiles = nb_pad / 256, d_tiles = (int)((m.fxMpad + 255) / 256);
+        const int sms = G().sm_count > 0 ? G().sm_count : 148;
+        const int grid = std::min(sms / 2 * 2, 2 * c_tiles * d_tiles);
+        FxEpilogue ep{fused ? d_rep : nullptr, r, {(m.fxF > -1000 && m.fxF < 1000) ? std::ldexp(1.0, -m.fxF) : 0.0, m.fxF},
+                      m.K, m.fxS, nb, ldrep, col0, G().opt_i8_dbg > 0 ? G().opt_i8_dbg : 0};
+        gemm_i8_2cta_kernel<6, 8><<<grid, G2P<6, 8>::threads, G2P<6, 8>::smem, st>>>(mapC, mapD, m.NP, d_partial, nb_pad, (int)m.fxMpad,
+                                                                                     c_tiles, d_tiles, ep);
+    } else if (one_shot) {
         dim3 grid((unsigned)m_tiles, (unsigned)n_tiles);
         gemm_i8_kernel<<<grid, G8_THREADS, G8_SMEM, st>>>(mapA, mapB, m.NP, d_partial, nb_pad, nb_pad);
     } else {

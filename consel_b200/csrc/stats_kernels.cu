@@ -533,7 +533,9 @@ int launch_rowsum_all_scales(const double *const *d_stat, const int *B, int S, i
         sl.B[s] = B[s];
     }
     const dim3 grid(cm, S, nsplit);
-    KT kt(nq == 1 ? "rowsum_multi_kernel<1>" : "rowsum_multi/sorted_kernel", st);
+    double sumB = 0;
+    for (int sc = 0; sc < S; sc++) sumB += B[sc];
+    KT kt(nq == 1 ? "rowsum_multi_kernel<1>" : "rowsum_multi/sorted_kernel", st, 8.0 * cm * sumB * ((nq + 7) / 8));  // one pass per 8 thresholds
     // more than 8 thresholds per row: two passes of <= 8 (64 registers, 3 CTAs/SM) stream faster
     // than one pass of 16 (204 registers)
 #define CGPU_RSM(NQ_)                                                                                                     \
@@ -565,7 +567,7 @@ int launch_rowsum(int mode, const RowSrc &src, int rows, int B, int nq, const do
         set_error(CGPU_EINVAL, "nq=%d (1..%d)", nq, RS_MAXQ);
         return CGPU_EINVAL;
     }
-    KT kt(mode == 0 ? "rowsum_kernel<plain>" : mode == 1 ? "rowsum_kernel<kh>" : "rowsum_kernel<sh>", st);
+    KT kt(mode == 0 ? "rowsum_kernel<plain>" : mode == 1 ? "rowsum_kernel<kh>" : "rowsum_kernel<sh>", st, (mode == 1 ? 16.0 : 8.0) * rows * B);
     if (mode == 0) rowsum_kernel<0><<<rows, RS_THREADS, 0, st>>>(src, B, nq, d_thr, d_out, out_stride, out_off);
     else if (mode == 1) rowsum_kernel<1><<<rows, RS_THREADS, 0, st>>>(src, B, nq, d_thr, d_out, out_stride, out_off);
     else rowsum_kernel<2><<<rows, RS_THREADS, 0, st>>>(src, B, nq, d_thr, d_out, out_stride, out_off);
@@ -629,7 +631,7 @@ order_stat_kernel(const double *__restrict__ stat, int B, int ld, const int *__r
 int launch_order_stat(const double *d_stat, int rows, int B, int ld, const int *d_rank, double *d_val,
                       cudaStream_t st) {
     if (rows <= 0) return CGPU_OK;
-    KT kt("order_stat_kernel", st);
+    KT kt("order_stat_kernel", st, 8.0 * rows * B);
     order_stat_kernel<<<rows, 256, 0, st>>>(d_stat, B, ld, d_rank, d_val);
     CGPU_LAUNCH_CHECK();
     return CGPU_OK;
@@ -902,7 +904,7 @@ int launch_col_top2(const double *x, int K, int B, int ld, double *m1, double *m
     const int rows_per = (K + ks - 1) / ks;
     ks = (K + rows_per - 1) / rows_per;
     if (ks == 1) {
-        KT kt("col_top2_kernel", st);
+        KT kt("col_top2_kernel", st, 8.0 * K * B);
         col_top2_kernel<<<dim3(tiles, 1), 128, 0, st>>>(x, K, B, ld, rows_per, m1, m2, a1);
         CGPU_LAUNCH_CHECK();
         return CGPU_OK;
@@ -912,7 +914,7 @@ int launch_col_top2(const double *x, int K, int B, int ld, double *m1, double *m
     CGPU_CUDA(dev_alloc(&pm, (size_t)2 * ks * B * sizeof(double)));
     CGPU_CUDA(dev_alloc(&pa, (size_t)ks * B * sizeof(int)));
     {
-        KT kt("col_top2_kernel", st);
+        KT kt("col_top2_kernel", st, 8.0 * K * B);
         col_top2_kernel<<<dim3(tiles, ks), 128, 0, st>>>(x, K, B, ld, rows_per, pm, pm + (size_t)ks * B, pa);
         CGPU_LAUNCH_CHECK();
     }
@@ -929,13 +931,13 @@ int launch_stat_build(const double *x, int K, int B, int ld, const double *m1, c
                       int cm, const int *ass_ptr, const int *ass_idx, double *stat, cudaStream_t st) {
     if (B <= 0 || cm <= 0) return CGPU_OK;
     int gy = std::min(cm, 64);
-    KT kt("stat_build_kernel", st);
+    KT kt("stat_build_kernel", st, 16.0 * cm * B);  // one replicate row read + one statistic row written per item (singleton items)
     stat_build_kernel<<<dim3((B + 127) / 128, gy), 128, 0, st>>>(x, K, B, ld, m1, m2, a1, cm, ass_ptr, ass_idx, stat);
     CGPU_LAUNCH_CHECK();
     return CGPU_OK;
 }
 int launch_center(const double *x, int K, int B, int ld, double *xc, cudaStream_t st, bool rescale, double rs) {
-    KT kt("center_rows_kernel", st);
+    KT kt("center_rows_kernel", st, 16.0 * K * B);
     center_rows_kernel<<<(K + 3) / 4, 128, 0, st>>>(x, K, B, ld, xc, rescale, rs);
     CGPU_LAUNCH_CHECK();
     return CGPU_OK;
@@ -945,7 +947,7 @@ int launch_pair_weight(const double *xc, int K, int B, int ld, double varadd, do
     int t = (K + PV_T - 1) / PV_T;
     const int ty = d_rows ? (nrows + PV_T - 1) / PV_T : t;
     if (ty <= 0) return CGPU_OK;
-    KT kt("pair_weight_kernel", st);
+    KT kt("pair_weight_kernel", st, 3.0 * B * (d_rows ? (double)nrows * (K - 1) : 0.5 * K * (K - 1)));  // (sub, mul, add) per pair and replicate
     pair_weight_kernel<<<dim3(t, ty), PV_T * PV_T, 0, st>>>(xc, K, B, ld, varadd, wt, nsmall, d_rows, nrows);
     CGPU_LAUNCH_CHECK();
     return CGPU_OK;
@@ -953,7 +955,7 @@ int launch_pair_weight(const double *xc, int K, int B, int ld, double varadd, do
 int launch_wsh_single(const double *x, int K, int B, int ld, const double *wt, const int *mem_tree, int nmem, double *out,
                       cudaStream_t st) {
     if (nmem <= 0 || B <= 0) return CGPU_OK;
-    KT kt("wsh_single_kernel", st);
+    KT kt("wsh_single_kernel", st, 3.0 * B * (double)nmem * (K - 1));  // (sub, mul, compare) per (member, other tree, replicate)
     wsh_single_kernel<<<dim3((B + 127) / 128, (nmem + WS_MI - 1) / WS_MI), 128, 0, st>>>(x, K, B, ld, wt, mem_tree, nmem, out);
     CGPU_LAUNCH_CHECK();
     return CGPU_OK;
@@ -973,7 +975,7 @@ int launch_weighted_obs(const double *dat, int K, const double *wt, int nmem, co
                         const int *mem_tree, const int *cass_ptr, const int *cass_idx, double *obs, int *argj,
                         cudaStream_t st) {
     if (nmem <= 0) return CGPU_OK;
-    KT kt("weighted_obs_kernel", st);
+    KT kt("weighted_obs_kernel", st, 0.0);
     weighted_obs_kernel<<<(nmem + 127) / 128, 128, 0, st>>>(dat, K, wt, nmem, mem_item, mem_tree, cass_ptr, cass_idx, obs, argj);
     CGPU_LAUNCH_CHECK();
     return CGPU_OK;

@@ -96,6 +96,9 @@ int cgpu_scaleboot_dev(const cgpu_matrix *m, int S, const int *bn, const int *bb
                        unsigned long long stream_offset, int rng_mode, int sum_mode, cgpu_reps **out);
 /* copy this rank's replicate columns into rep_out[s] (compact K x nb[s], see above) */
 int cgpu_reps_download(const cgpu_reps *r, double *const *rep_out);
+/* columns [col0, col0+ncols) of this rank's block of scale s -> out (K x ncols, row-major):
+ * spot checks of a large resident result without downloading all of it                      */
+int cgpu_reps_download_cols(const cgpu_reps *r, int s, int col0, int ncols, double *out);
 void cgpu_reps_free(cgpu_reps *r);
 
 /* Test/diagnostic seam: site-count matrix of scale s as the resampler produced it,
@@ -224,14 +227,17 @@ int cgpu_count_query_dist(const cgpu_reps *r, int all_rows, int nq, const double
  * [6] tensor-core GEMM only, [7] fixed-point recombination only (CGPU_SUM_INT8).   */
 int cgpu_last_timing(double *ms8);
 /* the same slots followed by finer ones: [8] MT19937 jump tree, [9] MT19937 draw kernel
- * ([1] is their sum); slots past the last defined one read 0                          */
+ * ([1] is their sum), [10] / [11] the number of tensor-core GEMM / histogram launches; slots past
+ * the last defined one read 0                          */
 int cgpu_last_timing_ex(double *ms, int n);
 /* Tuning switches (development / measurement): "overlap" 0|1 (two-stream pipeline of
  * resampling and contraction), "hist_algo" 0|1|2, "contract_algo" -1|0|1|2,
  * "i8_oneshot" 0|1, "i8_fuse" 0|1 (recombination in the GEMM epilogue), "draw_nch" 1|2|3,
  * "draw_fuse" 0|1 (draws + histograms in one kernel, int8 mode, opt-in), "stage" 0|1 (staged
  * index production of host-output int8 calls: 0 off, 1 always, default by size),
- * "chunk_log2" 10..30 (force a power-of-two chunk of the MT19937 jump tree), "chunk_fill" 0|1|2
+ * "hist_wide" 0|1 (one replicate per CTA
+ * on long alignments), "i8_2cta" 0|1 (cta_group::2 GEMM, default on), "batch" N (replicates per
+ * GEMM batch, tests), "ktime" 0|1 (per-kernel events, see cgpu_kernel_times), "chunk_log2" 10..30 (force a power-of-two chunk of the MT19937 jump tree), "chunk_fill" 0|1|2
  * (equal-fill chunk lengths that are not powers of two: off, by cost model (default), forced), "i8_dbg" 0..3 (switches parts of the GEMM epilogue off: timing only,
  * results are wrong), "mc_smooth" 0|1 (0 = consel --quick_mctest: the KH/SH p-values of
  * cgpu_mctest use the plain count #{v<=t} instead of the smoothed one, sw_pvaldist
@@ -241,7 +247,8 @@ int cgpu_last_timing_ex(double *ms, int n);
 int cgpu_set_option(const char *name, int value);
 /* With cgpu_set_option("ktime", 1) every kernel launch of the consel side (statistics, count
  * queries, order statistics, KH/SH tests) is bracketed by CUDA events; this call synchronises the
- * device, writes one line "kernel_name launches total_ms" per kernel into buf and clears the
+ * device, writes one line "kernel_name launches total_ms algorithmic_work" (bytes for the streaming kernels,
+ * fp64 instructions for the FP64-bound ones, summed over the launches) per kernel into buf and clears the
  * record (bench.py's per-kernel rooflines).                                              */
 int cgpu_kernel_times(char *buf, int len);
 /* shape of an uploaded matrix; slices/frac_bits/mpad describe the fixed-point split of
