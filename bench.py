@@ -230,6 +230,7 @@ def run_ours(args) -> None:
     else:
         cg.set_shard(0, 1)
 
+    live = cg.bench_peaks()  # burst int8 / fp64 rates, measured on the idle device before the workload heats it
     name = args.config
     c = workload(name, world)
     K, N_SITES = c["K"], c["n"]
@@ -385,7 +386,7 @@ def run_ours(args) -> None:
         return
 
     # ---- rooflines, measured live: every kernel of the step with its own bound
-    live = cg.bench_peaks()
+    live.update({k_: v for k_, v in cg.bench_peaks(sustained_seconds=2.0).items() if k_ == "int8_tops_sustained"})
     peaks = {}
     try:
         peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
@@ -393,7 +394,10 @@ def run_ours(args) -> None:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     peak_src = "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"
-    i8_peak = live["int8_tops"]
+    # a tensor-bound kernel inside a long step runs at the clock the power limit allows: grade it against the
+    # sustained rate there (B200_PROFILING.md), against the burst rate when the steps are short
+    long_step = dev_ms / args.steps > 50.0
+    i8_peak = live["int8_tops_sustained"] if long_step else live["int8_tops"]
     fp64_peak = live["fp64_tflops"]
     traffic_db = {}
     tp = ROOT / "profiles" / "kernel_traffic.json"
@@ -445,8 +449,9 @@ def run_ours(args) -> None:
               "recombination + rounding + /r fused into the epilogue)", phases["gemm_i8"], gemm_launches, "tensor",
               2.0 * S_SLICES * K * N_SITES * b_loc * nS / gemm_launches, i8_peak, "TOP/s (int8)",
               f"2*S int8-ops per tree-site accumulation (SURVEY 8d), S={S_SLICES} slices, x K*n*B_s per launch",
-              "peak = cgpu_bench_i8_peak: tcgen05.mma kind::i8 issue rate from smem-resident operands, measured in this run "
-              "(a burst figure at full clocks)"),
+              "peak = tcgen05.mma kind::i8 issue rate from smem-resident operands measured in this run: "
+              + ("cgpu_bench_i8_peak_sustained (2 s back to back: the step is long and the board power-caps)" if long_step
+                 else "cgpu_bench_i8_peak (burst, idle device: the steps are short)")),
         entry("fx_combine_kernel", "fx_combine_kernel (exact int128 recombination of the S slice sums, one rounding, /r)",
               phases["fx_combine"], nS, "hbm", 4.0 * M_PAD * b_loc + 8.0 * K * b_loc, hbm_peak, "GB/s",
               "4 B x Mpad int32 partial sums read + 8 B x K doubles written per replicate"),
@@ -490,7 +495,11 @@ def run_ours(args) -> None:
     roofline = dict(dominant)
     roofline["peak_source"] = peak_src + " (HBM); int8 and fp64 peaks measured live by cgpu_bench_i8_peak / cgpu_bench_fp64_peak"
     roofline["step_shares"] = {k_: v / total_ms for k_, v in phases.items() if k_ not in ("total", "rng")}
-    roofline["int8_peak_tops_measured_live"] = i8_peak
+    roofline["int8_peak_tops_measured_live"] = {"burst": live["int8_tops"], "sustained_2s": live["int8_tops_sustained"], "used": i8_peak}
+    for e_ in kernels:
+        if e_["kernel"].startswith("gemm_i8"):
+            e_["frac_of_burst_peak"] = e_["achieved"] / live["int8_tops"]
+            e_["frac_of_sustained_peak"] = e_["achieved"] / live["int8_tops_sustained"]
     roofline["fp64_dfma_peak_tflops_measured_live"] = fp64_peak
     floor_ms = 2.0 * S_SLICES * K * N_SITES * b_loc * nS / (i8_peak * 1e12) * 1e3
     roofline["step"] = {"floor_ms": floor_ms, "ms_per_step": dev_ms / args.steps, "frac": floor_ms / (dev_ms / args.steps),
@@ -570,22 +579,23 @@ def run_reference(args) -> None:
     cfg = config_json(name, c, max(world, args.gpus))
     _, bn, rr1 = orc.scale_setup(L, RR)
     use_cli = exe is not None and K * N_SITES <= 2_000_000
-    # one job ~ 6-10 s of one core at ~1.5e9 acc/s
-    parts = max(1, -(-2 * cores // len(RR))) if cores > len(RR) else 1
-    nproc = len(RR) * parts
-    b_each = max(2, int(9e9 / (K * N_SITES)))
+    # one job per host core (at least one per scale), job j on scale j % 10; a job is ~6 s of one core, so a
+    # step is one round of ~6-9 s and the driver's --steps 20 run stays within a few minutes
+    nproc = max(len(RR), cores)
+    parts = -(-nproc // len(RR))
+    jobs_sp = [(j % len(RR), j // len(RR)) for j in range(nproc)]
+    b_each = max(2, int((6e9 if K * N_SITES > 2_000_000 else 9e9) / (K * N_SITES)))
     pipe_ref = None
     with tempfile.TemporaryDirectory(prefix="consel_ref_") as td:
         td = Path(td)
         if use_cli:
             kind = "reference"
             orc.write_mt(td / "in.mt", L)
-            for s, r in enumerate(RR):
-                for p in range(parts):
-                    orc.write_pa(td / f"p{s}_{p}.pa", [r], [b_each])
+            for s_, p in jobs_sp:
+                orc.write_pa(td / f"p{s_}_{p}.pa", [RR[s_]], [b_each])
 
             def step():
-                jobs = [(s, p) for s in range(len(RR)) for p in range(parts)]
+                jobs = list(jobs_sp)
                 running = []
                 while jobs or running:
                     while jobs and len(running) < cores:
@@ -615,9 +625,9 @@ def run_reference(args) -> None:
             keep = {}
 
             def step():
-                jobs = [(str(so), shm.name, K, N_SITES, int(bn[s]), b_each, 151 + s * parts + p) for s in range(len(RR)) for p in range(parts)]
+                jobs = [(str(so), shm.name, K, N_SITES, int(bn[s_]), b_each, 151 + s_ * parts + p) for s_, p in jobs_sp]
                 res = pool.map(_ref_worker, jobs, chunksize=1)
-                keep["reps"] = [np.concatenate([res[s * parts + p][1] for p in range(parts)], axis=1) for s in range(len(RR))]
+                keep["reps"] = [res[s_][1] for s_ in range(len(RR))]  # part 0 of every scale: the consel sample
                 return None
             sample = (f"{nproc} calls of scaleboot() (unmodified /root/reference/src/makermt.c:35-75 compiled -O2 into "
                       f"oracle/_ref/libmakermt_ref.so), one per (scale, part), at most {cores} host processes at a time, {b_each} replicates "

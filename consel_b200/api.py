@@ -159,10 +159,10 @@ class Matrix:
         return Reps(h, self.K, bb)
 
     def info(self) -> dict:
-        K, n, NP, S, F = (C.c_int() for _ in range(5))
+        K, n, NP, S, F, P = (C.c_int() for _ in range(6))
         mp = C.c_longlong()
-        _check(load().cgpu_matrix_info(self._h, C.byref(K), C.byref(n), C.byref(NP), C.byref(S), C.byref(F), C.byref(mp)))
-        return dict(K=K.value, n=n.value, NP=NP.value, slices=S.value, frac_bits=F.value, mpad=mp.value)
+        _check(load().cgpu_matrix_info(self._h, C.byref(K), C.byref(n), C.byref(NP), C.byref(S), C.byref(F), C.byref(mp), C.byref(P)))
+        return dict(K=K.value, n=n.value, NP=NP.value, slices=S.value, frac_bits=F.value, mpad=mp.value, patterns=P.value)
 
     def free(self):
         if self._h:
@@ -321,12 +321,17 @@ def kernel_times() -> dict:
     return out
 
 
-def bench_peaks() -> dict:
-    """roofline denominators measured on this device: int8 tcgen05 issue rate, FP64 DFMA rate"""
-    a, b = C.c_double(), C.c_double()
+def bench_peaks(sustained_seconds: float = 0.0) -> dict:
+    """roofline denominators measured on this device: int8 tcgen05 issue rate (burst, and back to back
+    for `sustained_seconds` when given), FP64 DFMA rate"""
+    a, b, c = C.c_double(), C.c_double(), C.c_double()
     _check(load().cgpu_bench_i8_peak(C.byref(a)))
     _check(load().cgpu_bench_fp64_peak(C.byref(b)))
-    return {"int8_tops": a.value, "fp64_tflops": b.value}
+    out = {"int8_tops": a.value, "fp64_tflops": b.value}
+    if sustained_seconds > 0:
+        _check(load().cgpu_bench_i8_peak_sustained(C.c_double(sustained_seconds), C.byref(c)))
+        out["int8_tops_sustained"] = c.value
+    return out
 
 
 def smooth_count(rowsum, B: int, t: float) -> float:

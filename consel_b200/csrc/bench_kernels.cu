@@ -20,6 +20,7 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters, 
 }
 
 int bench_i8_peak(double *tops, cudaStream_t st);  // i8_kernels.cu
+int bench_i8_peak_sustained(double seconds, double *tops, cudaStream_t st);
 
 }  // namespace cgpu
 
@@ -30,6 +31,13 @@ extern "C" int cgpu_bench_i8_peak(double *tops) {
     CGPU_TRY(ensure_init());
     if (!tops) return CGPU_EINVAL;
     return bench_i8_peak(tops, G().stream);
+}
+
+extern "C" int cgpu_bench_i8_peak_sustained(double seconds, double *tops) {
+    using namespace cgpu;
+    CGPU_TRY(ensure_init());
+    if (!tops || !(seconds > 0) || seconds > 30) return CGPU_EINVAL;
+    return bench_i8_peak_sustained(seconds, tops, G().stream);
 }
 
 extern "C" int cgpu_bench_fp64_peak(double *tflops) {

@@ -499,7 +499,8 @@ static int scaleboot_core(DevMatrix &m, int S, const int *bn, const int *bb, uns
             set_error(CGPU_EINVAL, "scale %d: bn=%d bb=%d", s, bn[s], bb[s]);
             return CGPU_EINVAL;
         }
-    const int n = m.n, NP = m.NP;
+    const int n = m.n;
+    int NP = m.NP;  // length of a count row (the int8 path may shorten it to the pattern slots, below)
     // batch size: bound the index and count buffers (device memory is 180 GB; keep the
     // workspace near 8 GB so several processes can share a GPU in tests)
     const size_t budget = (size_t)4 << 30;
@@ -530,20 +531,31 @@ static int scaleboot_core(DevMatrix &m, int S, const int *bn, const int *bb, uns
     const int align = i8 ? 256 : 64;
     if (G().opt_batch > 0) cap = std::max<long long>(align, (long long)G().opt_batch / align * align);  // tests: force several batches per scale
     const int batch = (int)std::min<long long>(cap, std::max(align, (max_nb + align - 1) / align * align));
-    // The fixed-point slices of L (and the partial-sum buffer of an unfused recombination) are
-    // prepared right before the FIRST GEMM: the jump tree, the draws and the first histogram do
-    // not read L, so on a host-buffer call they run under the upload of L (copy stream)
+    // The fixed-point slices of L (and the partial-sum buffer of an unfused recombination) are prepared
+    // right before the FIRST GEMM when the matrix is still on its way to the device (a large host-buffer
+    // call): the jump tree, the draws and the first histogram do not read L, so they run under the
+    // upload.  Otherwise (resident matrix, or a small one) they are prepared up front, and identical
+    // columns of L are looked for: with pattern slots the count rows and the GEMM get shorter.
     bool fx_ready = !i8;
+    const bool fx_early = i8 && (!host_out || (size_t)m.K * (size_t)n <= ((size_t)8 << 20));
+    const bool allow_patterns = fx_early && (double)max_bn <= 4.0 * (double)n && G().opt_draw_fuse != 1;
     auto ensure_fx = [&]() -> int {
         if (fx_ready) return CGPU_OK;
         pt.begin(0);
-        CGPU_TRY(fx_prepare(m, st));
+        CGPU_TRY(fx_prepare(m, st, allow_patterns));
         pt.end();
         if (fx_needs_partial(m, max_bn))
             CGPU_CUDA(scratch_get(3, m.fxMpad * (size_t)batch * sizeof(int), reinterpret_cast<void **>(&d_partial)));
         fx_ready = true;
         return CGPU_OK;
     };
+    if (fx_early) {
+        CGPU_TRY(ensure_fx());
+        NP = m.NPc;
+    } else if (i8 && m.d_A8 && m.npat > 0) {
+        CGPU_TRY(ensure_fx());  // (re-slices uncompressed: this call cannot use the slots)
+    }
+    const unsigned int *pid = (i8 && m.npat > 0) ? m.d_pid : nullptr;
 
     Workspace ws;
     ws.borrowed = true;
@@ -765,11 +777,11 @@ static int scaleboot_core(DevMatrix &m, int S, const int *bn, const int *bb, uns
                     pt.end();
                 }
                 pt.begin(2, aux);
-                CGPU_TRY(launch_hist_from_idx(idx_src, n, NP, bn[s], nbat, ws.d_counts[buf], ws.d_err, aux, i8));
+                CGPU_TRY(launch_hist_from_idx(idx_src, n, NP, bn[s], nbat, ws.d_counts[buf], ws.d_err, aux, i8, pid));
                 pt.end();
             } else {
                 pt.begin(2, aux);
-                CGPU_TRY(launch_hist_philox((unsigned long long)seed, s, bA, n, NP, bn[s], nbat, ws.d_counts[buf], ws.d_err, aux, i8, stream_offset));
+                CGPU_TRY(launch_hist_philox((unsigned long long)seed, s, bA, n, NP, bn[s], nbat, ws.d_counts[buf], ws.d_err, aux, i8, stream_offset, pid));
                 pt.end();
             }
             if (overlap) {
@@ -1046,6 +1058,8 @@ int cgpu_set_option(const char *name, int value) {
     else if (!strcmp(name, "hist_wide")) g.opt_hist_wide = value;
     else if (!strcmp(name, "i8_2cta")) g.opt_i8_2cta = value;
     else if (!strcmp(name, "batch")) g.opt_batch = value;
+    else if (!strcmp(name, "i8_panel")) g.opt_i8_panel = value;
+    else if (!strcmp(name, "i8_patterns")) g.opt_i8_patterns = value;
     else if (!strcmp(name, "dist_upload")) g.opt_dist_upload = value;
     else {
         set_error(CGPU_EINVAL, "unknown option %s", name);
@@ -1086,7 +1100,7 @@ int cgpu_kernel_times(char *buf, int len) {
     return CGPU_OK;
 }
 
-int cgpu_matrix_info(const cgpu_matrix *mm, int *K, int *n, int *NP, int *slices, int *frac_bits, long long *mpad) {
+int cgpu_matrix_info(const cgpu_matrix *mm, int *K, int *n, int *NP, int *slices, int *frac_bits, long long *mpad, int *patterns) {
     const DevMatrix *m = reinterpret_cast<const DevMatrix *>(mm);
     if (!m) return CGPU_EINVAL;
     if (K) *K = m->K;
@@ -1095,6 +1109,7 @@ int cgpu_matrix_info(const cgpu_matrix *mm, int *K, int *n, int *NP, int *slices
     if (slices) *slices = m->fxS;
     if (frac_bits) *frac_bits = m->fxF;
     if (mpad) *mpad = (long long)m->fxMpad;
+    if (patterns) *patterns = m->npat;
     return CGPU_OK;
 }
 
@@ -1126,6 +1141,7 @@ void cgpu_matrix_free(cgpu_matrix *mm) {
     dev_free(m->d_L);
     dev_free(m->d_LT);
     dev_free(m->d_A8);
+    dev_free(m->d_pid);
     if (m->ready) cudaEventDestroy(m->ready);
     delete m;
 }

@@ -84,7 +84,7 @@ struct Globals {
     void *scratch[4] = {nullptr, nullptr, nullptr, nullptr};
     size_t scratch_cap[4] = {0, 0, 0, 0};
     // tuning switches (cgpu_set_option); -1 = built-in default
-    int opt_overlap = -1, opt_hist_algo = -1, opt_contract_algo = -1, opt_i8_oneshot = -1, opt_draw_nch = -1, opt_chunk_log2 = -1, opt_i8_fuse = -1, opt_draw_fuse = -1, opt_stage = -1, opt_i8_dbg = -1, opt_mc_smooth = -1, opt_chunk_fill = -1, opt_ktime = -1, opt_hist_wide = -1, opt_i8_2cta = -1, opt_batch = -1, opt_dist_upload = -1;
+    int opt_overlap = -1, opt_hist_algo = -1, opt_contract_algo = -1, opt_i8_oneshot = -1, opt_draw_nch = -1, opt_chunk_log2 = -1, opt_i8_fuse = -1, opt_draw_fuse = -1, opt_stage = -1, opt_i8_dbg = -1, opt_mc_smooth = -1, opt_chunk_fill = -1, opt_ktime = -1, opt_hist_wide = -1, opt_i8_2cta = -1, opt_batch = -1, opt_dist_upload = -1, opt_i8_panel = -1, opt_i8_patterns = -1;
 };
 Globals &G();
 int ensure_init();
@@ -114,6 +114,12 @@ struct DevMatrix {  // cgpu_matrix
     signed char *d_A8 = nullptr;  // [fxMpad][NP] int8 digits, row k*fxS+s
     int fxS = 0, fxF = 0;
     size_t fxMpad = 0;
+    // site-pattern compression of the int8 path: identical columns of L (PAML-style inputs:
+    // mam15 has 1054 distinct columns of 3414) share ONE column of A8, the histogram counts into pattern
+    // slots.  The integer sums are exact, so the result is bit-identical to the uncompressed contraction.
+    int npat = 0;                  // pattern slots (0: no compression)
+    int NPc = 0;                   // inner dimension of the GEMM: pad_sites(npat), or NP
+    unsigned int *d_pid = nullptr; // [n] site -> slot
 };
 
 struct DevReps {  // cgpu_reps
@@ -185,11 +191,13 @@ int launch_mt_draw_range(const MtPlan &mt, unsigned long long lo, unsigned long 
 // resample_kernels.cu
 // counts layout: rows == false -> "BJ8" words (8 replicates interleaved per site);
 //                rows == true  -> plain uint8 rows [replicate][NP] (tensor-core operand)
+// pid (optional, byte rows only): site -> pattern slot table; NP is then the padded slot count
 int launch_hist_from_idx(const void *d_idx, int n, int NP, int bn, int nb,
-                         unsigned long long *d_counts, int *d_err, cudaStream_t st, bool rows = false);
+                         unsigned long long *d_counts, int *d_err, cudaStream_t st, bool rows = false,
+                         const unsigned int *pid = nullptr);
 int launch_hist_philox(unsigned long long seed, int scale, int b_first, int n, int NP, int bn, int nb,
                        unsigned long long *d_counts, int *d_err, cudaStream_t st, bool rows = false,
-                       unsigned long long stream_offset = 0);
+                       unsigned long long stream_offset = 0, const unsigned int *pid = nullptr);
 int launch_counts_unpack(const unsigned long long *d_counts, int n, int NP, int nb,
                          unsigned char *d_out, cudaStream_t st);
 // contract_kernels.cu
@@ -198,7 +206,9 @@ int launch_transpose_L(const double *d_L, int K, int n, int NP, int TK, double *
 int launch_contract(const DevMatrix &m, const unsigned long long *d_counts, int nb, double r,
                     double *d_rep, int ldrep, int col0, int sum_mode, cudaStream_t st);
 // i8_kernels.cu
-int fx_prepare(DevMatrix &m, cudaStream_t st);
+// allow_patterns: look for identical columns and compress (a matrix prepared compressed is re-sliced
+// uncompressed when a later call cannot use the compression)
+int fx_prepare(DevMatrix &m, cudaStream_t st, bool allow_patterns = false);
 // does the tensor-core path need the int32 partial-sum buffer (recombination outside the GEMM epilogue)?
 bool fx_needs_partial(const DevMatrix &m, int max_draws);
 struct PhaseTimer;

@@ -29,6 +29,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <unordered_map>
+#include <vector>
 
 #include "cgpu_internal.h"
 
@@ -68,13 +70,15 @@ fx_scan_kernel(const double *__restrict__ L, size_t count, int *__restrict__ out
     }
 }
 
-// A[(k*S+s)*NP + j] = digit s of M = L[k][j]*2^F; rows >= K*S and sites >= n stay zero
+// A[(k*S+s)*NP + j] = digit s of M = L[k][col(j)]*2^F, col(j) = rep[j] (pattern slots) or j; ncols columns;
+// rows >= K*S and columns >= ncols stay zero
 __global__ void __launch_bounds__(256)
-fx_slice_kernel(const double *__restrict__ L, int K, int n, int NP, int S, int F, signed char *__restrict__ A) {
-    const size_t total = (size_t)K * n;
+fx_slice_kernel(const double *__restrict__ L, int K, int n, int ncols, const unsigned int *__restrict__ rep, int NP, int S, int F,
+                signed char *__restrict__ A) {
+    const size_t total = (size_t)K * ncols;
     for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
-        const int k = (int)(e / n), j = (int)(e % n);
-        const unsigned long long u = (unsigned long long)__double_as_longlong(L[e]);
+        const int k = (int)(e / ncols), j = (int)(e % ncols);
+        const unsigned long long u = (unsigned long long)__double_as_longlong(L[(size_t)k * n + (rep ? rep[j] : (unsigned int)j)]);
         const int ex = (int)((u >> 52) & 0x7ff);
         unsigned long long m = u & 0xfffffffffffffull;
         int e2 = -1074;
@@ -581,6 +585,24 @@ __device__ __forceinline__ void mb_arrive_leader(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(s2u(bar) & PEER_BIT_MASK) : "memory");
 }
 
+// Tile order of the pair kernel.  The ~74 pairs that run at the same time sweep the site axis
+// roughly in step, so every operand byte is fetched from HBM once per WAVE that uses it: a wave
+// should be a near-square patch of the tile grid.  Panels of G2_PANEL count-tile columns are
+// walked digit-tile by digit-tile (panel width 8: 74 consecutive tiles cover 8 x ~9 (17 operand tiles per
+// wave instead of 75 with a plain row-major order: at C5 that is 0.36 instead of 1.6 TB per step).
+__device__ __forceinline__ void g2_tile_coords(int tile, int c_tiles, int d_tiles, int pw, int &ct, int &dt) {
+    if (pw <= 0) {  // plain order, digit tiles fastest ("i8_panel" 0: measurement)
+        ct = tile / d_tiles;
+        dt = tile - ct * d_tiles;
+        return;
+    }
+    const int per_panel = pw * d_tiles;
+    const int panel = tile / per_panel, rem = tile - panel * per_panel;
+    const int width = min(pw, c_tiles - panel * pw);
+    dt = rem / width;
+    ct = panel * pw + (rem - dt * width);
+}
+
 // this thread's replicate b, 32/S trees starting at k0: digits in consecutive registers
 template <int S>
 __device__ __forceinline__ void fx_finish_regs(const uint32_t (&v)[32], int k0, int b, const FxEpilogue &ep) {
@@ -612,12 +634,12 @@ __device__ __forceinline__ void fx_finish_regs(const uint32_t (&v)[32], int k0, 
 }
 
 // mapC: count rows [nb_pad][NP] (uint8), box 128 rows; mapD: digit rows [Mpad][NP] (int8), box 128 rows.
-// A pair's tile: 256 replicates (ct) x 256 digit rows (dt); digit tiles run fastest so that pairs
-// working at the same time share count rows in L2.  P (unfused path): [p_rows][ldp] int32.
+// A pair's tile: 256 replicates (ct) x 256 digit rows (dt), visited in the order of g2_tile_coords.
+// P (unfused path): [p_rows][ldp] int32.
 template <int STAGES, int EW>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EW, 1)
 gemm_i8_2cta_kernel(const __grid_constant__ CUtensorMap mapC, const __grid_constant__ CUtensorMap mapD, int NP,
-                    int *__restrict__ P, int ldp, int p_rows, int c_tiles, int d_tiles, FxEpilogue ep) {
+                    int *__restrict__ P, int ldp, int p_rows, int c_tiles, int d_tiles, int panel_w, FxEpilogue ep) {
     extern __shared__ unsigned char g8_raw[];
     unsigned char *base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(g8_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char *sC = base;
@@ -659,8 +681,10 @@ gemm_i8_2cta_kernel(const __grid_constant__ CUtensorMap mapC, const __grid_const
         if (lane == 0) {
             int it = 0;  // k-block counter across tiles
             for (int tile = pair; tile < total_tiles; tile += npairs) {
-                const int row_c = (tile / d_tiles) * 256 + (int)rank * 128;
-                const int row_d = (tile % d_tiles) * 256 + (int)rank * 128;
+                int ct, dt;
+                g2_tile_coords(tile, c_tiles, d_tiles, panel_w, ct, dt);
+                const int row_c = ct * 256 + (int)rank * 128;
+                const int row_d = dt * 256 + (int)rank * 128;
                 for (int kb = 0; kb < nkb; kb++, it++) {
                     const int s = it % STAGES;
                     mb_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
@@ -701,8 +725,10 @@ gemm_i8_2cta_kernel(const __grid_constant__ CUtensorMap mapC, const __grid_const
         int tcount = 0;
         for (int tile = pair; tile < total_tiles; tile += npairs, tcount++) {
             const int acc = tcount & 1;
-            const int b = (tile / d_tiles) * 256 + (int)rank * 128 + q * 32 + lane;  // this thread's replicate (column of the batch)
-            const int n_base = (tile % d_tiles) * 256;                               // first digit row of the tile
+            int ct, dt;
+            g2_tile_coords(tile, c_tiles, d_tiles, panel_w, ct, dt);
+            const int b = ct * 256 + (int)rank * 128 + q * 32 + lane;  // this thread's replicate (column of the batch)
+            const int n_base = dt * 256;                               // first digit row of the tile
             mb_wait(&acc_full[acc], (tcount >> 1) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
@@ -795,6 +821,32 @@ __global__ void __launch_bounds__(64, 1) i8_peak_kernel(int iters) {
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(2 * G8_BN) : "memory");
 }
 
+// the same loop back to back for `seconds`: the rate of the second half, i.e. under whatever
+// clock the power limit settles at (a long GEMM-bound step runs against this, not the burst rate)
+int bench_i8_peak_sustained(double seconds, double *tops, cudaStream_t st) {
+    const size_t smem = 2 * (G8_A_BYTES + G8_B_BYTES) + 1024 + 64;
+    CGPU_CUDA(cudaFuncSetAttribute(i8_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int sms = G().sm_count > 0 ? G().sm_count : 148;
+    const int iters = 1 << 15;
+    const int launches = std::max(4, (int)(seconds / 2.6e-3)) / 2 * 2;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    for (int i = 0; i < launches; i++) {
+        if (i == launches / 2) cudaEventRecord(a, st);
+        i8_peak_kernel<<<sms, 64, smem, st>>>(iters);
+    }
+    cudaEventRecord(b, st);
+    cudaEventSynchronize(b);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    CGPU_LAUNCH_CHECK();
+    *tops = 2.0 * G8_BM * G8_BN * G8_BK * (double)iters * sms * (launches / 2) / (ms * 1e-3) / 1e12;
+    return CGPU_OK;
+}
+
 int bench_i8_peak(double *tops, cudaStream_t st) {
     const size_t smem = 2 * (G8_A_BYTES + G8_B_BYTES) + 1024 + 64;
     CGPU_CUDA(cudaFuncSetAttribute(i8_peak_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -856,6 +908,98 @@ static int make_map(CUtensorMap *map, const void *ptr, size_t rows, int NP, int 
     return CGPU_OK;
 }
 
+// ---- site patterns: identical columns of L
+// two independent 64-bit mixes of a column's bit patterns (candidates only: every match is verified bit for bit)
+__global__ void __launch_bounds__(256)
+col_hash_kernel(const double *__restrict__ L, int K, int n, unsigned long long *__restrict__ h) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    unsigned long long a = 0x9E3779B97F4A7C15ull, b = 0xC2B2AE3D27D4EB4Full;
+    for (int k = 0; k < K; k++) {
+        const unsigned long long u = (unsigned long long)__double_as_longlong(L[(size_t)k * n + j]);
+        a = (a ^ u) * 0xBF58476D1CE4E5B9ull;
+        a ^= a >> 29;
+        b = (b + u) * 0x94D049BB133111EBull;
+        b ^= b >> 31;
+    }
+    h[2 * (size_t)j] = a;
+    h[2 * (size_t)j + 1] = b;
+}
+__global__ void __launch_bounds__(256)
+col_verify_kernel(const double *__restrict__ L, int K, int n, const unsigned int *__restrict__ pid,
+                  const unsigned int *__restrict__ rep, int *__restrict__ bad) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const unsigned int r = rep[pid[j]];
+    if (r == (unsigned int)j) return;
+    for (int k = 0; k < K; k++)
+        if (__double_as_longlong(L[(size_t)k * n + j]) != __double_as_longlong(L[(size_t)k * n + r])) {
+            atomicExch(bad, 1);
+            return;
+        }
+}
+
+// at most this many sites share a slot: a slot's count is Poisson(r * multiplicity) and must stay below 256
+constexpr int FX_PATTERN_CAP = 32;
+
+static int fx_find_patterns(DevMatrix &m, cudaStream_t st, std::vector<unsigned int> *rep_out) {
+    const int n = m.n, K = m.K;
+    unsigned long long *d_h = nullptr;
+    CGPU_CUDA(dev_alloc(&d_h, (size_t)n * 16));
+    col_hash_kernel<<<(n + 255) / 256, 256, 0, st>>>(m.d_L, K, n, d_h);
+    CGPU_LAUNCH_CHECK();
+    std::vector<unsigned long long> h((size_t)2 * n);
+    CGPU_CUDA(cudaMemcpyAsync(h.data(), d_h, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
+    CGPU_CUDA(cudaStreamSynchronize(st));
+    dev_free(d_h);
+    // sites in order; a pattern opens a new slot every FX_PATTERN_CAP members
+    struct Slot {
+        unsigned int slot, members;
+    };
+    std::unordered_map<unsigned long long, Slot> open;  // keyed by the first mix; the second one is compared explicitly
+    std::vector<unsigned long long> second;             // per slot: second mix of its representative
+    std::vector<unsigned int> pid(n), rep;
+    open.reserve((size_t)n);
+    for (int j = 0; j < n; j++) {
+        const unsigned long long a = h[2 * (size_t)j], b = h[2 * (size_t)j + 1];
+        auto it = open.find(a);
+        if (it != open.end() && second[it->second.slot] == b && it->second.members < (unsigned)FX_PATTERN_CAP) {
+            pid[j] = it->second.slot;
+            it->second.members++;
+        } else {
+            const unsigned int sl = (unsigned int)rep.size();
+            rep.push_back((unsigned int)j);
+            second.push_back(b);
+            open[a] = Slot{sl, 1};
+            pid[j] = sl;
+        }
+    }
+    if (rep.size() * 8 > (size_t)n * 7) return CGPU_OK;  // less than 1/8 saved: not worth a table lookup per draw
+    unsigned int *d_rep = nullptr;
+    int *d_bad = nullptr;
+    CGPU_CUDA(dev_alloc(&m.d_pid, (size_t)n * 4));
+    CGPU_CUDA(dev_alloc(&d_rep, rep.size() * 4));
+    CGPU_CUDA(dev_alloc(&d_bad, 4));
+    CGPU_CUDA(cudaMemcpyAsync(m.d_pid, pid.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    CGPU_CUDA(cudaMemcpyAsync(d_rep, rep.data(), rep.size() * 4, cudaMemcpyHostToDevice, st));
+    CGPU_CUDA(cudaMemsetAsync(d_bad, 0, 4, st));
+    col_verify_kernel<<<(n + 255) / 256, 256, 0, st>>>(m.d_L, K, n, m.d_pid, d_rep, d_bad);
+    CGPU_LAUNCH_CHECK();
+    int bad = 0;
+    CGPU_CUDA(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, st));
+    CGPU_CUDA(cudaStreamSynchronize(st));
+    dev_free(d_rep);
+    dev_free(d_bad);
+    if (bad) {  // a hash collision: two different columns shared both mixes -- no compression for this matrix
+        dev_free(m.d_pid);
+        m.d_pid = nullptr;
+        return CGPU_OK;
+    }
+    m.npat = (int)rep.size();
+    *rep_out = std::move(rep);
+    return CGPU_OK;
+}
+
 static bool fx_can_fuse(const DevMatrix &m, int max_draws) {
     // S <= 8 dividing 8, a scale 2^-F that is a normal double, and group sums that are exact in fp64
     return m.fxS <= 8 && 8 % m.fxS == 0 && G().opt_i8_fuse != 0 && m.fxF > -1000 && m.fxF < 1000 && max_draws < (1 << 21);
@@ -866,8 +1010,15 @@ bool fx_needs_partial(const DevMatrix &m, int max_draws) {
     return one_shot || !fx_can_fuse(m, max_draws);
 }
 
-int fx_prepare(DevMatrix &m, cudaStream_t st) {
-    if (m.d_A8) return CGPU_OK;
+int fx_prepare(DevMatrix &m, cudaStream_t st, bool allow_patterns) {
+    if (m.d_A8 && (m.npat == 0 || allow_patterns)) return CGPU_OK;
+    if (m.d_A8) {  // prepared with pattern slots, but this call cannot use them: slice again, uncompressed
+        dev_free(m.d_A8);
+        dev_free(m.d_pid);
+        m.d_A8 = nullptr;
+        m.d_pid = nullptr;
+        m.npat = 0;
+    }
     if (m.ready) CGPU_CUDA(cudaStreamWaitEvent(st, m.ready, 0));  // the upload may still be in flight on the copy stream
     int *d_rng = nullptr;
     CGPU_CUDA(dev_alloc(&d_rng, 3 * sizeof(int)));
@@ -895,10 +1046,23 @@ int fx_prepare(DevMatrix &m, cudaStream_t st) {
     m.fxS = S < 1 ? 1 : S;
     m.fxF = -h[0];
     m.fxMpad = ((size_t)m.K * m.fxS + G8_BM - 1) / G8_BM * G8_BM;
-    CGPU_CUDA(dev_alloc(&m.d_A8, (size_t)m.fxMpad * m.NP));
-    CGPU_CUDA(cudaMemsetAsync(m.d_A8, 0, (size_t)m.fxMpad * m.NP, st));
-    fx_slice_kernel<<<G().sm_count * 8, 256, 0, st>>>(m.d_L, m.K, m.n, m.NP, m.fxS, m.fxF, m.d_A8);
+    std::vector<unsigned int> rep;
+    m.npat = 0;
+    if (allow_patterns && G().opt_i8_patterns != 0 && m.n >= 256) CGPU_TRY(fx_find_patterns(m, st, &rep));
+    m.NPc = m.npat > 0 ? pad_sites(m.npat) : m.NP;
+    unsigned int *d_rep = nullptr;
+    if (m.npat > 0) {
+        CGPU_CUDA(dev_alloc(&d_rep, rep.size() * 4));
+        CGPU_CUDA(cudaMemcpyAsync(d_rep, rep.data(), rep.size() * 4, cudaMemcpyHostToDevice, st));
+    }
+    CGPU_CUDA(dev_alloc(&m.d_A8, (size_t)m.fxMpad * m.NPc));
+    CGPU_CUDA(cudaMemsetAsync(m.d_A8, 0, (size_t)m.fxMpad * m.NPc, st));
+    fx_slice_kernel<<<G().sm_count * 8, 256, 0, st>>>(m.d_L, m.K, m.n, m.npat > 0 ? m.npat : m.n, d_rep, m.NPc, m.fxS, m.fxF, m.d_A8);
     CGPU_LAUNCH_CHECK();
+    if (d_rep) {
+        CGPU_CUDA(cudaStreamSynchronize(st));  // `rep` (pageable) has been consumed
+        dev_free(d_rep);
+    }
     return CGPU_OK;
 }
 
@@ -908,8 +1072,8 @@ int launch_contract_i8(const DevMatrix &m, const unsigned char *d_counts_rows, i
     if (nb <= 0) return CGPU_OK;
     // int32 accumulators: |sum_j c*d| <= 128 * (draws per replicate)
     CUtensorMap mapA, mapB;
-    CGPU_TRY(make_map(&mapA, m.d_A8, m.fxMpad, m.NP, G8_BM));
-    CGPU_TRY(make_map(&mapB, d_counts_rows, (size_t)nb_pad, m.NP, G8_BN));
+    CGPU_TRY(make_map(&mapA, m.d_A8, m.fxMpad, m.NPc, G8_BM));
+    CGPU_TRY(make_map(&mapB, d_counts_rows, (size_t)nb_pad, m.NPc, G8_BN));
     static bool attr_done = false;
     if (!attr_done) {
         CGPU_CUDA(cudaFuncSetAttribute(gemm_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G8_SMEM));
@@ -931,13 +1095,13 @@ int launch_contract_i8(const DevMatrix &m, const unsigned char *d_counts_rows, i
     const int m_tiles = (int)(m.fxMpad / G8_BM), n_tiles = nb_pad / G8_BN;
     // cta_group::2 pairs for long tiles; short tiles (C2: 27 k-blocks) are bound by the epilogue's
     // divisions, where the one-CTA kernel with twelve epilogue warps is faster (measured 2.2 vs 3.0 ms)
-    const bool two_cta = !one_shot && (G().opt_i8_2cta == 1 || (G().opt_i8_2cta != 0 && m.NP / G8_BK > 48)) &&
+    const bool two_cta = !one_shot && (G().opt_i8_2cta == 1 || (G().opt_i8_2cta != 0 && m.NPc / G8_BK > 48)) &&
                          (G().sm_count % 2 == 0 || G().sm_count <= 0);
     if (two_cta) {
         // cta_group::2: replicates on the M side (count rows are operand A), digit rows on N
         CUtensorMap mapC, mapD;
-        CGPU_TRY(make_map(&mapC, d_counts_rows, (size_t)nb_pad, m.NP, 128));
-        CGPU_TRY(make_map(&mapD, m.d_A8, m.fxMpad, m.NP, 128));
+        CGPU_TRY(make_map(&mapC, d_counts_rows, (size_t)nb_pad, m.NPc, 128));
+        CGPU_TRY(make_map(&mapD, m.d_A8, m.fxMpad, m.NPc, 128));
         static bool attr2_done = false;
         if (!attr2_done) {
             CGPU_CUDA(cudaFuncSetAttribute(gemm_i8_2cta_kernel<6, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G2P<6, 8>::smem));
@@ -948,21 +1112,22 @@ int launch_contract_i8(const DevMatrix &m, const unsigned char *d_counts_rows, i
         const int grid = std::min(sms / 2 * 2, 2 * c_tiles * d_tiles);
         FxEpilogue ep{fused ? d_rep : nullptr, r, {(m.fxF > -1000 && m.fxF < 1000) ? std::ldexp(1.0, -m.fxF) : 0.0, m.fxF},
                       m.K, m.fxS, nb, ldrep, col0, G().opt_i8_dbg > 0 ? G().opt_i8_dbg : 0};
-        gemm_i8_2cta_kernel<6, 8><<<grid, G2P<6, 8>::threads, G2P<6, 8>::smem, st>>>(mapC, mapD, m.NP, d_partial, nb_pad, (int)m.fxMpad,
-                                                                                     c_tiles, d_tiles, ep);
+        gemm_i8_2cta_kernel<6, 8><<<grid, G2P<6, 8>::threads, G2P<6, 8>::smem, st>>>(mapC, mapD, m.NPc, d_partial, nb_pad, (int)m.fxMpad,
+                                                                                     c_tiles, d_tiles,
+                                                                                     G().opt_i8_panel >= 0 ? G().opt_i8_panel : 8, ep);
     } else if (one_shot) {
         dim3 grid((unsigned)m_tiles, (unsigned)n_tiles);
-        gemm_i8_kernel<<<grid, G8_THREADS, G8_SMEM, st>>>(mapA, mapB, m.NP, d_partial, nb_pad, nb_pad);
+        gemm_i8_kernel<<<grid, G8_THREADS, G8_SMEM, st>>>(mapA, mapB, m.NPc, d_partial, nb_pad, nb_pad);
     } else {
         const int sms = G().sm_count > 0 ? G().sm_count : 148;
         const int grid = std::min(sms, m_tiles * n_tiles);
         FxEpilogue ep{fused ? d_rep : nullptr, r, {(m.fxF > -1000 && m.fxF < 1000) ? std::ldexp(1.0, -m.fxF) : 0.0, m.fxF},
                       m.K, m.fxS, nb, ldrep, col0, G().opt_i8_dbg > 0 ? G().opt_i8_dbg : 0};
         // short tiles (C2: 27 k-blocks) are epilogue bound, long ones feed bound (measured cross-over ~50)
-        if (fused && m.NP / G8_BK <= 48)
-            gemm_i8_persistent_kernel<3, 12><<<grid, G8P<3, 12>::threads, G8P<3, 12>::smem, st>>>(mapA, mapB, m.NP, d_partial, nb_pad, m_tiles, n_tiles, ep);
+        if (fused && m.NPc / G8_BK <= 48)
+            gemm_i8_persistent_kernel<3, 12><<<grid, G8P<3, 12>::threads, G8P<3, 12>::smem, st>>>(mapA, mapB, m.NPc, d_partial, nb_pad, m_tiles, n_tiles, ep);
         else
-            gemm_i8_persistent_kernel<4, 8><<<grid, G8P<4, 8>::threads, G8P<4, 8>::smem, st>>>(mapA, mapB, m.NP, d_partial, nb_pad, m_tiles, n_tiles, ep);
+            gemm_i8_persistent_kernel<4, 8><<<grid, G8P<4, 8>::threads, G8P<4, 8>::smem, st>>>(mapA, mapB, m.NPc, d_partial, nb_pad, m_tiles, n_tiles, ep);
     }
     CGPU_LAUNCH_CHECK();
     if (pt) pt->end();

@@ -100,7 +100,8 @@ template <int SRC, int HALGO, bool ROWS, int RPC>
 __global__ void __launch_bounds__(HIST_THREADS)
 hist_group_kernel(const void *__restrict__ idx_v, int n, int NP, int bn, int nb,
                   unsigned long long *__restrict__ counts, int *__restrict__ err,
-                  uint32_t key0, uint32_t key1, uint32_t scale, uint32_t b_first, uint32_t ctr3) {
+                  uint32_t key0, uint32_t key1, uint32_t scale, uint32_t b_first, uint32_t ctr3,
+                  const unsigned int *__restrict__ pid) {
     extern __shared__ unsigned char hsm[];  // RPC histograms of NP bytes (+ 8 tag arrays for HALGO 2)
     static_assert(RPC == 8 || (ROWS && HALGO == 1), "shared histograms need the atomic update and the row layout");
     constexpr int WPR = 8 / RPC;  // warps per replicate
@@ -123,7 +124,10 @@ hist_group_kernel(const void *__restrict__ idx_v, int n, int NP, int bn, int nb,
                     // replicate's draws and reads it with 16-byte loads (8 indices per lane), all updates
                     // unconditional; a scalar head (up to the 16-byte boundary) and tail frame the body
                     unsigned *h32 = reinterpret_cast<unsigned *>(hist);
-                    auto add = [&](uint32_t k) { atomicAdd(h32 + (k >> 2), 1u << ((k & 3u) * 8u)); };
+                    auto add = [&](uint32_t k) {
+                        if (pid) k = __ldg(pid + k);  // site -> pattern slot
+                        atomicAdd(h32 + (k >> 2), 1u << ((k & 3u) * 8u));
+                    };
                     const int seg = (bn + WPR - 1) / WPR;
                     int i = sub * seg;
                     const int hi = min(bn, i + seg);
@@ -154,6 +158,7 @@ hist_group_kernel(const void *__restrict__ idx_v, int n, int NP, int bn, int nb,
                         const int i = i0 + u * 32 + lane;
                         vv[u] = i < bn;
                         kk[u] = vv[u] ? (SRC == 2 ? (uint32_t)src16[i] : src32[i]) : 0u;
+                        if (pid && vv[u]) kk[u] = __ldg(pid + kk[u]);
                     }
 #pragma unroll
                     for (int u = 0; u < 8; u++) {
@@ -169,7 +174,9 @@ hist_group_kernel(const void *__restrict__ idx_v, int n, int NP, int bn, int nb,
 #pragma unroll
                     for (int u = 0; u < 4; u++) {
                         bool valid = q * 4 + u < bn;
-                        warp_hist_add<HALGO>(hist, tag, __umulhi(p.v[u], (uint32_t)n), valid, lane, &overflow);
+                        uint32_t k = __umulhi(p.v[u], (uint32_t)n);
+                        if (pid) k = __ldg(pid + k);
+                        warp_hist_add<HALGO>(hist, tag, k, valid, lane, &overflow);
                     }
                 }
             }
@@ -228,7 +235,7 @@ template <int SRC, bool ROWS>
 __global__ void __launch_bounds__(256)
 hist_global_kernel(const void *__restrict__ idx_v, int n, int NP, int bn, int nb,
                    unsigned int *__restrict__ counts32, uint32_t key0, uint32_t key1, uint32_t scale,
-                   uint32_t b_first, uint32_t ctr3) {
+                   uint32_t b_first, uint32_t ctr3, const unsigned int *__restrict__ pid) {
     const unsigned long long total = SRC != 1 ? (unsigned long long)nb * bn
                                               : (unsigned long long)nb * ((bn + 3) / 4);
     for (unsigned long long d = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; d < total;
@@ -236,6 +243,7 @@ hist_global_kernel(const void *__restrict__ idx_v, int n, int NP, int bn, int nb
         if (SRC != 1) {
             uint32_t r = (uint32_t)(d / bn);
             uint32_t k = SRC == 2 ? (uint32_t)static_cast<const uint16_t *>(idx_v)[d] : static_cast<const uint32_t *>(idx_v)[d];
+            if (pid) k = __ldg(pid + k);
             if (ROWS) {
                 atomicAdd(&counts32[((size_t)r * NP + k) >> 2], 1u << ((k & 3) * 8));
             } else {
@@ -250,6 +258,7 @@ hist_global_kernel(const void *__restrict__ idx_v, int n, int NP, int bn, int nb
             for (int u = 0; u < 4; u++) {
                 if ((int)(q * 4 + u) < bn) {
                     uint32_t k = __umulhi(p.v[u], (uint32_t)n);
+                    if (pid) k = __ldg(pid + k);
                     if (ROWS) {
                         atomicAdd(&counts32[((size_t)r * NP + k) >> 2], 1u << ((k & 3) * 8));
                     } else {
@@ -272,13 +281,17 @@ hist_global_kernel(const void *__restrict__ idx_v, int n, int NP, int bn, int nb
 template <int SRC, int TH>
 __global__ void __launch_bounds__(TH)
 hist_wide_kernel(const void *__restrict__ idx_v, int n, int NP, int bn, int nb, unsigned char *__restrict__ rows,
-                 int *__restrict__ err, uint32_t key0, uint32_t key1, uint32_t scale, uint32_t b_first, uint32_t ctr3) {
+                 int *__restrict__ err, uint32_t key0, uint32_t key1, uint32_t scale, uint32_t b_first, uint32_t ctr3,
+                 const unsigned int *__restrict__ pid) {
     extern __shared__ __align__(16) unsigned char hsm[];
     __shared__ unsigned int s_sum[TH / 32];
     constexpr int NW = TH / 32;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     unsigned *h32 = reinterpret_cast<unsigned *>(hsm);
-    auto add = [&](uint32_t k) { atomicAdd(h32 + (k >> 2), 1u << ((k & 3u) * 8u)); };
+    auto add = [&](uint32_t k) {
+        if (pid) k = __ldg(pid + k);  // site -> pattern slot
+        atomicAdd(h32 + (k >> 2), 1u << ((k & 3u) * 8u));
+    };
     for (int r = blockIdx.x; r < nb; r += gridDim.x) {
         for (int i = tid; i < NP / 16; i += TH) reinterpret_cast<uint4 *>(hsm)[i] = make_uint4(0, 0, 0, 0);
         __syncthreads();
@@ -354,7 +367,7 @@ hist_wide_kernel(const void *__restrict__ idx_v, int n, int NP, int bn, int nb, 
 
 template <int SRC, int TH>
 static int hist_wide_launch(const void *d_idx, int n, int NP, int bn, int nb, unsigned long long *d_counts, int *d_err,
-                            uint32_t k0, uint32_t k1, uint32_t scale, uint32_t b_first, uint32_t ctr3, cudaStream_t st) {
+                            uint32_t k0, uint32_t k1, uint32_t scale, uint32_t b_first, uint32_t ctr3, cudaStream_t st, const unsigned int *pid) {
     auto kern = hist_wide_kernel<SRC, TH>;
     static bool attr_done = false;
     if (!attr_done) {
@@ -365,7 +378,7 @@ static int hist_wide_launch(const void *d_idx, int n, int NP, int bn, int nb, un
     const int per_sm = std::max(1, std::min(2048 / TH, (int)((size_t)(224 * 1024) / ((size_t)NP + 1024))));
     const int grid = std::min(nb, sms * per_sm);
     kern<<<grid, TH, (size_t)NP, st>>>(d_idx, n, NP, bn, nb, reinterpret_cast<unsigned char *>(d_counts), d_err, k0, k1, scale,
-                                       b_first, ctr3);
+                                       b_first, ctr3, pid);
     CGPU_LAUNCH_CHECK();
     return CGPU_OK;
 }
@@ -381,7 +394,7 @@ static int hist_algo() {
 
 template <int SRC, int HALGO, bool ROWS, int RPC = 8>
 static int hist_group_launch(const void *d_idx, int n, int NP, int bn, int nb, unsigned long long *d_counts,
-                             int *d_err, uint32_t k0, uint32_t k1, uint32_t scale, uint32_t b_first, uint32_t ctr3, cudaStream_t st) {
+                             int *d_err, uint32_t k0, uint32_t k1, uint32_t scale, uint32_t b_first, uint32_t ctr3, cudaStream_t st, const unsigned int *pid) {
     auto kern = hist_group_kernel<SRC, HALGO, ROWS, RPC>;
     static bool attr_done = false;
     if (!attr_done) {
@@ -394,15 +407,19 @@ static int hist_group_launch(const void *d_idx, int n, int NP, int bn, int nb, u
     int per_sm = (int)std::min<size_t>(8, (220 * 1024) / smem);
     if (per_sm < 1) per_sm = 1;
     const int grid = std::min(ngroups, sms * per_sm);
-    kern<<<grid, HIST_THREADS, smem, st>>>(d_idx, n, NP, bn, nb, d_counts, d_err, k0, k1, scale, b_first, ctr3);
+    kern<<<grid, HIST_THREADS, smem, st>>>(d_idx, n, NP, bn, nb, d_counts, d_err, k0, k1, scale, b_first, ctr3, pid);
     CGPU_LAUNCH_CHECK();
     return CGPU_OK;
 }
 
 static int hist_dispatch(int src, const void *d_idx, int n, int NP, int bn, int nb,
                          unsigned long long *d_counts, int *d_err, uint32_t k0, uint32_t k1, uint32_t scale,
-                         uint32_t b_first, uint32_t ctr3, cudaStream_t st, bool rows) {
+                         uint32_t b_first, uint32_t ctr3, cudaStream_t st, bool rows, const unsigned int *pid) {
     if (nb <= 0) return CGPU_OK;
+    if (pid && !rows) {
+        set_error(CGPU_EINVAL, "pattern slots are a byte-row (int8 path) feature");
+        return CGPU_EINVAL;
+    }
     const int ngroups = (nb + 7) / 8;
     int algo = hist_algo();
     if (algo == 2 && 2 * NP > HIST_SMEM_SITES) algo = 0;  // tag arrays double the footprint
@@ -411,16 +428,16 @@ static int hist_dispatch(int src, const void *d_idx, int n, int NP, int bn, int 
         const bool th512 = (size_t)4 * ((size_t)NP + 1024) <= (size_t)224 * 1024;
 #define CGPU_HISTWIDE_CASE(S)                                                                                              \
     if (src == S)                                                                                                          \
-        return th512 ? hist_wide_launch<S, 512>(d_idx, n, NP, bn, nb, d_counts, d_err, k0, k1, scale, b_first, ctr3, st)    \
-                     : hist_wide_launch<S, 1024>(d_idx, n, NP, bn, nb, d_counts, d_err, k0, k1, scale, b_first, ctr3, st);
+        return th512 ? hist_wide_launch<S, 512>(d_idx, n, NP, bn, nb, d_counts, d_err, k0, k1, scale, b_first, ctr3, st, pid)    \
+                     : hist_wide_launch<S, 1024>(d_idx, n, NP, bn, nb, d_counts, d_err, k0, k1, scale, b_first, ctr3, st, pid);
         CGPU_HISTWIDE_CASE(0) CGPU_HISTWIDE_CASE(1) CGPU_HISTWIDE_CASE(2)
 #undef CGPU_HISTWIDE_CASE
     }
     if (NP <= HIST_SMEM_SITES) {
 #define CGPU_HIST_CASE(S, A)                                                                                     \
     if (src == S && algo == A)                                                                                    \
-        return rows ? hist_group_launch<S, A, true>(d_idx, n, NP, bn, nb, d_counts, d_err, k0, k1, scale, b_first, ctr3, st) \
-                    : hist_group_launch<S, A, false>(d_idx, n, NP, bn, nb, d_counts, d_err, k0, k1, scale, b_first, ctr3, st);
+        return rows ? hist_group_launch<S, A, true>(d_idx, n, NP, bn, nb, d_counts, d_err, k0, k1, scale, b_first, ctr3, st, pid) \
+                    : hist_group_launch<S, A, false>(d_idx, n, NP, bn, nb, d_counts, d_err, k0, k1, scale, b_first, ctr3, st, pid);
         CGPU_HIST_CASE(0, 0) CGPU_HIST_CASE(0, 1) CGPU_HIST_CASE(0, 2)
         CGPU_HIST_CASE(1, 0) CGPU_HIST_CASE(1, 1) CGPU_HIST_CASE(1, 2)
         CGPU_HIST_CASE(2, 0) CGPU_HIST_CASE(2, 1) CGPU_HIST_CASE(2, 2)
@@ -431,9 +448,9 @@ static int hist_dispatch(int src, const void *d_idx, int n, int NP, int bn, int 
         // byte rows of a long alignment: 4, 2 or 1 replicates per CTA share the 8 warps
 #define CGPU_HISTW_CASE(S)                                                                                               \
     if (src == S) {                                                                                                       \
-        if (NP <= 2 * HIST_SMEM_SITES) return hist_group_launch<S, 1, true, 4>(d_idx, n, NP, bn, nb, d_counts, d_err, k0, k1, scale, b_first, ctr3, st); \
-        if (NP <= 4 * HIST_SMEM_SITES) return hist_group_launch<S, 1, true, 2>(d_idx, n, NP, bn, nb, d_counts, d_err, k0, k1, scale, b_first, ctr3, st); \
-        return hist_group_launch<S, 1, true, 1>(d_idx, n, NP, bn, nb, d_counts, d_err, k0, k1, scale, b_first, ctr3, st);      \
+        if (NP <= 2 * HIST_SMEM_SITES) return hist_group_launch<S, 1, true, 4>(d_idx, n, NP, bn, nb, d_counts, d_err, k0, k1, scale, b_first, ctr3, st, pid); \
+        if (NP <= 4 * HIST_SMEM_SITES) return hist_group_launch<S, 1, true, 2>(d_idx, n, NP, bn, nb, d_counts, d_err, k0, k1, scale, b_first, ctr3, st, pid); \
+        return hist_group_launch<S, 1, true, 1>(d_idx, n, NP, bn, nb, d_counts, d_err, k0, k1, scale, b_first, ctr3, st, pid);      \
     }
         CGPU_HISTW_CASE(0) CGPU_HISTW_CASE(1) CGPU_HISTW_CASE(2)
 #undef CGPU_HISTW_CASE
@@ -446,7 +463,7 @@ static int hist_dispatch(int src, const void *d_idx, int n, int NP, int bn, int 
         unsigned int *c32 = reinterpret_cast<unsigned int *>(d_counts);
 #define CGPU_HISTG_CASE(S, R)                                                                                 \
     if (src == S && rows == R)                                                                                 \
-        hist_global_kernel<S, R><<<grid, 256, 0, st>>>(d_idx, n, NP, bn, nb, c32, k0, k1, scale, b_first, ctr3);
+        hist_global_kernel<S, R><<<grid, 256, 0, st>>>(d_idx, n, NP, bn, nb, c32, k0, k1, scale, b_first, ctr3, pid);
         CGPU_HISTG_CASE(0, false) CGPU_HISTG_CASE(0, true) CGPU_HISTG_CASE(1, false) CGPU_HISTG_CASE(1, true)
         CGPU_HISTG_CASE(2, false) CGPU_HISTG_CASE(2, true)
 #undef CGPU_HISTG_CASE
@@ -456,12 +473,13 @@ static int hist_dispatch(int src, const void *d_idx, int n, int NP, int bn, int 
 }
 
 int launch_hist_from_idx(const void *d_idx, int n, int NP, int bn, int nb,
-                         unsigned long long *d_counts, int *d_err, cudaStream_t st, bool rows) {
-    return hist_dispatch(idx_is16((uint32_t)n) ? 2 : 0, d_idx, n, NP, bn, nb, d_counts, d_err, 0, 0, 0, 0, 0, st, rows);
+                         unsigned long long *d_counts, int *d_err, cudaStream_t st, bool rows, const unsigned int *pid) {
+    return hist_dispatch(idx_is16((uint32_t)n) ? 2 : 0, d_idx, n, NP, bn, nb, d_counts, d_err, 0, 0, 0, 0, 0, st, rows, pid);
 }
 
 int launch_hist_philox(unsigned long long seed, int scale, int b_first, int n, int NP, int bn, int nb,
-                       unsigned long long *d_counts, int *d_err, cudaStream_t st, bool rows, unsigned long long stream_offset) {
+                       unsigned long long *d_counts, int *d_err, cudaStream_t st, bool rows, unsigned long long stream_offset,
+                       const unsigned int *pid) {
     // The counter-based generator has no stream position; calls that continue one logical stream
     // (makermt -g: one call per gene file, stream_offset = draws consumed so far) must still draw
     // independent replicates, so the offset is hashed (splitmix64 finaliser) into the fourth
@@ -475,7 +493,7 @@ int launch_hist_philox(unsigned long long seed, int scale, int b_first, int n, i
         z = (z & 0xffffffffull) ? z : 1;
     }
     return hist_dispatch(1, nullptr, n, NP, bn, nb, d_counts, d_err, (uint32_t)seed, (uint32_t)(seed >> 32),
-                         (uint32_t)scale, (uint32_t)b_first, (uint32_t)z, st, rows);
+                         (uint32_t)scale, (uint32_t)b_first, (uint32_t)z, st, rows, pid);
 }
 
 // BJ8 -> plain counts[b*n + j] bytes (test seam: cgpu_resample_counts)

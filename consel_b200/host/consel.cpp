@@ -34,6 +34,7 @@
 #include "../../include/consel_gpu.h"
 #include "assoc.h"
 #include "audriver.h"
+#include "pipeline.h"
 #include "aufit.h"
 #include "refio.h"
 #include "specfun.h"
@@ -459,6 +460,8 @@ static void run_multimode(const MultiArgs &A, const aufit::Options &opt) {
 }
 
 int main(int argc, char **argv) {
+    if (getenv("RANK") && atoi(getenv("RANK")) > 0 && getenv("WORLD_SIZE") && atoi(getenv("WORLD_SIZE")) > 1)
+        if (!freopen("/dev/null", "w", stdout)) return 1;  // rank 0 speaks for the job
     const char *fname_in = nullptr, *fname_out_arg = nullptr, *fname_ass = nullptr, *fname_vt = nullptr, *fname_pa = nullptr;
     bool fastrep = false;
     bool outrep = false, outcnt = false, smoothcnt = false, nosort = false, inrep = false, incnt = false, multi = false, quickmc = false;
@@ -733,6 +736,14 @@ int main(int argc, char **argv) {
 
     // ---------------- device: upload the replicate blocks
     CG(cgpu_init(gpu));
+    // one process per GPU (RANK / WORLD_SIZE): every rank uploads its share of the replicate columns of every
+    // scale; KH/SH tests and AU fits are split over items, count queries are NCCL collectives (pipeline.cpp);
+    // rank 0 writes the files.  The modes that need whole rows on one device stay single-GPU.
+    CG(cgpu_comm_init_env());
+    int g_rank = 0, g_world = 1;
+    cgpu_comm_info(&g_rank, &g_world);
+    if (g_world > 1 && (inrep || fastrep || outrep || quickmc || smoothcnt || debugmode > 0))
+        die("-R, -f, -r, --quick_mctest, smoothed -c and -d need a single GPU (WORLD_SIZE=%d)", g_world);
     cgpu_reps *reps = nullptr;
     {
         std::vector<const double *> ptrs(kk);
@@ -748,7 +759,25 @@ int main(int argc, char **argv) {
 
     // ---------------- KH / SH tests (do_mctest)
     std::vector<double> khp(cm), mcp(cm), khwp(cm), mcwp(cm);
-    if (domc) {
+    std::vector<double> d_pv, d_se, d_ax, d_ci;  // multi-rank results (pipeline::consel_run)
+    std::vector<int> d_ret;
+    std::vector<cgpu_rowsum> d_q0;
+    if (g_world > 1) {
+        d_pv.assign((size_t)cm * 8, 0.0); d_se.assign((size_t)cm * 8, 0.0); d_ax.assign((size_t)cm * 7, 0.0);
+        d_ci.assign((size_t)6 * cm * std::max(nalpha, 1), 0.0); d_ret.assign(cm, 0); d_q0.resize((size_t)cm * kk);
+        if (kk < 2) doau = false;
+        printf("\n# MC/BP/AU tests on %d GPUs", g_world);
+        fflush(stdout);
+        if (pipeline::consel_run(reps, mm, datvec.data(), kk, rr.data(), bb.data(), cm, ass.ptr.data(), ass.idx.data(), threshold,
+                                 varadd, opt, domc ? 1 : 0, doau ? 1 : 0, nalpha, alphavec.data(), d_pv.data(), d_se.data(), nullptr,
+                                 d_ax.data(), doau ? d_ci.data() : nullptr, d_ret.data(), nullptr, d_q0.data()) != 0)
+            die("%s", cgpu_last_error());
+        for (int i = 0; i < cm; i++) {
+            khp[i] = d_pv[8 * (size_t)i + 2]; mcp[i] = d_pv[8 * (size_t)i + 3];
+            khwp[i] = d_pv[8 * (size_t)i + 4]; mcwp[i] = d_pv[8 * (size_t)i + 5];
+        }
+    }
+    if (domc && g_world == 1) {
         if (quickmc) CG(cgpu_set_option("mc_smooth", 0));  // sw_pvaldist=0: plain counts, no smoothing
         printf("\n# MC-TEST STARTS");
         printf("\n# centering the replicates");
@@ -767,7 +796,9 @@ int main(int argc, char **argv) {
         thvec(cm), beta(3 * (size_t)cm, 0.0);
     std::vector<double> cimat, csmat, eimat, ci0mat, cs0mat, ei0mat, cntmat;
     std::vector<cgpu_rowsum> r0;
-    if (doau || dobp || outrep || outcnt) {
+    if (g_world > 1) {
+        r0 = d_q0;
+    } else if (doau || dobp || outrep || outcnt) {
         if (!inrep && fastrep) {  // genrep's rescaling branch (src/consel.c:757-771)
             printf("\n# calculate replicates of the statistics");
             const int kk1 = (int)rr1.size();
@@ -809,7 +840,25 @@ int main(int argc, char **argv) {
     std::vector<double> bbd(kk);
     for (int k = 0; k < kk; k++) bbd[k] = (double)bb[k];
 
-    if (doau) {  // do_bootrep
+    if (doau && g_world > 1) {
+        const size_t n2 = (size_t)cm * nalpha;
+        for (int i = 0; i < cm; i++) {
+            pvvec[i] = d_pv[8 * (size_t)i + 6]; sevec[i] = d_se[8 * (size_t)i + 6];
+            pv0vec[i] = d_pv[8 * (size_t)i + 7]; se0vec[i] = d_se[8 * (size_t)i + 7];
+            const double *a = &d_ax[7 * (size_t)i];
+            pfvec[i] = a[0]; rssvec[i] = a[1]; dfvec[i] = a[2]; thvec[i] = a[5];
+            if (d_ret[i]) {
+                warn("regression degenerated: df[%d]=%g", i + 1, dfvec[i]);
+            } else {
+                if (pfvec[i] < 0.01) warn("theory does not fit well: pfit[%d]=%.4f", i + 1, pfvec[i]);
+                beta[3 * (size_t)i] = a[3]; beta[3 * (size_t)i + 1] = a[4]; beta[3 * (size_t)i + 2] = a[6];
+            }
+        }
+        cimat.assign(d_ci.begin(), d_ci.begin() + n2); csmat.assign(d_ci.begin() + n2, d_ci.begin() + 2 * n2);
+        eimat.assign(d_ci.begin() + 2 * n2, d_ci.begin() + 3 * n2); ci0mat.assign(d_ci.begin() + 3 * n2, d_ci.begin() + 4 * n2);
+        cs0mat.assign(d_ci.begin() + 4 * n2, d_ci.begin() + 5 * n2); ei0mat.assign(d_ci.begin() + 5 * n2, d_ci.begin() + 6 * n2);
+        printf("\n# AU-TEST DONE");
+    } else if (doau) {  // do_bootrep
         printf("\n# AU-TEST STARTS");
         printf("\n# counting the replicates (sort-free row summaries on the device)");
         dots(kk);
@@ -877,6 +926,13 @@ int main(int argc, char **argv) {
                 const cgpu_rowsum &q = r0[(size_t)i * kk + k];
                 cntmat[(size_t)i * kk + k] = smoothcnt ? cgpu_smooth_count(&q, bb[k], threshold) : q.cnt;
             }
+    }
+
+    if (g_world > 1 && g_rank > 0) {  // rank 0 writes the files
+        cgpu_reps_free(reps);
+        cgpu_comm_destroy();
+        cgpu_shutdown();
+        return 0;
     }
 
     // ---------------- outputs (write_pv :1611-1683, write_ci :1685-1711, write_rep, write_cnt)

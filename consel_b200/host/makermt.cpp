@@ -78,6 +78,12 @@ static int genrmt(Params &P, const char *infile, const char *outfile) {
         rr1[i] = (double)bn[i] / nn;
     }
 
+    // one process per GPU (RANK / WORLD_SIZE, cgpu_comm_init_env): every rank resamples its share of the
+    // replicate columns, the blocks are all-gathered over NVLink and rank 0 alone writes the files
+    int g_rank = 0, g_world = 1;
+    cgpu_comm_info(&g_rank, &g_world);
+    const bool writer = g_rank == 0;
+    if (!writer) outfile = nullptr;  // (stdout of the other ranks is /dev/null)
     FILE *out = nullptr;
     if (outfile) {
         fp = open_file(outfile, ".vt", "w", &used);
@@ -112,9 +118,26 @@ static int genrmt(Params &P, const char *infile, const char *outfile) {
         rep[i].resize((size_t)mm * (P.bb[i] > 0 ? P.bb[i] : 0) + 1);
         rep_ptr[i] = rep[i].data();
     }
-    int rc = cgpu_scaleboot_all(L.data(), mm, nn, kk, bn.data(), P.bb.data(), P.seed_used, P.consumed, P.rng_mode,
-                                P.sum_mode, rep_ptr.data());
-    if (rc != CGPU_OK) die("%s", cgpu_last_error());
+    if (g_world == 1) {
+        int rc = cgpu_scaleboot_all(L.data(), mm, nn, kk, bn.data(), P.bb.data(), P.seed_used, P.consumed, P.rng_mode,
+                                    P.sum_mode, rep_ptr.data());
+        if (rc != CGPU_OK) die("%s", cgpu_last_error());
+    } else {
+        cgpu_matrix *dm = nullptr;
+        cgpu_reps *dr = nullptr;
+        if (cgpu_matrix_upload(L.data(), mm, nn, &dm) != CGPU_OK) die("%s", cgpu_last_error());
+        if (cgpu_scaleboot_dev(dm, kk, bn.data(), P.bb.data(), P.seed_used, P.consumed, P.rng_mode, P.sum_mode, &dr) != CGPU_OK)
+            die("%s", cgpu_last_error());
+        for (int i = 0; i < kk; i++) {
+            cgpu_reps *whole = nullptr;
+            if (cgpu_reps_gather_scale(dr, i, &whole) != CGPU_OK) die("%s", cgpu_last_error());
+            double *one[1] = {rep[i].data()};
+            if (writer && P.bb[i] > 0 && cgpu_reps_download(whole, one) != CGPU_OK) die("%s", cgpu_last_error());
+            cgpu_reps_free(whole);
+        }
+        cgpu_reps_free(dr);
+        cgpu_matrix_free(dm);
+    }
     for (int i = 0; i < kk; i++) P.consumed += (unsigned long long)P.bb[i] * (unsigned long long)bn[i];
 
     for (int i = 0; i < kk; i++) {
@@ -140,6 +163,8 @@ int main(int argc, char **argv) {
     bool fastrep = false, multi = false;
     int gpu = -1;
 
+    if (getenv("RANK") && atoi(getenv("RANK")) > 0 && getenv("WORLD_SIZE") && atoi(getenv("WORLD_SIZE")) > 1)
+        if (!freopen("/dev/null", "w", stdout)) return 1;  // rank 0 speaks for the job
     printf("# consel_b200 makermt (sm_100a); command line of makermt.c,v 1.16");
 
     for (int i = 1, j = 1; i < argc; i++) {  // src/makermt.c:237-279
@@ -215,6 +240,7 @@ int main(int argc, char **argv) {
     for (int i = 0; i < kk; i++) printf("%d ", P.bb[i]);
 
     if (cgpu_init(gpu) != CGPU_OK) die("%s", cgpu_last_error());
+    if (cgpu_comm_init_env() != CGPU_OK) die("%s", cgpu_last_error());
 
     if (multi) {  // src/makermt.c:303-318
         std::string used;

@@ -18,24 +18,18 @@
 
 #include "../../include/consel_gpu.h"
 #include "audriver.h"
+#include "pipeline.h"
 
 namespace {
 double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 }  // namespace
 
-extern "C" {
-
-// AU test of THIS rank's items through a caller-supplied collective query (the production
-// callback is cgpu_count_query_dist; the CPU tests drive it over gloo): see audriver.h.
-int chost_au_run_dist(int cm_own, int kk, const double *rr, const int *bb, int i0, double threshold, const double *median,
-                      const cgpu_rowsum *r0, int nalpha, const double *alpha, int fitmode, double kappa,
-                      audriver::DistQueryFn query, void *ctx, double *pv2, double *se2, double *ax7, double *ci6, int *ret) {
+static int au_run_dist_opt(int cm_own, int kk, const double *rr, const int *bb, int i0, double threshold, const double *median,
+                           const cgpu_rowsum *r0, int nalpha, const double *alpha, const aufit::Options &opt,
+                           audriver::DistQueryFn query, void *ctx, double *pv2, double *se2, double *ax7, double *ci6, int *ret) {
     audriver::Input in;
     in.cm = cm_own; in.kk = kk; in.rr = rr; in.bb = bb; in.i0 = i0; in.threshold = threshold;
     in.median = median; in.r0 = r0; in.nalpha = nalpha; in.alpha = alpha; in.confidence = ci6 != nullptr;
-    aufit::Options opt;
-    opt.fitmode = fitmode;
-    opt.kappa = kappa;
     audriver::Output o;
     if (int rc = audriver::run(in, opt, nullptr, ctx, &o, nullptr, query)) return rc;
     for (int i = 0; i < cm_own; i++) {
@@ -54,6 +48,19 @@ int chost_au_run_dist(int cm_own, int kk, const double *rr, const int *bb, int i
     return 0;
 }
 
+extern "C" {
+
+// AU test of THIS rank's items through a caller-supplied collective query (the production
+// callback is cgpu_count_query_dist; the CPU tests drive it over gloo): see audriver.h.
+int chost_au_run_dist(int cm_own, int kk, const double *rr, const int *bb, int i0, double threshold, const double *median,
+                      const cgpu_rowsum *r0, int nalpha, const double *alpha, int fitmode, double kappa,
+                      audriver::DistQueryFn query, void *ctx, double *pv2, double *se2, double *ax7, double *ci6, int *ret) {
+    aufit::Options opt;
+    opt.fitmode = fitmode;
+    opt.kappa = kappa;
+    return au_run_dist_opt(cm_own, kk, rr, bb, i0, threshold, median, r0, nalpha, alpha, opt, query, ctx, pv2, se2, ax7, ci6, ret);
+}
+
 // The consel half of the pipeline.  Items are given in output order (read_assoc's sort is done by
 // the caller: ass_ptr/ass_idx already permuted).  Outputs (every rank gets all of them):
 //   pv, se   cm x 8 in the .pv column order [bp, pp, kh, sh, wkh, wsh, au, np]; column 1 (pp, a
@@ -66,6 +73,19 @@ int chost_consel_run(cgpu_reps *reps, int K, const double *datvec, int kk, const
                      const int *ass_ptr, const int *ass_idx, double threshold, double varadd, int fitmode, double kappa,
                      int do_mc, int do_au, int nalpha, const double *alpha, double *pv, double *se, double *cnt, double *ax7,
                      double *ci6, int *ret, double *timing) {
+    aufit::Options opt;
+    opt.fitmode = fitmode;
+    opt.kappa = kappa;
+    return pipeline::consel_run(reps, K, datvec, kk, rr, bb, cm, ass_ptr, ass_idx, threshold, varadd, opt, do_mc, do_au, nalpha, alpha,
+                                pv, se, cnt, ax7, ci6, ret, timing, nullptr);
+}
+
+}  // extern "C"
+
+int pipeline::consel_run(cgpu_reps *reps, int K, const double *datvec, int kk, const double *rr, const int *bb, int cm,
+                         const int *ass_ptr, const int *ass_idx, double threshold, double varadd, const aufit::Options &opt,
+                         int do_mc, int do_au, int nalpha, const double *alpha, double *pv, double *se, double *cnt, double *ax7,
+                         double *ci6, int *ret, double *timing, cgpu_rowsum *q0_out) {
     if (!reps || !datvec || !rr || !bb || !ass_ptr || !ass_idx || !pv || !se || cm <= 0 || kk <= 0) return CGPU_EINVAL;
     int rank = 0, world = 1;
     cgpu_comm_info(&rank, &world);
@@ -127,6 +147,7 @@ int chost_consel_run(cgpu_reps *reps, int K, const double *datvec, int kk, const
         if (cnt)
             for (int k = 0; k < kk; k++) cnt[(size_t)i * kk + k] = q0[(size_t)i * kk + k].cnt;
     }
+    if (q0_out) std::copy(q0.begin(), q0.end(), q0_out);
     for (int i = 0; i < cm; i++)
         for (int c : {0, 2, 3, 4, 5}) {  // getseval (src/consel.c:2151-2158)
             const double p = pv[8 * (size_t)i + c];
@@ -159,15 +180,12 @@ int chost_consel_run(cgpu_reps *reps, int K, const double *datvec, int kk, const
         auto dq = [](void *ctx, int nq, const double *thr, cgpu_rowsum *out, int active, int *any) {
             return cgpu_count_query_dist(static_cast<const cgpu_reps *>(ctx), 0, nq, thr, out, active, any);
         };
-        rc = chost_au_run_dist(ne, kk, rr, bb, i0, threshold, med.data(), q0.data() + (size_t)e0 * kk, na, alpha, fitmode, kappa,
-                               dq, reps, pv2.data(), se2.data(), ax.data(), ci6 ? ci.data() : nullptr, rt.data());
+        rc = au_run_dist_opt(ne, kk, rr, bb, i0, threshold, med.data(), q0.data() + (size_t)e0 * kk, na, alpha, opt,
+                             dq, reps, pv2.data(), se2.data(), ax.data(), ci6 ? ci.data() : nullptr, rt.data());
     } else {
         audriver::Input in;
         in.cm = cm; in.kk = kk; in.rr = rr; in.bb = bb; in.i0 = i0; in.threshold = threshold;
         in.median = med.data(); in.r0 = q0.data(); in.nalpha = na; in.alpha = alpha; in.confidence = ci6 != nullptr;
-        aufit::Options opt;
-        opt.fitmode = fitmode;
-        opt.kappa = kappa;
         audriver::Output o;
         auto query = [](void *ctx, int nq, const double *thr, cgpu_rowsum *out) {
             return cgpu_count_query(static_cast<const cgpu_reps *>(ctx), nq, thr, out);
@@ -225,4 +243,4 @@ int chost_consel_run(cgpu_reps *reps, int K, const double *datvec, int kk, const
     return CGPU_OK;
 }
 
-}  // extern "C"
+

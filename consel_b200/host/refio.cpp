@@ -337,6 +337,92 @@ void write_bmat(FILE *fp, const double *a, int m, int n) {
 }
 
 // ------------------------------------------------------------------ foreign formats
+// Parallel parse of the tree blocks of a PAML .lnf file (src/freadmat.c:110-154 reads them
+// with fscanf: a K=1000 x 10^5-pattern file is gigabytes of text).  The rest of the file is read into
+// memory and cut into lines; tree i must be the non-blank line i*(p+1) holding the single integer i+1,
+// followed by p pattern lines `j count lnL ...` -- every such block is parsed on its own thread with
+// std::from_chars.  Anything else (comments, short files, wrong indices, hex floats) makes it give up
+// WITHOUT consuming input, so the serial loop below produces the reference's values and error messages.
+static bool read_paml_blocks_parallel(FILE *fp, int m, int n, int p, double *out) {
+    if ((long long)m * p < (1 << 15)) return false;
+    struct stat st;
+    const int fd = fileno(fp);
+    if (fd < 0 || fstat(fd, &st) != 0 || !S_ISREG(st.st_mode)) return false;
+    const long pos = ftell(fp);
+    if (pos < 0 || st.st_size <= pos) return false;
+    const size_t bytes = (size_t)(st.st_size - pos);
+    std::vector<char> buf(bytes + 1);
+    if (fread(buf.data(), 1, bytes, fp) != bytes) {
+        fseek(fp, pos, SEEK_SET);
+        return false;
+    }
+    buf[bytes] = '\n';
+    const char *base = buf.data();
+    // offsets of the non-blank lines
+    std::vector<size_t> line;
+    line.reserve((size_t)m * (p + 1) + 16);
+    for (size_t c = 0; c < bytes;) {
+        size_t e = c;
+        bool blank = true;
+        while (base[e] != '\n') {
+            if (!isspace((unsigned char)base[e])) blank = false;
+            e++;
+        }
+        if (!blank) line.push_back(c);
+        c = e + 1;
+    }
+    const size_t need = (size_t)m * ((size_t)p + 1);
+    bool ok = line.size() >= need;
+    if (ok) {
+        const int nthr = (int)std::max(1u, std::min(64u, std::min<unsigned>(std::thread::hardware_concurrency(), (unsigned)m)));
+        std::vector<char> good(nthr, 1);
+        auto tok_int = [&](const char *&c, long long *v) {
+            while (*c == ' ' || *c == '\t' || *c == '\r') c++;
+            const char *b = c;
+            while (*c != '\n' && !isspace((unsigned char)*c)) c++;
+            auto r = std::from_chars(b, c, *v);
+            return b < c && r.ec == std::errc() && r.ptr == c;
+        };
+        auto work = [&](int t) {
+            for (int i = t; i < m; i += nthr) {
+                const char *c = base + line[(size_t)i * (p + 1)];
+                long long v = 0;
+                if (*c == '#' || !tok_int(c, &v) || v != i + 1) { good[t] = 0; return; }
+                while (*c == ' ' || *c == '\t' || *c == '\r') c++;
+                if (*c != '\n') { good[t] = 0; return; }  // the tree line carries the index only
+                int col = 0;
+                for (int j = 0; j < p; j++) {
+                    c = base + line[(size_t)i * (p + 1) + 1 + j];
+                    long long idx = 0, reps = 0;
+                    if (*c == '#' || !tok_int(c, &idx) || idx != j + 1 || !tok_int(c, &reps) || reps < 0 || col + reps > n) { good[t] = 0; return; }
+                    while (*c == ' ' || *c == '\t' || *c == '\r') c++;
+                    const char *b = c;
+                    while (*c != '\n' && !isspace((unsigned char)*c)) c++;
+                    const char *b2 = (*b == '+') ? b + 1 : b;
+                    double x;
+                    auto r = std::from_chars(b2, c, x);
+                    if (b2 >= c || r.ec != std::errc() || r.ptr != c || (b2 + 1 < c && b2[0] == '0' && (b2[1] == 'x' || b2[1] == 'X'))) { good[t] = 0; return; }
+                    for (long long k = 0; k < reps; k++) out[(size_t)i * n + col++] = x;
+                }
+                if (col != n) { good[t] = 0; return; }
+            }
+        };
+        std::vector<std::thread> th;
+        for (int t = 0; t < nthr; t++) th.emplace_back(work, t);
+        for (auto &x : th) x.join();
+        for (int t = 0; t < nthr; t++) ok = ok && good[t];
+    }
+    if (!ok) {
+        fseek(fp, pos, SEEK_SET);
+        return false;
+    }
+    // leave the stream behind the last pattern line, as the serial reader does
+    size_t end = line[need - 1];
+    while (base[end] != '\n') end++;
+    fseek(fp, pos + (long)std::min(end + 1, bytes), SEEK_SET);
+    return true;
+}
+
 std::vector<double> read_mat_paml(FILE *fp, int *mp, int *np) {
     int m = read_int(fp), n = read_int(fp), p = read_int(fp);
     dprint(2, "\nm=%d n=%d p=%d", m, n, p);
@@ -347,6 +433,11 @@ std::vector<double> read_mat_paml(FILE *fp, int *mp, int *np) {
     std::vector<double> a;
     if ((long long)m * n == 0) return a;
     a.resize((size_t)m * n);
+    if (debugmode < 2 && p > 0 && read_paml_blocks_parallel(fp, m, n, p, a.data())) {
+        *mp = m;
+        *np = n;
+        return a;
+    }
     for (int i = 0; i < m; i++) {
         int t = read_int(fp);
         dprint(2, "\ni=%d", t);

@@ -23,12 +23,19 @@ static double lngamma(double xx) {
     return -tmp + log(2.5066282746310005 * ser / x);
 }
 
+// every call of the incomplete gamma function on this path has a = 0.5 (erfc): ln Gamma(0.5) is
+// evaluated once by the same routine (same bits as evaluating it per call, a third of pnorm's cost)
+static double lngamma_cached(double a) {
+    static const double half = lngamma(0.5);
+    return a == 0.5 ? half : lngamma(a);
+}
+
 static const int kItMax = 1000;
 static const double kEps = 3.0e-7, kFpMin = 1.0e-30;
 
 // P(a,x) by its series (NR 6.2 gser)
 static double gamma_series(double a, double x) {
-    const double gln = lngamma(a);
+    const double gln = lngamma_cached(a);
     if (x <= 0.0) {
         if (x < 0.0) refio::die("x less than 0 in routine gser");
         return 0.0;
@@ -45,7 +52,7 @@ static double gamma_series(double a, double x) {
 
 // Q(a,x) by the modified Lentz continued fraction (NR 6.2 gcf)
 static double gamma_cfrac(double a, double x) {
-    const double gln = lngamma(a);
+    const double gln = lngamma_cached(a);
     double b = x + 1.0 - a, c = 1.0 / kFpMin, d = 1.0 / b, h = d;
     int i;
     for (i = 1; i <= kItMax; i++) {

@@ -236,7 +236,8 @@ int cgpu_last_timing_ex(double *ms, int n);
  * "draw_fuse" 0|1 (draws + histograms in one kernel, int8 mode, opt-in), "stage" 0|1 (staged
  * index production of host-output int8 calls: 0 off, 1 always, default by size),
  * "hist_wide" 0|1 (one replicate per CTA
- * on long alignments), "i8_2cta" 0|1 (cta_group::2 GEMM, default on), "batch" N (replicates per
+ * on long alignments), "i8_2cta" 0|1 (cta_group::2 GEMM, default on), "i8_patterns" 0|1 (site-pattern compression of the int8 path,
+ * default on), "i8_panel" N (tile order of the pair GEMM), "dist_upload" 0|1, "batch" N (replicates per
  * GEMM batch, tests), "ktime" 0|1 (per-kernel events, see cgpu_kernel_times), "chunk_log2" 10..30 (force a power-of-two chunk of the MT19937 jump tree), "chunk_fill" 0|1|2
  * (equal-fill chunk lengths that are not powers of two: off, by cost model (default), forced), "i8_dbg" 0..3 (switches parts of the GEMM epilogue off: timing only,
  * results are wrong), "mc_smooth" 0|1 (0 = consel --quick_mctest: the KH/SH p-values of
@@ -253,11 +254,16 @@ int cgpu_set_option(const char *name, int value);
 int cgpu_kernel_times(char *buf, int len);
 /* shape of an uploaded matrix; slices/frac_bits/mpad describe the fixed-point split of
  * CGPU_SUM_INT8 (0 before the first int8 call): L = M * 2^-frac_bits, M in `slices` signed
- * base-256 digits, mpad = GEMM rows (slices*K rounded up to 128).  Any pointer may be NULL. */
-int cgpu_matrix_info(const cgpu_matrix *m, int *K, int *n, int *NP, int *slices, int *frac_bits, long long *mpad);
+ * base-256 digits, mpad = GEMM rows (slices*K rounded up to 128), patterns = number of column slots
+ * when identical columns of L share one (site-pattern compression, 0 = none).  Any pointer may be NULL. */
+int cgpu_matrix_info(const cgpu_matrix *m, int *K, int *n, int *NP, int *slices, int *frac_bits, long long *mpad,
+                     int *patterns);
 /* measured roofline denominators (MEASURED_PEAKS.json carries HBM and bf16 only): dense int8
  * tcgen05.mma issue rate from shared-memory-resident operands (TOP/s), FP64 DFMA rate (TFLOP/s) */
 int cgpu_bench_i8_peak(double *tops);
+/* the same loop back to back for `seconds` (<= 30), rate of the second half: the clock a long
+ * tensor-bound step settles at under the board's power limit                                */
+int cgpu_bench_i8_peak_sustained(double seconds, double *tops);
 int cgpu_bench_fp64_peak(double *tflops);
 /* draws per chunk of the most recent MT19937 jump plan (diagnostics / tests) */
 unsigned long long cgpu_last_chunk_len(void);

@@ -131,6 +131,10 @@ def main() -> None:
     orc.run_ref("consel", ["-r", "-c", "full"], work)
     for e in ("rmt", "vt", "pv", "ci", "cnt", "rep"):
         manifest["full_size"][f"mam15_s1234.{e}"] = md5(work / f"full.{e}")
+    # the full-size p-value table itself is small: kept as a fixture (C1's reference answer; the
+    # Monte-Carlo-error test of the counter-based resampler compares against it)
+    shutil.copy(work / "full.pv", GOLD / "full.pv")
+    manifest["files"]["full.pv"] = md5(GOLD / "full.pv")
     orc.run_ref("makermt", ["-s", "1234", "-p", str(REF_EXAMPLE / "k10s"), "--paml", "mam15", "g10s"], work)
     orc.run_ref("consel", ["-r", "-c", "g10s"], work)
     for e in ("rmt", "pv", "ci", "cnt", "rep"):

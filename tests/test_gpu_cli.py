@@ -222,3 +222,37 @@ def test_makermt_extension_flags(gold, orc, tmp_path):
     assert all(np.isfinite(r).all() for r in ph["reps"])
     out = run("consel", ["ph"], tmp_path)
     assert "# exit normally" in out and (tmp_path / "ph.pv").exists()
+
+
+def test_full_size_mam15_pipeline_and_philox_within_monte_carlo_error(gold, orc):
+    """C1 at full size (10 x 10^4 replicates).  (1) Driven by the reference's seeded stream the in-process
+    pipeline reproduces the reference's own full-size .pv (tests/golden/full.pv, md5 pinned in
+    MANIFEST.json) to printed precision.  (2) The north star's third correctness clause: under an
+    INDEPENDENT generator (Philox, two different keys) every BP/KH/SH/wKH/wSH/AU/NP p-value agrees
+    with the reference's within Monte-Carlo error: 5 standard errors of the difference, the SEs being
+    the .pv SE columns (getseval, src/consel.c:2151-2158, and the AU fit's own SE)."""
+    import consel_b200 as cg
+    from consel_b200 import pipeline
+    cg.init()
+    cg.set_shard(0, 1)
+    L = orc.read_lnf(gold / "mam15.lnf")
+    rr, bb = [0.5, 0.6, 0.7, 0.8, 0.9, 1.0, 1.1, 1.2, 1.3, 1.4], [10000] * 10
+    ref = orc.read_pv(gold / "full.pv")
+    same = pipeline.run(L, rr, bb, 1234)
+    assert np.array_equal(same["item"], ref["item"])
+    assert np.allclose(same["pv"], ref["pv"], rtol=6e-9, atol=1e-12)
+    assert np.allclose(same["se"], ref["se"], rtol=6e-9, atol=1e-12)
+    runs = [pipeline.run(L, rr, bb, seed, rng_mode=cg.RNG_PHILOX, sum_mode=cg.SUM_INT8) for seed in (1234, 99)]
+    cols = [0, 2, 3, 4, 5, 6, 7]  # bp kh sh wkh wsh au np (column 1, pp, does not depend on the replicates)
+    pairs = [(runs[0], ref), (runs[1], ref), (runs[0], runs[1])]
+    worst = 0.0
+    for a, b in pairs:
+        assert np.array_equal(a["item"], b["item"])
+        assert np.array_equal(a["pv"][:, 1], b["pv"][:, 1]) or np.allclose(a["pv"][:, 1], b["pv"][:, 1], rtol=1e-12)
+        for c in cols:
+            tol = 5.0 * np.sqrt(a["se"][:, c] ** 2 + b["se"][:, c] ** 2) + 2.0e-4  # + two counts of 10^4
+            diff = np.abs(a["pv"][:, c] - b["pv"][:, c])
+            worst = max(worst, float(np.max(diff / tol)))
+            assert np.all(diff <= tol), (c, a["pv"][:, c], b["pv"][:, c], tol)
+    # and the generator is not accidentally the reference stream
+    assert not np.array_equal(runs[0]["cnt"], same["cnt"])

@@ -29,6 +29,43 @@ def test_sharded_pipeline_equals_single_gpu():
     assert out.stdout.count("== single GPU: True") == 8  # 2 ranks x 2 cases x 2 sum modes
 
 
+def test_makermt_and_consel_programs_on_two_gpus(tmp_path, gold):
+    """the command-line programs as one process per GPU (RANK / WORLD_SIZE / MASTER_PORT, no launcher
+    framework): .rmt/.vt/.pv/.ci/.cnt byte-equal to the single-GPU run of the same programs"""
+    import os
+    import shutil
+    if _ngpu() < 2:
+        pytest.skip("one GPU on this box")
+    bindir = ROOT / "consel_b200" / "bin"
+    for d in ("one", "two"):
+        (tmp_path / d).mkdir()
+        shutil.copy(gold / "mam15.lnf", tmp_path / d / "mam15.lnf")
+
+    def run(prog, args, cwd, world):
+        procs = []
+        port = 21000 + os.getpid() % 20000
+        for r in range(world):
+            env = dict(os.environ)
+            if world > 1:
+                env.update(RANK=str(r), WORLD_SIZE=str(world), LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+            else:
+                for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+                    env.pop(k, None)
+            procs.append(subprocess.Popen([str(bindir / prog)] + args, cwd=cwd, env=env, stdout=subprocess.PIPE, text=True))
+        outs = [p.communicate(timeout=600)[0] for p in procs]
+        assert all(p.returncode == 0 for p in procs), outs
+        return outs
+
+    for d, world in (("one", 1), ("two", 2)):
+        run("makermt", ["-s", "1234", "-b", "0.3", "--paml", "mam15", "x"], tmp_path / d, world)
+        outs = run("consel", ["-c", "x"], tmp_path / d, world)
+        if world > 1:
+            assert outs[1] == ""  # rank 0 speaks for the job
+    for ext in ("rmt", "vt", "pv", "ci", "cnt"):
+        a, b = (tmp_path / "one" / f"x.{ext}").read_bytes(), (tmp_path / "two" / f"x.{ext}").read_bytes()
+        assert a == b, ext
+
+
 @pytest.fixture(scope="module")
 def cg():
     import consel_b200 as cg

@@ -245,3 +245,54 @@ def test_equal_fill_chunks_same_result(cg, orc):
         cg.set_shard(0, 1)
         cg.set_option("stage", -1)
         cg.set_option("chunk_fill", -1)
+
+
+def test_site_pattern_compression_is_bit_identical(cg, orc, gold):
+    """mam15 (PAML input) has 1054 distinct columns among its 3414 sites: the int8 path contracts over pattern
+    slots (count rows and GEMM inner dimension 3x shorter) and must return the same bits as the
+    uncompressed contraction, for both generators, for a sharded run, and when a later call with
+    r > 4 cannot use the slots (site counts of a slot could pass 255) and falls back."""
+    L = orc.read_lnf(gold / "mam15.lnf")
+    K, n = L.shape
+    rr, bb = [0.5, 1.0, 1.4], [300, 257, 64]
+    _, bn, _ = orc.scale_setup(L, rr)
+    m = cg.Matrix(L)
+    try:
+        for mode in (cg.RNG_MT19937, cg.RNG_PHILOX):
+            cg.set_option("i8_patterns", 0)
+            plain = m.scaleboot(bn, bb, 5, rng_mode=mode, sum_mode=cg.SUM_INT8)
+            want = plain.download()
+            plain.free()
+            assert m.info()["patterns"] == 0
+            m.free()
+            m = cg.Matrix(L)
+            cg.set_option("i8_patterns", -1)
+            comp = m.scaleboot(bn, bb, 5, rng_mode=mode, sum_mode=cg.SUM_INT8)
+            got = comp.download()
+            comp.free()
+            npat = m.info()["patterns"]
+            assert 1054 <= npat <= 1054 + n // 32 + 8, npat  # distinct columns, plus the extra slots of patterns with > 32 sites
+            for s in range(3):
+                assert np.array_equal(got[s], want[s]), (mode, s)
+        # sharded over two ranks: the same columns
+        for rank in range(2):
+            cg.set_shard(rank, 2)
+            part = m.scaleboot(bn, bb, 5, rng_mode=cg.RNG_PHILOX, sum_mode=cg.SUM_INT8)
+            blocks = part.download()
+            part.free()
+            for s in range(3):
+                b0, b1 = cg.shard_range(bb[s])
+                assert np.array_equal(blocks[s], want[s][:, b0:b1])
+        cg.set_shard(0, 1)
+        # r = 5: the slots are dropped for this matrix, results equal the exact sums of the oracle's counts
+        _, bn5, rr5 = orc.scale_setup(L, [5.0])
+        big = m.scaleboot(bn5, [40], 9, sum_mode=cg.SUM_INT8)
+        got5 = big.download()[0]
+        big.free()
+        assert m.info()["patterns"] == 0
+        counts = cg.resample_counts(n, bn5, [40], 9, 0)
+        assert np.array_equal(got5, orc.exact_rounded_contract(L, counts, rr5[0]))
+    finally:
+        cg.set_option("i8_patterns", -1)
+        cg.set_shard(0, 1)
+        m.free()

@@ -84,3 +84,36 @@ def test_seqmt_paml_mt_and_stdio(gold, orc, tmp_path):
     a, b = run(EXE, [], tmp_path, stdin=txt), run(orc.ref_bin("seqmt"), [], tmp_path, stdin=txt)
     assert a.returncode == b.returncode == 0 and body(a.stdout) == body(b.stdout)
     assert run(EXE, ["--nope"], tmp_path).returncode == 1
+
+
+def _write_lnf(path: Path, m: int, p: int, seed: int, comment_at=None):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    reps = rng.integers(1, 5, size=p)
+    n = int(reps.sum())
+    s = f"  {m}  {n}  {p}\n\n"
+    for i in range(m):
+        s += f"\n {i + 1}\n\n"
+        v = -rng.exponential(4.0, size=p) - 1.0
+        for j in range(p):
+            if comment_at == (i, j):
+                s += "# a comment line in the middle of a tree block\n"
+            s += f"{j + 1:6d}{reps[j]:6d}{v[j]:16.10f}{rng.uniform(0, 99):9.2f}  ACGT\n"
+    path.write_text(s)
+    return n
+
+
+@pytest.mark.parametrize("comment_at", [None, (17, 400)])
+def test_parallel_paml_reader_equals_reference_binary(orc, tmp_path, comment_at):
+    """a .lnf large enough for the threaded tree-block parser (m*p >= 2^15); with a comment line inside a
+    block the parser must step aside and the serial loop reproduces the reference's reading"""
+    if orc.ref_bin("seqmt") is None:
+        pytest.skip("oracle/_ref/seqmt not built")
+    for d in ("ours", "ref"):
+        (tmp_path / d).mkdir()
+        _write_lnf(tmp_path / d / "big.lnf", 40, 900, 3, comment_at)
+    a = run(EXE, ["--paml", "big"], tmp_path / "ours")
+    b = run(orc.ref_bin("seqmt"), ["--paml", "big"], tmp_path / "ref")
+    assert a.returncode == b.returncode
+    assert body(a.stdout) == body(b.stdout)
+    if b.returncode == 0:
+        assert (tmp_path / "ours" / "big.mt").read_bytes() == (tmp_path / "ref" / "big.mt").read_bytes()

@@ -12,7 +12,7 @@ for f in sys.argv[1:]:
     e = d["e2e"]; print(f"   e2e {e['value']:.3e} ms {e['ms_per_step']:.2f} h2d {e['h2d_bytes_per_step']/1e6:.0f}MB d2h {e['d2h_bytes_per_step']/1e6:.0f}MB")
     print("   clocks", d["clocks"], "spot", {k: v for k, v in (d.get("spot_check") or {}).items() if k != "what"})
     print("   phases", {k: round(v, 2) for k, v in d["phases_ms_per_step"].items() if v})
-    r = d["roofline"]; print(f"   roofline: {r['kernel'][:40]} frac {r['frac']:.3f}; step floor {r['step']['floor_ms']:.2f} ms frac {r['step']['frac']:.3f}; i8 peak {r['int8_peak_tops_measured_live']:.0f}")
+    r = d["roofline"]; print(f"   roofline: {r['kernel'][:40]} frac {r['frac']:.3f}; step floor {r['step']['floor_ms']:.2f} ms frac {r['step']['frac']:.3f}; i8 peak {r['int8_peak_tops_measured_live']}")
     for k in r["kernels"]:
         print(f"      {k['kernel'][:48]:48s} {k['bound']:6s} {k['achieved']:9.1f}/{k['peak']:7.1f} {k['unit'][:10]:10s} frac {k['frac']:.3f} n={k['launches_per_step']:4d} {k['us_per_launch']:9.1f}us share {k['share_of_step']:.3f}")
     print("   modes", {k: round(v["ms_per_step"], 2) for k, v in d["modes"].items()})
