@@ -379,10 +379,13 @@ def run_ours(args) -> None:
     barrier()
     e2e_ms = max_over_ranks(e2e_ms)
     assert np.isfinite(checksum)
-
+    if world > 1:
+        # every collective of the run is behind us: all ranks tear the communicators down TOGETHER (NCCL's
+        # destroy waits for its peers); rank 0 then finishes the report alone
+        barrier()
+        cg.load().cgpu_comm_destroy()
+        dist.destroy_process_group()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
         return
 
     # ---- rooflines, measured live: every kernel of the step with its own bound
@@ -530,9 +533,6 @@ def run_ours(args) -> None:
         "spot_check": spot, "modes": modes, "pipeline": pipe,
     }
     print(json.dumps(line))
-    if world > 1:
-        cg.load().cgpu_comm_destroy()
-        dist.destroy_process_group()
 
 
 # ------------------------------------------------------------------------ reference

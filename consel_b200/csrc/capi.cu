@@ -538,13 +538,13 @@ static int scaleboot_core(DevMatrix &m, int S, const int *bn, const int *bb, uns
     // columns of L are looked for: with pattern slots the count rows and the GEMM get shorter.
     bool fx_ready = !i8;
     const bool fx_early = i8 && (!host_out || (size_t)m.K * (size_t)n <= ((size_t)8 << 20));
-    const bool allow_patterns = fx_early && (double)max_bn <= 4.0 * (double)n && G().opt_draw_fuse != 1;
+    const bool allow_patterns = fx_early && (double)max_bn <= 4.0 * (double)n && G().opt_draw_fuse != 1 && G().opt_i8_patterns != 0;
     auto ensure_fx = [&]() -> int {
         if (fx_ready) return CGPU_OK;
         pt.begin(0);
         CGPU_TRY(fx_prepare(m, st, allow_patterns));
         pt.end();
-        if (fx_needs_partial(m, max_bn))
+        if (fx_needs_partial(m, max_bn, batch))
             CGPU_CUDA(scratch_get(3, m.fxMpad * (size_t)batch * sizeof(int), reinterpret_cast<void **>(&d_partial)));
         fx_ready = true;
         return CGPU_OK;
@@ -1003,6 +1003,7 @@ int cgpu_init(int device) {
 void cgpu_shutdown(void) {
     Globals &g = G();
     if (!g.inited) return;
+    cgpu_comm_destroy();  // (every rank of a job should get here: NCCL tears a communicator down together)
     cudaStreamSynchronize(g.stream);
     dev_free(g.d_jump_table);
     jump_cache_clear();
@@ -1060,6 +1061,7 @@ int cgpu_set_option(const char *name, int value) {
     else if (!strcmp(name, "batch")) g.opt_batch = value;
     else if (!strcmp(name, "i8_panel")) g.opt_i8_panel = value;
     else if (!strcmp(name, "i8_patterns")) g.opt_i8_patterns = value;
+    else if (!strcmp(name, "i8_ksplit")) g.opt_i8_ksplit = value;
     else if (!strcmp(name, "dist_upload")) g.opt_dist_upload = value;
     else {
         set_error(CGPU_EINVAL, "unknown option %s", name);

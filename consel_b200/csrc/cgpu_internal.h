@@ -84,7 +84,7 @@ struct Globals {
     void *scratch[4] = {nullptr, nullptr, nullptr, nullptr};
     size_t scratch_cap[4] = {0, 0, 0, 0};
     // tuning switches (cgpu_set_option); -1 = built-in default
-    int opt_overlap = -1, opt_hist_algo = -1, opt_contract_algo = -1, opt_i8_oneshot = -1, opt_draw_nch = -1, opt_chunk_log2 = -1, opt_i8_fuse = -1, opt_draw_fuse = -1, opt_stage = -1, opt_i8_dbg = -1, opt_mc_smooth = -1, opt_chunk_fill = -1, opt_ktime = -1, opt_hist_wide = -1, opt_i8_2cta = -1, opt_batch = -1, opt_dist_upload = -1, opt_i8_panel = -1, opt_i8_patterns = -1;
+    int opt_overlap = -1, opt_hist_algo = -1, opt_contract_algo = -1, opt_i8_oneshot = -1, opt_draw_nch = -1, opt_chunk_log2 = -1, opt_i8_fuse = -1, opt_draw_fuse = -1, opt_stage = -1, opt_i8_dbg = -1, opt_mc_smooth = -1, opt_chunk_fill = -1, opt_ktime = -1, opt_hist_wide = -1, opt_i8_2cta = -1, opt_batch = -1, opt_dist_upload = -1, opt_i8_panel = -1, opt_i8_patterns = -1, opt_i8_ksplit = -1;
 };
 Globals &G();
 int ensure_init();
@@ -210,7 +210,7 @@ int launch_contract(const DevMatrix &m, const unsigned long long *d_counts, int 
 // uncompressed when a later call cannot use the compression)
 int fx_prepare(DevMatrix &m, cudaStream_t st, bool allow_patterns = false);
 // does the tensor-core path need the int32 partial-sum buffer (recombination outside the GEMM epilogue)?
-bool fx_needs_partial(const DevMatrix &m, int max_draws);
+bool fx_needs_partial(const DevMatrix &m, int max_draws, int max_nb_pad);
 struct PhaseTimer;
 int launch_contract_i8(const DevMatrix &m, const unsigned char *d_counts_rows, int nb, int nb_pad, int *d_partial,
                        double r, double *d_rep, int ldrep, int col0, cudaStream_t st, PhaseTimer *pt = nullptr,

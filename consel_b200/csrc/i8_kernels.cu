@@ -639,7 +639,7 @@ __device__ __forceinline__ void fx_finish_regs(const uint32_t (&v)[32], int k0, 
 template <int STAGES, int EW>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(64 + 32 * EW, 1)
 gemm_i8_2cta_kernel(const __grid_constant__ CUtensorMap mapC, const __grid_constant__ CUtensorMap mapD, int NP,
-                    int *__restrict__ P, int ldp, int p_rows, int c_tiles, int d_tiles, int panel_w, FxEpilogue ep) {
+                    int *__restrict__ P, int ldp, int p_rows, int c_tiles, int d_tiles, int panel_w, int ksplit, FxEpilogue ep) {
     extern __shared__ unsigned char g8_raw[];
     unsigned char *base = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(g8_raw) + 1023) & ~(uintptr_t)1023);
     unsigned char *sC = base;
@@ -655,7 +655,9 @@ gemm_i8_2cta_kernel(const __grid_constant__ CUtensorMap mapC, const __grid_const
     const bool leader = rank == 0;
     const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
     const int nkb = NP / G8_BK;
-    const int total_tiles = c_tiles * d_tiles;
+    // work items: (tile, part of the site axis).  ksplit > 1 (few tiles, very long rows: C4) lets every
+    // pair work; the int32 partial sums of the parts are added with red.global (exact, order free)
+    const int total_tiles = c_tiles * d_tiles * ksplit;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; s++) {
@@ -682,10 +684,12 @@ gemm_i8_2cta_kernel(const __grid_constant__ CUtensorMap mapC, const __grid_const
             int it = 0;  // k-block counter across tiles
             for (int tile = pair; tile < total_tiles; tile += npairs) {
                 int ct, dt;
-                g2_tile_coords(tile, c_tiles, d_tiles, panel_w, ct, dt);
+                g2_tile_coords(tile / ksplit, c_tiles, d_tiles, panel_w, ct, dt);
+                const int kp = tile % ksplit;
+                const int kb0 = (int)((long long)nkb * kp / ksplit), kb1 = (int)((long long)nkb * (kp + 1) / ksplit);
                 const int row_c = ct * 256 + (int)rank * 128;
                 const int row_d = dt * 256 + (int)rank * 128;
-                for (int kb = 0; kb < nkb; kb++, it++) {
+                for (int kb = kb0; kb < kb1; kb++, it++) {
                     const int s = it % STAGES;
                     mb_wait(&empty[s], ((it / STAGES) & 1) ^ 1);
                     if (leader) mb_expect(&full[s], (uint32_t)(4 * G2_OP_BYTES));  // both operands of both CTAs
@@ -704,13 +708,15 @@ gemm_i8_2cta_kernel(const __grid_constant__ CUtensorMap mapC, const __grid_const
                 mb_wait(&acc_empty[acc], ((tcount >> 1) & 1) ^ 1);  // both epilogues have drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t d_tmem = tmem + (uint32_t)(acc * G8_BN);
-                for (int kb = 0; kb < nkb; kb++, it++) {
+                const int kp = tile % ksplit;
+                const int kb0 = (int)((long long)nkb * kp / ksplit), kb1 = (int)((long long)nkb * (kp + 1) / ksplit);
+                for (int kb = kb0; kb < kb1; kb++, it++) {
                     const int s = it % STAGES;
                     mb_wait(&full[s], (it / STAGES) & 1);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint64_t ad = umma_desc_sw128(sC + s * G2_OP_BYTES), bd = umma_desc_sw128(sD + s * G2_OP_BYTES);
 #pragma unroll
-                    for (int k = 0; k < G8_BK / 32; k++) umma_i8_2sm(d_tmem, ad + 2 * k, bd + 2 * k, idesc, (kb | k) ? 1u : 0u);
+                    for (int k = 0; k < G8_BK / 32; k++) umma_i8_2sm(d_tmem, ad + 2 * k, bd + 2 * k, idesc, ((kb - kb0) | k) ? 1u : 0u);
                     umma_commit_2sm(&empty[s]);
                 }
                 umma_commit_2sm(&acc_full[acc]);
@@ -726,7 +732,7 @@ gemm_i8_2cta_kernel(const __grid_constant__ CUtensorMap mapC, const __grid_const
         for (int tile = pair; tile < total_tiles; tile += npairs, tcount++) {
             const int acc = tcount & 1;
             int ct, dt;
-            g2_tile_coords(tile, c_tiles, d_tiles, panel_w, ct, dt);
+            g2_tile_coords(tile / ksplit, c_tiles, d_tiles, panel_w, ct, dt);
             const int b = ct * 256 + (int)rank * 128 + q * 32 + lane;  // this thread's replicate (column of the batch)
             const int n_base = dt * 256;                               // first digit row of the tile
             mb_wait(&acc_full[acc], (tcount >> 1) & 1);
@@ -754,9 +760,15 @@ gemm_i8_2cta_kernel(const __grid_constant__ CUtensorMap mapC, const __grid_const
                 const int n0 = n_base + c;
                 if (ep.rep == nullptr) {
                     if (b < ldp) {
+                        if (ksplit > 1) {
 #pragma unroll
-                        for (int i = 0; i < 32; i++)
-                            if (n0 + i < p_rows) P[(size_t)(n0 + i) * ldp + b] = (int)v[i];
+                            for (int i = 0; i < 32; i++)
+                                if (n0 + i < p_rows) atomicAdd(&P[(size_t)(n0 + i) * ldp + b], (int)v[i]);  // RED.ADD: no return value used
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; i++)
+                                if (n0 + i < p_rows) P[(size_t)(n0 + i) * ldp + b] = (int)v[i];
+                        }
                     }
                     continue;
                 }
@@ -789,8 +801,18 @@ __global__ void __launch_bounds__(64, 1) i8_peak_kernel(int iters) {
     uint64_t *done = reinterpret_cast<uint64_t *>(base + 2 * (G8_A_BYTES + G8_B_BYTES));
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(done + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (size_t i = threadIdx.x; i < 2 * (G8_A_BYTES + G8_B_BYTES) / 16; i += blockDim.x)
-        reinterpret_cast<uint4 *>(base)[i] = make_uint4(0x01010101u, 0x01010101u, 0x01010101u, 0x01010101u);
+    // pseudo-random operand bytes: the power a tensor instruction draws depends on how many operand
+    // bits toggle, and the sustained rate is a power-limited figure
+    for (size_t i = threadIdx.x; i < 2 * (G8_A_BYTES + G8_B_BYTES) / 16; i += blockDim.x) {
+        uint32_t h = (uint32_t)i * 2654435761u + blockIdx.x * 40503u;
+        uint32_t w[4];
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            h ^= h >> 15; h *= 2246822519u; h ^= h >> 13; h *= 3266489917u; h ^= h >> 16;
+            w[t] = h;
+        }
+        reinterpret_cast<uint4 *>(base)[i] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
     if (threadIdx.x == 0) {
         mb_init(done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -1000,14 +1022,29 @@ static int fx_find_patterns(DevMatrix &m, cudaStream_t st, std::vector<unsigned 
     return CGPU_OK;
 }
 
+// Parts of the site axis per tile of the pair GEMM: 1 unless the tile grid leaves most pairs idle
+// while the rows are very long (C4: K=100, n=10^7 -> 4 x 5 tiles of 78125 k-blocks for 74 pairs)
+static int g2_ksplit(const DevMatrix &m, int nb_pad) {
+    const int sms = G().sm_count > 0 ? G().sm_count : 148;
+    const int npairs = sms / 2;
+    const long long tiles = (long long)(nb_pad / 256) * (long long)((m.fxMpad + 255) / 256);
+    const int nkb = m.NPc / G8_BK;
+    if (tiles <= 0 || tiles * 2 > npairs || nkb < 512 || G().opt_i8_ksplit == 0) return 1;
+    int ks = (int)std::min<long long>({(long long)(2 * npairs / tiles), (long long)(nkb / 128), 32LL});
+    if (G().opt_i8_ksplit > 0) ks = G().opt_i8_ksplit;
+    return std::max(1, ks);
+}
+
 static bool fx_can_fuse(const DevMatrix &m, int max_draws) {
     // S <= 8 dividing 8, a scale 2^-F that is a normal double, and group sums that are exact in fp64
     return m.fxS <= 8 && 8 % m.fxS == 0 && G().opt_i8_fuse != 0 && m.fxF > -1000 && m.fxF < 1000 && max_draws < (1 << 21);
 }
-bool fx_needs_partial(const DevMatrix &m, int max_draws) {
+bool fx_needs_partial(const DevMatrix &m, int max_draws, int max_nb_pad) {
     static const bool env_one_shot = getenv("CGPU_I8_ONESHOT") != nullptr;
     const bool one_shot = G().opt_i8_oneshot >= 0 ? G().opt_i8_oneshot != 0 : env_one_shot;
-    return one_shot || !fx_can_fuse(m, max_draws);
+    // (the smallest batch of a call, 256 replicates, is the one that may want the split)
+    (void)max_nb_pad;
+    return one_shot || !fx_can_fuse(m, max_draws) || g2_ksplit(m, 256) > 1 || G().opt_i8_ksplit > 1;
 }
 
 int fx_prepare(DevMatrix &m, cudaStream_t st, bool allow_patterns) {
@@ -1086,7 +1123,10 @@ int launch_contract_i8(const DevMatrix &m, const unsigned char *d_counts_rows, i
     // the recombination runs in the GEMM epilogue when the digits of a tree stay inside one
     // 32-row epilogue slab ("i8_fuse" 0 keeps the two-kernel form for measurements)
     // (S <= 8, a scale 2^-F that is a normal double, and group sums that are exact in fp64)
-    const bool fused = !one_shot && fx_can_fuse(m, max_draws);
+    const bool two_cta = !one_shot && (G().opt_i8_2cta == 1 || (G().opt_i8_2cta != 0 && m.NPc / G8_BK > 48)) &&
+                         (G().sm_count % 2 == 0 || G().sm_count <= 0);
+    const int ksplit = (two_cta && d_partial) ? g2_ksplit(m, nb_pad) : 1;
+    const bool fused = !one_shot && fx_can_fuse(m, max_draws) && ksplit == 1;
     if (!fused && !d_partial) {
         set_error(CGPU_EINVAL, "launch_contract_i8: no partial-sum buffer for the unfused recombination");
         return CGPU_EINVAL;
@@ -1095,8 +1135,6 @@ int launch_contract_i8(const DevMatrix &m, const unsigned char *d_counts_rows, i
     const int m_tiles = (int)(m.fxMpad / G8_BM), n_tiles = nb_pad / G8_BN;
     // cta_group::2 pairs for long tiles; short tiles (C2: 27 k-blocks) are bound by the epilogue's
     // divisions, where the one-CTA kernel with twelve epilogue warps is faster (measured 2.2 vs 3.0 ms)
-    const bool two_cta = !one_shot && (G().opt_i8_2cta == 1 || (G().opt_i8_2cta != 0 && m.NPc / G8_BK > 48)) &&
-                         (G().sm_count % 2 == 0 || G().sm_count <= 0);
     if (two_cta) {
         // cta_group::2: replicates on the M side (count rows are operand A), digit rows on N
         CUtensorMap mapC, mapD;
@@ -1109,12 +1147,13 @@ int launch_contract_i8(const DevMatrix &m, const unsigned char *d_counts_rows, i
         }
         const int c_tiles = nb_pad / 256, d_tiles = (int)((m.fxMpad + 255) / 256);
         const int sms = G().sm_count > 0 ? G().sm_count : 148;
-        const int grid = std::min(sms / 2 * 2, 2 * c_tiles * d_tiles);
+        const int grid = std::min(sms / 2 * 2, 2 * c_tiles * d_tiles * ksplit);
+        if (ksplit > 1) CGPU_CUDA(cudaMemsetAsync(d_partial, 0, m.fxMpad * (size_t)nb_pad * sizeof(int), st));  // the parts add into it
         FxEpilogue ep{fused ? d_rep : nullptr, r, {(m.fxF > -1000 && m.fxF < 1000) ? std::ldexp(1.0, -m.fxF) : 0.0, m.fxF},
                       m.K, m.fxS, nb, ldrep, col0, G().opt_i8_dbg > 0 ? G().opt_i8_dbg : 0};
         gemm_i8_2cta_kernel<6, 8><<<grid, G2P<6, 8>::threads, G2P<6, 8>::smem, st>>>(mapC, mapD, m.NPc, d_partial, nb_pad, (int)m.fxMpad,
                                                                                      c_tiles, d_tiles,
-                                                                                     G().opt_i8_panel >= 0 ? G().opt_i8_panel : 8, ep);
+                                                                                     G().opt_i8_panel >= 0 ? G().opt_i8_panel : 8, ksplit, ep);
     } else if (one_shot) {
         dim3 grid((unsigned)m_tiles, (unsigned)n_tiles);
         gemm_i8_kernel<<<grid, G8_THREADS, G8_SMEM, st>>>(mapA, mapB, m.NPc, d_partial, nb_pad, nb_pad);

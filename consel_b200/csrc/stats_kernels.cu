@@ -137,35 +137,36 @@ __device__ __forceinline__ double row_value(const RowSrc &s, int row, int b, int
 }
 
 // one CTA per row; nq thresholds per row: thr[row*nq + q]; out[(row*out_stride + out_off)*nq + q]
-template <int MODE>
+// QCAP: compile-time capacity of the per-thread summaries (1 for the KH/SH tests, whose rows
+// have one threshold: 48 registers and full occupancy instead of ~200 and 12 %)
+template <int MODE, int QCAP>
 __global__ void __launch_bounds__(RS_THREADS)
 rowsum_kernel(RowSrc src, int B, int nq, const double *__restrict__ thr, cgpu_rowsum *__restrict__ out,
               int out_stride, int out_off) {
     const int row = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    __shared__ double s_thr[RS_MAXQ];
-    __shared__ unsigned long long s_cnt[RS_THREADS / 32][RS_MAXQ];
-    __shared__ double s_lo[RS_THREADS / 32][RS_MAXQ], s_hi[RS_THREADS / 32][RS_MAXQ];
+    __shared__ double s_thr[QCAP];
+    __shared__ unsigned long long s_cnt[RS_THREADS / 32][QCAP];
+    __shared__ double s_lo[RS_THREADS / 32][QCAP], s_hi[RS_THREADS / 32][QCAP];
     __shared__ double s_edge[RS_THREADS / 32][4];
     if (tid < nq) s_thr[tid] = thr[(size_t)row * nq + tid];
     __syncthreads();
     const int i_row = (MODE == 0) ? 0 : src.ia[row];
     const int j_row = (MODE == 1) ? src.ja[row] : 0;
 
-    unsigned long long cnt[RS_MAXQ];
-    double lo[RS_MAXQ], hi[RS_MAXQ];
+    unsigned long long cnt[QCAP];
+    double lo[QCAP], hi[QCAP];
 #pragma unroll
-    for (int q = 0; q < RS_MAXQ; q++) {
+    for (int q = 0; q < QCAP; q++) {
         cnt[q] = 0;
         lo[q] = -CG_HUGE;
         hi[q] = CG_HUGE;
     }
     double mn1 = CG_HUGE, mn2 = CG_HUGE, mx1 = -CG_HUGE, mx2 = -CG_HUGE;
-    for (int b = tid; b < B; b += RS_THREADS) {
-        const double v = row_value<MODE>(src, row, b, i_row, j_row);
+    auto take = [&](double v) {
         edge_insert(v, mn1, mn2, mx1, mx2);
 #pragma unroll
-        for (int q = 0; q < RS_MAXQ; q++) {
+        for (int q = 0; q < QCAP; q++) {
             if (q < nq) {
                 const double t = s_thr[q];
                 if (v <= t) {
@@ -176,12 +177,24 @@ rowsum_kernel(RowSrc src, int B, int nq, const double *__restrict__ thr, cgpu_ro
                 }
             }
         }
+    };
+    int b = tid;
+    for (; b + 3 * RS_THREADS < B; b += 4 * RS_THREADS) {  // four rows of loads in flight
+        const double v0 = row_value<MODE>(src, row, b, i_row, j_row);
+        const double v1 = row_value<MODE>(src, row, b + RS_THREADS, i_row, j_row);
+        const double v2 = row_value<MODE>(src, row, b + 2 * RS_THREADS, i_row, j_row);
+        const double v3 = row_value<MODE>(src, row, b + 3 * RS_THREADS, i_row, j_row);
+        take(v0);
+        take(v1);
+        take(v2);
+        take(v3);
     }
+    for (; b < B; b += RS_THREADS) take(row_value<MODE>(src, row, b, i_row, j_row));
     // warp reduce, then across warps through shared memory
 #pragma unroll
     for (int off = 16; off; off >>= 1) {
 #pragma unroll
-        for (int q = 0; q < RS_MAXQ; q++) {
+        for (int q = 0; q < QCAP; q++) {
             if (q < nq) {
                 cnt[q] += __shfl_xor_sync(0xffffffffu, cnt[q], off);
                 lo[q] = fmax(lo[q], __shfl_xor_sync(0xffffffffu, lo[q], off));
@@ -194,7 +207,7 @@ rowsum_kernel(RowSrc src, int B, int nq, const double *__restrict__ thr, cgpu_ro
     }
     if (lane == 0) {
 #pragma unroll
-        for (int q = 0; q < RS_MAXQ; q++)
+        for (int q = 0; q < QCAP; q++)
             if (q < nq) {
                 s_cnt[wid][q] = cnt[q];
                 s_lo[wid][q] = lo[q];
@@ -568,9 +581,15 @@ int launch_rowsum(int mode, const RowSrc &src, int rows, int B, int nq, const do
         return CGPU_EINVAL;
     }
     KT kt(mode == 0 ? "rowsum_kernel<plain>" : mode == 1 ? "rowsum_kernel<kh>" : "rowsum_kernel<sh>", st, (mode == 1 ? 16.0 : 8.0) * rows * B);
-    if (mode == 0) rowsum_kernel<0><<<rows, RS_THREADS, 0, st>>>(src, B, nq, d_thr, d_out, out_stride, out_off);
-    else if (mode == 1) rowsum_kernel<1><<<rows, RS_THREADS, 0, st>>>(src, B, nq, d_thr, d_out, out_stride, out_off);
-    else rowsum_kernel<2><<<rows, RS_THREADS, 0, st>>>(src, B, nq, d_thr, d_out, out_stride, out_off);
+#define CGPU_RS(M_)                                                                                                  \
+    do {                                                                                                             \
+        if (nq == 1) rowsum_kernel<M_, 1><<<rows, RS_THREADS, 0, st>>>(src, B, nq, d_thr, d_out, out_stride, out_off);        \
+        else rowsum_kernel<M_, RS_MAXQ><<<rows, RS_THREADS, 0, st>>>(src, B, nq, d_thr, d_out, out_stride, out_off);          \
+    } while (0)
+    if (mode == 0) CGPU_RS(0);
+    else if (mode == 1) CGPU_RS(1);
+    else CGPU_RS(2);
+#undef CGPU_RS
     CGPU_LAUNCH_CHECK();
     return CGPU_OK;
 }
@@ -690,34 +709,35 @@ center_rows_kernel(const double *__restrict__ x, int K, int B, int ld, double *_
 // pairwise variances -> weights (src/consel.c:1404-1415):
 //   wt[i][j] = 1/sqrt((sum_b (x_i - x_j)^2 + varadd)/(B-1)), sum in replicate order.
 // 16x16 pairs per CTA, one pair per thread, replicates staged through shared memory.
-constexpr int PV_T = 16, PV_BC = 64;
+constexpr int PV_T = 32, PV_BC = 64;  // 32 x 32 pairs per CTA (256 threads, 2 x 2 pairs each), 64 replicates per stage
 // rows == nullptr: all pairs, lower triangle computed once and mirrored (grid t x t).
-// rows != nullptr: only the weight rows i = rows[0..nrows) against every j (grid t x ceil(nrows/16)):
+// rows != nullptr: only the weight rows i = rows[0..nrows) against every j (grid t x ceil(nrows/32)):
 // a rank of a sharded run needs the rows of its own members only.  (x_i - x_j)^2 is the same
 // value whichever of the two is "i", so both forms give bit-identical weights.
-__global__ void __launch_bounds__(PV_T * PV_T)
+// Every thread owns 2 x 2 pairs: four shared-memory loads feed twelve fp64 operations per
+// replicate (one pair per thread was bound by its two loads per three operations).
+__global__ void __launch_bounds__(256)
 pair_weight_kernel(const double *__restrict__ xc, int K, int B, int ld, double varadd, double *__restrict__ wt,
                    int *__restrict__ nsmall, const int *__restrict__ rows, int nrows) {
     const int ti = blockIdx.y, tj = blockIdx.x;
     if (!rows && tj > ti) return;
     __shared__ double si[PV_T][PV_BC + 1], sj[PV_T][PV_BC + 1];
     __shared__ int s_row[PV_T];
-    const int tx = threadIdx.x % PV_T, ty = threadIdx.x / PV_T;  // pair (i = row ty of tile ti, j = tj*16+tx)
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // pairs (row ty / ty+16 of tile ti) x (tx / tx+16 of tile tj)
     if (threadIdx.x < PV_T) {
         const int r = ti * PV_T + threadIdx.x;
         s_row[threadIdx.x] = rows ? (r < nrows ? rows[r] : -1) : (r < K ? r : -1);
     }
     __syncthreads();
-    const int i = s_row[ty], j = tj * PV_T + tx;
-    // staging: thread e loads rows r = e/64 (+4, +8, +12) at column e%64 of both tiles; the next
+    // staging: thread e loads rows r = e/64 (+4, +8, ... +28) at column e%64 of both tiles; the next
     // chunk is fetched into registers while the current one is consumed from shared memory
-    constexpr int PER = PV_T * PV_BC / (PV_T * PV_T);  // 4 elements per thread and tile
+    constexpr int PER = PV_T * PV_BC / 256;  // 8 elements per thread and tile
     const int lc = threadIdx.x % PV_BC, lr = threadIdx.x / PV_BC;
     double ni[PER], nj[PER];
     auto fetch = [&](int b0) {
 #pragma unroll
         for (int u = 0; u < PER; u++) {
-            const int r = lr + u * (PV_T * PV_T / PV_BC);
+            const int r = lr + u * (256 / PV_BC);
             const int b = b0 + lc;
             const int gi = s_row[r], gj = tj * PV_T + r;
             ni[u] = (gi >= 0 && b < B) ? xc[(size_t)gi * ld + b] : 0.0;
@@ -725,51 +745,47 @@ pair_weight_kernel(const double *__restrict__ xc, int K, int B, int ld, double v
         }
     };
     fetch(0);
-    double acc = 0.0;
+    double acc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
     for (int b0 = 0; b0 < B; b0 += PV_BC) {
 #pragma unroll
         for (int u = 0; u < PER; u++) {
-            const int r = lr + u * (PV_T * PV_T / PV_BC);
+            const int r = lr + u * (256 / PV_BC);
             si[r][lc] = ni[u];
             sj[r][lc] = nj[u];
         }
         __syncthreads();
         fetch(b0 + PV_BC);
         const int m = min(PV_BC, B - b0);
-        if (m == PV_BC) {
-            // squares first (independent), then the chain of rounded adds in replicate order
-#pragma unroll
-            for (int c0 = 0; c0 < PV_BC; c0 += 8) {
-                double q[8];
-#pragma unroll
-                for (int c = 0; c < 8; c++) {
-                    const double d = __dsub_rn(si[ty][c0 + c], sj[tx][c0 + c]);
-                    q[c] = __dmul_rn(d, d);
-                }
-#pragma unroll
-                for (int c = 0; c < 8; c++) acc = __dadd_rn(acc, q[c]);
-            }
-        } else {
-            for (int c = 0; c < m; c++) {
-                double d = __dsub_rn(si[ty][c], sj[tx][c]);
-                acc = __dadd_rn(acc, __dmul_rn(d, d));
-            }
+        // per pair: the chain of rounded adds in replicate order (the squares are independent)
+#pragma unroll 8
+        for (int c = 0; c < m; c++) {
+            const double a0 = si[ty][c], a1 = si[ty + 16][c], b0v = sj[tx][c], b1v = sj[tx + 16][c];
+            double d;
+            d = __dsub_rn(a0, b0v); acc[0][0] = __dadd_rn(acc[0][0], __dmul_rn(d, d));
+            d = __dsub_rn(a0, b1v); acc[0][1] = __dadd_rn(acc[0][1], __dmul_rn(d, d));
+            d = __dsub_rn(a1, b0v); acc[1][0] = __dadd_rn(acc[1][0], __dmul_rn(d, d));
+            d = __dsub_rn(a1, b1v); acc[1][1] = __dadd_rn(acc[1][1], __dmul_rn(d, d));
         }
         __syncthreads();
     }
-    if (i < 0 || j >= K) return;
-    if (i == j) {
-        wt[(size_t)i * K + i] = 0.0;
-        return;
-    }
-    if (!rows && j > i) return;
-    // VARADDWARN (src/consel.c:154,1409) counts every pair once: in the row-subset form the pair is
-    // counted by the row with the larger tree index when both rows are present -- the caller only
-    // uses the count on single-device runs
-    if (acc < varadd * 100.0 && (!rows || j < i)) atomicAdd(nsmall, 1);
-    double w = __ddiv_rn(1.0, __dsqrt_rn(__ddiv_rn(__dadd_rn(acc, varadd), (double)(B - 1))));
-    wt[(size_t)i * K + j] = w;
-    if (!rows) wt[(size_t)j * K + i] = w;
+#pragma unroll
+    for (int p = 0; p < 2; p++)
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            const int i = s_row[ty + 16 * p], j = tj * PV_T + tx + 16 * q;
+            if (i < 0 || j >= K) continue;
+            if (i == j) {
+                wt[(size_t)i * K + i] = 0.0;
+                continue;
+            }
+            if (!rows && j > i) continue;
+            // VARADDWARN (src/consel.c:154,1409) counts every pair once: in the row-subset form the pair is
+            // counted by the row with the larger tree index -- the caller only uses the count on single-device runs
+            if (acc[p][q] < varadd * 100.0 && (!rows || j < i)) atomicAdd(nsmall, 1);
+            const double w = __ddiv_rn(1.0, __dsqrt_rn(__ddiv_rn(__dadd_rn(acc[p][q], varadd), (double)(B - 1))));
+            wt[(size_t)i * K + j] = w;
+            if (!rows) wt[(size_t)j * K + i] = w;
+        }
 }
 
 // SH statistic rows for general association sets (src/consel.c:2026-2030, 2017-2024):
@@ -948,7 +964,7 @@ int launch_pair_weight(const double *xc, int K, int B, int ld, double varadd, do
     const int ty = d_rows ? (nrows + PV_T - 1) / PV_T : t;
     if (ty <= 0) return CGPU_OK;
     KT kt("pair_weight_kernel", st, 3.0 * B * (d_rows ? (double)nrows * (K - 1) : 0.5 * K * (K - 1)));  // (sub, mul, add) per pair and replicate
-    pair_weight_kernel<<<dim3(t, ty), PV_T * PV_T, 0, st>>>(xc, K, B, ld, varadd, wt, nsmall, d_rows, nrows);
+    pair_weight_kernel<<<dim3(t, ty), 256, 0, st>>>(xc, K, B, ld, varadd, wt, nsmall, d_rows, nrows);
     CGPU_LAUNCH_CHECK();
     return CGPU_OK;
 }

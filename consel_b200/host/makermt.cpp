@@ -268,6 +268,6 @@ int main(int argc, char **argv) {
         genrmt(P, fname_mt, fname_rmt);
     }
     printf("\n# exit normally\n");
-    cgpu_shutdown();
+    cgpu_shutdown();  // (also tears the communicator down, on every rank)
     return 0;
 }

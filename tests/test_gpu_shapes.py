@@ -180,3 +180,24 @@ def test_more_than_32_scales_row_range_query(cg, orc):
     part = reps.count_query_rows(7, thr[7:15])
     assert part.tobytes() == whole[7:15].tobytes()
     reps.free()
+
+
+def test_split_k_pair_gemm(cg, orc):
+    """few tiles, long rows (the C4 shape in small): the site axis of a pair-GEMM tile is cut into parts whose
+    int32 partial sums are added with red.global; same bits as the unsplit kernel and as the exact sums"""
+    K, n = 12, 150000  # 96 digit rows -> 1 digit tile; 1172 k-blocks
+    L = synth(K, n, seed=4)
+    rr, bb = [0.5, 1.2], [40, 300]
+    _, bn, rr1 = orc.scale_setup(L, rr)
+    base = cg.scaleboot_all(L, bn, bb, 13, sum_mode=cg.SUM_INT8)
+    outs = {}
+    for ks in (1, 3, 8):
+        cg.set_option("i8_ksplit", ks if ks > 1 else 0)
+        outs[ks] = cg.scaleboot_all(L, bn, bb, 13, sum_mode=cg.SUM_INT8)
+    cg.set_option("i8_ksplit", -1)
+    for s in range(2):
+        for ks in (1, 3, 8):
+            assert np.array_equal(outs[ks][s], base[s]), (ks, s)
+    counts = orc.scaleboot_counts(n, bn, [4, 4], 13)
+    want = exact_sums(L[[0, K - 1]], counts[0], rr1[0])
+    assert np.array_equal(base[0][[0, K - 1]][:, :4], want)
