@@ -399,7 +399,8 @@ def run_ours(args) -> None:
     peak_src = "MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"
     # a tensor-bound kernel inside a long step runs at the clock the power limit allows: grade it against the
     # sustained rate there (B200_PROFILING.md), against the burst rate when the steps are short
-    long_step = dev_ms / args.steps > 50.0
+    # (evidence: the clock sampler saw the SMs below 95 % of their maximum during the timed steps)
+    long_step = bool(clocks and clocks.get("sm_mhz") and clocks.get("sm_max_mhz") and clocks["sm_mhz"] < 0.95 * clocks["sm_max_mhz"])
     i8_peak = live["int8_tops_sustained"] if long_step else live["int8_tops"]
     fp64_peak = live["fp64_tflops"]
     traffic_db = {}
@@ -453,8 +454,8 @@ def run_ours(args) -> None:
               2.0 * S_SLICES * K * N_SITES * b_loc * nS / gemm_launches, i8_peak, "TOP/s (int8)",
               f"2*S int8-ops per tree-site accumulation (SURVEY 8d), S={S_SLICES} slices, x K*n*B_s per launch",
               "peak = tcgen05.mma kind::i8 issue rate from smem-resident operands measured in this run: "
-              + ("cgpu_bench_i8_peak_sustained (2 s back to back: the step is long and the board power-caps)" if long_step
-                 else "cgpu_bench_i8_peak (burst, idle device: the steps are short)")),
+              + ("cgpu_bench_i8_peak_sustained (2 s back to back, random operand bytes: the timed steps ran power-capped, "
+                 "see `clocks`)" if long_step else "cgpu_bench_i8_peak (burst, idle device: the timed steps kept full clocks)")),
         entry("fx_combine_kernel", "fx_combine_kernel (exact int128 recombination of the S slice sums, one rounding, /r)",
               phases["fx_combine"], nS, "hbm", 4.0 * M_PAD * b_loc + 8.0 * K * b_loc, hbm_peak, "GB/s",
               "4 B x Mpad int32 partial sums read + 8 B x K doubles written per replicate"),

@@ -923,6 +923,7 @@ int cgpu_version(void) { return 100; }
 void cgpu_host_rowsums(const double *L, int K, int n, double *datvec) {
     if (!L || !datvec || K <= 0) return;
     unsigned hw = std::thread::hardware_concurrency();
+    if (const char *e = getenv("LOCAL_WORLD_SIZE")) hw = std::max(1u, hw / (unsigned)std::max(1, atoi(e)));  // one process per GPU shares the host
     int nt = (int)std::min<unsigned>(hw ? hw : 1, (unsigned)K);
     if ((long long)K * n < (1 << 20)) nt = 1;
     auto work = [&](int t) {

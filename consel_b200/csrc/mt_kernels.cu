@@ -58,8 +58,10 @@ __device__ __forceinline__ uint32_t mt_twist_bal(uint32_t hi, uint32_t lo, const
     return y1 ^ mag;
 }
 
-// tempering: left shifts become multiplies on their own, right shifts stay on the logic pipe
-// (with the twist above that evens out the two pipes: 7 multiplier / 8 logic ops per draw)
+// tempering as the draw kernel applies it: the plain shift/xor form of mt_temper (moving its left
+// shifts to the multiplier pipe as well measured slower -- exactly one multiply per twist is the
+// optimum); the hook keeps the call sites of the balanced twist and the
+// tempering symmetric
 __device__ __forceinline__ uint32_t mt_temper_bal(uint32_t y, const DrawConsts &) { return mt_temper(y); }
 
 // ------------------------------------------------------------------ jump
