@@ -6,6 +6,7 @@
 #include "refio.h"
 
 #include <cstdio>
+#include <cstring>
 #include <string>
 #include <vector>
 
@@ -77,4 +78,38 @@ extern "C" int refio_test_read_mat(const char *path, int *m, int *n, double *out
     snprintf(next_word, next_cap, "%s", w.c_str());
     fclose(fp);
     return 0;
+}
+
+extern "C" {
+// qnorm's shortcut against the plain 40-step bisection it replaces: number of arguments (out of n) on which the
+// two differ in any bit.  Arguments: uniform, both tails, exact pnorm values, the neighbourhoods of z = 0 and
+// of the series / continued-fraction switch (where the computed pnorm jumps).
+long long aufit_qnorm_mismatches(long long n, unsigned long long seed) {
+    unsigned long long st = seed * 0x9E3779B97F4A7C15ull + 1;
+    auto u01 = [&]() {
+        st ^= st << 13; st ^= st >> 7; st ^= st << 17;
+        return (double)(st >> 11) * (1.0 / 9007199254740992.0);
+    };
+    long long bad = 0;
+    for (long long i = 0; i < n; i++) {
+        const double r = u01();
+        double p;
+        switch ((int)(u01() * 6)) {
+            case 0: p = r; break;
+            case 1: p = r * 1e-3; break;
+            case 2: p = 1.0 - r * 1e-3; break;
+            case 3: p = specfun::pnorm(-8.0 + 16.0 * r); break;
+            case 4: p = 0.5 + (r - 0.5) * 1e-6; break;
+            default: p = specfun::pnorm((r < 0.5 ? -1.0 : 1.0) * (1.7320508 + (u01() - 0.5) * 1e-4)); break;
+        }
+        specfun::qnorm_set_fast(0);
+        const double a = specfun::qnorm(p);
+        specfun::qnorm_set_fast(1);
+        const double b = specfun::qnorm(p);
+        if (memcmp(&a, &b, sizeof(double)) != 0) bad++;
+    }
+    return bad;
+}
+int aufit_qnorm_grid_monotone(void) { return specfun::qnorm_grid_is_monotone() ? 1 : 0; }
+
 }

@@ -34,10 +34,11 @@ static const int kItMax = 1000;
 static const double kEps = 3.0e-7, kFpMin = 1.0e-30;
 
 // P(a,x) by its series (NR 6.2 gser)
-static double gamma_series(double a, double x) {
+static double gamma_series(double a, double x, int *iters = nullptr) {
     const double gln = lngamma_cached(a);
     if (x <= 0.0) {
         if (x < 0.0) refio::die("x less than 0 in routine gser");
+        if (iters) *iters = 0;
         return 0.0;
     }
     double ap = a, sum = 1.0 / a, del = sum;
@@ -45,13 +46,16 @@ static double gamma_series(double a, double x) {
         ++ap;
         del *= x / ap;
         sum += del;
-        if (fabs(del) < fabs(sum) * kEps) return sum * exp(-x + a * log(x) - gln);
+        if (fabs(del) < fabs(sum) * kEps) {
+            if (iters) *iters = n;
+            return sum * exp(-x + a * log(x) - gln);
+        }
     }
     refio::die("a too large, ITMAX too small in routine gser");
 }
 
 // Q(a,x) by the modified Lentz continued fraction (NR 6.2 gcf)
-static double gamma_cfrac(double a, double x) {
+static double gamma_cfrac(double a, double x, int *iters = nullptr) {
     const double gln = lngamma_cached(a);
     double b = x + 1.0 - a, c = 1.0 / kFpMin, d = 1.0 / b, h = d;
     int i;
@@ -68,6 +72,7 @@ static double gamma_cfrac(double a, double x) {
         if (fabs(del - 1.0) < kEps) break;
     }
     if (i > kItMax) refio::die("a too large, ITMAX too small in gcf");
+    if (iters) *iters = i;
     return exp(-x + a * log(x) - gln) * h;
 }
 
@@ -83,48 +88,197 @@ static double erfc_nr(double x) { return x < 0.0 ? 1.0 + gammp(0.5, x * x) : gam
 
 double pnorm(double x) { return 0.5 * erfc_nr(-x * 0.707106781186547524400844362105); }
 
-// qnorm is a plain bisection on pnorm over [-37, 37] to 1e-10 (about 40 halvings).  The
-// midpoints visited depend only on the left/right path, not on p, so pnorm at the nodes
-// of the first 20 levels is memoised (lazily, 1M doubles): identical arithmetic, identical
-// result, ~half the pnorm evaluations.  Benign race: every thread writes the same value.
-static std::atomic<uint64_t> *qnorm_table() {
-    static std::atomic<uint64_t> *t = [] {
-        auto *a = new std::atomic<uint64_t>[1u << 20];
-        for (size_t i = 0; i < (1u << 20); i++) a[i].store(~0ull, std::memory_order_relaxed);  // a NaN pattern = empty
-        return a;
+// pnorm together with a tag that names the path the evaluation took: which side of erfc, series or
+// continued fraction, and after how many terms the 3e-7 stopping rule fired.  Between two arguments
+// with the same tag the computed function is one fixed smooth expression (identical operation
+// sequence), hence monotone at any resolution far above one ulp; the tag changes exactly where the
+// computed function jumps (by up to ~3e-7 relative).
+static double pnorm_tagged(double z, uint32_t *tag) {
+    const double x = -z * 0.707106781186547524400844362105;
+    const double x2 = x * x;
+    int it = 0;
+    if (x < 0.0) {  // erfc = 1 + P(1/2, x^2)
+        if (x2 < 0.0) refio::die("Invalid arguments in routine gammp");
+        double g;
+        if (x2 < 1.5) {
+            g = gamma_series(0.5, x2, &it);
+            *tag = (0u << 16) | (uint32_t)it;
+        } else {
+            g = 1.0 - gamma_cfrac(0.5, x2, &it);
+            *tag = (1u << 16) | (uint32_t)it;
+        }
+        return 0.5 * (1.0 + g);
+    }
+    double g;  // erfc = Q(1/2, x^2)
+    if (x2 < 1.5) {
+        g = 1.0 - gamma_series(0.5, x2, &it);
+        *tag = (2u << 16) | (uint32_t)it;
+    } else {
+        g = gamma_cfrac(0.5, x2, &it);
+        *tag = (3u << 16) | (uint32_t)it;
+    }
+    return 0.5 * g;
+}
+
+// qnorm is a plain bisection on pnorm over [-37, 37] to 1e-10 (src/rand.c:465-493): 40 halvings, the
+// answer is the midpoint of the cell [g_j, g_j + h] of the grid h = 74 * 2^-40 with
+// pnorm(g_j) <= p < pnorm(g_j + h) (all grid arithmetic is exact in fp64).  To keep the printed
+// digits of the reference, that cell must be found for the COMPUTED pnorm, whose 3e-7 stopping
+// rule makes it jump wherever the number of series / continued-fraction terms changes.
+//
+// Levels 1-20.  On the coarse grid G_i = -37 + i * 74 * 2^-20 the computed pnorm is non-decreasing
+// (its increment per cell, >= 5e-5 relative, dwarfs any jump; tests/test_host_fit.py checks all
+// 2^20 + 1 values), so the state of the bisection after 20 halvings is THE cell with
+// pnorm(G_i) <= p < pnorm(G_{i+1}), whichever way it is found: a closed-form estimate of the quantile
+// picks the cell, the memoised end values (lazy table, 1M entries; benign race: every thread writes
+// the same values) confirm or correct it.
+//
+// Levels 21-40 all lie inside that cell of width 7e-5.  When both ends carry the SAME tag the
+// computed pnorm is one smooth monotone expression on the whole cell, the final cell is the unique
+// crossing, and it is found by interpolation + secant steps + verification (3-4 evaluations instead
+// of 20; every evaluation must show the same tag).  Otherwise (a tag boundary inside: the function
+// jumps there) the plain bisection runs over the remaining 20 levels.
+// The result is the bisection's, bit for bit (tests/test_host_fit.py compares the two on millions
+// of arguments: tails, exact grid values, the neighbourhoods of z = 0 and of the series /
+// continued-fraction switch).
+struct QnormGrid {
+    std::atomic<uint64_t> *pv;
+    std::atomic<uint32_t> *tag;
+};
+static constexpr int kGridBits = 20;
+static constexpr long long kGridCells = 1ll << kGridBits;
+static QnormGrid qnorm_grid() {
+    static QnormGrid t = [] {
+        QnormGrid m;
+        m.pv = new std::atomic<uint64_t>[kGridCells + 1];
+        m.tag = new std::atomic<uint32_t>[kGridCells + 1];
+        for (long long i = 0; i <= kGridCells; i++) {
+            m.pv[i].store(~0ull, std::memory_order_relaxed);  // a NaN pattern = empty
+            m.tag[i].store(0u, std::memory_order_relaxed);
+        }
+        return m;
     }();
     return t;
 }
+static inline double grid_point(long long i) { return -37.0 + (double)i * (74.0 / 1048576.0); }  // exact
+static inline double grid_value(const QnormGrid &g, long long i, uint32_t *tag) {
+    uint64_t bits = g.pv[i].load(std::memory_order_acquire);
+    double pv;
+    if (bits == ~0ull) {
+        pv = pnorm_tagged(grid_point(i), tag);
+        memcpy(&bits, &pv, 8);
+        g.tag[i].store(*tag, std::memory_order_relaxed);
+        g.pv[i].store(bits, std::memory_order_release);
+    } else {
+        memcpy(&pv, &bits, 8);
+        *tag = g.tag[i].load(std::memory_order_relaxed);
+    }
+    return pv;
+}
 
-double qnorm(double p) {
-    double lo = -37.0, hi = 37.0, z = 0.0;
-    if (p <= 0.0 || p >= 1.0) return 0.0;
-    std::atomic<uint64_t> *memo = qnorm_table();
-    uint64_t node = 1;
+// rational approximation of the normal quantile (P. J. Acklam), relative error ~1e-9: only used to
+// pick the coarse cell to look at first
+static double quantile_estimate(double p) {
+    static const double a[] = {-3.969683028665376e+01, 2.209460984245205e+02, -2.759285104469687e+02,
+                               1.383577518672690e+02,  -3.066479806614716e+01, 2.506628277459239e+00};
+    static const double b[] = {-5.447609879822406e+01, 1.615858368580409e+02, -1.556989798598866e+02,
+                               6.680131188771972e+01,  -1.328068155288572e+01};
+    static const double c[] = {-7.784894002430293e-03, -3.223964580411365e-01, -2.400758277161838e+00,
+                               -2.549732539343734e+00, 4.374664141464968e+00,  2.938163982698783e+00};
+    static const double d[] = {7.784695709041462e-03, 3.224671290700398e-01, 2.445134137142996e+00, 3.754408661907416e+00};
+    if (p < 0.02425) {
+        const double q = sqrt(-2.0 * log(p));
+        return (((((c[0] * q + c[1]) * q + c[2]) * q + c[3]) * q + c[4]) * q + c[5]) / ((((d[0] * q + d[1]) * q + d[2]) * q + d[3]) * q + 1.0);
+    }
+    if (p > 1.0 - 0.02425) {
+        const double q = sqrt(-2.0 * log(1.0 - p));
+        return -(((((c[0] * q + c[1]) * q + c[2]) * q + c[3]) * q + c[4]) * q + c[5]) / ((((d[0] * q + d[1]) * q + d[2]) * q + d[3]) * q + 1.0);
+    }
+    const double q = p - 0.5, r = q * q;
+    return (((((a[0] * r + a[1]) * r + a[2]) * r + a[3]) * r + a[4]) * r + a[5]) * q /
+           (((((b[0] * r + b[1]) * r + b[2]) * r + b[3]) * r + b[4]) * r + 1.0);
+}
+
+static std::atomic<int> g_qnorm_fast{1};
+void qnorm_set_fast(int on) { g_qnorm_fast.store(on); }
+
+// the reference's loop, as published
+static double qnorm_bisect(double p, double lo, double hi) {
+    double z = (hi + lo) * 0.5;
     while (hi - lo > 1e-10) {
-        double pv;
-        if (node < (1u << 20)) {
-            uint64_t bits = memo[node].load(std::memory_order_relaxed);
-            if (bits == ~0ull) {
-                pv = pnorm(z);
-                memcpy(&bits, &pv, 8);
-                memo[node].store(bits, std::memory_order_relaxed);
-            } else {
-                memcpy(&pv, &bits, 8);
-            }
-        } else {
-            pv = pnorm(z);
-        }
-        if (pv > p) {
-            hi = z;
-            node = node < (1ull << 40) ? 2 * node : node;
-        } else {
-            lo = z;
-            node = node < (1ull << 40) ? 2 * node + 1 : node;
-        }
+        if (pnorm(z) > p) hi = z; else lo = z;
         z = (hi + lo) * 0.5;
     }
     return z;
+}
+
+bool qnorm_grid_is_monotone() {  // tests: the property the coarse-cell shortcut rests on
+    const QnormGrid g = qnorm_grid();
+    uint32_t tag;
+    double prev = grid_value(g, 0, &tag);
+    for (long long i = 1; i <= kGridCells; i++) {
+        const double v = grid_value(g, i, &tag);
+        if (v < prev) return false;
+        prev = v;
+    }
+    return true;
+}
+
+double qnorm(double p) {
+    if (p <= 0.0 || p >= 1.0) return 0.0;
+    if (!g_qnorm_fast.load(std::memory_order_relaxed)) return qnorm_bisect(p, -37.0, 37.0);
+    const QnormGrid g = qnorm_grid();
+    // ---- levels 1-20: the coarse cell [G_i, G_{i+1}] with pnorm(G_i) <= p < pnorm(G_{i+1})
+    double zq = quantile_estimate(p);
+    if (!(zq > -37.0)) zq = -37.0;
+    if (zq > 37.0) zq = 37.0;
+    long long i = (long long)floor((zq + 37.0) * (1048576.0 / 74.0));
+    if (i < 0) i = 0;
+    if (i > kGridCells - 1) i = kGridCells - 1;
+    uint32_t tlo, thi;
+    double plo = grid_value(g, i, &tlo), phi = grid_value(g, i + 1, &thi);
+    // (the bisection never evaluates the ends -37 and 37: it takes pnorm(-37) <= p < pnorm(37) for granted)
+    while (i > 0 && plo > p) {
+        i--;
+        phi = plo;
+        thi = tlo;
+        plo = grid_value(g, i, &tlo);
+    }
+    while (i < kGridCells - 1 && phi <= p) {
+        i++;
+        plo = phi;
+        tlo = thi;
+        phi = grid_value(g, i + 1, &thi);
+    }
+    const double A = grid_point(i), B = grid_point(i + 1);
+    // ---- levels 21-40 inside the cell
+    if (tlo == thi && i > 0 && i < kGridCells - 1) {
+        const double h = 74.0 / 1099511627776.0;  // 74 * 2^-40: every grid point A + j*h is exact
+        const double slope = (phi - plo) / 1048576.0;  // pnorm per fine cell, good to ~1e-4 relative over 7e-5
+        bool ok = slope > 0.0;
+        long long j = ok ? (long long)((p - plo) / slope) : 0;
+        // invariant: P(A + jl*h) <= p < P(A + jh*h), jl < jh
+        long long jl = 0, jh = 1048576;
+        for (int step = 0; ok && step < 12 && jh - jl > 1; step++) {
+            if (j <= jl) j = jl + 1;
+            if (j >= jh) j = jh - 1;
+            uint32_t t2;
+            const double pj = pnorm_tagged(A + (double)j * h, &t2);
+            if (t2 != tlo) { ok = false; break; }
+            long long dj = (long long)floor((p - pj) / slope);
+            if (pj > p) {
+                jh = j;
+                if (dj > -1) dj = -1;
+            } else {
+                jl = j;
+                if (dj < 1) dj = 1;
+            }
+            j += dj;
+        }
+        if (ok && jh - jl == 1) return (A + (double)jl * h + (A + (double)jh * h)) * 0.5;
+        // not settled (a tag boundary inside the cell, or a flat stretch): the plain bisection decides
+    }
+    return qnorm_bisect(p, A, B);
 }
 
 double poz(double z) {

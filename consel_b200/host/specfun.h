@@ -12,6 +12,8 @@ namespace specfun {
 double dnorm(double x);
 double pnorm(double x);
 double qnorm(double p);
+void qnorm_set_fast(int on);  // 0: plain 40-step bisection at every call (tests compare the two)
+bool qnorm_grid_is_monotone();  // the computed pnorm on the 2^20-cell grid of qnorm's first 20 halvings
 double poz(double z);
 double pochisq(double x, int df);
 }  // namespace specfun
