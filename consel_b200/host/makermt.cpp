@@ -78,6 +78,16 @@ static int genrmt(Params &P, const char *infile, const char *outfile) {
         rr1[i] = (double)bn[i] / nn;
     }
 
+    // The device keeps site counts in bytes (a site drawn more than 255 times in one replicate is refused
+    // with CGPU_ERANGE).  That can only happen for toy alignments with large scales (n = 10, r = 30); it is
+    // recognised here, before any output file is opened, instead of after the whole run.
+    for (int i = 0; i < kk; i++) {
+        const double mu = (double)bn[i] / (double)nn;  // mean count per site
+        if (bn[i] <= 0) die("scale %g gives an empty replicate (n'=%d) for %d sites", P.rr[i], bn[i], nn);
+        if (mu + 9.0 * sqrt(mu) + 10.0 > 255.0)
+            die("scale %g on %d sites draws a site about %g times per replicate: beyond the byte counts of the device path", P.rr[i], nn, mu);
+    }
+
     // one process per GPU (RANK / WORLD_SIZE, cgpu_comm_init_env): every rank resamples its share of the
     // replicate columns, the blocks are all-gathered over NVLink and rank 0 alone writes the files
     int g_rank = 0, g_world = 1;
