@@ -479,6 +479,20 @@ def run_ours(args) -> None:
               "2.5 KB read + 2.5 KB written per chunk state; the work is 624 x ~10^4 shared-memory word reads per jump",
               "shared-memory bandwidth bound; launches_per_step=1 stands for the ~10 levels of the jump tree"),
     ]
+    # the draw kernel is bound by instruction issue, which the hbm|tensor vocabulary cannot express: add the
+    # issue-slot view (warp-instructions per draw from the ncu capture profiles/r01_final_draw_equalfill_ncu_full.json;
+    # the kernel has not changed since)
+    try:
+        prof = json.loads((ROOT / "profiles" / "r01_final_draw_equalfill_ncu_full.json").read_text())["launches"][0]
+        wi_per_draw = prof["warp_instructions"] / 3.243e9
+        sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        issue_peak = 4.0 * torch.cuda.get_device_properties(local).multi_processor_count * sm_mhz * 1e6
+        ach_i = wi_per_draw * draws / (max(phases["mt_draw"], 1e-9) * 1e-3)
+        kernels[0]["issue_view"] = {"achieved": ach_i / 1e9, "peak": issue_peak / 1e9, "unit": "G warp-instructions/s",
+                                    "frac": ach_i / issue_peak, "warp_instructions_per_draw": wi_per_draw,
+                                    "source": "instruction count from the ncu capture, time and SM clock from this run"}
+    except Exception:
+        pass
     kernels = [e for e in kernels if e["share_of_step"] > 1e-6]  # e.g. fx_combine runs inside the GEMM epilogue when S divides 8
     # consel side: per-kernel CUDA-event times of one pipeline pass (cgpu_kernel_times)
     consel_alg = {  # kernel -> (bound, what the library's per-launch work figure counts)
