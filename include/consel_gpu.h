@@ -80,6 +80,9 @@ void cgpu_host_rowsums(const double *L, int K, int n, double *datvec);
  *              exact payload fwrite_bmat (src/misc.c:637-645) writes after its
  *              two-int header.  With sharding (cgpu_set_shard) rep_out[s] is the
  *              rank-local compact block K x (b_end-b_begin) of cgpu_shard_range(bb[s]).
+ * With a communicator (cgpu_comm_init) the call is COLLECTIVE: every rank passes the same L,
+ * copies only its share of the rows from the host, and one NCCL all-gather over NVLink
+ * completes the matrix on every device ("dist_upload" 0 restores the plain per-rank upload).
  */
 int cgpu_scaleboot_all(const double *L, int K, int n, int S, const int *bn, const int *bb,
                        unsigned long seed, unsigned long long stream_offset, int rng_mode,
