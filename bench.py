@@ -566,14 +566,15 @@ def run_ours(args) -> None:
 
 
 # ------------------------------------------------------------------------ reference
+_REF_L = None  # the matrix of the in-process reference arm: set before the pool forks, inherited copy-on-write
+
+
 def _ref_worker(args):
     """one host process of the in-process reference arm: scaleboot() of the unmodified makermt.c"""
     import ctypes as C
-    so, shm_name, K, n, bn, b_each, seed = args
-    from multiprocessing import shared_memory
+    so, K, n, bn, b_each, seed = args
     lib = C.CDLL(so)
-    shm = shared_memory.SharedMemory(name=shm_name)
-    L = np.ndarray((K, n), dtype=np.float64, buffer=shm.buf)
+    L = _REF_L
     rows = (C.POINTER(C.c_double) * K)(*[C.cast(L.ctypes.data + 8 * n * k, C.POINTER(C.c_double)) for k in range(K)])
     out = np.zeros((K, b_each))
     orow = (C.POINTER(C.c_double) * K)(*[C.cast(out.ctypes.data + 8 * b_each * k, C.POINTER(C.c_double)) for k in range(K)])
@@ -583,8 +584,6 @@ def _ref_worker(args):
     t0 = time.perf_counter()
     lib.scaleboot(rows, orow, K, n, int(bn), int(b_each))
     dt = time.perf_counter() - t0
-    del L
-    shm.close()
     return dt, out
 
 
@@ -647,21 +646,21 @@ def run_reference(args) -> None:
                       f"{b_each} replicates each, same matrix read from a 17-digit .mt text file; wall clock includes process start and text parse")
         elif so.exists():
             kind = "reference"
-            from multiprocessing import get_context, shared_memory
-            shm = shared_memory.SharedMemory(create=True, size=L.nbytes)
-            np.ndarray(L.shape, dtype=np.float64, buffer=shm.buf)[:] = L
+            from multiprocessing import get_context
+            global _REF_L
+            _REF_L = np.ascontiguousarray(L, dtype=np.float64)  # read-only in the workers: the forked pages are shared
             ctx = get_context("fork")
             pool = ctx.Pool(min(cores, nproc))
             keep = {}
 
             def step():
-                jobs = [(str(so), shm.name, K, N_SITES, int(bn[s_]), b_each, 151 + s_ * parts + p) for s_, p in jobs_sp]
+                jobs = [(str(so), K, N_SITES, int(bn[s_]), b_each, 151 + s_ * parts + p) for s_, p in jobs_sp]
                 res = pool.map(_ref_worker, jobs, chunksize=1)
                 keep["reps"] = [res[s_][1] for s_ in range(len(RR))]  # part 0 of every scale: the consel sample
                 return None
             sample = (f"{nproc} calls of scaleboot() (unmodified /root/reference/src/makermt.c:35-75 compiled -O2 into "
                       f"oracle/_ref/libmakermt_ref.so), one per (scale, part), at most {cores} host processes at a time, {b_each} replicates "
-                      "each, matrix in shared memory (no .mt text parse: the file would be "
+                      "each, matrix shared by the forked workers (no .mt text parse: the file would be "
                       f"{K * N_SITES * 24 / 1e9:.1f} GB per process)")
         else:
             kind = "port"
@@ -704,8 +703,6 @@ def run_reference(args) -> None:
             pipe_ref = {"error": f"{type(e).__name__}: {e}"}
         if not use_cli and kind == "reference":
             pool.close()
-            shm.close()
-            shm.unlink()
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": t / args.steps * 1e3, "higher_is_better": True, "scaling": c["scaling"],
