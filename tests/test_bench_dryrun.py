@@ -1,0 +1,166 @@
+"""bench.py's host-side glue, end to end, without a GPU: the device library and the pipeline are
+replaced by stand-ins with the shapes of consel_b200.api / consel_b200.pipeline, and run_ours() must
+walk through every leg (timed steps, spot check, side modes, pipeline, host-buffer arm, rooflines,
+cpu_baseline) and print ONE JSON line carrying every key the measurement contract names.  Nothing
+here measures anything; it guards the report code that only runs AFTER the GPU work of a bench run.
+"""
+import json
+import sys
+import types
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+import bench  # noqa: E402
+
+
+class _Reps:
+    def __init__(self, owner, bn):
+        self.owner, self.bn = owner, bn
+
+    def free(self):
+        pass
+
+    def download_cols(self, s, col0, ncols):
+        # what the device must return: the correctly rounded exact sums over the reference's draws
+        o = self.owner
+        skip = sum(int(o.bb[t]) * int(self.bn[t]) for t in range(s)) + col0 * int(self.bn[s])
+        y = o.orc.mt_stream(7, skip, ncols * int(self.bn[s]))
+        idx = o.orc.site_indices(y, o.L.shape[1]).reshape(ncols, int(self.bn[s]))
+        counts = np.stack([np.bincount(idx[b], minlength=o.L.shape[1]) for b in range(ncols)])
+        return bench.exact_sums(o.L, counts, float(self.bn[s]) / o.L.shape[1])
+
+
+class _Matrix:
+    def __init__(self, L, orc):
+        self.L, self.orc, self.bb = np.asarray(L), orc, None
+
+    def scaleboot(self, bn, bb, seed, stream_offset=0, rng_mode=0, sum_mode=0):
+        self.bb = np.asarray(bb)
+        return _Reps(self, np.asarray(bn))
+
+    def info(self):
+        K, n = self.L.shape
+        return dict(K=K, n=n, NP=(n + 127) // 128 * 128, slices=8, frac_bits=50, mpad=128, patterns=0)
+
+    def free(self):
+        pass
+
+
+@pytest.mark.parametrize("clocks_low", [False, True])
+def test_run_ours_prints_the_contract_line(monkeypatch, capsys, orc, clocks_low):
+    import torch
+
+    import consel_b200 as cg
+    from consel_b200 import pipeline
+
+    # ---- torch.cuda stand-ins
+    monkeypatch.setattr(torch.cuda, "set_device", lambda d: None)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a: None)
+    monkeypatch.setattr(torch.cuda, "get_device_properties", lambda d: types.SimpleNamespace(multi_processor_count=148))
+    real_empty = torch.empty
+
+    def empty(*a, **kw):
+        kw.pop("device", None)
+        kw.pop("pin_memory", None)
+        return real_empty(*a, **kw)
+    monkeypatch.setattr(torch, "empty", empty)
+
+    # ---- device library stand-ins (shapes of consel_b200/api.py)
+    timing = dict(upload=0.0, rng=0.6, resample=0.4, contract=0.0, download=0.0, total=2.0, gemm_i8=0.9, fx_combine=0.0,
+                  mt_jump=0.2, mt_draw=0.4, n_gemm=10.0, n_hist=10.0)
+    launches = [0]
+
+    def launch_count():
+        launches[0] += 31
+        return launches[0]
+    monkeypatch.setattr(cg, "init", lambda d=-1: None)
+    monkeypatch.setattr(cg, "set_shard", lambda r, w: None)
+    monkeypatch.setattr(cg, "shard_range", lambda b: (0, int(b)))
+    monkeypatch.setattr(cg, "bench_peaks", lambda sustained_seconds=0.0: dict(
+        int8_tops=4500.0, fp64_tflops=33.0, **({"int8_tops_sustained": 3800.0} if sustained_seconds > 0 else {})))
+    monkeypatch.setattr(cg, "Matrix", lambda L: _Matrix(L, orc))
+    monkeypatch.setattr(cg, "last_timing", lambda: dict(timing))
+    monkeypatch.setattr(cg, "launch_count", launch_count)
+    monkeypatch.setattr(cg, "set_option", lambda k, v: None)
+    monkeypatch.setattr(cg, "kernel_times", lambda: {"col_top2_kernel": (11, 0.3, 1.3e8), "pair_weight_kernel": (1, 0.2, 3.0e7),
+                                                     "unknown_kernel": (1, 0.1, 1.0)})
+
+    def scaleboot_all(L, bn, bb, seed, stream_offset=0, rng_mode=0, sum_mode=0, out=None):
+        for o in out:
+            o[:] = 1.0
+        return out
+    monkeypatch.setattr(cg, "scaleboot_all", scaleboot_all)
+
+    def run(L, rr, bb, seed, rng_mode=0, sum_mode=0, matrix=None, **kw):
+        K = np.asarray(L).shape[0]
+        pv = np.full((K, 8), 0.5)
+        return dict(item=np.arange(K), pv=pv, timing={"mctest_s": 0.001, "stats_s": 0.001, "au_s": 0.002, "makermt_s": 0.002,
+                                                       "device_ms": dict(timing)})
+    monkeypatch.setattr(pipeline, "run", run)
+    monkeypatch.setattr(pipeline, "comm_init_from_torch", lambda: (0, 1))
+
+    class _Sampler:
+        def __init__(self, idx):
+            pass
+
+        def start(self):
+            pass
+
+        def stop(self):
+            return {"sm_mhz": 1400.0 if clocks_low else 1965.0, "sm_max_mhz": 1965.0,
+                    "reasons": ["sw_power_cap"] if clocks_low else [], "samples": 9}
+    monkeypatch.setattr(bench, "ClockSampler", _Sampler)
+    # the CPU baseline leg is the real oracle; keep its sample small here
+    real_makermt = orc.makermt
+    monkeypatch.setattr(orc, "makermt", lambda L, bn, bb, seed: real_makermt(L, bn, [min(int(b), 50) for b in bb], seed))
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        monkeypatch.delenv(k, raising=False)
+
+    args = types.SimpleNamespace(gpus=1, steps=2, warmup=3, impl="ours", config="C1")
+    bench.run_ours(args)
+    lines = [t for t in capsys.readouterr().out.splitlines() if t.strip()]
+    assert len(lines) == 1, "bench.py must print exactly one JSON line"
+    d = json.loads(lines[0])
+
+    # ---- the base contract
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
+        assert key in d, key
+    assert d["metric"] == bench.METRIC and d["unit"] == "acc/s" and d["n_gpus"] == 1 and d["steps"] == 2 and d["warmup"] == 3
+    assert d["vs_baseline"] is None and d["dtype"] == "f64" and d["higher_is_better"] is True
+    assert "workload" in d["config"] and "model" not in d["config"]
+    assert d["ms_per_step"] == pytest.approx(2.0) and d["value"] == pytest.approx(15 * 3414 * 1e5 / 2.0e-3)
+    assert d["gpu_launches"] > 0
+    e2e = d["e2e"]
+    assert e2e["h2d_bytes_per_step"] == 15 * 3414 * 8 and e2e["d2h_bytes_per_step"] == 15 * 10000 * 8 * 10 and e2e["value"] > 0
+    # ---- roofline of the dominant kernel + every kernel + the step-level floor
+    r = d["roofline"]
+    for key in ("bound", "achieved", "peak", "unit", "frac", "traffic", "kernels", "step"):
+        assert key in r, key
+    assert r["bound"] in ("hbm", "tensor") and r["frac"] == pytest.approx(r["achieved"] / r["peak"])
+    assert r["kernel"].startswith("gemm_i8")  # the largest share in the stand-in timing
+    # power-capped steps are graded against the sustained int8 rate, full-clock steps against the burst rate
+    assert r["peak"] == (3800.0 if clocks_low else 4500.0)
+    names = [k["kernel"] for k in r["kernels"]]
+    assert any("mt_draw_kernel" in n for n in names) and any("col_top2_kernel" in n for n in names)
+    assert not any("unknown_kernel" in n for n in names)
+    assert 0.0 < r["step"]["frac"] and r["step"]["ms_per_step"] == pytest.approx(2.0)
+    # ---- cpu baseline, spot check, side modes, pipeline
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] == 1 and cb["value"] > 0 and "sample" in cb
+    assert d["spot_check"]["ok"] is True and d["spot_check"]["bit_equal_to_exact_rounded_sums"] is True
+    assert set(d["modes"]) == {"strict_mt", "fast_mt", "int8_philox"}
+    p = d["pipeline"]
+    assert "error" not in p, p
+    assert p["items"] == 15 and p["host_matrix_table_identical"] is True and p["makermt_consel_from_host_matrix_ms"] > 0
+
+
+def test_reference_arm_non_zero_ranks_do_nothing(monkeypatch, capsys):
+    monkeypatch.setenv("RANK", "3")
+    monkeypatch.setenv("WORLD_SIZE", "8")
+    bench.run_reference(types.SimpleNamespace(gpus=8, steps=1, warmup=0, impl="reference", config="C3"))
+    assert capsys.readouterr().out == ""
