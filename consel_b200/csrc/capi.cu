@@ -1064,6 +1064,7 @@ int cgpu_set_option(const char *name, int value) {
     else if (!strcmp(name, "i8_patterns")) g.opt_i8_patterns = value;
     else if (!strcmp(name, "i8_ksplit")) g.opt_i8_ksplit = value;
     else if (!strcmp(name, "dist_upload")) g.opt_dist_upload = value;
+    else if (!strcmp(name, "hist_bucket")) g.opt_hist_bucket = value;
     else {
         set_error(CGPU_EINVAL, "unknown option %s", name);
         return CGPU_EINVAL;

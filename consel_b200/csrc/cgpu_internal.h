@@ -84,7 +84,7 @@ struct Globals {
     void *scratch[4] = {nullptr, nullptr, nullptr, nullptr};
     size_t scratch_cap[4] = {0, 0, 0, 0};
     // tuning switches (cgpu_set_option); -1 = built-in default
-    int opt_overlap = -1, opt_hist_algo = -1, opt_contract_algo = -1, opt_i8_oneshot = -1, opt_draw_nch = -1, opt_chunk_log2 = -1, opt_i8_fuse = -1, opt_draw_fuse = -1, opt_stage = -1, opt_i8_dbg = -1, opt_mc_smooth = -1, opt_chunk_fill = -1, opt_ktime = -1, opt_hist_wide = -1, opt_i8_2cta = -1, opt_batch = -1, opt_dist_upload = -1, opt_i8_panel = -1, opt_i8_patterns = -1, opt_i8_ksplit = -1;
+    int opt_overlap = -1, opt_hist_algo = -1, opt_contract_algo = -1, opt_i8_oneshot = -1, opt_draw_nch = -1, opt_chunk_log2 = -1, opt_i8_fuse = -1, opt_draw_fuse = -1, opt_stage = -1, opt_i8_dbg = -1, opt_mc_smooth = -1, opt_chunk_fill = -1, opt_ktime = -1, opt_hist_wide = -1, opt_i8_2cta = -1, opt_batch = -1, opt_dist_upload = -1, opt_i8_panel = -1, opt_i8_patterns = -1, opt_i8_ksplit = -1, opt_hist_bucket = -1;
 };
 Globals &G();
 int ensure_init();

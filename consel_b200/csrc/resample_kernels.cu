@@ -25,29 +25,13 @@
 #include <algorithm>
 
 #include "cgpu_internal.h"
+#include "philox.cuh"
+#include "hist_bucket.cuh"
 
 namespace cgpu {
 
 constexpr int HIST_SMEM_SITES = 28160;  // 8 * 28160 B = 220 KB of shared memory
 constexpr int HIST_THREADS = 256;
-
-// ------------------------------------------------------------------ Philox4x32-10
-struct Philox4 {
-    uint32_t v[4];
-};
-__device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                                                 uint32_t k0, uint32_t k1) {
-#pragma unroll
-    for (int r = 0; r < 10; r++) {
-        uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
-        uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
-        uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
-        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
-        k0 += 0x9E3779B9u;
-        k1 += 0xBB67AE85u;
-    }
-    return Philox4{{c0, c1, c2, c3}};
-}
 
 // one warp adds the site indices its lanes hold to a warp-private byte histogram.
 //  HALGO 0  match.any + popcount: the first lane of each group of equal sites adds the
@@ -383,6 +367,57 @@ static int hist_wide_launch(const void *d_idx, int n, int NP, int bn, int nb, un
     return CGPU_OK;
 }
 
+// Bucketed histogram of genome-length byte rows (hist_bucket.cuh): four launches per call, the
+// partition buffer (2 bytes per draw) and the bucket tables come from the stream-ordered pool.
+template <int SRC>
+static int hist_bucket_launch(const void *d_idx, int n, int NP, int bn, int nb, unsigned long long *d_counts, int *d_err,
+                              uint32_t k0, uint32_t k1, uint32_t scale, uint32_t b_first, uint32_t ctr3, cudaStream_t st) {
+    constexpr int WBL = 16;
+    const int nbk = (NP + (1 << WBL) - 1) >> WBL;
+    const int tiles = (bn + BK_TILE - 1) / BK_TILE;
+    const size_t pstride = (size_t)((bn + 7) / 8 * 8) + (size_t)8 * nbk;
+    auto k_count = bucket_count_kernel<SRC, WBL>;
+    auto k_scatter = bucket_scatter_kernel<SRC, WBL>;
+    auto k_hist = bucket_hist_kernel<WBL>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        CGPU_CUDA(cudaFuncSetAttribute(k_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bk_scatter_smem()));
+        CGPU_CUDA(cudaFuncSetAttribute(k_hist, cudaFuncAttributeMaxDynamicSharedMemorySize, 1 << WBL));
+        attr_done = true;
+    }
+    unsigned int *d_tab = nullptr;      // cnt | off | cur, nb x nbk each
+    unsigned short *d_part = nullptr;   // nb x pstride
+    const size_t tab = (size_t)nb * nbk;
+    CGPU_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&d_tab), 3 * tab * sizeof(unsigned int), st));
+    cudaError_t e = cudaMallocAsync(reinterpret_cast<void **>(&d_part), (size_t)nb * pstride * sizeof(unsigned short), st);
+    if (e != cudaSuccess) {
+        cudaFreeAsync(d_tab, st);
+        set_error(CGPU_ENOMEM, "bucketed histogram: %zu bytes of partition buffer: %s", (size_t)nb * pstride * 2, cudaGetErrorString(e));
+        return CGPU_ENOMEM;
+    }
+    unsigned int *d_cnt = d_tab, *d_off = d_tab + tab, *d_cur = d_tab + 2 * tab;
+    int rc = CGPU_OK;
+    auto body = [&]() -> int {
+        CGPU_CUDA(cudaMemsetAsync(d_cnt, 0, tab * sizeof(unsigned int), st));
+        const uint32_t *idx = static_cast<const uint32_t *>(d_idx);
+        k_count<<<dim3(tiles, nb), BK_THREADS, 0, st>>>(idx, (uint32_t)n, bn, nbk, d_cnt, k0, k1, scale, b_first, ctr3);
+        CGPU_LAUNCH_CHECK();
+        bucket_scan_kernel<<<(nb + 127) / 128, 128, 0, st>>>(d_cnt, nb, nbk, d_off, d_cur);
+        CGPU_LAUNCH_CHECK();
+        k_scatter<<<dim3(tiles, nb), BK_THREADS, bk_scatter_smem(), st>>>(idx, (uint32_t)n, bn, nbk, d_off, d_cur, d_part, pstride, k0, k1,
+                                                                          scale, b_first, ctr3);
+        CGPU_LAUNCH_CHECK();
+        k_hist<<<dim3(nbk, nb), BKH_THREADS, 1 << WBL, st>>>(d_part, pstride, d_cnt, d_off, nbk, NP,
+                                                             reinterpret_cast<unsigned char *>(d_counts), d_err);
+        CGPU_LAUNCH_CHECK();
+        return CGPU_OK;
+    };
+    rc = body();
+    cudaFreeAsync(d_part, st);
+    cudaFreeAsync(d_tab, st);
+    return rc;
+}
+
 // CGPU_HIST_ALGO selects the in-warp conflict scheme (development A/B switch)
 static int hist_algo() {
     static int v = [] {
@@ -421,6 +456,9 @@ static int hist_dispatch(int src, const void *d_idx, int n, int NP, int bn, int 
         return CGPU_EINVAL;
     }
     const int ngroups = (nb + 7) / 8;
+    if (G().opt_hist_bucket == 2 && rows && !pid && src != 2 && nb <= 65535 && (NP + 65535) / 65536 <= BK_MAXB)
+        return src == 1 ? hist_bucket_launch<1>(d_idx, n, NP, bn, nb, d_counts, d_err, k0, k1, scale, b_first, ctr3, st)
+                        : hist_bucket_launch<0>(d_idx, n, NP, bn, nb, d_counts, d_err, k0, k1, scale, b_first, ctr3, st);
     int algo = hist_algo();
     if (algo == 2 && 2 * NP > HIST_SMEM_SITES) algo = 0;  // tag arrays double the footprint
     if (rows && algo == 1 && NP > HIST_SMEM_SITES / 2 && NP <= 8 * HIST_SMEM_SITES && G().opt_hist_wide != 0) {
@@ -457,6 +495,12 @@ static int hist_dispatch(int src, const void *d_idx, int n, int NP, int bn, int 
         set_error(CGPU_EINVAL, "histogram source %d", src);
         return CGPU_EINVAL;
     } else {
+        // byte rows longer than any shared-memory histogram.  "hist_bucket" 1 (opt-in): partition the draws by
+        // 65536-site bucket and count every bucket in shared memory (hist_bucket.cuh); 2 takes that path for
+        // every uint32-index row (tests).  Default: 32-bit global atomics on the packed words.
+        if (rows && !pid && src != 2 && G().opt_hist_bucket >= 1 && nb <= 65535 && (NP + 65535) / 65536 <= BK_MAXB)
+            return src == 1 ? hist_bucket_launch<1>(d_idx, n, NP, bn, nb, d_counts, d_err, k0, k1, scale, b_first, ctr3, st)
+                            : hist_bucket_launch<0>(d_idx, n, NP, bn, nb, d_counts, d_err, k0, k1, scale, b_first, ctr3, st);
         CGPU_CUDA(cudaMemsetAsync(d_counts, 0, (size_t)ngroups * NP * 8, st));
         int sms = G().sm_count > 0 ? G().sm_count : 148;
         int grid = sms * 16;

@@ -239,7 +239,9 @@ int cgpu_last_timing_ex(double *ms, int n);
  * "draw_fuse" 0|1 (draws + histograms in one kernel, int8 mode, opt-in), "stage" 0|1 (staged
  * index production of host-output int8 calls: 0 off, 1 always, default by size),
  * "hist_wide" 0|1 (one replicate per CTA
- * on long alignments), "i8_2cta" 0|1 (cta_group::2 GEMM, default on), "i8_patterns" 0|1 (site-pattern compression of the int8 path,
+ * on long alignments), "hist_bucket" 0|1|2 (byte rows longer than 225280 sites: 1 = partition the draws by
+ * 65536-site bucket and count in shared memory instead of global atomics, opt-in; 2 = that path for every
+ * uint32-index row, tests), "i8_2cta" 0|1 (cta_group::2 GEMM, default on), "i8_patterns" 0|1 (site-pattern compression of the int8 path,
  * default on), "i8_panel" N (tile order of the pair GEMM), "dist_upload" 0|1, "batch" N (replicates per
  * GEMM batch, tests), "ktime" 0|1 (per-kernel events, see cgpu_kernel_times), "chunk_log2" 10..30 (force a power-of-two chunk of the MT19937 jump tree), "chunk_fill" 0|1|2
  * (equal-fill chunk lengths that are not powers of two: off, by cost model (default), forced), "i8_dbg" 0..3 (switches parts of the GEMM epilogue off: timing only,

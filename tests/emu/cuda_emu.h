@@ -1,0 +1,141 @@
+// CPU execution of plain CUDA kernels, for tests (test infrastructure only: nothing of the
+// product includes this file).
+//
+// A kernel is compiled as ordinary C++ (g++ -DCGPU_EMU) and launched with emu::launch(grid, block,
+// dynamic_smem_bytes, kernel, args...): ONE OS THREAD PER CUDA THREAD of a CTA, the CTAs of the
+// grid run one after another on the same threads.  threadIdx / blockIdx / blockDim / gridDim are
+// thread-local, __syncthreads is a real barrier over the CTA's threads, __shfl_*_sync exchange
+// through a per-warp mailbox behind warp barriers, atomics are the compiler's __atomic builtins.
+// Function-scope `__shared__` arrays become function-local statics (shared by the CTA's threads;
+// CTAs never overlap in time), dynamic shared memory is one buffer per launch (CGPU_DYN_SMEM).
+// Because every access is a real memory access of a real thread, ThreadSanitizer sees a missing
+// barrier or an unsynchronised shared-memory update as a data race.
+//
+// Supported: what consel_b200/csrc/hist_bucket.cuh and philox.cuh use.  Warp-collectives must be
+// called by all 32 lanes of a warp (as CUDA requires with a full mask).
+#pragma once
+#include <stdint.h>
+#include <string.h>
+
+#include <algorithm>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+struct dim3 {
+    unsigned x = 1, y = 1, z = 1;
+    dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
+};
+struct uint4 {
+    unsigned x, y, z, w;
+};
+static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{x, y, z, w}; }
+
+namespace emu {
+class Barrier {  // reusable barrier (mutex + condition variable: visible to ThreadSanitizer)
+  public:
+    explicit Barrier(int n) : n_(n) {}
+    void wait() {
+        std::unique_lock<std::mutex> lk(mu_);
+        const unsigned gen = gen_;
+        if (++count_ == n_) {
+            count_ = 0;
+            gen_++;
+            cv_.notify_all();
+        } else {
+            cv_.wait(lk, [&] { return gen_ != gen; });
+        }
+    }
+
+  private:
+    std::mutex mu_;
+    std::condition_variable cv_;
+    int n_, count_ = 0;
+    unsigned gen_ = 0;
+};
+struct Warp {
+    Barrier bar{32};
+    unsigned mail[32];
+    explicit Warp(int lanes) : bar(lanes) {}
+};
+struct Cta {
+    Barrier *bar = nullptr;
+    std::vector<Warp *> warps;
+    unsigned char *dyn = nullptr;
+};
+inline thread_local Cta *t_cta = nullptr;
+inline thread_local int t_lane = 0, t_warp = 0;
+inline unsigned char *dyn_smem() { return t_cta->dyn; }
+}  // namespace emu
+
+inline thread_local dim3 threadIdx, blockIdx, blockDim, gridDim;
+
+#define __global__
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __restrict__
+#define __launch_bounds__(...)
+#define __align__(x) alignas(x)
+#define __shared__ static
+#define CGPU_DYN_SMEM(T, name) T *name = reinterpret_cast<T *>(emu::dyn_smem())
+
+static inline void __syncthreads() { emu::t_cta->bar->wait(); }
+static inline void __syncwarp(unsigned = 0xffffffffu) { emu::t_cta->warps[emu::t_warp]->bar.wait(); }
+static inline unsigned emu_exchange(unsigned v, int src_lane) {
+    emu::Warp *w = emu::t_cta->warps[emu::t_warp];
+    w->mail[emu::t_lane] = v;
+    w->bar.wait();
+    const unsigned r = w->mail[src_lane & 31];
+    w->bar.wait();
+    return r;
+}
+static inline unsigned __shfl_xor_sync(unsigned, unsigned v, int off) { return emu_exchange(v, emu::t_lane ^ off); }
+static inline unsigned __shfl_up_sync(unsigned, unsigned v, int d) { return emu_exchange(v, emu::t_lane >= d ? emu::t_lane - d : emu::t_lane); }
+static inline unsigned atomicAdd(unsigned *p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+static inline int atomicExch(int *p, int v) { return __atomic_exchange_n(p, v, __ATOMIC_RELAXED); }
+static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
+static inline unsigned __dp4a(unsigned a, unsigned b, unsigned c) {
+    for (int i = 0; i < 4; i++) c += ((a >> (8 * i)) & 0xffu) * ((b >> (8 * i)) & 0xffu);
+    return c;
+}
+template <class T>
+static inline T __ldg(const T *p) { return *p; }
+using std::max;
+using std::min;
+
+namespace emu {
+// launch<<<grid, block, smem>>>: CTAs in order (x fastest), the block's threads persist over the CTAs
+template <class K, class... A>
+void launch(dim3 grid, dim3 block, size_t smem, K kernel, A... args) {
+    const int nthreads = (int)(block.x * block.y * block.z);
+    const int nwarps = (nthreads + 31) / 32;
+    Cta cta;
+    Barrier bar(nthreads);
+    cta.bar = &bar;
+    for (int w = 0; w < nwarps; w++) cta.warps.push_back(new Warp(std::min(32, nthreads - 32 * w)));
+    std::vector<unsigned char> dynbuf(smem + 64);
+    cta.dyn = dynbuf.data() + ((64 - (reinterpret_cast<uintptr_t>(dynbuf.data()) & 63)) & 63);
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; t++)
+        th.emplace_back([&, t] {
+            t_cta = &cta;
+            t_lane = t & 31;
+            t_warp = t >> 5;
+            blockDim = block;
+            gridDim = grid;
+            threadIdx = dim3((unsigned)t % block.x, ((unsigned)t / block.x) % block.y, (unsigned)t / (block.x * block.y));
+            for (unsigned bz = 0; bz < grid.z; bz++)
+                for (unsigned by = 0; by < grid.y; by++)
+                    for (unsigned bx = 0; bx < grid.x; bx++) {
+                        blockIdx = dim3(bx, by, bz);
+                        kernel(args...);
+                        bar.wait();  // the next CTA reuses the shared memory
+                    }
+        });
+    for (auto &t : th) t.join();
+    for (Warp *w : cta.warps) delete w;
+}
+}  // namespace emu
