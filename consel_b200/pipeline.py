@@ -172,10 +172,37 @@ def consel(reps: api.Reps, datvec, rr, bb, ass=None, alpha=(0.05, 0.10, 0.5, 0.9
     return out
 
 
+def scale_setup(L: np.ndarray, rr, _comm=None, _allgather=None):
+    """api.scale_setup with the row sums of a sharded run split over the ranks: one process per GPU shares the
+    host's cores and memory system, so every rank sums ceil(K/world) rows (sequentially, the reference's
+    rounding order: src/makermt.c:159-164) and one small all-gather completes datvec on every rank --
+    instead of `world` processes each streaming the whole matrix.  Collective when a communicator exists.
+    (_comm / _allgather: test seams -- (rank, world) and a stand-in for cgpu_comm_allgather_host.)"""
+    rank, world = _comm if _comm is not None else comm_info()
+    L = np.ascontiguousarray(L, dtype=np.float64)
+    K, n = L.shape
+    if world == 1 or K < 4 * world:
+        return api.scale_setup(L, rr)
+    per = -(-K // world)
+    r0, r1 = min(K, rank * per), min(K, rank * per + per)
+    mine, everyone = np.zeros(per), np.zeros(per * world)
+    lib = api.load()
+    if r1 > r0:
+        lib.cgpu_host_rowsums(api._dp(L[r0:r1]), r1 - r0, n, api._dp(mine))  # a row range of a C-contiguous matrix is contiguous
+    if _allgather is not None:
+        _allgather(mine, everyone)
+    else:
+        api._check(lib.cgpu_comm_allgather_host(mine.ctypes.data_as(C.c_void_p), everyone.ctypes.data_as(C.c_void_p),
+                                                C.c_longlong(per * 8)))
+    rr = np.asarray(rr, dtype=np.float64)
+    bn = (rr * np.float64(n)).astype(np.int32)
+    return everyone[:K].copy(), bn, bn.astype(np.float64) / np.float64(n)
+
+
 def run(L, rr, bb, seed: int, rng_mode: int = api.RNG_MT19937, sum_mode: int = api.SUM_STRICT, matrix=None, **kw) -> dict:
     """makermt + consel in one process: L (K x n) -> p-value table, nothing touches a file."""
     L = np.ascontiguousarray(L, dtype=np.float64)
-    datvec, bn, rr1 = api.scale_setup(L, rr)
+    datvec, bn, rr1 = scale_setup(L, rr)
     t0 = time.perf_counter()
     mat = matrix if matrix is not None else api.Matrix(L)
     reps = mat.scaleboot(bn, bb, seed, 0, rng_mode, sum_mode)

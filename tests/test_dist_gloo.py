@@ -209,3 +209,23 @@ def test_shard_and_item_ranges_partition():
     b0, b1 = C.c_int(), C.c_int()
     assert lib.cgpu_shard_range(100, C.byref(b0), C.byref(b1)) == 0 and (b0.value, b1.value) == (0, 100)
     assert lib.cgpu_comm_item_range(10, C.byref(b0), C.byref(b1)) == 0 and (b0.value, b1.value) == (0, 10)
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_sharded_row_sums_equal_the_sequential_sums(world):
+    """pipeline.scale_setup: every rank sums its own row range, one all-gather completes datvec; the result is
+    api.scale_setup's (the reference's left-to-right sums) bit for bit, for K not divisible by the world size"""
+    import consel_b200 as cg
+    rng = np.random.default_rng(world)
+    L = -rng.exponential(4.0, size=(37, 333)) - 1.0
+    rr = [0.5, 1.0, 1.4]
+    want = cg.scale_setup(L, rr)
+    per = -(-37 // world)
+    shares = {}
+    for rank in range(world):  # pass 1: what every rank would send
+        pipeline.scale_setup(L, rr, _comm=(rank, world), _allgather=lambda mine, out, r=rank: shares.__setitem__(r, mine.copy()))
+    assert all(len(v) == per for v in shares.values())
+    gathered = np.concatenate([shares[r] for r in range(world)])
+    for rank in range(world):  # pass 2: every rank receives the same gathered vector
+        got = pipeline.scale_setup(L, rr, _comm=(rank, world), _allgather=lambda mine, out: out.__setitem__(slice(None), gathered))
+        assert all(np.array_equal(a, b) for a, b in zip(got, want))
