@@ -17,6 +17,7 @@ from __future__ import annotations
 
 import ctypes as C
 import functools
+import threading
 import time
 
 import numpy as np
@@ -172,41 +173,80 @@ def consel(reps: api.Reps, datvec, rr, bb, ass=None, alpha=(0.05, 0.10, 0.5, 0.9
     return out
 
 
+def _rowsums_local(L: np.ndarray, comm):
+    """this rank's share of the row sums (all of them without a communicator): host threads only, no device or
+    collective call, so it may run beside a resampling call.  Returns (values, rows per rank, world)."""
+    rank, world = comm
+    K, n = L.shape
+    lib = api.load()
+    if world == 1 or K < 4 * world:
+        datvec = np.zeros(K)
+        lib.cgpu_host_rowsums(api._dp(L), K, n, api._dp(datvec))
+        return datvec, K, 1
+    per = -(-K // world)
+    r0, r1 = min(K, rank * per), min(K, rank * per + per)
+    mine = np.zeros(per)
+    if r1 > r0:
+        lib.cgpu_host_rowsums(api._dp(L[r0:r1]), r1 - r0, n, api._dp(mine))  # a row range of a C-contiguous matrix is contiguous
+    return mine, per, world
+
+
+def _rowsums_gather(part, K: int, _allgather=None) -> np.ndarray:
+    """completes datvec on every rank: one small all-gather of the per-rank shares (collective)"""
+    mine, per, world = part
+    if world == 1:
+        return mine
+    everyone = np.zeros(per * world)
+    if _allgather is not None:
+        _allgather(mine, everyone)
+    else:
+        api._check(api.load().cgpu_comm_allgather_host(mine.ctypes.data_as(C.c_void_p), everyone.ctypes.data_as(C.c_void_p),
+                                                       C.c_longlong(per * 8)))
+    return everyone[:K].copy()
+
+
 def scale_setup(L: np.ndarray, rr, _comm=None, _allgather=None):
     """api.scale_setup with the row sums of a sharded run split over the ranks: one process per GPU shares the
     host's cores and memory system, so every rank sums ceil(K/world) rows (sequentially, the reference's
     rounding order: src/makermt.c:159-164) and one small all-gather completes datvec on every rank --
     instead of `world` processes each streaming the whole matrix.  Collective when a communicator exists.
     (_comm / _allgather: test seams -- (rank, world) and a stand-in for cgpu_comm_allgather_host.)"""
-    rank, world = _comm if _comm is not None else comm_info()
     L = np.ascontiguousarray(L, dtype=np.float64)
     K, n = L.shape
-    if world == 1 or K < 4 * world:
-        return api.scale_setup(L, rr)
-    per = -(-K // world)
-    r0, r1 = min(K, rank * per), min(K, rank * per + per)
-    mine, everyone = np.zeros(per), np.zeros(per * world)
-    lib = api.load()
-    if r1 > r0:
-        lib.cgpu_host_rowsums(api._dp(L[r0:r1]), r1 - r0, n, api._dp(mine))  # a row range of a C-contiguous matrix is contiguous
-    if _allgather is not None:
-        _allgather(mine, everyone)
-    else:
-        api._check(lib.cgpu_comm_allgather_host(mine.ctypes.data_as(C.c_void_p), everyone.ctypes.data_as(C.c_void_p),
-                                                C.c_longlong(per * 8)))
+    datvec = _rowsums_gather(_rowsums_local(L, _comm if _comm is not None else comm_info()), K, _allgather)
     rr = np.asarray(rr, dtype=np.float64)
-    bn = (rr * np.float64(n)).astype(np.int32)
-    return everyone[:K].copy(), bn, bn.astype(np.float64) / np.float64(n)
+    bn = (rr * np.float64(n)).astype(np.int32)  # bn = (int)(rr*n), rr1 = bn/n: src/makermt.c:165-168, as api.scale_setup
+    return datvec, bn, bn.astype(np.float64) / np.float64(n)
 
 
 def run(L, rr, bb, seed: int, rng_mode: int = api.RNG_MT19937, sum_mode: int = api.SUM_STRICT, matrix=None, **kw) -> dict:
-    """makermt + consel in one process: L (K x n) -> p-value table, nothing touches a file."""
+    """makermt + consel in one process: L (K x n) -> p-value table, nothing touches a file.
+    The row sums (datvec; host threads) are formed while the device resamples: consel needs them first."""
     L = np.ascontiguousarray(L, dtype=np.float64)
-    datvec, bn, rr1 = scale_setup(L, rr)
-    t0 = time.perf_counter()
-    mat = matrix if matrix is not None else api.Matrix(L)
-    reps = mat.scaleboot(bn, bb, seed, 0, rng_mode, sum_mode)
-    t_boot = time.perf_counter() - t0
+    K, n = L.shape
+    rr_a = np.asarray(rr, dtype=np.float64)
+    bn = (rr_a * np.float64(n)).astype(np.int32)
+    rr1 = bn.astype(np.float64) / np.float64(n)
+    comm = comm_info()
+    box = {}
+
+    def sums():
+        try:
+            box["part"] = _rowsums_local(L, comm)
+        except BaseException as e:  # re-raised on the calling thread
+            box["error"] = e
+    th = threading.Thread(target=sums)
+    th.start()
+    try:
+        t0 = time.perf_counter()
+        mat = matrix if matrix is not None else api.Matrix(L)
+        reps = mat.scaleboot(bn, bb, seed, 0, rng_mode, sum_mode)
+        t_boot = time.perf_counter() - t0
+    finally:
+        th.join()
+    if "error" in box:
+        raise box["error"]
+    datvec = _rowsums_gather(box["part"], K)
     res = consel(reps, datvec, rr1, bb, **kw)
     res["timing"]["makermt_s"] = t_boot
     res["timing"]["device_ms"] = api.last_timing()
