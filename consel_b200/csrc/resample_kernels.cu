@@ -512,6 +512,10 @@ static int hist_dispatch(int src, const void *d_idx, int n, int NP, int bn, int 
         CGPU_HISTG_CASE(2, false) CGPU_HISTG_CASE(2, true)
 #undef CGPU_HISTG_CASE
         CGPU_LAUNCH_CHECK();
+        if (rows && d_err) {  // a byte that wrapped past 255 changes the row's byte sum (hist_bucket.cuh)
+            row_checksum_kernel<<<nb, RCS_THREADS, 0, st>>>(reinterpret_cast<const unsigned char *>(d_counts), NP, bn, d_err);
+            CGPU_LAUNCH_CHECK();
+        }
     }
     return CGPU_OK;
 }

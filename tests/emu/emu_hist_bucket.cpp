@@ -80,6 +80,15 @@ static int run(uint32_t n, int bn, int nb, int hot) {
         }
         if (tot != (unsigned)bn) bad++;
     }
+    // ---- the row checksum of the global-atomic path on the same rows: silent on exact rows, raised by a wrap
+    {
+        std::vector<unsigned char> exact((size_t)nb * NP + 16);
+        unsigned char *ex = exact.data() + ((16 - (reinterpret_cast<uintptr_t>(exact.data()) & 15)) & 15);
+        for (size_t e = 0; e < (size_t)nb * NP; e++) ex[e] = (unsigned char)want[e];  // a count above 255 loses 256 here
+        int err2 = 0;
+        emu::launch(dim3(nb), dim3(RCS_THREADS), 0, row_checksum_kernel, (const unsigned char *)ex, NP, bn, &err2);
+        if (err2 != (over ? 1 : 0)) bad++;
+    }
     printf("n=%u NP=%d bn=%d nb=%d src=%d wbl=%d buckets=%d tiles=%d: %lld mismatches, err=%d (expected %d)\n", n, NP, bn, nb, SRC,
            WBL, nbk, tiles, bad, err, over ? 1 : 0);
     return (bad == 0 && err == (over ? 1 : 0)) ? 0 : 1;
