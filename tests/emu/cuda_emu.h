@@ -15,6 +15,7 @@
 // called by all 32 lanes of a warp (as CUDA requires with a full mask).
 #pragma once
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -28,7 +29,7 @@ struct dim3 {
     unsigned x = 1, y = 1, z = 1;
     dim3(unsigned x_ = 1, unsigned y_ = 1, unsigned z_ = 1) : x(x_), y(y_), z(z_) {}
 };
-struct uint4 {
+struct alignas(16) uint4 {  // 16-byte aligned like CUDA's: -fsanitize=alignment flags a misaligned vector access
     unsigned x, y, z, w;
 };
 static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{x, y, z, w}; }
@@ -116,8 +117,9 @@ void launch(dim3 grid, dim3 block, size_t smem, K kernel, A... args) {
     Barrier bar(nthreads);
     cta.bar = &bar;
     for (int w = 0; w < nwarps; w++) cta.warps.push_back(new Warp(std::min(32, nthreads - 32 * w)));
-    std::vector<unsigned char> dynbuf(smem + 64);
-    cta.dyn = dynbuf.data() + ((64 - (reinterpret_cast<uintptr_t>(dynbuf.data()) & 63)) & 63);
+    // exactly `smem` bytes, 16-byte aligned like the hardware's window: AddressSanitizer sees an overrun
+    unsigned char *dynbuf = static_cast<unsigned char *>(aligned_alloc(16, std::max<size_t>(16, (smem + 15) / 16 * 16)));
+    cta.dyn = dynbuf;
     std::vector<std::thread> th;
     for (int t = 0; t < nthreads; t++)
         th.emplace_back([&, t] {
@@ -137,5 +139,6 @@ void launch(dim3 grid, dim3 block, size_t smem, K kernel, A... args) {
         });
     for (auto &t : th) t.join();
     for (Warp *w : cta.warps) delete w;
+    free(dynbuf);
 }
 }  // namespace emu

@@ -8,6 +8,7 @@
 // the error flag).  Exit status 0 = all rows equal and the flag is as expected.
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "cuda_emu.h"
@@ -50,9 +51,12 @@ static int run(uint32_t n, int bn, int nb, int hot) {
     // ---- the kernels
     const size_t pstride = (size_t)((bn + 7) / 8 * 8) + (size_t)8 * nbk;
     std::vector<unsigned> cnt((size_t)nb * nbk, 0), off((size_t)nb * nbk, 0xdeadbeefu), cur((size_t)nb * nbk, 0xdeadbeefu);
-    std::vector<unsigned short> part((size_t)nb * pstride, 0xffff);
-    std::vector<unsigned char> rows((size_t)nb * NP + 16, 0xee);
-    unsigned char *rows_al = rows.data() + ((16 - (reinterpret_cast<uintptr_t>(rows.data()) & 15)) & 15);
+    // "device" buffers: exactly sized and 16-byte aligned (cudaMalloc gives 256), so that the sanitizer builds see
+    // any overrun or misaligned 16-byte access
+    unsigned short *part = static_cast<unsigned short *>(aligned_alloc(16, ((size_t)nb * pstride * 2 + 15) / 16 * 16));
+    unsigned char *rows_al = static_cast<unsigned char *>(aligned_alloc(16, (size_t)nb * NP));
+    memset(part, 0xff, (size_t)nb * pstride * 2);
+    memset(rows_al, 0xee, (size_t)nb * NP);
     int err = 0;
     const int tiles = (bn + BK_TILE - 1) / BK_TILE;
     const uint32_t *d_idx = SRC == 0 ? idx.data() : nullptr;
@@ -61,8 +65,8 @@ static int run(uint32_t n, int bn, int nb, int hot) {
     emu::launch(dim3((nb + 127) / 128), dim3(128), 0, bucket_scan_kernel, (const unsigned *)cnt.data(), nb, nbk, off.data(),
                 cur.data());
     emu::launch(dim3(tiles, nb), dim3(BK_THREADS), bk_scatter_smem(), bucket_scatter_kernel<SRC, WBL>, d_idx, n, bn, nbk,
-                (const unsigned *)off.data(), cur.data(), part.data(), pstride, key0, key1, scale, b_first, ctr3);
-    emu::launch(dim3(nbk, nb), dim3(BKH_THREADS), (size_t)1 << WBL, bucket_hist_kernel<WBL>, (const unsigned short *)part.data(),
+                (const unsigned *)off.data(), cur.data(), part, pstride, key0, key1, scale, b_first, ctr3);
+    emu::launch(dim3(nbk, nb), dim3(BKH_THREADS), (size_t)1 << WBL, bucket_hist_kernel<WBL>, (const unsigned short *)part,
                 pstride, (const unsigned *)cnt.data(), (const unsigned *)off.data(), nbk, NP, rows_al, &err);
     // ---- compare
     long long bad = 0;
@@ -82,15 +86,17 @@ static int run(uint32_t n, int bn, int nb, int hot) {
     }
     // ---- the row checksum of the global-atomic path on the same rows: silent on exact rows, raised by a wrap
     {
-        std::vector<unsigned char> exact((size_t)nb * NP + 16);
-        unsigned char *ex = exact.data() + ((16 - (reinterpret_cast<uintptr_t>(exact.data()) & 15)) & 15);
+        unsigned char *ex = static_cast<unsigned char *>(aligned_alloc(16, (size_t)nb * NP));
         for (size_t e = 0; e < (size_t)nb * NP; e++) ex[e] = (unsigned char)want[e];  // a count above 255 loses 256 here
         int err2 = 0;
         emu::launch(dim3(nb), dim3(RCS_THREADS), 0, row_checksum_kernel, (const unsigned char *)ex, NP, bn, &err2);
         if (err2 != (over ? 1 : 0)) bad++;
+        free(ex);
     }
     printf("n=%u NP=%d bn=%d nb=%d src=%d wbl=%d buckets=%d tiles=%d: %lld mismatches, err=%d (expected %d)\n", n, NP, bn, nb, SRC,
            WBL, nbk, tiles, bad, err, over ? 1 : 0);
+    free(part);
+    free(rows_al);
     return (bad == 0 && err == (over ? 1 : 0)) ? 0 : 1;
 }
 

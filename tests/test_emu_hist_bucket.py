@@ -64,3 +64,20 @@ def test_bucket_kernels_are_race_free_under_thread_sanitizer(tmp_path):
         r = subprocess.run([str(exe), *map(str, case)], capture_output=True, text=True, timeout=900)
         assert r.returncode == 0, r.stdout + r.stderr
         assert "ThreadSanitizer" not in r.stderr and " 0 mismatches" in r.stdout
+
+
+def test_bucket_kernels_stay_in_bounds_and_aligned(tmp_path):
+    """AddressSanitizer + UndefinedBehaviorSanitizer: the "device" buffers are exactly sized and 16-byte aligned,
+    uint4 is 16-byte aligned as on the device, so an overrun or a misaligned vector access aborts the run
+    (what would be an illegal-address / misaligned-address fault on the GPU)."""
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    try:
+        exe = _build(tmp_path, "emu_hist_bucket_asan", ["-fsanitize=address,undefined", "-fno-sanitize-recover=all"])
+    except subprocess.CalledProcessError as e:
+        pytest.skip("sanitizer build unavailable: " + e.stderr[-200:])
+    for case in ((150000, 120001, 2, 0, 16), (150000, 120001, 1, 1, 16), (40000, 30001, 1, 0, 8), (1000, 5, 2, 1, 8),
+                 (70000, 8193, 1, 0, 16), (300, 3000, 2, 0, 8, 300)):
+        r = subprocess.run([str(exe), *map(str, case)], capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0, r.stdout + r.stderr
+        assert "runtime error" not in r.stderr and "AddressSanitizer" not in r.stderr and " 0 mismatches" in r.stdout
