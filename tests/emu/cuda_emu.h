@@ -11,7 +11,7 @@
 // Because every access is a real memory access of a real thread, ThreadSanitizer sees a missing
 // barrier or an unsynchronised shared-memory update as a data race.
 //
-// Supported: what consel_b200/csrc/hist_bucket.cuh and philox.cuh use.  Warp-collectives must be
+// Supported: what consel_b200/csrc/{hist_bucket.cuh,philox.cuh,stats_kernels.cu,resample_kernels.cu} use.  Warp-collectives must be
 // called by all 32 lanes of a warp (as CUDA requires with a full mask).
 #pragma once
 #include <stdint.h>
@@ -31,6 +31,9 @@ struct dim3 {
 };
 struct alignas(16) uint4 {  // 16-byte aligned like CUDA's: -fsanitize=alignment flags a misaligned vector access
     unsigned x, y, z, w;
+};
+struct alignas(16) double2 {
+    double x, y;
 };
 static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{x, y, z, w}; }
 
@@ -58,8 +61,9 @@ class Barrier {  // reusable barrier (mutex + condition variable: visible to Thr
 };
 struct Warp {
     Barrier bar{32};
-    unsigned mail[32];
-    explicit Warp(int lanes) : bar(lanes) {}
+    unsigned long long mail[32];
+    int lanes;
+    explicit Warp(int n) : bar(n), lanes(n) {}
 };
 struct Cta {
     Barrier *bar = nullptr;
@@ -79,24 +83,91 @@ inline thread_local dim3 threadIdx, blockIdx, blockDim, gridDim;
 #define __forceinline__ inline
 #define __restrict__
 #define __launch_bounds__(...)
-#define __align__(x) alignas(x)
+#define __align__(x) __attribute__((aligned(x)))
 #define __shared__ static
 #define CGPU_DYN_SMEM(T, name) T *name = reinterpret_cast<T *>(emu::dyn_smem())
 
 static inline void __syncthreads() { emu::t_cta->bar->wait(); }
 static inline void __syncwarp(unsigned = 0xffffffffu) { emu::t_cta->warps[emu::t_warp]->bar.wait(); }
-static inline unsigned emu_exchange(unsigned v, int src_lane) {
+// warp collectives: every lane deposits 64 bits in the warp's mailbox, barrier, read, barrier
+static inline unsigned long long emu_exchange64(unsigned long long v, int src_lane) {
     emu::Warp *w = emu::t_cta->warps[emu::t_warp];
     w->mail[emu::t_lane] = v;
     w->bar.wait();
-    const unsigned r = w->mail[src_lane & 31];
+    const unsigned long long r = w->mail[src_lane & 31];
     w->bar.wait();
     return r;
 }
-static inline unsigned __shfl_xor_sync(unsigned, unsigned v, int off) { return emu_exchange(v, emu::t_lane ^ off); }
-static inline unsigned __shfl_up_sync(unsigned, unsigned v, int d) { return emu_exchange(v, emu::t_lane >= d ? emu::t_lane - d : emu::t_lane); }
+template <class T>
+static inline T emu_shfl(T v, int src_lane) {
+    static_assert(sizeof(T) <= 8, "shuffle of at most 64 bits");
+    unsigned long long bits = 0;
+    memcpy(&bits, &v, sizeof(T));
+    bits = emu_exchange64(bits, src_lane);
+    T r;
+    memcpy(&r, &bits, sizeof(T));
+    return r;
+}
+template <class T>
+static inline T __shfl_xor_sync(unsigned, T v, int off) { return emu_shfl(v, emu::t_lane ^ off); }
+template <class T>
+static inline T __shfl_up_sync(unsigned, T v, int d) { return emu_shfl(v, emu::t_lane >= d ? emu::t_lane - d : emu::t_lane); }
+template <class T>
+static inline T __shfl_down_sync(unsigned, T v, int d) { return emu_shfl(v, emu::t_lane + d < 32 ? emu::t_lane + d : emu::t_lane); }
+template <class T>
+static inline T __shfl_sync(unsigned, T v, int lane) { return emu_shfl(v, lane); }
+static inline unsigned __ballot_sync(unsigned, int pred) {
+    emu::Warp *w = emu::t_cta->warps[emu::t_warp];
+    w->mail[emu::t_lane] = pred ? 1ull : 0ull;
+    w->bar.wait();
+    unsigned m = 0;
+    for (int l = 0; l < w->lanes; l++) m |= (unsigned)w->mail[l] << l;
+    w->bar.wait();
+    return m;
+}
+static inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0; }
+static inline int __all_sync(unsigned mask, int pred) {
+    return __ballot_sync(mask, !pred) == 0;
+}
+// lanes of `mask` whose value equals mine (called by exactly the lanes of `mask`: the others must still
+// take part in the mailbox exchange, so this emulation requires a full warp to call it -- as the kernels do)
+static inline unsigned __match_any_sync(unsigned mask, unsigned v) {
+    emu::Warp *w = emu::t_cta->warps[emu::t_warp];
+    w->mail[emu::t_lane] = v;
+    w->bar.wait();
+    unsigned m = 0;
+    for (int l = 0; l < w->lanes; l++)
+        if (((mask >> l) & 1u) && (unsigned)w->mail[l] == v) m |= 1u << l;
+    w->bar.wait();
+    return m;
+}
 static inline unsigned atomicAdd(unsigned *p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 static inline int atomicExch(int *p, int v) { return __atomic_exchange_n(p, v, __ATOMIC_RELAXED); }
+static inline int atomicAdd(int *p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
+static inline unsigned atomicExch(unsigned *p, unsigned v) { return __atomic_exchange_n(p, v, __ATOMIC_RELAXED); }
+// IEEE round-to-nearest fp64 operations, one rounding each (compile with -ffp-contract=off)
+static inline double __dadd_rn(double a, double b) { return a + b; }
+static inline double __dsub_rn(double a, double b) { return a - b; }
+static inline double __dmul_rn(double a, double b) { return a * b; }
+static inline double __ddiv_rn(double a, double b) { return a / b; }
+static inline double __dsqrt_rn(double a) { return __builtin_sqrt(a); }
+static inline double __fma_rn(double a, double b, double c) { return __builtin_fma(a, b, c); }
+static inline long long __double_as_longlong(double x) { long long r; memcpy(&r, &x, 8); return r; }
+static inline double __longlong_as_double(long long x) { double r; memcpy(&r, &x, 8); return r; }
+static inline int __popc(unsigned x) { return __builtin_popcount(x); }
+static inline int __ffs(int x) { return __builtin_ffs(x); }
+static inline unsigned __byte_perm(unsigned a, unsigned b, unsigned sel) {
+    const unsigned long long ab = ((unsigned long long)b << 32) | a;
+    unsigned r = 0;
+    for (int i = 0; i < 4; i++) {
+        const unsigned s4 = (sel >> (4 * i)) & 0xfu;
+        unsigned byte = (unsigned)(ab >> (8 * (s4 & 7u))) & 0xffu;
+        if (s4 & 8u) byte = (byte & 0x80u) ? 0xffu : 0u;  // replicate the sign bit
+        r |= byte << (8 * i);
+    }
+    return r;
+}
 static inline unsigned __umulhi(unsigned a, unsigned b) { return (unsigned)(((unsigned long long)a * b) >> 32); }
 static inline unsigned __dp4a(unsigned a, unsigned b, unsigned c) {
     for (int i = 0; i < 4; i++) c += ((a >> (8 * i)) & 0xffu) * ((b >> (8 * i)) & 0xffu);

@@ -1,0 +1,65 @@
+// Entry points of the translation units that are NOT part of the emulated library (see
+// build_emu_lib.py): the MT19937 stream, the contractions and the tensor-core path need the GPU and
+// fail with CGPU_ENODEV here; the communicator degenerates to a single rank.
+#include <string.h>
+
+#include "cgpu_internal.h"
+
+namespace cgpu {
+static int gpu_only(const char *what) {
+    set_error(CGPU_ENODEV, "%s needs the GPU (emulated library: statistics, count queries, KH/SH tests and the Philox histogram only)", what);
+    return CGPU_ENODEV;
+}
+int fx_prepare(DevMatrix &, cudaStream_t, bool) { return gpu_only("fx_prepare"); }
+bool fx_needs_partial(const DevMatrix &, int, int) { return false; }
+int launch_contract(const DevMatrix &, const unsigned long long *, int, double, double *, int, int, int, cudaStream_t) { return gpu_only("contract_kernel"); }
+int launch_contract_i8(const DevMatrix &, const unsigned char *, int, int, int *, double, double *, int, int, cudaStream_t, PhaseTimer *, int) {
+    return gpu_only("the tcgen05 GEMM");
+}
+int launch_transpose_L(const double *, int, int, int, int, double *, int *, cudaStream_t) { return gpu_only("transpose_L"); }
+int mt_poly_positions(const Gf2Poly *, uint32_t *) { return 0; }
+int launch_mt_jump(uint32_t *, const int2 *, const uint32_t *, int, int, cudaStream_t) { return gpu_only("mt_jump_kernel"); }
+bool mt_draw_hist_fits(int) { return false; }
+int launch_mt_draw(const MtPlan &, const DrawPlan &, uint32_t, void *, cudaStream_t) { return gpu_only("mt_draw_kernel"); }
+int launch_mt_draw_hist(const MtPlan &, const DrawPlan &, const unsigned int *, unsigned char *const *, int, uint32_t, int *, cudaStream_t) {
+    return gpu_only("mt_draw_hist_kernel");
+}
+int launch_mt_draw_range(const MtPlan &, unsigned long long, unsigned long long, uint32_t, void *, cudaStream_t) { return gpu_only("mt_draw_kernel"); }
+int make_draw_plan(int, const unsigned long long *, const unsigned long long *, const unsigned long long *, unsigned long long,
+                   unsigned long long, DrawPlan *) {
+    return gpu_only("the MT19937 draw plan");
+}
+int resolve_draw_slots(const MtPlan &, DrawPlan *) { return gpu_only("the MT19937 draw plan"); }
+
+int comm_world() { return 1; }
+int comm_rank() { return 0; }
+int comm_group_start() { return CGPU_OK; }
+int comm_group_end() { return CGPU_OK; }
+int comm_allgather_f64(const double *send, double *recv, size_t n, cudaStream_t) {
+    if (send != recv) memmove(recv, send, n * sizeof(double));
+    return CGPU_OK;
+}
+int comm_allreduce_f64(const double *send, double *recv, size_t n, int, cudaStream_t) {
+    if (send != recv) memmove(recv, send, n * sizeof(double));
+    return CGPU_OK;
+}
+int comm_reduce_scatter_f64(const double *send, double *recv, size_t n, int, cudaStream_t) {
+    if (send != recv) memmove(recv, send, n * sizeof(double));
+    return CGPU_OK;
+}
+}  // namespace cgpu
+
+extern "C" {
+int cgpu_comm_allreduce_host(double *, long long, int) { return CGPU_OK; }
+int cgpu_comm_item_range(int cm, int *row0, int *nrows) {
+    if (row0) *row0 = 0;
+    if (nrows) *nrows = cm;
+    return CGPU_OK;
+}
+int cgpu_comm_info(int *rank, int *world) {
+    if (rank) *rank = 0;
+    if (world) *world = 1;
+    return CGPU_OK;
+}
+void cgpu_comm_destroy(void) {}
+}

@@ -1,0 +1,111 @@
+"""The consel side of the PRODUCT library on the CPU: tests/emu/build_emu_lib.py compiles the C ABI and the
+CUDA sources of the statistics / count-query / KH-SH kernels and of the histogram kernels for the host
+(kernel launches become emu::launch, one OS thread per CUDA thread) and the usual ctypes binding
+(consel_b200.api) drives it.  Everything is compared bit for bit with oracle/oracle.c, exactly like the
+`-m gpu` tests do on the device -- so the kernel arithmetic and the host glue of capi_stats.cu are pinned
+even where no GPU is available.  (The MT19937 stream and the contractions need the GPU: the emulated
+library refuses them with CGPU_ENODEV.)"""
+import ctypes as C
+import shutil
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT / "tests" / "emu"))
+
+
+@pytest.fixture(scope="module")
+def cg(tmp_path_factory):
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    import build_emu_lib
+
+    import consel_b200 as cg
+    from consel_b200 import api
+    lib = C.CDLL(str(build_emu_lib.build(tmp_path_factory.mktemp("emulib"))))
+    lib.cgpu_last_error.restype = C.c_char_p
+    lib.cgpu_launch_count.restype = C.c_longlong
+    lib.cgpu_smooth_count.restype = C.c_double
+    saved = api._lib
+    api._lib = lib  # the binding now talks to the emulated library
+    try:
+        cg.init()
+        cg.set_shard(0, 1)
+        yield cg
+    finally:
+        api._lib = saved
+
+
+def _ordered(orc, datvec, ass=None):
+    ptr, idx = orc.identity_assoc(len(datvec)) if ass is None else ass
+    _, _, sptr, sidx = orc.order_items(datvec, ptr, idx)
+    return sptr, sidx
+
+
+def test_statistics_counts_order_statistics_bit_exact(cg, orc):
+    rng = np.random.default_rng(1)
+    K, bbs = 9, [40, 64, 33]
+    reps_host = [rng.normal(size=(K, b)) for b in bbs]
+    reps_host[1][3] = reps_host[1][5]  # two identical trees: ties in the max over the complement
+    datvec = rng.normal(size=K) * 3
+    sptr, sidx = _ordered(orc, datvec)
+    reps = cg.Reps.upload(reps_host)
+    reps.stats_build(sptr, sidx)
+    got = reps.stats_download()
+    for s, r in enumerate(reps_host):
+        assert np.array_equal(got[s], orc.repminmaxs(r, sptr, sidx)), s
+    srt = reps.stats_download(sorted_rows=True)
+    for s in range(len(bbs)):
+        assert np.array_equal(srt[s], np.sort(got[s], axis=1))
+    thr = np.concatenate([rng.normal(size=(K, 2)), np.zeros((K, 1)), got[1][:, :1]], axis=1)  # incl. an exact statistic value
+    q = reps.count_query(thr)
+    for s in range(len(bbs)):
+        v = np.sort(got[s], axis=1)
+        for i in range(K):
+            for k in range(thr.shape[1]):
+                t = thr[i, k]
+                c = int(np.searchsorted(v[i], t, side="right"))
+                assert q["cnt"][i, s, k] == c
+                assert q["lo"][i, s, k] == (v[i][c - 1] if c > 0 else -1e30) and q["hi"][i, s, k] == (v[i][c] if c < len(v[i]) else 1e30)
+                assert (q["min1"][i, s, k], q["min2"][i, s, k], q["max1"][i, s, k], q["max2"][i, s, k]) == (v[i][0], v[i][1], v[i][-1], v[i][-2])
+                # the smoothed count the AU fit uses is cntdist3 of the sorted row
+                assert cg.smooth_count(q[i, s, k], len(v[i]), float(t)) == orc.cntdist(v[i], float(t), 3)
+    part = reps.count_query_rows(2, thr[2:6])
+    assert part.tobytes() == q[2:6].tobytes()
+    rank = np.array([0, 1, bbs[1] // 2, bbs[1] - 1, 5, 7, 11, 13, 17], dtype=np.int32)
+    assert np.array_equal(reps.order_stat(1, rank), np.sort(got[1], axis=1)[np.arange(K), rank])
+    reps.free()
+
+
+def test_kh_sh_tests_bit_exact_identity_and_grouped_associations(cg, orc):
+    rng = np.random.default_rng(2)
+    K, B = 8, 50
+    x = rng.normal(size=(K, B)) + np.linspace(0, 1.5, K)[:, None]
+    datvec = -np.linspace(0, 6, K) + rng.normal(size=K)
+    for ass in (None, (np.array([0, 2, 3, 6, 8], dtype=np.int32), np.array([0, 1, 2, 3, 4, 5, 6, 7], dtype=np.int32))):
+        sptr, sidx = _ordered(orc, datvec, ass)
+        reps = cg.Reps.upload([x])
+        got = reps.mctest(0, datvec, sptr, sidx)
+        want = orc.mctest(x, datvec, sptr, sidx)
+        for g, w in zip(got, want):
+            assert np.array_equal(g, w)
+        reps.free()
+
+
+def test_philox_histogram_paths_agree_and_are_multinomial(cg):
+    # byte-row paths are internal to the int8 contraction; the BJ8 seam (cgpu_resample_counts) runs the group kernel
+    n, bn, bb = 700, [350, 980], [9, 17]
+    a = cg.resample_counts(n, bn, bb, 5, 1, rng_mode=cg.RNG_PHILOX)
+    assert a.shape == (17, n) and (a.sum(axis=1) == 980).all()
+    b = cg.resample_counts(n, bn, bb, 5, 1, rng_mode=cg.RNG_PHILOX)
+    c = cg.resample_counts(n, bn, bb, 6, 1, rng_mode=cg.RNG_PHILOX)
+    assert np.array_equal(a, b) and not np.array_equal(a, c)
+
+
+def test_gpu_only_paths_are_refused_not_emulated(cg):
+    L = -np.ones((3, 64))
+    with pytest.raises(cg.CgpuError):
+        cg.scaleboot_all(L, [32], [4], 1)  # MT19937 stream + contraction: device only
