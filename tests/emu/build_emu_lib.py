@@ -74,7 +74,9 @@ def build(out_dir: Path, extra_flags=()) -> Path:
         dst.write_text(f'#line 1 "{CSRC / name}"\n' + text)
         cpps.append(dst)
     lib = out_dir / "libconselgpu_emu.so"
-    cmd = ["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-pthread", "-ffp-contract=off", "-DCGPU_EMU", "-w",
+    # -Bsymbolic: the library's own calls bind to ITSELF even when the real libconselgpu.so (same symbol names) is
+    # already loaded into the process with global visibility (libconselhost.so pulls it in that way)
+    cmd = ["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-pthread", "-ffp-contract=off", "-DCGPU_EMU", "-w", "-Wl,-Bsymbolic",
            f"-I{EMU / 'shim'}", f"-I{EMU}", f"-I{CSRC}", f"-I{ROOT / 'include'}", *extra_flags, "-o", str(lib),
            *map(str, cpps), str(EMU / "emu_stubs.cpp"), str(CSRC / "gf2_mt.cpp")]
     r = subprocess.run(cmd, capture_output=True, text=True)
