@@ -25,6 +25,10 @@ EMU = Path(__file__).resolve().parent
 ROOT = EMU.parent.parent
 CSRC = ROOT / "consel_b200" / "csrc"
 SOURCES = ["capi.cu", "capi_stats.cu", "stats_kernels.cu", "resample_kernels.cu"]
+HOST = ROOT / "consel_b200" / "host"
+# the native makermt->consel pipeline and AU driver (libconselhost.so) go INTO the emulated library, so that their
+# cgpu_* calls bind to the emulated entry points whatever else the process has loaded
+HOST_SOURCES = ["pipeline.cpp", "audriver.cpp", "aufit.cpp", "specfun.cpp", "refio.cpp"]
 
 LAUNCH = re.compile(r"(?P<kern>[A-Za-z_]\w*(?:<[^<>;(){}]*>)?)\s*<<<(?P<cfg>[^;]*?)>>>\s*\((?P<args>[^;]*?)\);")
 DYN = re.compile(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?(?P<type>[A-Za-z_][\w ]*?)\s+(?P<name>\w+)\[\];")
@@ -65,7 +69,9 @@ def rewrite(text: str) -> tuple[str, int]:
     return text, n
 
 
-def build(out_dir: Path, extra_flags=()) -> Path:
+def build(out_dir: Path, extra_flags=(), fibers: bool = True) -> Path:
+    """fibers: coroutine execution (fast; several CTAs at once).  False: one OS thread per CUDA thread, CTAs in
+    order -- the mode the sanitizers understand."""
     out_dir.mkdir(parents=True, exist_ok=True)
     cpps = []
     for name in SOURCES:
@@ -77,8 +83,9 @@ def build(out_dir: Path, extra_flags=()) -> Path:
     # -Bsymbolic: the library's own calls bind to ITSELF even when the real libconselgpu.so (same symbol names) is
     # already loaded into the process with global visibility (libconselhost.so pulls it in that way)
     cmd = ["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-pthread", "-ffp-contract=off", "-DCGPU_EMU", "-w", "-Wl,-Bsymbolic",
-           f"-I{EMU / 'shim'}", f"-I{EMU}", f"-I{CSRC}", f"-I{ROOT / 'include'}", *extra_flags, "-o", str(lib),
-           *map(str, cpps), str(EMU / "emu_stubs.cpp"), str(CSRC / "gf2_mt.cpp")]
+           *(["-DCGPU_EMU_FIBERS"] if fibers else []),
+           f"-I{EMU / 'shim'}", f"-I{EMU}", f"-I{CSRC}", f"-I{ROOT / 'include'}", f"-I{HOST}", *extra_flags, "-o", str(lib),
+           *map(str, cpps), str(EMU / "emu_stubs.cpp"), str(CSRC / "gf2_mt.cpp"), *[str(HOST / h) for h in HOST_SOURCES]]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("emulated library failed to build:\n" + r.stderr[-6000:])

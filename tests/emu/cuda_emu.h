@@ -11,6 +11,15 @@
 // Because every access is a real memory access of a real thread, ThreadSanitizer sees a missing
 // barrier or an unsynchronised shared-memory update as a data race.
 //
+// Two execution modes, chosen at compile time:
+//   default            one OS thread per CUDA thread, CTAs one after another (what the sanitizers see)
+//   -DCGPU_EMU_FIBERS  the threads of a CTA are coroutines (ucontext) of ONE OS thread that switch at barriers
+//                      and warp collectives; several CTAs run at once on the host's cores.  ~50x faster: for
+//                      end-to-end runs of the emulated library.  `__shared__` arrays are then thread_local
+//                      statics (per OS thread = per CTA).
+// A thread that returns from the kernel counts as arrived at every later barrier (as on the GPU) in fiber mode;
+// the OS-thread mode requires all threads of a CTA (warp) to reach every barrier (collective).
+//
 // Supported: what consel_b200/csrc/{hist_bucket.cuh,philox.cuh,stats_kernels.cu,resample_kernels.cu} use.  Warp-collectives must be
 // called by all 32 lanes of a warp (as CUDA requires with a full mask).
 #pragma once
@@ -18,6 +27,12 @@
 #include <stdlib.h>
 #include <string.h>
 
+#ifdef CGPU_EMU_FIBERS
+#include <sys/mman.h>
+#include <ucontext.h>
+
+#include <atomic>
+#endif
 #include <algorithm>
 #include <condition_variable>
 #include <functional>
@@ -38,6 +53,7 @@ struct alignas(16) double2 {
 static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{x, y, z, w}; }
 
 namespace emu {
+#ifndef CGPU_EMU_FIBERS
 class Barrier {  // reusable barrier (mutex + condition variable: visible to ThreadSanitizer)
   public:
     explicit Barrier(int n) : n_(n) {}
@@ -52,6 +68,8 @@ class Barrier {  // reusable barrier (mutex + condition variable: visible to Thr
             cv_.wait(lk, [&] { return gen_ != gen; });
         }
     }
+    void reset(int n) { n_ = n; count_ = 0; }
+    void drop() {}
 
   private:
     std::mutex mu_;
@@ -59,6 +77,34 @@ class Barrier {  // reusable barrier (mutex + condition variable: visible to Thr
     int n_, count_ = 0;
     unsigned gen_ = 0;
 };
+#else
+void yield();  // switch to the next runnable coroutine of this CTA
+class Barrier {  // all participants are coroutines of one OS thread: plain counters
+  public:
+    explicit Barrier(int n) : n_(n) {}
+    void wait() {
+        const unsigned gen = gen_;
+        if (++count_ >= n_) {
+            count_ = 0;
+            gen_++;
+        } else {
+            while (gen_ == gen) yield();
+        }
+    }
+    void reset(int n) { n_ = n; count_ = 0; }
+    void drop() {  // a participant returned from the kernel: it counts as arrived from now on
+        n_--;
+        if (n_ > 0 && count_ >= n_) {
+            count_ = 0;
+            gen_++;
+        }
+    }
+
+  private:
+    int n_, count_ = 0;
+    unsigned gen_ = 0;
+};
+#endif
 struct Warp {
     Barrier bar{32};
     unsigned long long mail[32];
@@ -84,7 +130,11 @@ inline thread_local dim3 threadIdx, blockIdx, blockDim, gridDim;
 #define __restrict__
 #define __launch_bounds__(...)
 #define __align__(x) __attribute__((aligned(x)))
+#ifdef CGPU_EMU_FIBERS
+#define __shared__ static thread_local
+#else
 #define __shared__ static
+#endif
 #define CGPU_DYN_SMEM(T, name) T *name = reinterpret_cast<T *>(emu::dyn_smem())
 
 static inline void __syncthreads() { emu::t_cta->bar->wait(); }
@@ -178,6 +228,125 @@ static inline T __ldg(const T *p) { return *p; }
 using std::max;
 using std::min;
 
+#ifdef CGPU_EMU_FIBERS
+namespace emu {
+struct Fiber {
+    ucontext_t ctx;
+    bool done = false;
+};
+struct Worker {  // one OS thread: runs CTAs one at a time, the CTA's threads as coroutines
+    ucontext_t sched;
+    std::vector<Fiber> fibers;
+    std::vector<void *> stacks;
+    int cur = 0;
+    const std::function<void()> *body = nullptr;
+};
+inline thread_local Worker *t_worker = nullptr;
+inline void yield() {
+    Worker *w = t_worker;
+    swapcontext(&w->fibers[w->cur].ctx, &w->sched);
+}
+inline void fiber_entry() {
+    Worker *w = t_worker;
+    (*w->body)();
+    Fiber &f = w->fibers[w->cur];
+    f.done = true;
+    t_cta->bar->drop();
+    t_cta->warps[t_warp]->bar.drop();
+    // returns to the scheduler through uc_link
+}
+constexpr size_t kFiberStack = 256 * 1024;
+// coroutine stacks are recycled across launches (a launch needs workers x threads of them)
+inline std::mutex g_stack_mu;
+inline std::vector<void *> g_stack_pool;
+inline void *stack_get() {
+    {
+        std::lock_guard<std::mutex> lk(g_stack_mu);
+        if (!g_stack_pool.empty()) {
+            void *p = g_stack_pool.back();
+            g_stack_pool.pop_back();
+            return p;
+        }
+    }
+    return mmap(nullptr, kFiberStack, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_STACK, -1, 0);
+}
+inline void stack_put(void *p) {
+    std::lock_guard<std::mutex> lk(g_stack_mu);
+    g_stack_pool.push_back(p);
+}
+
+template <class K, class... A>
+void launch(dim3 grid, dim3 block, size_t smem, K kernel, A... args) {
+    const int nthreads = (int)(block.x * block.y * block.z);
+    const int nwarps = (nthreads + 31) / 32;
+    const long long nctas = (long long)grid.x * grid.y * grid.z;
+    if (nctas <= 0 || nthreads <= 0) return;
+    const std::function<void()> body = [&] { kernel(args...); };
+    std::atomic<long long> next{0};
+    const int nworkers = (int)std::min<long long>(nctas, std::max(1u, std::thread::hardware_concurrency()));
+    auto work = [&] {
+        Worker wk;
+        wk.body = &body;
+        wk.fibers.resize(nthreads);
+        wk.stacks.resize(nthreads);
+        for (int t = 0; t < nthreads; t++)
+            wk.stacks[t] = stack_get();
+        t_worker = &wk;
+        Cta cta;
+        Barrier bar(nthreads);
+        cta.bar = &bar;
+        for (int w = 0; w < nwarps; w++) cta.warps.push_back(new Warp(std::min(32, nthreads - 32 * w)));
+        unsigned char *dynbuf = static_cast<unsigned char *>(aligned_alloc(16, std::max<size_t>(16, (smem + 15) / 16 * 16)));
+        cta.dyn = dynbuf;
+        t_cta = &cta;
+        blockDim = block;
+        gridDim = grid;
+        for (;;) {
+            const long long c = next.fetch_add(1);
+            if (c >= nctas) break;
+            blockIdx = dim3((unsigned)(c % grid.x), (unsigned)((c / grid.x) % grid.y), (unsigned)(c / ((long long)grid.x * grid.y)));
+            bar.reset(nthreads);
+            for (int w = 0; w < nwarps; w++) cta.warps[w]->bar.reset(cta.warps[w]->lanes);
+            for (int t = 0; t < nthreads; t++) {
+                Fiber &f = wk.fibers[t];
+                f.done = false;
+                getcontext(&f.ctx);
+                f.ctx.uc_stack.ss_sp = wk.stacks[t];
+                f.ctx.uc_stack.ss_size = kFiberStack;
+                f.ctx.uc_link = &wk.sched;
+                makecontext(&f.ctx, fiber_entry, 0);
+            }
+            int alive = nthreads;
+            while (alive > 0) {
+                alive = 0;
+                for (int t = 0; t < nthreads; t++) {
+                    Fiber &f = wk.fibers[t];
+                    if (f.done) continue;
+                    wk.cur = t;
+                    t_lane = t & 31;
+                    t_warp = t >> 5;
+                    threadIdx = dim3((unsigned)t % block.x, ((unsigned)t / block.x) % block.y, (unsigned)t / (block.x * block.y));
+                    swapcontext(&wk.sched, &f.ctx);
+                    if (!f.done) alive++;
+                }
+            }
+        }
+        for (Warp *w : cta.warps) delete w;
+        free(dynbuf);
+        for (int t = 0; t < nthreads; t++) stack_put(wk.stacks[t]);
+        t_worker = nullptr;
+        t_cta = nullptr;
+    };
+    if (nworkers == 1) {
+        std::thread(work).join();  // a fresh OS thread: the caller's thread-locals stay untouched
+    } else {
+        std::vector<std::thread> th;
+        for (int i = 0; i < nworkers; i++) th.emplace_back(work);
+        for (auto &t : th) t.join();
+    }
+}
+}  // namespace emu
+#else
 namespace emu {
 // launch<<<grid, block, smem>>>: CTAs in order (x fastest), the block's threads persist over the CTAs
 template <class K, class... A>
@@ -213,3 +382,4 @@ void launch(dim3 grid, dim3 block, size_t smem, K kernel, A... args) {
     free(dynbuf);
 }
 }  // namespace emu
+#endif  // CGPU_EMU_FIBERS

@@ -62,4 +62,8 @@ int cgpu_comm_info(int *rank, int *world) {
     return CGPU_OK;
 }
 void cgpu_comm_destroy(void) {}
+int cgpu_comm_allgather_host(const void *send, void *recv, long long bytes) {
+    if (send != recv && bytes > 0) memmove(recv, send, (size_t)bytes);
+    return CGPU_OK;
+}
 }

@@ -29,14 +29,16 @@ def cg(tmp_path_factory):
     lib.cgpu_last_error.restype = C.c_char_p
     lib.cgpu_launch_count.restype = C.c_longlong
     lib.cgpu_smooth_count.restype = C.c_double
-    saved = api._lib
-    api._lib = lib  # the binding now talks to the emulated library
+    from consel_b200 import pipeline
+    saved, saved_host = api._lib, pipeline._host
+    api._lib = lib       # the binding now talks to the emulated library ...
+    pipeline._host = lib  # ... which also carries the native pipeline / AU driver (libconselhost's sources)
     try:
         cg.init()
         cg.set_shard(0, 1)
         yield cg
     finally:
-        api._lib = saved
+        api._lib, pipeline._host = saved, saved_host
 
 
 def _ordered(orc, datvec, ass=None):
@@ -109,3 +111,23 @@ def test_gpu_only_paths_are_refused_not_emulated(cg):
     L = -np.ones((3, 64))
     with pytest.raises(cg.CgpuError):
         cg.scaleboot_all(L, [32], [4], 1)  # MT19937 stream + contraction: device only
+
+
+@pytest.mark.parametrize("name", ["tiny", "g100"])
+def test_consel_half_end_to_end_reproduces_the_reference_pv(cg, orc, gold, name):
+    """foo.rmt -> p-value table through the product's own code path on the CPU: replicate blocks uploaded,
+    KH/SH/wKH/wSH tests, statistics, BP, the lockstep AU driver with its count queries and fits
+    (chost_consel_run), compared with the files the unmodified reference wrote (tests/golden): items and
+    counts exactly, every p-value, standard error and fit diagnostic to the nine printed digits."""
+    from consel_b200 import pipeline
+    ref_pv = orc.read_pv(gold / f"{name}.pv")
+    rmt = orc.read_rmt(gold / f"{name}.rmt")
+    reps = cg.Reps.upload(rmt["reps"])
+    res = pipeline.consel(reps, rmt["datvec"], rmt["rr"], rmt["bb"])
+    reps.free()
+    assert np.array_equal(res["item"], ref_pv["item"])
+    assert np.allclose(res["stat"], ref_pv["stat"], rtol=6e-9)
+    assert np.allclose(res["pv"], ref_pv["pv"], rtol=6e-9, atol=1e-12), (res["pv"], ref_pv["pv"])
+    assert np.allclose(res["se"], ref_pv["se"], rtol=6e-9, atol=1e-12)
+    assert np.allclose(res["ax"], ref_pv["ax"], rtol=6e-9, atol=1e-12)
+    assert np.array_equal(res["cnt"], orc.read_cnt(gold / f"{name}.cnt")["cnt"])
