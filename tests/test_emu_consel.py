@@ -5,40 +5,13 @@ CUDA sources of the statistics / count-query / KH-SH kernels and of the histogra
 `-m gpu` tests do on the device -- so the kernel arithmetic and the host glue of capi_stats.cu are pinned
 even where no GPU is available.  (The MT19937 stream and the contractions need the GPU: the emulated
 library refuses them with CGPU_ENODEV.)"""
-import ctypes as C
-import shutil
-import sys
-from pathlib import Path
-
 import numpy as np
 import pytest
 
-ROOT = Path(__file__).resolve().parent.parent
-sys.path.insert(0, str(ROOT / "tests" / "emu"))
-
 
 @pytest.fixture(scope="module")
-def cg(tmp_path_factory):
-    if shutil.which("g++") is None:
-        pytest.skip("g++ not available")
-    import build_emu_lib
-
-    import consel_b200 as cg
-    from consel_b200 import api
-    lib = C.CDLL(str(build_emu_lib.build(tmp_path_factory.mktemp("emulib"))))
-    lib.cgpu_last_error.restype = C.c_char_p
-    lib.cgpu_launch_count.restype = C.c_longlong
-    lib.cgpu_smooth_count.restype = C.c_double
-    from consel_b200 import pipeline
-    saved, saved_host = api._lib, pipeline._host
-    api._lib = lib       # the binding now talks to the emulated library ...
-    pipeline._host = lib  # ... which also carries the native pipeline / AU driver (libconselhost's sources)
-    try:
-        cg.init()
-        cg.set_shard(0, 1)
-        yield cg
-    finally:
-        api._lib, pipeline._host = saved, saved_host
+def cg(emu_cg):
+    return emu_cg
 
 
 def _ordered(orc, datvec, ass=None):
