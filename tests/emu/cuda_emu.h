@@ -29,7 +29,9 @@
 
 #ifdef CGPU_EMU_FIBERS
 #include <sys/mman.h>
+#if !defined(__x86_64__) || defined(CGPU_EMU_UCONTEXT)
 #include <ucontext.h>
+#endif
 
 #include <atomic>
 #endif
@@ -229,13 +231,48 @@ using std::max;
 using std::min;
 
 #ifdef CGPU_EMU_FIBERS
+// ---- coroutine switch.  x86-64: a dozen instructions (callee-saved registers + stack pointer); elsewhere
+// ucontext (whose swapcontext makes two signal-mask system calls per switch: ~50x slower).
+#if defined(__x86_64__) && !defined(CGPU_EMU_UCONTEXT)
+#define CGPU_EMU_ASM_SWITCH 1
+extern "C" void cgpu_emu_switch(void **save_sp, void *load_sp);
+__asm__(
+    ".text\n"
+    ".weak cgpu_emu_switch\n"
+    ".type cgpu_emu_switch,@function\n"
+    "cgpu_emu_switch:\n"
+    "    pushq %rbp\n"
+    "    pushq %rbx\n"
+    "    pushq %r12\n"
+    "    pushq %r13\n"
+    "    pushq %r14\n"
+    "    pushq %r15\n"
+    "    movq %rsp, (%rdi)\n"
+    "    movq %rsi, %rsp\n"
+    "    popq %r15\n"
+    "    popq %r14\n"
+    "    popq %r13\n"
+    "    popq %r12\n"
+    "    popq %rbx\n"
+    "    popq %rbp\n"
+    "    ret\n"
+    ".size cgpu_emu_switch,.-cgpu_emu_switch\n");
+#endif
 namespace emu {
 struct Fiber {
+#ifdef CGPU_EMU_ASM_SWITCH
+    void *sp = nullptr;
+#else
     ucontext_t ctx;
+#endif
     bool done = false;
 };
 struct Worker {  // one OS thread: runs CTAs one at a time, the CTA's threads as coroutines
+#ifdef CGPU_EMU_ASM_SWITCH
+    void *sched_sp = nullptr;
+#else
     ucontext_t sched;
+#endif
     std::vector<Fiber> fibers;
     std::vector<void *> stacks;
     int cur = 0;
@@ -244,7 +281,11 @@ struct Worker {  // one OS thread: runs CTAs one at a time, the CTA's threads as
 inline thread_local Worker *t_worker = nullptr;
 inline void yield() {
     Worker *w = t_worker;
+#ifdef CGPU_EMU_ASM_SWITCH
+    cgpu_emu_switch(&w->fibers[w->cur].sp, w->sched_sp);
+#else
     swapcontext(&w->fibers[w->cur].ctx, &w->sched);
+#endif
 }
 inline void fiber_entry() {
     Worker *w = t_worker;
@@ -253,26 +294,31 @@ inline void fiber_entry() {
     f.done = true;
     t_cta->bar->drop();
     t_cta->warps[t_warp]->bar.drop();
-    // returns to the scheduler through uc_link
+#ifdef CGPU_EMU_ASM_SWITCH
+    cgpu_emu_switch(&f.sp, w->sched_sp);  // never resumed
+    __builtin_trap();
+#endif
+    // (ucontext: returns to the scheduler through uc_link)
 }
 constexpr size_t kFiberStack = 256 * 1024;
 // coroutine stacks are recycled across launches (a launch needs workers x threads of them)
 inline std::mutex g_stack_mu;
 inline std::vector<void *> g_stack_pool;
-inline void *stack_get() {
+inline void stack_get_many(std::vector<void *> &out) {
+    size_t have = 0;
     {
         std::lock_guard<std::mutex> lk(g_stack_mu);
-        if (!g_stack_pool.empty()) {
-            void *p = g_stack_pool.back();
+        while (have < out.size() && !g_stack_pool.empty()) {
+            out[have++] = g_stack_pool.back();
             g_stack_pool.pop_back();
-            return p;
         }
     }
-    return mmap(nullptr, kFiberStack, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_STACK, -1, 0);
+    for (; have < out.size(); have++)
+        out[have] = mmap(nullptr, kFiberStack, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS | MAP_STACK, -1, 0);
 }
-inline void stack_put(void *p) {
+inline void stack_put_many(const std::vector<void *> &v) {
     std::lock_guard<std::mutex> lk(g_stack_mu);
-    g_stack_pool.push_back(p);
+    g_stack_pool.insert(g_stack_pool.end(), v.begin(), v.end());
 }
 
 template <class K, class... A>
@@ -289,8 +335,7 @@ void launch(dim3 grid, dim3 block, size_t smem, K kernel, A... args) {
         wk.body = &body;
         wk.fibers.resize(nthreads);
         wk.stacks.resize(nthreads);
-        for (int t = 0; t < nthreads; t++)
-            wk.stacks[t] = stack_get();
+        stack_get_many(wk.stacks);
         t_worker = &wk;
         Cta cta;
         Barrier bar(nthreads);
@@ -310,11 +355,22 @@ void launch(dim3 grid, dim3 block, size_t smem, K kernel, A... args) {
             for (int t = 0; t < nthreads; t++) {
                 Fiber &f = wk.fibers[t];
                 f.done = false;
+#ifdef CGPU_EMU_ASM_SWITCH
+                // initial frame: six zeroed callee-saved registers, then the entry point as return address; after the
+                // `ret` the stack pointer is 8 mod 16, as at any function entry
+                uintptr_t top = (reinterpret_cast<uintptr_t>(wk.stacks[t]) + kFiberStack) & ~(uintptr_t)15;
+                void **frame = reinterpret_cast<void **>(top - 64);
+                for (int i = 0; i < 6; i++) frame[i] = nullptr;
+                frame[6] = reinterpret_cast<void *>(&fiber_entry);
+                frame[7] = nullptr;
+                f.sp = frame;
+#else
                 getcontext(&f.ctx);
                 f.ctx.uc_stack.ss_sp = wk.stacks[t];
                 f.ctx.uc_stack.ss_size = kFiberStack;
                 f.ctx.uc_link = &wk.sched;
                 makecontext(&f.ctx, fiber_entry, 0);
+#endif
             }
             int alive = nthreads;
             while (alive > 0) {
@@ -326,14 +382,18 @@ void launch(dim3 grid, dim3 block, size_t smem, K kernel, A... args) {
                     t_lane = t & 31;
                     t_warp = t >> 5;
                     threadIdx = dim3((unsigned)t % block.x, ((unsigned)t / block.x) % block.y, (unsigned)t / (block.x * block.y));
+#ifdef CGPU_EMU_ASM_SWITCH
+                    cgpu_emu_switch(&wk.sched_sp, f.sp);
+#else
                     swapcontext(&wk.sched, &f.ctx);
+#endif
                     if (!f.done) alive++;
                 }
             }
         }
         for (Warp *w : cta.warps) delete w;
         free(dynbuf);
-        for (int t = 0; t < nthreads; t++) stack_put(wk.stacks[t]);
+        stack_put_many(wk.stacks);
         t_worker = nullptr;
         t_cta = nullptr;
     };
