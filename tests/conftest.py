@@ -36,7 +36,9 @@ def emu_lib(tmp_path_factory):
         pytest.skip("g++ not available")
     sys.path.insert(0, str(ROOT / "tests" / "emu"))
     import build_emu_lib
-    lib = C.CDLL(str(build_emu_lib.build(tmp_path_factory.mktemp("emulib"))))
+    path = build_emu_lib.build(tmp_path_factory.mktemp("emulib"))
+    lib = C.CDLL(str(path))
+    lib._path = path
     lib.cgpu_last_error.restype = C.c_char_p
     lib.cgpu_launch_count.restype = C.c_longlong
     lib.cgpu_smooth_count.restype = C.c_double
@@ -57,3 +59,24 @@ def emu_cg(emu_lib):
         yield cg
     finally:
         api._lib, pipeline._host = saved, saved_host
+
+
+@pytest.fixture(scope="session")
+def emu_bin(emu_lib):
+    """a bin/ directory whose `consel` is the product's host program (consel_b200/host/consel.cpp + pipeline,
+    AU driver, fit, readers: the sources of the real binary) linked against the EMULATED device library;
+    catpv / makermt are the real binaries (catpv never touches the device, makermt only for its argument errors)"""
+    import subprocess
+    host = ROOT / "consel_b200" / "host"
+    out = emu_lib._path.parent / "bin"
+    out.mkdir(exist_ok=True)
+    srcs = ["consel.cpp", "pipeline.cpp", "audriver.cpp", "aufit.cpp", "specfun.cpp", "refio.cpp"]
+    cmd = ["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-pthread", "-w", "-o", str(out / "consel"), *[str(host / f) for f in srcs],
+           f"-L{emu_lib._path.parent}", "-lconselgpu_emu", f"-Wl,-rpath,{emu_lib._path.parent}", "-lm"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    for prog in ("catpv", "makermt"):
+        dst = out / prog
+        if not dst.exists():
+            dst.symlink_to(ROOT / "consel_b200" / "bin" / prog)
+    return out

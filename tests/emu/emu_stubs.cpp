@@ -62,6 +62,10 @@ int cgpu_comm_info(int *rank, int *world) {
     return CGPU_OK;
 }
 void cgpu_comm_destroy(void) {}
+int cgpu_comm_init_env(void) {  // single rank: what the real entry point does when WORLD_SIZE <= 1
+    if (int rc = cgpu::ensure_init()) return rc;
+    return cgpu_set_shard(0, 1);
+}
 int cgpu_comm_allgather_host(const void *send, void *recv, long long bytes) {
     if (send != recv && bytes > 0) memmove(recv, send, (size_t)bytes);
     return CGPU_OK;

@@ -26,7 +26,7 @@ def _build(tmp: Path, name: str, extra) -> Path:
 def exe(tmp_path_factory):
     if shutil.which("g++") is None:
         pytest.skip("g++ not available")
-    return _build(tmp_path_factory.mktemp("emu"), "emu_hist_bucket", [])
+    return _build(tmp_path_factory.mktemp("emu"), "emu_hist_bucket", ["-DCGPU_EMU_FIBERS"])  # coroutine mode: fast
 
 
 CASES = [
@@ -35,7 +35,11 @@ CASES = [
     (150000, 120000, 2, 1, 16, 0),
     (40000, 30001, 2, 0, 8, 0),      # 157 buckets (C4 has 153), ragged last tile
     (40000, 30001, 2, 1, 8, 0),
-    (262144, 9000, 1, 0, 8, 0),      # 1024 buckets (the most a replicate may have), sparse
+    (200000, 70001, 3, 0, 8, 0),     # 782 buckets
+    (200000, 70001, 3, 1, 8, 0),
+    (262144, 9000, 3, 0, 8, 0),      # 1024 buckets (the most a replicate may have), sparse
+    (1000000, 1400000, 2, 0, 16, 0), # 16 buckets of 65536 sites, 171 tiles per replicate (a C4 row in small)
+    (1000000, 1400000, 2, 1, 16, 0),
     (1000, 5, 2, 0, 8, 0),           # fewer draws than threads
     (1000, 5, 2, 1, 8, 0),
     (70000, 8192, 1, 0, 16, 0),      # exactly one tile
