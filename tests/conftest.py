@@ -63,19 +63,26 @@ def emu_cg(emu_lib):
 
 @pytest.fixture(scope="session")
 def emu_bin(emu_lib):
-    """a bin/ directory whose `consel` is the product's host program (consel_b200/host/consel.cpp + pipeline,
-    AU driver, fit, readers: the sources of the real binary) linked against the EMULATED device library;
-    catpv / makermt are the real binaries (catpv never touches the device, makermt only for its argument errors)"""
+    """a bin/ directory whose makermt / makerep / consel are the product's host programs (the sources of the real
+    binaries) linked against the EMULATED device library"""
     import subprocess
     host = ROOT / "consel_b200" / "host"
     out = emu_lib._path.parent / "bin"
     out.mkdir(exist_ok=True)
-    srcs = ["consel.cpp", "pipeline.cpp", "audriver.cpp", "aufit.cpp", "specfun.cpp", "refio.cpp"]
-    cmd = ["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-pthread", "-w", "-o", str(out / "consel"), *[str(host / f) for f in srcs],
-           f"-L{emu_lib._path.parent}", "-lconselgpu_emu", f"-Wl,-rpath,{emu_lib._path.parent}", "-lm"]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    assert r.returncode == 0, r.stderr[-3000:]
-    for prog in ("catpv", "makermt"):
+    programs = {  # as consel_b200/host/Makefile links them, with the emulated library in place of libconselgpu.so
+        "consel": ["consel.cpp", "pipeline.cpp", "audriver.cpp", "aufit.cpp", "specfun.cpp", "refio.cpp"],
+        "makermt": ["makermt.cpp", "refio.cpp"],
+        "makerep": ["makerep.cpp", "refio.cpp"],
+    }
+    procs = []
+    for prog, srcs in programs.items():
+        cmd = ["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-pthread", "-w", "-o", str(out / prog), *[str(host / f) for f in srcs],
+               f"-L{emu_lib._path.parent}", "-lconselgpu_emu", f"-Wl,-rpath,{emu_lib._path.parent}", "-lm"]
+        procs.append((prog, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)))
+    for prog, p in procs:
+        _, err = p.communicate()
+        assert p.returncode == 0, f"{prog}: {err[-3000:]}"
+    for prog in ("catpv", "catrep", "catmt", "seqmt", "catci"):  # never touch the device: the real binaries
         dst = out / prog
         if not dst.exists():
             dst.symlink_to(ROOT / "consel_b200" / "bin" / prog)

@@ -1,18 +1,21 @@
-"""Builds libconselgpu_emu.so: the CONSEL-SIDE of libconselgpu.so -- the C ABI (capi.cu, capi_stats.cu), the
-statistics kernels (stats_kernels.cu) and the histogram kernels (resample_kernels.cu) -- compiled FOR THE
-CPU, so that the parity tests of the replicate statistics, the count queries, the KH/SH tests and the Philox
-resampler can run in the CPU test tier against the same oracle as on the GPU.  Test infrastructure only:
-the product library is built by nvcc from the very same files (consel_b200/csrc/Makefile), nothing of the
-product loads this one.
+"""Builds libconselgpu_emu.so: libconselgpu.so WITHOUT its tensor-core path -- the C ABI (capi.cu, capi_stats.cu),
+the MT19937 jump-ahead and draw kernels (mt_kernels.cu), the histogram kernels (resample_kernels.cu), the
+fp64 contractions with their mbarrier / bulk-copy pipeline (contract_kernels.cu), the statistics, count-query
+and KH/SH kernels (stats_kernels.cu) and the native pipeline / AU driver (consel_b200/host) -- compiled FOR
+THE CPU, so that the `-m gpu` parity tests of the strict (bit-exact) makermt path and of the whole consel side
+run in the CPU test tier against the same oracle and goldens as on the device.  Test infrastructure only: the
+product library is built by nvcc from the very same files (consel_b200/csrc/Makefile), nothing of the product
+loads this one, and the product still refuses to compute without an sm_100 device.
 
-How: the sources are taken as they are, with two mechanical rewrites --
+How: the sources are taken as they are, with mechanical rewrites --
     kernel<<<grid, block, smem, stream>>>(args);     ->  emu::launch(dim3(grid), dim3(block), smem, kernel, args);
     extern __shared__ [__align__(N)] T name[];       ->  T *name = reinterpret_cast<T *>(emu::dyn_smem());
+    three one-instruction inline-PTX statements of mt_kernels.cu -> the same instruction in C++ (PATCHES)
+    the mbarrier / cp.async.bulk helper block of contract_kernels.cu -> tests/emu/shim/mbarrier_emu.h (BLOCKS)
 -- and compiled by g++ against tests/emu/shim/cuda_runtime.h (host memory as device memory, synchronous
-streams) and tests/emu/cuda_emu.h (one OS thread per CUDA thread, real barriers, real atomics).  The
-translation units that need the tensor cores, TMA or inline PTX (mt_kernels, contract_kernels, i8_kernels,
-bench_kernels) and NCCL (comm) are replaced by emu_stubs.cpp, whose entry points fail with CGPU_ENODEV:
-the MT19937 / contraction paths stay GPU-only.
+streams) and tests/emu/cuda_emu.h (CUDA threads as coroutines or OS threads, real barriers, real atomics).
+What is NOT emulated: the tcgen05 / TMEM / TMA GEMM of the int8 mode (i8_kernels.cu), the peak-measurement
+kernels (bench_kernels.cu) and NCCL (comm.cu); emu_stubs.cpp answers for them (CGPU_ENODEV; one rank).
 """
 from __future__ import annotations
 
@@ -24,7 +27,22 @@ from pathlib import Path
 EMU = Path(__file__).resolve().parent
 ROOT = EMU.parent.parent
 CSRC = ROOT / "consel_b200" / "csrc"
-SOURCES = ["capi.cu", "capi_stats.cu", "stats_kernels.cu", "resample_kernels.cu"]
+SOURCES = ["capi.cu", "capi_stats.cu", "stats_kernels.cu", "resample_kernels.cu", "mt_kernels.cu", "contract_kernels.cu"]
+# Inline PTX cannot be compiled for the host: the few helper functions that contain it are replaced, by exact text,
+# with C++ statements of the same instruction (every patch must apply exactly once, or the build fails).
+PATCHES = {
+    "mt_kernels.cu": [
+        ('asm("mul.hi.u32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(pow2_32_minus_s));', "r = __umulhi(v, pow2_32_minus_s);"),
+        ('asm("lop3.b32 %0, %1, %2, 0x80000000, 0xe4;" : "=r"(y) : "r"(hi), "r"(lo));', "y = (hi & 0x80000000u) | (lo & 0x7fffffffu);"),
+        ('asm("mul.lo.u32 %0, %1, %2;" : "=r"(mag) : "r"(lo & 1u), "r"(k.mag));', "mag = (lo & 1u) * k.mag;"),
+    ],
+}
+# contract_kernels.cu: the block of mbarrier / cp.async.bulk helpers -> tests/emu/shim/mbarrier_emu.h
+BLOCKS = {
+    "contract_kernels.cu": ("// ------------------------------------------------------------------ PTX helpers",
+                            "// ------------------------------------------------------------------ L -> site-major tiles",
+                            '}  // namespace cgpu\n#include "mbarrier_emu.h"\nnamespace cgpu {\n'),
+}
 HOST = ROOT / "consel_b200" / "host"
 # the native makermt->consel pipeline and AU driver (libconselhost.so) go INTO the emulated library, so that their
 # cgpu_* calls bind to the emulated entry points whatever else the process has loaded
@@ -75,7 +93,17 @@ def build(out_dir: Path, extra_flags=(), fibers: bool = True) -> Path:
     out_dir.mkdir(parents=True, exist_ok=True)
     cpps = []
     for name in SOURCES:
-        text, n = rewrite((CSRC / name).read_text())
+        src = (CSRC / name).read_text()
+        for old, new in PATCHES.get(name, []):
+            if src.count(old) != 1:
+                raise ValueError(f"{name}: patch target not found exactly once: {old[:50]}")
+            src = src.replace(old, new)
+        if name in BLOCKS:
+            a, b, repl = BLOCKS[name]
+            if src.count(a) != 1 or src.count(b) != 1:
+                raise ValueError(f"{name}: block markers not found exactly once")
+            src = src[:src.index(a)] + repl + src[src.index(b):]
+        text, n = rewrite(src)
         dst = out_dir / (Path(name).stem + "_emu.cpp")
         dst.write_text(f'#line 1 "{CSRC / name}"\n' + text)
         cpps.append(dst)

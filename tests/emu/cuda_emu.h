@@ -52,6 +52,10 @@ struct alignas(16) uint4 {  // 16-byte aligned like CUDA's: -fsanitize=alignment
 struct alignas(16) double2 {
     double x, y;
 };
+struct alignas(16) double4 {
+    double x, y, z, w;
+};
+static inline double4 make_double4(double x, double y, double z, double w) { return double4{x, y, z, w}; }
 static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { return uint4{x, y, z, w}; }
 
 namespace emu {
@@ -195,6 +199,7 @@ static inline unsigned __match_any_sync(unsigned mask, unsigned v) {
 }
 static inline unsigned atomicAdd(unsigned *p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 static inline int atomicExch(int *p, int v) { return __atomic_exchange_n(p, v, __ATOMIC_RELAXED); }
+static inline unsigned atomicXor(unsigned *p, unsigned v) { return __atomic_fetch_xor(p, v, __ATOMIC_RELAXED); }
 static inline int atomicAdd(int *p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 static inline unsigned long long atomicAdd(unsigned long long *p, unsigned long long v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
 static inline unsigned atomicExch(unsigned *p, unsigned v) { return __atomic_exchange_n(p, v, __ATOMIC_RELAXED); }
@@ -207,6 +212,8 @@ static inline double __dsqrt_rn(double a) { return __builtin_sqrt(a); }
 static inline double __fma_rn(double a, double b, double c) { return __builtin_fma(a, b, c); }
 static inline long long __double_as_longlong(double x) { long long r; memcpy(&r, &x, 8); return r; }
 static inline double __longlong_as_double(long long x) { double r; memcpy(&r, &x, 8); return r; }
+static inline double __uint2double_rn(unsigned x) { return (double)x; }
+static inline size_t __cvta_generic_to_shared(const void *p) { return reinterpret_cast<size_t>(p); }
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 static inline int __ffs(int x) { return __builtin_ffs(x); }
 static inline unsigned __byte_perm(unsigned a, unsigned b, unsigned sel) {
@@ -341,7 +348,7 @@ void launch(dim3 grid, dim3 block, size_t smem, K kernel, A... args) {
         Barrier bar(nthreads);
         cta.bar = &bar;
         for (int w = 0; w < nwarps; w++) cta.warps.push_back(new Warp(std::min(32, nthreads - 32 * w)));
-        unsigned char *dynbuf = static_cast<unsigned char *>(aligned_alloc(16, std::max<size_t>(16, (smem + 15) / 16 * 16)));
+        unsigned char *dynbuf = static_cast<unsigned char *>(aligned_alloc(128, std::max<size_t>(128, (smem + 127) / 128 * 128)));
         cta.dyn = dynbuf;
         t_cta = &cta;
         blockDim = block;
@@ -418,7 +425,7 @@ void launch(dim3 grid, dim3 block, size_t smem, K kernel, A... args) {
     cta.bar = &bar;
     for (int w = 0; w < nwarps; w++) cta.warps.push_back(new Warp(std::min(32, nthreads - 32 * w)));
     // exactly `smem` bytes, 16-byte aligned like the hardware's window: AddressSanitizer sees an overrun
-    unsigned char *dynbuf = static_cast<unsigned char *>(aligned_alloc(16, std::max<size_t>(16, (smem + 15) / 16 * 16)));
+    unsigned char *dynbuf = static_cast<unsigned char *>(aligned_alloc(128, std::max<size_t>(128, (smem + 127) / 128 * 128)));
     cta.dyn = dynbuf;
     std::vector<std::thread> th;
     for (int t = 0; t < nthreads; t++)

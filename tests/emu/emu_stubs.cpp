@@ -1,35 +1,20 @@
 // Entry points of the translation units that are NOT part of the emulated library (see
-// build_emu_lib.py): the MT19937 stream, the contractions and the tensor-core path need the GPU and
-// fail with CGPU_ENODEV here; the communicator degenerates to a single rank.
+// build_emu_lib.py): the tcgen05 tensor-core path (i8_kernels.cu) needs the GPU and fails with
+// CGPU_ENODEV here; the communicator (comm.cu, NCCL) degenerates to a single rank.
 #include <string.h>
 
 #include "cgpu_internal.h"
 
 namespace cgpu {
 static int gpu_only(const char *what) {
-    set_error(CGPU_ENODEV, "%s needs the GPU (emulated library: statistics, count queries, KH/SH tests and the Philox histogram only)", what);
+    set_error(CGPU_ENODEV, "%s needs the GPU (the emulated library has everything but the tensor-core path)", what);
     return CGPU_ENODEV;
 }
 int fx_prepare(DevMatrix &, cudaStream_t, bool) { return gpu_only("fx_prepare"); }
 bool fx_needs_partial(const DevMatrix &, int, int) { return false; }
-int launch_contract(const DevMatrix &, const unsigned long long *, int, double, double *, int, int, int, cudaStream_t) { return gpu_only("contract_kernel"); }
 int launch_contract_i8(const DevMatrix &, const unsigned char *, int, int, int *, double, double *, int, int, cudaStream_t, PhaseTimer *, int) {
     return gpu_only("the tcgen05 GEMM");
 }
-int launch_transpose_L(const double *, int, int, int, int, double *, int *, cudaStream_t) { return gpu_only("transpose_L"); }
-int mt_poly_positions(const Gf2Poly *, uint32_t *) { return 0; }
-int launch_mt_jump(uint32_t *, const int2 *, const uint32_t *, int, int, cudaStream_t) { return gpu_only("mt_jump_kernel"); }
-bool mt_draw_hist_fits(int) { return false; }
-int launch_mt_draw(const MtPlan &, const DrawPlan &, uint32_t, void *, cudaStream_t) { return gpu_only("mt_draw_kernel"); }
-int launch_mt_draw_hist(const MtPlan &, const DrawPlan &, const unsigned int *, unsigned char *const *, int, uint32_t, int *, cudaStream_t) {
-    return gpu_only("mt_draw_hist_kernel");
-}
-int launch_mt_draw_range(const MtPlan &, unsigned long long, unsigned long long, uint32_t, void *, cudaStream_t) { return gpu_only("mt_draw_kernel"); }
-int make_draw_plan(int, const unsigned long long *, const unsigned long long *, const unsigned long long *, unsigned long long,
-                   unsigned long long, DrawPlan *) {
-    return gpu_only("the MT19937 draw plan");
-}
-int resolve_draw_slots(const MtPlan &, DrawPlan *) { return gpu_only("the MT19937 draw plan"); }
 
 int comm_world() { return 1; }
 int comm_rank() { return 0; }

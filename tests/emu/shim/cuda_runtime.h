@@ -6,6 +6,9 @@
 #pragma once
 #include <math.h>
 
+#include <cmath>
+using std::isfinite;
+
 #include <chrono>
 #include <cstdlib>
 #include <cstring>

@@ -1,10 +1,8 @@
-"""The `consel` COMMAND LINE on the CPU: the host program's own sources linked against the emulated device
-library (conftest.emu_bin), run on the reference's golden inputs and compared with the files the unmodified
-reference wrote -- `.rep` / `.cnt` byte for byte, `.pv` / `.ci` to the printed digits, `catpv` text equal.
-The consel-only tests of tests/test_gpu_cli.py run unchanged (edge associations, -R rep mode, -f rescaling,
---quick_mctest, --pdm, the error protocol); makermt needs the GPU (MT19937 stream + contraction) and is not
-part of this tier."""
-import shutil
+"""The makermt / makerep / consel COMMAND LINES on the CPU: the host programs' own sources linked against the
+emulated device library (conftest.emu_bin), run on the reference's inputs and compared with the files the
+unmodified reference wrote -- `.rmt` / `.vt` / `.rep` / `.cnt` byte for byte, `.pv` / `.ci` to the printed
+digits, `catpv` text equal -- and against a fresh run of the compiled reference.  These are the tests of
+tests/test_gpu_cli.py, unchanged; the four that use the int8 tensor-core mode stay GPU-only."""
 import sys
 from pathlib import Path
 
@@ -14,25 +12,13 @@ sys.path.insert(0, str(Path(__file__).resolve().parent))
 
 import test_gpu_cli as _cli  # noqa: E402
 
-for _name in ("test_consel_with_edge_associations", "test_consel_rep_mode", "test_consel_rescaling_approximation",
-              "test_quick_mctest", "test_pdm_aic_correction", "test_cli_error_protocol"):
-    globals()[_name] = getattr(_cli, _name)
+GPU_ONLY = {"test_makerep_matches_reference", "test_in_process_pipeline_matches_reference_pv", "test_makermt_extension_flags",
+            "test_full_size_mam15_pipeline_and_philox_within_monte_carlo_error"}  # end with / consist of --sum int8 runs
+for _name in dir(_cli):
+    if _name.startswith("test_") and _name not in GPU_ONLY:
+        globals()[_name] = getattr(_cli, _name)
 
 
 @pytest.fixture(autouse=True)
-def _emulated_programs(emu_bin, monkeypatch):
+def _emulated_programs(emu_bin, emu_cg, monkeypatch):
     monkeypatch.setattr(_cli, "BIN", emu_bin)
-
-
-@pytest.mark.parametrize("case", ["g100", "tiny"])
-def test_consel_catpv_on_the_reference_rmt(case, gold, orc, tmp_path):
-    """the consel -> catpv half of tests/test_gpu_cli.py::test_makermt_consel_catpv_pipeline, from the .rmt the
-    reference's makermt wrote"""
-    shutil.copy(gold / f"{case}.rmt", tmp_path / f"{case}.rmt")
-    out = _cli.run("consel", ["-r", "-c", case], tmp_path)
-    assert "# exit normally" in out
-    assert (tmp_path / f"{case}.rep").read_bytes() == (gold / f"{case}.rep").read_bytes()
-    assert (tmp_path / f"{case}.cnt").read_bytes() == (gold / f"{case}.cnt").read_bytes()
-    for ext in ("pv", "ci"):
-        _cli.same_numbers(tmp_path / f"{case}.{ext}", gold / f"{case}.{ext}", orc)
-    assert _cli.run("catpv", [case], tmp_path) == (gold / f"{case}.txt").read_text()

@@ -1,10 +1,18 @@
 """`-m gpu` parity tests run UNCHANGED against the emulated build of the product library
 (tests/emu/build_emu_lib.py), i.e. on the CPU: the same assertions, the same goldens, the same C ABI --
-only the `cg` fixture differs.  All of tests/test_gpu_consel.py (statistics and .rep payloads, count queries
-vs .cnt files and cntdist smoothing, order statistics, KH/SH/wKH/wSH vs oracle and .pv, BP, mixed
-associations, input validation, row-range queries, uploaded statistics, rescaled statistics) and the tests
-of the other GPU modules that need neither the MT19937 stream nor a contraction (those stay GPU-only:
-tensor cores, TMA and inline PTX are not emulated)."""
+only the `cg` fixture differs.
+
+  tests/test_gpu_makermt.py  all of it: the device MT19937 stream (incl. jumps of 3e9 and 2^33 draws), site counts
+                             on every histogram path, `.rmt` payloads bit-equal to the reference's (tiny, 1 % and
+                             FULL-SIZE mam15: the md5 of SURVEY Appendix C), the strict contraction over all tree
+                             tiles, the fast mode's tolerance, NaN/inf propagation, stream offsets, sharding, Philox
+  tests/test_gpu_consel.py   all of it: statistics and .rep payloads, count queries vs .cnt files and cntdist
+                             smoothing, order statistics, KH/SH/wKH/wSH vs oracle and .pv, BP, mixed associations,
+                             input validation, row-range queries, uploaded statistics, rescaled statistics
+  tests/test_gpu_shapes.py   the tests that do not need the int8 mode
+
+The tcgen05 tensor-core path (CGPU_SUM_INT8) is not emulated: tests/test_gpu_i8.py and the int8 shape tests stay
+GPU-only."""
 import sys
 from pathlib import Path
 
@@ -17,14 +25,12 @@ import test_gpu_makermt as _makermt  # noqa: E402
 import test_gpu_shapes as _shapes  # noqa: E402
 
 # re-collected here without the source modules' `gpu` mark
-for _name in dir(_consel):
-    if _name.startswith("test_"):
-        globals()[_name] = getattr(_consel, _name)
-for _mod, _names in ((_makermt, ("test_philox_mode_is_a_valid_multinomial", "test_bad_arguments_fail_loudly")),
-                     (_shapes, ("test_philox_stream_offset_gives_independent_replicates",
-                                "test_more_than_32_scales_row_range_query"))):
-    for _name in _names:
-        globals()[_name] = getattr(_mod, _name)
+for _mod in (_consel, _makermt):
+    for _name in dir(_mod):
+        if _name.startswith("test_"):
+            globals()[_name] = getattr(_mod, _name)
+for _name in ("test_philox_stream_offset_gives_independent_replicates", "test_more_than_32_scales_row_range_query"):
+    globals()[_name] = getattr(_shapes, _name)
 
 
 @pytest.fixture(scope="module")
