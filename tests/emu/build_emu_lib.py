@@ -55,9 +55,9 @@ DYN = re.compile(r"extern\s+__shared__\s+(?:__align__\(\d+\)\s+)?(?P<type>[A-Za-
 def split_top(s: str) -> list[str]:
     out, depth, cur = [], 0, ""
     for ch in s:
-        if ch in "(<[":
-            depth += 1
-        elif ch in ")>]":
+        if ch in "([{":  # (angle brackets are not tracked: `1 << 16` is a shift; a template argument list with a
+            depth += 1   #  comma inside a launch configuration would yield more than four parts and be refused)
+        elif ch in ")]}":
             depth -= 1
         if ch == "," and depth == 0:
             out.append(cur.strip())

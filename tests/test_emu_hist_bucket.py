@@ -85,3 +85,28 @@ def test_bucket_kernels_stay_in_bounds_and_aligned(tmp_path):
         r = subprocess.run([str(exe), *map(str, case)], capture_output=True, text=True, timeout=900)
         assert r.returncode == 0, r.stdout + r.stderr
         assert "runtime error" not in r.stderr and "AddressSanitizer" not in r.stderr and " 0 mismatches" in r.stdout
+
+
+@pytest.mark.parametrize("case", [
+    # n, draws per replicate, replicates, source, hist_bucket option (0 = default kernels: the test's own control)
+    (300000, 200001, 3, 0, 1), (300000, 200001, 3, 1, 1),    # above 225280 sites: the opt-in takes over from global atomics
+    (300000, 200001, 3, 0, 0), (300000, 200001, 3, 1, 0),
+    (100000, 140000, 9, 0, 2), (100000, 140000, 9, 1, 2),    # forced below that (tests): instead of hist_wide_kernel
+    (100000, 140000, 9, 0, 0),
+    (70000, 3, 2, 0, 2),                                     # fewer draws than threads
+], ids=lambda c: "n%d_bn%d_nb%d_src%d_opt%d" % c)
+def test_library_histogram_launchers_byte_rows(emu_lib, tmp_path_factory, case):
+    """the library's own launchers (hist_bucket_launch behind cgpu_set_option("hist_bucket", ...)) inside the
+    emulated library: workspace sizes, table offsets, grids, launch order"""
+    exe = emu_lib._path.parent / "emu_hist_rows"
+    if not exe.exists():
+        cmd = ["g++", "-O1", "-g", "-std=c++17", "-pthread", "-DCGPU_EMU", "-DCGPU_EMU_FIBERS", "-w", f"-I{EMU / 'shim'}", f"-I{EMU}",
+               f"-I{CSRC}", f"-I{ROOT / 'include'}", "-o", str(exe), str(EMU / "emu_hist_rows.cpp"), f"-L{emu_lib._path.parent}",
+               "-lconselgpu_emu", f"-Wl,-rpath,{emu_lib._path.parent}"]
+        subprocess.run(cmd, check=True, capture_output=True, text=True)
+    r = subprocess.run([str(exe), *map(str, case)], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert " 0 mismatches, err=0" in r.stdout
+    launches = int(r.stdout.split(",")[-1].split()[0])
+    if case[4] in (1, 2):
+        assert launches == 4  # count, scan, scatter, histogram
