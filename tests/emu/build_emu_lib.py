@@ -15,7 +15,8 @@ How: the sources are taken as they are, with mechanical rewrites --
 -- and compiled by g++ against tests/emu/shim/cuda_runtime.h (host memory as device memory, synchronous
 streams) and tests/emu/cuda_emu.h (CUDA threads as coroutines or OS threads, real barriers, real atomics).
 What is NOT emulated: the tcgen05 / TMEM / TMA GEMM of the int8 mode (i8_kernels.cu), the peak-measurement
-kernels (bench_kernels.cu) and NCCL (comm.cu); emu_stubs.cpp answers for them (CGPU_ENODEV; one rank).
+kernels (bench_kernels.cu); emu_stubs.cpp answers for them (CGPU_ENODEV).  comm.cu is compiled as it is; the
+libnccl.so.2 it binds at run time is tests/emu/fake_nccl.cpp (collectives between processes over shared memory).
 """
 from __future__ import annotations
 
@@ -27,7 +28,7 @@ from pathlib import Path
 EMU = Path(__file__).resolve().parent
 ROOT = EMU.parent.parent
 CSRC = ROOT / "consel_b200" / "csrc"
-SOURCES = ["capi.cu", "capi_stats.cu", "stats_kernels.cu", "resample_kernels.cu", "mt_kernels.cu", "contract_kernels.cu"]
+SOURCES = ["capi.cu", "capi_stats.cu", "stats_kernels.cu", "resample_kernels.cu", "mt_kernels.cu", "contract_kernels.cu", "comm.cu"]
 # Inline PTX cannot be compiled for the host: the few helper functions that contain it are replaced, by exact text,
 # with C++ statements of the same instruction (every patch must apply exactly once, or the build fails).
 PATCHES = {
@@ -117,6 +118,11 @@ def build(out_dir: Path, extra_flags=(), fibers: bool = True) -> Path:
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("emulated library failed to build:\n" + r.stderr[-6000:])
+    # the libnccl.so.2 that comm.cu dlopens in a multi-rank run: collectives between processes over shared memory
+    r = subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-pthread", f"-I{EMU}", "-o", str(out_dir / "libnccl.so.2"),
+                        str(EMU / "fake_nccl.cpp"), "-lrt"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("stand-in NCCL failed to build:\n" + r.stderr[-3000:])
     return lib
 
 

@@ -84,7 +84,8 @@ class Barrier {  // reusable barrier (mutex + condition variable: visible to Thr
     unsigned gen_ = 0;
 };
 #else
-void yield();  // switch to the next runnable coroutine of this CTA
+void yield();              // back to the CTA's scheduler (next runnable coroutine of the CTA)
+void yield_in_warp(int w);  // straight to the next live lane of warp w: a warp collective costs 32 switches, not a CTA round
 class Barrier {  // all participants are coroutines of one OS thread: plain counters
   public:
     explicit Barrier(int n) : n_(n) {}
@@ -93,10 +94,13 @@ class Barrier {  // all participants are coroutines of one OS thread: plain coun
         if (++count_ >= n_) {
             count_ = 0;
             gen_++;
+        } else if (warp_ >= 0) {
+            while (gen_ == gen) yield_in_warp(warp_);
         } else {
             while (gen_ == gen) yield();
         }
     }
+    void set_warp(int w) { warp_ = w; }
     void reset(int n) { n_ = n; count_ = 0; }
     void drop() {  // a participant returned from the kernel: it counts as arrived from now on
         n_--;
@@ -107,13 +111,17 @@ class Barrier {  // all participants are coroutines of one OS thread: plain coun
     }
 
   private:
-    int n_, count_ = 0;
+    int n_, count_ = 0, warp_ = -1;
     unsigned gen_ = 0;
 };
 #endif
 struct Warp {
     Barrier bar{32};
-    unsigned long long mail[32];
+    // mailboxes of the warp collectives, double buffered: collective k uses buffer k & 1, so ONE barrier per
+    // collective suffices (a lane can be at most one collective ahead of the slowest lane of its warp: it cannot
+    // pass barrier k+1 before every lane has read buffer k & 1 and arrived there)
+    unsigned long long mail[2][32];
+    unsigned seq[32] = {0};
     int lanes;
     explicit Warp(int n) : bar(n), lanes(n) {}
 };
@@ -145,14 +153,13 @@ inline thread_local dim3 threadIdx, blockIdx, blockDim, gridDim;
 
 static inline void __syncthreads() { emu::t_cta->bar->wait(); }
 static inline void __syncwarp(unsigned = 0xffffffffu) { emu::t_cta->warps[emu::t_warp]->bar.wait(); }
-// warp collectives: every lane deposits 64 bits in the warp's mailbox, barrier, read, barrier
+// warp collectives: every lane deposits 64 bits in the warp's mailbox, barrier, read
 static inline unsigned long long emu_exchange64(unsigned long long v, int src_lane) {
     emu::Warp *w = emu::t_cta->warps[emu::t_warp];
-    w->mail[emu::t_lane] = v;
+    const unsigned k = w->seq[emu::t_lane]++ & 1u;
+    w->mail[k][emu::t_lane] = v;
     w->bar.wait();
-    const unsigned long long r = w->mail[src_lane & 31];
-    w->bar.wait();
-    return r;
+    return w->mail[k][src_lane & 31];
 }
 template <class T>
 static inline T emu_shfl(T v, int src_lane) {
@@ -174,11 +181,11 @@ template <class T>
 static inline T __shfl_sync(unsigned, T v, int lane) { return emu_shfl(v, lane); }
 static inline unsigned __ballot_sync(unsigned, int pred) {
     emu::Warp *w = emu::t_cta->warps[emu::t_warp];
-    w->mail[emu::t_lane] = pred ? 1ull : 0ull;
+    const unsigned k = w->seq[emu::t_lane]++ & 1u;
+    w->mail[k][emu::t_lane] = pred ? 1ull : 0ull;
     w->bar.wait();
     unsigned m = 0;
-    for (int l = 0; l < w->lanes; l++) m |= (unsigned)w->mail[l] << l;
-    w->bar.wait();
+    for (int l = 0; l < w->lanes; l++) m |= (unsigned)w->mail[k][l] << l;
     return m;
 }
 static inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0; }
@@ -189,12 +196,12 @@ static inline int __all_sync(unsigned mask, int pred) {
 // take part in the mailbox exchange, so this emulation requires a full warp to call it -- as the kernels do)
 static inline unsigned __match_any_sync(unsigned mask, unsigned v) {
     emu::Warp *w = emu::t_cta->warps[emu::t_warp];
-    w->mail[emu::t_lane] = v;
+    const unsigned k = w->seq[emu::t_lane]++ & 1u;
+    w->mail[k][emu::t_lane] = v;
     w->bar.wait();
     unsigned m = 0;
     for (int l = 0; l < w->lanes; l++)
-        if (((mask >> l) & 1u) && (unsigned)w->mail[l] == v) m |= 1u << l;
-    w->bar.wait();
+        if (((mask >> l) & 1u) && (unsigned)w->mail[k][l] == v) m |= 1u << l;
     return m;
 }
 static inline unsigned atomicAdd(unsigned *p, unsigned v) { return __atomic_fetch_add(p, v, __ATOMIC_RELAXED); }
@@ -294,6 +301,39 @@ inline void yield() {
     swapcontext(&w->fibers[w->cur].ctx, &w->sched);
 #endif
 }
+struct WorkerDims {
+    dim3 block;
+    int nthreads = 0;
+};
+inline thread_local WorkerDims t_dims;
+inline void become(int t) {  // the identity of coroutine t in the thread-locals the kernels read
+    t_worker->cur = t;
+    t_lane = t & 31;
+    t_warp = t >> 5;
+    const dim3 &b = t_dims.block;
+    threadIdx = dim3((unsigned)t % b.x, ((unsigned)t / b.x) % b.y, (unsigned)t / (b.x * b.y));
+}
+inline void yield_in_warp(int wp) {
+    Worker *w = t_worker;
+    const int me = w->cur, base = wp * 32, lanes = std::min(32, t_dims.nthreads - base);
+    for (int d = 1; d < lanes; d++) {
+        const int t = base + ((me - base) + d) % lanes;
+        if (w->fibers[t].done) continue;
+#ifdef CGPU_EMU_ASM_SWITCH
+        if (!w->fibers[t].sp) continue;
+        become(t);
+        cgpu_emu_switch(&w->fibers[me].sp, w->fibers[t].sp);
+        become(me);  // (whoever switched back to us restored nothing: re-assert our identity)
+        return;
+#else
+        become(t);
+        swapcontext(&w->fibers[me].ctx, &w->fibers[t].ctx);
+        become(me);
+        return;
+#endif
+    }
+    yield();  // no other live lane in this warp
+}
 inline void fiber_entry() {
     Worker *w = t_worker;
     (*w->body)();
@@ -347,10 +387,15 @@ void launch(dim3 grid, dim3 block, size_t smem, K kernel, A... args) {
         Cta cta;
         Barrier bar(nthreads);
         cta.bar = &bar;
-        for (int w = 0; w < nwarps; w++) cta.warps.push_back(new Warp(std::min(32, nthreads - 32 * w)));
+        for (int w = 0; w < nwarps; w++) {
+            cta.warps.push_back(new Warp(std::min(32, nthreads - 32 * w)));
+            cta.warps.back()->bar.set_warp(w);
+        }
         unsigned char *dynbuf = static_cast<unsigned char *>(aligned_alloc(128, std::max<size_t>(128, (smem + 127) / 128 * 128)));
         cta.dyn = dynbuf;
         t_cta = &cta;
+        t_dims.block = block;
+        t_dims.nthreads = nthreads;
         blockDim = block;
         gridDim = grid;
         for (;;) {
@@ -358,7 +403,10 @@ void launch(dim3 grid, dim3 block, size_t smem, K kernel, A... args) {
             if (c >= nctas) break;
             blockIdx = dim3((unsigned)(c % grid.x), (unsigned)((c / grid.x) % grid.y), (unsigned)(c / ((long long)grid.x * grid.y)));
             bar.reset(nthreads);
-            for (int w = 0; w < nwarps; w++) cta.warps[w]->bar.reset(cta.warps[w]->lanes);
+            for (int w = 0; w < nwarps; w++) {
+                cta.warps[w]->bar.reset(cta.warps[w]->lanes);
+                memset(cta.warps[w]->seq, 0, sizeof(cta.warps[w]->seq));
+            }
             for (int t = 0; t < nthreads; t++) {
                 Fiber &f = wk.fibers[t];
                 f.done = false;
@@ -385,10 +433,7 @@ void launch(dim3 grid, dim3 block, size_t smem, K kernel, A... args) {
                 for (int t = 0; t < nthreads; t++) {
                     Fiber &f = wk.fibers[t];
                     if (f.done) continue;
-                    wk.cur = t;
-                    t_lane = t & 31;
-                    t_warp = t >> 5;
-                    threadIdx = dim3((unsigned)t % block.x, ((unsigned)t / block.x) % block.y, (unsigned)t / (block.x * block.y));
+                    become(t);
 #ifdef CGPU_EMU_ASM_SWITCH
                     cgpu_emu_switch(&wk.sched_sp, f.sp);
 #else
@@ -440,6 +485,7 @@ void launch(dim3 grid, dim3 block, size_t smem, K kernel, A... args) {
                 for (unsigned by = 0; by < grid.y; by++)
                     for (unsigned bx = 0; bx < grid.x; bx++) {
                         blockIdx = dim3(bx, by, bz);
+                        cta.warps[t_warp]->seq[t_lane] = 0;
                         kernel(args...);
                         bar.wait();  // the next CTA reuses the shared memory
                     }

@@ -1,0 +1,60 @@
+"""The N>1 path of the PRODUCT on the CPU: world_size 2 and 3, one process per rank, each running the emulated
+library (tests/emu/build_emu_lib.py) with the real comm.cu over a stand-in NCCL (tests/emu/fake_nccl.cpp:
+collectives between processes through shared memory).  What a one-process-per-GPU job does is done here
+unchanged: cgpu_comm_init_env with its TCP rendezvous, MT19937 jump-ahead to the rank's own replicate columns,
+the split row sums with their all-gather, cgpu_reps_gather_scale, the KH/SH tests split over items
+(cgpu_mctest_rows), the collective count queries of the lockstep AU driver (cgpu_count_query_dist: all-gather of
+thresholds, grouped reduce-scatter of count / max / min), the final all-gather of the per-item results.  Every
+rank must return the table the single-process run returns, bit for bit (tests/test_gpu_dist.py checks the same
+on two real GPUs)."""
+import os
+import socket
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _run_ranks(lib_path: Path, out: Path, world: int, mode: str):
+    env = dict(os.environ)
+    env.update(WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(_free_port()), CHOST_THREADS="2",
+               LD_LIBRARY_PATH=f"{lib_path.parent}:{env.get('LD_LIBRARY_PATH', '')}")
+    env.pop("LOCAL_RANK", None)
+    procs = []
+    for rank in range(world):
+        e = dict(env, RANK=str(rank))
+        procs.append(subprocess.Popen([sys.executable, str(ROOT / "tests" / "emu" / "dist_worker.py"), str(lib_path), str(out), mode],
+                                      env=e, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    logs = []
+    for p in procs:
+        try:
+            log, _ = p.communicate(timeout=600)
+        except subprocess.TimeoutExpired:
+            for q in procs:
+                q.kill()
+            raise
+        logs.append(log)
+    for rank, p in enumerate(procs):
+        assert p.returncode == 0, f"rank {rank}:\n{logs[rank][-3000:]}"
+    return [np.load(f"{out}.{rank}.npz") for rank in range(world)]
+
+
+@pytest.mark.parametrize("world,mode", [(2, "identity"), (3, "identity"), (2, "edges")])
+def test_sharded_pipeline_equals_single_process_bit_for_bit(emu_lib, tmp_path, world, mode):
+    one = _run_ranks(emu_lib._path, tmp_path / "one", 1, mode)[0]
+    many = _run_ranks(emu_lib._path, tmp_path / "many", world, mode)
+    assert int(one["world"]) == 1
+    for rank, got in enumerate(many):
+        assert (int(got["rank"]), int(got["world"])) == (rank, world)
+        for key in ("item", "stat", "pv", "se", "cnt", "ax", "ci", "ret", "datvec"):
+            assert np.array_equal(got[key], one[key], equal_nan=True), (rank, key)
