@@ -58,3 +58,36 @@ def test_sharded_pipeline_equals_single_process_bit_for_bit(emu_lib, tmp_path, w
         assert (int(got["rank"]), int(got["world"])) == (rank, world)
         for key in ("item", "stat", "pv", "se", "cnt", "ax", "ci", "ret", "datvec"):
             assert np.array_equal(got[key], one[key], equal_nan=True), (rank, key)
+
+
+def test_makermt_and_consel_programs_as_two_ranks(emu_lib, emu_bin, gold, tmp_path):
+    """the command-line programs as one process per rank (RANK / WORLD_SIZE / MASTER_PORT, no launcher framework):
+    .rmt/.vt/.pv/.ci/.cnt byte-equal to the single-process run of the same programs -- what
+    tests/test_gpu_dist.py::test_makermt_and_consel_programs_on_two_gpus checks on two GPUs"""
+    import shutil
+    for d in ("one", "two"):
+        (tmp_path / d).mkdir()
+        shutil.copy(gold / "mam15.lnf", tmp_path / d / "mam15.lnf")
+
+    def run(prog, args, cwd, world):
+        procs = []
+        port = _free_port()
+        for r in range(world):
+            env = dict(os.environ, LD_LIBRARY_PATH=f"{emu_lib._path.parent}:{os.environ.get('LD_LIBRARY_PATH', '')}", CHOST_THREADS="2")
+            for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+                env.pop(k, None)
+            if world > 1:
+                env.update(RANK=str(r), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+            procs.append(subprocess.Popen([str(emu_bin / prog)] + args, cwd=cwd, env=env, stdout=subprocess.PIPE, text=True))
+        outs = [p.communicate(timeout=600)[0] for p in procs]
+        assert all(p.returncode == 0 for p in procs), outs
+        return outs
+
+    for d, world in (("one", 1), ("two", 2)):
+        run("makermt", ["-s", "1234", "-b", "0.05", "--paml", "mam15", "x"], tmp_path / d, world)
+        outs = run("consel", ["-c", "x"], tmp_path / d, world)
+        if world > 1:
+            assert outs[1] == ""  # rank 0 speaks for the job
+    for ext in ("rmt", "vt", "pv", "ci", "cnt"):
+        a, b = (tmp_path / "one" / f"x.{ext}").read_bytes(), (tmp_path / "two" / f"x.{ext}").read_bytes()
+        assert a == b, ext

@@ -10,6 +10,7 @@ only the `cg` fixture differs.
                              smoothing, order statistics, KH/SH/wKH/wSH vs oracle and .pv, BP, mixed associations,
                              input validation, row-range queries, uploaded statistics, rescaled statistics
   tests/test_gpu_shapes.py   the tests that do not need the int8 mode
+  tests/test_gpu_dist.py     the single-rank behaviour of the collective entry points
 
 The tcgen05 tensor-core path (CGPU_SUM_INT8) is not emulated: tests/test_gpu_i8.py and the int8 shape tests stay
 GPU-only."""
@@ -21,6 +22,7 @@ import pytest
 sys.path.insert(0, str(Path(__file__).resolve().parent))
 
 import test_gpu_consel as _consel  # noqa: E402
+import test_gpu_dist as _dist  # noqa: E402
 import test_gpu_makermt as _makermt  # noqa: E402
 import test_gpu_shapes as _shapes  # noqa: E402
 
@@ -31,6 +33,9 @@ for _mod in (_consel, _makermt):
             globals()[_name] = getattr(_mod, _name)
 for _name in ("test_philox_stream_offset_gives_independent_replicates", "test_more_than_32_scales_row_range_query"):
     globals()[_name] = getattr(_shapes, _name)
+# the single-rank behaviour of the collective entry points (the multi-rank runs are tests/test_emu_dist.py)
+for _name in ("test_collective_entry_points_without_communicator", "test_mctest_item_ranges_compose"):
+    globals()[_name] = getattr(_dist, _name)
 
 
 @pytest.fixture(scope="module")
