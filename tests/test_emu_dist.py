@@ -20,9 +20,20 @@ ROOT = Path(__file__).resolve().parent.parent
 
 
 def _free_port():
-    with socket.socket() as s:
-        s.bind(("127.0.0.1", 0))
-        return s.getsockname()[1]
+    """a MASTER_PORT whose rendezvous port (MASTER_PORT + 17, consel_b200/csrc/comm.cu) is free as well"""
+    for _ in range(64):
+        with socket.socket() as s:
+            s.bind(("127.0.0.1", 0))
+            port = s.getsockname()[1]
+        if port + 17 > 65535:
+            continue
+        try:
+            with socket.socket() as t:
+                t.bind(("0.0.0.0", port + 17))
+            return port
+        except OSError:
+            continue
+    raise RuntimeError("no free port pair")
 
 
 def _run_ranks(lib_path: Path, out: Path, world: int, mode: str):
