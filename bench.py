@@ -294,29 +294,32 @@ def run_ours(args) -> None:
     # two replicates of scales 0 and 1 -- scale 1 starts bb[0]*bn[0] draws into the MT19937 stream)
     spot = None
     if rank == 0:
-        from oracle import oracle as orc
-        t0 = time.perf_counter()
-        ok_counts, ok_exact, worst_rel = True, True, 0.0
-        ktrees = np.unique(np.linspace(0, K - 1, 3).astype(int))
-        skip = 0
-        for s in (0, 1):
-            nrep = 2
-            y = orc.mt_stream(7, skip, nrep * int(bn[s]))
-            idx = orc.site_indices(y, N_SITES).reshape(nrep, int(bn[s]))
-            counts = np.stack([np.bincount(idx[b], minlength=N_SITES) for b in range(nrep)])
-            got = keep["reps"].download_cols(s, 0, nrep)
-            r_s = float(bn[s]) / float(N_SITES)
-            want = exact_sums(L[ktrees], counts, r_s)
-            ok_exact = ok_exact and bool(np.array_equal(got[ktrees], want))
-            seq = orc.contract_counts(L[ktrees], counts, r_s)  # the reference's sequentially rounded sums
-            worst_rel = max(worst_rel, float(np.max(np.abs(got[ktrees] - seq) / np.abs(seq))))
-            skip += int(bb[s]) * int(bn[s])
-            if skip > 3_000_000_000:
-                break
-        spot = {"ok": bool(ok_exact and worst_rel <= 1e-9), "bit_equal_to_exact_rounded_sums": ok_exact,
-                "max_rel_diff_to_reference_sequential_sums": worst_rel,
-                "what": f"replicates 0,1 of scales 0 and 1 of the LAST timed step, trees {ktrees.tolist()}: MT19937 draws and site "
-                        "indices by the oracle (oracle/oracle.c), exact sums by math.fsum", "seconds": time.perf_counter() - t0}
+        try:  # an auxiliary leg must never cost the run its headline line
+            from oracle import oracle as orc
+            t0 = time.perf_counter()
+            ok_counts, ok_exact, worst_rel = True, True, 0.0
+            ktrees = np.unique(np.linspace(0, K - 1, 3).astype(int))
+            skip = 0
+            for s in (0, 1):
+                nrep = 2
+                y = orc.mt_stream(7, skip, nrep * int(bn[s]))
+                idx = orc.site_indices(y, N_SITES).reshape(nrep, int(bn[s]))
+                counts = np.stack([np.bincount(idx[b], minlength=N_SITES) for b in range(nrep)])
+                got = keep["reps"].download_cols(s, 0, nrep)
+                r_s = float(bn[s]) / float(N_SITES)
+                want = exact_sums(L[ktrees], counts, r_s)
+                ok_exact = ok_exact and bool(np.array_equal(got[ktrees], want))
+                seq = orc.contract_counts(L[ktrees], counts, r_s)  # the reference's sequentially rounded sums
+                worst_rel = max(worst_rel, float(np.max(np.abs(got[ktrees] - seq) / np.abs(seq))))
+                skip += int(bb[s]) * int(bn[s])
+                if skip > 3_000_000_000:
+                    break
+            spot = {"ok": bool(ok_exact and worst_rel <= 1e-9), "bit_equal_to_exact_rounded_sums": ok_exact,
+                    "max_rel_diff_to_reference_sequential_sums": worst_rel,
+                    "what": f"replicates 0,1 of scales 0 and 1 of the LAST timed step, trees {ktrees.tolist()}: MT19937 draws and site "
+                            "indices by the oracle (oracle/oracle.c), exact sums by math.fsum", "seconds": time.perf_counter() - t0}
+        except Exception as e:
+            spot = {"ok": False, "error": f"{type(e).__name__}: {e}"}
     keep.pop("reps").free()
 
     modes = {}
@@ -329,9 +332,12 @@ def run_ours(args) -> None:
     for mname, rm, sm in side:
         is_fp64 = sm != cg.SUM_INT8
         st_ = 1 if (heavy and is_fp64) else max(1, min(args.steps, 3))
-        d, w_, ph = timed_steps(rm, sm, st_, 1 if (heavy and is_fp64) else 2)
-        modes[mname] = {"ms_per_step": d / st_, "value": acc_per_step_total * st_ / (d * 1e-3), "steps": st_,
-                        "phases_ms_per_step": ph}
+        try:
+            d, w_, ph = timed_steps(rm, sm, st_, 1 if (heavy and is_fp64) else 2)
+            modes[mname] = {"ms_per_step": d / st_, "value": acc_per_step_total * st_ / (d * 1e-3), "steps": st_,
+                            "phases_ms_per_step": ph}
+        except Exception as e:  # side lines: the headline must still be printed
+            modes[mname] = {"error": f"{type(e).__name__}: {e}"}
 
     # pinned host copy of L (the host-buffer arms below read it)
     Lh = torch.empty((K, N_SITES), dtype=torch.float64, pin_memory=True)
@@ -381,19 +387,24 @@ def run_ours(args) -> None:
     h2d = int(L.nbytes)
     d2h = int(K * (b1 - b0) * 8 * len(RR))
     e2e_steps = max(1, min(args.steps, 3))
-    cg.scaleboot_all(Lh.numpy(), bn, bb, 7, sum_mode=cg.SUM_INT8, out=outs)  # warm-up (page-locks, pool growth)
+    e2e_error = None
     e2e_ms = 0.0
-    checksum = 0.0
-    for step in range(e2e_steps):
-        flush.fill_(step & 0xFF)
+    try:
+        cg.scaleboot_all(Lh.numpy(), bn, bb, 7, sum_mode=cg.SUM_INT8, out=outs)  # warm-up (page-locks, pool growth)
+        checksum = 0.0
+        for step in range(e2e_steps):
+            flush.fill_(step & 0xFF)
+            barrier()
+            t0 = time.perf_counter()
+            cg.scaleboot_all(Lh.numpy(), bn, bb, 7, sum_mode=cg.SUM_INT8, out=outs)
+            checksum = float(outs[0][0, 0])  # the step's result is read on the host
+            e2e_ms += (time.perf_counter() - t0) * 1e3
         barrier()
-        t0 = time.perf_counter()
-        cg.scaleboot_all(Lh.numpy(), bn, bb, 7, sum_mode=cg.SUM_INT8, out=outs)
-        checksum = float(outs[0][0, 0])  # the step's result is read on the host
-        e2e_ms += (time.perf_counter() - t0) * 1e3
-    barrier()
-    e2e_ms = max_over_ranks(e2e_ms)
-    assert np.isfinite(checksum)
+        e2e_ms = max_over_ranks(e2e_ms)
+        if not np.isfinite(checksum):
+            e2e_error = "the host-buffer call returned a non-finite replicate sum"
+    except Exception as e:  # the headline line must still be printed
+        e2e_error = f"{type(e).__name__}: {e}"
     if world > 1:
         # every collective of the run is behind us: all ranks tear the communicators down TOGETHER (NCCL's
         # destroy waits for its peers); rank 0 then finishes the report alone
@@ -404,7 +415,10 @@ def run_ours(args) -> None:
         return
 
     # ---- rooflines, measured live: every kernel of the step with its own bound
-    live.update({k_: v for k_, v in cg.bench_peaks(sustained_seconds=2.0).items() if k_ == "int8_tops_sustained"})
+    try:
+        live.update({k_: v for k_, v in cg.bench_peaks(sustained_seconds=2.0).items() if k_ == "int8_tops_sustained"})
+    except Exception:
+        live["int8_tops_sustained"] = live["int8_tops"]
     peaks = {}
     try:
         peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
@@ -541,13 +555,16 @@ def run_ours(args) -> None:
     roofline["kernels"] = kernels
 
     # ---- CPU baseline: the oracle port, single thread, bounded sample (~10-20 s)
-    from oracle import oracle as orc
-    b_cpu = max(1, int(2.4e10 / (K * N_SITES * len(RR))))
-    t0 = time.perf_counter()
-    orc.makermt(L, bn, [b_cpu] * len(RR), 7)
-    t_cpu = time.perf_counter() - t0
-    cpu_baseline = {"value": K * N_SITES * b_cpu * len(RR) / t_cpu, "unit": UNIT, "cores": 1, "kind": "port",
-                    "sample": f"same matrix and scales, {b_cpu} replicates per scale ({t_cpu:.1f} s of oracle/oracle.c)"}
+    try:
+        from oracle import oracle as orc
+        b_cpu = max(1, int(2.4e10 / (K * N_SITES * len(RR))))
+        t0 = time.perf_counter()
+        orc.makermt(L, bn, [b_cpu] * len(RR), 7)
+        t_cpu = time.perf_counter() - t0
+        cpu_baseline = {"value": K * N_SITES * b_cpu * len(RR) / t_cpu, "unit": UNIT, "cores": 1, "kind": "port",
+                        "sample": f"same matrix and scales, {b_cpu} replicates per scale ({t_cpu:.1f} s of oracle/oracle.c)"}
+    except Exception as e:
+        cpu_baseline = {"error": f"{type(e).__name__}: {e}", "unit": UNIT, "cores": 1, "kind": "port"}
 
     line = {
         "metric": METRIC, "value": acc_per_step_total * args.steps / (dev_ms * 1e-3), "unit": UNIT,
@@ -556,9 +573,10 @@ def run_ours(args) -> None:
         "config": config_json(name, c, world),
         "timing": "CUDA events on the library stream, first to last event of each step, max over ranks",
         "wall_ms_per_step": wall_ms / args.steps, "phases_ms_per_step": phases,
-        "e2e": {"value": acc_per_step_total * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-                "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
-                "api": "cgpu_scaleboot_all(CGPU_RNG_MT19937, CGPU_SUM_INT8): pinned host L in, this rank's pinned host replicate blocks out"},
+        "e2e": ({"error": e2e_error, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h} if e2e_error else
+                {"value": acc_per_step_total * e2e_steps / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                 "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps,
+                 "api": "cgpu_scaleboot_all(CGPU_RNG_MT19937, CGPU_SUM_INT8): pinned host L in, this rank's pinned host replicate blocks out"}),
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
         "spot_check": spot, "modes": modes, "pipeline": pipe,
     }

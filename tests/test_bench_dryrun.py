@@ -164,3 +164,61 @@ def test_reference_arm_non_zero_ranks_do_nothing(monkeypatch, capsys):
     monkeypatch.setenv("WORLD_SIZE", "8")
     bench.run_reference(types.SimpleNamespace(gpus=8, steps=1, warmup=0, impl="reference", config="C3"))
     assert capsys.readouterr().out == ""
+
+
+def test_auxiliary_legs_cannot_cost_the_headline_line(monkeypatch, capsys, orc):
+    """side modes, the host-buffer arm, the sustained-peak measurement and the CPU baseline fail: the line is still
+    printed, with the headline value and the failures named"""
+    import torch
+
+    import consel_b200 as cg
+    from consel_b200 import pipeline
+    monkeypatch.setattr(torch.cuda, "set_device", lambda d: None)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a: None)
+    monkeypatch.setattr(torch.cuda, "get_device_properties", lambda d: types.SimpleNamespace(multi_processor_count=148))
+    real_empty = torch.empty
+
+    def empty(*a, **kw):
+        kw.pop("device", None)
+        kw.pop("pin_memory", None)
+        return real_empty(*a, **kw)
+    monkeypatch.setattr(torch, "empty", empty)
+    timing = dict(upload=0.0, rng=0.6, resample=0.4, contract=0.0, download=0.0, total=2.0, gemm_i8=0.9, fx_combine=0.0,
+                  mt_jump=0.2, mt_draw=0.4, n_gemm=10.0, n_hist=10.0)
+
+    class Mat(_Matrix):
+        def scaleboot(self, bn, bb, seed, stream_offset=0, rng_mode=0, sum_mode=0):
+            if (rng_mode, sum_mode) != (cg.RNG_MT19937, cg.SUM_INT8):
+                raise cg.CgpuError(-3, "side mode broke")
+            return super().scaleboot(bn, bb, seed, stream_offset, rng_mode, sum_mode)
+
+    def peaks(sustained_seconds=0.0):
+        if sustained_seconds > 0:
+            raise cg.CgpuError(-3, "no sustained peak")
+        return dict(int8_tops=4500.0, fp64_tflops=33.0)
+
+    def boom(*a, **k):
+        raise cg.CgpuError(-3, "host-buffer call broke")
+    monkeypatch.setattr(cg, "init", lambda d=-1: None)
+    monkeypatch.setattr(cg, "set_shard", lambda r, w: None)
+    monkeypatch.setattr(cg, "shard_range", lambda b: (0, int(b)))
+    monkeypatch.setattr(cg, "bench_peaks", peaks)
+    monkeypatch.setattr(cg, "Matrix", lambda L: Mat(L, orc))
+    monkeypatch.setattr(cg, "last_timing", lambda: dict(timing))
+    monkeypatch.setattr(cg, "launch_count", lambda: 31)
+    monkeypatch.setattr(cg, "set_option", lambda k, v: None)
+    monkeypatch.setattr(cg, "kernel_times", lambda: {})
+    monkeypatch.setattr(cg, "scaleboot_all", boom)
+    monkeypatch.setattr(pipeline, "run", boom)
+    monkeypatch.setattr(bench, "ClockSampler", lambda idx: types.SimpleNamespace(start=lambda: None, stop=lambda: None))
+    monkeypatch.setattr(orc, "makermt", boom)
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
+        monkeypatch.delenv(k, raising=False)
+    bench.run_ours(types.SimpleNamespace(gpus=1, steps=2, warmup=3, impl="ours", config="C1"))
+    lines = [t for t in capsys.readouterr().out.splitlines() if t.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["value"] == pytest.approx(15 * 3414 * 1e5 / 2.0e-3) and d["spot_check"]["ok"] is True
+    assert "error" in d["e2e"] and "error" in d["cpu_baseline"] and "error" in d["pipeline"]
+    assert all("error" in m for m in d["modes"].values())
+    assert d["roofline"]["peak"] == 4500.0 and d["clocks"] is None
