@@ -28,7 +28,7 @@ from pathlib import Path
 EMU = Path(__file__).resolve().parent
 ROOT = EMU.parent.parent
 CSRC = ROOT / "consel_b200" / "csrc"
-SOURCES = ["capi.cu", "capi_stats.cu", "stats_kernels.cu", "resample_kernels.cu", "mt_kernels.cu", "contract_kernels.cu", "comm.cu"]
+SOURCES = ["capi.cu", "capi_stats.cu", "stats_kernels.cu", "resample_kernels.cu", "mt_kernels.cu", "contract_kernels.cu", "comm.cu", "i8_kernels.cu"]
 # Inline PTX cannot be compiled for the host: the few helper functions that contain it are replaced, by exact text,
 # with C++ statements of the same instruction (every patch must apply exactly once, or the build fails).
 PATCHES = {
@@ -39,10 +39,19 @@ PATCHES = {
     ],
 }
 # contract_kernels.cu: the block of mbarrier / cp.async.bulk helpers -> tests/emu/shim/mbarrier_emu.h
+# i8_kernels.cu: the tcgen05 / TMEM / TMA GEMM kernels with their tensor-map helpers are cut, and the launcher that
+# drives them is replaced by tests/emu/shim/i8_gemm_emu.h (a plain int32 matrix product IN PLACE OF THE MMA; the
+# fixed-point set-up, the pattern kernels and both recombinations stay the product's own code)
 BLOCKS = {
-    "contract_kernels.cu": ("// ------------------------------------------------------------------ PTX helpers",
-                            "// ------------------------------------------------------------------ L -> site-major tiles",
-                            '}  // namespace cgpu\n#include "mbarrier_emu.h"\nnamespace cgpu {\n'),
+    "contract_kernels.cu": [("// ------------------------------------------------------------------ PTX helpers",
+                             "// ------------------------------------------------------------------ L -> site-major tiles",
+                             '}  // namespace cgpu\n#include "mbarrier_emu.h"\nnamespace cgpu {\n')],
+    "i8_kernels.cu": [("// ------------------------------------------------------------------ tcgen05 GEMM tiles",
+                       "// ---- site patterns: identical columns of L",
+                       "constexpr int G8_BM = 128, G8_BN = 256, G8_BK = 128;\n"),
+                      ("// counts: plain rows [nb_pad][NP] uint8 (nb_pad multiple of 256, padding rows zero)",
+                       "}  // namespace cgpu",
+                       '#include <thread>\n#include "i8_gemm_emu.h"\n')],
 }
 HOST = ROOT / "consel_b200" / "host"
 # the native makermt->consel pipeline and AU driver (libconselhost.so) go INTO the emulated library, so that their
@@ -99,11 +108,11 @@ def build(out_dir: Path, extra_flags=(), fibers: bool = True) -> Path:
             if src.count(old) != 1:
                 raise ValueError(f"{name}: patch target not found exactly once: {old[:50]}")
             src = src.replace(old, new)
-        if name in BLOCKS:
-            a, b, repl = BLOCKS[name]
-            if src.count(a) != 1 or src.count(b) != 1:
-                raise ValueError(f"{name}: block markers not found exactly once")
-            src = src[:src.index(a)] + repl + src[src.index(b):]
+        for a, b, repl in BLOCKS.get(name, []):
+            if src.count(a) != 1 or src.count(b) < 1:
+                raise ValueError(f"{name}: block markers not found")
+            ia = src.index(a)
+            src = src[:ia] + repl + src[src.index(b, ia):]
         text, n = rewrite(src)
         dst = out_dir / (Path(name).stem + "_emu.cpp")
         dst.write_text(f'#line 1 "{CSRC / name}"\n' + text)

@@ -221,6 +221,18 @@ static inline long long __double_as_longlong(double x) { long long r; memcpy(&r,
 static inline double __longlong_as_double(long long x) { double r; memcpy(&r, &x, 8); return r; }
 static inline double __uint2double_rn(unsigned x) { return (double)x; }
 static inline size_t __cvta_generic_to_shared(const void *p) { return reinterpret_cast<size_t>(p); }
+static inline int __ffsll(long long x) { return __builtin_ffsll(x); }
+static inline int __clzll(long long x) { return x ? __builtin_clzll((unsigned long long)x) : 64; }
+static inline int atomicMin(int *p, int v) {
+    int old = __atomic_load_n(p, __ATOMIC_RELAXED);
+    while (old > v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+    return old;
+}
+static inline int atomicMax(int *p, int v) {
+    int old = __atomic_load_n(p, __ATOMIC_RELAXED);
+    while (old < v && !__atomic_compare_exchange_n(p, &old, v, false, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {}
+    return old;
+}
 static inline int __popc(unsigned x) { return __builtin_popcount(x); }
 static inline int __ffs(int x) { return __builtin_ffs(x); }
 static inline unsigned __byte_perm(unsigned a, unsigned b, unsigned sel) {

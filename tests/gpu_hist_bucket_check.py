@@ -21,23 +21,24 @@ def synth(K, n, seed):
     return base[None, :] + 0.106 * rng.standard_normal((K, n)) - 0.5 * np.arange(K)[:, None] / n
 
 
-def main() -> int:
-    import consel_b200 as cg
-    from oracle import oracle as orc
+CASES_GPU = ((4, 300000, [0.6, 1.3], [6, 5], 1), (3, 1600000, [1.4], [3], 1), (5, 100000, [0.5, 1.2], [300, 7], 2))
 
-    cg.init(0)
-    cg.set_shard(0, 1)
+
+def check(cg, orc, cases=CASES_GPU) -> list:
+    """(K, n, scales, replicates, option value): 1 = the opt-in path above 225280 sites, 2 = forced below.
+    Returns the list of mismatches (empty = the bucketed path returns the bits of the default kernels)."""
     bad = []
-    # (K, n, scales, replicates, option value): 1 = the opt-in path above 225280 sites, 2 = forced below
-    for K, n, rr, bb, opt in ((4, 300000, [0.6, 1.3], [6, 5], 1), (3, 1600000, [1.4], [3], 1), (5, 100000, [0.5, 1.2], [300, 7], 2)):
+    for K, n, rr, bb, opt in cases:
         L = synth(K, n, 11 + K)
         _, bn, rr1 = orc.scale_setup(L, rr)
         for rng_mode in (cg.RNG_MT19937, cg.RNG_PHILOX):
             cg.set_option("hist_bucket", 0)
             base = cg.scaleboot_all(L, bn, bb, 5, rng_mode=rng_mode, sum_mode=cg.SUM_INT8)
             cg.set_option("hist_bucket", opt)
-            got = cg.scaleboot_all(L, bn, bb, 5, rng_mode=rng_mode, sum_mode=cg.SUM_INT8)
-            cg.set_option("hist_bucket", -1)
+            try:
+                got = cg.scaleboot_all(L, bn, bb, 5, rng_mode=rng_mode, sum_mode=cg.SUM_INT8)
+            finally:
+                cg.set_option("hist_bucket", -1)
             for s in range(len(rr)):
                 if not np.array_equal(base[s], got[s]):
                     bad.append(f"n={n} rng={rng_mode} scale {s}: bucketed sums differ from the default kernels")
@@ -50,6 +51,16 @@ def main() -> int:
                         want = math.fsum(np.repeat(L[0], c)) / np.float64(rr1[s])
                         if got[s][0, b] != want:
                             bad.append(f"n={n} scale {s} replicate {b}: not the exact sum over the reference's draws")
+    return bad
+
+
+def main() -> int:
+    import consel_b200 as cg
+    from oracle import oracle as orc
+
+    cg.init(0)
+    cg.set_shard(0, 1)
+    bad = check(cg, orc)
     for line in bad:
         print("MISMATCH", line)
     print("hist_bucket check:", "ok" if not bad else f"{len(bad)} mismatches")

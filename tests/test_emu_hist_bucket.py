@@ -110,3 +110,15 @@ def test_library_histogram_launchers_byte_rows(emu_lib, tmp_path_factory, case):
     launches = int(r.stdout.split(",")[-1].split()[0])
     if case[4] in (1, 2):
         assert launches == 4  # count, scan, scatter, histogram
+
+
+def test_bucketed_path_through_the_c_abi_on_the_emulated_library(emu_cg, orc):
+    """what tests/test_zz_gpu_hist_bucket.py runs on the device (tests/gpu_hist_bucket_check.py: the int8 replicate
+    sums with cgpu_set_option("hist_bucket", 1|2) against the default histogram kernels and against the exact sums
+    of the oracle's counts), at sizes the CPU finishes in seconds"""
+    import sys
+    sys.path.insert(0, str(ROOT / "tests"))
+    import gpu_hist_bucket_check as chk
+    launches = emu_cg.launch_count()
+    bad = chk.check(emu_cg, orc, cases=((3, 300000, [0.6, 1.3], [3, 2], 1), (3, 100000, [0.5, 1.2], [20, 3], 2)))
+    assert bad == [] and emu_cg.launch_count() > launches
