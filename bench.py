@@ -31,6 +31,9 @@ oracle (`spot_check`).
              makermt AND consel sides with its own bound, `roofline.step` the whole step against
              SURVEY 8(d)'s floor (2*S*K*n*sum(B) int8-ops at the int8 peak MEASURED in this run).
 
+  side_c4    (N=1, default workload) one GPU's share of the 8-GPU genome-scale job C4, measured in a
+             process of its own after every other leg: default histogram and the bucketed one.
+
 --impl reference times the reference's own CPU code on the host cores: the unmodified makermt
 binary (one process per scale and part, src/program.tex:1089-1109) when the matrix is small enough
 to pass as a .mt text file, else the reference's scaleboot() compiled unmodified from
@@ -566,6 +569,25 @@ def run_ours(args) -> None:
     except Exception as e:
         cpu_baseline = {"error": f"{type(e).__name__}: {e}", "unit": UNIT, "cores": 1, "kind": "port"}
 
+    # ---- side leg (N=1, default workload only): the per-GPU share of C4 in a process of its own
+    side_c4 = None
+    if world == 1 and name == DEFAULT_CONFIG and os.environ.get("BENCH_SIDE", "1") != "0":
+        try:
+            mat.free()
+            del flush, Lh, out_t, outs
+            torch.cuda.empty_cache()
+            # the library keeps freed blocks in the device's default stream-ordered pool (release threshold = max):
+            # hand them back to the driver, the child process needs ~40 GB of its own
+            import ctypes
+            cu = ctypes.CDLL("libcuda.so.1")
+            pool = ctypes.c_void_p()
+            torch.cuda.synchronize()
+            if cu.cuDeviceGetDefaultMemPool(ctypes.byref(pool), ctypes.c_int(local)) == 0:
+                cu.cuMemPoolTrimTo(pool, ctypes.c_size_t(0))
+        except Exception:
+            pass
+        side_c4 = side_c4_from(args)
+
     line = {
         "metric": METRIC, "value": acc_per_step_total * args.steps / (dev_ms * 1e-3), "unit": UNIT,
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
@@ -580,7 +602,132 @@ def run_ours(args) -> None:
         "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu_baseline,
         "spot_check": spot, "modes": modes, "pipeline": pipe,
     }
+    if side_c4 is not None:
+        line["side_c4"] = side_c4
     print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------ side leg: C4
+def synth_matrix_threads(k: int, n: int, seed: int = 20261019) -> np.ndarray:
+    """synth_matrix's distribution, filled by row blocks on all host threads (one PCG64 stream per block):
+    10^9 entries in seconds instead of half a minute.  Side leg only -- the headline uses synth_matrix."""
+    from concurrent.futures import ThreadPoolExecutor
+    base = -2.3 - 4.07 * np.random.Generator(np.random.PCG64(seed)).exponential(size=n)
+    L = np.empty((k, n))
+    step = max(1, (1 << 25) // n)
+
+    def fill(k0):
+        k1 = min(k, k0 + step)
+        blk = L[k0:k1]
+        np.random.Generator(np.random.PCG64([seed, k0])).standard_normal(out=blk)  # releases the GIL
+        blk *= 0.106
+        blk += base[None, :]
+        blk -= 0.5 * np.arange(k0, k1)[:, None] / n
+    with ThreadPoolExecutor(max_workers=min(32, os.cpu_count() or 4)) as ex:
+        list(ex.map(fill, range(0, k, step)))
+    return L
+
+
+def run_side_c4(args) -> None:
+    """`--side c4` (started by run_ours as its OWN process, after every leg of the default line): the
+    per-GPU share of the 8-GPU genome-scale job C4 (K=100 x n=10^7, 1250 replicates per scale) on one GPU,
+    reference MT19937 stream + int8 sums, once with the default histogram of rows that long (32-bit global
+    atomics) and once with the bucketed histogram (csrc/hist_bucket.cuh, cgpu_set_option("hist_bucket", 1)).
+    One JSON line per variant, flushed as soon as it exists: the bucketed kernels were written after the
+    round's GPU budget was spent (pinned on the CPU by emulated execution only), so whatever they do on
+    hardware must not cost the lines before them."""
+    import torch
+
+    import consel_b200 as cg
+
+    t_start = time.perf_counter()
+    torch.cuda.set_device(0)
+    cg.init(0)
+    cg.set_shard(0, 1)
+    c = workload("C4", 1)
+    if args.side_reps > 0:
+        c["B_total"] = args.side_reps
+    K = c["K"] if args.side_trees <= 0 else args.side_trees  # (the size switches exist for the CPU test of this leg)
+    n = c["n"] if args.side_sites <= 0 else args.side_sites
+    L = synth_matrix_threads(K, n)
+    _, bn, _ = cg.scale_setup(L, RR)
+    bb = np.full(len(RR), c["B_total"], dtype=np.int32)
+    acc = float(K) * n * float(bb.sum())
+    draws = float(np.sum(bn.astype(np.float64) * bb))
+    t0 = time.perf_counter()
+    mat = cg.Matrix(L)
+    t_up = time.perf_counter() - t0
+    print(json.dumps({"side": "C4", "variant": "setup", "K": K, "n": n, "replicates_per_scale": int(c["B_total"]),
+                      "draws_per_step": draws, "matrix_s": round(t0 - t_start, 2), "upload_s": round(t_up, 2)}), flush=True)
+    first = None
+    for label, opt in (("global_atomics (default)", 0), ("bucketed (hist_bucket=1)", 1)):
+        cg.set_option("hist_bucket", opt)
+        out = {"side": "C4", "variant": label}
+        try:
+            mat.scaleboot(bn, bb, 7, rng_mode=cg.RNG_MT19937, sum_mode=cg.SUM_INT8).free()  # warm-up (fixed-point slices, pools)
+            ms, ph = [], {}
+            cols = None
+            for step in range(args.steps):
+                reps = mat.scaleboot(bn, bb, 7, rng_mode=cg.RNG_MT19937, sum_mode=cg.SUM_INT8)
+                tm = cg.last_timing()
+                ms.append(tm["total"])
+                for k_, v in tm.items():
+                    ph[k_] = ph.get(k_, 0.0) + v / args.steps
+                if step == args.steps - 1:
+                    cols = [reps.download_cols(s, 0, 2) for s in (0, len(RR) - 1)] + \
+                           [reps.download_cols(len(RR) - 1, int(bb[-1]) - 2, 2)]
+                reps.free()
+            t = float(np.mean(ms))
+            out.update({"ms_per_step": t, "value": acc / (t * 1e-3), "unit": UNIT, "steps": args.steps,
+                        "draws_per_s_through_draw_and_histogram": draws / ((ph["rng"] + ph["resample"]) * 1e-3),
+                        "phases_ms_per_step": ph})
+            if first is None:
+                first = cols
+                # the oracle's stream and site indices for replicate 0 of scale 0, exact sums by math.fsum
+                from oracle import oracle as orc
+                y = orc.mt_stream(7, 0, int(bn[0]))
+                cnt = np.bincount(orc.site_indices(y, n), minlength=n)[None, :]
+                kt = np.array([0, K - 1])
+                want = exact_sums(L[kt], cnt, float(bn[0]) / float(n))
+                out["spot_check"] = {"bit_equal_to_exact_rounded_sums": bool(np.array_equal(cols[0][kt, :1], want)),
+                                     "what": "replicate 0 of scale 0, first and last tree: MT19937 draws and site indices by the "
+                                             "oracle, exact sums by math.fsum"}
+            else:
+                out["identical_to_default_histogram"] = bool(all(np.array_equal(a, b) for a, b in zip(first, cols)))
+        except Exception as e:
+            out["error"] = f"{type(e).__name__}: {e}"
+        print(json.dumps(out), flush=True)
+    cg.set_option("hist_bucket", -1)
+
+
+def side_c4_from(parent_args) -> dict:
+    """runs `bench.py --side c4` as its own process with a time limit and collects its lines; never raises"""
+    limit = float(os.environ.get("BENCH_SIDE_TIMEOUT_S", "240"))
+    cmd = [sys.executable, str(Path(__file__).resolve()), "--side", "c4", "--steps", "2"]
+    env = {k_: v for k_, v in os.environ.items() if k_ not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "LOCAL_WORLD_SIZE")}
+    t0 = time.perf_counter()
+    text, status = "", "ok"
+    try:
+        p = subprocess.run(cmd, capture_output=True, text=True, timeout=limit, env=env, cwd=str(ROOT))
+        text = p.stdout
+        if p.returncode != 0:
+            status = f"exit status {p.returncode}: {p.stderr.strip().splitlines()[-1][:300] if p.stderr.strip() else ''}"
+    except subprocess.TimeoutExpired as e:
+        text = e.stdout.decode() if isinstance(e.stdout, bytes) else (e.stdout or "")
+        status = f"time limit of {limit:.0f} s reached: the variants printed so far are kept"
+    except Exception as e:
+        status = f"{type(e).__name__}: {e}"
+    variants = []
+    for ln in text.splitlines():
+        if ln.startswith("{"):
+            try:
+                variants.append(json.loads(ln))
+            except ValueError:
+                pass
+    return {"what": "C4 (BASELINE.json configs[3]: K=100 x n=10^7, an 8-GPU job) -- one GPU's share, 1250 replicates per scale, "
+                    "MT19937 stream + int8 sums, in a process of its own after the default line was measured; "
+                    "`bucketed` is the first hardware run of csrc/hist_bucket.cuh",
+            "status": status, "seconds": round(time.perf_counter() - t0, 1), "variants": variants}
 
 
 # ------------------------------------------------------------------------ reference
@@ -738,8 +885,14 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default=DEFAULT_CONFIG, choices=sorted(CONFIGS))
+    ap.add_argument("--side", default="", choices=["", "c4"], help=argparse.SUPPRESS)  # run_ours starts this itself
+    ap.add_argument("--side-reps", type=int, default=0, help=argparse.SUPPRESS)
+    ap.add_argument("--side-sites", type=int, default=0, help=argparse.SUPPRESS)
+    ap.add_argument("--side-trees", type=int, default=0, help=argparse.SUPPRESS)
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.side == "c4":
+        run_side_c4(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

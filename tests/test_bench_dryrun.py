@@ -214,11 +214,59 @@ def test_auxiliary_legs_cannot_cost_the_headline_line(monkeypatch, capsys, orc):
     monkeypatch.setattr(orc, "makermt", boom)
     for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
         monkeypatch.delenv(k, raising=False)
+    # the side leg of the default workload (its own process on the GPU box) is walked too: here the default is C1
+    # and the child is a stub, what is checked is the parent's branch (buffers released, result attached)
+    monkeypatch.setattr(bench, "DEFAULT_CONFIG", "C1")
+    monkeypatch.setattr(bench, "side_c4_from", lambda a: {"status": "stub", "variants": []})
     bench.run_ours(types.SimpleNamespace(gpus=1, steps=2, warmup=3, impl="ours", config="C1"))
     lines = [t for t in capsys.readouterr().out.splitlines() if t.strip()]
     assert len(lines) == 1
     d = json.loads(lines[0])
+    assert d["side_c4"] == {"status": "stub", "variants": []}
     assert d["value"] == pytest.approx(15 * 3414 * 1e5 / 2.0e-3) and d["spot_check"]["ok"] is True
     assert "error" in d["e2e"] and "error" in d["cpu_baseline"] and "error" in d["pipeline"]
     assert all("error" in m for m in d["modes"].values())
     assert d["roofline"]["peak"] == 4500.0 and d["clocks"] is None
+
+
+# ---------------------------------------------------------------------------------------------- the C4 side leg
+def test_side_c4_leg_on_the_emulated_library(monkeypatch, capsys, emu_cg):
+    """bench.run_side_c4 end to end on the CPU (emulated device library, a few trees / replicates, 300000 sites so
+    that the rows are longer than every shared-memory histogram): both variants print a line, the default one is
+    bit-equal to the exact sums over the oracle's draws, the bucketed one identical to the default."""
+    import types
+
+    import torch
+
+    monkeypatch.setattr(torch.cuda, "set_device", lambda d: None)
+    monkeypatch.setattr(emu_cg, "init", lambda d=-1: None)
+    bench.run_side_c4(types.SimpleNamespace(steps=1, side_reps=3, side_sites=300000, side_trees=3))
+    lines = [json.loads(t) for t in capsys.readouterr().out.splitlines() if t.startswith("{")]
+    assert [x["variant"] for x in lines] == ["setup", "global_atomics (default)", "bucketed (hist_bucket=1)"]
+    assert "error" not in lines[1] and "error" not in lines[2], lines
+    assert lines[1]["spot_check"]["bit_equal_to_exact_rounded_sums"] is True
+    assert lines[2]["identical_to_default_histogram"] is True
+    assert lines[1]["value"] > 0 and lines[2]["phases_ms_per_step"]["n_hist"] > 0
+
+
+def test_side_c4_collector_keeps_what_was_printed(monkeypatch, tmp_path):
+    """the parent side: a child that prints one variant and then dies (or hangs past the limit) costs nothing but
+    its own missing lines"""
+    import subprocess as sp
+    import types
+
+    real_run = sp.run
+    script = tmp_path / "child.py"
+
+    def fake(mode):
+        def run(cmd, **kw):
+            script.write_text("import json, sys, time\nprint(json.dumps({'side': 'C4', 'variant': 'a', 'value': 1.0}), flush=True)\n"
+                              + ("time.sleep(60)\n" if mode == "hang" else "sys.stderr.write('boom\\n'); sys.exit(3)\n"))
+            return real_run([sys.executable, str(script)], **kw)
+        return run
+    monkeypatch.setenv("BENCH_SIDE_TIMEOUT_S", "3")
+    for mode, word in (("die", "exit status 3: boom"), ("hang", "time limit")):
+        monkeypatch.setattr(bench.subprocess, "run", fake(mode))
+        out = bench.side_c4_from(types.SimpleNamespace())
+        assert word in out["status"], out
+        assert out["variants"] == [{"side": "C4", "variant": "a", "value": 1.0}]
