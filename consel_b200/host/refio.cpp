@@ -5,6 +5,8 @@
 
 #include <algorithm>
 #include <sys/stat.h>
+#include <unistd.h>
+#include <memory>
 #include <thread>
 #include <charconv>
 #include <cctype>
@@ -146,51 +148,91 @@ std::vector<std::string> read_svec(FILE *fp) {
     for (int i = 0; i < m; i++) a.push_back(read_word(fp));
     return a;
 }
+// The rest of a regular file in memory, with a '\n' sentinel behind it.  Every host thread reads its own
+// slice with pread into an uninitialised buffer, so the first touch of the pages (the expensive part of a
+// gigabyte-sized allocation) and the copy out of the page cache run on all cores.  The stream position of
+// `fp` does not move.
+namespace {
+// isspace of the "C" locale as an inline test (the parsers below call it once per byte)
+inline bool is_space(unsigned char c) { return c == ' ' || (c >= '\t' && c <= '\r'); }
+
+int io_threads() { return (int)std::max(1u, std::min(64u, std::thread::hardware_concurrency())); }
+
+struct FileTail {
+    std::unique_ptr<char[]> buf;
+    size_t bytes = 0;
+    long pos = 0;
+    bool load(FILE *fp) {
+        struct stat st;
+        const int fd = fileno(fp);
+        if (fd < 0 || fstat(fd, &st) != 0 || !S_ISREG(st.st_mode)) return false;
+        pos = ftell(fp);
+        if (pos < 0 || st.st_size <= pos) return false;
+        bytes = (size_t)(st.st_size - pos);
+        buf.reset(new (std::nothrow) char[bytes + 1]);
+        if (!buf) return false;
+        const int nthr = bytes < ((size_t)8 << 20) ? 1 : io_threads();
+        std::vector<char> good(nthr, 1);
+        auto work = [&](int t) {
+            size_t lo = bytes / nthr * t, hi = t == nthr - 1 ? bytes : bytes / nthr * (t + 1);
+            while (lo < hi) {
+                const ssize_t r = pread(fd, buf.get() + lo, hi - lo, (off_t)pos + (off_t)lo);
+                if (r <= 0) { good[t] = 0; return; }
+                lo += (size_t)r;
+            }
+        };
+        std::vector<std::thread> th;
+        for (int t = 1; t < nthr; t++) th.emplace_back(work, t);
+        work(0);
+        for (auto &x : th) x.join();
+        for (int t = 0; t < nthr; t++)
+            if (!good[t]) return false;
+        buf[bytes] = '\n';
+        return true;
+    }
+};
+}  // namespace
+
 // Parallel text parse of `count` doubles from a regular file (a K=1000 x n=10^5
 // matrix is 2 GB of text, minutes of fscanf).  The rest of the file is read into memory, cut
 // at line ends (a '#' comment never spans a line end), tokenised and converted with
-// std::from_chars on all host threads.  Anything the strict tokenizer does not understand
-// (hex floats, trailing garbage, too few values) makes it give up WITHOUT consuming input,
-// and the caller falls back to the fscanf loop, so error behaviour stays the reference's.
+// std::from_chars on all host threads, and copied into place on all host threads.  Anything the
+// strict tokenizer does not understand (hex floats, trailing garbage, too few values) makes it
+// give up WITHOUT consuming input, and the caller falls back to the fscanf loop, so error
+// behaviour stays the reference's.
 static bool read_doubles_parallel(FILE *fp, double *out, size_t count) {
     if (count < (1u << 16)) return false;
-    struct stat st;
-    const int fd = fileno(fp);
-    if (fd < 0 || fstat(fd, &st) != 0 || !S_ISREG(st.st_mode)) return false;
-    const long pos = ftell(fp);
-    if (pos < 0 || st.st_size <= pos) return false;
-    const size_t bytes = (size_t)(st.st_size - pos);
-    std::vector<char> buf(bytes + 1);
-    if (fread(buf.data(), 1, bytes, fp) != bytes) {
-        fseek(fp, pos, SEEK_SET);
-        return false;
-    }
-    buf[bytes] = '\n';
-    const char *base = buf.data();
-    const int nthr = (int)std::max(1u, std::min(64u, std::thread::hardware_concurrency()));
+    FileTail file;
+    if (!file.load(fp)) return false;
+    const size_t bytes = file.bytes;
+    const long pos = file.pos;
+    const char *base = file.buf.get();
+    const int nthr = io_threads();
     std::vector<size_t> cut(nthr + 1, bytes);
     cut[0] = 0;
     for (int t = 1; t < nthr; t++) {
-        size_t c = bytes / nthr * t;
-        while (c < bytes && base[c] != '\n') c++;
-        cut[t] = c < bytes ? c + 1 : bytes;
+        size_t c = std::max(cut[t - 1], bytes / nthr * t);
+        const void *nl = c < bytes ? memchr(base + c, '\n', bytes - c) : nullptr;
+        cut[t] = nl ? (size_t)(static_cast<const char *>(nl) - base) + 1 : bytes;
     }
     // tokens of [lo, hi): every value, or stop as soon as `limit` values were taken
     struct Part {
         std::vector<double> vals;
-        size_t end = 0;  // offset just behind the last token taken
+        std::vector<size_t> ends;  // only filled when asked for: offset just behind every token
+        size_t end = 0;            // offset just behind the last token taken
         bool ok = true;
     };
     auto parse = [&](size_t lo, size_t hi, size_t limit, Part *p) {
         const char *c = base + lo, *e = base + hi;
         while (c < e && p->vals.size() < limit) {
-            if (isspace((unsigned char)*c)) { c++; continue; }
+            if (is_space((unsigned char)*c)) { c++; continue; }
             if (*c == '#') {
-                while (c < e && *c != '\n') c++;
+                const void *nl = memchr(c, '\n', (size_t)(e - c));
+                c = nl ? static_cast<const char *>(nl) : e;
                 continue;
             }
             const char *tok = c;
-            while (c < e && !isspace((unsigned char)*c)) c++;
+            while (c < e && !is_space((unsigned char)*c)) c++;
             const char *b = tok;
             if (*b == '+') b++;
             double v;
@@ -206,29 +248,47 @@ static bool read_doubles_parallel(FILE *fp, double *out, size_t count) {
     std::vector<Part> parts(nthr);
     {
         std::vector<std::thread> th;
-        for (int t = 0; t < nthr; t++) th.emplace_back([&, t] { parse(cut[t], cut[t + 1], ~(size_t)0, &parts[t]); });
+        auto work = [&](int t) {
+            try {  // a value takes at least two bytes; typical files spend 15-25 on one
+                parts[t].vals.reserve((cut[t + 1] - cut[t]) / 12 + 16);
+            } catch (...) {
+            }
+            parse(cut[t], cut[t + 1], ~(size_t)0, &parts[t]);
+        };
+        for (int t = 1; t < nthr; t++) th.emplace_back(work, t);
+        work(0);
         for (auto &x : th) x.join();
     }
     // the matrix may be followed by other data: take exactly `count` values in file order
     size_t have = 0, end = 0;
     bool ok = true;
+    std::vector<size_t> first(nthr, 0), take(nthr, 0);
     for (int t = 0; t < nthr && have < count; t++) {
         if (!parts[t].ok && parts[t].vals.size() < count - have) { ok = false; break; }
-        const size_t take = std::min(parts[t].vals.size(), count - have);
-        if (take == parts[t].vals.size()) {
+        take[t] = std::min(parts[t].vals.size(), count - have);
+        first[t] = have;
+        if (take[t] == parts[t].vals.size()) {
             end = parts[t].end ? parts[t].end : end;
         } else {  // the matrix ends inside this part: find where, sequentially
             Part q;
-            parse(cut[t], cut[t + 1], take, &q);
-            if (!q.ok || q.vals.size() != take) { ok = false; break; }
+            parse(cut[t], cut[t + 1], take[t], &q);
+            if (!q.ok || q.vals.size() != take[t]) { ok = false; break; }
             end = q.end;
         }
-        memcpy(out + have, parts[t].vals.data(), take * sizeof(double));
-        have += take;
+        have += take[t];
     }
     if (!ok || have != count) {
         fseek(fp, pos, SEEK_SET);
         return false;
+    }
+    {
+        std::vector<std::thread> th;
+        auto copy = [&](int t) {
+            if (take[t]) memcpy(out + first[t], parts[t].vals.data(), take[t] * sizeof(double));
+        };
+        for (int t = 1; t < nthr; t++) th.emplace_back(copy, t);
+        copy(0);
+        for (auto &x : th) x.join();
     }
     fseek(fp, pos + (long)end, SEEK_SET);
     return true;
@@ -345,31 +405,56 @@ void write_bmat(FILE *fp, const double *a, int m, int n) {
 // WITHOUT consuming input, so the serial loop below produces the reference's values and error messages.
 static bool read_paml_blocks_parallel(FILE *fp, int m, int n, int p, double *out) {
     if ((long long)m * p < (1 << 15)) return false;
-    struct stat st;
-    const int fd = fileno(fp);
-    if (fd < 0 || fstat(fd, &st) != 0 || !S_ISREG(st.st_mode)) return false;
-    const long pos = ftell(fp);
-    if (pos < 0 || st.st_size <= pos) return false;
-    const size_t bytes = (size_t)(st.st_size - pos);
-    std::vector<char> buf(bytes + 1);
-    if (fread(buf.data(), 1, bytes, fp) != bytes) {
-        fseek(fp, pos, SEEK_SET);
-        return false;
-    }
-    buf[bytes] = '\n';
-    const char *base = buf.data();
-    // offsets of the non-blank lines
+    FileTail file;
+    if (!file.load(fp)) return false;
+    const size_t bytes = file.bytes;
+    const long pos = file.pos;
+    const char *base = file.buf.get();
+    // offsets of the non-blank lines: every thread indexes a slice that starts at a line start, the
+    // slices' lists are then laid end to end
     std::vector<size_t> line;
-    line.reserve((size_t)m * (p + 1) + 16);
-    for (size_t c = 0; c < bytes;) {
-        size_t e = c;
-        bool blank = true;
-        while (base[e] != '\n') {
-            if (!isspace((unsigned char)base[e])) blank = false;
-            e++;
+    {
+        const int nt = io_threads();
+        std::vector<size_t> cut(nt + 1, bytes);
+        cut[0] = 0;
+        for (int t = 1; t < nt; t++) {
+            size_t c = std::max(cut[t - 1], bytes / nt * t);
+            const void *nl = c < bytes ? memchr(base + c, '\n', bytes - c) : nullptr;
+            cut[t] = nl ? (size_t)(static_cast<const char *>(nl) - base) + 1 : bytes;
         }
-        if (!blank) line.push_back(c);
-        c = e + 1;
+        std::vector<std::vector<size_t>> local(nt);
+        auto index = [&](int t) {
+            std::vector<size_t> &v = local[t];
+            try {
+                v.reserve((cut[t + 1] - cut[t]) / 24 + 16);
+            } catch (...) {
+            }
+            for (size_t c = cut[t]; c < cut[t + 1];) {
+                const size_t e = (size_t)(static_cast<const char *>(memchr(base + c, '\n', bytes + 1 - c)) - base);  // the sentinel ends the last line
+                size_t k = c;
+                while (k < e && is_space((unsigned char)base[k])) k++;
+                if (k < e) v.push_back(c);
+                c = e + 1;
+            }
+        };
+        std::vector<std::thread> th;
+        for (int t = 1; t < nt; t++) th.emplace_back(index, t);
+        index(0);
+        for (auto &x : th) x.join();
+        size_t total = 0;
+        std::vector<size_t> off(nt, 0);
+        for (int t = 0; t < nt; t++) {
+            off[t] = total;
+            total += local[t].size();
+        }
+        line.resize(total);
+        std::vector<std::thread> th2;
+        auto place = [&](int t) {
+            if (!local[t].empty()) memcpy(line.data() + off[t], local[t].data(), local[t].size() * sizeof(size_t));
+        };
+        for (int t = 1; t < nt; t++) th2.emplace_back(place, t);
+        place(0);
+        for (auto &x : th2) x.join();
     }
     const size_t need = (size_t)m * ((size_t)p + 1);
     bool ok = line.size() >= need;
@@ -379,7 +464,7 @@ static bool read_paml_blocks_parallel(FILE *fp, int m, int n, int p, double *out
         auto tok_int = [&](const char *&c, long long *v) {
             while (*c == ' ' || *c == '\t' || *c == '\r') c++;
             const char *b = c;
-            while (*c != '\n' && !isspace((unsigned char)*c)) c++;
+            while (*c != '\n' && !is_space((unsigned char)*c)) c++;
             auto r = std::from_chars(b, c, *v);
             return b < c && r.ec == std::errc() && r.ptr == c;
         };
@@ -397,7 +482,7 @@ static bool read_paml_blocks_parallel(FILE *fp, int m, int n, int p, double *out
                     if (*c == '#' || !tok_int(c, &idx) || idx != j + 1 || !tok_int(c, &reps) || reps < 0 || col + reps > n) { good[t] = 0; return; }
                     while (*c == ' ' || *c == '\t' || *c == '\r') c++;
                     const char *b = c;
-                    while (*c != '\n' && !isspace((unsigned char)*c)) c++;
+                    while (*c != '\n' && !is_space((unsigned char)*c)) c++;
                     const char *b2 = (*b == '+') ? b + 1 : b;
                     double x;
                     auto r = std::from_chars(b2, c, x);

@@ -155,6 +155,21 @@ def test_parallel_matrix_reader_equals_token_reader(tmp_path):
         assert np.array_equal(out.view(np.uint64), a.ravel().view(np.uint64))
         assert word.value == b"TRAILER"
 
+    # a file above 8 MB is also LOADED by all host threads (pread slices into one uninitialised buffer)
+    m, n = 230, 3000
+    a = -np.exp(rng.uniform(-3, 4, size=(m, n)))
+    p = tmp_path / "big.mt"
+    with open(p, "w") as f:
+        f.write("%d %d\n" % (m, n))
+        np.savetxt(f, a.reshape(-1, 6), fmt="%.17g")
+        f.write("TRAILER\n")
+    assert p.stat().st_size > (8 << 20)
+    out = np.zeros(m * n)
+    assert lib.refio_test_read_mat(str(p).encode(), C.byref(mm), C.byref(nn), out.ctypes.data_as(C.POINTER(C.c_double)),
+                                   m * n, word, 64) == 0
+    assert (mm.value, nn.value) == (m, n) and word.value == b"TRAILER"
+    assert np.array_equal(out.view(np.uint64), a.ravel().view(np.uint64))
+
 
 @pytest.mark.parametrize("case", ["g100", "g100e", "tiny", "g100fe"])
 def test_consel_cnt_mode_cli(case, gold, tmp_path):
