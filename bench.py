@@ -571,7 +571,7 @@ def run_ours(args) -> None:
 
     # ---- side leg (N=1, default workload only): the per-GPU share of C4 in a process of its own
     side_c4 = None
-    if world == 1 and name == DEFAULT_CONFIG and os.environ.get("BENCH_SIDE", "1") != "0":
+    if world in (1, 8) and name == DEFAULT_CONFIG and os.environ.get("BENCH_SIDE", "1") != "0":
         try:
             mat.free()
             del flush, Lh, out_t, outs
@@ -586,7 +586,7 @@ def run_ours(args) -> None:
                 cu.cuMemPoolTrimTo(pool, ctypes.c_size_t(0))
         except Exception:
             pass
-        side_c4 = side_c4_from(args)
+        side_c4 = side_c4_from(args, world)
 
     line = {
         "metric": METRIC, "value": acc_per_step_total * args.steps / (dev_ms * 1e-3), "unit": UNIT,
@@ -623,110 +623,163 @@ def synth_matrix_threads(k: int, n: int, seed: int = 20261019) -> np.ndarray:
         blk *= 0.106
         blk += base[None, :]
         blk -= 0.5 * np.arange(k0, k1)[:, None] / n
-    with ThreadPoolExecutor(max_workers=min(32, os.cpu_count() or 4)) as ex:
+    share = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))  # one process per GPU shares the host's cores
+    with ThreadPoolExecutor(max_workers=max(1, min(32, (os.cpu_count() or 4) // share))) as ex:
         list(ex.map(fill, range(0, k, step)))
     return L
 
 
 def run_side_c4(args) -> None:
-    """`--side c4` (started by run_ours as its OWN process, after every leg of the default line): the
-    per-GPU share of the 8-GPU genome-scale job C4 (K=100 x n=10^7, 1250 replicates per scale) on one GPU,
-    reference MT19937 stream + int8 sums, once with the default histogram of rows that long (32-bit global
-    atomics) and once with the bucketed histogram (csrc/hist_bucket.cuh, cgpu_set_option("hist_bucket", 1)).
-    One JSON line per variant, flushed as soon as it exists: the bucketed kernels were written after the
-    round's GPU budget was spent (pinned on the CPU by emulated execution only), so whatever they do on
-    hardware must not cost the lines before them."""
+    """`--side c4` (started by run_ours as its OWN process or torchrun job, after every leg of the default
+    line): the genome-scale job C4 (K=100 x n=10^7, BASELINE.json configs[3]) -- all of it (10^4 replicates per
+    scale) when started as 8 ranks, one GPU's share of it (1250 per scale) as a single process -- reference
+    MT19937 stream + int8 sums, once with the default histogram of rows that long (32-bit global atomics) and
+    once with the bucketed histogram (csrc/hist_bucket.cuh, cgpu_set_option("hist_bucket", 1)).  The makermt
+    side has no data-path collective: every rank jumps the stream to its own replicate columns; the ranks only
+    agree on the step time (max over ranks, gloo).  One JSON line per variant, flushed by rank 0 as soon as it
+    exists: the bucketed kernels were written after the round's GPU budget was spent (pinned on the CPU by
+    emulated execution only), so whatever they do on hardware must not cost the lines before them."""
     import torch
 
     import consel_b200 as cg
 
     t_start = time.perf_counter()
-    torch.cuda.set_device(0)
-    cg.init(0)
-    cg.set_shard(0, 1)
-    c = workload("C4", 1)
+    rank, world, local = dist_env()
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("gloo")
+    cg.init(local)
+    cg.set_shard(rank, world)
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def say(d: dict) -> None:
+        if rank == 0:
+            print(json.dumps(d), flush=True)
+
+    c = workload("C4", world)
     if args.side_reps > 0:
         c["B_total"] = args.side_reps
     K = c["K"] if args.side_trees <= 0 else args.side_trees  # (the size switches exist for the CPU test of this leg)
     n = c["n"] if args.side_sites <= 0 else args.side_sites
     L = synth_matrix_threads(K, n)
-    _, bn, _ = cg.scale_setup(L, RR)
+    bn = (np.asarray(RR, dtype=np.float64) * np.float64(n)).astype(np.int32)  # bn = (int)(rr*n): src/makermt.c:165-168
     bb = np.full(len(RR), c["B_total"], dtype=np.int32)
+    b0, b1 = cg.shard_range(int(bb[-1]))
     acc = float(K) * n * float(bb.sum())
     draws = float(np.sum(bn.astype(np.float64) * bb))
     t0 = time.perf_counter()
     mat = cg.Matrix(L)
     t_up = time.perf_counter() - t0
-    print(json.dumps({"side": "C4", "variant": "setup", "K": K, "n": n, "replicates_per_scale": int(c["B_total"]),
-                      "draws_per_step": draws, "matrix_s": round(t0 - t_start, 2), "upload_s": round(t_up, 2)}), flush=True)
+    say({"side": "C4", "variant": "setup", "n_gpus": world, "K": K, "n": n, "replicates_per_scale_total": int(c["B_total"]),
+         "replicates_per_scale_per_gpu": b1 - b0, "draws_per_step_total": draws, "matrix_s": round(t0 - t_start, 2),
+         "upload_s": round(t_up, 2)})
     first = None
     for label, opt in (("global_atomics (default)", 0), ("bucketed (hist_bucket=1)", 1)):
         cg.set_option("hist_bucket", opt)
-        out = {"side": "C4", "variant": label}
+        out = {"side": "C4", "variant": label, "n_gpus": world}
         try:
             mat.scaleboot(bn, bb, 7, rng_mode=cg.RNG_MT19937, sum_mode=cg.SUM_INT8).free()  # warm-up (fixed-point slices, pools)
             ms, ph = [], {}
             cols = None
             for step in range(args.steps):
+                max_over_ranks(0.0)  # the ranks start a step together
                 reps = mat.scaleboot(bn, bb, 7, rng_mode=cg.RNG_MT19937, sum_mode=cg.SUM_INT8)
                 tm = cg.last_timing()
-                ms.append(tm["total"])
+                ms.append(max_over_ranks(tm["total"]))
                 for k_, v in tm.items():
                     ph[k_] = ph.get(k_, 0.0) + v / args.steps
-                if step == args.steps - 1:
+                if step == args.steps - 1:  # the first two and the last two replicate columns of this rank
                     cols = [reps.download_cols(s, 0, 2) for s in (0, len(RR) - 1)] + \
-                           [reps.download_cols(len(RR) - 1, int(bb[-1]) - 2, 2)]
+                           [reps.download_cols(len(RR) - 1, max(0, b1 - b0 - 2), min(2, b1 - b0))]
                 reps.free()
             t = float(np.mean(ms))
             out.update({"ms_per_step": t, "value": acc / (t * 1e-3), "unit": UNIT, "steps": args.steps,
-                        "draws_per_s_through_draw_and_histogram": draws / ((ph["rng"] + ph["resample"]) * 1e-3),
-                        "phases_ms_per_step": ph})
+                        "timing": "CUDA events on the library stream (cgpu_last_timing), max over ranks",
+                        "draws_per_s_per_gpu_through_draw_and_histogram": draws / world / ((ph["rng"] + ph["resample"]) * 1e-3),
+                        "phases_ms_per_step_rank0": ph})
             if first is None:
                 first = cols
-                # the oracle's stream and site indices for replicate 0 of scale 0, exact sums by math.fsum
-                from oracle import oracle as orc
-                y = orc.mt_stream(7, 0, int(bn[0]))
-                cnt = np.bincount(orc.site_indices(y, n), minlength=n)[None, :]
-                kt = np.array([0, K - 1])
-                want = exact_sums(L[kt], cnt, float(bn[0]) / float(n))
-                out["spot_check"] = {"bit_equal_to_exact_rounded_sums": bool(np.array_equal(cols[0][kt, :1], want)),
-                                     "what": "replicate 0 of scale 0, first and last tree: MT19937 draws and site indices by the "
-                                             "oracle, exact sums by math.fsum"}
+                if rank == 0:
+                    # the oracle's stream and site indices for replicate 0 of scale 0, exact sums by math.fsum
+                    from oracle import oracle as orc
+                    y = orc.mt_stream(7, 0, int(bn[0]))
+                    cnt = np.bincount(orc.site_indices(y, n), minlength=n)[None, :]
+                    kt = np.array([0, K - 1])
+                    want = exact_sums(L[kt], cnt, float(bn[0]) / float(n))
+                    out["spot_check"] = {"bit_equal_to_exact_rounded_sums": bool(np.array_equal(cols[0][kt, :1], want)),
+                                         "what": "replicate 0 of scale 0, first and last tree: MT19937 draws and site indices by "
+                                                 "the oracle, exact sums by math.fsum"}
             else:
-                out["identical_to_default_histogram"] = bool(all(np.array_equal(a, b) for a, b in zip(first, cols)))
+                same = all(np.array_equal(a_, b_) for a_, b_ in zip(first, cols))
+                out["identical_to_default_histogram"] = bool(max_over_ranks(0.0 if same else 1.0) == 0.0)
         except Exception as e:
             out["error"] = f"{type(e).__name__}: {e}"
-        print(json.dumps(out), flush=True)
+        say(out)
     cg.set_option("hist_bucket", -1)
+    if world > 1:
+        dist.destroy_process_group()
 
 
-def side_c4_from(parent_args) -> dict:
-    """runs `bench.py --side c4` as its own process with a time limit and collects its lines; never raises"""
-    limit = float(os.environ.get("BENCH_SIDE_TIMEOUT_S", "240"))
-    cmd = [sys.executable, str(Path(__file__).resolve()), "--side", "c4", "--steps", "2"]
-    env = {k_: v for k_, v in os.environ.items() if k_ not in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "LOCAL_WORLD_SIZE")}
+def _free_port() -> int:
+    import socket
+    with socket.socket() as so:
+        so.bind(("127.0.0.1", 0))
+        return int(so.getsockname()[1])
+
+
+def side_c4_from(parent_args, world: int = 1) -> dict:
+    """runs `bench.py --side c4` as its own process (world 1) or its own torchrun job (world 8: every other rank
+    of the parent job has exited by now) with a time limit and collects its lines; never raises"""
+    limit = float(os.environ.get("BENCH_SIDE_TIMEOUT_S", "200"))
+    me = str(Path(__file__).resolve())
+    if world > 1:
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+               "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), me, "--side", "c4", "--steps", "2"]
+    else:
+        cmd = [sys.executable, me, "--side", "c4", "--steps", "2"]
+    scrub = ("RANK", "WORLD_SIZE", "LOCAL_RANK", "LOCAL_WORLD_SIZE", "GROUP_RANK", "GROUP_WORLD_SIZE", "ROLE_RANK",
+             "ROLE_WORLD_SIZE", "ROLE_NAME", "MASTER_ADDR", "MASTER_PORT", "OMP_NUM_THREADS")
+    env = {k_: v for k_, v in os.environ.items() if k_ not in scrub and not k_.startswith("TORCHELASTIC_")}
     t0 = time.perf_counter()
     text, status = "", "ok"
     try:
-        p = subprocess.run(cmd, capture_output=True, text=True, timeout=limit, env=env, cwd=str(ROOT))
-        text = p.stdout
-        if p.returncode != 0:
-            status = f"exit status {p.returncode}: {p.stderr.strip().splitlines()[-1][:300] if p.stderr.strip() else ''}"
-    except subprocess.TimeoutExpired as e:
-        text = e.stdout.decode() if isinstance(e.stdout, bytes) else (e.stdout or "")
-        status = f"time limit of {limit:.0f} s reached: the variants printed so far are kept"
+        # its own process group: on a time-out the whole job (torchrun agent and ranks) is killed, not just its head
+        p = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env, cwd=str(ROOT),
+                             start_new_session=True)
+        try:
+            text, err = p.communicate(timeout=limit)
+            if p.returncode != 0:
+                tail = [t for t in err.strip().splitlines() if "Error" in t or "error" in t] or err.strip().splitlines() or [""]
+                status = f"exit status {p.returncode}: {tail[-1].strip()[:300]}"
+        except subprocess.TimeoutExpired:
+            import signal
+            try:
+                os.killpg(p.pid, signal.SIGKILL)
+            except Exception:
+                p.kill()
+            text, _ = p.communicate()
+            status = f"time limit of {limit:.0f} s reached: the variants printed so far are kept"
     except Exception as e:
         status = f"{type(e).__name__}: {e}"
     variants = []
-    for ln in text.splitlines():
+    for ln in (text or "").splitlines():
         if ln.startswith("{"):
             try:
                 variants.append(json.loads(ln))
             except ValueError:
                 pass
-    return {"what": "C4 (BASELINE.json configs[3]: K=100 x n=10^7, an 8-GPU job) -- one GPU's share, 1250 replicates per scale, "
-                    "MT19937 stream + int8 sums, in a process of its own after the default line was measured; "
-                    "`bucketed` is the first hardware run of csrc/hist_bucket.cuh",
+    return {"what": "C4 (BASELINE.json configs[3]: K=100 x n=10^7, 10 x 10^4 replicates, an 8-GPU job), MT19937 stream + int8 sums, "
+                    + ("the whole job as 8 ranks" if world == 8 else "one GPU's share of it (1250 replicates per scale)")
+                    + ", in a process of its own after the default line was measured; `bucketed` is the first hardware run of "
+                      "csrc/hist_bucket.cuh",
             "status": status, "seconds": round(time.perf_counter() - t0, 1), "variants": variants}
 
 

@@ -217,7 +217,7 @@ def test_auxiliary_legs_cannot_cost_the_headline_line(monkeypatch, capsys, orc):
     # the side leg of the default workload (its own process on the GPU box) is walked too: here the default is C1
     # and the child is a stub, what is checked is the parent's branch (buffers released, result attached)
     monkeypatch.setattr(bench, "DEFAULT_CONFIG", "C1")
-    monkeypatch.setattr(bench, "side_c4_from", lambda a: {"status": "stub", "variants": []})
+    monkeypatch.setattr(bench, "side_c4_from", lambda a, w=1: {"status": "stub", "variants": []})
     bench.run_ours(types.SimpleNamespace(gpus=1, steps=2, warmup=3, impl="ours", config="C1"))
     lines = [t for t in capsys.readouterr().out.splitlines() if t.strip()]
     assert len(lines) == 1
@@ -246,7 +246,7 @@ def test_side_c4_leg_on_the_emulated_library(monkeypatch, capsys, emu_cg):
     assert "error" not in lines[1] and "error" not in lines[2], lines
     assert lines[1]["spot_check"]["bit_equal_to_exact_rounded_sums"] is True
     assert lines[2]["identical_to_default_histogram"] is True
-    assert lines[1]["value"] > 0 and lines[2]["phases_ms_per_step"]["n_hist"] > 0
+    assert lines[1]["value"] > 0 and lines[2]["phases_ms_per_step_rank0"]["n_hist"] > 0
 
 
 def test_side_c4_collector_keeps_what_was_printed(monkeypatch, tmp_path):
@@ -255,18 +255,64 @@ def test_side_c4_collector_keeps_what_was_printed(monkeypatch, tmp_path):
     import subprocess as sp
     import types
 
-    real_run = sp.run
+    real_popen = sp.Popen
     script = tmp_path / "child.py"
 
     def fake(mode):
-        def run(cmd, **kw):
+        def popen(cmd, **kw):
             script.write_text("import json, sys, time\nprint(json.dumps({'side': 'C4', 'variant': 'a', 'value': 1.0}), flush=True)\n"
                               + ("time.sleep(60)\n" if mode == "hang" else "sys.stderr.write('boom\\n'); sys.exit(3)\n"))
-            return real_run([sys.executable, str(script)], **kw)
-        return run
+            return real_popen([sys.executable, str(script)], **kw)
+        return popen
     monkeypatch.setenv("BENCH_SIDE_TIMEOUT_S", "3")
     for mode, word in (("die", "exit status 3: boom"), ("hang", "time limit")):
-        monkeypatch.setattr(bench.subprocess, "run", fake(mode))
-        out = bench.side_c4_from(types.SimpleNamespace())
+        monkeypatch.setattr(bench.subprocess, "Popen", fake(mode))
+        out = bench.side_c4_from(types.SimpleNamespace(), 8 if mode == "hang" else 1)
         assert word in out["status"], out
         assert out["variants"] == [{"side": "C4", "variant": "a", "value": 1.0}]
+
+
+def test_side_c4_leg_as_two_ranks_on_the_emulated_library(emu_lib, tmp_path):
+    """the multi-rank form of the leg (the 8-rank job the 8-GPU bench starts), here as 2 ranks over gloo on the
+    CPU: every rank resamples its own replicate columns, rank 0 prints, the spot check and the bucketed == default
+    comparison hold"""
+    import os
+    import socket
+    import subprocess as sp
+
+    worker = tmp_path / "worker.py"
+    worker.write_text(f"""
+import ctypes as C, sys, types
+sys.path.insert(0, {str(ROOT)!r})
+import torch
+torch.cuda.set_device = lambda d: None
+import consel_b200 as cg
+from consel_b200 import api
+lib = C.CDLL({str(emu_lib._path)!r})
+lib.cgpu_last_error.restype = C.c_char_p
+lib.cgpu_launch_count.restype = C.c_longlong
+lib.cgpu_smooth_count.restype = C.c_double
+api._lib = lib
+real_init = cg.init
+import bench
+bench_cg_init = lambda d=-1: real_init()
+cg.init = bench_cg_init
+bench.run_side_c4(types.SimpleNamespace(steps=1, side_reps=6, side_sites=300000, side_trees=3))
+""")
+    with socket.socket() as so:
+        so.bind(("127.0.0.1", 0))
+        port = so.getsockname()[1]
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", LOCAL_RANK=str(r), LOCAL_WORLD_SIZE="2", MASTER_ADDR="127.0.0.1",
+                   MASTER_PORT=str(port))
+        procs.append(sp.Popen([sys.executable, str(worker)], env=env, stdout=sp.PIPE, stderr=sp.PIPE, text=True))
+    outs = [p.communicate(timeout=600) for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert not [t for t in outs[1][0].splitlines() if t.startswith("{")], "only rank 0 prints"
+    lines = [json.loads(t) for t in outs[0][0].splitlines() if t.startswith("{")]
+    assert [x["variant"] for x in lines] == ["setup", "global_atomics (default)", "bucketed (hist_bucket=1)"]
+    assert lines[0]["n_gpus"] == 2 and lines[0]["replicates_per_scale_per_gpu"] == 3
+    assert "error" not in lines[1] and "error" not in lines[2], lines
+    assert lines[1]["spot_check"]["bit_equal_to_exact_rounded_sums"] is True
+    assert lines[2]["identical_to_default_histogram"] is True
