@@ -685,6 +685,11 @@ def run_side_c4(args) -> None:
     for label, opt in (("global_atomics (default)", 0), ("bucketed (hist_bucket=1)", 1)):
         cg.set_option("hist_bucket", opt)
         out = {"side": "C4", "variant": label, "n_gpus": world}
+        late = max_over_ranks(time.perf_counter() - t_start) > float(os.environ.get("BENCH_SIDE_SECOND_VARIANT_BY_S", "80"))
+        if opt and late:  # the leg is a side line: it must not stretch the bench run
+            out["skipped"] = "the default variant took too long for a second one inside the leg's time budget"
+            say(out)
+            continue
         try:
             mat.scaleboot(bn, bb, 7, rng_mode=cg.RNG_MT19937, sum_mode=cg.SUM_INT8).free()  # warm-up (fixed-point slices, pools)
             ms, ph = [], {}
@@ -738,7 +743,7 @@ def _free_port() -> int:
 def side_c4_from(parent_args, world: int = 1) -> dict:
     """runs `bench.py --side c4` as its own process (world 1) or its own torchrun job (world 8: every other rank
     of the parent job has exited by now) with a time limit and collects its lines; never raises"""
-    limit = float(os.environ.get("BENCH_SIDE_TIMEOUT_S", "200"))
+    limit = float(os.environ.get("BENCH_SIDE_TIMEOUT_S", "150"))
     me = str(Path(__file__).resolve())
     if world > 1:
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
