@@ -557,17 +557,8 @@ def run_ours(args) -> None:
                                 "device-resident step (draws + histograms + GEMMs)"}
     roofline["kernels"] = kernels
 
-    # ---- CPU baseline: the oracle port, single thread, bounded sample (~10-20 s)
-    try:
-        from oracle import oracle as orc
-        b_cpu = max(1, int(2.4e10 / (K * N_SITES * len(RR))))
-        t0 = time.perf_counter()
-        orc.makermt(L, bn, [b_cpu] * len(RR), 7)
-        t_cpu = time.perf_counter() - t0
-        cpu_baseline = {"value": K * N_SITES * b_cpu * len(RR) / t_cpu, "unit": UNIT, "cores": 1, "kind": "port",
-                        "sample": f"same matrix and scales, {b_cpu} replicates per scale ({t_cpu:.1f} s of oracle/oracle.c)"}
-    except Exception as e:
-        cpu_baseline = {"error": f"{type(e).__name__}: {e}", "unit": UNIT, "cores": 1, "kind": "port"}
+    # ---- CPU baseline: the reference's own scaleboot() on ONE host core, bounded sample (~10-20 s)
+    cpu_baseline = cpu_baseline_leg(L, bn, K, N_SITES)
 
     # ---- side leg (N=1, default workload only): the per-GPU share of C4 in a process of its own
     side_c4 = None
@@ -605,6 +596,41 @@ def run_ours(args) -> None:
     if side_c4 is not None:
         line["side_c4"] = side_c4
     print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------ CPU baseline leg
+CPU_BASELINE_ACC = 2.4e10  # tree-site accumulations of the sample: ~20 s of one core
+
+
+def cpu_baseline_leg(L: np.ndarray, bn, K: int, n: int) -> dict:
+    """single-threaded CPU baseline on a bounded sample of the same workload (same matrix, all ten scales): the
+    UNMODIFIED reference's scaleboot() (src/makermt.c:35-75, compiled into oracle/_ref/libmakermt_ref.so) driven
+    the way genrmt drives it (one seeded MT19937 stream, scale after scale) when that library was built
+    (`kind: reference`), else the oracle's C restatement (`kind: port`).  Never raises."""
+    try:
+        from oracle import oracle as orc
+        b_cpu = max(1, int(CPU_BASELINE_ACC / (K * n * len(RR))))
+        so = orc.REF_DIR / "libmakermt_ref.so"
+        if so.exists():
+            global _REF_L
+            _REF_L = np.ascontiguousarray(L, dtype=np.float64)
+            try:
+                t_cpu = 0.0
+                for s_ in range(len(RR)):
+                    dt, _ = _ref_worker((str(so), K, n, int(bn[s_]), b_cpu, 7), seed_it=(s_ == 0))
+                    t_cpu += dt
+            finally:
+                _REF_L = None
+            kind, what = "reference", "unmodified src/makermt.c:35-75 scaleboot(), -O2, oracle/_ref/libmakermt_ref.so"
+        else:
+            t0 = time.perf_counter()
+            orc.makermt(L, bn, [b_cpu] * len(RR), 7)
+            t_cpu = time.perf_counter() - t0
+            kind, what = "port", "oracle/oracle.c"
+        return {"value": K * n * b_cpu * len(RR) / t_cpu, "unit": UNIT, "cores": 1, "kind": kind,
+                "sample": f"same matrix and scales, {b_cpu} replicates per scale ({t_cpu:.1f} s of {what})"}
+    except Exception as e:
+        return {"error": f"{type(e).__name__}: {e}", "unit": UNIT, "cores": 1, "kind": "port"}
 
 
 # ------------------------------------------------------------------------ side leg: C4
@@ -792,8 +818,9 @@ def side_c4_from(parent_args, world: int = 1) -> dict:
 _REF_L = None  # the matrix of the in-process reference arm: set before the pool forks, inherited copy-on-write
 
 
-def _ref_worker(args):
-    """one host process of the in-process reference arm: scaleboot() of the unmodified makermt.c"""
+def _ref_worker(args, seed_it: bool = True):
+    """one host process of the in-process reference arm: scaleboot() of the unmodified makermt.c
+    (seed_it False: the MT19937 stream continues where the previous call left it, as between the scales of genrmt)"""
     import ctypes as C
     so, K, n, bn, b_each, seed = args
     lib = C.CDLL(so)
@@ -803,7 +830,8 @@ def _ref_worker(args):
     orow = (C.POINTER(C.c_double) * K)(*[C.cast(out.ctypes.data + 8 * b_each * k, C.POINTER(C.c_double)) for k in range(K)])
     lib.smrand.argtypes = [C.c_ulong]
     lib.scaleboot.restype = C.c_void_p
-    lib.smrand(int(seed))
+    if seed_it:
+        lib.smrand(int(seed))
     t0 = time.perf_counter()
     lib.scaleboot(rows, orow, K, n, int(bn), int(b_each))
     dt = time.perf_counter() - t0

@@ -115,8 +115,7 @@ def test_run_ours_prints_the_contract_line(monkeypatch, capsys, orc, clocks_low)
                     "reasons": ["sw_power_cap"] if clocks_low else [], "samples": 9}
     monkeypatch.setattr(bench, "ClockSampler", _Sampler)
     # the CPU baseline leg is the real oracle; keep its sample small here
-    real_makermt = orc.makermt
-    monkeypatch.setattr(orc, "makermt", lambda L, bn, bb, seed: real_makermt(L, bn, [min(int(b), 50) for b in bb], seed))
+    monkeypatch.setattr(bench, "CPU_BASELINE_ACC", 15 * 3414 * 10 * 50.0)  # 50 replicates per scale
     for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
         monkeypatch.delenv(k, raising=False)
 
@@ -151,7 +150,8 @@ def test_run_ours_prints_the_contract_line(monkeypatch, capsys, orc, clocks_low)
     assert 0.0 < r["step"]["frac"] and r["step"]["ms_per_step"] == pytest.approx(2.0)
     # ---- cpu baseline, spot check, side modes, pipeline
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] == 1 and cb["value"] > 0 and "sample" in cb
+    assert cb["kind"] == ("reference" if (orc.REF_DIR / "libmakermt_ref.so").exists() else "port")
+    assert cb["cores"] == 1 and cb["value"] > 0 and "50 replicates per scale" in cb["sample"]
     assert d["spot_check"]["ok"] is True and d["spot_check"]["bit_equal_to_exact_rounded_sums"] is True
     assert set(d["modes"]) == {"strict_mt", "fast_mt", "int8_philox"}
     p = d["pipeline"]
@@ -212,6 +212,7 @@ def test_auxiliary_legs_cannot_cost_the_headline_line(monkeypatch, capsys, orc):
     monkeypatch.setattr(pipeline, "run", boom)
     monkeypatch.setattr(bench, "ClockSampler", lambda idx: types.SimpleNamespace(start=lambda: None, stop=lambda: None))
     monkeypatch.setattr(orc, "makermt", boom)
+    monkeypatch.setattr(bench, "_ref_worker", boom)
     for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"):
         monkeypatch.delenv(k, raising=False)
     # the side leg of the default workload (its own process on the GPU box) is walked too: here the default is C1

@@ -46,3 +46,32 @@ def test_synthetic_matrix_is_reproducible_and_row_blocked():
     b = bench.synth_matrix(37, 501)
     assert a.shape == (37, 501) and np.array_equal(a, b)
     assert -60.0 < a.min() < a.max() < 0.0
+
+
+def test_cpu_baseline_drives_the_reference_scaleboot_like_genrmt(orc, monkeypatch):
+    """bench.cpu_baseline_leg calls the unmodified scaleboot() scale after scale on ONE seeded MT19937 stream
+    (src/makermt.c:196-207): the replicate sums are the oracle's, i.e. the .rmt payload of `makermt -s 7`"""
+    import numpy as np
+    import pytest
+
+    import bench
+    so = orc.REF_DIR / "libmakermt_ref.so"
+    if not so.exists():
+        pytest.skip("oracle/_ref/libmakermt_ref.so not built")
+    rng = np.random.default_rng(3)
+    K, n = 4, 500
+    L = -np.exp(rng.uniform(-1, 3, size=(K, n)))
+    rr, bb = [0.5, 1.0, 1.4], [5, 5, 5]
+    _, bn, _ = orc.scale_setup(L, rr)
+    want = orc.makermt(L, bn, bb, 7)
+    bench._REF_L = np.ascontiguousarray(L)
+    try:
+        for s in range(len(rr)):
+            _, out = bench._ref_worker((str(so), K, n, int(bn[s]), bb[s], 7), seed_it=(s == 0))
+            assert np.array_equal(out, want[s])
+    finally:
+        bench._REF_L = None
+    _, bn10, _ = orc.scale_setup(L, bench.RR)
+    monkeypatch.setattr(bench, "CPU_BASELINE_ACC", 4 * 500 * 10 * 200.0)
+    line = bench.cpu_baseline_leg(L, bn10, K, n)
+    assert line.get("kind") == "reference" and line["cores"] == 1 and line["value"] > 0, line
