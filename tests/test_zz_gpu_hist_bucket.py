@@ -19,6 +19,6 @@ ROOT = Path(__file__).resolve().parent.parent
 @pytest.mark.xfail(strict=False, reason="first execution on hardware (opt-in path, written without GPU access)")
 def test_bucketed_histogram_matches_the_verified_kernels():
     r = subprocess.run([sys.executable, str(ROOT / "tests" / "gpu_hist_bucket_check.py")], capture_output=True, text=True,
-                       timeout=900, cwd=ROOT)
+                       timeout=300, cwd=ROOT)
     print(r.stdout[-2000:], r.stderr[-2000:])
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
