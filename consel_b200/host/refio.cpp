@@ -156,7 +156,12 @@ namespace {
 // isspace of the "C" locale as an inline test (the parsers below call it once per byte)
 inline bool is_space(unsigned char c) { return c == ' ' || (c >= '\t' && c <= '\r'); }
 
-int io_threads() { return (int)std::max(1u, std::min(64u, std::thread::hardware_concurrency())); }
+int io_threads() {
+    unsigned hw = std::thread::hardware_concurrency();
+    // one process per GPU shares the host: torchrun exports LOCAL_WORLD_SIZE
+    if (const char *e = getenv("LOCAL_WORLD_SIZE")) hw /= (unsigned)std::max(1, atoi(e));
+    return (int)std::max(1u, std::min(64u, hw));
+}
 
 struct FileTail {
     std::unique_ptr<char[]> buf;
@@ -459,7 +464,7 @@ static bool read_paml_blocks_parallel(FILE *fp, int m, int n, int p, double *out
     const size_t need = (size_t)m * ((size_t)p + 1);
     bool ok = line.size() >= need;
     if (ok) {
-        const int nthr = (int)std::max(1u, std::min(64u, std::min<unsigned>(std::thread::hardware_concurrency(), (unsigned)m)));
+        const int nthr = std::max(1, std::min(io_threads(), m));
         std::vector<char> good(nthr, 1);
         auto tok_int = [&](const char *&c, long long *v) {
             while (*c == ' ' || *c == '\t' || *c == '\r') c++;
