@@ -919,7 +919,9 @@ int main(int argc, char **argv) {
     }
 
     if (inrep && !doau) outrep = outcnt = false;  // do_repmode writes them only after the AU test (:1236-1240)
-    if (outcnt && (doau || dobp)) {
+    // cntmat exists only when the AU test ran (do_bootrep allocates it, src/consel.c:1464, 1502-1507): without it
+    // -- a single scale (:868), --no_au -- write_cnt2 (:1770) emits the CNT header alone
+    if (outcnt && doau) {
         cntmat.resize((size_t)cm * kk);
         for (int i = 0; i < cm; i++)
             for (int k = 0; k < kk; k++) {
@@ -1007,9 +1009,13 @@ int main(int argc, char **argv) {
             st[k].resize((size_t)cm * bb[k]);
             ptrs[k] = st[k].data();
         }
-        // the reference writes the rows after do_bootrep/do_bptest sorted them in place
-        const bool sorted = doau || dobp;
-        CG(cgpu_stats_download(reps, sorted ? 1 : 0, ptrs.data()));
+        // The reference writes the rows in whatever state its tests left them: do_bootrep sorts every row of every
+        // scale in place (src/consel.c:1466-1471); without the AU test only do_bptest touches them -- its pvaldist
+        // sorts the rows of scale i0 alone (:1298, cntdist mode 4 :1870), and not at all under --quick_mctest
+        // (sw_pvaldist = 0, :323).
+        CG(cgpu_stats_download(reps, doau ? 1 : 0, ptrs.data()));
+        if (!doau && dobp && !quickmc)
+            for (int j = 0; j < cm; j++) std::sort(st[i0].begin() + (size_t)j * bb[i0], st[i0].begin() + (size_t)(j + 1) * bb[i0]);
         const std::string repbase = (inrep && fname_in) ? std::string(fname_in) : outbase;  // fname_rep (:438, :443)
         if (fname_out) {
             FILE *fp = open_file(repbase.c_str(), ".rep", "wb", &used);
@@ -1034,7 +1040,7 @@ int main(int argc, char **argv) {
             for (int k = 0; k < kk; k++) write_mat(stdout, st[k].data(), cm, bb[k]);
         }
     }
-    if (outcnt && !cntmat.empty()) {
+    if (outcnt) {
         FILE *fp = stdout;
         if (fname_out) {
             fp = open_file(fname_out, ".cnt", "w", &used);
@@ -1052,7 +1058,7 @@ int main(int argc, char **argv) {
         fprintf(fp, "\n# STAT:\n"); write_vec(fp, obsvec.data(), cm);
         fprintf(fp, "\n# R:\n"); write_mat(fp, rrmat.data(), cm, kk);
         fprintf(fp, "\n# B:\n"); write_mat(fp, bbmat.data(), cm, kk);
-        fprintf(fp, "\n# CNT:\n"); write_mat(fp, cntmat.data(), cm, kk);
+        fprintf(fp, "\n# CNT:\n"); write_mat(fp, cntmat.empty() ? nullptr : cntmat.data(), cm, kk);
         if (fname_out) fclose(fp);
     }
     cgpu_reps_free(reps);

@@ -27,7 +27,12 @@ void die(const char *fmt, ...) {
     vprintf(fmt, ap);
     printf(".\n");
     va_end(ap);
-    exit(1);
+    // The reference is single-threaded and calls exit(1) (src/misc.c:40-49).  Here the message may come from a
+    // worker thread of the fit pool: exit() would run the static destructors -- the pool joining its own thread --
+    // and abort.  Flush every open stream (the stdout protocol line, partially written output files: what exit()
+    // would have done for them) and leave without unwinding; the status is the reference's.
+    fflush(nullptr);
+    _exit(1);
 }
 
 void warn(const char *fmt, ...) {

@@ -1,0 +1,86 @@
+"""Edge cases of the consel command line found by the randomised differential run (tools/emu_stress.py): the
+product's consel (its own sources on the emulated device library, conftest.emu_bin) against the UNMODIFIED
+reference binary on the same .rmt, file by file.
+
+  * no AU test (a single scale, src/consel.c:868; or --no_au): the .cnt file carries the CNT header alone (cntmat
+    is allocated by do_bootrep only, :1464 / :1770) and the .rep rows are in whatever state the tests left them --
+    do_bptest's pvaldist sorts the rows of scale i0 only (:1298, :1870), nothing is sorted under --quick_mctest (:323)
+  * a fit that ends in the reference's error() (`a too large, ITMAX too small in gcf`, raised inside the fit that
+    here runs on a pool thread): `#! Terminated: ...` on stdout and exit status 1, not an abort"""
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+@pytest.fixture(scope="module")
+def progs(emu_bin, orc):
+    if orc.ref_bin("consel") is None or orc.ref_bin("makermt") is None:
+        pytest.skip("oracle/_ref not built")
+    return emu_bin
+
+
+def make_rmt(orc, d: Path, seed: int, K: int, n: int, rr, bb, sd: float):
+    rng = np.random.default_rng(seed)
+    base = -2.3 - 4.07 * rng.exponential(size=n)
+    L = base[None, :] + sd * rng.standard_normal((K, n))
+    orc.write_mt(d / "in.mt", L)
+    orc.write_pa(d / "p.pa", rr, bb)
+    orc.run_ref("makermt", ["-s", seed, "-p", "p", "in", "x"], d)
+
+
+def both(progs, orc, d: Path, args, tag):
+    r = subprocess.run([str(orc.ref_bin("consel"))] + args + ["x", f"r{tag}"], cwd=d, capture_output=True, text=True)
+    o = subprocess.run([str(progs / "consel")] + args + ["x", f"o{tag}"], cwd=d, capture_output=True, text=True)
+    return r, o
+
+
+def same_files(orc, d: Path, tag, binary=("rep", "cnt"), text=("pv", "ci")):
+    for ext in binary:
+        a, b = d / f"o{tag}.{ext}", d / f"r{tag}.{ext}"
+        assert a.exists() == b.exists(), ext
+        if b.exists():
+            assert a.read_bytes() == b.read_bytes(), ext
+    for ext in text:
+        a, b = d / f"o{tag}.{ext}", d / f"r{tag}.{ext}"
+        assert a.exists() == b.exists(), ext
+        if b.exists():
+            x, y = orc.read_text_blocks(a), orc.read_text_blocks(b)
+            assert len(x) == len(y) and np.allclose(x, y, rtol=2e-9, atol=1e-12, equal_nan=True), ext
+
+
+@pytest.mark.parametrize("extra", [[], ["--quick_mctest"], ["--smooth_cnt"]])
+def test_single_scale_skips_the_au_test_like_the_reference(progs, orc, tmp_path, extra):
+    make_rmt(orc, tmp_path, 5, 7, 120, [1.0], [90], 0.106)
+    r, o = both(progs, orc, tmp_path, extra + ["-r", "-c"], "a")
+    assert r.returncode == 0 and o.returncode == 0, o.stdout[-500:]
+    assert "AU-TEST" not in o.stdout
+    same_files(orc, tmp_path, "a")
+    assert not (tmp_path / "oa.ci").exists()
+
+
+@pytest.mark.parametrize("extra", [["--no_au"], ["--no_au", "--quick_mctest"], ["--no_au", "--no_bp"], ["--no_au", "--no_sh", "--no_pp"]])
+def test_no_au_leaves_rep_and_cnt_as_the_reference_does(progs, orc, tmp_path, extra):
+    make_rmt(orc, tmp_path, 9, 6, 200, [0.6, 1.0, 1.4], [70, 80, 60], 0.106)
+    r, o = both(progs, orc, tmp_path, extra + ["-r", "-c"], "b")
+    assert r.returncode == o.returncode == 0, o.stdout[-500:]
+    same_files(orc, tmp_path, "b")
+
+
+def test_fit_failure_terminates_like_the_reference(progs, orc, tmp_path):
+    rng = np.random.default_rng(66)
+    K, n = int(rng.integers(4, 10)), int(rng.integers(30, 200))
+    base = -2.3 - 4.07 * rng.exponential(size=n)
+    L = base[None, :] + 1.0 * rng.standard_normal((K, n))
+    rr = np.sort(np.concatenate([np.round(rng.uniform(0.3, 0.7, 3), 2), np.round(rng.uniform(1.4, 2.0, 5), 2)]))
+    bb = rng.integers(20, 120, size=8)
+    orc.write_mt(tmp_path / "in.mt", L)
+    orc.write_pa(tmp_path / "p.pa", rr, bb)
+    orc.run_ref("makermt", ["-s", 66, "-p", "p", "in", "x"], tmp_path)
+    r, o = both(progs, orc, tmp_path, [], "c")
+    assert r.returncode == 1 and "#! Terminated: a too large, ITMAX too small in gcf." in r.stdout, "the recipe no longer fails in the reference"
+    assert o.returncode == 1, (o.returncode, o.stdout[-300:], o.stderr[-300:])
+    assert "#! Terminated: a too large, ITMAX too small in gcf." in o.stdout

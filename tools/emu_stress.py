@@ -1,0 +1,164 @@
+#!/usr/bin/env python
+"""Randomised differential test on the CPU: the product's makermt / consel programs (their own sources linked
+against the EMULATED device library, tests/emu/) against the UNMODIFIED reference binaries (oracle/_ref) on random
+small inputs -- random tree / site counts, scale sets, replicate counts, tied rows and columns, random edge
+associations, the -f / -R / --quick_mctest variants.  `.rmt` `.vt` `.rep` `.cnt` must be byte-equal, `.pv` `.ci`
+equal to the printed digits.
+
+    python tools/emu_stress.py [SEED=1] [CASES=50] [workdir=/tmp/emu_stress]      (EMU_STRESS_KEEP=1 keeps every case directory)
+"""
+import os
+import shutil
+import subprocess
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent.parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "tests" / "emu"))
+from oracle import oracle as orc  # noqa: E402
+
+
+def build_programs(work: Path) -> Path:
+    import build_emu_lib
+    lib = build_emu_lib.build(work / "lib")
+    host = ROOT / "consel_b200" / "host"
+    out = work / "bin"
+    out.mkdir(exist_ok=True)
+    programs = {"consel": ["consel.cpp", "pipeline.cpp", "audriver.cpp", "aufit.cpp", "specfun.cpp", "refio.cpp"],
+                "makermt": ["makermt.cpp", "refio.cpp"], "makerep": ["makerep.cpp", "refio.cpp"]}
+    for prog, srcs in programs.items():
+        subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-pthread", "-w", "-o", str(out / prog),
+                        *[str(host / f) for f in srcs], f"-L{lib.parent}", "-lconselgpu_emu", f"-Wl,-rpath,{lib.parent}", "-lm"],
+                       check=True)
+    return out
+
+
+def write_ass(path: Path, sets):
+    with open(path, "w") as f:
+        f.write(f"\n# EDGE->TREE\n{len(sets)}\n")
+        for i, s in enumerate(sets):
+            f.write(f"\n# item: {i}\n#!VEC:\n{len(s)}\n" + " ".join(f"{int(x):10d}" for x in s) + " \n")
+
+
+def numbers_equal(a: Path, b: Path) -> bool:
+    x, y = orc.read_text_blocks(a), orc.read_text_blocks(b)
+    return len(x) == len(y) and bool(np.allclose(x, y, rtol=2e-9, atol=1e-12, equal_nan=True))
+
+
+STATS = {"variants": 0, "both_ok": 0, "both_refused": 0}
+
+
+def one_case(rng, bindir: Path, d: Path) -> list:
+    bad = []
+    K = int(rng.integers(2, 15))
+    n = int(rng.choice([int(rng.integers(3, 40)), int(rng.integers(40, 700))]))
+    base = -2.3 - 4.07 * rng.exponential(size=n)
+    L = base[None, :] + rng.choice([0.01, 0.106, 1.0]) * rng.standard_normal((K, n))
+    if rng.random() < 0.3 and K > 2:
+        L[int(rng.integers(1, K))] = L[0]                       # tied trees
+    if rng.random() < 0.3 and n > 4:
+        L[:, int(rng.integers(1, n))] = L[:, 0]                 # repeated site pattern
+    if rng.random() < 0.2:
+        L = np.round(L, 3)                                      # few significant digits
+    kk = int(rng.integers(1, 12))
+    rr = np.sort(np.round(rng.uniform(0.3, 2.0, size=kk), 2))
+    if rng.random() < 0.7:
+        rr[int(rng.integers(0, kk))] = 1.0
+        rr = np.sort(rr)
+    bb = rng.integers(2, 250, size=kk)
+    seed = int(rng.integers(1, 10**6))
+    orc.write_mt(d / "in.mt", L)
+    orc.write_pa(d / "p.pa", rr, bb)
+    desc = f"K={K} n={n} kk={kk} rr={rr.tolist()} bb={bb.tolist()} seed={seed}"
+
+    def ours(prog, args):
+        r = subprocess.run([str(bindir / prog)] + [str(a) for a in args], cwd=d, capture_output=True, text=True)
+        return r.returncode, r.stdout
+
+    def ref(prog, args):
+        r = subprocess.run([str(orc.ref_bin(prog))] + [str(a) for a in args], cwd=d, capture_output=True, text=True)
+        return r.returncode, r.stdout
+
+    ra, _ = ref("makermt", ["-s", seed, "-p", "p", "in", "ref"])
+    oa, oout = ours("makermt", ["-s", seed, "-p", "p", "in", "our"])
+    if ra != oa:
+        return [f"makermt exit status {oa} vs reference {ra}: {desc}\n{oout[-400:]}"]
+    if ra != 0:
+        return []
+    for ext in ("rmt", "vt"):
+        if (d / f"our.{ext}").read_bytes() != (d / f"ref.{ext}").read_bytes():
+            bad.append(f".{ext} differs: {desc}")
+    # consel variants on the REFERENCE's .rmt (so that a makermt difference does not cascade)
+    shutil.copy(d / "ref.rmt", d / "x.rmt")
+    variants = [([], "plain")]
+    if rng.random() < 0.5:
+        nass = int(rng.integers(1, 8))
+        sets = [sorted(rng.choice(K, size=int(rng.integers(1, K)), replace=False).tolist()) for _ in range(nass)]
+        write_ass(d / "a.ass", sets)
+        variants.append((["-a", "a"], f"assoc {sets}"))
+    if rng.random() < 0.4:
+        variants.append((["-f"], "rescaling approximation"))
+    if rng.random() < 0.3:
+        variants.append((["--quick_mctest"], "quick mctest"))
+    # a random handful of the switches that select tests, smoothing, sorting and fit parameters
+    pool = [["--no_au"], ["--no_bp"], ["--no_pp"], ["--no_sh"], ["--smooth_cnt"], ["--no_sort"], ["--wls"],
+            ["--th", f"{rng.uniform(-2, 2):.3f}"], ["--kappa", f"{rng.uniform(0.5, 1.5):.2f}"], ["--rmin", "0.5"], ["--rmax", "1.5"],
+            ["-t", f"{rng.uniform(0.2, 2):.2f}"], ["--cieps", "0.05"], ["--dmin", "1"], ["--mleeps", "0.001"], ["--ppcoef", "0.5"]]
+    if rng.random() < 0.8:
+        pick = rng.choice(len(pool), size=int(rng.integers(1, 4)), replace=False)
+        extra = [x for i in sorted(pick) for x in pool[i]]
+        if rng.random() < 0.3 and len(variants) > 1:
+            extra = variants[1][0] + extra
+        variants.append((extra, "switches " + " ".join(extra)))
+    for vi, (extra, what) in enumerate(variants):
+        for tag, fn in (("r", ref), ("o", ours)):
+            rc, out = fn("consel", extra + ["-r", "-c", "x", f"{tag}{vi}"])
+            if tag == "r":
+                rrc = rc
+            elif rc != rrc:
+                bad.append(f"consel ({what}) exit status {rc} vs reference {rrc}: {desc}\n{out[-400:]}")
+        STATS["variants"] += 1
+        STATS["both_refused" if rrc != 0 else "both_ok"] += 0 if bad else 1
+        if rrc != 0 or bad:
+            continue
+        stem = str(vi)
+        for ext in ("rep", "cnt"):
+            pa, pb = d / f"o{stem}.{ext}", d / f"r{stem}.{ext}"
+            if pb.exists() and (not pa.exists() or pa.read_bytes() != pb.read_bytes()):
+                bad.append(f"consel ({what}) .{ext} differs: {desc}")
+        for ext in ("pv", "ci"):
+            pa, pb = d / f"o{stem}.{ext}", d / f"r{stem}.{ext}"
+            if pb.exists() and (not pa.exists() or not numbers_equal(pa, pb)):
+                bad.append(f"consel ({what}) .{ext} differs: {desc}")
+    return bad
+
+
+def main() -> int:
+    seed = int(sys.argv[1]) if len(sys.argv) > 1 else 1
+    cases = int(sys.argv[2]) if len(sys.argv) > 2 else 50
+    work = Path(sys.argv[3] if len(sys.argv) > 3 else "/tmp/emu_stress")
+    work.mkdir(parents=True, exist_ok=True)
+    bindir = build_programs(work)
+    rng = np.random.default_rng(seed)
+    nbad = 0
+    for c in range(cases):
+        d = work / f"case{c}"
+        if d.exists():
+            shutil.rmtree(d)
+        d.mkdir()
+        bad = one_case(rng, bindir, d)
+        for line in bad:
+            print(f"[case {c}] MISMATCH {line}", flush=True)
+        nbad += bool(bad)
+        if not bad and not os.environ.get("EMU_STRESS_KEEP"):
+            shutil.rmtree(d)
+    print(f"emu_stress seed {seed}: {cases - nbad} of {cases} cases identical to the reference "
+          f"({STATS['variants']} consel runs: {STATS['both_ok']} compared file by file, {STATS['both_refused']} refused by both programs alike)")
+    return 1 if nbad else 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
