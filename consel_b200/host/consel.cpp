@@ -24,11 +24,14 @@
 // Not carried by this build (error at the command line): the --chi* spherical fit (off the
 // hot path, SURVEY 8f "next").
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <thread>
+#include <utility>
 #include <vector>
 
 #include "../../include/consel_gpu.h"
@@ -46,6 +49,51 @@ static void dots(int n) {
     for (int i = 0; i < n; i++) putchar('.');
     fflush(stdout);
 }
+// The "small variance" warnings of do_mctest (src/consel.c:1403-1415): the pairwise sums
+// x_ij = sum_b (xc_ib - xc_jb)^2 over the centred r~1 block are formed on the device (pair_weight_kernel), which
+// reports no per-pair diagnostics.  For blocks small enough (mm^2 * nb <= 2e9: every case the reference finishes
+// in seconds) the sums are replayed here on the host threads in the reference's order of operations, and the
+// warnings are printed where the reference prints them, between the progress dots of the rows; larger blocks
+// print the dots alone.
+static void small_variance_warnings(const double *rep0, int mm, int nb, double varadd) {
+    const double kWarn = 100.0;  // VARADDWARN, src/consel.c:154
+    std::vector<std::vector<std::pair<int, double>>> small(mm);
+    if (rep0 && (double)mm * mm * nb <= 2e9) {
+        std::vector<double> xc(rep0, rep0 + (size_t)mm * nb);
+        for (int j = 0; j < mm; j++) {  // centring, :1374-1382
+            double *row = &xc[(size_t)j * nb];
+            double x = 0.0;
+            for (int i = 0; i < nb; i++) x += row[i];
+            x = x / nb;
+            for (int i = 0; i < nb; i++) row[i] -= x;
+        }
+        std::atomic<int> next{0};
+        auto work = [&]() {
+            for (int i = next.fetch_add(1); i < mm; i = next.fetch_add(1)) {
+                const double *xp = &xc[(size_t)(mm - 1 - i) * nb];  // long rows first
+                const int ii = mm - 1 - i;
+                for (int j = 0; j < ii; j++) {
+                    const double *yp = &xc[(size_t)j * nb];
+                    double x = 0.0;
+                    for (int ib = 0; ib < nb; ib++) x += (xp[ib] - yp[ib]) * (xp[ib] - yp[ib]);
+                    if (x < varadd * kWarn) small[ii].push_back({j, x});
+                }
+            }
+        };
+        unsigned nt = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+        if ((double)mm * mm * nb < 4e6) nt = 1;
+        std::vector<std::thread> th;
+        for (unsigned t = 1; t < nt; t++) th.emplace_back(work);
+        work();
+        for (auto &t : th) t.join();
+    }
+    for (int i = 0; i < mm; i++) {
+        for (const auto &w : small[i]) warn("small variance [%d,%d]: %g<%g*%g", i + 1, w.first + 1, w.second, varadd, kWarn);
+        putchar('.');
+    }
+    fflush(stdout);
+}
+
 #define CG(call)                                           \
     do {                                                   \
         if ((call) != CGPU_OK) die("%s", cgpu_last_error()); \
@@ -785,7 +833,8 @@ int main(int argc, char **argv) {
                        khwp.data(), mcwp.data()));
         printf("\n# calculating kh-pvalue"); dots(cm);
         printf("\n# calculating mc-pvalue"); dots(cm);
-        printf("\n# calculating the variances"); dots(mm);
+        printf("\n# calculating the variances");
+        small_variance_warnings(inrep ? nullptr : repmats[i0].data(), mm, nb0, varadd);
         printf("\n# calculating weighted kh-pvalue"); dots(cm);
         printf("\n# calculating weighted mc-pvalue"); dots(cm);
         printf("\n# MC-TEST DONE");

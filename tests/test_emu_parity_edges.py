@@ -84,3 +84,18 @@ def test_fit_failure_terminates_like_the_reference(progs, orc, tmp_path):
     assert r.returncode == 1 and "#! Terminated: a too large, ITMAX too small in gcf." in r.stdout, "the recipe no longer fails in the reference"
     assert o.returncode == 1, (o.returncode, o.stdout[-300:], o.stderr[-300:])
     assert "#! Terminated: a too large, ITMAX too small in gcf." in o.stdout
+
+
+def test_small_variance_warnings_are_printed_where_the_reference_prints_them(progs, orc, tmp_path):
+    """do_mctest warns about every tree pair whose centred replicate rows nearly coincide (src/consel.c:1403-1415),
+    between the progress dots of the rows; the sums live on the device here, consel.cpp replays them on the host
+    for blocks this small"""
+    make_rmt(orc, tmp_path, 21, 6, 40, [0.7, 1.0, 1.3], [40, 50, 45], 0.02)
+    r, o = both(progs, orc, tmp_path, [], "w")
+    assert r.returncode == o.returncode == 0
+
+    def section(text):
+        a = text.index("# calculating the variances")
+        return text[a:text.index("# calculating weighted kh-pvalue")]
+    assert "small variance" in section(r.stdout), "the recipe no longer triggers the warning in the reference"
+    assert section(o.stdout) == section(r.stdout)

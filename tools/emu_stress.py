@@ -43,6 +43,19 @@ def write_ass(path: Path, sets):
             f.write(f"\n# item: {i}\n#!VEC:\n{len(s)}\n" + " ".join(f"{int(x):10d}" for x in s) + " \n")
 
 
+def protocol(text: str, stem: str) -> list:
+    """the stdout protocol without what differs by design: the program id line, wall times, the wording of the
+    sort / count step, and the output file stem"""
+    import re
+    out = []
+    for ln in text.replace(stem, "OUT").splitlines():
+        if ln.startswith("# $Id") or ln.startswith("# consel_b200") or "time elapsed" in ln:
+            continue
+        ln = re.sub(r"# (sorting the replicates|counting the replicates \(sort-free row summaries on the device\))", "# SORT", ln)
+        out.append(ln.rstrip())
+    return out
+
+
 def numbers_equal(a: Path, b: Path) -> bool:
     x, y = orc.read_text_blocks(a), orc.read_text_blocks(b)
     return len(x) == len(y) and bool(np.allclose(x, y, rtol=2e-9, atol=1e-12, equal_nan=True))
@@ -82,10 +95,12 @@ def one_case(rng, bindir: Path, d: Path) -> list:
         r = subprocess.run([str(orc.ref_bin(prog))] + [str(a) for a in args], cwd=d, capture_output=True, text=True)
         return r.returncode, r.stdout
 
-    ra, _ = ref("makermt", ["-s", seed, "-p", "p", "in", "ref"])
+    ra, rout = ref("makermt", ["-s", seed, "-p", "p", "in", "ref"])
     oa, oout = ours("makermt", ["-s", seed, "-p", "p", "in", "our"])
     if ra != oa:
         return [f"makermt exit status {oa} vs reference {ra}: {desc}\n{oout[-400:]}"]
+    if protocol(rout, "ref") != protocol(oout, "our"):
+        bad.append(f"makermt stdout differs: {desc}")
     if ra != 0:
         return []
     for ext in ("rmt", "vt"):
@@ -117,9 +132,15 @@ def one_case(rng, bindir: Path, d: Path) -> list:
         for tag, fn in (("r", ref), ("o", ours)):
             rc, out = fn("consel", extra + ["-r", "-c", "x", f"{tag}{vi}"])
             if tag == "r":
-                rrc = rc
+                rrc, rtext = rc, out
             elif rc != rrc:
                 bad.append(f"consel ({what}) exit status {rc} vs reference {rrc}: {desc}\n{out[-400:]}")
+            elif protocol(rtext, f"r{vi}") != protocol(out, f"o{vi}"):
+                STATS["stdout_diffs"] = STATS.get("stdout_diffs", 0) + 1
+                if os.environ.get("EMU_STRESS_STDOUT"):
+                    import difflib
+                    bad.append(f"consel ({what}) stdout differs: {desc}\n" + "\n".join(list(difflib.unified_diff(
+                        protocol(rtext, f"r{vi}"), protocol(out, f"o{vi}"), lineterm="", n=0))[:12]))
         STATS["variants"] += 1
         STATS["both_refused" if rrc != 0 else "both_ok"] += 0 if bad else 1
         if rrc != 0 or bad:
@@ -133,6 +154,28 @@ def one_case(rng, bindir: Path, d: Path) -> list:
             pa, pb = d / f"o{stem}.{ext}", d / f"r{stem}.{ext}"
             if pb.exists() and (not pa.exists() or not numbers_equal(pa, pb)):
                 bad.append(f"consel ({what}) .{ext} differs: {desc}")
+    # the reference's own .rep / .cnt of the plain run as INPUT: consel -R (do_repmode) and consel -C (do_cntmode)
+    if (d / "r0.rep").exists() and (d / "r0.cnt").exists() and not bad:
+        for flag, src in (("-R", "r0.rep"), ("-C", "r0.cnt")):
+            shutil.copy(d / src, d / ("y" + Path(src).suffix))
+            extra = [flag] + (["-c"] if flag == "-R" and rng.random() < 0.5 else [])
+            rrc, rtext = ref("consel", extra + ["y", "rY" + flag[1]])
+            orc_, otext = ours("consel", extra + ["y", "oY" + flag[1]])
+            STATS["variants"] += 1
+            if rrc != orc_:
+                bad.append(f"consel {flag} exit status {orc_} vs reference {rrc}: {desc}\n{otext[-400:]}")
+                continue
+            STATS["both_refused" if rrc != 0 else "both_ok"] += 1
+            if rrc != 0:
+                continue
+            for ext in ("cnt",):
+                pa, pb = d / f"oY{flag[1]}.{ext}", d / f"rY{flag[1]}.{ext}"
+                if pa.exists() != pb.exists() or (pb.exists() and pa.read_bytes() != pb.read_bytes()):
+                    bad.append(f"consel {flag} .{ext} differs: {desc}")
+            for ext in ("pv", "ci"):
+                pa, pb = d / f"oY{flag[1]}.{ext}", d / f"rY{flag[1]}.{ext}"
+                if pa.exists() != pb.exists() or (pb.exists() and not numbers_equal(pa, pb)):
+                    bad.append(f"consel {flag} .{ext} differs: {desc}")
     return bad
 
 
@@ -156,7 +199,8 @@ def main() -> int:
         if not bad and not os.environ.get("EMU_STRESS_KEEP"):
             shutil.rmtree(d)
     print(f"emu_stress seed {seed}: {cases - nbad} of {cases} cases identical to the reference "
-          f"({STATS['variants']} consel runs: {STATS['both_ok']} compared file by file, {STATS['both_refused']} refused by both programs alike)")
+          f"({STATS['variants']} consel runs: {STATS['both_ok']} compared file by file, {STATS['both_refused']} refused by both programs alike, "
+          f"{STATS.get('stdout_diffs', 0)} with a different stdout protocol)")
     return 1 if nbad else 0
 
 
