@@ -874,7 +874,9 @@ int main(int argc, char **argv) {
         r0.resize((size_t)cm * kk);
         CG(cgpu_count_query(reps, 1, thr.data(), r0.data()));
     }
-    if (kk < 2) doau = false;
+    // do_rmtmode drops the AU test for a single scale (src/consel.c:868); do_repmode has no such guard (:1231-1232):
+    // `consel -R` on a one-scale .rep runs the (degenerate) fit and writes .ci / .cnt
+    if (kk < 2 && !inrep) doau = false;
 
     if (dobp) {  // do_bptest
         printf("\n# BP-TEST STARTS");

@@ -99,3 +99,16 @@ def test_small_variance_warnings_are_printed_where_the_reference_prints_them(pro
         return text[a:text.index("# calculating weighted kh-pvalue")]
     assert "small variance" in section(r.stdout), "the recipe no longer triggers the warning in the reference"
     assert section(o.stdout) == section(r.stdout)
+
+
+def test_rep_mode_runs_the_au_test_on_a_single_scale_like_the_reference(progs, orc, tmp_path):
+    """do_repmode has no `kk<2` guard (src/consel.c:1231-1240): `consel -R` on a one-scale .rep runs the degenerate
+    fit and writes .pv / .ci / .cnt"""
+    import shutil
+    make_rmt(orc, tmp_path, 31, 5, 80, [1.0], [70], 0.106)
+    orc.run_ref("consel", ["-r", "x", "s"], tmp_path)
+    shutil.copy(tmp_path / "s.rep", tmp_path / "x.rep")
+    r, o = both(progs, orc, tmp_path, ["-R", "-c"], "q")
+    assert r.returncode == o.returncode == 0, o.stdout[-400:]
+    assert (tmp_path / "rq.ci").exists() and (tmp_path / "rq.cnt").exists()
+    same_files(orc, tmp_path, "q", binary=(), text=("pv", "ci", "cnt"))

@@ -106,6 +106,57 @@ def one_case(rng, bindir: Path, d: Path) -> list:
     for ext in ("rmt", "vt"):
         if (d / f"our.{ext}").read_bytes() != (d / f"ref.{ext}").read_bytes():
             bad.append(f".{ext} differs: {desc}")
+    # makermt variants: -b (replicate factor, truncated to int), -f (the rescaling defaults: 1 scale), the built-in ten
+    # scales, -g (multi-gene: file names from a .svt, the MT19937 stream continues from gene to gene), and makerep
+    mk = []
+    if rng.random() < 0.5:
+        mk.append((["-s", seed, "-b", f"{rng.uniform(0.2, 2.5):.3f}", "-p", "p", "in"], "mb"))
+    if rng.random() < 0.3:
+        mk.append((["-s", seed, "-b", "0.004", "in"], "md"))        # built-in scales, 40 replicates each
+    if rng.random() < 0.3:
+        mk.append((["-s", seed, "-f", "-b", "0.01", "in"], "mf"))
+    for args, stem in mk:
+        r1, t1 = ref("makermt", args + [f"r{stem}"])
+        o1, t2 = ours("makermt", args + [f"o{stem}"])
+        if r1 != o1:
+            bad.append(f"makermt {args} exit status {o1} vs reference {r1}: {desc}")
+        elif r1 == 0:
+            for ext in ("rmt", "vt"):
+                if (d / f"o{stem}.{ext}").read_bytes() != (d / f"r{stem}.{ext}").read_bytes():
+                    bad.append(f"makermt {args} .{ext} differs: {desc}")
+            if protocol(t1, f"r{stem}") != protocol(t2, f"o{stem}"):
+                bad.append(f"makermt {args} stdout differs: {desc}")
+    if rng.random() < 0.35:
+        L2 = base[None, :int(max(3, n // 2))] + 0.2 * rng.standard_normal((K, int(max(3, n // 2))))
+        orc.write_mt(d / "g2.mt", L2)
+        shutil.copy(d / "in.mt", d / "g1.mt")
+        for who in ("r", "o"):
+            (d / f"{who}g.svt").write_text("2\ng1 g2\n")
+        # input names and output names come from two .svt files (src/makermt.c:303-312)
+        (d / "gin.svt").write_text("2\ng1 g2\n")
+        (d / "rgo.svt").write_text("2\nrg1 rg2\n")
+        (d / "ogo.svt").write_text("2\nog1 og2\n")
+        r1, t1 = ref("makermt", ["-s", seed, "-g", "-p", "p", "gin", "rgo"])
+        o1, t2 = ours("makermt", ["-s", seed, "-g", "-p", "p", "gin", "ogo"])
+        if r1 != o1:
+            bad.append(f"makermt -g exit status {o1} vs reference {r1}: {desc}\n{t2[-300:]}")
+        elif r1 == 0:
+            for g in ("g1", "g2"):
+                for ext in ("rmt", "vt"):
+                    pa, pb = d / f"o{g}.{ext}", d / f"r{g}.{ext}"
+                    if pa.exists() != pb.exists() or (pb.exists() and pa.read_bytes() != pb.read_bytes()):
+                        bad.append(f"makermt -g {g}.{ext} differs: {desc}")
+    if rng.random() < 0.35 and orc.ref_bin("makerep") is not None:
+        r1, t1 = ref("makerep", ["-s", seed, "-p", "p", "in", "rmr"])
+        o1, t2 = ours("makerep", ["-s", seed, "-p", "p", "in", "omr"])
+        if r1 != o1:
+            bad.append(f"makerep exit status {o1} vs reference {r1}: {desc}\n{t2[-300:]}")
+        elif r1 == 0:
+            for ext in ("rep", "vt"):
+                pa, pb = d / f"omr.{ext}", d / f"rmr.{ext}"
+                if pa.exists() != pb.exists() or (pb.exists() and pa.read_bytes() != pb.read_bytes()):
+                    bad.append(f"makerep .{ext} differs: {desc}")
+
     # consel variants on the REFERENCE's .rmt (so that a makermt difference does not cascade)
     shutil.copy(d / "ref.rmt", d / "x.rmt")
     variants = [([], "plain")]
