@@ -235,7 +235,9 @@ static unsigned long long pick_chunk_len(unsigned long long needed_draws, unsign
         }
     }
     const bool force_fill = G().opt_chunk_fill == 2;  // tests: equal-fill whatever the model says
-    if (G().opt_chunk_fill == 0 || nranges > 32 || (!force_fill && needed_draws < (1ull << 22))) return best;
+    // (needed_draws == 0: a rank whose shard of every scale is empty -- fewer replicates than ranks; the forced
+    // equal-fill length would be zero)
+    if (G().opt_chunk_fill == 0 || nranges > 32 || needed_draws == 0 || (!force_fill && needed_draws < (1ull << 22))) return best;
     constexpr unsigned long long ALIGN = 4 * MT_N;  // whole groups of four blocks (the branch-free body of the draw kernel)
     std::vector<unsigned long long> off(nranges, 0);
     unsigned long long pick = best;
