@@ -31,6 +31,8 @@ def main():
     L = orc.read_lnf(gold / "mam15.lnf")
     rr = [0.5, 0.6, 0.7, 0.8, 0.9, 1.0, 1.1, 1.2, 1.3, 1.4]
     bb = [100, 101, 99, 100, 103, 100, 97, 100, 100, 102]  # not all divisible by the world size
+    if mode == "tinyb":  # fewer replicates than ranks at some scales: a rank's share of a scale can be EMPTY
+        bb = [2, 1, 3, 2, 1, 2, 4, 1, 2, 2]
     ass = None
     if mode == "edges":
         ass = orc.read_ass(gold / "mam15.ass")

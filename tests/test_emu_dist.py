@@ -60,7 +60,7 @@ def _run_ranks(lib_path: Path, out: Path, world: int, mode: str):
     return [np.load(f"{out}.{rank}.npz") for rank in range(world)]
 
 
-@pytest.mark.parametrize("world,mode", [(2, "identity"), (3, "identity"), (2, "edges")])
+@pytest.mark.parametrize("world,mode", [(2, "identity"), (3, "identity"), (2, "edges"), (3, "tinyb")])
 def test_sharded_pipeline_equals_single_process_bit_for_bit(emu_lib, tmp_path, world, mode):
     one = _run_ranks(emu_lib._path, tmp_path / "one", 1, mode)[0]
     many = _run_ranks(emu_lib._path, tmp_path / "many", world, mode)
