@@ -205,6 +205,20 @@ def one_case(rng, bindir: Path, d: Path) -> list:
             pa, pb = d / f"o{stem}.{ext}", d / f"r{stem}.{ext}"
             if pb.exists() and (not pa.exists() or not numbers_equal(pa, pb)):
                 bad.append(f"consel ({what}) .{ext} differs: {desc}")
+    # catpv on the reference's .pv files: the table text must be the reference's, for random display switches
+    real_catpv = ROOT / "consel_b200" / "bin" / "catpv"
+    for vi in range(len(variants)):
+        if not (d / f"r{vi}.pv").exists() or orc.ref_bin("catpv") is None:
+            continue
+        pool = [["-v"], ["-e"], ["-r"], ["-s", str(int(rng.integers(1, 10)))], ["-l"], ["--no_au"], ["--no_bp"], ["--no_pp"], ["--no_sh"]]
+        pick = rng.choice(len(pool), size=int(rng.integers(0, 4)), replace=False)
+        args = [x for i in sorted(pick) for x in pool[i]] + [f"r{vi}"]
+        a = subprocess.run([str(orc.ref_bin("catpv"))] + args, cwd=d, capture_output=True, text=True)
+        b = subprocess.run([str(real_catpv)] + args, cwd=d, capture_output=True, text=True)
+        STATS["catpv"] = STATS.get("catpv", 0) + 1
+        if a.returncode != b.returncode or protocol(a.stdout, "\0") != protocol(b.stdout, "\0"):
+            bad.append(f"catpv {args} differs (exit {b.returncode} vs {a.returncode}): {desc}")
+
     # the reference's own .rep / .cnt of the plain run as INPUT: consel -R (do_repmode) and consel -C (do_cntmode)
     if (d / "r0.rep").exists() and (d / "r0.cnt").exists() and not bad:
         for flag, src in (("-R", "r0.rep"), ("-C", "r0.cnt")):
@@ -251,7 +265,7 @@ def main() -> int:
             shutil.rmtree(d)
     print(f"emu_stress seed {seed}: {cases - nbad} of {cases} cases identical to the reference "
           f"({STATS['variants']} consel runs: {STATS['both_ok']} compared file by file, {STATS['both_refused']} refused by both programs alike, "
-          f"{STATS.get('stdout_diffs', 0)} with a different stdout protocol)")
+          f"{STATS.get('stdout_diffs', 0)} with a different stdout protocol; {STATS.get('catpv', 0)} catpv tables compared)")
     return 1 if nbad else 0
 
 
