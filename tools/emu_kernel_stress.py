@@ -76,12 +76,16 @@ def makermt_case(rng, case):
     ref = orc.makermt(L, bn, bb, seed)
     counts = orc.scaleboot_counts(n, bn, bb, seed)
     base_i8 = cg.scaleboot_all(L, bn, bb, seed, sum_mode=cg.SUM_INT8)
+    base_ph = cg.scaleboot_all(L, bn, bb, seed, rng_mode=cg.RNG_PHILOX, sum_mode=cg.SUM_INT8)
     try:
         for k, v in opts.items():
             cg.set_option(k, v)
         strict = cg.scaleboot_all(L, bn, bb, seed, sum_mode=cg.SUM_STRICT)
         i8 = cg.scaleboot_all(L, bn, bb, seed, sum_mode=cg.SUM_INT8)
         fast = cg.scaleboot_all(L, bn, bb, seed, sum_mode=cg.SUM_FAST)
+        ph = cg.scaleboot_all(L, bn, bb, seed, rng_mode=cg.RNG_PHILOX, sum_mode=cg.SUM_INT8)
+        for s in range(S):  # the counter-based resampler through the byte-row histograms (bucketed one included)
+            assert np.array_equal(ph[s], base_ph[s]), ("options changed a Philox int8 bit", s)
         for s in range(S):
             assert np.array_equal(strict[s], ref[s]), ("strict != oracle", s)
             assert np.array_equal(i8[s], base_i8[s]), ("options changed an int8 bit", s)
