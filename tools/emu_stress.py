@@ -146,6 +146,22 @@ def one_case(rng, bindir: Path, d: Path) -> list:
                     pa, pb = d / f"o{g}.{ext}", d / f"r{g}.{ext}"
                     if pa.exists() != pb.exists() or (pb.exists() and pa.read_bytes() != pb.read_bytes()):
                         bad.append(f"makermt -g {g}.{ext} differs: {desc}")
+            # consel -g on the two genes the REFERENCE wrote (do_rmtmultimode, src/consel.c:1056-1192)
+            (d / "gg.svt").write_text("2\nrg1 rg2\n")
+            gx = ["-g"] + (["--smooth_cnt"] if rng.random() < 0.4 else []) + (["-f"] if rng.random() < 0.3 else []) + ["-c"]
+            r2, t3 = ref("consel", gx + ["gg", "rgg"])
+            o2, t4 = ours("consel", gx + ["gg", "ogg"])
+            STATS["variants"] += 1
+            if r2 != o2:
+                bad.append(f"consel {gx} exit status {o2} vs reference {r2}: {desc}\n{t4[-300:]}")
+            elif r2 == 0:
+                STATS["both_ok"] += 1
+                for ext in ("cnt", "pv", "ci"):
+                    pa, pb = d / f"ogg.{ext}", d / f"rgg.{ext}"
+                    if pa.exists() != pb.exists() or (pb.exists() and not numbers_equal(pa, pb)):
+                        bad.append(f"consel {gx} .{ext} differs: {desc}")
+            else:
+                STATS["both_refused"] += 1
     if rng.random() < 0.35 and orc.ref_bin("makerep") is not None:
         r1, t1 = ref("makerep", ["-s", seed, "-p", "p", "in", "rmr"])
         o1, t2 = ours("makerep", ["-s", seed, "-p", "p", "in", "omr"])
@@ -173,6 +189,10 @@ def one_case(rng, bindir: Path, d: Path) -> list:
     pool = [["--no_au"], ["--no_bp"], ["--no_pp"], ["--no_sh"], ["--smooth_cnt"], ["--no_sort"], ["--wls"],
             ["--th", f"{rng.uniform(-2, 2):.3f}"], ["--kappa", f"{rng.uniform(0.5, 1.5):.2f}"], ["--rmin", "0.5"], ["--rmax", "1.5"],
             ["-t", f"{rng.uniform(0.2, 2):.2f}"], ["--cieps", "0.05"], ["--dmin", "1"], ["--mleeps", "0.001"], ["--ppcoef", "0.5"]]
+    if rng.random() < 0.3:   # AIC / BIC correction of the log-likelihoods (read_pdm, do_pdm: src/consel.c:675-744)
+        with open(d / "pdm.vt", "w") as f:
+            f.write(f"#!VEC:\n{K}\n" + " ".join(str(int(x)) for x in rng.integers(1, 30, size=K)) + "\n")
+        pool.append(["--pdm", "pdm", "--aictype", str(int(rng.integers(1, 4))), "--ppn", str(n)])
     if rng.random() < 0.8:
         pick = rng.choice(len(pool), size=int(rng.integers(1, 4)), replace=False)
         extra = [x for i in sorted(pick) for x in pool[i]]
