@@ -5,6 +5,7 @@
 // that follows the reference's observable behaviour line by line (citations inline).
 //
 // Extensions (not in the reference): --rng mt|philox, --sum strict|fast|int8, --gpu N.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -83,7 +84,7 @@ static int genrmt(Params &P, const char *infile, const char *outfile) {
     // recognised here, before any output file is opened, instead of after the whole run.
     for (int i = 0; i < kk; i++) {
         const double mu = (double)bn[i] / (double)nn;  // mean count per site
-        if (bn[i] <= 0) die("scale %g gives an empty replicate (n'=%d) for %d sites", P.rr[i], bn[i], nn);
+        if (bn[i] < 0) die("scale %g gives a negative replicate size (n'=%d) for %d sites", P.rr[i], bn[i], nn);
         if (mu + 9.0 * sqrt(mu) + 10.0 > 255.0)
             die("scale %g on %d sites draws a site about %g times per replicate: beyond the byte counts of the device path", P.rr[i], nn, mu);
     }
@@ -128,21 +129,41 @@ static int genrmt(Params &P, const char *infile, const char *outfile) {
         rep[i].resize((size_t)mm * (P.bb[i] > 0 ? P.bb[i] : 0) + 1);
         rep_ptr[i] = rep[i].data();
     }
-    if (g_world == 1) {
-        int rc = cgpu_scaleboot_all(L.data(), mm, nn, kk, bn.data(), P.bb.data(), P.seed_used, P.consumed, P.rng_mode,
-                                    P.sum_mode, rep_ptr.data());
+    // A scale with n' = (int)(r*n) = 0 (a toy alignment under a small scale) draws nothing: the reference's loop
+    // (src/makermt.c:52-70) leaves x = 0 and stores x / r with r = 0/n -- the NaN of 0.0/0.0, formed here by the
+    // same division at run time.  Such scales consume no draws of the stream and never reach the device.
+    std::vector<int> live, bn_live, bb_live;
+    std::vector<double *> ptr_live;
+    for (int i = 0; i < kk; i++) {
+        if (bn[i] > 0) {
+            live.push_back(i);
+            bn_live.push_back(bn[i]);
+            bb_live.push_back(P.bb[i]);
+            ptr_live.push_back(rep_ptr[i]);
+        } else {
+            volatile double zero = 0.0;
+            const double v = zero / (zero / (double)nn);
+            std::fill(rep[i].begin(), rep[i].end(), v);
+        }
+    }
+    const int kl = (int)live.size();
+    if (kl == 0) {
+        // nothing to resample
+    } else if (g_world == 1) {
+        int rc = cgpu_scaleboot_all(L.data(), mm, nn, kl, bn_live.data(), bb_live.data(), P.seed_used, P.consumed, P.rng_mode,
+                                    P.sum_mode, ptr_live.data());
         if (rc != CGPU_OK) die("%s", cgpu_last_error());
     } else {
         cgpu_matrix *dm = nullptr;
         cgpu_reps *dr = nullptr;
         if (cgpu_matrix_upload(L.data(), mm, nn, &dm) != CGPU_OK) die("%s", cgpu_last_error());
-        if (cgpu_scaleboot_dev(dm, kk, bn.data(), P.bb.data(), P.seed_used, P.consumed, P.rng_mode, P.sum_mode, &dr) != CGPU_OK)
+        if (cgpu_scaleboot_dev(dm, kl, bn_live.data(), bb_live.data(), P.seed_used, P.consumed, P.rng_mode, P.sum_mode, &dr) != CGPU_OK)
             die("%s", cgpu_last_error());
-        for (int i = 0; i < kk; i++) {
+        for (int q = 0; q < kl; q++) {
             cgpu_reps *whole = nullptr;
-            if (cgpu_reps_gather_scale(dr, i, &whole) != CGPU_OK) die("%s", cgpu_last_error());
-            double *one[1] = {rep[i].data()};
-            if (writer && P.bb[i] > 0 && cgpu_reps_download(whole, one) != CGPU_OK) die("%s", cgpu_last_error());
+            if (cgpu_reps_gather_scale(dr, q, &whole) != CGPU_OK) die("%s", cgpu_last_error());
+            double *one[1] = {ptr_live[q]};
+            if (writer && bb_live[q] > 0 && cgpu_reps_download(whole, one) != CGPU_OK) die("%s", cgpu_last_error());
             cgpu_reps_free(whole);
         }
         cgpu_reps_free(dr);

@@ -4,6 +4,7 @@
 #include "refio.h"
 
 #include <algorithm>
+#include <atomic>
 #include <sys/stat.h>
 #include <unistd.h>
 #include <memory>
@@ -21,12 +22,17 @@ namespace refio {
 int debugmode = 0;
 
 void die(const char *fmt, ...) {
+    // several fits of the thread pool can fail in the same round: the first caller reports and ends the
+    // process, the others wait for that (the reference, single-threaded, prints exactly one line)
+    static std::atomic<bool> dying{false};
+    if (dying.exchange(true))
+        for (;;) pause();
+    char msg[1024];
     va_list ap;
     va_start(ap, fmt);
-    printf("\n#! Terminated: ");
-    vprintf(fmt, ap);
-    printf(".\n");
+    vsnprintf(msg, sizeof msg, fmt, ap);
     va_end(ap);
+    printf("\n#! Terminated: %s.\n", msg);
     // The reference is single-threaded and calls exit(1) (src/misc.c:40-49).  Here the message may come from a
     // worker thread of the fit pool: exit() would run the static destructors -- the pool joining its own thread --
     // and abort.  Flush every open stream (the stdout protocol line, partially written output files: what exit()

@@ -112,3 +112,22 @@ def test_rep_mode_runs_the_au_test_on_a_single_scale_like_the_reference(progs, o
     assert r.returncode == o.returncode == 0, o.stdout[-400:]
     assert (tmp_path / "rq.ci").exists() and (tmp_path / "rq.cnt").exists()
     same_files(orc, tmp_path, "q", binary=(), text=("pv", "ci", "cnt"))
+
+
+def test_scale_without_draws_and_one_termination_line(progs, orc, tmp_path):
+    """n' = (int)(r*n) = 0 (three sites under r = 0.31): the reference stores 0.0/0.0 for every replicate of that
+    scale and goes on (src/makermt.c:52-70) -- the .rmt is byte-equal; consel on it ends in `luinverse: singular
+    matrix` in several fits at once: one `#! Terminated` line, exit status 1"""
+    rng = np.random.default_rng(4)
+    L = (-2.3 - 4.07 * rng.exponential(size=3))[None, :] + 0.2 * rng.standard_normal((5, 3))
+    orc.write_mt(tmp_path / "in.mt", L)
+    orc.write_pa(tmp_path / "p.pa", [0.31, 1.0, 1.58], [9, 8, 6])
+    orc.run_ref("makermt", ["-s", 3, "-p", "p", "in", "r"], tmp_path)
+    o = subprocess.run([str(progs / "makermt"), "-s", "3", "-p", "p", "in", "o"], cwd=tmp_path, capture_output=True, text=True)
+    assert o.returncode == 0, o.stdout[-300:]
+    for ext in ("rmt", "vt"):
+        assert (tmp_path / f"o.{ext}").read_bytes() == (tmp_path / f"r.{ext}").read_bytes(), ext
+    (tmp_path / "x.rmt").write_bytes((tmp_path / "r.rmt").read_bytes())
+    r, o = both(progs, orc, tmp_path, [], "z")
+    assert r.returncode == 1 and "#! Terminated: luinverse: singular matrix." in r.stdout, "the recipe no longer fails in the reference"
+    assert o.returncode == 1 and o.stdout.count("#! Terminated") == 1 and "#! Terminated: luinverse: singular matrix." in o.stdout
