@@ -172,6 +172,7 @@ static int genrmt(Params &P, const char *infile, const char *outfile) {
     for (int i = 0; i < kk; i++) P.consumed += (unsigned long long)P.bb[i] * (unsigned long long)bn[i];
 
     for (int i = 0; i < kk; i++) {
+        if (bn[i] == 0) warn("zero size in malloc");  // scaleboot's new_vec(bn) of an empty draw list (src/makermt.c:48, misc.c:98)
         if (outfile) {
             write_bmat(out, rep[i].data(), mm, P.bb[i]);
             putchar('.');

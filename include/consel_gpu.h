@@ -71,7 +71,9 @@ void cgpu_host_rowsums(const double *L, int K, int n, double *datvec);
  *
  *   L          K*n doubles, row-major == datmat[0] of new_mat (src/misc.c:115-126)
  *   bn[s]      replicate sample size (int)(rr[s]*n), computed by the HOST exactly
- *              as src/makermt.c:165-168 does
+ *              as src/makermt.c:165-168 does; must be positive (CGPU_EINVAL otherwise: a scale
+ *              that draws nothing never reaches the device -- the caller stores the reference's
+ *              0.0/0.0 for it, as consel_b200/host/makermt.cpp does)
  *   bb[s]      number of replicates of scale s
  *   seed       already time()-substituted (src/rand.c:33-37)
  *   stream_offset  uniform draws already consumed from the stream (makermt -g

@@ -162,6 +162,34 @@ def one_case(rng, bindir: Path, d: Path) -> list:
                         bad.append(f"consel {gx} .{ext} differs: {desc}")
             else:
                 STATS["both_refused"] += 1
+    if rng.random() < 0.35:   # the PAML .lnf reader (src/freadmat.c:110-154): patterns with multiplicities
+        npat = int(rng.integers(1, 60))
+        mult = rng.integers(1, 6, size=npat)
+        with open(d / "pl.lnf", "w") as f:
+            f.write(f"  {K}  {int(mult.sum())}  {npat}\n\n")
+            for i in range(K):
+                f.write(f"\n {i + 1}\n\n")
+                v = -rng.exponential(4.0, size=npat) - 1.0
+                for j in range(npat):
+                    f.write(f"{j + 1:6d}{int(mult[j]):6d}{v[j]:16.10f}{rng.uniform(0, 99):9.2f}  ACGT\n")
+        r1, t1 = ref("makermt", ["-s", seed, "-p", "p", "--paml", "pl", "rpl"])
+        o1, t2 = ours("makermt", ["-s", seed, "-p", "p", "--paml", "pl", "opl"])
+        if r1 != o1:
+            bad.append(f"makermt --paml exit status {o1} vs reference {r1}: {desc}\n{t2[-300:]}")
+        elif r1 == 0:
+            for ext in ("rmt", "vt"):
+                if (d / f"opl.{ext}").read_bytes() != (d / f"rpl.{ext}").read_bytes():
+                    bad.append(f"makermt --paml .{ext} differs: {desc}")
+            # the tensor-core mode on the same file: every sum within 1e-9 of the reference's (contract of --sum int8)
+            o3, t4 = ours("makermt", ["-s", seed, "-p", "p", "--paml", "--sum", "int8", "pl", "opl8"])
+            if o3 != 0:
+                bad.append(f"makermt --sum int8 failed: {desc}\n{t4[-300:]}")
+            else:
+                a8, b8 = orc.read_rmt(d / "opl8.rmt"), orc.read_rmt(d / "rpl.rmt")
+                for x8, y8 in zip(a8["reps"], b8["reps"]):
+                    if x8.shape != y8.shape or not np.allclose(x8, y8, rtol=1e-9, atol=0, equal_nan=True):
+                        bad.append(f"makermt --sum int8 differs from the reference by more than 1e-9: {desc}")
+                        break
     if rng.random() < 0.35 and orc.ref_bin("makerep") is not None:
         r1, t1 = ref("makerep", ["-s", seed, "-p", "p", "in", "rmr"])
         o1, t2 = ours("makerep", ["-s", seed, "-p", "p", "in", "omr"])
