@@ -253,6 +253,24 @@ def one_case(rng, bindir: Path, d: Path) -> list:
             pa, pb = d / f"o{stem}.{ext}", d / f"r{stem}.{ext}"
             if pb.exists() and (not pa.exists() or not numbers_equal(pa, pb)):
                 bad.append(f"consel ({what}) .{ext} differs: {desc}")
+    # catrep (merge of .rep / .rmt files) on the reference's own files
+    if orc.ref_bin("catrep") is not None:
+        jobs = []
+        if (d / "r0.rep").exists():
+            jobs.append((["r0", "r0"], "rep"))
+        if (d / "rmb.rmt").exists():
+            jobs.append((["-m", "ref", "rmb"], "rmt"))
+        for args, ext in jobs:
+            a = subprocess.run([str(orc.ref_bin("catrep"))] + args + ["rcat"], cwd=d, capture_output=True, text=True)
+            b = subprocess.run([str(ROOT / "consel_b200" / "bin" / "catrep")] + args + ["ocat"], cwd=d, capture_output=True, text=True)
+            STATS["catrep"] = STATS.get("catrep", 0) + 1
+            pa, pb = d / f"ocat.{ext}", d / f"rcat.{ext}"
+            if a.returncode != b.returncode or pa.exists() != pb.exists() or (pb.exists() and pa.read_bytes() != pb.read_bytes()):
+                bad.append(f"catrep {args} differs (exit {b.returncode} vs {a.returncode}): {desc}")
+            for q in (pa, pb):
+                if q.exists():
+                    q.unlink()
+
     # catpv on the reference's .pv files: the table text must be the reference's, for random display switches
     real_catpv = ROOT / "consel_b200" / "bin" / "catpv"
     for vi in range(len(variants)):
@@ -313,7 +331,7 @@ def main() -> int:
             shutil.rmtree(d)
     print(f"emu_stress seed {seed}: {cases - nbad} of {cases} cases identical to the reference "
           f"({STATS['variants']} consel runs: {STATS['both_ok']} compared file by file, {STATS['both_refused']} refused by both programs alike, "
-          f"{STATS.get('stdout_diffs', 0)} with a different stdout protocol; {STATS.get('catpv', 0)} catpv tables compared)")
+          f"{STATS.get('stdout_diffs', 0)} with a different stdout protocol; {STATS.get('catpv', 0)} catpv tables, {STATS.get('catrep', 0)} catrep merges compared)")
     return 1 if nbad else 0
 
 
