@@ -118,7 +118,9 @@ def one_case(rng, bindir: Path, d: Path) -> list:
     for args, stem in mk:
         r1, t1 = ref("makermt", args + [f"r{stem}"])
         o1, t2 = ours("makermt", args + [f"o{stem}"])
-        if r1 != o1:
+        if r1 < 0:  # the reference itself crashed (e.g. SIGSEGV on a scale whose -b factor leaves 0 replicates): nothing to match
+            STATS["ref_crashed"] = STATS.get("ref_crashed", 0) + 1
+        elif r1 != o1:
             bad.append(f"makermt {args} exit status {o1} vs reference {r1}: {desc}")
         elif r1 == 0:
             for ext in ("rmt", "vt"):
