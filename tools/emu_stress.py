@@ -5,7 +5,8 @@ small inputs -- random tree / site counts, scale sets, replicate counts, tied ro
 associations, the -f / -R / --quick_mctest variants.  `.rmt` `.vt` `.rep` `.cnt` must be byte-equal, `.pv` `.ci`
 equal to the printed digits.
 
-    python tools/emu_stress.py [SEED=1] [CASES=50] [workdir=/tmp/emu_stress]      (EMU_STRESS_KEEP=1 keeps every case directory)
+    python tools/emu_stress.py [SEED=1] [CASES=50] [workdir=/tmp/emu_stress]      (EMU_STRESS_KEEP=1 keeps every case directory;
+                                                                                   EMU_STRESS_SIZE=medium: tens of trees, ten scales x thousands of replicates)
 """
 import os
 import shutil
@@ -62,6 +63,7 @@ def numbers_equal(a: Path, b: Path) -> bool:
 
 
 STATS = {"variants": 0, "both_ok": 0, "both_refused": 0}
+RR10 = [0.5, 0.6, 0.7, 0.8, 0.9, 1.0, 1.1, 1.2, 1.3, 1.4]
 
 
 def one_case(rng, bindir: Path, d: Path) -> list:
@@ -82,6 +84,14 @@ def one_case(rng, bindir: Path, d: Path) -> list:
         rr[int(rng.integers(0, kk))] = 1.0
         rr = np.sort(rr)
     bb = rng.integers(2, 250, size=kk)
+    if os.environ.get("EMU_STRESS_SIZE") == "medium":  # the regime of real use: tens of trees, thousands of replicates, well-behaved fits
+        K = int(rng.integers(15, 70))
+        n = int(rng.integers(200, 1500))
+        base = -2.3 - 4.07 * rng.exponential(size=n)
+        L = base[None, :] + rng.choice([0.106, 0.3]) * rng.standard_normal((K, n)) - rng.uniform(0, 3) * np.arange(K)[:, None] / n
+        kk = 10
+        rr = np.array(RR10)
+        bb = np.full(kk, int(rng.integers(500, 3000)))
     seed = int(rng.integers(1, 10**6))
     orc.write_mt(d / "in.mt", L)
     orc.write_pa(d / "p.pa", rr, bb)
