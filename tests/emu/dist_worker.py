@@ -36,6 +36,19 @@ def main():
     ass = None
     if mode == "edges":
         ass = orc.read_ass(gold / "mam15.ass")
+    if mode.startswith("rand"):  # tools/emu_dist_worlds.py: random shapes, scale sets, replicate counts, associations
+        rng = np.random.default_rng(int(mode[4:]))
+        K, n = int(rng.integers(2, 40)), int(rng.integers(5, 400))
+        L = (-2.3 - 4.07 * rng.exponential(size=n))[None, :] + rng.choice([0.05, 0.3]) * rng.standard_normal((K, n))
+        kk = int(rng.integers(2, 9))
+        rr = np.sort(np.round(rng.uniform(0.4, 1.8, size=kk), 2))
+        rr[int(rng.integers(0, kk))] = 1.0
+        rr = [float(x) for x in np.sort(rr)]
+        bb = [int(x) for x in rng.integers(1, 150, size=kk)]
+        if rng.random() < 0.5:
+            cm = int(rng.integers(1, 10))
+            sets = [np.sort(rng.choice(K, size=int(rng.integers(1, K)), replace=False)) for _ in range(cm)]
+            ass = (np.cumsum([0] + [len(x) for x in sets]).astype(np.int32), np.concatenate(sets).astype(np.int32))
     res = pipeline.run(L, rr, bb, 1234, sum_mode=cg.SUM_STRICT, ass=ass)
     np.savez(f"{out}.{rank}.npz", rank=rank, world=world, item=res["item"], stat=res["stat"], pv=res["pv"], se=res["se"], cnt=res["cnt"],
              ax=res["ax"], ci=res["ci"], ret=res["ret"], datvec=res["datvec"])

@@ -3,7 +3,7 @@
 (tests/test_emu_dist.py runs 2 and 3): every rank of a 4- and an 8-process run returns the single-process table
 bit for bit -- item ranges with fewer items than ranks * 2, reduce-scatter padding, the collective AU rounds.
 
-    python tools/emu_dist_worlds.py [worlds=4,8] [builddir=/tmp/emu_dist_worlds]
+    python tools/emu_dist_worlds.py [worlds=4,8] [builddir=/tmp/emu_dist_worlds] [SEED COUNT: random shapes / associations instead]
 """
 import sys
 from pathlib import Path
@@ -23,7 +23,11 @@ def main() -> int:
     lib = build_emu_lib.build(build)
     out = build / "out"
     out.mkdir(exist_ok=True)
-    for mode in ("identity", "edges"):
+    modes = ("identity", "edges")
+    if len(sys.argv) > 3:  # random cases: python tools/emu_dist_worlds.py 2,3,5 /tmp/x SEED COUNT
+        seed, count = int(sys.argv[3]), int(sys.argv[4]) if len(sys.argv) > 4 else 5
+        modes = tuple(f"rand{seed * 1000 + c}" for c in range(count))
+    for mode in modes:
         one = t._run_ranks(lib, out / f"one_{mode}", 1, mode)[0]
         for world in worlds:
             many = t._run_ranks(lib, out / f"w{world}_{mode}", world, mode)
