@@ -28,7 +28,13 @@ def main() -> int:
         seed, count = int(sys.argv[3]), int(sys.argv[4]) if len(sys.argv) > 4 else 5
         modes = tuple(f"rand{seed * 1000 + c}" for c in range(count))
     for mode in modes:
-        one = t._run_ranks(lib, out / f"one_{mode}", 1, mode)[0]
+        try:
+            one = t._run_ranks(lib, out / f"one_{mode}", 1, mode)[0]
+        except AssertionError as e:
+            if "#! Terminated" not in str(e):
+                raise
+            print(f"{mode}: skipped (the fit ends in the reference's error() for this input)", flush=True)
+            continue
         for world in worlds:
             many = t._run_ranks(lib, out / f"w{world}_{mode}", world, mode)
             for rank, got in enumerate(many):
