@@ -173,15 +173,26 @@ int main(int argc, char **argv) {
     cgpu_matrix *mat = nullptr;
     cgpu_reps *reps = nullptr;
     CG(cgpu_matrix_upload(L.data(), mm, nn, &mat));
-    CG(cgpu_scaleboot_dev(mat, kk, bn.data(), bb.data(), seed_used, 0, rng_mode, sum_mode, &reps));
-    CG(cgpu_stats_build(reps, cm, ass.ptr.data(), ass.idx.data()));
+    // A scale with n' = (int)(r*n) = 0 draws nothing: every replicate sum of the reference is 0.0/0.0, every
+    // comparison of calcmaxs / calcassmins with it is false, and the statistic stays at the 1e30 the minimum over an
+    // association starts from (src/consel.c:1923-1937 via makerep.c:304-331).  Such scales consume no draws and
+    // never reach the device.
+    std::vector<int> bn_live, bb_live;
     std::vector<std::vector<double>> st(kk);
-    std::vector<double *> ptrs(kk);
+    std::vector<double *> ptrs;
     for (int k = 0; k < kk; k++) {
-        st[k].resize((size_t)cm * (bb[k] > 0 ? bb[k] : 0) + 1);
-        ptrs[k] = st[k].data();
+        st[k].assign((size_t)cm * (bb[k] > 0 ? bb[k] : 0) + 1, 1.0e30);
+        if (bn[k] > 0) {
+            bn_live.push_back(bn[k]);
+            bb_live.push_back(bb[k]);
+            ptrs.push_back(st[k].data());
+        }
     }
-    CG(cgpu_stats_download(reps, /*sorted=*/0, ptrs.data()));  // makerep writes the rows unsorted
+    if (!bn_live.empty()) {
+        CG(cgpu_scaleboot_dev(mat, (int)bn_live.size(), bn_live.data(), bb_live.data(), seed_used, 0, rng_mode, sum_mode, &reps));
+        CG(cgpu_stats_build(reps, cm, ass.ptr.data(), ass.idx.data()));
+        CG(cgpu_stats_download(reps, /*sorted=*/0, ptrs.data()));  // makerep writes the rows unsorted
+    }
     for (int k = 0; k < kk; k++) {
         if (out) {
             write_bmat(out, st[k].data(), cm, bb[k]);

@@ -131,3 +131,18 @@ def test_scale_without_draws_and_one_termination_line(progs, orc, tmp_path):
     r, o = both(progs, orc, tmp_path, [], "z")
     assert r.returncode == 1 and "#! Terminated: luinverse: singular matrix." in r.stdout, "the recipe no longer fails in the reference"
     assert o.returncode == 1 and o.stdout.count("#! Terminated") == 1 and "#! Terminated: luinverse: singular matrix." in o.stdout
+
+
+def test_makerep_scale_without_draws(progs, orc, tmp_path):
+    """makerep on the same toy input: the statistics of a scale that draws nothing are the 1e30 calcassmins starts
+    from (every comparison with 0.0/0.0 is false); .rep byte-equal to the reference's"""
+    if orc.ref_bin("makerep") is None:
+        pytest.skip("oracle/_ref/makerep not built")
+    rng = np.random.default_rng(4)
+    L = (-2.3 - 4.07 * rng.exponential(size=3))[None, :] + 0.2 * rng.standard_normal((5, 3))
+    orc.write_mt(tmp_path / "in.mt", L)
+    orc.write_pa(tmp_path / "p.pa", [0.31, 1.0, 1.58], [9, 8, 6])
+    orc.run_ref("makerep", ["-s", 3, "-p", "p", "in", "r"], tmp_path)
+    o = subprocess.run([str(progs / "makerep"), "-s", "3", "-p", "p", "in", "o"], cwd=tmp_path, capture_output=True, text=True)
+    assert o.returncode == 0, o.stdout[-300:]
+    assert (tmp_path / "o.rep").read_bytes() == (tmp_path / "r.rep").read_bytes()
