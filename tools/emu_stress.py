@@ -147,7 +147,8 @@ def one_case(rng, bindir: Path, d: Path) -> list:
             if protocol(t1, f"r{stem}") != protocol(t2, f"o{stem}"):
                 bad.append(f"makermt {args} stdout differs: {desc}")
     if rng.random() < 0.35:
-        L2 = base[None, :int(max(3, n // 2))] + 0.2 * rng.standard_normal((K, int(max(3, n // 2))))
+        n2 = int(max(2, n // 2))
+        L2 = (-2.3 - 4.07 * rng.exponential(size=n2))[None, :] + 0.2 * rng.standard_normal((K, n2))
         orc.write_mt(d / "g2.mt", L2)
         shutil.copy(d / "in.mt", d / "g1.mt")
         for who in ("r", "o"):
