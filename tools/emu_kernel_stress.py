@@ -14,6 +14,7 @@ CPU twin of tools/stress.py, for odd shapes and option combinations the fixed te
 """
 import ctypes as C
 import math
+import os
 import sys
 import time
 from pathlib import Path
@@ -56,6 +57,10 @@ def makermt_case(rng, case):
         while n * sum(bb) > 1.2e6:
             bb = [max(1, b // 2) for b in bb]
         K = int(rng.integers(1, max(2, min(70, int(4e6 / (n * sum(bb)))))))
+    if os.environ.get("EMU_KSTRESS_WIDE") and not big:  # many trees on few sites: several tree tiles of the fp64 contraction, several digit-row tiles
+        n = int(rng.integers(5, 400))
+        K = int(rng.integers(70, 420))
+        bb = [int(rng.integers(1, 40)) for _ in range(S)]
     rr = [float(x) for x in np.round(rng.uniform(0.3, 1.7, size=S), 3)]
     seed = int(rng.integers(1, 2 ** 31))
     base = -2.3 - 4.07 * rng.exponential(size=n)
